@@ -1,0 +1,26 @@
+"""Helpers shared by the golden-vector tests (tests/golden/*.npz are written by oracle/make_golden.py)."""
+import glob
+import json
+import os
+
+import numpy as np
+import torch
+
+from controlvar_b200.config import PathConfig
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def golden_names():
+    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    meta = json.loads(bytes(z["meta"]).decode())
+    cfg = PathConfig(depth=meta["depth"], patch_nums=tuple(meta["patch_nums"]), embed_dim=meta.get("embed_dim", 0),
+                     heads=meta.get("heads", 0))
+    idx = [torch.from_numpy(z[f"idx_{si}"].astype(np.int64)) for si in range(len(cfg.patch_nums))]
+    return dict(meta=meta, cfg=cfg, idx=idx, f_hat=torch.from_numpy(z["f_hat"]),
+                img_sub=torch.from_numpy(z["img_sub"]), img_mean=float(z["img_mean"][0]),
+                logits_row=torch.from_numpy(z["logits_cfg_last_row0"]))

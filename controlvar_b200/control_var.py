@@ -1,0 +1,299 @@
+"""Host mirror of the reference ``ControlVAR`` for the next-scale sampling hot path.
+
+Same constructor arguments, ``state_dict`` keys and ``autoregressive_infer_cfg`` signature / return value as
+/root/reference/models/control_var.py:23-67, 356-565, so it drops in for inference.
+The Python here only sequences kernel launches of libcvar_sm100.so and owns the device memory:
+
+  prologue                         cvar_lvl_pos, cvar_prologue                  control_var.py:381-409
+  per block, per scale             cvar_ln_modulate, cvar_qkv_project, cvar_attn_kvcache, cvar_gemm x3
+                                                                                 basic_var.py:203-210, 89-119, 43-51
+  head + CFG + sampling            cvar_ln_modulate, cvar_gemm, cvar_cfg_sample  control_var.py:499-505, helpers.py:6-19
+  VQ step                          cvar_vq_step                                  control_var.py:512-560, quant.py:243-270
+  decode (both streams, one pass)  VQVAE._fhat_to_img -> cvar_conv2d / cvar_gn_stats / ...   control_var.py:563-565
+
+Differences from the reference that do not change results: ``ada_lin`` (constant across scales) is evaluated once
+per call instead of once per block per scale; the KV cache is a pre-allocated arena written in place instead of
+``torch.cat`` growth; the control and image halves of ``f_hat`` are decoded in one batched decoder pass.
+Branches no released configuration uses (``separator``, ``type_pos``, ``bidirectional``, ``separate_decoding``,
+``shared_aln``, ``aln < 0``, ``mask_factor == 1``, ``more_smooth``) raise NotImplementedError.
+"""
+from __future__ import annotations
+
+import math
+import random
+from typing import Dict, List, Optional, Tuple, Union
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from .config import PathConfig, DEFAULT_PATCH_NUMS
+from .vqvae import VQVAE, register_tree
+from .weights import attn_bias_for_masking, lvl_1L, var_key_shapes
+
+_BUFFERS = ("lvl_1L", "attn_bias_for_masking", "zero_k_bias")
+
+
+def bicubic_matrix(n_in: int, n_out: int) -> torch.Tensor:
+    """(n_out, n_in) matrix U of F.interpolate(mode='bicubic', align_corners=False) along one axis, read off impulse
+    responses so that the coefficients (A = -0.75, border clamping) are exactly ATen's.  Host-side constant."""
+    eye = torch.eye(n_in, dtype=torch.float32).view(n_in, 1, 1, n_in)          # one impulse per batch entry
+    out = F.interpolate(eye, size=(1, n_out), mode="bicubic")                  # height 1 -> 1 is the identity
+    return out[:, 0, 0, :].t().contiguous()                                    # U[X, j]
+
+
+class ControlVAR(nn.Module):
+    def __init__(
+        self, vae_local: VQVAE,
+        num_classes=1000, norm_eps=1e-6, aln=1, aln_gamma_init=1e-3, shared_aln=False, cond_drop_rate=0.1,
+        depth=16, embed_dim=1024, num_heads=16, mlp_ratio=4., drop_rate=0., attn_drop_rate=0., drop_path_rate=0.,
+        layer_scale=-1., tau=4, cos_attn=False,
+        patch_nums=DEFAULT_PATCH_NUMS,
+        flash_if_available=True, fused_if_available=True, mask_factor=2, bidirectional=False,
+        separate_decoding=False, separator=False, type_pos=False, indep=True, multi_cond=False,
+    ):
+        super().__init__()
+        if shared_aln or aln < 0:
+            raise NotImplementedError("only AdaLNSABlock with per-block ada_lin (aln >= 0, shared_aln=False) is implemented")
+        if separator or type_pos or bidirectional or separate_decoding:
+            raise NotImplementedError("separator / type_pos / bidirectional / separate_decoding are not used by any "
+                                      "released configuration and are not implemented")
+        if mask_factor != 2:
+            raise NotImplementedError("mask_type='replace' (mask_factor=1) ends in a NameError in the reference sampler "
+                                      "(control_var.py:563); only 'interleave_append' is implemented")
+        if embed_dim % num_heads != 0 or embed_dim // num_heads != 64:
+            raise NotImplementedError("the attention kernels are specialised for head_dim = 64")
+        if mlp_ratio != 4.0 or tau != 4:
+            raise NotImplementedError("mlp_ratio must be 4 and tau 4 (the released models)")
+        self.cfg = PathConfig(depth=depth, patch_nums=tuple(patch_nums), num_classes=num_classes,
+                              vocab_size=vae_local.vocab_size, Cvae=vae_local.Cvae, norm_eps=norm_eps,
+                              multi_cond=multi_cond, embed_dim=embed_dim if embed_dim != 64 * depth else 0,
+                              heads=num_heads if num_heads != depth else 0)
+        cfg = self.cfg
+        self.Cvae, self.V = vae_local.Cvae, vae_local.vocab_size
+        self.depth, self.C, self.D, self.num_heads = depth, embed_dim, embed_dim, num_heads
+        self.cos_attn = cfg.cos_attn                       # control_var.py:35: forced by depth == 30
+        self.multi_cond, self.indep, self.mask_factor = multi_cond, indep, mask_factor
+        self.cond_drop_rate, self.prog_si = cond_drop_rate, -1
+        self.patch_nums = tuple(patch_nums)
+        self.L, self.first_l = cfg.L, cfg.first_l
+        self.num_stages_minus_1 = len(self.patch_nums) - 1
+        self.num_classes = num_classes
+        self.norm_eps = norm_eps
+        self.vae_proxy: Tuple[VQVAE] = (vae_local,)
+        self.vae_quant_proxy = (vae_local.quantize,)
+        for key, shape in var_key_shapes(cfg).items():
+            last = key.split(".")[-1]
+            if key == "lvl_1L":
+                t = lvl_1L(cfg)
+            elif key == "attn_bias_for_masking":
+                t = attn_bias_for_masking(cfg)
+            else:
+                t = torch.zeros(shape)
+            register_tree(self, key, t, last in _BUFFERS)
+        # RNG: the reference binds self.rng to dist.get_device() (control_var.py:68).  'cuda' reproduces the
+        # reference's stream on a GPU host; 'cpu' reproduces the stream of the reference run on CPU (used by the
+        # parity tests against the CPU oracle): the Exp(1) noise is then drawn on the host and copied over.
+        self.rng_device = "cuda"
+        self._rng: Optional[torch.Generator] = None
+        self._ws: Dict[Tuple, torch.Tensor] = {}
+        self._consts: Dict[str, object] = {}
+        self.last_idx: List[torch.Tensor] = []           # tokens of the last call, per scale (diagnostics / tests)
+        self.eval()
+
+    # ------------------------------------------------------------------------------------------ plumbing
+    def _apply(self, fn, recurse=True):
+        self._ws.clear()
+        self._consts.clear()
+        return super()._apply(fn, recurse)
+
+    def load_state_dict(self, state_dict, strict=True, assign=False):
+        self._consts.clear()
+        return super().load_state_dict(state_dict, strict=strict, assign=assign)
+
+    @property
+    def device(self) -> torch.device:
+        return self.pos_1LC.device
+
+    def _buf(self, name: str, shape, dtype=torch.float32) -> torch.Tensor:
+        key = (name, dtype)
+        n = 1
+        for s in shape:
+            n *= s
+        t = self._ws.get(key)
+        if t is None or t.numel() < n or t.device != self.device:
+            t = torch.empty(n, device=self.device, dtype=dtype)
+            self._ws[key] = t
+        return t[:n].view(shape)
+
+    def release_workspace(self):
+        """Free the KV arena and activation scratch (they are cached across calls)."""
+        self._ws.clear()
+        self.vae_proxy[0].release_workspace()
+
+    def _generator(self, seed: Optional[int]) -> Optional[torch.Generator]:
+        if seed is None:
+            return None
+        dev = "cpu" if self.rng_device == "cpu" else self.device
+        if self._rng is None or self._rng.device != torch.device(dev):
+            self._rng = torch.Generator(device=dev)
+        self._rng.manual_seed(seed)
+        return self._rng
+
+    def _noise(self, rows: int, V: int, rng: Optional[torch.Generator]) -> torch.Tensor:
+        """The Exp(1) tensor torch.multinomial(num_samples=1) draws internally (helpers.py:19)."""
+        if self.rng_device == "cpu":
+            return torch.empty(rows, V, dtype=torch.float32).exponential_(1, generator=rng).to(self.device, non_blocking=True)
+        return torch.empty(rows, V, dtype=torch.float32, device=self.device).exponential_(1, generator=rng)
+
+    def _constants(self):
+        c = self._consts
+        if not c:
+            dev, cfg = self.device, self.cfg
+            hw = self.patch_nums[-1]
+            c["U"] = {pn: bicubic_matrix(pn, hw).to(dev) for pn in set(self.patch_nums) if pn != hw}
+            c["lvl_pos"] = ops.lvl_pos(self.get_parameter("lvl_embed.weight"), self.lvl_1L, self.pos_1LC,
+                                       torch.empty(self.L, self.C, device=dev))
+            P = self.get_parameter
+            blocks = []
+            for i in range(self.depth):
+                p = f"blocks.{i}."
+                blocks.append(dict(
+                    qkv_w=P(p + "attn.mat_qkv.weight"), q_bias=P(p + "attn.q_bias"), v_bias=P(p + "attn.v_bias"),
+                    k_bias=self.get_buffer(p + "attn.zero_k_bias"),
+                    proj_w=P(p + "attn.proj.weight"), proj_b=P(p + "attn.proj.bias"),
+                    fc1_w=P(p + "ffn.fc1.weight"), fc1_b=P(p + "ffn.fc1.bias"),
+                    fc2_w=P(p + "ffn.fc2.weight"), fc2_b=P(p + "ffn.fc2.bias"),
+                    ada_w=P(p + "ada_lin.1.weight"), ada_b=P(p + "ada_lin.1.bias"),
+                    scale_mul=P(p + "attn.scale_mul_1H11").reshape(-1).contiguous() if self.cos_attn else None,
+                ))
+            c["blocks"] = blocks
+            c["head_ada_w"], c["head_ada_b"] = P("head_nm.ada_lin.1.weight"), P("head_nm.ada_lin.1.bias")
+            vq = self.vae_proxy[0]
+            c["phi"] = [(vq.get_parameter(f"quantize.quant_resi.qresi_ls.{k}.weight"),
+                         vq.get_parameter(f"quantize.quant_resi.qresi_ls.{k}.bias"))
+                        for k in range(self.cfg.share_quant_resi)]
+            c["codebook"] = vq.get_parameter("quantize.embedding.weight")
+        return c
+
+    # ------------------------------------------------------------------------------------------- sampler
+    @torch.no_grad()
+    def autoregressive_infer_cfg(
+        self, B: int, label_B: Optional[Union[int, torch.LongTensor]],
+        g_seed: Optional[int] = None, cfg=1.5, top_k=0, top_p=0.0,
+        more_smooth=False, cond_type=None,
+    ) -> torch.Tensor:   # (B, 3, 2*H, W) in [0, 1]: control map on top, image below
+        """Drop-in for ControlVAR.autoregressive_infer_cfg (control_var.py:356-565), released branch."""
+        if more_smooth:
+            raise NotImplementedError("more_smooth (Gumbel-softmax visualisation path) is not implemented")
+        if not self.pos_1LC.is_cuda:
+            raise RuntimeError("controlvar_b200.ControlVAR runs on CUDA only (no CPU fallback); call .cuda() first")
+        dev = self.device
+        rng = self._generator(g_seed)
+        rng_dev = "cpu" if self.rng_device == "cpu" else dev
+
+        # ---- host-side argument handling, as in control_var.py:376-403
+        if label_B is None:
+            sel = torch.full((1, self.num_classes), 1 / self.num_classes, dtype=torch.float32, device=rng_dev)
+            label_B = torch.multinomial(sel, num_samples=B, replacement=True, generator=rng).reshape(B)
+        elif isinstance(label_B, int):
+            label_B = torch.full((B,), self.num_classes if label_B < 0 else label_B)
+        label_B = label_B.to(device=dev, dtype=torch.long).contiguous()
+        if self.multi_cond:
+            if cond_type is None:
+                if B == 4:
+                    cond_type = torch.tensor([0, 1, 2, 3])
+                else:
+                    cond_idx = torch.full((1, 4), 1 / 4, dtype=torch.float32, device=rng_dev)
+                    cond_type = torch.multinomial(cond_idx, num_samples=B, replacement=True, generator=rng).reshape(B)
+            elif isinstance(cond_type, int):
+                assert cond_type <= 3 and cond_type > 0
+                cond_type = torch.full((B,), cond_type)
+            cond_type = cond_type.to(device=dev, dtype=torch.long).contiguous()
+            random.random()      # control_var.py:403 draws from Python's global RNG even when bidirectional=False
+        else:
+            cond_type = torch.zeros(B, dtype=torch.long, device=dev)
+        assert label_B.shape == (B,) and cond_type.shape == (B,)
+
+        cst = self._constants()
+        vae = self.vae_proxy[0]
+        C, H, depth, V, Cvae = self.C, self.num_heads, self.depth, self.V, self.Cvae
+        R, T, hw = 2 * B, self.L, self.patch_nums[-1]
+        SN = len(self.patch_nums)
+        lens = self.cfg.scale_lens
+        lmax = max(lens)
+        attn_scale = self.cfg.attn_scale
+        lvl_pos = cst["lvl_pos"]
+
+        # ---- workspaces (cached across calls)
+        cond_BD = self._buf("cond_BD", (R, C))
+        silu_cond = self._buf("silu_cond", (R, C))
+        ada = self._buf("ada", (depth, R, 6 * C))
+        ada_head = self._buf("ada_head", (R, 2 * C))
+        x = self._buf("x", (R * lmax, C))
+        xn = self._buf("xn", (R * lmax, C))
+        attn_o = self._buf("attn_o", (R * lmax, C))
+        qbuf = self._buf("q", (R * H * lmax * 64,))
+        hid = self._buf("hid", (R * lmax, 4 * C))
+        logits = self._buf("logits", (R * lmax, V))
+        idx = self._buf("idx", (B * lmax,), torch.int64)
+        kc = self._buf("k_cache", (depth, R, H, T, 64))
+        vc = self._buf("v_cache", (depth, R, H, T, 64))
+        f_hat = self._buf("f_hat", (B, Cvae, 2 * hw, hw))
+        f_hat.zero_()
+
+        # ---- prologue
+        ops.prologue(self.get_parameter("class_emb.weight"),
+                     self.get_parameter("cond_embed.weight") if self.multi_cond else None, self.pos_start,
+                     lvl_pos, label_B, cond_type, self.num_classes, cond_BD, silu_cond, x)
+        for bi, blk in enumerate(cst["blocks"]):       # ada_lin = Linear(SiLU(cond)): constant across scales
+            ops.gemm(silu_cond, blk["ada_w"], blk["ada_b"], ada[bi], R, 6 * C, C)
+        ops.gemm(silu_cond, cst["head_ada_w"], cst["head_ada_b"], ada_head, R, 2 * C, C)
+
+        self.last_idx = []
+        cur_L = 0
+        for si, pn in enumerate(self.patch_nums):
+            l = lens[si]
+            M = R * l
+            L_prev = cur_L
+            cur_L += l
+            for bi, blk in enumerate(cst["blocks"]):
+                a = ada[bi]                                # (R, 6C): gamma1, gamma2, scale1, scale2, shift1, shift2
+                g1, g2, s1, s2, b1, b2 = (a[:, k * C:(k + 1) * C] for k in range(6))
+                ops.ln_modulate(x, s1, b1, 6 * C, xn, M, C, l, self.norm_eps)
+                ops.qkv_project(xn, blk["qkv_w"], blk["q_bias"], blk["k_bias"], blk["v_bias"], qbuf, kc[bi], vc[bi],
+                                R, l, L_prev, T, H, self.cos_attn, blk["scale_mul"])
+                ops.attn_kvcache(qbuf, kc[bi], vc[bi], attn_o, R, H, l, cur_L, T, attn_scale)
+                ops.gemm(attn_o, blk["proj_w"], blk["proj_b"], x, M, C, C,
+                         epilogue=ops.EPI_BIAS_GAMMA_RESID, gamma=g1, gamma_row_stride=6 * C, rows_per_sample=l)
+                ops.ln_modulate(x, s2, b2, 6 * C, xn, M, C, l, self.norm_eps)
+                ops.gemm(xn, blk["fc1_w"], blk["fc1_b"], hid, M, 4 * C, C, epilogue=ops.EPI_BIAS_GELU)
+                ops.gemm(hid, blk["fc2_w"], blk["fc2_b"], x, M, C, 4 * C,
+                         epilogue=ops.EPI_BIAS_GAMMA_RESID, gamma=g2, gamma_row_stride=6 * C, rows_per_sample=l)
+            # head: AdaLNBeforeHead + Linear(C, V)
+            ops.ln_modulate(x, ada_head[:, :C], ada_head[:, C:], 2 * C, xn, M, C, l, self.norm_eps)
+            ops.gemm(xn, self.get_parameter("head.weight"), self.get_parameter("head.bias"), logits, M, V, C)
+            # CFG + top-k/top-p + multinomial
+            t = cfg * (si / self.num_stages_minus_1)
+            q_noise = self._noise(B * l, V, rng)
+            ops.cfg_sample(logits, q_noise, idx, B, l, V, t, top_k, top_p)
+            self.last_idx.append(idx[:B * l].view(B, l).clone())
+            # VQ step + next-scale input
+            phi_w, phi_b = cst["phi"][self.cfg.phi_index(si)]
+            pn_next = self.patch_nums[si + 1] if si != SN - 1 else 0
+            ops.vq_step(idx, cst["codebook"], cst["U"].get(pn), phi_w, phi_b,
+                        self.get_parameter("word_embed.weight"), self.get_parameter("word_embed.bias"),
+                        lvl_pos[cur_L:] if pn_next else None, f_hat, x if pn_next else None,
+                        B, pn, pn_next, hw, Cvae, C)
+
+        # ---- decode both halves (control rows on top, image rows below): control_var.py:563-565
+        side = hw * vae.downsample
+        img = torch.empty(B, 3, 2 * side, side, device=dev, dtype=torch.float32)
+        vae._fhat_to_img(f_hat[:, :, :hw, :], out=img, rows_total=2 * side, row_offset=0, out_mode=1)
+        vae._fhat_to_img(f_hat[:, :, hw:, :], out=img, rows_total=2 * side, row_offset=side, out_mode=1)
+        self.last_f_hat = f_hat
+        return img
+
+    def forward(self, *a, **k):
+        raise NotImplementedError("ControlVAR.forward is the training pass of the reference and is out of scope here")

@@ -1,0 +1,66 @@
+// Shared helpers for libcvar_sm100.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <math.h>
+#include "../../include/cvar.h"
+
+namespace cvar {
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+extern int g_gemm_engine;
+
+#define CVAR_REQUIRE(cond, ...)                 \
+  do {                                          \
+    if (!(cond)) {                              \
+      cvar::set_error(__VA_ARGS__);             \
+      return -1;                                \
+    }                                           \
+  } while (0)
+
+// After a launch: catch configuration errors synchronously (asynchronous faults surface at the caller's next sync).
+#define CVAR_CHECK_LAUNCH(name)                                                           \
+  do {                                                                                    \
+    cudaError_t e__ = cudaGetLastError();                                                 \
+    if (e__ != cudaSuccess) {                                                             \
+      cvar::set_error("%s: launch failed: %s", name, cudaGetErrorString(e__));            \
+      return -2;                                                                          \
+    }                                                                                     \
+    cvar::count_launch();                                                                 \
+  } while (0)
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// x * sigmoid(x), the form ATen evaluates: x / (1 + exp(-x))      (vae_modules.py:14-15, F.silu)
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }
+
+// GELU(approximate='tanh')                                         (basic_var.py:39)
+__device__ __forceinline__ float gelu_tanh_f(float x) {
+  const float kBeta = 0.7978845608028654f;   // sqrt(2/pi)
+  const float kKappa = 0.044715f;
+  float inner = kBeta * (x + kKappa * x * x * x);
+  return 0.5f * x * (1.0f + tanhf(inner));
+}
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+}  // namespace cvar

@@ -1,0 +1,114 @@
+// C-ABI entry points built on the GEMM engines: dense layers, fused QKV + KV-cache append, decoder convolutions.
+#include "sgemm.cuh"
+
+using namespace cvar;
+
+namespace cvar {
+// tcgen05 engine (gemm_tc.cu); returns 1 when it took the problem, 0 when the shape is not supported, <0 on error.
+int tc_gemm_try(const cvar_gemm_args* a, cudaStream_t s);
+int tc_qkv_try(const float* A, const float* Wqkv, const QkvEpilogue& ep, int M, int C, cudaStream_t s);
+int tc_conv_try(const cvar_conv_args* a, cudaStream_t s);
+}  // namespace cvar
+
+extern "C" int cvar_gemm(const cvar_gemm_args* a, void* stream) {
+  CVAR_REQUIRE(a != nullptr, "cvar_gemm: null args");
+  CVAR_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0 && a->batch > 0, "cvar_gemm: bad shape M=%d N=%d K=%d", a->M, a->N,
+               a->K);
+  CVAR_REQUIRE(a->K % 4 == 0 && a->lda % 4 == 0 && a->ldw % 4 == 0, "cvar_gemm: K, lda, ldw must be multiples of 4");
+  CVAR_REQUIRE((((uintptr_t)a->A) & 15) == 0 && (((uintptr_t)a->W) & 15) == 0, "cvar_gemm: operands must be 16B aligned");
+  CVAR_REQUIRE(!a->w_is_kn || a->N % 4 == 0, "cvar_gemm: [K,N] weights need N %% 4 == 0");
+  CVAR_REQUIRE(a->epilogue != CVAR_EPI_BIAS_GAMMA_RESID || (a->gamma && a->rows_per_sample > 0),
+               "cvar_gemm: gamma epilogue without gamma");
+  CVAR_REQUIRE(a->epilogue != CVAR_EPI_BIAS_RESID || a->resid, "cvar_gemm: residual epilogue without resid");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (g_gemm_engine != 0) {
+    int took = tc_gemm_try(a, s);
+    if (took < 0) return took;
+    if (took == 1) return 0;
+  }
+  DenseALoader al{a->A, a->lda, a->strideA, a->M, a->K};
+  DenseBLoader bl{a->W, a->ldw, a->strideW, a->N, a->K, a->w_is_kn};
+  DenseEpilogue ep{a->out, a->ldo, a->strideO, a->bias, a->epilogue, a->alpha, a->gamma, a->gamma_row_stride,
+                   a->rows_per_sample, a->resid, a->ldr, a->strideR};
+  return launch_sgemm(al, bl, ep, (long long)a->M, a->N, a->K, a->batch, s, "cvar_gemm");
+}
+
+// F.normalize(q).mul(scale_mul), F.normalize(k)                                         basic_var.py:99-104
+__global__ void cos_attn_normalize_kernel(float* __restrict__ q, float* __restrict__ kc, const float* __restrict__ sm,
+                                          int R, int H, int l, int L_prev, int T_max) {
+  // one warp per 64-float head row; rows [0, R*H*l) are q rows, the next R*H*l are the freshly appended k rows
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  long long row = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+  long long nq = (long long)R * H * l;
+  if (row >= 2 * nq) return;
+  bool is_q = row < nq;
+  long long i = is_q ? row : row - nq;
+  int t = (int)(i % l);
+  long long rh = i / l;
+  int h = (int)(rh % H);
+  float* p = is_q ? q + i * 64 : kc + (rh * T_max + L_prev + t) * 64;
+  float2 v = *reinterpret_cast<float2*>(p + lane * 2);
+  float ss = warp_sum(v.x * v.x + v.y * v.y);
+  float denom = fmaxf(sqrtf(ss), 1e-12f);
+  v.x = v.x / denom;
+  v.y = v.y / denom;
+  if (is_q) {
+    float mul = expf(fminf(sm[h], 4.605170185988092f));   // clamp_max(log(100)).exp()
+    v.x = __fmul_rn(v.x, mul);
+    v.y = __fmul_rn(v.y, mul);
+  }
+  *reinterpret_cast<float2*>(p + lane * 2) = v;
+}
+
+extern "C" int cvar_qkv_project(const float* A, const float* Wqkv, const float* q_bias, const float* k_bias,
+                                const float* v_bias, float* q_out, float* k_cache, float* v_cache, int R, int l,
+                                int L_prev, int T_max, int H, int cos_attn, const float* scale_mul_H, void* stream) {
+  CVAR_REQUIRE(R > 0 && l > 0 && H > 0 && L_prev >= 0 && L_prev + l <= T_max, "cvar_qkv_project: bad shape");
+  CVAR_REQUIRE(!cos_attn || scale_mul_H != nullptr, "cvar_qkv_project: cosine attention needs scale_mul");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int C = H * 64, M = R * l;
+  QkvEpilogue ep{q_bias, k_bias, v_bias, q_out, k_cache, v_cache, C, H, l, L_prev, T_max};
+  int took = 0;
+  if (g_gemm_engine != 0) {
+    took = tc_qkv_try(A, Wqkv, ep, M, C, s);
+    if (took < 0) return took;
+  }
+  if (took == 0) {
+    DenseALoader al{A, C, 0, M, C};
+    DenseBLoader bl{Wqkv, C, 0, 3 * C, C, 0};
+    int rc = launch_sgemm(al, bl, ep, (long long)M, 3 * C, C, 1, s, "cvar_qkv_project");
+    if (rc) return rc;
+  }
+  if (cos_attn) {
+    long long rows = 2LL * R * H * l;
+    cos_attn_normalize_kernel<<<cdiv(rows, 8), 256, 0, s>>>(q_out, k_cache, scale_mul_H, R, H, l, L_prev, T_max);
+    CVAR_CHECK_LAUNCH("cvar_qkv_project/cos_normalize");
+  }
+  return 0;
+}
+
+extern "C" int cvar_conv2d(const cvar_conv_args* a, void* stream) {
+  CVAR_REQUIRE(a != nullptr, "cvar_conv2d: null args");
+  CVAR_REQUIRE(a->ks == 1 || a->ks == 3, "cvar_conv2d: ks must be 1 or 3");
+  CVAR_REQUIRE(a->Cin % 16 == 0, "cvar_conv2d: Cin must be a multiple of 16 (got %d)", a->Cin);
+  CVAR_REQUIRE(a->out_mode >= 0 && a->out_mode <= 2, "cvar_conv2d: bad out_mode");
+  CVAR_REQUIRE(a->out_mode == 0 || a->resid == nullptr, "cvar_conv2d: image output takes no residual");
+  CVAR_REQUIRE((a->in_a == nullptr) == (a->in_b == nullptr), "cvar_conv2d: in_a/in_b must come together");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (g_gemm_engine != 0) {
+    int took = tc_conv_try(a, s);
+    if (took < 0) return took;
+    if (took == 1) return 0;
+  }
+  const int up = a->upsample2x ? 1 : 0;
+  const int Hout = a->Hin << up, Wout = a->Win << up;
+  const long long M = (long long)a->B * Hout * Wout;
+  const int K = a->ks * a->ks * a->Cin;
+  ConvALoader al;
+  al.x = a->x, al.in_a = a->in_a, al.in_b = a->in_b, al.in_silu = a->in_silu;
+  al.Hin = a->Hin, al.Win = a->Win, al.Cin = a->Cin, al.ks = a->ks, al.up = up;
+  al.Hout = Hout, al.Wout = Wout, al.Mtot = M, al.K = K;
+  DenseBLoader bl{a->w, K, 0, a->Cout, K, 0};
+  ConvEpilogue ep{a->out, a->bias, a->resid, a->Cout, a->out_mode, Hout, Wout, a->out_rows_total, a->row_offset};
+  return launch_sgemm(al, bl, ep, M, a->Cout, K, 1, s, "cvar_conv2d");
+}

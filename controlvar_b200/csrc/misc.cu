@@ -1,0 +1,328 @@
+// Library state + the small HBM-bound kernels of the path (prologue, AdaLN LayerNorm, GroupNorm statistics, layout).
+#include <stdarg.h>
+#include <atomic>
+#include "common.cuh"
+
+namespace cvar {
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+int g_gemm_engine = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+}  // namespace cvar
+
+using namespace cvar;
+
+extern "C" int cvar_abi_version(void) { return CVAR_ABI_VERSION; }
+extern "C" const char* cvar_last_error(void) { return cvar::g_err; }
+extern "C" long long cvar_launch_count(void) { return cvar::g_launches.load(); }
+extern "C" int cvar_set_gemm_engine(int e) {
+  int old = cvar::g_gemm_engine;
+  if (e >= 0 && e <= 2) cvar::g_gemm_engine = e;
+  return old;
+}
+extern "C" int cvar_get_gemm_engine(void) { return cvar::g_gemm_engine; }
+
+// ------------------------------------------------------------------------------------------------ lvl_pos
+__global__ void lvl_pos_kernel(const float* __restrict__ lvl_embed, const int64_t* __restrict__ lvl_1L,
+                               const float* __restrict__ pos, float* __restrict__ out, int T, int C) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // float4 index
+  long long n4 = (long long)T * C / 4;
+  if (i >= n4) return;
+  int t = (int)(i / (C / 4));
+  int c4 = (int)(i % (C / 4));
+  float4 a = ld4(lvl_embed + (long long)lvl_1L[t] * C + c4 * 4);
+  float4 b = ld4(pos + (long long)t * C + c4 * 4);
+  st4(out + i * 4, make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w));
+}
+
+extern "C" int cvar_lvl_pos(const float* lvl_embed, const int64_t* lvl_1L, const float* pos_1LC, float* lvl_pos,
+                            int T, int C, void* stream) {
+  CVAR_REQUIRE(C % 4 == 0 && T > 0, "cvar_lvl_pos: bad shape T=%d C=%d", T, C);
+  long long n4 = (long long)T * C / 4;
+  lvl_pos_kernel<<<cdiv(n4, 256), 256, 0, (cudaStream_t)stream>>>(lvl_embed, lvl_1L, pos_1LC, lvl_pos, T, C);
+  CVAR_CHECK_LAUNCH("cvar_lvl_pos");
+  return 0;
+}
+
+// ----------------------------------------------------------------------------------------------- prologue
+__global__ void prologue_kernel(const float* __restrict__ class_emb, const float* __restrict__ cond_embed,
+                                const float* __restrict__ pos_start, const float* __restrict__ lvl_pos,
+                                const int64_t* __restrict__ label, const int64_t* __restrict__ ctype, int B, int C,
+                                int num_classes, float* __restrict__ cond_BD, float* __restrict__ silu_cond,
+                                float* __restrict__ x0) {
+  int r = blockIdx.x;
+  long long lab = r < B ? label[r] : (long long)num_classes;
+  long long ct = r < B ? ctype[r] : 4;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float ce = class_emb[lab * C + c];
+    float te = cond_embed != nullptr ? cond_embed[ct * C + c] : ce;   // multi_cond=False: both start tokens = sos
+    cond_BD[(long long)r * C + c] = ce;
+    silu_cond[(long long)r * C + c] = silu_f(ce);
+    // (next_token_map + pos_start) + lvl_pos[:, :2]                      control_var.py:409
+    x0[((long long)r * 2 + 0) * C + c] = __fadd_rn(__fadd_rn(te, pos_start[c]), lvl_pos[c]);
+    x0[((long long)r * 2 + 1) * C + c] = __fadd_rn(__fadd_rn(ce, pos_start[C + c]), lvl_pos[C + c]);
+  }
+}
+
+extern "C" int cvar_prologue(const float* class_emb, const float* cond_embed, const float* pos_start,
+                             const float* lvl_pos, const int64_t* label_B, const int64_t* cond_type_B, int B, int C,
+                             int num_classes, float* cond_BD, float* silu_cond, float* x0, void* stream) {
+  CVAR_REQUIRE(B > 0 && C > 0, "cvar_prologue: bad shape");
+  prologue_kernel<<<2 * B, 256, 0, (cudaStream_t)stream>>>(class_emb, cond_embed, pos_start, lvl_pos, label_B,
+                                                           cond_type_B, B, C, num_classes, cond_BD, silu_cond, x0);
+  CVAR_CHECK_LAUNCH("cvar_prologue");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------- ln_modulate
+// One warp per row; the row (C <= 2048 floats) lives in registers between the statistics pass and the write.
+template <int MAXV>   // float4 per lane
+__global__ void __launch_bounds__(256) ln_modulate_kernel(const float* __restrict__ x, const float* __restrict__ scale,
+                                                          const float* __restrict__ shift, long long mod_stride,
+                                                          float* __restrict__ y, int M, int C, int rows_per_sample,
+                                                          float eps) {
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  long long m = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+  if (m >= M) return;
+  const float* xr = x + m * C;
+  int nv = C >> 2;
+  float4 v[MAXV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    int idx = lane + i * 32;
+    if (idx < nv) {
+      v[i] = ld4(xr + idx * 4);
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  }
+  float mean = warp_sum(s) / (float)C;
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    int idx = lane + i * 32;
+    if (idx < nv) {
+      float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      ss += (a * a + b * b) + (c * c + d * d);
+    }
+  }
+  float var = warp_sum(ss) / (float)C;
+  float rstd = 1.0f / sqrtf(var + eps);
+  long long r = m / rows_per_sample;
+  const float* sc = scale + r * mod_stride;
+  const float* sh = shift + r * mod_stride;
+  float* yr = y + m * C;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    int idx = lane + i * 32;
+    if (idx < nv) {
+      float4 a = ld4(sc + idx * 4), b = ld4(sh + idx * 4), o;
+      // ln(x).mul(scale.add(1)).add_(shift): three separately rounded steps          basic_var.py:208
+      o.x = __fadd_rn(__fmul_rn(__fmul_rn(v[i].x - mean, rstd), __fadd_rn(a.x, 1.f)), b.x);
+      o.y = __fadd_rn(__fmul_rn(__fmul_rn(v[i].y - mean, rstd), __fadd_rn(a.y, 1.f)), b.y);
+      o.z = __fadd_rn(__fmul_rn(__fmul_rn(v[i].z - mean, rstd), __fadd_rn(a.z, 1.f)), b.z);
+      o.w = __fadd_rn(__fmul_rn(__fmul_rn(v[i].w - mean, rstd), __fadd_rn(a.w, 1.f)), b.w);
+      st4(yr + idx * 4, o);
+    }
+  }
+}
+
+extern "C" int cvar_ln_modulate(const float* x, const float* scale, const float* shift, long long mod_row_stride,
+                                float* y, int M, int C, int rows_per_sample, float eps, void* stream) {
+  CVAR_REQUIRE(C % 4 == 0 && C <= 2048 && M > 0 && rows_per_sample > 0, "cvar_ln_modulate: bad shape M=%d C=%d", M, C);
+  CVAR_REQUIRE(mod_row_stride % 4 == 0, "cvar_ln_modulate: modulation stride must be a multiple of 4 floats");
+  dim3 grid(cdiv(M, 8));
+  cudaStream_t s = (cudaStream_t)stream;
+  int nv = C / 4;
+  if (nv <= 32 * 4)
+    ln_modulate_kernel<4><<<grid, 256, 0, s>>>(x, scale, shift, mod_row_stride, y, M, C, rows_per_sample, eps);
+  else if (nv <= 32 * 8)
+    ln_modulate_kernel<8><<<grid, 256, 0, s>>>(x, scale, shift, mod_row_stride, y, M, C, rows_per_sample, eps);
+  else
+    ln_modulate_kernel<16><<<grid, 256, 0, s>>>(x, scale, shift, mod_row_stride, y, M, C, rows_per_sample, eps);
+  CVAR_CHECK_LAUNCH("cvar_ln_modulate");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------- layout / GN
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int H, int W,
+                                    long long in_batch_stride, long long in_chan_stride, long long in_row_stride,
+                                    long long total) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int c = (int)(i % C);
+  long long p = i / C;
+  int xw = (int)(p % W);
+  long long q = p / W;
+  int yh = (int)(q % H);
+  long long n = q / H;
+  out[i] = in[n * in_batch_stride + (long long)c * in_chan_stride + (long long)yh * in_row_stride + xw];
+}
+
+extern "C" int cvar_nchw_to_nhwc(const float* in, float* out, int B, int C, int H, int W, long long in_batch_stride,
+                                 void* stream) {
+  // the f_hat halves of control_var.py:525-526 are views of a (B, C, 2H, W) tensor: channel stride 2*H*W
+  long long chan_stride = in_batch_stride / C;
+  long long total = (long long)B * C * H * W;
+  nchw_to_nhwc_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(in, out, C, H, W, in_batch_stride,
+                                                                          chan_stride, W, total);
+  CVAR_CHECK_LAUNCH("cvar_nchw_to_nhwc");
+  return 0;
+}
+
+static const int kGnChunkPixels = 256;
+extern "C" int cvar_gn_chunks(int HW) { return (HW + kGnChunkPixels - 1) / kGnChunkPixels; }
+
+// stage 1: per (chunk of pixels, sample): per-channel double sums, reduced to per-group partials.
+__global__ void gn_partial_kernel(const float* __restrict__ x, double* __restrict__ scratch, int HW, int C, int groups,
+                                  int chunks) {
+  extern __shared__ double sm[];   // [2][C]
+  int n = blockIdx.y, chunk = blockIdx.x;
+  int p0 = chunk * kGnChunkPixels;
+  int p1 = min(HW, p0 + kGnChunkPixels);
+  int cpg = C / groups;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float* base = x + ((long long)n * HW) * C + c;
+    double s = 0.0, ss = 0.0;
+    for (int p = p0; p < p1; ++p) {
+      double v = (double)base[(long long)p * C];
+      s += v;
+      ss += v * v;
+    }
+    sm[c] = s;
+    sm[C + c] = ss;
+  }
+  __syncthreads();
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+    double s = 0.0, ss = 0.0;
+    for (int j = 0; j < cpg; ++j) {
+      s += sm[g * cpg + j];
+      ss += sm[C + g * cpg + j];
+    }
+    long long o = (((long long)n * groups + g) * chunks + chunk) * 2;
+    scratch[o] = s;
+    scratch[o + 1] = ss;
+  }
+}
+
+// stage 2: fold mean / rstd with the affine into per-(n,c) a, b.
+__global__ void gn_finalize_kernel(const double* __restrict__ scratch, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ a_out,
+                                   float* __restrict__ b_out, int HW, int C, int groups, int chunks, float eps) {
+  int n = blockIdx.x;
+  int cpg = C / groups;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    int g = c / cpg;
+    const double* sp = scratch + (((long long)n * groups + g) * chunks) * 2;
+    double s = 0.0, ss = 0.0;
+    for (int k = 0; k < chunks; ++k) {
+      s += sp[2 * k];
+      ss += sp[2 * k + 1];
+    }
+    double cnt = (double)HW * cpg;
+    double mean = s / cnt;
+    double var = ss / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    float rstd = 1.0f / sqrtf((float)var + eps);
+    float a = rstd * gamma[c];
+    a_out[(long long)n * C + c] = a;
+    b_out[(long long)n * C + c] = beta[c] - (float)mean * a;
+  }
+}
+
+extern "C" int cvar_gn_stats(const float* x_nhwc, const float* gamma, const float* beta, float* a_out, float* b_out,
+                             double* scratch, int B, int HW, int C, int groups, float eps, void* stream) {
+  CVAR_REQUIRE(C % groups == 0 && C <= 4096, "cvar_gn_stats: bad C=%d groups=%d", C, groups);
+  int chunks = cvar_gn_chunks(HW);
+  int threads = ((C + 31) / 32) * 32;
+  if (threads > 640) threads = 640;
+  gn_partial_kernel<<<dim3(chunks, B), threads, 2 * C * sizeof(double), (cudaStream_t)stream>>>(x_nhwc, scratch, HW, C,
+                                                                                              groups, chunks);
+  CVAR_CHECK_LAUNCH("cvar_gn_stats/partial");
+  gn_finalize_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(scratch, gamma, beta, a_out, b_out, HW, C, groups, chunks,
+                                                          eps);
+  CVAR_CHECK_LAUNCH("cvar_gn_stats/finalize");
+  return 0;
+}
+
+__global__ void affine_nc_kernel(const float* __restrict__ x, const float* __restrict__ a, const float* __restrict__ b,
+                                 float* __restrict__ y, long long HWC4, int C4, long long total4, int silu) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  long long n = i / HWC4;
+  int c4 = (int)(i % C4);
+  float4 v = ld4(x + i * 4);
+  float4 av = ld4(a + (n * C4 + c4) * 4), bv = ld4(b + (n * C4 + c4) * 4);
+  v.x = fmaf(v.x, av.x, bv.x);
+  v.y = fmaf(v.y, av.y, bv.y);
+  v.z = fmaf(v.z, av.z, bv.z);
+  v.w = fmaf(v.w, av.w, bv.w);
+  if (silu) {
+    v.x = silu_f(v.x);
+    v.y = silu_f(v.y);
+    v.z = silu_f(v.z);
+    v.w = silu_f(v.w);
+  }
+  st4(y + i * 4, v);
+}
+
+extern "C" int cvar_affine_nc(const float* x_nhwc, const float* a, const float* b, float* y, int B, int HW, int C,
+                              int silu, void* stream) {
+  CVAR_REQUIRE(C % 4 == 0, "cvar_affine_nc: C %% 4 != 0");
+  long long total4 = (long long)B * HW * C / 4;
+  affine_nc_kernel<<<cdiv(total4, 256), 256, 0, (cudaStream_t)stream>>>(x_nhwc, a, b, y, (long long)HW * C / 4, C / 4,
+                                                                        total4, silu);
+  CVAR_CHECK_LAUNCH("cvar_affine_nc");
+  return 0;
+}
+
+// row softmax, one warp per row (AttnBlock: 256 columns)
+__global__ void softmax_rows_kernel(float* __restrict__ x, int rows, int cols) {
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  long long r = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+  if (r >= rows) return;
+  float* xr = x + r * cols;
+  float mx = -INFINITY;
+  for (int c = lane; c < cols; c += 32) mx = fmaxf(mx, xr[c]);
+  mx = warp_max(mx);
+  float s = 0.f;
+  for (int c = lane; c < cols; c += 32) {
+    float e = expf(xr[c] - mx);
+    xr[c] = e;
+    s += e;
+  }
+  s = warp_sum(s);
+  for (int c = lane; c < cols; c += 32) xr[c] = xr[c] / s;
+}
+
+extern "C" int cvar_softmax_rows(float* x, int rows, int cols, void* stream) {
+  softmax_rows_kernel<<<cdiv(rows, 8), 256, 0, (cudaStream_t)stream>>>(x, rows, cols);
+  CVAR_CHECK_LAUNCH("cvar_softmax_rows");
+  return 0;
+}
+
+__global__ void repack_conv_weight_kernel(const float* __restrict__ w, float* __restrict__ o, int Cout, int Cin,
+                                          int ks) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)Cout * Cin * ks * ks;
+  if (i >= total) return;
+  int ci = (int)(i % Cin);
+  long long r = i / Cin;
+  int tap = (int)(r % (ks * ks));
+  int co = (int)(r / (ks * ks));
+  o[i] = w[((long long)co * Cin + ci) * ks * ks + tap];
+}
+
+extern "C" int cvar_repack_conv_weight(const float* w_oihw, float* w_out, int Cout, int Cin, int ks, void* stream) {
+  long long total = (long long)Cout * Cin * ks * ks;
+  repack_conv_weight_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(w_oihw, w_out, Cout, Cin, ks);
+  CVAR_CHECK_LAUNCH("cvar_repack_conv_weight");
+  return 0;
+}

@@ -1,0 +1,263 @@
+// CFG mix + top-k + top-p + multinomial(1) for one scale (control_var.py:501-505, helpers.py:6-19).
+// One CTA per (sample, token) row of V = 4096 logits.  The combined logits never go back to HBM: they live in
+// shared memory between the CFG mix, the k-th-largest radix select, the ascending sort that top-p needs, and
+// the final argmax(softmax(v) / q).
+#include "common.cuh"
+
+using namespace cvar;
+
+namespace {
+constexpr int V_FIXED = 4096;
+constexpr int NT = 256;
+constexpr int PER = V_FIXED / NT;   // 16
+
+__device__ __forceinline__ unsigned orderable(float f) {
+  unsigned b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float from_orderable(unsigned u) {
+  unsigned b = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+  return __uint_as_float(b);
+}
+
+struct SampleSmem {
+  unsigned long long keys[V_FIXED];   // (orderable value << 32) | index
+  float vals[V_FIXED];
+  unsigned hist[256];
+  float redf[NT / 32];
+  int redi[NT / 32];
+  unsigned sel_prefix;
+  unsigned sel_remaining;
+};
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int w = 0; w < NT / 32; ++w) t += red[w];
+  return t;
+}
+__device__ __forceinline__ float block_max(float v, float* red) {
+  v = warp_max(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = -INFINITY;
+#pragma unroll
+  for (int w = 0; w < NT / 32; ++w) t = fmaxf(t, red[w]);
+  return t;
+}
+
+__global__ void __launch_bounds__(NT) cfg_sample_kernel(const float* __restrict__ logits, const float* __restrict__ qn,
+                                                        int64_t* __restrict__ idx_out, int B, int l, float s1, float s2,
+                                                        int top_k, int use_top_p, float thr) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SampleSmem& sm = *reinterpret_cast<SampleSmem*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long row = blockIdx.x;
+  const int b = (int)(row / l), t = (int)(row % l);
+  const float* lc = logits + ((long long)b * l + t) * V_FIXED;
+  const float* lu = logits + ((long long)(B + b) * l + t) * V_FIXED;
+
+  // (1 + t) * logits[:B] - t * logits[B:], two rounded products and one rounded difference   control_var.py:502
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    int e = tid + i * NT;
+    sm.vals[e] = __fsub_rn(__fmul_rn(s1, lc[e]), __fmul_rn(s2, lu[e]));
+  }
+  __syncthreads();
+
+  // ---- top-k: logits < (k-th largest) -> -inf (ties with the k-th kept)                    helpers.py:8-10
+  if (top_k > 0 && top_k < V_FIXED) {
+    if (tid == 0) {
+      sm.sel_prefix = 0u;
+      sm.sel_remaining = (unsigned)top_k;
+    }
+    for (int pass = 0; pass < 4; ++pass) {
+      const int shift = 24 - 8 * pass;
+      sm.hist[tid] = 0u;
+      __syncthreads();
+      const unsigned prefix = sm.sel_prefix;
+#pragma unroll
+      for (int i = 0; i < PER; ++i) {
+        unsigned u = orderable(sm.vals[tid + i * NT]);
+        bool match = (pass == 0) || ((u >> (shift + 8)) == (prefix >> (shift + 8)));
+        if (match) atomicAdd(&sm.hist[(u >> shift) & 255u], 1u);
+      }
+      __syncthreads();
+      if (warp == 0) {
+        // lane owns bins [255 - 8*lane - 7, 255 - 8*lane], scanned from the top bin down
+        unsigned cnt[8], local = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          cnt[j] = sm.hist[255 - 8 * lane - j];
+          local += cnt[j];
+        }
+        unsigned incl = local;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          unsigned n = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += n;
+        }
+        unsigned excl = incl - local;
+        const unsigned rem = sm.sel_remaining;
+        if (excl < rem && rem <= incl) {
+          unsigned c = excl;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (c < rem && rem <= c + cnt[j]) {
+              sm.sel_prefix = prefix | ((unsigned)(255 - 8 * lane - j) << shift);
+              sm.sel_remaining = rem - c;
+            }
+            c += cnt[j];
+          }
+        }
+      }
+      __syncthreads();
+    }
+    const unsigned kth = sm.sel_prefix;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      int e = tid + i * NT;
+      if (orderable(sm.vals[e]) < kth) sm.vals[e] = -INFINITY;
+    }
+    __syncthreads();
+  }
+
+  float vmax;
+  // ---- top-p: remove the ascending prefix whose softmax mass is <= 1 - top_p               helpers.py:11-15
+  if (use_top_p) {
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      int e = tid + i * NT;
+      sm.keys[e] = ((unsigned long long)orderable(sm.vals[e]) << 32) | (unsigned)e;
+    }
+    __syncthreads();
+    for (int k = 2; k <= V_FIXED; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+        for (int pi = 0; pi < V_FIXED / 2 / NT; ++pi) {
+          int p = tid + pi * NT;
+          int i = 2 * p - (p & (j - 1));
+          int ixj = i + j;
+          bool up = (i & k) == 0;
+          unsigned long long a = sm.keys[i], c = sm.keys[ixj];
+          if ((a > c) == up) {
+            sm.keys[i] = c;
+            sm.keys[ixj] = a;
+          }
+        }
+        __syncthreads();
+      }
+    }
+    vmax = from_orderable((unsigned)(sm.keys[V_FIXED - 1] >> 32));
+    // softmax over the sorted values, then the running sum in ascending order
+    float ev[PER];
+    float loc = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      float v = from_orderable((unsigned)(sm.keys[tid * PER + i] >> 32));
+      ev[i] = expf(v - vmax);
+      loc += ev[i];
+    }
+    const float total = block_sum(loc, sm.redf);
+    float run = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      ev[i] = ev[i] / total;
+      run += ev[i];
+      ev[i] = run;
+    }
+    // exclusive scan of the per-thread totals
+    float incl = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      float n = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += n;
+    }
+    __syncthreads();
+    if (lane == 31) sm.redf[warp] = incl;
+    __syncthreads();
+    float woff = 0.f;
+    for (int w = 0; w < warp; ++w) woff += sm.redf[w];
+    const float off = woff + (incl - run);
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      int s = tid * PER + i;
+      float cum = off + ev[i];
+      if (cum <= thr && s != V_FIXED - 1) sm.vals[(unsigned)(sm.keys[s] & 0xffffffffu)] = -INFINITY;
+    }
+    __syncthreads();
+  } else {
+    float m = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) m = fmaxf(m, sm.vals[tid + i * NT]);
+    vmax = block_max(m, sm.redf);
+  }
+
+  // ---- multinomial(softmax(v), 1) = argmax(softmax(v) / q)                                 helpers.py:19
+  float ev[PER];
+  float loc = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    ev[i] = expf(sm.vals[tid + i * NT] - vmax);
+    loc += ev[i];
+  }
+  const float total = block_sum(loc, sm.redf);
+  const float* qr = qn + row * V_FIXED;
+  float best = -INFINITY;
+  int besti = V_FIXED;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    int e = tid + i * NT;
+    float r = (ev[i] / total) / qr[e];
+    if (r > best) {        // ascending e: the first maximum wins, like torch.argmax
+      best = r;
+      besti = e;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+    if (ob > best || (ob == best && oi < besti)) {
+      best = ob;
+      besti = oi;
+    }
+  }
+  __syncthreads();
+  if (lane == 0) {
+    sm.redf[warp] = best;
+    sm.redi[warp] = besti;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < NT / 32; ++w) {
+      if (sm.redf[w] > best || (sm.redf[w] == best && sm.redi[w] < besti)) {
+        best = sm.redf[w];
+        besti = sm.redi[w];
+      }
+    }
+    idx_out[row] = (int64_t)(besti < V_FIXED ? besti : 0);
+  }
+}
+}  // namespace
+
+extern "C" int cvar_cfg_sample(const float* logits, const float* q_noise, int64_t* idx_out, int B, int l, int V,
+                               double t, int top_k, double top_p, void* stream) {
+  CVAR_REQUIRE(V == V_FIXED, "cvar_cfg_sample: V must be %d (got %d)", V_FIXED, V);
+  CVAR_REQUIRE(B > 0 && l > 0 && top_k >= 0 && top_k <= V, "cvar_cfg_sample: bad arguments");
+  // python evaluates (1 + t) and (1 - top_p) in double, then the scalar meets an fp32 tensor as an fp32 value
+  const float s1 = (float)(1.0 + t), s2 = (float)t;
+  const float thr = (float)(1.0 - top_p);
+  cudaError_t e = cudaFuncSetAttribute(cfg_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sizeof(SampleSmem));
+  CVAR_REQUIRE(e == cudaSuccess, "cvar_cfg_sample: cannot raise shared memory: %s", cudaGetErrorString(e));
+  cfg_sample_kernel<<<(unsigned)((long long)B * l), NT, sizeof(SampleSmem), (cudaStream_t)stream>>>(
+      logits, q_noise, idx_out, B, l, s1, s2, top_k, top_p > 0.0 ? 1 : 0, thr);
+  CVAR_CHECK_LAUNCH("cvar_cfg_sample");
+  return 0;
+}

@@ -1,0 +1,343 @@
+// SIMT fp32 GEMM core (FFMA, round-to-nearest accumulate): out = epilogue(A[M,K] * B[N,K]^T).
+// This is the exact-arithmetic engine of the library: it serves the shapes the tcgen05 engine does not take
+// (tiny M, K = 32, odd N) and is the fp32 yard-stick the tensor-core engine is validated against on the GPU.
+// Operand access and the epilogue are functors, so dense layers, the fused QKV/KV-cache append and the
+// implicit-GEMM decoder convolutions share one main loop.
+#pragma once
+#include "common.cuh"
+
+namespace cvar {
+
+// ---------------------------------------------------------------------------------------------- loaders
+// A loader contract:   void prep(int slot, long long m, int batch);  float4 fetch(int slot, int k) (k % 4 == 0)
+struct DenseALoader {
+  const float* A;
+  long long lda, strideA;
+  int M, K;
+  static constexpr int kMaxSlots = 4;
+  const float* ptr[kMaxSlots];
+  __device__ __forceinline__ void prep(int slot, long long m, int batch) {
+    ptr[slot] = (m < M) ? A + (long long)batch * strideA + m * lda : nullptr;
+  }
+  __device__ __forceinline__ float4 fetch(int slot, int k) const {
+    if (ptr[slot] != nullptr && k < K) return ld4(ptr[slot] + k);
+    return make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+};
+
+// Implicit-GEMM view of a stride-1 'same' convolution over an NHWC activation (vae_modules.py Conv2d call sites):
+// row m = (n, y, x) of the OUTPUT grid, column k = (tap, ci).  Optional nearest x2 upsampling of the input
+// (Upsample2x, vae_modules.py:27-28) and optional fused GroupNorm-affine (+SiLU) on the input (vae_modules.py:58-59).
+struct ConvALoader {
+  const float* x;
+  const float* in_a;
+  const float* in_b;
+  int in_silu;
+  int Hin, Win, Cin, ks, up;      // up: 0 or 1 (log2 of the upsampling factor)
+  int Hout, Wout;
+  long long Mtot;
+  int K;
+  static constexpr int kMaxSlots = 4;
+  int sn[kMaxSlots], sy[kMaxSlots], sx[kMaxSlots];
+  __device__ __forceinline__ void prep(int slot, long long m, int /*batch*/) {
+    if (m < Mtot) {
+      int xw = (int)(m % Wout);
+      long long q = m / Wout;
+      sy[slot] = (int)(q % Hout);
+      sn[slot] = (int)(q / Hout);
+      sx[slot] = xw;
+    } else {
+      sn[slot] = -1;
+    }
+  }
+  __device__ __forceinline__ float4 fetch(int slot, int k) const {
+    float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (sn[slot] < 0 || k >= K) return z;
+    int tap = k / Cin;
+    int ci = k - tap * Cin;
+    int pad = ks >> 1;
+    int ky = tap / ks, kx = tap - ky * ks;
+    int yy = sy[slot] + ky - pad, xx = sx[slot] + kx - pad;
+    if (yy < 0 || yy >= Hout || xx < 0 || xx >= Wout) return z;      // zero padding is applied AFTER norm+act
+    int n = sn[slot];
+    const float* p = x + (((long long)n * Hin + (yy >> up)) * Win + (xx >> up)) * Cin + ci;
+    float4 v = ld4(p);
+    if (in_a != nullptr) {
+      float4 a = ld4(in_a + (long long)n * Cin + ci), b = ld4(in_b + (long long)n * Cin + ci);
+      v.x = fmaf(v.x, a.x, b.x);
+      v.y = fmaf(v.y, a.y, b.y);
+      v.z = fmaf(v.z, a.z, b.z);
+      v.w = fmaf(v.w, a.w, b.w);
+      if (in_silu) {
+        v.x = silu_f(v.x);
+        v.y = silu_f(v.y);
+        v.z = silu_f(v.z);
+        v.w = silu_f(v.w);
+      }
+    }
+    return v;
+  }
+};
+
+// B operand: W[N,K] row-major (nn.Linear / repacked conv weight), or W[K,N] row-major when kn != 0.
+struct DenseBLoader {
+  const float* W;
+  long long ldw, strideW;
+  int N, K, kn;
+};
+
+// -------------------------------------------------------------------------------------------- epilogues
+// Epilogue contract: void store(long long m, int n, const float v[4], int nvalid, int batch)
+struct DenseEpilogue {
+  float* out;
+  long long ldo, strideO;
+  const float* bias;
+  int mode;
+  float alpha;
+  const float* gamma;
+  long long gamma_row_stride;
+  int rows_per_sample;
+  const float* resid;
+  long long ldr, strideR;
+  __device__ __forceinline__ void store(long long m, int n, const float* v, int nvalid, int batch) const {
+    float* o = out + (long long)batch * strideO + m * ldo + n;
+    float r[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float b = (bias != nullptr && j < nvalid) ? bias[n + j] : 0.f;
+      float t = (mode == CVAR_EPI_BIAS) ? __fadd_rn(__fmul_rn(v[j], alpha), b) : __fadd_rn(v[j], b);
+      if (mode == CVAR_EPI_BIAS_GELU) t = gelu_tanh_f(t);
+      r[j] = t;
+    }
+    if (mode == CVAR_EPI_BIAS_GAMMA_RESID) {
+      const float* g = gamma + (m / rows_per_sample) * gamma_row_stride + n;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (j < nvalid) r[j] = __fadd_rn(o[j], __fmul_rn(r[j], g[j]));      // x + branch.mul(gamma)
+    } else if (mode == CVAR_EPI_BIAS_RESID) {
+      const float* rs = resid + (long long)batch * strideR + m * ldr + n;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (j < nvalid) r[j] = __fadd_rn(rs[j], r[j]);                      // shortcut + h
+    }
+    if (nvalid == 4 && ((((uintptr_t)o) & 15) == 0)) {
+      st4(o, make_float4(r[0], r[1], r[2], r[3]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (j < nvalid) o[j] = r[j];
+    }
+  }
+};
+
+// qkv = x W^T + [q_bias, k_bias, v_bias]; q to (R,H,l,64), k/v appended to the cache      (basic_var.py:92-108)
+struct QkvEpilogue {
+  const float* q_bias;
+  const float* k_bias;
+  const float* v_bias;
+  float* q_out;
+  float* k_cache;
+  float* v_cache;
+  int C, H, l, L_prev, T_max;
+  __device__ __forceinline__ void store(long long m, int n, const float* v, int nvalid, int /*batch*/) const {
+    int which = n / C;
+    int c = n - which * C;
+    int h = c >> 6, d = c & 63;
+    int r = (int)(m / l), t = (int)(m - (long long)r * l);
+    const float* bias = which == 0 ? q_bias : (which == 1 ? k_bias : v_bias);
+    float4 o;
+    o.x = __fadd_rn(v[0], bias[c + 0]);
+    o.y = __fadd_rn(v[1], bias[c + 1]);
+    o.z = __fadd_rn(v[2], bias[c + 2]);
+    o.w = __fadd_rn(v[3], bias[c + 3]);
+    float* dst;
+    if (which == 0)
+      dst = q_out + (((long long)r * H + h) * l + t) * 64 + d;
+    else
+      dst = (which == 1 ? k_cache : v_cache) + (((long long)r * H + h) * T_max + L_prev + t) * 64 + d;
+    st4(dst, o);
+    (void)nvalid;
+  }
+};
+
+// conv output: NHWC (+bias, +residual) or the final image plane write                    (vqvae.py:88-89)
+struct ConvEpilogue {
+  float* out;
+  const float* bias;
+  const float* resid;
+  int Cout, out_mode;
+  int Hout, Wout, out_rows_total, row_offset;
+  __device__ __forceinline__ void store(long long m, int n, const float* v, int nvalid, int /*batch*/) const {
+    if (out_mode == 0) {
+      float* o = out + m * Cout + n;
+      float r[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) r[j] = __fadd_rn(v[j], (j < nvalid) ? bias[n + j] : 0.f);
+      if (resid != nullptr) {
+        const float* rs = resid + m * Cout + n;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (j < nvalid) r[j] = __fadd_rn(rs[j], r[j]);
+      }
+      if (nvalid == 4) {
+        st4(o, make_float4(r[0], r[1], r[2], r[3]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (j < nvalid) o[j] = r[j];
+      }
+    } else {
+      int xw = (int)(m % Wout);
+      long long q = m / Wout;
+      int y = (int)(q % Hout);
+      long long nimg = q / Hout;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (j < nvalid) {
+          float t = __fadd_rn(v[j], bias[n + j]);
+          t = fminf(fmaxf(t, -1.f), 1.f);                    // .clamp_(-1, 1)            vqvae.py:89
+          if (out_mode == 1) t = __fmul_rn(__fadd_rn(t, 1.f), 0.5f);   // .add_(1).mul_(0.5)  control_var.py:563
+          out[((nimg * Cout + (n + j)) * out_rows_total + row_offset + y) * Wout + xw] = t;
+        }
+      }
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------ main kernel
+template <int BM, int BN, int FM, int FN, class AL, class EP>
+__global__ void __launch_bounds__((BM / (4 * FM)) * (BN / (4 * FN)))
+sgemm_kernel(AL al, DenseBLoader bl, EP ep, long long M, int N, int K) {
+  constexpr int BK = 16;
+  constexpr int TX = BN / (4 * FN), TY = BM / (4 * FM), NT = TX * TY;
+  constexpr int SA = (BM * BK / 4) / NT;
+  constexpr int SB = (BN * BK / 4) / NT;
+  static_assert(SA >= 1 && SA <= 4 && SB >= 1 && SB <= 4, "tile/thread configuration");
+  __shared__ __align__(16) float As[2][BK][BM + 4];
+  __shared__ __align__(16) float Bs[2][BK][BN + 4];
+
+  const int tid = threadIdx.x, tx = tid % TX, ty = tid / TX;
+  const long long m0 = (long long)blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  const int bz = blockIdx.z;
+
+#pragma unroll
+  for (int s = 0; s < SA; ++s) al.prep(s, m0 + (s * NT + tid) / 4, bz);
+  const float* Wb = bl.W + (long long)bz * bl.strideW;
+
+  float4 ra[SA], rb[SB];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int s = 0; s < SA; ++s) ra[s] = al.fetch(s, k0 + ((s * NT + tid) & 3) * 4);
+#pragma unroll
+    for (int s = 0; s < SB; ++s) {
+      int item = s * NT + tid;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (!bl.kn) {
+        int n = n0 + (item >> 2), k = k0 + (item & 3) * 4;
+        if (n < N && k < K) v = ld4(Wb + (long long)n * bl.ldw + k);
+      } else {
+        int k = k0 + item / (BN / 4), n = n0 + (item % (BN / 4)) * 4;
+        if (k < K && n < N) v = ld4(Wb + (long long)k * bl.ldw + n);
+      }
+      rb[s] = v;
+    }
+  };
+  auto stash = [&](int buf) {
+#pragma unroll
+    for (int s = 0; s < SA; ++s) {
+      int item = s * NT + tid, row = item >> 2, kq = (item & 3) * 4;
+      As[buf][kq + 0][row] = ra[s].x;
+      As[buf][kq + 1][row] = ra[s].y;
+      As[buf][kq + 2][row] = ra[s].z;
+      As[buf][kq + 3][row] = ra[s].w;
+    }
+#pragma unroll
+    for (int s = 0; s < SB; ++s) {
+      int item = s * NT + tid;
+      if (!bl.kn) {
+        int row = item >> 2, kq = (item & 3) * 4;
+        Bs[buf][kq + 0][row] = rb[s].x;
+        Bs[buf][kq + 1][row] = rb[s].y;
+        Bs[buf][kq + 2][row] = rb[s].z;
+        Bs[buf][kq + 3][row] = rb[s].w;
+      } else {
+        int k = item / (BN / 4), nq = (item % (BN / 4)) * 4;
+        *reinterpret_cast<float4*>(&Bs[buf][k][nq]) = rb[s];
+      }
+    }
+  };
+
+  float acc[4 * FM][4 * FN];
+#pragma unroll
+  for (int i = 0; i < 4 * FM; ++i)
+#pragma unroll
+    for (int j = 0; j < 4 * FN; ++j) acc[i][j] = 0.f;
+
+  const int nk = (K + BK - 1) / BK;
+  fetch(0);
+  stash(0);
+  __syncthreads();
+  for (int kt = 0; kt < nk; ++kt) {
+    const int cur = kt & 1;
+    if (kt + 1 < nk) fetch((kt + 1) * BK);
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float a[4 * FM], b[4 * FN];
+#pragma unroll
+      for (int f = 0; f < FM; ++f) {
+        float4 t = *reinterpret_cast<const float4*>(&As[cur][k][f * (BM / FM) + ty * 4]);
+        a[4 * f + 0] = t.x, a[4 * f + 1] = t.y, a[4 * f + 2] = t.z, a[4 * f + 3] = t.w;
+      }
+#pragma unroll
+      for (int g = 0; g < FN; ++g) {
+        float4 t = *reinterpret_cast<const float4*>(&Bs[cur][k][g * (BN / FN) + tx * 4]);
+        b[4 * g + 0] = t.x, b[4 * g + 1] = t.y, b[4 * g + 2] = t.z, b[4 * g + 3] = t.w;
+      }
+#pragma unroll
+      for (int i = 0; i < 4 * FM; ++i)
+#pragma unroll
+        for (int j = 0; j < 4 * FN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (kt + 1 < nk) stash(cur ^ 1);
+    __syncthreads();
+  }
+
+#pragma unroll
+  for (int f = 0; f < FM; ++f)
+#pragma unroll
+    for (int ii = 0; ii < 4; ++ii) {
+      long long m = m0 + f * (BM / FM) + ty * 4 + ii;
+      if (m >= M) continue;
+#pragma unroll
+      for (int g = 0; g < FN; ++g) {
+        int n = n0 + g * (BN / FN) + tx * 4;
+        if (n >= N) continue;
+        int nvalid = min(4, N - n);
+        ep.store(m, n, &acc[4 * f + ii][4 * g], nvalid, bz);
+      }
+    }
+}
+
+template <class AL, class EP>
+static int launch_sgemm(AL al, DenseBLoader bl, EP ep, long long M, int N, int K, int batch, cudaStream_t s,
+                        const char* name) {
+  // tile choice: 128x128 for bulk work, 128x32 when N is narrow / not a multiple of 64 (decoder 160-channel
+  // layers, the 3-channel image conv), 64x64 when the 128-tiles would leave most of the 148 SMs idle.
+  long long tiles_L = (long long)cdiv(M, 128) * cdiv(N, 128) * batch;
+  bool narrow = (N <= 32) || (N % 64 != 0 && N <= 192);
+  if (narrow) {
+    dim3 grid(cdiv(M, 128), cdiv(N, 32), batch);
+    sgemm_kernel<128, 32, 2, 1, AL, EP><<<grid, 128, 0, s>>>(al, bl, ep, M, N, K);
+  } else if (tiles_L < 148) {
+    dim3 grid(cdiv(M, 64), cdiv(N, 64), batch);
+    sgemm_kernel<64, 64, 1, 1, AL, EP><<<grid, 256, 0, s>>>(al, bl, ep, M, N, K);
+  } else {
+    dim3 grid(cdiv(M, 128), cdiv(N, 128), batch);
+    sgemm_kernel<128, 128, 2, 2, AL, EP><<<grid, 256, 0, s>>>(al, bl, ep, M, N, K);
+  }
+  CVAR_CHECK_LAUNCH(name);
+  return 0;
+}
+
+}  // namespace cvar

@@ -1,0 +1,170 @@
+"""Thin tensor-level wrappers over the C ABI (include/cvar.h).  PyTorch supplies device memory and the current
+stream; every computation below happens inside libcvar_sm100.so."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import ConvArgs, GemmArgs, check
+
+EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_GAMMA_RESID, EPI_BIAS_RESID = 0, 1, 2, 3
+ENGINE_SIMT, ENGINE_TC_3XTF32, ENGINE_TC_BF16 = 0, 1, 2
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(*ts):
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise _lib.CvarError("controlvar_b200 ops need CUDA tensors (there is no CPU fallback)")
+        if t.dtype not in (torch.float32, torch.int64, torch.float64):
+            raise _lib.CvarError(f"unsupported dtype {t.dtype}")
+
+
+def launch_count() -> int:
+    return int(_lib.load().cvar_launch_count())
+
+
+def set_gemm_engine(engine: int) -> int:
+    return int(_lib.load().cvar_set_gemm_engine(int(engine)))
+
+
+def get_gemm_engine() -> int:
+    return int(_lib.load().cvar_get_gemm_engine())
+
+
+def lvl_pos(lvl_embed, lvl_1L, pos_1LC, out):
+    _chk(lvl_embed, lvl_1L, pos_1LC, out)
+    T, Cdim = pos_1LC.shape[-2], pos_1LC.shape[-1]
+    check(_lib.load().cvar_lvl_pos(_p(lvl_embed), _p(lvl_1L), _p(pos_1LC), _p(out), T, Cdim, _stream()), "cvar_lvl_pos")
+    return out
+
+
+def prologue(class_emb, cond_embed, pos_start, lvl_pos_t, label_B, cond_type_B, num_classes, cond_BD, silu_cond, x0):
+    _chk(class_emb, cond_embed, pos_start, lvl_pos_t, label_B, cond_type_B, cond_BD, silu_cond, x0)
+    B, Cdim = label_B.shape[0], class_emb.shape[1]
+    check(_lib.load().cvar_prologue(_p(class_emb), _p(cond_embed), _p(pos_start), _p(lvl_pos_t), _p(label_B),
+                                    _p(cond_type_B), B, Cdim, num_classes, _p(cond_BD), _p(silu_cond), _p(x0),
+                                    _stream()), "cvar_prologue")
+
+
+def ln_modulate(x, scale, shift, mod_row_stride, out, M, Cdim, rows_per_sample, eps):
+    """scale/shift: views into an ada_lin output; only their data pointers and the common row stride are used."""
+    _chk(x, scale, shift, out)
+    check(_lib.load().cvar_ln_modulate(_p(x), _p(scale), _p(shift), mod_row_stride, _p(out), M, Cdim, rows_per_sample,
+                                       float(eps), _stream()), "cvar_ln_modulate")
+    return out
+
+
+def gemm(A, W, bias, out, M, N, K, *, lda=None, ldw=None, ldo=None, epilogue=EPI_BIAS, alpha=1.0, w_is_kn=False,
+         batch=1, strideA=0, strideW=0, strideO=0, gamma=None, gamma_row_stride=0, rows_per_sample=1,
+         resid=None, ldr=None, strideR=0):
+    _chk(A, W, bias, out, gamma, resid)
+    a = GemmArgs()
+    a.A, a.lda, a.strideA = _p(A), (K if lda is None else lda), strideA
+    a.W, a.ldw, a.strideW, a.w_is_kn = _p(W), ((N if w_is_kn else K) if ldw is None else ldw), strideW, int(w_is_kn)
+    a.bias = _p(bias)
+    a.out, a.ldo, a.strideO = _p(out), (N if ldo is None else ldo), strideO
+    a.M, a.N, a.K, a.batch = M, N, K, batch
+    a.epilogue, a.alpha = epilogue, float(alpha)
+    a.gamma, a.gamma_row_stride, a.rows_per_sample = _p(gamma), gamma_row_stride, rows_per_sample
+    a.resid, a.ldr, a.strideR = _p(resid), (N if ldr is None else ldr), strideR
+    check(_lib.load().cvar_gemm(C.byref(a), _stream()), "cvar_gemm")
+    return out
+
+
+def qkv_project(A, Wqkv, q_bias, k_bias, v_bias, q_out, k_cache, v_cache, R, l, L_prev, T_max, H, cos_attn,
+                scale_mul_H):
+    _chk(A, Wqkv, q_bias, k_bias, v_bias, q_out, k_cache, v_cache, scale_mul_H)
+    check(_lib.load().cvar_qkv_project(_p(A), _p(Wqkv), _p(q_bias), _p(k_bias), _p(v_bias), _p(q_out), _p(k_cache),
+                                       _p(v_cache), R, l, L_prev, T_max, H, int(cos_attn), _p(scale_mul_H),
+                                       _stream()), "cvar_qkv_project")
+
+
+def attn_kvcache(q, k_cache, v_cache, out, R, H, l, L, T_max, scale):
+    _chk(q, k_cache, v_cache, out)
+    check(_lib.load().cvar_attn_kvcache(_p(q), _p(k_cache), _p(v_cache), _p(out), R, H, l, L, T_max, float(scale),
+                                        _stream()), "cvar_attn_kvcache")
+    return out
+
+
+def cfg_sample(logits, q_noise, idx_out, B, l, V, t, top_k, top_p):
+    _chk(logits, q_noise, idx_out)
+    check(_lib.load().cvar_cfg_sample(_p(logits), _p(q_noise), _p(idx_out), B, l, V, float(t), int(top_k),
+                                      float(top_p), _stream()), "cvar_cfg_sample")
+    return idx_out
+
+
+def vq_step(idx, embedding, U, phi_w, phi_b, word_w, word_b, lvl_pos_next, f_hat, x_next, B, pn, pn_next, hw, Cvae, Cdim):
+    _chk(idx, embedding, U, phi_w, phi_b, word_w, word_b, lvl_pos_next, f_hat, x_next)
+    check(_lib.load().cvar_vq_step(_p(idx), _p(embedding), _p(U), _p(phi_w), _p(phi_b), _p(word_w), _p(word_b),
+                                   _p(lvl_pos_next), _p(f_hat), _p(x_next), B, pn, pn_next, hw, Cvae, Cdim,
+                                   _stream()), "cvar_vq_step")
+
+
+def vq_nearest(z_NC, embedding, idx_out):
+    _chk(z_NC, embedding, idx_out)
+    N, Cv = z_NC.shape
+    check(_lib.load().cvar_vq_nearest(_p(z_NC), _p(embedding), _p(idx_out), N, Cv, embedding.shape[0], _stream()),
+          "cvar_vq_nearest")
+    return idx_out
+
+
+def nchw_to_nhwc(x_view, out, B, Cdim, H, W, in_batch_stride):
+    _chk(x_view, out)
+    check(_lib.load().cvar_nchw_to_nhwc(_p(x_view), _p(out), B, Cdim, H, W, in_batch_stride, _stream()),
+          "cvar_nchw_to_nhwc")
+    return out
+
+
+def gn_chunks(HW: int) -> int:
+    return int(_lib.load().cvar_gn_chunks(HW))
+
+
+def gn_stats(x_nhwc, gamma, beta, a_out, b_out, scratch, B, HW, Cdim, groups=32, eps=1e-6):
+    _chk(x_nhwc, gamma, beta, a_out, b_out, scratch)
+    check(_lib.load().cvar_gn_stats(_p(x_nhwc), _p(gamma), _p(beta), _p(a_out), _p(b_out), _p(scratch), B, HW, Cdim,
+                                    groups, float(eps), _stream()), "cvar_gn_stats")
+
+
+def conv2d(x, w_packed, bias, out, B, Hin, Win, Cin, Cout, ks, *, in_a=None, in_b=None, in_silu=False, resid=None,
+           upsample2x=False, out_mode=0, out_rows_total=0, row_offset=0):
+    _chk(x, w_packed, bias, out, in_a, in_b, resid)
+    a = ConvArgs()
+    a.x, a.w, a.bias, a.out = _p(x), _p(w_packed), _p(bias), _p(out)
+    a.in_a, a.in_b, a.in_silu = _p(in_a), _p(in_b), int(in_silu)
+    a.resid = _p(resid)
+    a.B, a.Hin, a.Win, a.Cin, a.Cout, a.ks, a.upsample2x = B, Hin, Win, Cin, Cout, ks, int(upsample2x)
+    a.out_mode, a.out_rows_total, a.row_offset = out_mode, out_rows_total, row_offset
+    check(_lib.load().cvar_conv2d(C.byref(a), _stream()), "cvar_conv2d")
+    return out
+
+
+def repack_conv_weight(w_oihw, out):
+    _chk(w_oihw, out)
+    Cout, Cin, ks, _ = w_oihw.shape
+    check(_lib.load().cvar_repack_conv_weight(_p(w_oihw), _p(out), Cout, Cin, ks, _stream()), "cvar_repack_conv_weight")
+    return out
+
+
+def affine_nc(x, a, b, out, B, HW, Cdim, silu=False):
+    _chk(x, a, b, out)
+    check(_lib.load().cvar_affine_nc(_p(x), _p(a), _p(b), _p(out), B, HW, Cdim, int(silu), _stream()), "cvar_affine_nc")
+    return out
+
+
+def softmax_rows(x, rows, cols):
+    _chk(x)
+    check(_lib.load().cvar_softmax_rows(_p(x), rows, cols, _stream()), "cvar_softmax_rows")
+    return x

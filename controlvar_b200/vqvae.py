@@ -1,0 +1,239 @@
+"""Host mirror of the reference VQVAE for the decode side of the sampling path.
+
+Same constructor arguments, attribute names (``quantize``, ``Cvae``, ``vocab_size``) and ``state_dict`` keys as
+/root/reference/models/vqvae.py:16-48, so checkpoints load with ``load_state_dict``.  ``fhat_to_img``
+(models/vqvae.py:88-89; alias ``decode``) runs the whole Decoder (models/vae_modules.py:163-226) through
+libcvar_sm100.so: NHWC activations, GroupNorm folded to a per-(sample, channel) affine that the next convolution
+applies (with SiLU) while it loads its operand, nearest-x2 upsampling folded into the convolution's gather, residual
+adds and the final clamp / de-normalise / NCHW store folded into epilogues.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .config import PathConfig, DEFAULT_PATCH_NUMS
+from .weights import decoder_plan, vae_key_shapes
+
+_BUFFER_KEYS = ("ema_vocab_hit_SV",)
+
+
+class _Node(nn.Module):
+    """Anonymous container used to reproduce the reference's dotted parameter names."""
+
+
+def register_tree(root: nn.Module, key: str, tensor: torch.Tensor, is_buffer: bool) -> None:
+    parts = key.split(".")
+    mod = root
+    for p in parts[:-1]:
+        if not hasattr(mod, p):
+            mod.add_module(p, _Node())
+        mod = getattr(mod, p)
+    if is_buffer:
+        mod.register_buffer(parts[-1], tensor)
+    else:
+        mod.register_parameter(parts[-1], nn.Parameter(tensor, requires_grad=False))
+
+
+class VQVAE(nn.Module):
+    def __init__(
+        self, vocab_size=4096, z_channels=32, ch=128, dropout=0.0, beta=0.25, using_znorm=False, quant_conv_ks=3,
+        quant_resi=0.5, share_quant_resi=4, default_qresi_counts=0, v_patch_nums=DEFAULT_PATCH_NUMS, test_mode=True,
+    ):
+        super().__init__()
+        if using_znorm or quant_conv_ks != 3 or share_quant_resi != 4 or abs(quant_resi - 0.5) > 1e-9:
+            raise NotImplementedError("only the released VQVAE configuration (vae_ch160v4096z32) is implemented")
+        if z_channels != 32:
+            raise NotImplementedError("the sm_100a kernels are specialised for Cvae = 32")
+        self.test_mode = test_mode
+        self.V, self.Cvae = vocab_size, z_channels
+        self.vocab_size = vocab_size
+        self.cfg = PathConfig(patch_nums=tuple(v_patch_nums), vocab_size=vocab_size, Cvae=z_channels, vae_ch=ch,
+                              share_quant_resi=share_quant_resi)
+        self.downsample = 2 ** (len(self.cfg.vae_ch_mult) - 1)
+        for key, shape in vae_key_shapes(self.cfg, with_encoder=True).items():
+            is_buf = key.split(".")[-1] in _BUFFER_KEYS
+            register_tree(self, key, torch.zeros(shape), is_buf)
+        # attribute surface of VectorQuantizer2 that callers read (quant.py:15-37)
+        q = self.quantize
+        q.vocab_size, q.Cvae, q.v_patch_nums, q.share_quant_resi = vocab_size, z_channels, tuple(v_patch_nums), share_quant_resi
+        self._plan = decoder_plan(self.cfg)
+        self._packed: Dict[str, torch.Tensor] = {}
+        self._ws: Dict[Tuple, torch.Tensor] = {}
+        self.eval()
+
+    # -------------------------------------------------------------------------------------------- weights
+    def load_state_dict(self, state_dict, strict=True, assign=False):
+        # models/vqvae.py:106-109: tolerate a different number of scales in the usage statistics buffer
+        sd = dict(state_dict)
+        k = "quantize.ema_vocab_hit_SV"
+        if k in sd and sd[k].shape[0] != self.quantize.ema_vocab_hit_SV.shape[0]:
+            sd[k] = self.quantize.ema_vocab_hit_SV
+        self._packed.clear()
+        return super().load_state_dict(sd, strict=strict, assign=assign)
+
+    def _apply(self, fn, recurse=True):
+        self._packed.clear()
+        self._ws.clear()
+        return super()._apply(fn, recurse)
+
+    def _w(self, key: str) -> torch.Tensor:
+        return self.get_parameter(key)
+
+    def _conv_w(self, prefix: str) -> torch.Tensor:
+        """Conv weight repacked (Cout, ks*ks*Cin) tap-major for the implicit-GEMM kernels (cached)."""
+        key = prefix + ".weight"
+        t = self._packed.get(key)
+        if t is None:
+            w = self._w(key)
+            t = torch.empty(w.shape[0], w.shape[1] * w.shape[2] * w.shape[3], device=w.device, dtype=torch.float32)
+            ops.repack_conv_weight(w.contiguous(), t)
+            self._packed[key] = t
+        return t
+
+    def _buf(self, name: str, shape, dtype=torch.float32) -> torch.Tensor:
+        dev = self._w("post_quant_conv.weight").device
+        key = (name, tuple(shape), dtype)
+        t = self._ws.get(key)
+        if t is None or t.device != dev:
+            t = torch.empty(shape, device=dev, dtype=dtype)
+            self._ws[key] = t
+        return t
+
+    def release_workspace(self):
+        self._ws.clear()
+
+    # -------------------------------------------------------------------------------------------- decoder
+    def _gn(self, x, prefix: str, B, HW, Cn, slot: int):
+        a = self._buf(f"gn_a{slot}", (B, Cn))
+        b = self._buf(f"gn_b{slot}", (B, Cn))
+        scratch = self._buf("gn_scratch", (2 * B * 32 * ops.gn_chunks(HW),), torch.float64)
+        ops.gn_stats(x, self._w(prefix + ".weight"), self._w(prefix + ".bias"), a, b, scratch, B, HW, Cn)
+        return a, b
+
+    def _resblock(self, x, prefix, B, H, W, cin, cout, bufs):
+        """ResnetBlock.forward (vae_modules.py:57-60); x is never written."""
+        h1, out = bufs
+        a1, b1 = self._gn(x, prefix + "norm1", B, H * W, cin, 0)
+        ops.conv2d(x, self._conv_w(prefix + "conv1"), self._w(prefix + "conv1.bias"), h1, B, H, W, cin, cout, 3,
+                   in_a=a1, in_b=b1, in_silu=True)
+        a2, b2 = self._gn(h1, prefix + "norm2", B, H * W, cout, 1)
+        if cin != cout:
+            sc = self._buf("shortcut", (B, H, W, cout))
+            ops.conv2d(x, self._conv_w(prefix + "nin_shortcut"), self._w(prefix + "nin_shortcut.bias"), sc, B, H, W,
+                       cin, cout, 1)
+        else:
+            sc = x
+        ops.conv2d(h1, self._conv_w(prefix + "conv2"), self._w(prefix + "conv2.bias"), out, B, H, W, cout, cout, 3,
+                   in_a=a2, in_b=b2, in_silu=True, resid=sc)
+        return out
+
+    def _attnblock(self, x, prefix, B, H, W, Cn, out):
+        """AttnBlock.forward (vae_modules.py:73-92) on NHWC: single head over HW positions."""
+        HW = H * W
+        a, b = self._gn(x, prefix + "norm", B, HW, Cn, 0)
+        xn = self._buf("attn_xn", (B, HW, Cn))
+        ops.affine_nc(x, a, b, xn, B, HW, Cn, silu=False)
+        qkv = self._buf("attn_qkv", (B, HW, 3 * Cn))
+        ops.gemm(xn, self._conv_w(prefix + "qkv"), self._w(prefix + "qkv.bias"), qkv, B * HW, 3 * Cn, Cn)
+        S = self._buf("attn_S", (B, HW, HW))
+        # w = bmm(q, k).mul_(C ** -0.5)
+        ops.gemm(qkv, qkv[:, :, Cn:], None, S, HW, HW, Cn, lda=3 * Cn, ldw=3 * Cn, ldo=HW, alpha=int(Cn) ** (-0.5),
+                 batch=B, strideA=HW * 3 * Cn, strideW=HW * 3 * Cn, strideO=HW * HW)
+        ops.softmax_rows(S, B * HW, HW)
+        hbuf = self._buf("attn_h", (B, HW, Cn))
+        # h[i, c] = sum_j P[i, j] v[j, c]
+        ops.gemm(S, qkv[:, :, 2 * Cn:], None, hbuf, HW, Cn, HW, lda=HW, ldw=3 * Cn, ldo=Cn, w_is_kn=True, batch=B,
+                 strideA=HW * HW, strideW=HW * 3 * Cn, strideO=HW * Cn)
+        ops.gemm(hbuf, self._conv_w(prefix + "proj_out"), self._w(prefix + "proj_out.bias"), out, B * HW, Cn, Cn,
+                 epilogue=ops.EPI_BIAS_RESID, resid=x)
+        return out
+
+    def _decode_nhwc(self, z_nhwc: torch.Tensor, B: int, hw: int, img_out: torch.Tensor, rows_total: int,
+                     row_offset: int, out_mode: int = 1) -> None:
+        """post_quant_conv + Decoder.forward + clamp + (x+1)/2, image planes written into img_out (NCHW)."""
+        cfg = self.cfg
+        H = W = hw
+        zq = self._buf("z_pq", (B, H, W, cfg.Cvae))
+        ops.conv2d(z_nhwc, self._conv_w("post_quant_conv"), self._w("post_quant_conv.bias"), zq, B, H, W, cfg.Cvae,
+                   cfg.Cvae, 3)
+        cur = zq
+        ring_i = 0
+
+        def ring(shape):
+            # three flat activation buffers, sized for the largest tensor of the plan, handed out round-robin
+            nonlocal ring_i
+            ring_i = (ring_i + 1) % 3
+            n = 1
+            for s_ in shape:
+                n *= s_
+            return self._buf(f"act{ring_i}", (act_numel,))[:n].view(shape)
+
+        act_numel, hh = 0, hw
+        for op, _, cin, cout in self._plan:
+            if op == "up":
+                hh *= 2
+            act_numel = max(act_numel, B * hh * hh * max(cin if op == "out" else cout, 1))
+
+        for op, prefix, cin, cout in self._plan:
+            if op == "conv3":
+                out = ring((B, H, W, cout))
+                ops.conv2d(cur, self._conv_w(prefix), self._w(prefix + ".bias"), out, B, H, W, cin, cout, 3)
+                cur = out
+            elif op == "res":
+                h1 = ring((B, H, W, cout))
+                out = ring((B, H, W, cout))
+                cur = self._resblock(cur, prefix, B, H, W, cin, cout, (h1, out))
+            elif op == "attn":
+                out = ring((B, H, W, cout))
+                cur = self._attnblock(cur, prefix, B, H, W, cin, out)
+            elif op == "up":
+                out = ring((B, 2 * H, 2 * W, cout))
+                ops.conv2d(cur, self._conv_w(prefix), self._w(prefix + ".bias"), out, B, H, W, cin, cout, 3,
+                           upsample2x=True)
+                H, W = 2 * H, 2 * W
+                cur = out
+            elif op == "out":
+                a, b = self._gn(cur, "decoder.norm_out", B, H * W, cin, 0)
+                ops.conv2d(cur, self._conv_w("decoder.conv_out"), self._w("decoder.conv_out.bias"), img_out, B, H, W,
+                           cin, 3, 3, in_a=a, in_b=b, in_silu=True, out_mode=out_mode, out_rows_total=rows_total,
+                           row_offset=row_offset)
+            else:
+                raise AssertionError(op)
+
+    @torch.no_grad()
+    def fhat_to_img(self, f_hat: torch.Tensor) -> torch.Tensor:
+        """decoder(post_quant_conv(f_hat)).clamp_(-1, 1) - models/vqvae.py:88-89.  f_hat: (B, Cvae, h, w) NCHW
+        (may be a strided view such as the halves of control_var.py:525-526).  Returns (B, 3, 16h, 16w) in [-1, 1]."""
+        return self._fhat_to_img(f_hat, out_mode=2)
+
+    decode = fhat_to_img   # the name BASELINE.json's north_star uses for this entry point
+
+    @torch.no_grad()
+    def _fhat_to_img(self, f_hat: torch.Tensor, out: Optional[torch.Tensor] = None, rows_total: int = 0,
+                     row_offset: int = 0, out_mode: int = 1) -> torch.Tensor:
+        """out_mode 1: clamp + (x+1)/2 fused (what control_var.py:563-565 does right after); 2: clamp only."""
+        if not f_hat.is_cuda:
+            raise RuntimeError("controlvar_b200.VQVAE runs on CUDA only (no CPU fallback)")
+        B, Cz, h, w = f_hat.shape
+        assert Cz == self.Cvae and h == w
+        if f_hat.stride(3) != 1 or f_hat.stride(2) != w or f_hat.stride(0) != Cz * f_hat.stride(1):
+            f_hat = f_hat.contiguous()
+        z = self._buf("z_nhwc", (B, h, w, Cz))
+        ops.nchw_to_nhwc(f_hat, z, B, Cz, h, w, f_hat.stride(0))
+        side = h * self.downsample
+        if out is None:
+            out = torch.empty(B, 3, side, side, device=f_hat.device, dtype=torch.float32)
+            rows_total, row_offset = side, 0
+        self._decode_nhwc(z, B, h, out, rows_total, row_offset, out_mode)
+        return out
+
+    # the remaining reference entry points touch the encoder / training side (SURVEY.md section 8f "next")
+    def img_to_idxBl(self, *a, **k):
+        raise NotImplementedError("VQVAE.img_to_idxBl (encoder side) is scheduled after the sampling path, see DESIGN.md")
+
+    def forward(self, *a, **k):
+        raise NotImplementedError("VQVAE.forward is training-only in the reference and out of scope")

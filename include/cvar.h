@@ -1,0 +1,160 @@
+/*
+ * cvar.h - C ABI of libcvar_sm100.so: the sm_100a kernels behind ControlVAR's next-scale sampling hot path.
+ *
+ * The reference (lxa9867/ControlVAR) has no plugin / FFI layer: its boundary is the Python method surface
+ *   ControlVAR.autoregressive_infer_cfg      models/control_var.py:356-565
+ *   VQVAE.fhat_to_img                        models/vqvae.py:88-89
+ * (SURVEY.md section 8b).  The host mirror in controlvar_b200/ keeps those signatures and calls the entry points
+ * below through ctypes.  Each entry point names the reference code it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless named host_*;
+ *   - all launches are asynchronous on the caller's stream (a cudaStream_t passed as void*);
+ *   - nothing is allocated or freed inside the library; scratch memory is caller-owned;
+ *   - return value 0 = ok, negative = error; cvar_last_error() returns a thread-local message;
+ *   - tensors are dense fp32 row-major unless a stride is given; token / class indices are int64.
+ */
+#ifndef CVAR_H_
+#define CVAR_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CVAR_ABI_VERSION 1
+#if defined(__GNUC__)
+#define CVAR_API __attribute__((visibility("default")))
+#else
+#define CVAR_API
+#endif
+
+CVAR_API int cvar_abi_version(void);
+CVAR_API const char* cvar_last_error(void);
+/* Number of kernel launches issued by this library in the calling process since load (bench.py: gpu_launches). */
+CVAR_API long long cvar_launch_count(void);
+/* Which GEMM engine serves cvar_gemm/conv when the shape allows: 0 = SIMT fp32 FFMA, 1 = tcgen05 3xTF32 (fp32-class),
+ * 2 = tcgen05 bf16 (fast, not parity-grade).  Returns the previous value. */
+CVAR_API int cvar_set_gemm_engine(int engine);
+CVAR_API int cvar_get_gemm_engine(void);
+
+/* ---- prologue: control_var.py:381-383, 399-409 -------------------------------------------------------------
+ * lvl_pos[t,:] = lvl_embed[lvl_1L[t],:] + pos_1LC[t,:]                                   (control_var.py:383) */
+CVAR_API int cvar_lvl_pos(const float* lvl_embed, const int64_t* lvl_1L, const float* pos_1LC, float* lvl_pos,
+                 int T, int C, void* stream);
+/* rows r < B use (label[r], cond_type[r]); rows r >= B use (num_classes, 4) - the CFG "unconditional" half.
+ * cond_BD[r,:]   = class_emb[lab,:]                                  (control_var.py:381)
+ * silu_cond[r,:] = SiLU(cond_BD[r,:])                                (input of every ada_lin, basic_var.py:198)
+ * x0[r,0,:] = cond_embed[ct,:] + pos_start[0,:] + lvl_pos[0,:]       (control_var.py:402-409)
+ * x0[r,1,:] = class_emb[lab,:] + pos_start[1,:] + lvl_pos[1,:] */
+CVAR_API int cvar_prologue(const float* class_emb, const float* cond_embed, const float* pos_start, const float* lvl_pos,
+                  const int64_t* label_B, const int64_t* cond_type_B, int B, int C, int num_classes,
+                  float* cond_BD, float* silu_cond, float* x0, void* stream);
+
+/* ---- AdaLN-modulated LayerNorm: basic_var.py:208-209, control_var.py:699-701 ---------------------------------
+ * y[m,:] = LayerNorm(x[m,:], eps, no affine) * (scale[r,:] + 1) + shift[r,:],  r = m / rows_per_sample.
+ * scale/shift are slices of an ada_lin output, so they carry a row stride (6C or 2C floats). */
+CVAR_API int cvar_ln_modulate(const float* x, const float* scale, const float* shift, long long mod_row_stride,
+                     float* y, int M, int C, int rows_per_sample, float eps, void* stream);
+
+/* ---- dense layers: F.linear call sites of basic_var.py:51,92,119 and control_var.py:221 -----------------------
+ * out = epilogue(A[M,K] @ W[N,K]^T + bias[N]).  A, W, out row-major with leading dimensions lda/ldw/ldo.
+ * batch > 1 runs independent problems separated by the given strides (decoder attention).
+ * w_is_kn != 0 means W is stored [K,N] row-major (used for P @ V in vae_modules.py:89). */
+enum {
+  CVAR_EPI_BIAS = 0,            /* out = acc*alpha + bias                                                  */
+  CVAR_EPI_BIAS_GELU = 1,       /* out = GELU_tanh(acc + bias)               (FFN.fc1 + act, basic_var.py:51) */
+  CVAR_EPI_BIAS_GAMMA_RESID = 2,/* out[m,n] += gamma[m/rows_per_sample, n] * (acc + bias[n])  (basic_var.py:208-209) */
+  CVAR_EPI_BIAS_RESID = 3       /* out[m,n] = resid[m,n] + (acc + bias[n])                    (vae_modules.py:60,92) */
+};
+typedef struct {
+  const float* A; long long lda; long long strideA;
+  const float* W; long long ldw; long long strideW; int w_is_kn;
+  const float* bias;                      /* [N] or NULL */
+  float* out; long long ldo; long long strideO;
+  int M, N, K, batch;
+  int epilogue; float alpha;
+  const float* gamma; long long gamma_row_stride; int rows_per_sample;   /* CVAR_EPI_BIAS_GAMMA_RESID */
+  const float* resid; long long ldr; long long strideR;                  /* CVAR_EPI_BIAS_RESID */
+} cvar_gemm_args;
+CVAR_API int cvar_gemm(const cvar_gemm_args* args, void* stream);
+
+/* ---- QKV projection fused with the KV-cache append: basic_var.py:92-108 ------------------------------------
+ * qkv = A[M,C] @ Wqkv[3C,C]^T + [q_bias, k_bias, v_bias];  M = R*l, row m = r*l + t.
+ * q  -> q_out[r, h, t, :]                    (R, H, l, 64)
+ * k,v-> k_cache/v_cache[r, h, L_prev + t, :] (R, H, T_max, 64): in-place replacement of the torch.cat growth.
+ * cos_attn != 0 (depth 30, basic_var.py:99-104): q = normalize(q) * exp(min(scale_mul[h], ln 100)), k = normalize(k). */
+CVAR_API int cvar_qkv_project(const float* A, const float* Wqkv, const float* q_bias, const float* k_bias, const float* v_bias,
+                     float* q_out, float* k_cache, float* v_cache,
+                     int R, int l, int L_prev, int T_max, int H, int cos_attn, const float* scale_mul_H,
+                     void* stream);
+
+/* ---- KV-cached attention: F.scaled_dot_product_attention at basic_var.py:117 --------------------------------
+ * out[r, t, h*64:(h+1)*64] = softmax(q[r,h,t,:] . K[r,h,0:L,:]^T * scale) @ V[r,h,0:L,:]
+ * q (R,H,l,64); caches (R,H,T_max,64); out (R,l,H*64) - the layout proj consumes.  No mask: the cache holds exactly
+ * the keys of scales <= current, which is the block-causal pattern of control_var.py:168. */
+CVAR_API int cvar_attn_kvcache(const float* q, const float* k_cache, const float* v_cache, float* out,
+                      int R, int H, int l, int L, int T_max, float scale, void* stream);
+
+/* ---- CFG + top-k/top-p + multinomial(1): control_var.py:501-505, helpers.py:6-19 -----------------------------
+ * logits (2B, l, V): rows [0,B) conditional, [B,2B) unconditional.  v = (1+t)*lc - t*lu; top-k keeps v >= k-th
+ * largest (ties kept); top-p removes the ascending-sorted prefix whose softmax mass is <= 1-top_p (the largest is
+ * always kept); idx = argmax(softmax(v) / q_noise) - the ATen multinomial(num_samples=1) rule.  q_noise (B*l, V) is
+ * Exp(1) noise supplied by the caller's generator.  V must be 4096.  idx_out (B, l) int64.  t and top_p are doubles
+ * because the reference forms (1+t) and (1-top_p) in Python double precision before they meet the fp32 tensors. */
+CVAR_API int cvar_cfg_sample(const float* logits, const float* q_noise, int64_t* idx_out,
+                    int B, int l, int V, double t, int top_k, double top_p, void* stream);
+
+/* ---- multi-scale VQ step: control_var.py:512-560 + quant.py:243-270 ------------------------------------------
+ * For sample b and stream s in {0: control, 1: image}:
+ *   h  = embedding[idx[b, s*pn*pn + i], :] as a (32, pn, pn) map                      (control_var.py:512-524)
+ *   hu = bicubic(h -> hw x hw) = U h U^T   (identity at the last scale)               (quant.py:254)
+ *   f_hat[b, :, s*hw:(s+1)*hw, :] += 0.5*hu + 0.5*(conv3x3(hu; phi_w, phi_b))         (quant.py:269-270, 255)
+ *   nxt = area(f_hat_s -> pn_next x pn_next)  (adaptive average pooling bins)         (quant.py:256)
+ *   x_next[b (and B+b), s*pn_next^2 + j, :] = word_embed(nxt[:, j]) + lvl_pos_next[s*pn_next^2 + j, :]   (control_var.py:555-560)
+ * U (hw x pn) is the 1-D interpolation matrix of F.interpolate(mode='bicubic', align_corners=False); f_hat is (B, 32, 2*hw, hw) NCHW as in the reference.  pn_next == 0 marks the last scale (no x_next). */
+CVAR_API int cvar_vq_step(const int64_t* idx, const float* embedding, const float* U, const float* phi_w, const float* phi_b,
+                 const float* word_w, const float* word_b, const float* lvl_pos_next,
+                 float* f_hat, float* x_next, int B, int pn, int pn_next, int hw, int Cvae, int C, void* stream);
+
+/* L2 nearest code: quant.py:203-206.  idx[n] = argmin_v (|z_n|^2 + |e_v|^2 - 2 z_n.e_v), first index on ties. */
+CVAR_API int cvar_vq_nearest(const float* z_NC, const float* embedding, int64_t* idx_out, int N, int Cvae, int V, void* stream);
+
+/* ---- VQVAE decoder: vae_modules.py:18-28,57-60,73-92,210-226; vqvae.py:88-89 ---------------------------------
+ * Activations are NHWC inside the library. */
+/* (B,C,H,W) -> (B,H,W,C) */
+CVAR_API int cvar_nchw_to_nhwc(const float* in, float* out, int B, int C, int H, int W,
+                      long long in_batch_stride, void* stream);
+/* GroupNorm statistics folded with the affine: a[n,c] = rstd[n,g]*gamma[c], b[n,c] = beta[c] - mean[n,g]*a[n,c],
+ * so GroupNorm(x)[n,:,:,c] = x*a + b.  scratch: 2*B*groups*chunks doubles (chunks = cvar_gn_chunks(HW)). */
+CVAR_API int cvar_gn_chunks(int HW);
+CVAR_API int cvar_gn_stats(const float* x_nhwc, const float* gamma, const float* beta, float* a_out, float* b_out,
+                  double* scratch, int B, int HW, int C, int groups, float eps, void* stream);
+/* conv2d, stride 1, 'same' padding, ks in {1,3}; x (B,Hin,Win,Cin) NHWC; w repacked (Cout, ks*ks*Cin) tap-major
+ * (cvar_repack_conv_weight); optional fused input transform in = [silu](x*a[n,c] + b[n,c]) (GroupNorm [+SiLU]);
+ * upsample2x != 0 applies nearest x2 to the input first (Upsample2x, vae_modules.py:27-28), output is
+ * (B, Hout, Wout, Cout) with Hout = Hin * (upsample2x ? 2 : 1); resid (same shape as out) is added when not NULL.
+ * out_mode 0: NHWC fp32.  out_mode 1: final image - clamp(-1,1), (v+1)*0.5, written NCHW into
+ * out[n, c, row_offset + y, x] of a (B, Cout, out_rows_total, Wout) tensor   (vqvae.py:89, control_var.py:563-565).
+ * out_mode 2: as 1 without the (v+1)*0.5 step (plain VQVAE.fhat_to_img). */
+typedef struct {
+  const float* x; const float* w; const float* bias; float* out;
+  const float* in_a; const float* in_b; int in_silu;
+  const float* resid;
+  int B, Hin, Win, Cin, Cout, ks, upsample2x;
+  int out_mode, out_rows_total, row_offset;
+} cvar_conv_args;
+CVAR_API int cvar_conv2d(const cvar_conv_args* args, void* stream);
+/* (Cout,Cin,ks,ks) -> (Cout, ks*ks*Cin), k index = (ky*ks+kx)*Cin + ci */
+CVAR_API int cvar_repack_conv_weight(const float* w_oihw, float* w_out, int Cout, int Cin, int ks, void* stream);
+/* y = x*a[n,c] + b[n,c] (GroupNorm without activation, AttnBlock.norm) */
+CVAR_API int cvar_affine_nc(const float* x_nhwc, const float* a, const float* b, float* y, int B, int HW, int C, int silu,
+                   void* stream);
+/* in-place row softmax of a (rows, cols) matrix (AttnBlock, vae_modules.py:84) */
+CVAR_API int cvar_softmax_rows(float* x, int rows, int cols, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CVAR_H_ */

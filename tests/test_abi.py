@@ -1,0 +1,73 @@
+"""CPU: the C-ABI library loads and exports every symbol include/cvar.h declares (no compute calls)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "cvar.h")
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    return sorted(set(re.findall(r"CVAR_API\s+[\w\s\*]+?\b(cvar_\w+)\s*\(", src)))
+
+
+def test_header_declares_the_path():
+    syms = declared_symbols()
+    for needed in ("cvar_attn_kvcache", "cvar_qkv_project", "cvar_gemm", "cvar_ln_modulate", "cvar_cfg_sample",
+                   "cvar_vq_step", "cvar_vq_nearest", "cvar_conv2d", "cvar_gn_stats"):
+        assert needed in syms
+
+
+def test_library_exports_every_declared_symbol():
+    from controlvar_b200 import _lib
+    assert os.path.exists(_lib.LIB_PATH), "build the extension first (__graft_entry__.build())"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for s in declared_symbols():
+        assert hasattr(lib, s), f"{s} declared in cvar.h but not exported"
+    assert set(_lib.PROTOTYPES) == set(declared_symbols()), "ctypes prototypes out of sync with cvar.h"
+    loaded = _lib.load()
+    assert loaded.cvar_abi_version() == 1
+    assert loaded.cvar_launch_count() == 0 or loaded.cvar_launch_count() > 0
+
+
+def test_product_path_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "controlvar_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "oracle" not in src.replace("the CPU oracle", "").replace("CPU-oracle", ""), fn
+
+
+def test_no_cpu_fallback():
+    import torch
+    from controlvar_b200 import VQVAE, build_control_var
+    pn = (1, 2)
+    vae = VQVAE(ch=160, v_patch_nums=pn)
+    var = build_control_var(vae, depth=1, patch_nums=pn, mask_type="interleave_append", multi_cond=True)
+    with pytest.raises(RuntimeError):
+        var.autoregressive_infer_cfg(1, torch.tensor([1]), g_seed=0, cond_type=torch.tensor([1]))
+    with pytest.raises(RuntimeError):
+        vae.fhat_to_img(torch.zeros(1, 32, 2, 2))
+
+
+def test_state_dict_contract():
+    from controlvar_b200 import VQVAE, build_control_var, weights as W
+    from controlvar_b200.config import PathConfig
+    pn = (1, 2, 3)
+    for depth in (2, 30):
+        cfg = PathConfig(depth=depth, patch_nums=pn, embed_dim=128 if depth == 30 else 0, heads=2 if depth == 30 else 0)
+        vae = VQVAE(ch=160, v_patch_nums=pn)
+        if depth == 30:
+            from controlvar_b200 import ControlVAR
+            var = ControlVAR(vae, depth=30, embed_dim=128, num_heads=2, patch_nums=pn, multi_cond=True, indep=False)
+        else:
+            var = build_control_var(vae, depth=depth, patch_nums=pn, mask_type="interleave_append", multi_cond=True)
+        sd = W.synthetic_var_state_dict(cfg, 0)
+        var.load_state_dict(sd, strict=True)
+        assert list(var.state_dict().keys()) == list(sd.keys())
+    vsd = W.synthetic_vae_state_dict(cfg, 0)
+    vae.load_state_dict(vsd, strict=True)
+    assert list(vae.state_dict().keys()) == list(vsd.keys())

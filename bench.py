@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""bench.py - images/sec of ControlVAR next-scale sampling (BASELINE.json metric) on N B200s of one node.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload d24_b64|d12_b16|...]
+
+A "step" = one ControlVAR.autoregressive_infer_cfg call over one synthetic batch: prologue, 10-scale KV-cached
+transformer loop, CFG + top-k/top-p sampling, VQ steps and BOTH decoder passes (control map + image).
+  value  - whole-job images/s with labels / condition types already resident in HBM, result left in HBM;
+  e2e    - same call through the public API with HOST buffers: pinned-host -> device copy of labels / condition types and
+           device -> host copy of the (B,3,512,256) fp32 images inside the timed region;
+  roofline - dominant kernel class of the step (CUDA events around every launch of that class, same timed region);
+  cpu_baseline - the CPU oracle port (oracle/controlvar_oracle.py; the reference is a Python package and does not
+           exist on the GPU box) timed on this box's host cores on a bounded sample of the same workload.
+--impl reference times that CPU port alone (the reference's own fp32 PyTorch path, restated) on all host threads.
+Multi-GPU: one process per GPU (torchrun), batch sharded with B per GPU fixed (weak scaling), ONE NCCL broadcast of
+the weight arena before timing, no collective inside the sampling loop; time = max over ranks.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[2]: the configuration the metric is quoted on (d24, 256x256, CFG 1.5, canny), fits one GPU
+    "d24_b64": dict(depth=24, B=64, cond=1, cfg=1.5, desc="d24 ControlVAR 256x256 10-scale, batch 64/GPU, CFG=1.5, canny condition"),
+    # BASELINE.json configs[1]
+    "d12_b16": dict(depth=12, B=16, cond=0, cfg=1.5, desc="d12 ControlVAR 256x256 10-scale, batch 16/GPU, CFG=1.5, mask condition"),
+    # BASELINE.json configs[4] per-GPU shard (cosine attention)
+    "d30_b32": dict(depth=30, B=32, cond=2, cfg=1.5, desc="d30 ControlVAR 256x256 10-scale, batch 32/GPU, CFG=1.5, depth condition"),
+    "d24_b8": dict(depth=24, B=8, cond=1, cfg=1.5, desc="d24 ControlVAR 256x256 10-scale, batch 8/GPU (small-batch probe)"),
+}
+TOP_K, TOP_P = 900, 0.96          # reference validate() defaults, train_control_var_hpu.py:338
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    src="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.path = gpu_index, None, f"/tmp/cvar_clocks_{os.getpid()}.csv"
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])), smax.append(float(f[2])), power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = [s for s, p in zip(sm, power) if p > 0.5 * max(power)] or sm
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(smax), "power_w_max": max(power),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def work_per_image(depth):
+    """Algorithmic FLOP per generated sample, for the config block."""
+    C, T = 64 * depth, 1360
+    lens = [2 * p * p for p in (1, 2, 3, 4, 5, 6, 8, 10, 13, 16)]
+    sum_lL, L = 0, 0
+    for l in lens:
+        L += l
+        sum_lL += l * L
+    linear = 2 * depth * 24 * C * C * T
+    attn = 2 * depth * 4 * sum_lL * C
+    head = 2 * T * 2 * C * 4096
+    return dict(linear_tflop=linear / 1e12, attn_tflop=attn / 1e12, head_tflop=head / 1e12, decoder_tflop=0.786)
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def run_cpu_port(depth, B_sample, cond, cfg_scale, steps, warmup, threads=None):
+    """Times the CPU oracle port (fp32 PyTorch ops == what the reference executes on CPU) on B_sample images."""
+    import torch
+    from controlvar_b200.config import PathConfig
+    from controlvar_b200 import weights as W
+    from oracle import controlvar_oracle as O
+    if threads:
+        torch.set_num_threads(threads)
+    cfgp = PathConfig(depth=depth)
+    dev = "cuda" if torch.cuda.is_available() else None       # weight generation only (bit-identical on any device)
+    sd = {k: v.cpu() for k, v in W.synthetic_var_state_dict(cfgp, 0, device=dev).items()}
+    vsd = {k: v.cpu() for k, v in W.synthetic_vae_state_dict(cfgp, 0, with_encoder=False, device=dev).items()}
+    label = torch.arange(B_sample) % 1000
+    ct = torch.full((B_sample,), cond)
+    # page in MKL / oneDNN / the thread pool on a tiny problem so the first timed step is not a cold start
+    tiny = PathConfig(depth=2, patch_nums=(1, 2))
+    O.autoregressive_infer_cfg(W.synthetic_var_state_dict(tiny, 0), W.synthetic_vae_state_dict(tiny, 0, False),
+                               tiny.patch_nums, 2, 1, label[:1], ct[:1], cfg_scale, TOP_K, TOP_P,
+                               O.cpu_generator_noise(0), decode=True)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        O.autoregressive_infer_cfg(sd, vsd, cfgp.patch_nums, depth, B_sample, label, ct, cfg_scale, TOP_K, TOP_P,
+                                   O.cpu_generator_noise(it), decode=True)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    return times, torch.get_num_threads()
+
+
+def main_reference(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    B_s = args.cpu_sample_batch
+    times, cores = run_cpu_port(wl["depth"], B_s, wl["cond"], wl["cfg"], args.steps, min(args.warmup, 1))
+    ms = 1e3 * sum(times) / len(times)
+    v = B_s / (ms / 1e3)
+    sample = f"{B_s} image(s) per step of the same workload ({wl['desc']}); CPU throughput is flat in batch size"
+    line = {"impl": "reference", "metric": "images/sec (256x256, d24, CFG=1.5)" if wl["depth"] == 24 else f"images/sec (256x256, d{wl['depth']}, CFG=1.5)",
+            "value": v, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1),
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": args.workload, "desc": wl["desc"], "top_k": TOP_K, "top_p": TOP_P},
+            "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------- our arm
+def main_ours(args, wl):
+    import torch
+    import torch.distributed as dist
+    from controlvar_b200 import VQVAE, build_control_var, ops, weights as W
+    from controlvar_b200.config import PathConfig
+    from controlvar_b200 import shard
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ops.set_gemm_engine(args.engine)
+
+    depth, B = wl["depth"], (args.batch or wl["B"])
+    cfgp = PathConfig(depth=depth)
+    vae = VQVAE(ch=160).to(dev)
+    var = build_control_var(vae, depth=depth, mask_type="interleave_append", multi_cond=True).to(dev)
+    if rank == 0:     # rank 0 materialises the synthetic weights, everyone else receives them over NVLink
+        var.load_state_dict(W.synthetic_var_state_dict(cfgp, 0, device=dev))
+        vae.load_state_dict(W.synthetic_vae_state_dict(cfgp, 0, device=dev))
+    arena = shard.pack_parameters([var, vae])
+    t_b0 = time.perf_counter()
+    shard.broadcast_weights(arena, src=0)
+    torch.cuda.synchronize()
+    bcast_ms = (time.perf_counter() - t_b0) * 1e3
+
+    label_h = (torch.arange(B) + rank * B) % 1000
+    ct_h = torch.full((B,), wl["cond"], dtype=torch.long)
+    label_d, ct_d = label_h.to(dev), ct_h.to(dev)
+    label_pin, ct_pin = label_h.pin_memory(), ct_h.pin_memory()
+    img_host = torch.empty(B, 3, 512, 256, dtype=torch.float32).pin_memory()
+    kw = dict(cfg=wl["cfg"], top_k=TOP_K, top_p=TOP_P)
+
+    def step_device(it):
+        return var.autoregressive_infer_cfg(B, label_d, g_seed=it * world + rank, cond_type=ct_d, **kw)
+
+    def step_e2e(it):
+        lab = label_pin.to(dev, non_blocking=True)
+        ct = ct_pin.to(dev, non_blocking=True)
+        img = var.autoregressive_infer_cfg(B, lab, g_seed=it * world + rank, cond_type=ct, **kw)
+        img_host.copy_(img, non_blocking=True)
+        return img
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, first_it, profile=False):
+        barrier()
+        if profile:
+            ops.profile_begin()
+        n0 = ops.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(first_it + i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = ops.launch_count() - n0
+        prof = ops.profile_end() if profile else None
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms, launches, prof
+
+    for w in range(args.warmup):
+        step_device(w)
+    torch.cuda.synchronize()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ms_total, launches, prof = timed(step_device, args.steps, 1000, profile=True)
+    ms_e2e, _, _ = timed(step_e2e, args.steps, 2000)
+    clk = clocks.stop() if rank == 0 else None
+    mem_gb = torch.cuda.max_memory_allocated() / 2**30
+
+    if rank == 0:
+        pk = peaks()
+        ms_step = ms_total / args.steps
+        value = world * B / (ms_step / 1e3)
+        e2e_v = world * B / (ms_e2e / args.steps / 1e3)
+        # dominant kernel class by device time inside the timed region
+        classes = {k: v for k, v in prof.items() if k in ("gemm", "conv", "attn")}
+        dom = max(classes, key=lambda k: classes[k]["ms"])
+        d = classes[dom]
+        ach_tf = d["work"] / (d["ms"] / 1e3) / 1e12
+        roof = {"kernel": {"gemm": "dense-layer GEMM (cvar_gemm / cvar_qkv_project)", "conv": "decoder implicit-GEMM conv (cvar_conv2d)",
+                           "attn": "KV-cached attention (cvar_attn_kvcache)"}[dom],
+                "bound": "tensor", "achieved": ach_tf, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": ach_tf / pk["tf_sust"],
+                "traffic": None, "peak_source": pk["src"] + ", sustained bf16 (kernel timed inside a long step)",
+                "launches": d["launches"], "avg_launch_ms": d["ms"] / d["launches"],
+                "share_of_step": d["ms"] / ms_total}
+        kernels = {}
+        for k, v in prof.items():
+            e = {"launches": v["launches"], "ms_per_step": v["ms"] / args.steps, "share_of_step": v["ms"] / ms_total}
+            if v["work"] > 0:
+                e["tflops"] = v["work"] / (v["ms"] / 1e3) / 1e12
+                e["frac_of_bf16_sustained"] = e["tflops"] / pk["tf_sust"]
+            if v["bytes"] > 0:
+                e["algorithmic_gbs"] = v["bytes"] / (v["ms"] / 1e3) / 1e9
+                e["frac_of_hbm"] = e["algorithmic_gbs"] / pk["hbm"]
+            kernels[k] = e
+        cpu = None
+        if not args.no_cpu_baseline:
+            times, cores = run_cpu_port(depth, args.cpu_sample_batch, wl["cond"], wl["cfg"], 1, 0)
+            cpu = {"value": args.cpu_sample_batch / times[0], "unit": "images/s", "cores": cores, "kind": "port",
+                   "sample": f"{args.cpu_sample_batch} image(s), one call of the same workload on the host cores (CPU throughput is flat in batch)"}
+        engine_name = {0: "simt-fp32", 1: "tcgen05-3xtf32", 2: "tcgen05-bf16"}[ops.get_gemm_engine()]
+        line = {"metric": f"images/sec (256x256, d{depth}, CFG=1.5)", "value": value, "unit": "images/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": args.workload, "desc": wl["desc"], "batch_per_gpu": B, "global_batch": world * B,
+                           "top_k": TOP_K, "top_p": TOP_P, "gemm_engine": engine_name,
+                           "l2": "working set >> L2: weights %.1f GB + KV arena %.1f GB streamed every step" % (
+                               arena.numel() * 4 / 1e9, 2 * depth * 2 * B * 1360 * 64 * depth * 4 / 1e9),
+                           "parallelism": f"dp{world} (batch sharded, one NCCL weight broadcast: {bcast_ms:.1f} ms)",
+                           "algorithmic_tflop_per_image": work_per_image(depth), "peak_mem_gib": round(mem_gb, 1)},
+                "e2e": {"value": e2e_v, "unit": "images/s", "h2d_bytes_per_step": int(16 * B * world),
+                        "d2h_bytes_per_step": int(B * 3 * 512 * 256 * 4 * world)},
+                "gpu_launches": launches, "roofline": roof, "kernels": kernels, "cpu_baseline": cpu, "clocks": clk}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="d24_b64", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch of the workload")
+    ap.add_argument("--engine", type=int, default=int(os.environ.get("CVAR_GEMM_ENGINE", "0")),
+                    help="0 simt fp32, 1 tcgen05 3xTF32, 2 tcgen05 bf16")
+    ap.add_argument("--cpu-sample-batch", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        main_reference(args, wl)
+    else:
+        main_ours(args, wl)

@@ -14,9 +14,11 @@ extern "C" int cvar_gemm(const cvar_gemm_args* a, void* stream) {
   CVAR_REQUIRE(a != nullptr, "cvar_gemm: null args");
   CVAR_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0 && a->batch > 0, "cvar_gemm: bad shape M=%d N=%d K=%d", a->M, a->N,
                a->K);
-  CVAR_REQUIRE(a->K % 4 == 0 && a->lda % 4 == 0 && a->ldw % 4 == 0, "cvar_gemm: K, lda, ldw must be multiples of 4");
-  CVAR_REQUIRE((((uintptr_t)a->A) & 15) == 0 && (((uintptr_t)a->W) & 15) == 0, "cvar_gemm: operands must be 16B aligned");
-  CVAR_REQUIRE(!a->w_is_kn || a->N % 4 == 0, "cvar_gemm: [K,N] weights need N %% 4 == 0");
+  // 128-bit operand loads need 16-byte aligned rows; ragged problems (the 3x3 / 5x5 decoder attention of truncated
+  // pyramids) take the scalar-load variant of the same kernel
+  const int a_vec = (a->K % 4 == 0) && (a->lda % 4 == 0) && (a->strideA % 4 == 0) && ((((uintptr_t)a->A) & 15) == 0);
+  const int w_vec = (a->ldw % 4 == 0) && (a->strideW % 4 == 0) && ((((uintptr_t)a->W) & 15) == 0) &&
+                    (a->w_is_kn ? (a->N % 4 == 0) : (a->K % 4 == 0));
   CVAR_REQUIRE(a->epilogue != CVAR_EPI_BIAS_GAMMA_RESID || (a->gamma && a->rows_per_sample > 0),
                "cvar_gemm: gamma epilogue without gamma");
   CVAR_REQUIRE(a->epilogue != CVAR_EPI_BIAS_RESID || a->resid, "cvar_gemm: residual epilogue without resid");
@@ -26,8 +28,8 @@ extern "C" int cvar_gemm(const cvar_gemm_args* a, void* stream) {
     if (took < 0) return took;
     if (took == 1) return 0;
   }
-  DenseALoader al{a->A, a->lda, a->strideA, a->M, a->K};
-  DenseBLoader bl{a->W, a->ldw, a->strideW, a->N, a->K, a->w_is_kn};
+  DenseALoader al{a->A, a->lda, a->strideA, a->M, a->K, a_vec};
+  DenseBLoader bl{a->W, a->ldw, a->strideW, a->N, a->K, a->w_is_kn, w_vec};
   DenseEpilogue ep{a->out, a->ldo, a->strideO, a->bias, a->epilogue, a->alpha, a->gamma, a->gamma_row_stride,
                    a->rows_per_sample, a->resid, a->ldr, a->strideR};
   return launch_sgemm(al, bl, ep, (long long)a->M, a->N, a->K, a->batch, s, "cvar_gemm");
@@ -74,8 +76,8 @@ extern "C" int cvar_qkv_project(const float* A, const float* Wqkv, const float* 
     if (took < 0) return took;
   }
   if (took == 0) {
-    DenseALoader al{A, C, 0, M, C};
-    DenseBLoader bl{Wqkv, C, 0, 3 * C, C, 0};
+    DenseALoader al{A, C, 0, M, C, 1};
+    DenseBLoader bl{Wqkv, C, 0, 3 * C, C, 0, 1};
     int rc = launch_sgemm(al, bl, ep, (long long)M, 3 * C, C, 1, s, "cvar_qkv_project");
     if (rc) return rc;
   }
@@ -108,7 +110,7 @@ extern "C" int cvar_conv2d(const cvar_conv_args* a, void* stream) {
   al.x = a->x, al.in_a = a->in_a, al.in_b = a->in_b, al.in_silu = a->in_silu;
   al.Hin = a->Hin, al.Win = a->Win, al.Cin = a->Cin, al.ks = a->ks, al.up = up;
   al.Hout = Hout, al.Wout = Wout, al.Mtot = M, al.K = K;
-  DenseBLoader bl{a->w, K, 0, a->Cout, K, 0};
+  DenseBLoader bl{a->w, K, 0, a->Cout, K, 0, 1};
   ConvEpilogue ep{a->out, a->bias, a->resid, a->Cout, a->out_mode, Hout, Wout, a->out_rows_total, a->row_offset};
   return launch_sgemm(al, bl, ep, M, a->Cout, K, 1, s, "cvar_conv2d");
 }

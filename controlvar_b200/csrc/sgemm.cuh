@@ -14,14 +14,22 @@ struct DenseALoader {
   const float* A;
   long long lda, strideA;
   int M, K;
+  int vec;   // 1: K, lda multiples of 4 and 16-byte aligned base -> 128-bit loads; 0: scalar loads (ragged shapes)
   static constexpr int kMaxSlots = 4;
   const float* ptr[kMaxSlots];
   __device__ __forceinline__ void prep(int slot, long long m, int batch) {
     ptr[slot] = (m < M) ? A + (long long)batch * strideA + m * lda : nullptr;
   }
   __device__ __forceinline__ float4 fetch(int slot, int k) const {
-    if (ptr[slot] != nullptr && k < K) return ld4(ptr[slot] + k);
-    return make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* p = ptr[slot];
+    if (p == nullptr || k >= K) return v;
+    if (vec) return ld4(p + k);
+    v.x = p[k];
+    if (k + 1 < K) v.y = p[k + 1];
+    if (k + 2 < K) v.z = p[k + 2];
+    if (k + 3 < K) v.w = p[k + 3];
+    return v;
   }
 };
 
@@ -84,6 +92,7 @@ struct DenseBLoader {
   const float* W;
   long long ldw, strideW;
   int N, K, kn;
+  int vec;   // as DenseALoader::vec
 };
 
 // -------------------------------------------------------------------------------------------- epilogues
@@ -235,10 +244,30 @@ sgemm_kernel(AL al, DenseBLoader bl, EP ep, long long M, int N, int K) {
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (!bl.kn) {
         int n = n0 + (item >> 2), k = k0 + (item & 3) * 4;
-        if (n < N && k < K) v = ld4(Wb + (long long)n * bl.ldw + k);
+        if (n < N && k < K) {
+          const float* p = Wb + (long long)n * bl.ldw + k;
+          if (bl.vec) {
+            v = ld4(p);
+          } else {
+            v.x = p[0];
+            if (k + 1 < K) v.y = p[1];
+            if (k + 2 < K) v.z = p[2];
+            if (k + 3 < K) v.w = p[3];
+          }
+        }
       } else {
         int k = k0 + item / (BN / 4), n = n0 + (item % (BN / 4)) * 4;
-        if (k < K && n < N) v = ld4(Wb + (long long)k * bl.ldw + n);
+        if (k < K && n < N) {
+          const float* p = Wb + (long long)k * bl.ldw + n;
+          if (bl.vec) {
+            v = ld4(p);
+          } else {
+            v.x = p[0];
+            if (n + 1 < N) v.y = p[1];
+            if (n + 2 < N) v.z = p[2];
+            if (n + 3 < N) v.w = p[3];
+          }
+        }
       }
       rb[s] = v;
     }

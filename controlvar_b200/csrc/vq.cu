@@ -50,7 +50,8 @@ __global__ void __launch_bounds__(256) vq_step_kernel(const int64_t* __restrict_
     int tap = r % 9, ci = r / 9;
     w_s[i] = phi_w[(co * CV + ci) * 9 + tap];
   }
-  for (int i = tid; i < hw * pn; i += 256) U_s[i] = U[i];
+  if (pn != hw)
+    for (int i = tid; i < hw * pn; i += 256) U_s[i] = U[i];
   for (int i = tid; i < CV * hp * hp; i += 256) hu_s[i] = 0.f;
   const int64_t* ib = idx + (long long)b * (2 * npix) + s * npix;
   for (int i = tid; i < CV * npix; i += 256) {

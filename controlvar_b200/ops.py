@@ -32,6 +32,48 @@ def _chk(*ts):
             raise _lib.CvarError(f"unsupported dtype {t.dtype}")
 
 
+# ---- optional per-kernel-class timing with CUDA events on the launching stream (bench.py's roofline object) -------
+_prof = None
+
+
+def profile_begin():
+    global _prof
+    _prof = []
+
+
+def profile_end():
+    """-> {tag: dict(launches, work, bytes, ms)}; call after torch.cuda.synchronize()."""
+    global _prof
+    rec, _prof = _prof, None
+    out = {}
+    for tag, work, nbytes, e0, e1 in rec or []:
+        d = out.setdefault(tag, dict(launches=0, work=0.0, bytes=0.0, ms=0.0))
+        d["launches"] += 1
+        d["work"] += work
+        d["bytes"] += nbytes
+        d["ms"] += e0.elapsed_time(e1)
+    return out
+
+
+class _Timed:
+    __slots__ = ("tag", "work", "nbytes", "e0")
+
+    def __init__(self, tag, work, nbytes=0.0):
+        self.tag, self.work, self.nbytes = tag, work, nbytes
+
+    def __enter__(self):
+        if _prof is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *exc):
+        if _prof is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            _prof.append((self.tag, self.work, self.nbytes, self.e0, e1))
+        return False
+
+
 def launch_count() -> int:
     return int(_lib.load().cvar_launch_count())
 
@@ -80,29 +122,35 @@ def gemm(A, W, bias, out, M, N, K, *, lda=None, ldw=None, ldo=None, epilogue=EPI
     a.epilogue, a.alpha = epilogue, float(alpha)
     a.gamma, a.gamma_row_stride, a.rows_per_sample = _p(gamma), gamma_row_stride, rows_per_sample
     a.resid, a.ldr, a.strideR = _p(resid), (N if ldr is None else ldr), strideR
-    check(_lib.load().cvar_gemm(C.byref(a), _stream()), "cvar_gemm")
+    with _Timed("gemm", 2.0 * M * N * K * batch, 4.0 * batch * (M * K + N * K + M * N)):
+        check(_lib.load().cvar_gemm(C.byref(a), _stream()), "cvar_gemm")
     return out
 
 
 def qkv_project(A, Wqkv, q_bias, k_bias, v_bias, q_out, k_cache, v_cache, R, l, L_prev, T_max, H, cos_attn,
                 scale_mul_H):
     _chk(A, Wqkv, q_bias, k_bias, v_bias, q_out, k_cache, v_cache, scale_mul_H)
-    check(_lib.load().cvar_qkv_project(_p(A), _p(Wqkv), _p(q_bias), _p(k_bias), _p(v_bias), _p(q_out), _p(k_cache),
-                                       _p(v_cache), R, l, L_prev, T_max, H, int(cos_attn), _p(scale_mul_H),
-                                       _stream()), "cvar_qkv_project")
+    Cd = H * 64
+    with _Timed("gemm", 2.0 * R * l * 3 * Cd * Cd, 4.0 * (R * l * Cd + 3 * Cd * Cd + R * l * 3 * Cd)):
+        check(_lib.load().cvar_qkv_project(_p(A), _p(Wqkv), _p(q_bias), _p(k_bias), _p(v_bias), _p(q_out), _p(k_cache),
+                                           _p(v_cache), R, l, L_prev, T_max, H, int(cos_attn), _p(scale_mul_H),
+                                           _stream()), "cvar_qkv_project")
 
 
 def attn_kvcache(q, k_cache, v_cache, out, R, H, l, L, T_max, scale):
     _chk(q, k_cache, v_cache, out)
-    check(_lib.load().cvar_attn_kvcache(_p(q), _p(k_cache), _p(v_cache), _p(out), R, H, l, L, T_max, float(scale),
-                                        _stream()), "cvar_attn_kvcache")
+    # algorithmic work of SURVEY.md section 8d: 4*l*L*64 flop and (2l + 2L)*64*4 bytes per (row, head)
+    with _Timed("attn", 4.0 * l * L * 64 * R * H, (2.0 * l + 2.0 * L) * 64 * 4 * R * H):
+        check(_lib.load().cvar_attn_kvcache(_p(q), _p(k_cache), _p(v_cache), _p(out), R, H, l, L, T_max, float(scale),
+                                            _stream()), "cvar_attn_kvcache")
     return out
 
 
 def cfg_sample(logits, q_noise, idx_out, B, l, V, t, top_k, top_p):
     _chk(logits, q_noise, idx_out)
-    check(_lib.load().cvar_cfg_sample(_p(logits), _p(q_noise), _p(idx_out), B, l, V, float(t), int(top_k),
-                                      float(top_p), _stream()), "cvar_cfg_sample")
+    with _Timed("sample", 0.0, 4.0 * B * l * V * 3 + 8.0 * B * l):
+        check(_lib.load().cvar_cfg_sample(_p(logits), _p(q_noise), _p(idx_out), B, l, V, float(t), int(top_k),
+                                          float(top_p), _stream()), "cvar_cfg_sample")
     return idx_out
 
 
@@ -147,7 +195,10 @@ def conv2d(x, w_packed, bias, out, B, Hin, Win, Cin, Cout, ks, *, in_a=None, in_
     a.resid = _p(resid)
     a.B, a.Hin, a.Win, a.Cin, a.Cout, a.ks, a.upsample2x = B, Hin, Win, Cin, Cout, ks, int(upsample2x)
     a.out_mode, a.out_rows_total, a.row_offset = out_mode, out_rows_total, row_offset
-    check(_lib.load().cvar_conv2d(C.byref(a), _stream()), "cvar_conv2d")
+    up = 2 if upsample2x else 1
+    Mo = B * Hin * up * Win * up
+    with _Timed("conv", 2.0 * Mo * Cout * ks * ks * Cin, 4.0 * (B * Hin * Win * Cin + Mo * Cout + Cout * ks * ks * Cin)):
+        check(_lib.load().cvar_conv2d(C.byref(a), _stream()), "cvar_conv2d")
     return out
 
 

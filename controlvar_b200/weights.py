@@ -35,9 +35,9 @@ _C2 = _s64(0xBF58476D1CE4E5B9)
 _C3 = _s64(0x94D049BB133111EB)
 
 
-def hash_uniform(n: int, seed: int, stream: int) -> torch.Tensor:
-    """n float32 values in [-1, 1), bit-identical on every host (int64 wrap-around arithmetic only)."""
-    i = torch.arange(n, dtype=torch.int64)
+def hash_uniform(n: int, seed: int, stream: int, device=None) -> torch.Tensor:
+    """n float32 values in [-1, 1), bit-identical on every host and device (int64 wrap-around arithmetic only)."""
+    i = torch.arange(n, dtype=torch.int64, device=device)
     z = i * _C1 + _s64((seed * 0x632BE59BD9B4E019 + stream * 0xD1342543DE82EF95) & _M64)
     z = (z ^ ((z >> 30) & ((1 << 34) - 1))) * _C2     # logical shifts (int64 '>>' is arithmetic)
     z = (z ^ ((z >> 27) & ((1 << 37) - 1))) * _C3
@@ -47,11 +47,14 @@ def hash_uniform(n: int, seed: int, stream: int) -> torch.Tensor:
     return u * 2.0 - 1.0                            # exact
 
 
+_DEVICE = None   # set by synthetic_*_state_dict(device=...) for the duration of one call
+
+
 def _fill(shape, bound, seed, key, center=0.0):
     n = 1
     for s in shape:
         n *= s
-    t = hash_uniform(n, seed, zlib.crc32(key.encode())) * float(bound)
+    t = hash_uniform(n, seed, zlib.crc32(key.encode()), _DEVICE) * float(bound)
     if center != 0.0:
         t = t + float(center)
     return t.reshape(shape).contiguous()
@@ -223,19 +226,28 @@ def attn_bias_for_masking(cfg: PathConfig) -> torch.Tensor:
 
 
 # -------------------------------------------------------------------------------- synthetic generators
-def synthetic_var_state_dict(cfg: PathConfig, seed: int = 0) -> Dict[str, torch.Tensor]:
+def synthetic_var_state_dict(cfg: PathConfig, seed: int = 0, device=None) -> Dict[str, torch.Tensor]:
+    global _DEVICE
+    _DEVICE = device
+    try:
+        return _synthetic_var_state_dict(cfg, seed)
+    finally:
+        _DEVICE = None
+
+
+def _synthetic_var_state_dict(cfg: PathConfig, seed: int) -> Dict[str, torch.Tensor]:
     C = cfg.C
     sd: Dict[str, torch.Tensor] = OrderedDict()
     emb_bound = 1.0 / math.sqrt(C)      # uniform with std sqrt(1/C/3), cf. control_var.py:77
     for key, shape in var_key_shapes(cfg).items():
         if key == "lvl_1L":
-            sd[key] = lvl_1L(cfg)
+            sd[key] = lvl_1L(cfg).to(_DEVICE) if _DEVICE else lvl_1L(cfg)
         elif key == "attn_bias_for_masking":
-            sd[key] = attn_bias_for_masking(cfg)
+            sd[key] = attn_bias_for_masking(cfg).to(_DEVICE) if _DEVICE else attn_bias_for_masking(cfg)
         elif key in ("pos_start", "pos_1LC", "class_emb.weight", "lvl_embed.weight", "cond_embed.weight"):
             sd[key] = _fill(shape, emb_bound, seed, key)
         elif key.endswith("zero_k_bias"):
-            sd[key] = torch.zeros(shape)
+            sd[key] = torch.zeros(shape, device=_DEVICE)
         elif key.endswith("q_bias") or key.endswith("v_bias"):
             sd[key] = _fill(shape, 0.1, seed, key)          # zeros at init; trained checkpoints carry values
         elif key.endswith("scale_mul_1H11"):
@@ -250,12 +262,21 @@ def synthetic_var_state_dict(cfg: PathConfig, seed: int = 0) -> Dict[str, torch.
     return sd
 
 
-def synthetic_vae_state_dict(cfg: PathConfig, seed: int = 0, with_encoder: bool = True) -> Dict[str, torch.Tensor]:
+def synthetic_vae_state_dict(cfg: PathConfig, seed: int = 0, with_encoder: bool = True, device=None) -> Dict[str, torch.Tensor]:
+    global _DEVICE
+    _DEVICE = device
+    try:
+        return _synthetic_vae_state_dict(cfg, seed, with_encoder)
+    finally:
+        _DEVICE = None
+
+
+def _synthetic_vae_state_dict(cfg: PathConfig, seed: int, with_encoder: bool) -> Dict[str, torch.Tensor]:
     shapes = vae_key_shapes(cfg, with_encoder)
     sd: Dict[str, torch.Tensor] = OrderedDict()
     for key, shape in shapes.items():
         if key == "quantize.ema_vocab_hit_SV":
-            sd[key] = torch.zeros(shape)
+            sd[key] = torch.zeros(shape, device=_DEVICE)
         elif key == "quantize.embedding.weight":
             sd[key] = _fill(shape, math.sqrt(3.0), seed, key)                   # unit variance like N(0,1)
         elif ".norm" in key or "norm_out" in key:

@@ -301,3 +301,20 @@ def test_fhat_to_img_matches_oracle_decoder():
     got = vae.fhat_to_img(g(f_hat)[:, :, 16:, :])
     assert got.shape == ref.shape == (1, 3, 256, 256)
     assert (got.cpu() - ref).abs().max().item() < 1e-4
+
+
+def test_gemm_ragged_scalar_path():
+    """K / ld not multiples of 4 (decoder attention of truncated pyramids: 3x3 -> HW = 9, 5x5 -> HW = 25)."""
+    torch.manual_seed(12)
+    Bn, HW, Cn = 2, 25, 64
+    qkv = torch.randn(Bn, HW, 3 * Cn)
+    qg = g(qkv)
+    S = torch.empty(Bn, HW, HW, device=DEV)
+    ops.gemm(qg, qg[:, :, Cn:], None, S, HW, HW, Cn, lda=3 * Cn, ldw=3 * Cn, ldo=HW, alpha=0.125, batch=Bn,
+             strideA=HW * 3 * Cn, strideW=HW * 3 * Cn, strideO=HW * HW)
+    S_ref = torch.bmm(qkv[..., :Cn].double(), qkv[..., Cn:2 * Cn].double().transpose(1, 2)) * 0.125
+    assert rel_err(S.cpu().double(), S_ref) < 1e-5
+    h = torch.empty(Bn, HW, Cn, device=DEV)
+    ops.gemm(S, qg[:, :, 2 * Cn:], None, h, HW, Cn, HW, lda=HW, ldw=3 * Cn, ldo=Cn, w_is_kn=True, batch=Bn,
+             strideA=HW * HW, strideW=HW * 3 * Cn, strideO=HW * Cn)
+    assert rel_err(h.cpu().double(), torch.bmm(S.cpu().double(), qkv[..., 2 * Cn:].double())) < 1e-5

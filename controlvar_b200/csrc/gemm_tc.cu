@@ -1,9 +1,484 @@
-// tcgen05 / TMEM / TMA GEMM engine (placeholder until the tensor-core engine lands: every query answers
-// "shape not taken", so the SIMT fp32 engine serves all problems).
+// tcgen05 / TMEM / TMA GEMM engine for sm_100a: out = epilogue(A[M,K] * W[N,K]^T) at fp32-class accuracy.
+//
+// Arithmetic: error-compensated 3xTF32.  Every fp32 operand x is split into hi = x with the 13 low mantissa bits
+// cleared (exactly what a TF32 tensor-core input keeps) and lo = x - hi (exact in fp32); the product is accumulated as
+//   a_lo*b_hi + a_hi*b_lo + a_hi*b_hi      (three tcgen05.mma.kind::tf32 per 8-wide k-step, fp32 accumulate in TMEM).
+// The dropped a_lo*b_lo term is below 2^-20 relative.  Reference inference is fp32, so bf16
+// operands would break token parity (section 7.2); this keeps the tensor cores AND the parity contract.
+//
+// Structure (one persistent CTA per SM, 14 warps, warp-specialised, everything handed over through mbarriers):
+//   warps 0-3   epilogue: tcgen05.ld the 128 x BN fp32 accumulator (row = TMEM lane = thread), apply the epilogue
+//               functor (bias / GELU / gamma-residual / QKV scatter into the KV cache / conv NHWC+residual / image)
+//   warps 4-7   A producers: LDG the activation tile (dense rows, or the implicit-GEMM gather of a 3x3 convolution with
+//               fused GroupNorm+SiLU and nearest-x2 upsampling), split hi/lo, store both into 128B/64B-swizzled,
+//               K-major shared-memory tiles (software swizzle = the pattern TMA / UMMA expect)
+//   warps 8-11  B converters: the weight tile arrives by TMA (cp.async.bulk.tensor, hardware swizzle); split it hi/lo
+//   warp 12     TMA issue (one elected lane)
+//   warp 13     TMEM allocation + MMA issue (one elected lane): tcgen05.mma.cta_group::1.kind::tf32, M = 128, N = BN
+// The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include <cuda.h>
+#include <mutex>
+#include <unordered_map>
 #include "sgemm.cuh"
 
 namespace cvar {
-int tc_gemm_try(const cvar_gemm_args*, cudaStream_t) { return 0; }
-int tc_qkv_try(const float*, const float*, const QkvEpilogue&, int, int, cudaStream_t) { return 0; }
-int tc_conv_try(const cvar_conv_args*, cudaStream_t) { return 0; }
+namespace tc {
+
+constexpr int BM = 128;
+constexpr int kEpiWarps = 4, kProdWarps = 4, kConvWarps = 4;
+constexpr int kThreads = (kEpiWarps + kProdWarps + kConvWarps + 2) * 32;   // 448
+constexpr int kMaxSmem = 227 * 1024;
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a trap (an error the host sees), never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 28)) {
+      printf("cvar tc_gemm: mbarrier timeout block %d thread %d\n", (int)blockIdx.x, (int)threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ---------------------------------------------------------------------------------------------- tile geometry
+// K-major operand tile of ROWS x BK fp32 in the canonical UMMA layout: rows of BK*4 bytes (128 B -> SWIZZLE_128B,
+// 64 B -> SWIZZLE_64B), 8-row swizzle atoms stacked every SBO = 8 * row bytes; the 16-byte chunk index inside a row is
+// XOR-ed with address bits [7, 7 + log2(chunks)).
+template <int BK>
+struct Geo {
+  static constexpr int kRowBytes = BK * 4;
+  static constexpr int kChunks = kRowBytes / 16;              // 8 (SW128) or 4 (SW64)
+  static constexpr uint32_t kSBO = 8 * kRowBytes;             // 1024 or 512
+  static constexpr uint64_t kLayoutType = (BK == 32) ? 2ull : 4ull;
+  __device__ __forceinline__ static uint32_t offset(int row, int chunk) {
+    int sw = (BK == 32) ? (row & 7) : ((row >> 1) & 3);
+    return (uint32_t)row * kRowBytes + (uint32_t)((chunk ^ sw) << 4);
+  }
+  __device__ __forceinline__ static uint64_t desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(kSBO >> 4) << 32) | (1ull << 46) |
+           (kLayoutType << 61);
+  }
+};
+
+template <int BN, int BK>
+struct SmemPlan {
+  static constexpr int kABytes = BM * BK * 4;
+  static constexpr int kBBytes = BN * BK * 4;
+  static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
+  static constexpr int kBarrierBytes = 1024;
+  static constexpr int kStages = (kMaxSmem - kBarrierBytes - 1024) / kStageBytes > 6
+                                     ? 6
+                                     : (kMaxSmem - kBarrierBytes - 1024) / kStageBytes;
+  static constexpr int kTotal = kStages * kStageBytes + kBarrierBytes + 1024;   // +1024: manual 1 KiB alignment
+  static_assert(kStages >= 2, "tile too large for shared memory");
+};
+
+__device__ __forceinline__ float trunc_tf32(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
+// -------------------------------------------------------------------------------------------------- the kernel
+template <int BN, int BK, class AL, class EP>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmapB, AL al, EP ep, long long M, int N, int K, int m_tiles,
+               int n_tiles) {
+  using G = Geo<BK>;
+  using P = SmemPlan<BN, BK>;
+  constexpr int S = P::kStages;
+  // TMEM plan (512 columns): every tile owns TWO fp32 accumulators - 'main' takes a_hi*b_hi, 'lo' takes the two small
+  // cross terms.  The tensor core truncates (round-toward-zero) the accumulator after every instruction, a bias that
+  // grows with the number of accumulation steps and with |accumulator|; keeping the 2^-11-sized terms out of the main
+  // accumulator cuts its steps by 3x (measured on B200: K=1536 error 1.1e-5 -> see profiles/r01_tc_accuracy.md).
+  // BN <= 128: two such pairs (epilogue of tile i overlaps MMAs of tile i+1); BN > 128: one pair.
+  constexpr int kAccStride = (BN <= 128) ? 128 : 256;      // columns between main and lo
+  constexpr int kAccBufs = (BN <= 128) ? 2 : 1;
+  constexpr int kTmemCols = 512;
+  static_assert(BN <= 256 && BN % 16 == 0 && BN >= 16, "BN");
+  constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  auto a_hi = [&](int s) { return smem + s * P::kStageBytes; };
+  auto a_lo = [&](int s) { return smem + s * P::kStageBytes + P::kABytes; };
+  auto b_hi = [&](int s) { return smem + s * P::kStageBytes + 2 * P::kABytes; };
+  auto b_lo = [&](int s) { return smem + s * P::kStageBytes + 2 * P::kABytes + P::kBBytes; };
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * P::kStageBytes);
+  uint64_t* b_full = bars;                 // [S]  TMA bytes of the weight tile landed
+  uint64_t* ab_ready = bars + S;           // [S]  hi/lo tiles of A and B written (256 arrivals)
+  uint64_t* empty = bars + 2 * S;          // [S]  MMAs reading the stage retired (tcgen05.commit)
+  uint64_t* tm_full = bars + 3 * S;        // [2]  accumulator complete
+  uint64_t* tm_empty = bars + 3 * S + 2;   // [2]  accumulator drained by the epilogue (128 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * S + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkb = K / BK;
+  const int total_tiles = m_tiles * n_tiles;
+
+  if (warp == 12 && lane == 0) {
+    tma_prefetch_desc(&tmapB);
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&b_full[s], 1);
+      mbar_init(&ab_ready[s], (kProdWarps + kConvWarps) * 32);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < kAccBufs; ++a) {
+      mbar_init(&tm_full[a], 1);
+      mbar_init(&tm_empty[a], kEpiWarps * 32);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 13) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < kEpiWarps) {
+    // ================================================================ epilogue: TMEM -> registers -> global
+    int tcount = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+      const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
+      const int acc = tcount % kAccBufs;
+      const uint32_t acc_phase = (tcount / kAccBufs) & 1;
+      mbar_wait(&tm_full[acc], acc_phase);
+      tc_fence_after();
+      const long long m = (long long)mt * BM + warp * 32 + lane;
+      const uint32_t tcol = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * 2 * kAccStride);
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        float v[32], w[32];
+        tmem_ld_32x32b_x32(tcol + (uint32_t)c, v);
+        tmem_ld_32x32b_x32(tcol + (uint32_t)(kAccStride + c), w);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] += w[i];          // main + small terms, one rounded fp32 add
+        const int nbase = nt * BN + c;
+        if (m < M) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            int n = nbase + q * 4;
+            if (n < N) ep.store(m, n, &v[q * 4], min(4, N - n), 0);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tm_empty[acc]);
+    }
+  } else if (warp < kEpiWarps + kProdWarps) {
+    // ================================================================ A producers: LDG (+gather/transform) -> hi/lo
+    constexpr int kVec = BM * BK / 4 / (kProdWarps * 32);     // float4 per thread per k-block: 8 (BK=32) or 4 (BK=16)
+    constexpr int kCh = G::kChunks;
+    const int t = threadIdx.x - kEpiWarps * 32;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int mt = tile / n_tiles;
+#pragma unroll
+      for (int i = 0; i < kVec; ++i) al.prep(i, (long long)mt * BM + (i * 128 + t) / kCh, 0);
+      float4 cur[kVec], nxt[kVec];
+#pragma unroll
+      for (int i = 0; i < kVec; ++i) cur[i] = al.fetch(i, ((i * 128 + t) % kCh) * 4);
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int s = it % S;
+        const uint32_t ph = (it / S) & 1;
+        if (kb + 1 < nkb) {
+#pragma unroll
+          for (int i = 0; i < kVec; ++i) nxt[i] = al.fetch(i, (kb + 1) * BK + ((i * 128 + t) % kCh) * 4);
+        }
+        mbar_wait(&empty[s], ph ^ 1);
+        unsigned char* hi = a_hi(s);
+        unsigned char* lo = a_lo(s);
+#pragma unroll
+        for (int i = 0; i < kVec; ++i) {
+          const int item = i * 128 + t;
+          const uint32_t off = G::offset(item / kCh, item % kCh);
+          float4 x = cur[i], h, l;
+          h.x = trunc_tf32(x.x), h.y = trunc_tf32(x.y), h.z = trunc_tf32(x.z), h.w = trunc_tf32(x.w);
+          l.x = x.x - h.x, l.y = x.y - h.y, l.z = x.z - h.z, l.w = x.w - h.w;
+          *reinterpret_cast<float4*>(hi + off) = h;
+          *reinterpret_cast<float4*>(lo + off) = l;
+        }
+        fence_proxy_async();
+        mbar_arrive(&ab_ready[s]);
+#pragma unroll
+        for (int i = 0; i < kVec; ++i) cur[i] = nxt[i];
+      }
+    }
+  } else if (warp < kEpiWarps + kProdWarps + kConvWarps) {
+    // ================================================================ B converters: TMA tile -> hi (in place) / lo
+    constexpr int kVec = BN * BK / 4 / (kConvWarps * 32);
+    const int t = threadIdx.x - (kEpiWarps + kProdWarps) * 32;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int s = it % S;
+        const uint32_t ph = (it / S) & 1;
+        mbar_wait(&b_full[s], ph);
+        float4* hi = reinterpret_cast<float4*>(b_hi(s));
+        float4* lo = reinterpret_cast<float4*>(b_lo(s));
+#pragma unroll
+        for (int i = 0; i < kVec; ++i) {
+          const int idx = i * 128 + t;     // the split is elementwise, so the swizzled position is simply kept
+          float4 x = hi[idx], h, l;
+          h.x = trunc_tf32(x.x), h.y = trunc_tf32(x.y), h.z = trunc_tf32(x.z), h.w = trunc_tf32(x.w);
+          l.x = x.x - h.x, l.y = x.y - h.y, l.z = x.z - h.z, l.w = x.w - h.w;
+          hi[idx] = h;
+          lo[idx] = l;
+        }
+        fence_proxy_async();
+        mbar_arrive(&ab_ready[s]);
+      }
+    }
+  } else if (warp == 12) {
+    // ================================================================ TMA issue (weights)
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % S;
+          const uint32_t ph = (it / S) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&b_full[s], (uint32_t)P::kBBytes);
+          tma_load_2d(&tmapB, &b_full[s], b_hi(s), kb * BK, nt * BN);
+        }
+      }
+    }
+  } else {
+    // ================================================================ MMA issue
+    if (lane == 0) {
+      int it = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+        const int acc = tcount % kAccBufs;
+        const uint32_t acc_phase = (tcount / kAccBufs) & 1;
+        mbar_wait(&tm_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d = tmem_base + (uint32_t)(acc * 2 * kAccStride);
+        const uint32_t dl = d + (uint32_t)kAccStride;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % S;
+          const uint32_t ph = (it / S) & 1;
+          mbar_wait(&ab_ready[s], ph);
+          tc_fence_after();
+          const uint64_t dah = G::desc(smem_u32(a_hi(s))), dal = G::desc(smem_u32(a_lo(s)));
+          const uint64_t dbh = G::desc(smem_u32(b_hi(s))), dbl = G::desc(smem_u32(b_lo(s)));
+#pragma unroll
+          for (int k = 0; k < BK / 8; ++k) {
+            const uint64_t adv = (uint64_t)(k * 2);          // 8 fp32 = 32 bytes = 2 x 16 B along K inside the atom
+            umma_tf32(dl, dal + adv, dbh + adv, kIdesc, (kb | k) != 0);
+            umma_tf32(dl, dah + adv, dbl + adv, kIdesc, 1u);
+            umma_tf32(d, dah + adv, dbh + adv, kIdesc, (kb | k) != 0);
+          }
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&tm_full[acc]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 13) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// ------------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// weight matrix W[N, K] fp32 row-major -> 2-D tensor map with a (BK x BN) box, hardware swizzle matching Geo<BK>
+static int make_weight_map(CUtensorMap* map, const float* W, int N, int K, long long ldw, int BN, int BK) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("tc_gemm: cuTensorMapEncodeTiled is not available from the driver");
+    return -3;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
+  cuuint64_t strides[1] = {(cuuint64_t)ldw * 4};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BN};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(W), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, BK == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("tc_gemm: cuTensorMapEncodeTiled failed with %d (N=%d K=%d ldw=%lld)", (int)r, N, K, ldw);
+    return -3;
+  }
+  return 0;
+}
+
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+
+int g_tc_bk = 32;   // K-block of the engine: 32 (SWIZZLE_128B) or 16 (SWIZZLE_64B, deeper pipeline)
+
+template <int BN, int BK, class AL, class EP>
+static int launch_tc(const AL& al, const EP& ep, const float* W, long long ldw, long long M, int N, int K,
+                     cudaStream_t s, const char* name) {
+  CUtensorMap map;
+  int rc = make_weight_map(&map, W, N, K, ldw, BN, BK);
+  if (rc) return rc;
+  using P = SmemPlan<BN, BK>;
+  auto kern = tc_gemm_kernel<BN, BK, AL, EP>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P::kTotal);
+  if (e != cudaSuccess) {
+    set_error("%s: cannot raise shared memory to %d: %s", name, P::kTotal, cudaGetErrorString(e));
+    return -2;
+  }
+  const int m_tiles = cdiv(M, BM), n_tiles = cdiv(N, BN);
+  const int grid = min(num_sms(), m_tiles * n_tiles);
+  kern<<<grid, kThreads, P::kTotal, s>>>(map, al, ep, M, N, K, m_tiles, n_tiles);
+  CVAR_CHECK_LAUNCH(name);
+  return 0;
+}
+
+template <class AL, class EP>
+static int dispatch_tc(const AL& al, const EP& ep, const float* W, long long ldw, long long M, int N, int K,
+                       cudaStream_t s, const char* name) {
+  // BN: 256 for the wide transformer layers, 160 for the decoder's 160/320/640-channel convolutions, 128 otherwise
+  const bool bk16 = (g_tc_bk == 16);
+  if (N % 160 == 0 && N % 256 != 0 && N <= 640) {
+    return bk16 ? launch_tc<160, 16>(al, ep, W, ldw, M, N, K, s, name) : launch_tc<160, 32>(al, ep, W, ldw, M, N, K, s, name);
+  }
+  if (N >= 256) {
+    return bk16 ? launch_tc<256, 16>(al, ep, W, ldw, M, N, K, s, name) : launch_tc<256, 32>(al, ep, W, ldw, M, N, K, s, name);
+  }
+  return bk16 ? launch_tc<128, 16>(al, ep, W, ldw, M, N, K, s, name) : launch_tc<128, 32>(al, ep, W, ldw, M, N, K, s, name);
+}
+
+static bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
+
+int tc_gemm_try(const cvar_gemm_args* a, cudaStream_t s) {
+  if (g_gemm_engine != 1) return 0;
+  if (a->batch != 1 || a->w_is_kn || a->M < 64 || a->N < 64 || a->K % 32 != 0 || a->N % 4 != 0) return 0;
+  if (a->lda % 4 != 0 || a->ldw % 4 != 0 || !aligned16(a->A) || !aligned16(a->W)) return 0;
+  DenseALoader al{a->A, a->lda, a->strideA, a->M, a->K, 1};
+  DenseEpilogue ep{a->out, a->ldo, a->strideO, a->bias, a->epilogue, a->alpha, a->gamma, a->gamma_row_stride,
+                   a->rows_per_sample, a->resid, a->ldr, a->strideR};
+  int rc = dispatch_tc(al, ep, a->W, a->ldw, (long long)a->M, a->N, a->K, s, "cvar_gemm[tc]");
+  return rc ? rc : 1;
+}
+
+int tc_qkv_try(const float* A, const float* Wqkv, const QkvEpilogue& ep, int M, int C, cudaStream_t s) {
+  if (g_gemm_engine != 1) return 0;
+  if (M < 64 || C % 32 != 0 || !aligned16(A) || !aligned16(Wqkv)) return 0;
+  DenseALoader al{A, C, 0, M, C, 1};
+  int rc = dispatch_tc(al, ep, Wqkv, C, (long long)M, 3 * C, C, s, "cvar_qkv_project[tc]");
+  return rc ? rc : 1;
+}
+
+int tc_conv_try(const cvar_conv_args* a, cudaStream_t s) {
+  if (g_gemm_engine != 1) return 0;
+  if (a->Cin % 32 != 0 || a->Cout % 16 != 0 || a->Cout < 32) return 0;
+  const int up = a->upsample2x ? 1 : 0;
+  const int Hout = a->Hin << up, Wout = a->Win << up;
+  const long long M = (long long)a->B * Hout * Wout;
+  if (M < 64) return 0;
+  const int K = a->ks * a->ks * a->Cin;
+  ConvALoader al;
+  al.x = a->x, al.in_a = a->in_a, al.in_b = a->in_b, al.in_silu = a->in_silu;
+  al.Hin = a->Hin, al.Win = a->Win, al.Cin = a->Cin, al.ks = a->ks, al.up = up;
+  al.Hout = Hout, al.Wout = Wout, al.Mtot = M, al.K = K;
+  ConvEpilogue ep{a->out, a->bias, a->resid, a->Cout, a->out_mode, Hout, Wout, a->out_rows_total, a->row_offset};
+  int rc = dispatch_tc(al, ep, a->w, K, M, a->Cout, K, s, "cvar_conv2d[tc]");
+  return rc ? rc : 1;
+}
+
+}  // namespace tc
+
+int tc_gemm_try(const cvar_gemm_args* a, cudaStream_t s) { return tc::tc_gemm_try(a, s); }
+int tc_qkv_try(const float* A, const float* Wqkv, const QkvEpilogue& ep, int M, int C, cudaStream_t s) {
+  return tc::tc_qkv_try(A, Wqkv, ep, M, C, s);
+}
+int tc_conv_try(const cvar_conv_args* a, cudaStream_t s) { return tc::tc_conv_try(a, s); }
 }  // namespace cvar

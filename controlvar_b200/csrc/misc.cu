@@ -28,6 +28,12 @@ extern "C" int cvar_set_gemm_engine(int e) {
   return old;
 }
 extern "C" int cvar_get_gemm_engine(void) { return cvar::g_gemm_engine; }
+namespace cvar { namespace tc { extern int g_tc_bk; } }
+extern "C" int cvar_set_tc_kblock(int bk) {
+  int old = cvar::tc::g_tc_bk;
+  if (bk == 16 || bk == 32) cvar::tc::g_tc_bk = bk;
+  return old;
+}
 
 // ------------------------------------------------------------------------------------------------ lvl_pos
 __global__ void lvl_pos_kernel(const float* __restrict__ lvl_embed, const int64_t* __restrict__ lvl_1L,

@@ -15,7 +15,7 @@ struct DenseALoader {
   long long lda, strideA;
   int M, K;
   int vec;   // 1: K, lda multiples of 4 and 16-byte aligned base -> 128-bit loads; 0: scalar loads (ragged shapes)
-  static constexpr int kMaxSlots = 4;
+  static constexpr int kMaxSlots = 8;
   const float* ptr[kMaxSlots];
   __device__ __forceinline__ void prep(int slot, long long m, int batch) {
     ptr[slot] = (m < M) ? A + (long long)batch * strideA + m * lda : nullptr;
@@ -45,7 +45,7 @@ struct ConvALoader {
   int Hout, Wout;
   long long Mtot;
   int K;
-  static constexpr int kMaxSlots = 4;
+  static constexpr int kMaxSlots = 8;
   int sn[kMaxSlots], sy[kMaxSlots], sx[kMaxSlots];
   __device__ __forceinline__ void prep(int slot, long long m, int /*batch*/) {
     if (m < Mtot) {

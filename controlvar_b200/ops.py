@@ -82,6 +82,10 @@ def set_gemm_engine(engine: int) -> int:
     return int(_lib.load().cvar_set_gemm_engine(int(engine)))
 
 
+def set_tc_kblock(bk: int) -> int:
+    return int(_lib.load().cvar_set_tc_kblock(int(bk)))
+
+
 def get_gemm_engine() -> int:
     return int(_lib.load().cvar_get_gemm_engine())
 

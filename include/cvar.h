@@ -38,6 +38,9 @@ CVAR_API long long cvar_launch_count(void);
  * 2 = tcgen05 bf16 (fast, not parity-grade).  Returns the previous value. */
 CVAR_API int cvar_set_gemm_engine(int engine);
 CVAR_API int cvar_get_gemm_engine(void);
+/* K-block of the tcgen05 engine: 32 (128-byte swizzle, default) or 16 (64-byte swizzle, deeper pipeline). Returns the
+ * previous value. */
+CVAR_API int cvar_set_tc_kblock(int bk);
 
 /* ---- prologue: control_var.py:381-383, 399-409 -------------------------------------------------------------
  * lvl_pos[t,:] = lvl_embed[lvl_1L[t],:] + pos_1LC[t,:]                                   (control_var.py:383) */

@@ -34,8 +34,15 @@ def build(cfg, weight_seed=0):
     return vae, var, sd, vsd
 
 
+@pytest.fixture(params=[0, 1], ids=["simt", "tc3xtf32"])
+def engine(request):
+    old = ops.set_gemm_engine(request.param)
+    yield request.param
+    ops.set_gemm_engine(old)
+
+
 @pytest.mark.parametrize("name", golden_names())
-def test_sampler_matches_reference_golden(name):
+def test_sampler_matches_reference_golden(engine, name):
     gold = load_golden(name)
     m, cfg = gold["meta"], gold["cfg"]
     vae, var, _, _ = build(cfg, m["weight_seed"])
@@ -56,7 +63,7 @@ def test_sampler_matches_reference_golden(name):
     assert torch.equal(img, img2)
 
 
-def test_sampler_vs_oracle_fresh_inputs():
+def test_sampler_vs_oracle_fresh_inputs(engine):
     """d6, 8 scales, B=4 on inputs no golden covers: free-running tokens must equal the oracle's wherever the
     oracle's own sampling margin exceeds 1e-4; below that a draw is ambiguous at fp32 resolution."""
     from controlvar_b200.config import PathConfig

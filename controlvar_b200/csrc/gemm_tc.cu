@@ -246,14 +246,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmapB, AL al, EP ep, long lon
 #pragma unroll
       for (int i = 0; i < kVec; ++i) al.prep(i, (long long)mt * BM + (i * 128 + t) / kCh, 0);
       float4 cur[kVec], nxt[kVec];
+      al.begin_block(0);
 #pragma unroll
-      for (int i = 0; i < kVec; ++i) cur[i] = al.fetch(i, ((i * 128 + t) % kCh) * 4);
+      for (int i = 0; i < kVec; ++i) cur[i] = al.fetch_blk(i, 0, ((i * 128 + t) % kCh) * 4);
       for (int kb = 0; kb < nkb; ++kb, ++it) {
         const int s = it % S;
         const uint32_t ph = (it / S) & 1;
         if (kb + 1 < nkb) {
+          al.begin_block((kb + 1) * BK);
 #pragma unroll
-          for (int i = 0; i < kVec; ++i) nxt[i] = al.fetch(i, (kb + 1) * BK + ((i * 128 + t) % kCh) * 4);
+          for (int i = 0; i < kVec; ++i) nxt[i] = al.fetch_blk(i, (kb + 1) * BK, ((i * 128 + t) % kCh) * 4);
         }
         mbar_wait(&empty[s], ph ^ 1);
         unsigned char* hi = a_hi(s);

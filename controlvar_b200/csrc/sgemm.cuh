@@ -31,6 +31,9 @@ struct DenseALoader {
     if (k + 3 < K) v.w = p[k + 3];
     return v;
   }
+  // tcgen05 engine: k0 = first column of the K-block (multiple of the block size), koff = offset inside the block
+  __device__ __forceinline__ void begin_block(int /*k0*/) {}
+  __device__ __forceinline__ float4 fetch_blk(int slot, int k0, int koff) const { return fetch(slot, k0 + koff); }
 };
 
 // Implicit-GEMM view of a stride-1 'same' convolution over an NHWC activation (vae_modules.py Conv2d call sites):
@@ -47,6 +50,31 @@ struct ConvALoader {
   int K;
   static constexpr int kMaxSlots = 8;
   int sn[kMaxSlots], sy[kMaxSlots], sx[kMaxSlots];
+  int blk_dy, blk_dx, blk_ci;   // tap offset and first input channel of the current K-block (tcgen05 engine)
+  // A K-block never straddles two taps when Cin is a multiple of the block size, so the tap decode (two integer
+  // divisions) is done once per block instead of once per 16-byte fetch.
+  __device__ __forceinline__ void begin_block(int k0) {
+    int tap = k0 / Cin;
+    blk_ci = k0 - tap * Cin;
+    int ky = tap / ks;
+    blk_dy = ky - (ks >> 1);
+    blk_dx = (tap - ky * ks) - (ks >> 1);
+  }
+  __device__ __forceinline__ float4 fetch_blk(int slot, int /*k0*/, int koff) const {
+    float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (sn[slot] < 0) return z;
+    int yy = sy[slot] + blk_dy, xx = sx[slot] + blk_dx;
+    if (yy < 0 || yy >= Hout || xx < 0 || xx >= Wout) return z;
+    int ci = blk_ci + koff;
+    int n = sn[slot];
+    float4 v = ld4(x + (((long long)n * Hin + (yy >> up)) * Win + (xx >> up)) * Cin + ci);
+    if (in_a != nullptr) {
+      float4 a = ld4(in_a + (long long)n * Cin + ci), b = ld4(in_b + (long long)n * Cin + ci);
+      v.x = fmaf(v.x, a.x, b.x), v.y = fmaf(v.y, a.y, b.y), v.z = fmaf(v.z, a.z, b.z), v.w = fmaf(v.w, a.w, b.w);
+      if (in_silu) v.x = silu_f(v.x), v.y = silu_f(v.y), v.z = silu_f(v.z), v.w = silu_f(v.w);
+    }
+    return v;
+  }
   __device__ __forceinline__ void prep(int slot, long long m, int /*batch*/) {
     if (m < Mtot) {
       int xw = (int)(m % Wout);

@@ -114,21 +114,27 @@ class VQVAE(nn.Module):
         ops.gn_stats(x, self._w(prefix + ".weight"), self._w(prefix + ".bias"), a, b, scratch, B, HW, Cn)
         return a, b
 
+    def _norm_act(self, x, prefix, B, H, W, Cn, slot: int):
+        """silu(GroupNorm(x)) materialised once (vae_modules.py:58-59).  One HBM-bound pass instead of re-evaluating
+        the normalisation + SiLU for each of the 9 taps inside the convolution's operand gather."""
+        a, b = self._gn(x, prefix, B, H * W, Cn, slot)
+        y = self._buf("normact", (self._act_numel,))[:B * H * W * Cn].view(B, H, W, Cn)
+        ops.affine_nc(x, a, b, y, B, H * W, Cn, silu=True)
+        return y
+
     def _resblock(self, x, prefix, B, H, W, cin, cout, bufs):
         """ResnetBlock.forward (vae_modules.py:57-60); x is never written."""
         h1, out = bufs
-        a1, b1 = self._gn(x, prefix + "norm1", B, H * W, cin, 0)
-        ops.conv2d(x, self._conv_w(prefix + "conv1"), self._w(prefix + "conv1.bias"), h1, B, H, W, cin, cout, 3,
-                   in_a=a1, in_b=b1, in_silu=True)
-        a2, b2 = self._gn(h1, prefix + "norm2", B, H * W, cout, 1)
+        ops.conv2d(self._norm_act(x, prefix + "norm1", B, H, W, cin, 0), self._conv_w(prefix + "conv1"),
+                   self._w(prefix + "conv1.bias"), h1, B, H, W, cin, cout, 3)
         if cin != cout:
             sc = self._buf("shortcut", (B, H, W, cout))
             ops.conv2d(x, self._conv_w(prefix + "nin_shortcut"), self._w(prefix + "nin_shortcut.bias"), sc, B, H, W,
                        cin, cout, 1)
         else:
             sc = x
-        ops.conv2d(h1, self._conv_w(prefix + "conv2"), self._w(prefix + "conv2.bias"), out, B, H, W, cout, cout, 3,
-                   in_a=a2, in_b=b2, in_silu=True, resid=sc)
+        ops.conv2d(self._norm_act(h1, prefix + "norm2", B, H, W, cout, 1), self._conv_w(prefix + "conv2"),
+                   self._w(prefix + "conv2.bias"), out, B, H, W, cout, cout, 3, resid=sc)
         return out
 
     def _attnblock(self, x, prefix, B, H, W, Cn, out):
@@ -177,6 +183,7 @@ class VQVAE(nn.Module):
             if op == "up":
                 hh *= 2
             act_numel = max(act_numel, B * hh * hh * max(cin if op == "out" else cout, 1))
+        self._act_numel = act_numel
 
         for op, prefix, cin, cout in self._plan:
             if op == "conv3":
@@ -197,10 +204,9 @@ class VQVAE(nn.Module):
                 H, W = 2 * H, 2 * W
                 cur = out
             elif op == "out":
-                a, b = self._gn(cur, "decoder.norm_out", B, H * W, cin, 0)
-                ops.conv2d(cur, self._conv_w("decoder.conv_out"), self._w("decoder.conv_out.bias"), img_out, B, H, W,
-                           cin, 3, 3, in_a=a, in_b=b, in_silu=True, out_mode=out_mode, out_rows_total=rows_total,
-                           row_offset=row_offset)
+                ops.conv2d(self._norm_act(cur, "decoder.norm_out", B, H, W, cin, 0), self._conv_w("decoder.conv_out"),
+                           self._w("decoder.conv_out.bias"), img_out, B, H, W, cin, 3, 3, out_mode=out_mode,
+                           out_rows_total=rows_total, row_offset=row_offset)
             else:
                 raise AssertionError(op)
 

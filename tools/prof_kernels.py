@@ -1,0 +1,60 @@
+"""Runs the three hot kernels once each at the sizes of the d24 / batch-64 workload (last scale), for ncu captures:
+   ncu --set full --clock-control none --import-source on -k regex:<name> -o gpurun_out/<name> python tools/prof_kernels.py <which>
+which in {gemm, conv, attn, all}.  Never a benchmark: numbers printed under a profiler are not bench values."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from controlvar_b200 import ops  # noqa: E402
+
+which = sys.argv[1] if len(sys.argv) > 1 else "all"
+engine = int(os.environ.get("CVAR_GEMM_ENGINE", "1"))
+ops.set_gemm_engine(engine)
+dev = "cuda"
+torch.manual_seed(0)
+
+
+def timed(fn, n=3):
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
+if which in ("gemm", "all"):
+    M, N, K = 65536, 6144, 1536            # fc1 of d24 at the last scale (R*l = 128*512 rows)
+    A = torch.randn(M, K, device=dev)
+    W = torch.randn(N, K, device=dev) / 40
+    b = torch.randn(N, device=dev)
+    out = torch.empty(M, N, device=dev)
+    ms = timed(lambda: ops.gemm(A, W, b, out, M, N, K, epilogue=ops.EPI_BIAS_GELU))
+    print(f"gemm fc1 M={M} N={N} K={K}: {ms:.3f} ms  {2.0 * M * N * K / ms / 1e9:.1f} TFLOP/s")
+    del A, W, out
+
+if which in ("conv", "all"):
+    B, H, C = 8, 256, 160                  # decoder up.0 ResnetBlock conv at 256x256
+    x = torch.randn(B, H, H, C, device=dev)
+    w = torch.randn(C, 9 * C, device=dev) / 38
+    b = torch.randn(C, device=dev)
+    out = torch.empty(B, H, H, C, device=dev)
+    ms = timed(lambda: ops.conv2d(x, w, b, out, B, H, H, C, C, 3))
+    print(f"conv3x3 B={B} {H}x{H} {C}->{C}: {ms:.3f} ms  {2.0 * B * H * H * C * 9 * C / ms / 1e9:.1f} TFLOP/s")
+    del x, out
+
+if which in ("attn", "all"):
+    R, Hh, l, L, T = 128, 24, 512, 1360, 1360
+    q = torch.randn(R, Hh, l, 64, device=dev)
+    kc = torch.randn(R, Hh, T, 64, device=dev)
+    vc = torch.randn(R, Hh, T, 64, device=dev)
+    out = torch.empty(R, l, Hh * 64, device=dev)
+    ms = timed(lambda: ops.attn_kvcache(q, kc, vc, out, R, Hh, l, L, T, 1 / 32))
+    fl = 4.0 * l * L * 64 * R * Hh
+    by = (2.0 * l + 2.0 * L) * 64 * 4 * R * Hh
+    print(f"attn R={R} H={Hh} l={l} L={L}: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s  {by / ms / 1e6:.0f} GB/s algorithmic")

@@ -20,6 +20,7 @@ class GemmArgs(C.Structure):
     _fields_ = [
         ("A", C.c_void_p), ("lda", c_ll), ("strideA", c_ll),
         ("W", C.c_void_p), ("ldw", c_ll), ("strideW", c_ll), ("w_is_kn", C.c_int),
+        ("W_hi", C.c_void_p), ("W_lo", C.c_void_p),
         ("bias", C.c_void_p),
         ("out", C.c_void_p), ("ldo", c_ll), ("strideO", c_ll),
         ("M", C.c_int), ("N", C.c_int), ("K", C.c_int), ("batch", C.c_int),
@@ -31,7 +32,8 @@ class GemmArgs(C.Structure):
 
 class ConvArgs(C.Structure):
     _fields_ = [
-        ("x", C.c_void_p), ("w", C.c_void_p), ("bias", C.c_void_p), ("out", C.c_void_p),
+        ("x", C.c_void_p), ("w", C.c_void_p), ("w_hi", C.c_void_p), ("w_lo", C.c_void_p), ("bias", C.c_void_p),
+        ("out", C.c_void_p),
         ("in_a", C.c_void_p), ("in_b", C.c_void_p), ("in_silu", C.c_int),
         ("resid", C.c_void_p),
         ("B", C.c_int), ("Hin", C.c_int), ("Win", C.c_int), ("Cin", C.c_int), ("Cout", C.c_int), ("ks", C.c_int),
@@ -48,12 +50,14 @@ PROTOTYPES = {
     "cvar_set_gemm_engine": (C.c_int, [C.c_int]),
     "cvar_get_gemm_engine": (C.c_int, []),
     "cvar_set_tc_kblock": (C.c_int, [C.c_int]),
+    "cvar_debug_set_trace": (C.c_int, [C.c_void_p]),
     "cvar_lvl_pos": (C.c_int, [c_f, c_f, c_f, c_f, C.c_int, C.c_int, C.c_void_p]),
     "cvar_prologue": (C.c_int, [c_f, c_f, c_f, c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, c_f, c_f, c_f, C.c_void_p]),
     "cvar_ln_modulate": (C.c_int, [c_f, c_f, c_f, c_ll, c_f, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
     "cvar_gemm": (C.c_int, [C.POINTER(GemmArgs), C.c_void_p]),
-    "cvar_qkv_project": (C.c_int, [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, C.c_int,
+    "cvar_qkv_project": (C.c_int, [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.c_int, C.c_int, c_f, C.c_void_p]),
+    "cvar_split_tf32": (C.c_int, [c_f, c_f, c_f, c_ll, C.c_void_p]),
     "cvar_attn_kvcache": (C.c_int, [c_f, c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                     C.c_void_p]),
     "cvar_cfg_sample": (C.c_int, [c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_double,

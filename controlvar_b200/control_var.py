@@ -159,17 +159,19 @@ class ControlVAR(nn.Module):
             blocks = []
             for i in range(self.depth):
                 p = f"blocks.{i}."
+                SW = ops.SplitWeight     # TF32 hi/lo split, once per weight: the tcgen05 engine's TMA operands
                 blocks.append(dict(
-                    qkv_w=P(p + "attn.mat_qkv.weight"), q_bias=P(p + "attn.q_bias"), v_bias=P(p + "attn.v_bias"),
+                    qkv_w=SW(P(p + "attn.mat_qkv.weight")), q_bias=P(p + "attn.q_bias"), v_bias=P(p + "attn.v_bias"),
                     k_bias=self.get_buffer(p + "attn.zero_k_bias"),
-                    proj_w=P(p + "attn.proj.weight"), proj_b=P(p + "attn.proj.bias"),
-                    fc1_w=P(p + "ffn.fc1.weight"), fc1_b=P(p + "ffn.fc1.bias"),
-                    fc2_w=P(p + "ffn.fc2.weight"), fc2_b=P(p + "ffn.fc2.bias"),
-                    ada_w=P(p + "ada_lin.1.weight"), ada_b=P(p + "ada_lin.1.bias"),
+                    proj_w=SW(P(p + "attn.proj.weight")), proj_b=P(p + "attn.proj.bias"),
+                    fc1_w=SW(P(p + "ffn.fc1.weight")), fc1_b=P(p + "ffn.fc1.bias"),
+                    fc2_w=SW(P(p + "ffn.fc2.weight")), fc2_b=P(p + "ffn.fc2.bias"),
+                    ada_w=SW(P(p + "ada_lin.1.weight")), ada_b=P(p + "ada_lin.1.bias"),
                     scale_mul=P(p + "attn.scale_mul_1H11").reshape(-1).contiguous() if self.cos_attn else None,
                 ))
             c["blocks"] = blocks
             c["head_ada_w"], c["head_ada_b"] = P("head_nm.ada_lin.1.weight"), P("head_nm.ada_lin.1.bias")
+            c["head_w"] = ops.SplitWeight(P("head.weight"))
             vq = self.vae_proxy[0]
             c["phi"] = [(vq.get_parameter(f"quantize.quant_resi.qresi_ls.{k}.weight"),
                          vq.get_parameter(f"quantize.quant_resi.qresi_ls.{k}.bias"))
@@ -273,7 +275,7 @@ class ControlVAR(nn.Module):
                          epilogue=ops.EPI_BIAS_GAMMA_RESID, gamma=g2, gamma_row_stride=6 * C, rows_per_sample=l)
             # head: AdaLNBeforeHead + Linear(C, V)
             ops.ln_modulate(x, ada_head[:, :C], ada_head[:, C:], 2 * C, xn, M, C, l, self.norm_eps)
-            ops.gemm(xn, self.get_parameter("head.weight"), self.get_parameter("head.bias"), logits, M, V, C)
+            ops.gemm(xn, cst["head_w"], self.get_parameter("head.bias"), logits, M, V, C)
             # CFG + top-k/top-p + multinomial
             t = cfg * (si / self.num_stages_minus_1)
             q_noise = self._noise(B * l, V, rng)

@@ -57,7 +57,8 @@ __device__ __forceinline__ float gelu_tanh_f(float x) {
   const float kBeta = 0.7978845608028654f;   // sqrt(2/pi)
   const float kKappa = 0.044715f;
   float inner = kBeta * (x + kKappa * x * x * x);
-  return 0.5f * x * (1.0f + tanhf(inner));
+  // 0.5 * x * (1 + tanh(u)) == x * sigmoid(2u) == x / (1 + exp(-2u)): same function, no tanhf, no cancellation
+  return x / (1.0f + expf(-2.0f * inner));
 }
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }

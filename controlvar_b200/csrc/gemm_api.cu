@@ -6,7 +6,9 @@ using namespace cvar;
 namespace cvar {
 // tcgen05 engine (gemm_tc.cu); returns 1 when it took the problem, 0 when the shape is not supported, <0 on error.
 int tc_gemm_try(const cvar_gemm_args* a, cudaStream_t s);
-int tc_qkv_try(const float* A, const float* Wqkv, const QkvEpilogue& ep, int M, int C, cudaStream_t s);
+int tc_qkv_try(const float* A, const float* Wqkv_hi, const float* Wqkv_lo, const QkvEpilogue& ep, int M, int C,
+               cudaStream_t s);
+int tc_split(const float* w, float* hi, float* lo, long long n, cudaStream_t s);
 int tc_conv_try(const cvar_conv_args* a, cudaStream_t s);
 }  // namespace cvar
 
@@ -23,7 +25,7 @@ extern "C" int cvar_gemm(const cvar_gemm_args* a, void* stream) {
                "cvar_gemm: gamma epilogue without gamma");
   CVAR_REQUIRE(a->epilogue != CVAR_EPI_BIAS_RESID || a->resid, "cvar_gemm: residual epilogue without resid");
   cudaStream_t s = (cudaStream_t)stream;
-  if (g_gemm_engine != 0) {
+  if (g_gemm_engine != 0 && a->W_hi != nullptr && a->W_lo != nullptr) {
     int took = tc_gemm_try(a, s);
     if (took < 0) return took;
     if (took == 1) return 0;
@@ -62,8 +64,8 @@ __global__ void cos_attn_normalize_kernel(float* __restrict__ q, float* __restri
   *reinterpret_cast<float2*>(p + lane * 2) = v;
 }
 
-extern "C" int cvar_qkv_project(const float* A, const float* Wqkv, const float* q_bias, const float* k_bias,
-                                const float* v_bias, float* q_out, float* k_cache, float* v_cache, int R, int l,
+extern "C" int cvar_qkv_project(const float* A, const float* Wqkv, const float* Wqkv_hi, const float* Wqkv_lo,
+                                const float* q_bias, const float* k_bias, const float* v_bias, float* q_out, float* k_cache, float* v_cache, int R, int l,
                                 int L_prev, int T_max, int H, int cos_attn, const float* scale_mul_H, void* stream) {
   CVAR_REQUIRE(R > 0 && l > 0 && H > 0 && L_prev >= 0 && L_prev + l <= T_max, "cvar_qkv_project: bad shape");
   CVAR_REQUIRE(!cos_attn || scale_mul_H != nullptr, "cvar_qkv_project: cosine attention needs scale_mul");
@@ -71,8 +73,8 @@ extern "C" int cvar_qkv_project(const float* A, const float* Wqkv, const float* 
   const int C = H * 64, M = R * l;
   QkvEpilogue ep{q_bias, k_bias, v_bias, q_out, k_cache, v_cache, C, H, l, L_prev, T_max};
   int took = 0;
-  if (g_gemm_engine != 0) {
-    took = tc_qkv_try(A, Wqkv, ep, M, C, s);
+  if (g_gemm_engine != 0 && Wqkv_hi != nullptr && Wqkv_lo != nullptr) {
+    took = tc_qkv_try(A, Wqkv_hi, Wqkv_lo, ep, M, C, s);
     if (took < 0) return took;
   }
   if (took == 0) {
@@ -97,7 +99,7 @@ extern "C" int cvar_conv2d(const cvar_conv_args* a, void* stream) {
   CVAR_REQUIRE(a->out_mode == 0 || a->resid == nullptr, "cvar_conv2d: image output takes no residual");
   CVAR_REQUIRE((a->in_a == nullptr) == (a->in_b == nullptr), "cvar_conv2d: in_a/in_b must come together");
   cudaStream_t s = (cudaStream_t)stream;
-  if (g_gemm_engine != 0) {
+  if (g_gemm_engine != 0 && a->w_hi != nullptr && a->w_lo != nullptr) {
     int took = tc_conv_try(a, s);
     if (took < 0) return took;
     if (took == 1) return 0;
@@ -113,4 +115,9 @@ extern "C" int cvar_conv2d(const cvar_conv_args* a, void* stream) {
   DenseBLoader bl{a->w, K, 0, a->Cout, K, 0, 1};
   ConvEpilogue ep{a->out, a->bias, a->resid, a->Cout, a->out_mode, Hout, Wout, a->out_rows_total, a->row_offset};
   return launch_sgemm(al, bl, ep, M, a->Cout, K, 1, s, "cvar_conv2d");
+}
+
+extern "C" int cvar_split_tf32(const float* w, float* w_hi, float* w_lo, long long n, void* stream) {
+  CVAR_REQUIRE(n > 0 && n % 4 == 0, "cvar_split_tf32: n must be a positive multiple of 4");
+  return tc_split(w, w_hi, w_lo, n, (cudaStream_t)stream);
 }

@@ -28,7 +28,8 @@ extern "C" int cvar_set_gemm_engine(int e) {
   return old;
 }
 extern "C" int cvar_get_gemm_engine(void) { return cvar::g_gemm_engine; }
-namespace cvar { namespace tc { extern int g_tc_bk; } }
+namespace cvar { namespace tc { extern int g_tc_bk; int set_trace(long long*); } }
+extern "C" int cvar_debug_set_trace(long long* dev_buf) { return cvar::tc::set_trace(dev_buf); }
 extern "C" int cvar_set_tc_kblock(int bk) {
   int old = cvar::tc::g_tc_bk;
   if (bk == 16 || bk == 32) cvar::tc::g_tc_bk = bk;

@@ -167,6 +167,55 @@ struct DenseEpilogue {
   }
 };
 
+// ---- two-phase form used by the tcgen05 epilogue: all global READS of a pass are issued first (load_aux), then the
+// math and the stores (store_aux), so the loads of independent rows overlap instead of serialising behind stores.
+struct EpiAux {
+  float4 a, b;
+};
+
+__device__ __forceinline__ EpiAux dense_load_aux(const DenseEpilogue& e, long long m, int n, int nvalid, int batch) {
+  EpiAux x;
+  x.a = make_float4(0.f, 0.f, 0.f, 0.f);
+  x.b = x.a;
+  if (nvalid != 4) return x;            // ragged tail: store_aux falls back to the scalar path
+  if (e.mode == CVAR_EPI_BIAS_GAMMA_RESID) {
+    x.a = ld4(e.out + (long long)batch * e.strideO + m * e.ldo + n);
+    x.b = ld4(e.gamma + (m / e.rows_per_sample) * e.gamma_row_stride + n);
+  } else if (e.mode == CVAR_EPI_BIAS_RESID) {
+    x.a = ld4(e.resid + (long long)batch * e.strideR + m * e.ldr + n);
+  }
+  return x;
+}
+// fast, fp32-class GELU(tanh) for the tensor-core epilogue: x * sigmoid(2u) with ex2.approx / rcp.approx (<= ~1e-6 rel)
+__device__ __forceinline__ float gelu_tanh_fast(float x) {
+  float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
+  return __fdividef(x, 1.0f + __expf(-2.0f * u));
+}
+__device__ __forceinline__ void dense_store_aux(const DenseEpilogue& e, long long m, int n, const float* v, int nvalid,
+                                                int batch, const EpiAux& x) {
+  float* o = e.out + (long long)batch * e.strideO + m * e.ldo + n;
+  if (nvalid != 4 || ((((uintptr_t)o) & 15) != 0)) {
+    e.store(m, n, v, nvalid, batch);
+    return;
+  }
+  float4 b4 = e.bias != nullptr ? ld4(e.bias + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+  float r[4] = {v[0], v[1], v[2], v[3]};
+  const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float t = (e.mode == CVAR_EPI_BIAS) ? __fadd_rn(__fmul_rn(r[j], e.alpha), bb[j]) : __fadd_rn(r[j], bb[j]);
+    if (e.mode == CVAR_EPI_BIAS_GELU) t = gelu_tanh_fast(t);
+    r[j] = t;
+  }
+  if (e.mode == CVAR_EPI_BIAS_GAMMA_RESID) {
+    r[0] = __fadd_rn(x.a.x, __fmul_rn(r[0], x.b.x)), r[1] = __fadd_rn(x.a.y, __fmul_rn(r[1], x.b.y));
+    r[2] = __fadd_rn(x.a.z, __fmul_rn(r[2], x.b.z)), r[3] = __fadd_rn(x.a.w, __fmul_rn(r[3], x.b.w));
+  } else if (e.mode == CVAR_EPI_BIAS_RESID) {
+    r[0] = __fadd_rn(x.a.x, r[0]), r[1] = __fadd_rn(x.a.y, r[1]), r[2] = __fadd_rn(x.a.z, r[2]), r[3] = __fadd_rn(x.a.w, r[3]);
+  }
+  st4(o, make_float4(r[0], r[1], r[2], r[3]));
+}
+
 // qkv = x W^T + [q_bias, k_bias, v_bias]; q to (R,H,l,64), k/v appended to the cache      (basic_var.py:92-108)
 struct QkvEpilogue {
   const float* q_bias;
@@ -240,6 +289,43 @@ struct ConvEpilogue {
     }
   }
 };
+
+__device__ __forceinline__ EpiAux epi_load_aux(const DenseEpilogue& e, long long m, int n, int nv, int b) {
+  return dense_load_aux(e, m, n, nv, b);
+}
+__device__ __forceinline__ void epi_store_aux(const DenseEpilogue& e, long long m, int n, const float* v, int nv, int b,
+                                              const EpiAux& x) {
+  dense_store_aux(e, m, n, v, nv, b, x);
+}
+__device__ __forceinline__ EpiAux epi_load_aux(const QkvEpilogue&, long long, int, int, int) {
+  EpiAux x;
+  x.a = make_float4(0.f, 0.f, 0.f, 0.f);
+  x.b = x.a;
+  return x;
+}
+__device__ __forceinline__ void epi_store_aux(const QkvEpilogue& e, long long m, int n, const float* v, int nv, int b,
+                                              const EpiAux&) {
+  e.store(m, n, v, nv, b);
+}
+__device__ __forceinline__ EpiAux epi_load_aux(const ConvEpilogue& e, long long m, int n, int nv, int) {
+  EpiAux x;
+  x.a = make_float4(0.f, 0.f, 0.f, 0.f);
+  x.b = x.a;
+  if (e.out_mode == 0 && e.resid != nullptr && nv == 4) x.a = ld4(e.resid + m * e.Cout + n);
+  return x;
+}
+__device__ __forceinline__ void epi_store_aux(const ConvEpilogue& e, long long m, int n, const float* v, int nv, int b,
+                                              const EpiAux& x) {
+  if (e.out_mode != 0 || nv != 4) {
+    e.store(m, n, v, nv, b);
+    return;
+  }
+  float4 b4 = ld4(e.bias + n);
+  float4 r = make_float4(__fadd_rn(v[0], b4.x), __fadd_rn(v[1], b4.y), __fadd_rn(v[2], b4.z), __fadd_rn(v[3], b4.w));
+  if (e.resid != nullptr)
+    r = make_float4(__fadd_rn(x.a.x, r.x), __fadd_rn(x.a.y, r.y), __fadd_rn(x.a.z, r.z), __fadd_rn(x.a.w, r.w));
+  st4(e.out + m * e.Cout + n, r);
+}
 
 // ------------------------------------------------------------------------------------------ main kernel
 template <int BM, int BN, int FM, int FN, class AL, class EP>

@@ -113,11 +113,33 @@ def ln_modulate(x, scale, shift, mod_row_stride, out, M, Cdim, rows_per_sample, 
     return out
 
 
+class SplitWeight:
+    """A weight matrix with its TF32 hi/lo split (made once): what the tcgen05 engine consumes by TMA."""
+    __slots__ = ("w", "hi", "lo")
+
+    def __init__(self, w: torch.Tensor):
+        self.w = w.contiguous()
+        self.hi = torch.empty_like(self.w)
+        self.lo = torch.empty_like(self.w)
+        if self.w.numel() % 4 != 0:
+            raise _lib.CvarError("SplitWeight: number of elements must be a multiple of 4")
+        check(_lib.load().cvar_split_tf32(_p(self.w), _p(self.hi), _p(self.lo), self.w.numel(), _stream()),
+              "cvar_split_tf32")
+
+
+def _wparts(W):
+    if isinstance(W, SplitWeight):
+        return W.w, W.hi, W.lo
+    return W, None, None
+
+
 def gemm(A, W, bias, out, M, N, K, *, lda=None, ldw=None, ldo=None, epilogue=EPI_BIAS, alpha=1.0, w_is_kn=False,
          batch=1, strideA=0, strideW=0, strideO=0, gamma=None, gamma_row_stride=0, rows_per_sample=1,
          resid=None, ldr=None, strideR=0):
+    W, W_hi, W_lo = _wparts(W)
     _chk(A, W, bias, out, gamma, resid)
     a = GemmArgs()
+    a.W_hi, a.W_lo = _p(W_hi), _p(W_lo)
     a.A, a.lda, a.strideA = _p(A), (K if lda is None else lda), strideA
     a.W, a.ldw, a.strideW, a.w_is_kn = _p(W), ((N if w_is_kn else K) if ldw is None else ldw), strideW, int(w_is_kn)
     a.bias = _p(bias)
@@ -133,10 +155,11 @@ def gemm(A, W, bias, out, M, N, K, *, lda=None, ldw=None, ldo=None, epilogue=EPI
 
 def qkv_project(A, Wqkv, q_bias, k_bias, v_bias, q_out, k_cache, v_cache, R, l, L_prev, T_max, H, cos_attn,
                 scale_mul_H):
+    Wqkv, W_hi, W_lo = _wparts(Wqkv)
     _chk(A, Wqkv, q_bias, k_bias, v_bias, q_out, k_cache, v_cache, scale_mul_H)
     Cd = H * 64
     with _Timed("gemm", 2.0 * R * l * 3 * Cd * Cd, 4.0 * (R * l * Cd + 3 * Cd * Cd + R * l * 3 * Cd)):
-        check(_lib.load().cvar_qkv_project(_p(A), _p(Wqkv), _p(q_bias), _p(k_bias), _p(v_bias), _p(q_out), _p(k_cache),
+        check(_lib.load().cvar_qkv_project(_p(A), _p(Wqkv), _p(W_hi), _p(W_lo), _p(q_bias), _p(k_bias), _p(v_bias), _p(q_out), _p(k_cache),
                                            _p(v_cache), R, l, L_prev, T_max, H, int(cos_attn), _p(scale_mul_H),
                                            _stream()), "cvar_qkv_project")
 
@@ -192,9 +215,11 @@ def gn_stats(x_nhwc, gamma, beta, a_out, b_out, scratch, B, HW, Cdim, groups=32,
 
 def conv2d(x, w_packed, bias, out, B, Hin, Win, Cin, Cout, ks, *, in_a=None, in_b=None, in_silu=False, resid=None,
            upsample2x=False, out_mode=0, out_rows_total=0, row_offset=0):
+    w_packed, w_hi, w_lo = _wparts(w_packed)
     _chk(x, w_packed, bias, out, in_a, in_b, resid)
     a = ConvArgs()
     a.x, a.w, a.bias, a.out = _p(x), _p(w_packed), _p(bias), _p(out)
+    a.w_hi, a.w_lo = _p(w_hi), _p(w_lo)
     a.in_a, a.in_b, a.in_silu = _p(in_a), _p(in_b), int(in_silu)
     a.resid = _p(resid)
     a.B, a.Hin, a.Win, a.Cin, a.Cout, a.ks, a.upsample2x = B, Hin, Win, Cin, Cout, ks, int(upsample2x)

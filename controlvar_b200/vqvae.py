@@ -91,6 +91,8 @@ class VQVAE(nn.Module):
             w = self._w(key)
             t = torch.empty(w.shape[0], w.shape[1] * w.shape[2] * w.shape[3], device=w.device, dtype=torch.float32)
             ops.repack_conv_weight(w.contiguous(), t)
+            if t.numel() % 4 == 0:
+                t = ops.SplitWeight(t)       # + TF32 hi/lo split for the tcgen05 engine
             self._packed[key] = t
         return t
 

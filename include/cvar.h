@@ -41,6 +41,9 @@ CVAR_API int cvar_get_gemm_engine(void);
 /* K-block of the tcgen05 engine: 32 (128-byte swizzle, default) or 16 (64-byte swizzle, deeper pipeline). Returns the
  * previous value. */
 CVAR_API int cvar_set_tc_kblock(int bk);
+/* Diagnostics: device buffer of 4*64*2 int64 that CTA 0 of the tcgen05 engine fills with clock64() stamps of its
+ * pipeline hand-overs (NULL switches the trace off). */
+CVAR_API int cvar_debug_set_trace(long long* dev_buf);
 
 /* ---- prologue: control_var.py:381-383, 399-409 -------------------------------------------------------------
  * lvl_pos[t,:] = lvl_embed[lvl_1L[t],:] + pos_1LC[t,:]                                   (control_var.py:383) */
@@ -74,6 +77,9 @@ enum {
 typedef struct {
   const float* A; long long lda; long long strideA;
   const float* W; long long ldw; long long strideW; int w_is_kn;
+  /* optional TF32 split of W made once by cvar_split_tf32 (same shape / ldw): the tcgen05 engine takes the problem only
+   * when both are given; W itself always stays valid for the SIMT engine */
+  const float* W_hi; const float* W_lo;
   const float* bias;                      /* [N] or NULL */
   float* out; long long ldo; long long strideO;
   int M, N, K, batch;
@@ -88,7 +94,8 @@ CVAR_API int cvar_gemm(const cvar_gemm_args* args, void* stream);
  * q  -> q_out[r, h, t, :]                    (R, H, l, 64)
  * k,v-> k_cache/v_cache[r, h, L_prev + t, :] (R, H, T_max, 64): in-place replacement of the torch.cat growth.
  * cos_attn != 0 (depth 30, basic_var.py:99-104): q = normalize(q) * exp(min(scale_mul[h], ln 100)), k = normalize(k). */
-CVAR_API int cvar_qkv_project(const float* A, const float* Wqkv, const float* q_bias, const float* k_bias, const float* v_bias,
+CVAR_API int cvar_qkv_project(const float* A, const float* Wqkv, const float* Wqkv_hi, const float* Wqkv_lo,
+                     const float* q_bias, const float* k_bias, const float* v_bias,
                      float* q_out, float* k_cache, float* v_cache,
                      int R, int l, int L_prev, int T_max, int H, int cos_attn, const float* scale_mul_H,
                      void* stream);
@@ -142,13 +149,16 @@ CVAR_API int cvar_gn_stats(const float* x_nhwc, const float* gamma, const float*
  * out[n, c, row_offset + y, x] of a (B, Cout, out_rows_total, Wout) tensor   (vqvae.py:89, control_var.py:563-565).
  * out_mode 2: as 1 without the (v+1)*0.5 step (plain VQVAE.fhat_to_img). */
 typedef struct {
-  const float* x; const float* w; const float* bias; float* out;
+  const float* x; const float* w; const float* w_hi; const float* w_lo; const float* bias; float* out;
   const float* in_a; const float* in_b; int in_silu;
   const float* resid;
   int B, Hin, Win, Cin, Cout, ks, upsample2x;
   int out_mode, out_rows_total, row_offset;
 } cvar_conv_args;
 CVAR_API int cvar_conv2d(const cvar_conv_args* args, void* stream);
+/* hi = w with the 13 low mantissa bits cleared (what a TF32 tensor-core operand keeps), lo = w - hi (exact): the
+ * error-compensated 3xTF32 operands of the tcgen05 engine.  n must be a multiple of 4. */
+CVAR_API int cvar_split_tf32(const float* w, float* w_hi, float* w_lo, long long n, void* stream);
 /* (Cout,Cin,ks,ks) -> (Cout, ks*ks*Cin), k index = (ky*ks+kx)*Cin + ci */
 CVAR_API int cvar_repack_conv_weight(const float* w_oihw, float* w_out, int Cout, int Cin, int ks, void* stream);
 /* y = x*a[n,c] + b[n,c] (GroupNorm without activation, AttnBlock.norm) */

@@ -80,9 +80,9 @@ def test_gemm_bias_and_gelu(engine, M, N, K):
     A, Wt, b = torch.randn(M, K), torch.randn(N, K) / math.sqrt(K), torch.randn(N)
     ref = (A.double() @ Wt.double().T + b.double())
     out = torch.empty(M, N, device=DEV)
-    ops.gemm(g(A), g(Wt), g(b), out, M, N, K)
+    ops.gemm(g(A), ops.SplitWeight(g(Wt)), g(b), out, M, N, K)
     assert rel_err(out.cpu().double(), ref) < 1e-5
-    ops.gemm(g(A), g(Wt), g(b), out, M, N, K, epilogue=ops.EPI_BIAS_GELU)
+    ops.gemm(g(A), ops.SplitWeight(g(Wt)), g(b), out, M, N, K, epilogue=ops.EPI_BIAS_GELU)
     assert rel_err(out.cpu().double(), F.gelu(ref, approximate="tanh")) < 1e-5
 
 
@@ -97,7 +97,7 @@ def test_gemm_gamma_residual(engine):
     ref = x0.double() + (A.double() @ Wt.double().T + b.double()) * gamma.double().repeat_interleave(l, 0)
     x = g(x0)
     ada_g = g(ada)
-    ops.gemm(g(A), g(Wt), g(b), x, M, C, K, epilogue=ops.EPI_BIAS_GAMMA_RESID, gamma=ada_g[:, C:2 * C],
+    ops.gemm(g(A), ops.SplitWeight(g(Wt)), g(b), x, M, C, K, epilogue=ops.EPI_BIAS_GAMMA_RESID, gamma=ada_g[:, C:2 * C],
              gamma_row_stride=6 * C, rows_per_sample=l)
     assert rel_err(x.cpu().double(), ref) < 1e-5
 
@@ -125,7 +125,7 @@ def test_gemm_batched_strided_and_kn(engine):
     resid = torch.randn(Bn * HW, Cn)
     Wp, bp = torch.randn(Cn, Cn) / math.sqrt(Cn), torch.randn(Cn)
     out = torch.empty(Bn * HW, Cn, device=DEV)
-    ops.gemm(h.view(-1, Cn), g(Wp), g(bp), out, Bn * HW, Cn, Cn, epilogue=ops.EPI_BIAS_RESID, resid=g(resid))
+    ops.gemm(h.view(-1, Cn), ops.SplitWeight(g(Wp)), g(bp), out, Bn * HW, Cn, Cn, epilogue=ops.EPI_BIAS_RESID, resid=g(resid))
     ref = resid.double() + h.cpu().double().view(-1, Cn) @ Wp.double().T + bp.double()
     assert rel_err(out.cpu().double(), ref) < 1e-5
 
@@ -153,7 +153,7 @@ def test_qkv_project_and_kvcache_attention(engine, cos_attn):
         x = torch.randn(R, l, C)
         ref = O.self_attention(x, sd, "", H, cache, cos_attn, scale)      # proj is the identity here
         q = torch.empty(R, H, l, 64, device=DEV)
-        ops.qkv_project(g(x), sdg["mat_qkv.weight"], sdg["q_bias"], sdg["zero_k_bias"], sdg["v_bias"], q, kc, vc, R, l,
+        ops.qkv_project(g(x), ops.SplitWeight(sdg["mat_qkv.weight"]), sdg["q_bias"], sdg["zero_k_bias"], sdg["v_bias"], q, kc, vc, R, l,
                         L, T, H, cos_attn, sm if cos_attn else None)
         L += l
         assert (kc[:, :, :L].cpu() - cache["k"]).abs().max().item() < 2e-5
@@ -261,7 +261,7 @@ def test_conv2d_with_fused_groupnorm_silu(engine, cin, cout, ks, up, H):
     resid = torch.randn(B, cout, Ho, Wo)
     ref = ref + resid.double()
     x_nhwc = g(x.permute(0, 2, 3, 1))
-    wp = ops.repack_conv_weight(g(w), torch.empty(cout, ks * ks * cin, device=DEV))
+    wp = ops.SplitWeight(ops.repack_conv_weight(g(w), torch.empty(cout, ks * ks * cin, device=DEV)))
     a = torch.empty(B, cin, device=DEV)
     bb = torch.empty(B, cin, device=DEV)
     scratch = torch.empty(2 * B * 32 * ops.gn_chunks(H * Wd), dtype=torch.float64, device=DEV)

@@ -37,12 +37,12 @@ def test_tc_gemm_accuracy(tc, M, N, K):
     A, W, b = torch.randn(M, K), torch.randn(N, K) / math.sqrt(K), torch.randn(N)
     ref = A.double() @ W.double().T + b.double()
     out = torch.empty(M, N, device=DEV)
-    ops.gemm(g(A), g(W), g(b), out, M, N, K)
+    ops.gemm(g(A), ops.SplitWeight(g(W)), g(b), out, M, N, K)
     torch.cuda.synchronize()
     e_tc = err(out.cpu(), ref)
     ops.set_gemm_engine(0)
     out2 = torch.empty(M, N, device=DEV)
-    ops.gemm(g(A), g(W), g(b), out2, M, N, K)
+    ops.gemm(g(A), ops.SplitWeight(g(W)), g(b), out2, M, N, K)
     e_simt = err(out2.cpu(), ref)
     ops.set_gemm_engine(1)
     print(f"\n[tc-accuracy] bk={tc} M={M} N={N} K={K}: 3xTF32 err {e_tc:.3e}   SIMT fp32 err {e_simt:.3e}")
@@ -57,11 +57,11 @@ def test_tc_gemm_epilogues(tc):
     x0, ada = torch.randn(M, C), torch.randn(R, 6 * C)
     ref = x0.double() + (A.double() @ Wt.double().T + b.double()) * ada[:, C:2 * C].double().repeat_interleave(l, 0)
     x, ada_g = g(x0), g(ada)
-    ops.gemm(g(A), g(Wt), g(b), x, M, C, K, epilogue=ops.EPI_BIAS_GAMMA_RESID, gamma=ada_g[:, C:2 * C],
+    ops.gemm(g(A), ops.SplitWeight(g(Wt)), g(b), x, M, C, K, epilogue=ops.EPI_BIAS_GAMMA_RESID, gamma=ada_g[:, C:2 * C],
              gamma_row_stride=6 * C, rows_per_sample=l)
     assert err(x.cpu(), ref) < 1e-5
     out = torch.empty(M, C, device=DEV)
-    ops.gemm(g(A), g(Wt), g(b), out, M, C, K, epilogue=ops.EPI_BIAS_GELU)
+    ops.gemm(g(A), ops.SplitWeight(g(Wt)), g(b), out, M, C, K, epilogue=ops.EPI_BIAS_GELU)
     assert err(out.cpu(), F.gelu(A.double() @ Wt.double().T + b.double(), approximate="tanh")) < 1e-5
 
 
@@ -82,7 +82,7 @@ def test_tc_conv(tc, cin, cout, ks, up, H):
     resid = torch.randn(B, cout, Ho, Wo)
     ref = ref + resid.double()
     x_nhwc = g(x.permute(0, 2, 3, 1))
-    wp = ops.repack_conv_weight(g(w), torch.empty(cout, ks * ks * cin, device=DEV))
+    wp = ops.SplitWeight(ops.repack_conv_weight(g(w), torch.empty(cout, ks * ks * cin, device=DEV)))
     a, bb = torch.empty(B, cin, device=DEV), torch.empty(B, cin, device=DEV)
     scratch = torch.empty(2 * B * 32 * ops.gn_chunks(H * Wd), dtype=torch.float64, device=DEV)
     ops.gn_stats(x_nhwc, g(gam), g(bet), a, bb, scratch, B, H * Wd, cin)
@@ -95,7 +95,7 @@ def test_tc_conv(tc, cin, cout, ks, up, H):
 def test_tc_gemm_throughput(tc):
     """Not a benchmark (bench.py is): a sanity check that the tensor-core engine is far above the SIMT engine."""
     M, N, K = 16384, 1536, 1536
-    A, W, b = torch.randn(M, K, device=DEV), torch.randn(N, K, device=DEV) / 40, torch.randn(N, device=DEV)
+    A, W, b = torch.randn(M, K, device=DEV), ops.SplitWeight(torch.randn(N, K, device=DEV) / 40), torch.randn(N, device=DEV)
     out = torch.empty(M, N, device=DEV)
     res = {}
     for eng in (1, 0):

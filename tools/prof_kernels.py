@@ -12,6 +12,7 @@ from controlvar_b200 import ops  # noqa: E402
 which = sys.argv[1] if len(sys.argv) > 1 else "all"
 engine = int(os.environ.get("CVAR_GEMM_ENGINE", "1"))
 ops.set_gemm_engine(engine)
+ops.set_tc_kblock(int(os.environ.get("CVAR_TC_BK", "32")))
 dev = "cuda"
 torch.manual_seed(0)
 
@@ -31,17 +32,17 @@ def timed(fn, n=3):
 if which in ("gemm", "all"):
     M, N, K = 65536, 6144, 1536            # fc1 of d24 at the last scale (R*l = 128*512 rows)
     A = torch.randn(M, K, device=dev)
-    W = torch.randn(N, K, device=dev) / 40
+    W = ops.SplitWeight(torch.randn(N, K, device=dev) / 40)
     b = torch.randn(N, device=dev)
     out = torch.empty(M, N, device=dev)
     ms = timed(lambda: ops.gemm(A, W, b, out, M, N, K, epilogue=ops.EPI_BIAS_GELU))
     print(f"gemm fc1 M={M} N={N} K={K}: {ms:.3f} ms  {2.0 * M * N * K / ms / 1e9:.1f} TFLOP/s")
-    del A, W, out
+    del A, out
 
 if which in ("conv", "all"):
     B, H, C = 8, 256, 160                  # decoder up.0 ResnetBlock conv at 256x256
     x = torch.randn(B, H, H, C, device=dev)
-    w = torch.randn(C, 9 * C, device=dev) / 38
+    w = ops.SplitWeight(torch.randn(C, 9 * C, device=dev) / 38)
     b = torch.randn(C, device=dev)
     out = torch.empty(B, H, H, C, device=dev)
     ms = timed(lambda: ops.conv2d(x, w, b, out, B, H, H, C, C, 3))

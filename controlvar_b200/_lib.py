@@ -55,11 +55,11 @@ PROTOTYPES = {
     "cvar_prologue": (C.c_int, [c_f, c_f, c_f, c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, c_f, c_f, c_f, C.c_void_p]),
     "cvar_ln_modulate": (C.c_int, [c_f, c_f, c_f, c_ll, c_f, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
     "cvar_gemm": (C.c_int, [C.POINTER(GemmArgs), C.c_void_p]),
-    "cvar_qkv_project": (C.c_int, [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, C.c_int,
-                                   C.c_int, C.c_int, c_f, C.c_void_p]),
+    "cvar_qkv_project": (C.c_int, [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, C.c_int, C.c_int,
+                                   C.c_int, C.c_int, C.c_int, C.c_int, c_f, C.c_void_p]),
     "cvar_split_tf32": (C.c_int, [c_f, c_f, c_f, c_ll, C.c_void_p]),
-    "cvar_attn_kvcache": (C.c_int, [c_f, c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
-                                    C.c_void_p]),
+    "cvar_attn_kvcache": (C.c_int, [c_f, c_f, c_f, c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                    C.c_float, C.c_int, C.c_void_p]),
     "cvar_cfg_sample": (C.c_int, [c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_double,
                                   C.c_void_p]),
     "cvar_vq_step": (C.c_int, [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, C.c_int,

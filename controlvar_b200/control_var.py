@@ -127,6 +127,19 @@ class ControlVAR(nn.Module):
             self._ws[key] = t
         return t[:n].view(shape)
 
+    def _kv_caches(self, depth, R, H, T):
+        """Per-block KV arenas (cached across calls; zero-filled once - every call rewrites the keys it reads)."""
+        key = ("kv", depth, R, H, T)
+        c = self._ws.get(key)
+        if c is None or c[0].k_hi.device != self.device:
+            for k in [k for k in self._ws if isinstance(k, tuple) and k and k[0] == "kv"]:
+                del self._ws[k]
+            n = ops.KVCache.numel(R, H, T)
+            arena = torch.zeros(depth * n, dtype=torch.float32, device=self.device)
+            c = [ops.KVCache(R, H, T, self.device, arena[i * n:(i + 1) * n]) for i in range(depth)]
+            self._ws[key] = c
+        return c
+
     def release_workspace(self):
         """Free the KV arena and activation scratch (they are cached across calls)."""
         self._ws.clear()
@@ -240,8 +253,7 @@ class ControlVAR(nn.Module):
         hid = self._buf("hid", (R * lmax, 4 * C))
         logits = self._buf("logits", (R * lmax, V))
         idx = self._buf("idx", (B * lmax,), torch.int64)
-        kc = self._buf("k_cache", (depth, R, H, T, 64))
-        vc = self._buf("v_cache", (depth, R, H, T, 64))
+        caches = self._kv_caches(depth, R, H, T)
         f_hat = self._buf("f_hat", (B, Cvae, 2 * hw, hw))
         f_hat.zero_()
 
@@ -264,9 +276,9 @@ class ControlVAR(nn.Module):
                 a = ada[bi]                                # (R, 6C): gamma1, gamma2, scale1, scale2, shift1, shift2
                 g1, g2, s1, s2, b1, b2 = (a[:, k * C:(k + 1) * C] for k in range(6))
                 ops.ln_modulate(x, s1, b1, 6 * C, xn, M, C, l, self.norm_eps)
-                ops.qkv_project(xn, blk["qkv_w"], blk["q_bias"], blk["k_bias"], blk["v_bias"], qbuf, kc[bi], vc[bi],
-                                R, l, L_prev, T, H, self.cos_attn, blk["scale_mul"])
-                ops.attn_kvcache(qbuf, kc[bi], vc[bi], attn_o, R, H, l, cur_L, T, attn_scale)
+                ops.qkv_project(xn, blk["qkv_w"], blk["q_bias"], blk["k_bias"], blk["v_bias"], qbuf, caches[bi],
+                                R, l, L_prev, H, self.cos_attn, blk["scale_mul"])
+                ops.attn_kvcache(qbuf, caches[bi], attn_o, R, H, l, cur_L, attn_scale)
                 ops.gemm(attn_o, blk["proj_w"], blk["proj_b"], x, M, C, C,
                          epilogue=ops.EPI_BIAS_GAMMA_RESID, gamma=g1, gamma_row_stride=6 * C, rows_per_sample=l)
                 ops.ln_modulate(x, s2, b2, 6 * C, xn, M, C, l, self.norm_eps)

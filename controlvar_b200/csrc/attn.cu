@@ -3,6 +3,7 @@
 // fp32 flash-style kernel: one CTA = 64 queries of one (row, head); K/V streamed through shared memory in 64-key
 // tiles, online softmax, accumulators in registers.
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 using namespace cvar;
 
@@ -17,16 +18,22 @@ struct AttnSmem {
   float Pt[BKV][PS];    // Pt[j][i]  = exp(s[i][j] - m[i])
 };
 
-__global__ void __launch_bounds__(256) attn_kvcache_kernel(const float* __restrict__ q, const float* __restrict__ kc,
-                                                           const float* __restrict__ vc, float* __restrict__ out,
+__global__ void __launch_bounds__(256) attn_kvcache_kernel(const float* __restrict__ q, const float* __restrict__ k_hi,
+                                                           const float* __restrict__ k_lo,
+                                                           const float* __restrict__ vt_hi,
+                                                           const float* __restrict__ vt_lo, float* __restrict__ out,
                                                            int H, int l, int L, int T_max, float scale) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   AttnSmem& sm = *reinterpret_cast<AttnSmem*>(smem_raw);
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int q0 = blockIdx.x * BQ, h = blockIdx.y, r = blockIdx.z;
   const float* qb = q + (((long long)r * H + h) * l) * D;
-  const float* kb = kc + (((long long)r * H + h) * T_max) * D;
-  const float* vb = vc + (((long long)r * H + h) * T_max) * D;
+  // cache format of cvar_qkv_project: K split hi/lo [rh][T][64] (hi + lo == k exactly), V^T split [rh][64][T]
+  const long long kv_off = (((long long)r * H + h) * T_max) * D;
+  const float* kbh = k_hi + kv_off;
+  const float* kbl = k_lo + kv_off;
+  const float* vbh = vt_hi + kv_off;
+  const float* vbl = vt_lo + kv_off;
 
   // Q tile, transposed into shared memory (lanes walk the query index so the transposing store is conflict-free)
   for (int it = 0; it < 4; ++it) {
@@ -56,7 +63,10 @@ __global__ void __launch_bounds__(256) attn_kvcache_kernel(const float* __restri
       int item = it * 256 + tid;
       int j = item & 63, dq = item >> 6;          // lanes walk the key index: conflict-free transposing store
       float4 kv = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (k0 + j < L) kv = ld4(kb + (long long)(k0 + j) * D + dq * 4);
+      if (k0 + j < L) {
+        float4 a = ld4(kbh + (long long)(k0 + j) * D + dq * 4), b = ld4(kbl + (long long)(k0 + j) * D + dq * 4);
+        kv = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+      }
       sm.Kt[dq * 4 + 0][j] = kv.x;
       sm.Kt[dq * 4 + 1][j] = kv.y;
       sm.Kt[dq * 4 + 2][j] = kv.z;
@@ -64,10 +74,22 @@ __global__ void __launch_bounds__(256) attn_kvcache_kernel(const float* __restri
     }
     for (int it = 0; it < 4; ++it) {
       int item = it * 256 + tid;
-      int j = item >> 4, dq = item & 15;          // lanes walk the head dimension: coalesced, natural layout
-      float4 vv = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (k0 + j < L) vv = ld4(vb + (long long)(k0 + j) * D + dq * 4);
-      *reinterpret_cast<float4*>(&sm.V[j][dq * 4]) = vv;
+      int d = item >> 4, jq = item & 15;          // V^T rows are keys-contiguous: 16 lanes read 64 consecutive keys
+      const long long base = (long long)d * T_max + k0 + jq * 4;
+      float vv[4] = {0.f, 0.f, 0.f, 0.f};
+      if (k0 + jq * 4 + 3 < T_max) {
+        float4 a = ld4(vbh + base), b = ld4(vbl + base);
+        vv[0] = a.x + b.x, vv[1] = a.y + b.y, vv[2] = a.z + b.z, vv[3] = a.w + b.w;
+      } else {
+        for (int i = 0; i < 4; ++i)
+          if (k0 + jq * 4 + i < T_max) vv[i] = vbh[base + i] + vbl[base + i];
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        int j = jq * 4 + i;
+        // 16-byte chunk index XOR-swizzled with the key so the transposing store spreads over banks
+        sm.V[j][(((d >> 2) ^ (j & 15)) << 2) + (d & 3)] = (k0 + j < L) ? vv[i] : 0.f;
+      }
     }
     __syncthreads();
 
@@ -121,7 +143,7 @@ __global__ void __launch_bounds__(256) attn_kvcache_kernel(const float* __restri
 #pragma unroll 8
     for (int j = 0; j < BKV; ++j) {
       float4 a = *reinterpret_cast<const float4*>(&sm.Pt[j][ty * 4]);
-      float4 b = *reinterpret_cast<const float4*>(&sm.V[j][tx * 4]);
+      float4 b = *reinterpret_cast<const float4*>(&sm.V[j][(tx ^ (j & 15)) << 2]);
       o[0][0] = fmaf(a.x, b.x, o[0][0]), o[0][1] = fmaf(a.x, b.y, o[0][1]), o[0][2] = fmaf(a.x, b.z, o[0][2]), o[0][3] = fmaf(a.x, b.w, o[0][3]);
       o[1][0] = fmaf(a.y, b.x, o[1][0]), o[1][1] = fmaf(a.y, b.y, o[1][1]), o[1][2] = fmaf(a.y, b.z, o[1][2]), o[1][3] = fmaf(a.y, b.w, o[1][3]);
       o[2][0] = fmaf(a.z, b.x, o[2][0]), o[2][1] = fmaf(a.z, b.y, o[2][1]), o[2][2] = fmaf(a.z, b.z, o[2][2]), o[2][3] = fmaf(a.z, b.w, o[2][3]);
@@ -142,17 +164,345 @@ __global__ void __launch_bounds__(256) attn_kvcache_kernel(const float* __restri
 }
 }  // namespace
 
-extern "C" int cvar_attn_kvcache(const float* q, const float* k_cache, const float* v_cache, float* out, int R, int H,
-                                 int l, int L, int T_max, float scale, void* stream) {
+
+// =====================================================================================================================
+// Tensor-core path (tcgen05 + TMEM + TMA), fp32-class accuracy through the same 3xTF32 split as the GEMM engine.
+//   CTA = 128 queries of one (row, head); KV streamed in 64-key tiles through a 2-stage TMA ring.  K tiles and V^T tiles
+//   arrive already split hi/lo (cvar_qkv_project wrote them that way), so the kernel does no operand conversion for K/V.
+//   warps 0-3  softmax: thread i owns query row i.  S = Q K^T is read from TMEM (tcgen05.ld), exp'ed, split hi/lo and
+//              written back to TMEM as the A operand of P @ V (tcgen05.st).  The running output row lives in REGISTERS:
+//              every 64-key tile produces a fresh O_tile in TMEM that is added with round-to-nearest fp32 adds, so the
+//              tensor core's round-toward-zero accumulation never runs longer than 8 steps.
+//   warp 4     TMA issue (8 boxes per tile: K_hi, K_lo, V^T_hi, V^T_lo, two 128-byte-wide blocks each)
+//   warp 5     TMEM allocation + MMA issue; S(j+1) is issued before P@V(j) so QK^T of the next tile overlaps softmax(j)
+//   TMEM columns: S_main [0,64) S_lo [64,128) P_hi [128,192) P_lo [192,256) O_tile [256,320)
+namespace tcattn {
+using namespace cvar::tc;
+constexpr int BQ = 128, BKV = 64, D = 64;
+constexpr int kThreads = 192;
+constexpr int kQBlock = BQ * 128;         // bytes of one 32-wide K-block of a Q tile (128 rows x 128 B)
+constexpr int kKVBlock = BKV * 128;       // bytes of one 32-wide K-block of a K / V^T tile (64 rows x 128 B)
+constexpr int kQBytes = 2 * 2 * kQBlock;                 // hi + lo, two d-blocks each       = 64 KiB
+constexpr int kStageBytes = 4 * 2 * kKVBlock;            // K_hi K_lo VT_hi VT_lo, two blocks = 64 KiB
+constexpr int kSmem = kQBytes + 2 * kStageBytes + 1024 + 1024;
+constexpr uint32_t kColSmain = 0, kColSlo = 64, kColPhi = 128, kColPlo = 192, kColO = 256;
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const float* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+      "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+      "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+      "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])),
+      "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])),
+      "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])),
+      "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])),
+      "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__global__ void __launch_bounds__(kThreads, 1)
+attn_tc_kernel(const __grid_constant__ CUtensorMap mapKhi, const __grid_constant__ CUtensorMap mapKlo,
+               const __grid_constant__ CUtensorMap mapVhi, const __grid_constant__ CUtensorMap mapVlo,
+               const float* __restrict__ q, float* __restrict__ out, int H, int l, int L, float scale) {
+  using G = Geo<32>;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* q_hi = smem;                       // [2 blocks][128 rows][128 B]
+  unsigned char* q_lo = smem + 2 * kQBlock;
+  auto stage = [&](int s) { return smem + kQBytes + s * kStageBytes; };   // K_hi | K_lo | VT_hi | VT_lo (2 blocks each)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kQBytes + 2 * kStageBytes);
+  uint64_t* kv_full = bars;          // [2]
+  uint64_t* kv_empty = bars + 2;     // [2]
+  uint64_t* s_full = bars + 4;       // S(j) accumulated
+  uint64_t* s_free = bars + 5;       // S(j) read by all 128 softmax threads
+  uint64_t* p_ready = bars + 6;      // P(j) written to TMEM by all 128 softmax threads
+  uint64_t* o_full = bars + 7;       // O_tile(j) accumulated
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * BQ, h = blockIdx.y, r = blockIdx.z;
+  const long long rh = (long long)r * H + h;
+  const int ntiles = (L + BKV - 1) / BKV;
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&mapKhi), tma_prefetch_desc(&mapKlo), tma_prefetch_desc(&mapVhi), tma_prefetch_desc(&mapVlo);
+    for (int s = 0; s < 2; ++s) mbar_init(&kv_full[s], 1), mbar_init(&kv_empty[s], 1);
+    mbar_init(s_full, 1);
+    mbar_init(s_free, 128);
+    mbar_init(p_ready, 128);
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 5) tmem_alloc(tmem_slot, 512);
+  if (warp < 4) {
+    // Q tile: load, pre-scale, split hi/lo, store K-major 128B-swizzled (two 32-wide d-blocks)
+    const float* qb = q + (rh * l) * D;
+    for (int i = 0; i < 16; ++i) {
+      int item = i * 128 + threadIdx.x;
+      int row = item >> 4, c16 = item & 15;
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (q0 + row < l) x = ld4(qb + (long long)(q0 + row) * D + c16 * 4);
+      x.x *= scale, x.y *= scale, x.z *= scale, x.w *= scale;
+      float4 hv, lv;
+      hv.x = trunc_tf32(x.x), hv.y = trunc_tf32(x.y), hv.z = trunc_tf32(x.z), hv.w = trunc_tf32(x.w);
+      lv.x = x.x - hv.x, lv.y = x.y - hv.y, lv.z = x.z - hv.z, lv.w = x.w - hv.w;
+      uint32_t off = (uint32_t)(c16 >> 3) * kQBlock + G::offset(row, c16 & 7);
+      *reinterpret_cast<float4*>(q_hi + off) = hv;
+      *reinterpret_cast<float4*>(q_lo + off) = lv;
+    }
+    fence_proxy_async();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ================================================================ softmax + output rows
+    const int row = threadIdx.x;
+    const uint32_t tlane = tmem_base + ((uint32_t)(warp * 32) << 16);
+    float o_reg[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) o_reg[d] = 0.f;
+    float m_run = -INFINITY, l_run = 0.f;
+    for (int j = 0; j < ntiles; ++j) {
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      float s[BKV];
+      {
+        float a[32], b[32];
+        tmem_ld_32x32b_x32(tlane + kColSmain, a);
+        tmem_ld_32x32b_x32(tlane + kColSlo, b);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) s[c] = a[c] + b[c];
+        tmem_ld_32x32b_x32(tlane + kColSmain + 32, a);
+        tmem_ld_32x32b_x32(tlane + kColSlo + 32, b);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) s[32 + c] = a[c] + b[c];
+      }
+      tc_fence_before();
+      mbar_arrive(s_free);
+      const int kbase = j * BKV;
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < BKV; ++c) {
+        if (kbase + c >= L) s[c] = -INFINITY;
+        mx = fmaxf(mx, s[c]);
+      }
+      const float m_new = fmaxf(m_run, mx);
+      // expf, not exp2f(x * log2e): the rounding of that product is an ABSOLUTE exponent error of |x| * 2^-24, i.e. a
+      // relative error in p that grows with the logit range (cosine attention multiplies q by up to 100)
+      const float corr = expf(m_run - m_new);                 // 0 on the first tile
+      float rs = 0.f;
+#pragma unroll
+      for (int c = 0; c < BKV; ++c) {
+        s[c] = expf(s[c] - m_new);
+        rs += s[c];
+      }
+      l_run = l_run * corr + rs;
+      m_run = m_new;
+      if (j > 0) {
+        mbar_wait(o_full, (j - 1) & 1);
+        tc_fence_after();
+        float a[32];
+        tmem_ld_32x32b_x32(tlane + kColO, a);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) o_reg[c] = (o_reg[c] + a[c]) * corr;
+        tmem_ld_32x32b_x32(tlane + kColO + 32, a);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) o_reg[32 + c] = (o_reg[32 + c] + a[c]) * corr;
+      }
+      // P(j) -> TMEM as the A operand of P @ V, split hi/lo (P(j-1) was consumed: o_full(j-1) has been observed)
+      {
+        float hi[32], lo[32];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            hi[c] = trunc_tf32(s[half * 32 + c]);
+            lo[c] = s[half * 32 + c] - hi[c];
+          }
+          tmem_st_32x32b_x32(tlane + kColPhi + half * 32, hi);
+          tmem_st_32x32b_x32(tlane + kColPlo + half * 32, lo);
+        }
+        tmem_wait_st();
+      }
+      tc_fence_before();
+      mbar_arrive(p_ready);
+    }
+    mbar_wait(o_full, (ntiles - 1) & 1);
+    tc_fence_after();
+    {
+      float a[32];
+      tmem_ld_32x32b_x32(tlane + kColO, a);
+#pragma unroll
+      for (int c = 0; c < 32; ++c) o_reg[c] += a[c];
+      tmem_ld_32x32b_x32(tlane + kColO + 32, a);
+#pragma unroll
+      for (int c = 0; c < 32; ++c) o_reg[32 + c] += a[c];
+    }
+    const int t = q0 + row;
+    if (t < l) {
+      const float inv = 1.0f / l_run;
+      float* op = out + ((long long)r * l + t) * (H * D) + h * D;
+#pragma unroll
+      for (int d = 0; d < D; d += 4)
+        st4(op + d, make_float4(o_reg[d] * inv, o_reg[d + 1] * inv, o_reg[d + 2] * inv, o_reg[d + 3] * inv));
+    }
+  } else if (warp == 4) {
+    // ================================================================ TMA: K / V^T tiles, pre-split
+    if (lane == 0) {
+      for (int j = 0; j < ntiles; ++j) {
+        const int s = j & 1;
+        mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&kv_full[s], (uint32_t)kStageBytes);
+        unsigned char* st = stage(s);
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          tma_load_3d(&mapKhi, &kv_full[s], st + (0 + b) * kKVBlock, b * 32, j * BKV, (int)rh);
+          tma_load_3d(&mapKlo, &kv_full[s], st + (2 + b) * kKVBlock, b * 32, j * BKV, (int)rh);
+          tma_load_3d(&mapVhi, &kv_full[s], st + (4 + b) * kKVBlock, j * BKV + b * 32, 0, (int)rh);
+          tma_load_3d(&mapVlo, &kv_full[s], st + (6 + b) * kKVBlock, j * BKV + b * 32, 0, (int)rh);
+        }
+      }
+    }
+  } else {
+    // ================================================================ MMA issue
+    if (lane == 0) {
+      auto issue_S = [&](int j) {
+        unsigned char* st = stage(j & 1);
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb) {
+          const uint64_t dqh = G::desc(smem_u32(q_hi + kb * kQBlock)), dql = G::desc(smem_u32(q_lo + kb * kQBlock));
+          const uint64_t dkh = G::desc(smem_u32(st + (0 + kb) * kKVBlock)), dkl = G::desc(smem_u32(st + (2 + kb) * kKVBlock));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t adv = (uint64_t)(2 * k);
+            umma_tf32(tmem_base + kColSlo, dql + adv, dkh + adv, kIdesc, (kb | k) != 0);
+            umma_tf32(tmem_base + kColSlo, dqh + adv, dkl + adv, kIdesc, 1u);
+            umma_tf32(tmem_base + kColSmain, dqh + adv, dkh + adv, kIdesc, (kb | k) != 0);
+          }
+        }
+        umma_commit(s_full);
+      };
+      mbar_wait(&kv_full[0], 0);
+      tc_fence_after();
+      issue_S(0);
+      for (int j = 0; j < ntiles; ++j) {
+        if (j + 1 < ntiles) {
+          mbar_wait(&kv_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
+          mbar_wait(s_free, j & 1);
+          tc_fence_after();
+          issue_S(j + 1);
+        }
+        mbar_wait(p_ready, j & 1);
+        tc_fence_after();
+        unsigned char* st = stage(j & 1);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint64_t adv = (uint64_t)(2 * (k & 3));
+          const uint64_t dvh = G::desc(smem_u32(st + (4 + (k >> 2)) * kKVBlock)) + adv;
+          const uint64_t dvl = G::desc(smem_u32(st + (6 + (k >> 2)) * kKVBlock)) + adv;
+          umma_tf32_ts(tmem_base + kColO, tmem_base + kColPlo + 8 * k, dvh, kIdesc, k != 0);
+          umma_tf32_ts(tmem_base + kColO, tmem_base + kColPhi + 8 * k, dvl, kIdesc, 1u);
+          umma_tf32_ts(tmem_base + kColO, tmem_base + kColPhi + 8 * k, dvh, kIdesc, 1u);
+        }
+        umma_commit(o_full);
+        umma_commit(&kv_empty[j & 1]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc(tmem_base, 512);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+// 3-D map over a cache array: dims (inner, mid, RH) with a (32, 64, 1) box and 128-byte swizzle
+static int make_map3(CUtensorMap* map, const float* base, long long inner, long long mid, long long rh) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("cvar_attn_kvcache: cuTensorMapEncodeTiled is not available from the driver");
+    return -3;
+  }
+  cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)mid, (cuuint64_t)rh};
+  cuuint64_t strides[2] = {(cuuint64_t)inner * 4, (cuuint64_t)inner * mid * 4};
+  cuuint32_t box[3] = {32, 64, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult rc = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) {
+    set_error("cvar_attn_kvcache: cuTensorMapEncodeTiled failed with %d", (int)rc);
+    return -3;
+  }
+  return 0;
+}
+}  // namespace tcattn
+
+extern "C" int cvar_attn_kvcache(const float* q, const float* k_hi, const float* k_lo, const float* vt_hi,
+                                 const float* vt_lo, float* out, int R, int H, int l, int L, int T_max, float scale,
+                                 int engine, void* stream) {
   CVAR_REQUIRE(R > 0 && H > 0 && l > 0 && L >= l && L <= T_max, "cvar_attn_kvcache: bad shape l=%d L=%d T=%d", l, L,
                T_max);
   CVAR_REQUIRE(R <= 65535 && H <= 65535, "cvar_attn_kvcache: grid too large");
+  CVAR_REQUIRE(T_max % 4 == 0, "cvar_attn_kvcache: T_max must be a multiple of 4 (got %d)", T_max);
+  if (engine < 0) engine = (g_gemm_engine != 0 && l >= 64) ? 1 : 0;
+  if (engine == 1) {
+    CUtensorMap mkh, mkl, mvh, mvl;
+    const long long RH = (long long)R * H;
+    int rc = tcattn::make_map3(&mkh, k_hi, 64, T_max, RH);
+    if (!rc) rc = tcattn::make_map3(&mkl, k_lo, 64, T_max, RH);
+    if (!rc) rc = tcattn::make_map3(&mvh, vt_hi, T_max, 64, RH);
+    if (!rc) rc = tcattn::make_map3(&mvl, vt_lo, T_max, 64, RH);
+    if (rc) return rc;
+    cudaError_t e = cudaFuncSetAttribute(tcattn::attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         tcattn::kSmem);
+    CVAR_REQUIRE(e == cudaSuccess, "cvar_attn_kvcache: cannot raise shared memory: %s", cudaGetErrorString(e));
+    dim3 grid(cdiv(l, tcattn::BQ), H, R);
+    tcattn::attn_tc_kernel<<<grid, tcattn::kThreads, tcattn::kSmem, (cudaStream_t)stream>>>(mkh, mkl, mvh, mvl, q, out, H,
+                                                                                          l, L, scale);
+    CVAR_CHECK_LAUNCH("cvar_attn_kvcache[tc]");
+    return 0;
+  }
   cudaError_t e = cudaFuncSetAttribute(attn_kvcache_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)sizeof(AttnSmem));
   CVAR_REQUIRE(e == cudaSuccess, "cvar_attn_kvcache: cannot raise shared memory: %s", cudaGetErrorString(e));
   dim3 grid(cdiv(l, BQ), H, R);
-  attn_kvcache_kernel<<<grid, 256, sizeof(AttnSmem), (cudaStream_t)stream>>>(q, k_cache, v_cache, out, H, l, L, T_max,
-                                                                            scale);
+  attn_kvcache_kernel<<<grid, 256, sizeof(AttnSmem), (cudaStream_t)stream>>>(q, k_hi, k_lo, vt_hi, vt_lo, out, H, l, L,
+                                                                            T_max, scale);
   CVAR_CHECK_LAUNCH("cvar_attn_kvcache");
   return 0;
 }

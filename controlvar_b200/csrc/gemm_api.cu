@@ -38,9 +38,10 @@ extern "C" int cvar_gemm(const cvar_gemm_args* a, void* stream) {
 }
 
 // F.normalize(q).mul(scale_mul), F.normalize(k)                                         basic_var.py:99-104
-__global__ void cos_attn_normalize_kernel(float* __restrict__ q, float* __restrict__ kc, const float* __restrict__ sm,
-                                          int R, int H, int l, int L_prev, int T_max) {
+__global__ void cos_attn_normalize_kernel(float* __restrict__ q, float* __restrict__ k_hi, float* __restrict__ k_lo,
+                                          const float* __restrict__ sm, int R, int H, int l, int L_prev, int T_max) {
   // one warp per 64-float head row; rows [0, R*H*l) are q rows, the next R*H*l are the freshly appended k rows
+  // (stored split: k = hi + lo exactly; normalise the sum, split again)
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   long long row = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
   long long nq = (long long)R * H * l;
@@ -50,8 +51,14 @@ __global__ void cos_attn_normalize_kernel(float* __restrict__ q, float* __restri
   int t = (int)(i % l);
   long long rh = i / l;
   int h = (int)(rh % H);
-  float* p = is_q ? q + i * 64 : kc + (rh * T_max + L_prev + t) * 64;
-  float2 v = *reinterpret_cast<float2*>(p + lane * 2);
+  long long off = is_q ? i * 64 : (rh * T_max + L_prev + t) * 64;
+  float2 v;
+  if (is_q) {
+    v = *reinterpret_cast<float2*>(q + off + lane * 2);
+  } else {
+    float2 a = *reinterpret_cast<float2*>(k_hi + off + lane * 2), b = *reinterpret_cast<float2*>(k_lo + off + lane * 2);
+    v = make_float2(a.x + b.x, a.y + b.y);
+  }
   float ss = warp_sum(v.x * v.x + v.y * v.y);
   float denom = fmaxf(sqrtf(ss), 1e-12f);
   v.x = v.x / denom;
@@ -60,18 +67,24 @@ __global__ void cos_attn_normalize_kernel(float* __restrict__ q, float* __restri
     float mul = expf(fminf(sm[h], 4.605170185988092f));   // clamp_max(log(100)).exp()
     v.x = __fmul_rn(v.x, mul);
     v.y = __fmul_rn(v.y, mul);
+    *reinterpret_cast<float2*>(q + off + lane * 2) = v;
+  } else {
+    float2 hi = make_float2(__uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u),
+                            __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u));
+    *reinterpret_cast<float2*>(k_hi + off + lane * 2) = hi;
+    *reinterpret_cast<float2*>(k_lo + off + lane * 2) = make_float2(v.x - hi.x, v.y - hi.y);
   }
-  *reinterpret_cast<float2*>(p + lane * 2) = v;
 }
 
 extern "C" int cvar_qkv_project(const float* A, const float* Wqkv, const float* Wqkv_hi, const float* Wqkv_lo,
-                                const float* q_bias, const float* k_bias, const float* v_bias, float* q_out, float* k_cache, float* v_cache, int R, int l,
-                                int L_prev, int T_max, int H, int cos_attn, const float* scale_mul_H, void* stream) {
+                                const float* q_bias, const float* k_bias, const float* v_bias, float* q_out,
+                                float* k_hi, float* k_lo, float* vt_hi, float* vt_lo, int R, int l, int L_prev,
+                                int T_max, int H, int cos_attn, const float* scale_mul_H, void* stream) {
   CVAR_REQUIRE(R > 0 && l > 0 && H > 0 && L_prev >= 0 && L_prev + l <= T_max, "cvar_qkv_project: bad shape");
   CVAR_REQUIRE(!cos_attn || scale_mul_H != nullptr, "cvar_qkv_project: cosine attention needs scale_mul");
   cudaStream_t s = (cudaStream_t)stream;
   const int C = H * 64, M = R * l;
-  QkvEpilogue ep{q_bias, k_bias, v_bias, q_out, k_cache, v_cache, C, H, l, L_prev, T_max};
+  QkvEpilogue ep{q_bias, k_bias, v_bias, q_out, k_hi, k_lo, vt_hi, vt_lo, C, H, l, L_prev, T_max};
   int took = 0;
   if (g_gemm_engine != 0 && Wqkv_hi != nullptr && Wqkv_lo != nullptr) {
     took = tc_qkv_try(A, Wqkv_hi, Wqkv_lo, ep, M, C, s);
@@ -85,7 +98,7 @@ extern "C" int cvar_qkv_project(const float* A, const float* Wqkv, const float* 
   }
   if (cos_attn) {
     long long rows = 2LL * R * H * l;
-    cos_attn_normalize_kernel<<<cdiv(rows, 8), 256, 0, s>>>(q_out, k_cache, scale_mul_H, R, H, l, L_prev, T_max);
+    cos_attn_normalize_kernel<<<cdiv(rows, 8), 256, 0, s>>>(q_out, k_hi, k_lo, scale_mul_H, R, H, l, L_prev, T_max);
     CVAR_CHECK_LAUNCH("cvar_qkv_project/cos_normalize");
   }
   return 0;

@@ -222,8 +222,13 @@ struct QkvEpilogue {
   const float* k_bias;
   const float* v_bias;
   float* q_out;
-  float* k_cache;
-  float* v_cache;
+  // KV cache in the operand format of the tensor-core attention kernel (split once here, consumed by TMA there):
+  //   K   : k_hi / k_lo   [R*H][T_max][64]   (TF32 hi/lo split, hi + lo == k exactly)
+  //   V^T : vt_hi / vt_lo [R*H][64][T_max]   (transposed so that keys are the contiguous, K-major dimension of P @ V)
+  float* k_hi;
+  float* k_lo;
+  float* vt_hi;
+  float* vt_lo;
   int C, H, l, L_prev, T_max;
   __device__ __forceinline__ void store(long long m, int n, const float* v, int nvalid, int /*batch*/) const {
     int which = n / C;
@@ -231,17 +236,32 @@ struct QkvEpilogue {
     int h = c >> 6, d = c & 63;
     int r = (int)(m / l), t = (int)(m - (long long)r * l);
     const float* bias = which == 0 ? q_bias : (which == 1 ? k_bias : v_bias);
-    float4 o;
-    o.x = __fadd_rn(v[0], bias[c + 0]);
-    o.y = __fadd_rn(v[1], bias[c + 1]);
-    o.z = __fadd_rn(v[2], bias[c + 2]);
-    o.w = __fadd_rn(v[3], bias[c + 3]);
-    float* dst;
-    if (which == 0)
-      dst = q_out + (((long long)r * H + h) * l + t) * 64 + d;
-    else
-      dst = (which == 1 ? k_cache : v_cache) + (((long long)r * H + h) * T_max + L_prev + t) * 64 + d;
-    st4(dst, o);
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j] = __fadd_rn(v[j], bias[c + j]);
+    const long long rh = (long long)r * H + h;
+    if (which == 0) {
+      st4(q_out + ((rh * l + t) << 6) + d, make_float4(o[0], o[1], o[2], o[3]));
+    } else {
+      float hi[4], lo[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        hi[j] = __uint_as_float(__float_as_uint(o[j]) & 0xFFFFE000u);
+        lo[j] = o[j] - hi[j];
+      }
+      if (which == 1) {
+        const long long off = ((rh * T_max + L_prev + t) << 6) + d;
+        st4(k_hi + off, make_float4(hi[0], hi[1], hi[2], hi[3]));
+        st4(k_lo + off, make_float4(lo[0], lo[1], lo[2], lo[3]));
+      } else {
+        const long long off = (rh * 64 + d) * T_max + L_prev + t;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          vt_hi[off + (long long)j * T_max] = hi[j];
+          vt_lo[off + (long long)j * T_max] = lo[j];
+        }
+      }
+    }
     (void)nvalid;
   }
 };

@@ -153,23 +153,49 @@ def gemm(A, W, bias, out, M, N, K, *, lda=None, ldw=None, ldo=None, epilogue=EPI
     return out
 
 
-def qkv_project(A, Wqkv, q_bias, k_bias, v_bias, q_out, k_cache, v_cache, R, l, L_prev, T_max, H, cos_attn,
-                scale_mul_H):
+class KVCache:
+    """KV arena of one transformer block in the operand format of the tensor-core attention kernel:
+    K split hi/lo (R, H, T, 64) and V transposed + split (R, H, 64, T); T padded to a multiple of 4; zero-initialised
+    once (stale tail keys are masked but must be finite).  Replaces the reference's torch.cat growth (basic_var.py:106-108)."""
+    __slots__ = ("k_hi", "k_lo", "vt_hi", "vt_lo", "R", "H", "T")
+
+    def __init__(self, R: int, H: int, T: int, device, storage: Optional[torch.Tensor] = None):
+        self.R, self.H, self.T = R, H, (T + 3) // 4 * 4
+        n = R * H * self.T * 64
+        if storage is None:
+            storage = torch.zeros(4 * n, dtype=torch.float32, device=device)
+        self.k_hi, self.k_lo, self.vt_hi, self.vt_lo = (storage[i * n:(i + 1) * n] for i in range(4))
+
+    @staticmethod
+    def numel(R: int, H: int, T: int) -> int:
+        return 4 * R * H * ((T + 3) // 4 * 4) * 64
+
+    def keys(self, L: int) -> torch.Tensor:
+        """(R, H, L, 64) view of the cached keys (hi + lo), for tests / debugging."""
+        return (self.k_hi + self.k_lo).view(self.R, self.H, self.T, 64)[:, :, :L]
+
+    def values(self, L: int) -> torch.Tensor:
+        return (self.vt_hi + self.vt_lo).view(self.R, self.H, 64, self.T)[:, :, :, :L].transpose(2, 3)
+
+
+def qkv_project(A, Wqkv, q_bias, k_bias, v_bias, q_out, cache: KVCache, R, l, L_prev, H, cos_attn, scale_mul_H):
     Wqkv, W_hi, W_lo = _wparts(Wqkv)
-    _chk(A, Wqkv, q_bias, k_bias, v_bias, q_out, k_cache, v_cache, scale_mul_H)
+    _chk(A, Wqkv, q_bias, k_bias, v_bias, q_out, cache.k_hi, scale_mul_H)
     Cd = H * 64
     with _Timed("gemm", 2.0 * R * l * 3 * Cd * Cd, 4.0 * (R * l * Cd + 3 * Cd * Cd + R * l * 3 * Cd)):
-        check(_lib.load().cvar_qkv_project(_p(A), _p(Wqkv), _p(W_hi), _p(W_lo), _p(q_bias), _p(k_bias), _p(v_bias), _p(q_out), _p(k_cache),
-                                           _p(v_cache), R, l, L_prev, T_max, H, int(cos_attn), _p(scale_mul_H),
-                                           _stream()), "cvar_qkv_project")
+        check(_lib.load().cvar_qkv_project(_p(A), _p(Wqkv), _p(W_hi), _p(W_lo), _p(q_bias), _p(k_bias), _p(v_bias),
+                                           _p(q_out), _p(cache.k_hi), _p(cache.k_lo), _p(cache.vt_hi), _p(cache.vt_lo),
+                                           R, l, L_prev, cache.T, H, int(cos_attn), _p(scale_mul_H), _stream()),
+              "cvar_qkv_project")
 
 
-def attn_kvcache(q, k_cache, v_cache, out, R, H, l, L, T_max, scale):
-    _chk(q, k_cache, v_cache, out)
+def attn_kvcache(q, cache: KVCache, out, R, H, l, L, scale, engine: int = -1):
+    _chk(q, cache.k_hi, out)
     # algorithmic work of SURVEY.md section 8d: 4*l*L*64 flop and (2l + 2L)*64*4 bytes per (row, head)
     with _Timed("attn", 4.0 * l * L * 64 * R * H, (2.0 * l + 2.0 * L) * 64 * 4 * R * H):
-        check(_lib.load().cvar_attn_kvcache(_p(q), _p(k_cache), _p(v_cache), _p(out), R, H, l, L, T_max, float(scale),
-                                            _stream()), "cvar_attn_kvcache")
+        check(_lib.load().cvar_attn_kvcache(_p(q), _p(cache.k_hi), _p(cache.k_lo), _p(cache.vt_hi), _p(cache.vt_lo),
+                                            _p(out), R, H, l, L, cache.T, float(scale), int(engine), _stream()),
+              "cvar_attn_kvcache")
     return out
 
 

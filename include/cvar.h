@@ -91,21 +91,27 @@ CVAR_API int cvar_gemm(const cvar_gemm_args* args, void* stream);
 
 /* ---- QKV projection fused with the KV-cache append: basic_var.py:92-108 ------------------------------------
  * qkv = A[M,C] @ Wqkv[3C,C]^T + [q_bias, k_bias, v_bias];  M = R*l, row m = r*l + t.
- * q  -> q_out[r, h, t, :]                    (R, H, l, 64)
- * k,v-> k_cache/v_cache[r, h, L_prev + t, :] (R, H, T_max, 64): in-place replacement of the torch.cat growth.
- * cos_attn != 0 (depth 30, basic_var.py:99-104): q = normalize(q) * exp(min(scale_mul[h], ln 100)), k = normalize(k). */
+ * q  -> q_out[r, h, t, :]                         (R, H, l, 64)
+ * k  -> k_hi / k_lo[r, h, L_prev + t, :]          (R, H, T_max, 64)   TF32 split, k_hi + k_lo == k exactly
+ * v  -> vt_hi / vt_lo[r, h, :, L_prev + t]        (R, H, 64, T_max)   same split, stored TRANSPOSED (keys contiguous)
+ * This is the in-place replacement of the reference's torch.cat cache growth; the split / transposed layout is the
+ * operand format of the tensor-core attention kernel (K tiles and V^T tiles are fetched by TMA as they are).
+ * T_max must be a multiple of 4.  The caller zero-initialises the cache once (stale tail keys are masked, but must be
+ * finite).  cos_attn != 0 (depth 30, basic_var.py:99-104): q = normalize(q) * exp(min(scale_mul[h], ln 100)),
+ * k = normalize(k). */
 CVAR_API int cvar_qkv_project(const float* A, const float* Wqkv, const float* Wqkv_hi, const float* Wqkv_lo,
                      const float* q_bias, const float* k_bias, const float* v_bias,
-                     float* q_out, float* k_cache, float* v_cache,
+                     float* q_out, float* k_hi, float* k_lo, float* vt_hi, float* vt_lo,
                      int R, int l, int L_prev, int T_max, int H, int cos_attn, const float* scale_mul_H,
                      void* stream);
 
 /* ---- KV-cached attention: F.scaled_dot_product_attention at basic_var.py:117 --------------------------------
  * out[r, t, h*64:(h+1)*64] = softmax(q[r,h,t,:] . K[r,h,0:L,:]^T * scale) @ V[r,h,0:L,:]
- * q (R,H,l,64); caches (R,H,T_max,64); out (R,l,H*64) - the layout proj consumes.  No mask: the cache holds exactly
- * the keys of scales <= current, which is the block-causal pattern of control_var.py:168. */
-CVAR_API int cvar_attn_kvcache(const float* q, const float* k_cache, const float* v_cache, float* out,
-                      int R, int H, int l, int L, int T_max, float scale, void* stream);
+ * q (R,H,l,64); cache arrays as written by cvar_qkv_project; out (R,l,H*64) - the layout proj consumes.  No mask: the
+ * cache holds exactly the keys of scales <= current, which is the block-causal pattern of control_var.py:168.
+ * engine: -1 = library default (tensor cores when l >= 64), 0 = SIMT fp32, 1 = tcgen05 3xTF32. */
+CVAR_API int cvar_attn_kvcache(const float* q, const float* k_hi, const float* k_lo, const float* vt_hi, const float* vt_lo,
+                      float* out, int R, int H, int l, int L, int T_max, float scale, int engine, void* stream);
 
 /* ---- CFG + top-k/top-p + multinomial(1): control_var.py:501-505, helpers.py:6-19 -----------------------------
  * logits (2B, l, V): rows [0,B) conditional, [B,2B) unconditional.  v = (1+t)*lc - t*lu; top-k keeps v >= k-th

@@ -144,23 +144,32 @@ def test_qkv_project_and_kvcache_attention(engine, cos_attn):
           "scale_mul_1H11": torch.tensor([1.0, 1.386, 3.0, 5.0]).view(1, H, 1, 1)}
     scale = 1.0 if cos_attn else 0.25 / math.sqrt(64)
     cache = {}
-    kc = torch.zeros(R, H, T, 64, device=DEV)
-    vc = torch.zeros(R, H, T, 64, device=DEV)
+    kv = ops.KVCache(R, H, T, DEV)
     sdg = {k: g(v) for k, v in sd.items()}
     sm = sdg["scale_mul_1H11"].reshape(-1).contiguous()
+    wq = ops.SplitWeight(sdg["mat_qkv.weight"])
     L = 0
     for l in (2, 50, 130):
         x = torch.randn(R, l, C)
         ref = O.self_attention(x, sd, "", H, cache, cos_attn, scale)      # proj is the identity here
         q = torch.empty(R, H, l, 64, device=DEV)
-        ops.qkv_project(g(x), ops.SplitWeight(sdg["mat_qkv.weight"]), sdg["q_bias"], sdg["zero_k_bias"], sdg["v_bias"], q, kc, vc, R, l,
-                        L, T, H, cos_attn, sm if cos_attn else None)
+        ops.qkv_project(g(x), wq, sdg["q_bias"], sdg["zero_k_bias"], sdg["v_bias"], q, kv, R, l, L, H, cos_attn,
+                        sm if cos_attn else None)
         L += l
-        assert (kc[:, :, :L].cpu() - cache["k"]).abs().max().item() < 2e-5
-        assert (vc[:, :, :L].cpu() - cache["v"]).abs().max().item() < 2e-5
-        out = torch.empty(R, l, C, device=DEV)
-        ops.attn_kvcache(q, kc, vc, out, R, H, l, L, T, scale)
-        assert (out.cpu() - ref).abs().max().item() < 3e-5, f"l={l} L={L}"
+        assert (kv.keys(L).cpu() - cache["k"]).abs().max().item() < 2e-5
+        assert (kv.values(L).cpu() - cache["v"]).abs().max().item() < 2e-5
+        # Tolerance scales with the logit range.  Attention output error is ~ max|S| x (relative error of q, k): measured on
+        # B200 (tools/diag_cos_attn.py, profiles/r01_cos_attn_error.md) the all-SIMT path gives 2e-7 / 2e-6 / 1e-5 for
+        # heads with max|S| = 1.4 / 10 / 51, i.e. fp32 resolution of the logit itself.  Cosine attention multiplies q by
+        # up to 100 (basic_var.py:100), so a flat absolute bound is wrong for it.  Both attention engines are within
+        # 1.1x of each other on identical inputs; the tcgen05 GEMM's q is ~4.5x less accurate than the SIMT GEMM's.
+        s_max = (q.double().cpu() @ kv.keys(L).double().cpu().transpose(-1, -2)).abs().max().item() * scale
+        tol = max(3e-5, 1.5e-6 * s_max)
+        for eng in ((0, 1) if l >= 50 else (0,)):
+            out = torch.empty(R, l, C, device=DEV)
+            ops.attn_kvcache(q, kv, out, R, H, l, L, scale, engine=eng)
+            err = (out.cpu() - ref).abs().max().item()
+            assert err < tol, f"l={l} L={L} engine={eng}: {err:.3e} (max|S| {s_max:.1f}, tol {tol:.1e})"
 
 
 # ---------------------------------------------------------------------------------------------- sampling

@@ -52,10 +52,15 @@ if which in ("conv", "all"):
 if which in ("attn", "all"):
     R, Hh, l, L, T = 128, 24, 512, 1360, 1360
     q = torch.randn(R, Hh, l, 64, device=dev)
-    kc = torch.randn(R, Hh, T, 64, device=dev)
-    vc = torch.randn(R, Hh, T, 64, device=dev)
+    kv = ops.KVCache(R, Hh, T, dev)
+    for t in (kv.k_hi, kv.vt_hi):
+        t.normal_()
+        t.copy_(t.view(torch.int32).bitwise_and_(-8192).view(torch.float32))
+    for t in (kv.k_lo, kv.vt_lo):
+        t.normal_().mul_(2.0 ** -12)
     out = torch.empty(R, l, Hh * 64, device=dev)
-    ms = timed(lambda: ops.attn_kvcache(q, kc, vc, out, R, Hh, l, L, T, 1 / 32))
     fl = 4.0 * l * L * 64 * R * Hh
     by = (2.0 * l + 2.0 * L) * 64 * 4 * R * Hh
-    print(f"attn R={R} H={Hh} l={l} L={L}: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s  {by / ms / 1e6:.0f} GB/s algorithmic")
+    for eng in (1, 0):
+        ms = timed(lambda: ops.attn_kvcache(q, kv, out, R, Hh, l, L, 1 / 32, engine=eng))
+        print(f"attn engine={eng} R={R} H={Hh} l={l} L={L}: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s  {by / ms / 1e6:.0f} GB/s algorithmic")

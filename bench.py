@@ -216,8 +216,10 @@ def main_ours(args, wl):
         n0 = ops.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        torch.cuda.nvtx.range_push("bench_step")     # lets `ncu --nvtx --nvtx-include "bench_step/"` scope a launch list
         for i in range(steps):
             fn(first_it + i)
+        torch.cuda.nvtx.range_pop()
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -250,10 +252,17 @@ def main_ours(args, wl):
         dom = max(classes, key=lambda k: classes[k]["ms"])
         d = classes[dom]
         ach_tf = d["work"] / (d["ms"] / 1e3) / 1e12
+        traffic = {}
+        tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.exists(tp):        # ncu --set full figure of ONE representative launch (the class mixes many shapes)
+            tj = json.load(open(tp))
+            traffic = {"traffic": tj["traffic"], "note": f"dram read+write of one launch ({tj['launch']}), algorithmic "
+                                                         f"{tj['algorithmic_bytes']} B; {tj['source']}"}
         roof = {"kernel": {"gemm": "dense-layer GEMM (cvar_gemm / cvar_qkv_project)", "conv": "decoder implicit-GEMM conv (cvar_conv2d)",
                            "attn": "KV-cached attention (cvar_attn_kvcache)"}[dom],
                 "bound": "tensor", "achieved": ach_tf, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": ach_tf / pk["tf_sust"],
-                "traffic": None, "peak_source": pk["src"] + ", sustained bf16 (kernel timed inside a long step)",
+                "traffic": traffic.get("traffic") if dom == "gemm" else None, "traffic_note": traffic.get("note"),
+                "peak_source": pk["src"] + ", sustained bf16 (kernel timed inside a long step)",
                 "launches": d["launches"], "avg_launch_ms": d["ms"] / d["launches"],
                 "share_of_step": d["ms"] / ms_total}
         kernels = {}
@@ -297,7 +306,7 @@ if __name__ == "__main__":
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="d24_b64", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch of the workload")
-    ap.add_argument("--engine", type=int, default=int(os.environ.get("CVAR_GEMM_ENGINE", "0")),
+    ap.add_argument("--engine", type=int, default=int(os.environ.get("CVAR_GEMM_ENGINE", "1")),
                     help="0 simt fp32, 1 tcgen05 3xTF32, 2 tcgen05 bf16")
     ap.add_argument("--cpu-sample-batch", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")

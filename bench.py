@@ -115,8 +115,9 @@ def run_cpu_port(depth, B_sample, cond, cfg_scale, steps, warmup, threads=None):
     from controlvar_b200.config import PathConfig
     from controlvar_b200 import weights as W
     from oracle import controlvar_oracle as O
-    if threads:
-        torch.set_num_threads(threads)
+    # all host cores, explicitly: torchrun exports OMP_NUM_THREADS=1, which would silently make the reference arm
+    # single-threaded (and ~16x slower) in every N > 1 launch                                   BASELINE.md section 5
+    torch.set_num_threads(threads or os.cpu_count())
     cfgp = PathConfig(depth=depth)
     dev = "cuda" if torch.cuda.is_available() else None       # weight generation only (bit-identical on any device)
     sd = {k: v.cpu() for k, v in W.synthetic_var_state_dict(cfgp, 0, device=dev).items()}

@@ -19,6 +19,7 @@ c_ll = C.c_longlong
 class GemmArgs(C.Structure):
     _fields_ = [
         ("A", C.c_void_p), ("lda", c_ll), ("strideA", c_ll),
+        ("A_lo", C.c_void_p),
         ("W", C.c_void_p), ("ldw", c_ll), ("strideW", c_ll), ("w_is_kn", C.c_int),
         ("W_hi", C.c_void_p), ("W_lo", C.c_void_p),
         ("bias", C.c_void_p),
@@ -27,6 +28,7 @@ class GemmArgs(C.Structure):
         ("epilogue", C.c_int), ("alpha", C.c_float),
         ("gamma", C.c_void_p), ("gamma_row_stride", c_ll), ("rows_per_sample", C.c_int),
         ("resid", C.c_void_p), ("ldr", c_ll), ("strideR", c_ll),
+        ("out_lo", C.c_void_p),
     ]
 
 
@@ -53,12 +55,12 @@ PROTOTYPES = {
     "cvar_debug_set_trace": (C.c_int, [C.c_void_p]),
     "cvar_lvl_pos": (C.c_int, [c_f, c_f, c_f, c_f, C.c_int, C.c_int, C.c_void_p]),
     "cvar_prologue": (C.c_int, [c_f, c_f, c_f, c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, c_f, c_f, c_f, C.c_void_p]),
-    "cvar_ln_modulate": (C.c_int, [c_f, c_f, c_f, c_ll, c_f, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
+    "cvar_ln_modulate": (C.c_int, [c_f, c_f, c_f, c_ll, c_f, c_f, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
     "cvar_gemm": (C.c_int, [C.POINTER(GemmArgs), C.c_void_p]),
-    "cvar_qkv_project": (C.c_int, [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, C.c_int, C.c_int,
+    "cvar_qkv_project": (C.c_int, [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, C.c_int, C.c_int,
                                    C.c_int, C.c_int, C.c_int, C.c_int, c_f, C.c_void_p]),
     "cvar_split_tf32": (C.c_int, [c_f, c_f, c_f, c_ll, C.c_void_p]),
-    "cvar_attn_kvcache": (C.c_int, [c_f, c_f, c_f, c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+    "cvar_attn_kvcache": (C.c_int, [c_f, c_f, c_f, c_f, c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                     C.c_float, C.c_int, C.c_void_p]),
     "cvar_cfg_sample": (C.c_int, [c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_double,
                                   C.c_void_p]),

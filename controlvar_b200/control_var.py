@@ -251,6 +251,11 @@ class ControlVAR(nn.Module):
         attn_o = self._buf("attn_o", (R * lmax, C))
         qbuf = self._buf("q", (R * H * lmax * 64,))
         hid = self._buf("hid", (R * lmax, 4 * C))
+        # engine 3 (2-CTA all-TMA GEMM): every GEMM input is produced already split hi/lo; the '*_lo' halves live here
+        split = ops.get_gemm_engine() == ops.ENGINE_TC_2CTA
+        xn_lo = self._buf("xn_lo", (R * lmax, C)) if split else None
+        attn_o_lo = self._buf("attn_o_lo", (R * lmax, C)) if split else None
+        hid_lo = self._buf("hid_lo", (R * lmax, 4 * C)) if split else None
         logits = self._buf("logits", (R * lmax, V))
         idx = self._buf("idx", (B * lmax,), torch.int64)
         caches = self._kv_caches(depth, R, H, T)
@@ -275,19 +280,20 @@ class ControlVAR(nn.Module):
             for bi, blk in enumerate(cst["blocks"]):
                 a = ada[bi]                                # (R, 6C): gamma1, gamma2, scale1, scale2, shift1, shift2
                 g1, g2, s1, s2, b1, b2 = (a[:, k * C:(k + 1) * C] for k in range(6))
-                ops.ln_modulate(x, s1, b1, 6 * C, xn, M, C, l, self.norm_eps)
+                ops.ln_modulate(x, s1, b1, 6 * C, xn, M, C, l, self.norm_eps, out_lo=xn_lo)
                 ops.qkv_project(xn, blk["qkv_w"], blk["q_bias"], blk["k_bias"], blk["v_bias"], qbuf, caches[bi],
-                                R, l, L_prev, H, self.cos_attn, blk["scale_mul"])
-                ops.attn_kvcache(qbuf, caches[bi], attn_o, R, H, l, cur_L, attn_scale)
-                ops.gemm(attn_o, blk["proj_w"], blk["proj_b"], x, M, C, C,
+                                R, l, L_prev, H, self.cos_attn, blk["scale_mul"], A_lo=xn_lo)
+                ops.attn_kvcache(qbuf, caches[bi], attn_o, R, H, l, cur_L, attn_scale, out_lo=attn_o_lo)
+                ops.gemm(attn_o, blk["proj_w"], blk["proj_b"], x, M, C, C, A_lo=attn_o_lo,
                          epilogue=ops.EPI_BIAS_GAMMA_RESID, gamma=g1, gamma_row_stride=6 * C, rows_per_sample=l)
-                ops.ln_modulate(x, s2, b2, 6 * C, xn, M, C, l, self.norm_eps)
-                ops.gemm(xn, blk["fc1_w"], blk["fc1_b"], hid, M, 4 * C, C, epilogue=ops.EPI_BIAS_GELU)
-                ops.gemm(hid, blk["fc2_w"], blk["fc2_b"], x, M, C, 4 * C,
+                ops.ln_modulate(x, s2, b2, 6 * C, xn, M, C, l, self.norm_eps, out_lo=xn_lo)
+                ops.gemm(xn, blk["fc1_w"], blk["fc1_b"], hid, M, 4 * C, C, epilogue=ops.EPI_BIAS_GELU, A_lo=xn_lo,
+                         out_lo=hid_lo)
+                ops.gemm(hid, blk["fc2_w"], blk["fc2_b"], x, M, C, 4 * C, A_lo=hid_lo,
                          epilogue=ops.EPI_BIAS_GAMMA_RESID, gamma=g2, gamma_row_stride=6 * C, rows_per_sample=l)
             # head: AdaLNBeforeHead + Linear(C, V)
-            ops.ln_modulate(x, ada_head[:, :C], ada_head[:, C:], 2 * C, xn, M, C, l, self.norm_eps)
-            ops.gemm(xn, cst["head_w"], self.get_parameter("head.bias"), logits, M, V, C)
+            ops.ln_modulate(x, ada_head[:, :C], ada_head[:, C:], 2 * C, xn, M, C, l, self.norm_eps, out_lo=xn_lo)
+            ops.gemm(xn, cst["head_w"], self.get_parameter("head.bias"), logits, M, V, C, A_lo=xn_lo)
             # CFG + top-k/top-p + multinomial
             t = cfg * (si / self.num_stages_minus_1)
             q_noise = self._noise(B * l, V, rng)

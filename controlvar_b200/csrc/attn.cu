@@ -22,7 +22,8 @@ __global__ void __launch_bounds__(256) attn_kvcache_kernel(const float* __restri
                                                            const float* __restrict__ k_lo,
                                                            const float* __restrict__ vt_hi,
                                                            const float* __restrict__ vt_lo, float* __restrict__ out,
-                                                           int H, int l, int L, int T_max, float scale) {
+                                                           float* __restrict__ out_lo, int H, int l, int L, int T_max,
+                                                           float scale) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   AttnSmem& sm = *reinterpret_cast<AttnSmem*>(smem_raw);
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -158,7 +159,13 @@ __global__ void __launch_bounds__(256) attn_kvcache_kernel(const float* __restri
     if (t < l) {
       float inv = 1.0f / lrow[i];
       float4 v = make_float4(o[i][0] * inv, o[i][1] * inv, o[i][2] * inv, o[i][3] * inv);
-      st4(out + ((long long)r * l + t) * C + h * D + tx * 4, v);
+      const long long off = ((long long)r * l + t) * C + h * D + tx * 4;
+      if (out_lo != nullptr) {     // TF32 split for the all-TMA proj GEMM
+        float4 hi = make_float4(tc::trunc_tf32(v.x), tc::trunc_tf32(v.y), tc::trunc_tf32(v.z), tc::trunc_tf32(v.w));
+        st4(out_lo + off, make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w));
+        v = hi;
+      }
+      st4(out + off, v);
     }
   }
 }
@@ -222,7 +229,8 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 __global__ void __launch_bounds__(kThreads, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap mapKhi, const __grid_constant__ CUtensorMap mapKlo,
                const __grid_constant__ CUtensorMap mapVhi, const __grid_constant__ CUtensorMap mapVlo,
-               const float* __restrict__ q, float* __restrict__ out, int H, int l, int L, float scale) {
+               const float* __restrict__ q, float* __restrict__ out, float* __restrict__ out_lo, int H, int l, int L,
+               float scale) {
   using G = Geo<32>;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -363,10 +371,17 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapKhi, const __grid_constant
     const int t = q0 + row;
     if (t < l) {
       const float inv = 1.0f / l_run;
-      float* op = out + ((long long)r * l + t) * (H * D) + h * D;
+      const long long off = ((long long)r * l + t) * (H * D) + h * D;
 #pragma unroll
-      for (int d = 0; d < D; d += 4)
-        st4(op + d, make_float4(o_reg[d] * inv, o_reg[d + 1] * inv, o_reg[d + 2] * inv, o_reg[d + 3] * inv));
+      for (int d = 0; d < D; d += 4) {
+        float4 v = make_float4(o_reg[d] * inv, o_reg[d + 1] * inv, o_reg[d + 2] * inv, o_reg[d + 3] * inv);
+        if (out_lo != nullptr) {   // TF32 split for the all-TMA proj GEMM
+          float4 hi = make_float4(trunc_tf32(v.x), trunc_tf32(v.y), trunc_tf32(v.z), trunc_tf32(v.w));
+          st4(out_lo + off + d, make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w));
+          v = hi;
+        }
+        st4(out + off + d, v);
+      }
     }
   } else if (warp == 4) {
     // ================================================================ TMA: K / V^T tiles, pre-split
@@ -473,8 +488,8 @@ static int make_map3(CUtensorMap* map, const float* base, long long inner, long 
 }  // namespace tcattn
 
 extern "C" int cvar_attn_kvcache(const float* q, const float* k_hi, const float* k_lo, const float* vt_hi,
-                                 const float* vt_lo, float* out, int R, int H, int l, int L, int T_max, float scale,
-                                 int engine, void* stream) {
+                                 const float* vt_lo, float* out, float* out_lo, int R, int H, int l, int L, int T_max,
+                                 float scale, int engine, void* stream) {
   CVAR_REQUIRE(R > 0 && H > 0 && l > 0 && L >= l && L <= T_max, "cvar_attn_kvcache: bad shape l=%d L=%d T=%d", l, L,
                T_max);
   CVAR_REQUIRE(R <= 65535 && H <= 65535, "cvar_attn_kvcache: grid too large");
@@ -492,8 +507,8 @@ extern "C" int cvar_attn_kvcache(const float* q, const float* k_hi, const float*
                                          tcattn::kSmem);
     CVAR_REQUIRE(e == cudaSuccess, "cvar_attn_kvcache: cannot raise shared memory: %s", cudaGetErrorString(e));
     dim3 grid(cdiv(l, tcattn::BQ), H, R);
-    tcattn::attn_tc_kernel<<<grid, tcattn::kThreads, tcattn::kSmem, (cudaStream_t)stream>>>(mkh, mkl, mvh, mvl, q, out, H,
-                                                                                          l, L, scale);
+    tcattn::attn_tc_kernel<<<grid, tcattn::kThreads, tcattn::kSmem, (cudaStream_t)stream>>>(mkh, mkl, mvh, mvl, q, out,
+                                                                                          out_lo, H, l, L, scale);
     CVAR_CHECK_LAUNCH("cvar_attn_kvcache[tc]");
     return 0;
   }
@@ -501,8 +516,8 @@ extern "C" int cvar_attn_kvcache(const float* q, const float* k_hi, const float*
                                        (int)sizeof(AttnSmem));
   CVAR_REQUIRE(e == cudaSuccess, "cvar_attn_kvcache: cannot raise shared memory: %s", cudaGetErrorString(e));
   dim3 grid(cdiv(l, BQ), H, R);
-  attn_kvcache_kernel<<<grid, 256, sizeof(AttnSmem), (cudaStream_t)stream>>>(q, k_hi, k_lo, vt_hi, vt_lo, out, H, l, L,
-                                                                            T_max, scale);
+  attn_kvcache_kernel<<<grid, 256, sizeof(AttnSmem), (cudaStream_t)stream>>>(q, k_hi, k_lo, vt_hi, vt_lo, out, out_lo, H,
+                                                                            l, L, T_max, scale);
   CVAR_CHECK_LAUNCH("cvar_attn_kvcache");
   return 0;
 }

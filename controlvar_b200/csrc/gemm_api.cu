@@ -6,9 +6,13 @@ using namespace cvar;
 namespace cvar {
 // tcgen05 engine (gemm_tc.cu); returns 1 when it took the problem, 0 when the shape is not supported, <0 on error.
 int tc_gemm_try(const cvar_gemm_args* a, cudaStream_t s);
-int tc_qkv_try(const float* A, const float* Wqkv_hi, const float* Wqkv_lo, const QkvEpilogue& ep, int M, int C,
-               cudaStream_t s);
+int tc_qkv_try(const float* A, const float* A_lo, const float* Wqkv_hi, const float* Wqkv_lo, const QkvEpilogue& ep, int M,
+               int C, cudaStream_t s);
 int tc_split(const float* w, float* hi, float* lo, long long n, cudaStream_t s);
+// 2-CTA all-TMA engine (gemm_tc2.cu): needs the activation pre-split (A_lo) as well as the weights
+int tc2_gemm_try(const cvar_gemm_args* a, cudaStream_t s);
+int tc2_qkv_try(const float* A_hi, const float* A_lo, const float* Wqkv_hi, const float* Wqkv_lo, const QkvEpilogue& ep,
+                int M, int C, cudaStream_t s);
 int tc_conv_try(const cvar_conv_args* a, cudaStream_t s);
 }  // namespace cvar
 
@@ -25,15 +29,24 @@ extern "C" int cvar_gemm(const cvar_gemm_args* a, void* stream) {
                "cvar_gemm: gamma epilogue without gamma");
   CVAR_REQUIRE(a->epilogue != CVAR_EPI_BIAS_RESID || a->resid, "cvar_gemm: residual epilogue without resid");
   cudaStream_t s = (cudaStream_t)stream;
+  CVAR_REQUIRE(a->out_lo == nullptr || a->epilogue == CVAR_EPI_BIAS || a->epilogue == CVAR_EPI_BIAS_GELU,
+               "cvar_gemm: out_lo only goes with the BIAS / BIAS_GELU epilogues");
+  if (g_gemm_engine == 3 && a->A_lo != nullptr) {
+    int took = tc2_gemm_try(a, s);
+    if (took < 0) return took;
+    if (took == 1) return 0;
+  }
   if (g_gemm_engine != 0 && a->W_hi != nullptr && a->W_lo != nullptr) {
     int took = tc_gemm_try(a, s);
     if (took < 0) return took;
     if (took == 1) return 0;
   }
+  CVAR_REQUIRE(a->A_lo == nullptr || a_vec, "cvar_gemm: a pre-split activation needs 16-byte aligned rows");
   DenseALoader al{a->A, a->lda, a->strideA, a->M, a->K, a_vec};
+  al.A_lo = a->A_lo;
   DenseBLoader bl{a->W, a->ldw, a->strideW, a->N, a->K, a->w_is_kn, w_vec};
   DenseEpilogue ep{a->out, a->ldo, a->strideO, a->bias, a->epilogue, a->alpha, a->gamma, a->gamma_row_stride,
-                   a->rows_per_sample, a->resid, a->ldr, a->strideR};
+                   a->rows_per_sample, a->resid, a->ldr, a->strideR, a->out_lo};
   return launch_sgemm(al, bl, ep, (long long)a->M, a->N, a->K, a->batch, s, "cvar_gemm");
 }
 
@@ -76,7 +89,8 @@ __global__ void cos_attn_normalize_kernel(float* __restrict__ q, float* __restri
   }
 }
 
-extern "C" int cvar_qkv_project(const float* A, const float* Wqkv, const float* Wqkv_hi, const float* Wqkv_lo,
+extern "C" int cvar_qkv_project(const float* A, const float* A_lo, const float* Wqkv, const float* Wqkv_hi,
+                                const float* Wqkv_lo,
                                 const float* q_bias, const float* k_bias, const float* v_bias, float* q_out,
                                 float* k_hi, float* k_lo, float* vt_hi, float* vt_lo, int R, int l, int L_prev,
                                 int T_max, int H, int cos_attn, const float* scale_mul_H, void* stream) {
@@ -86,12 +100,17 @@ extern "C" int cvar_qkv_project(const float* A, const float* Wqkv, const float* 
   const int C = H * 64, M = R * l;
   QkvEpilogue ep{q_bias, k_bias, v_bias, q_out, k_hi, k_lo, vt_hi, vt_lo, C, H, l, L_prev, T_max};
   int took = 0;
-  if (g_gemm_engine != 0 && Wqkv_hi != nullptr && Wqkv_lo != nullptr) {
-    took = tc_qkv_try(A, Wqkv_hi, Wqkv_lo, ep, M, C, s);
+  if (g_gemm_engine == 3 && A_lo != nullptr && Wqkv_hi != nullptr && Wqkv_lo != nullptr) {
+    took = tc2_qkv_try(A, A_lo, Wqkv_hi, Wqkv_lo, ep, M, C, s);
+    if (took < 0) return took;
+  }
+  if (took == 0 && g_gemm_engine != 0 && Wqkv_hi != nullptr && Wqkv_lo != nullptr) {
+    took = tc_qkv_try(A, A_lo, Wqkv_hi, Wqkv_lo, ep, M, C, s);
     if (took < 0) return took;
   }
   if (took == 0) {
     DenseALoader al{A, C, 0, M, C, 1};
+    al.A_lo = A_lo;
     DenseBLoader bl{Wqkv, C, 0, 3 * C, C, 0, 1};
     int rc = launch_sgemm(al, bl, ep, (long long)M, 3 * C, C, 1, s, "cvar_qkv_project");
     if (rc) return rc;

@@ -400,21 +400,23 @@ static int dispatch_tc(const AL& al, const EP& ep, const float* W_hi, const floa
 static bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
 
 int tc_gemm_try(const cvar_gemm_args* a, cudaStream_t s) {
-  if (g_gemm_engine != 1) return 0;
+  if (g_gemm_engine == 0) return 0;
   if (a->batch != 1 || a->w_is_kn || a->M < 64 || a->N < 64 || a->K % 32 != 0 || a->N % 4 != 0) return 0;
   if (a->lda % 4 != 0 || a->ldw % 4 != 0 || !aligned16(a->A) || !aligned16(a->W_hi) || !aligned16(a->W_lo)) return 0;
   DenseALoader al{a->A, a->lda, a->strideA, a->M, a->K, 1};
+  al.A_lo = a->A_lo;
   DenseEpilogue ep{a->out, a->ldo, a->strideO, a->bias, a->epilogue, a->alpha, a->gamma, a->gamma_row_stride,
-                   a->rows_per_sample, a->resid, a->ldr, a->strideR};
+                   a->rows_per_sample, a->resid, a->ldr, a->strideR, a->out_lo};
   int rc = dispatch_tc(al, ep, a->W_hi, a->W_lo, a->ldw, (long long)a->M, a->N, a->K, s, "cvar_gemm[tc]");
   return rc ? rc : 1;
 }
 
-int tc_qkv_try(const float* A, const float* Wqkv_hi, const float* Wqkv_lo, const QkvEpilogue& ep, int M, int C,
-               cudaStream_t s) {
-  if (g_gemm_engine != 1) return 0;
+int tc_qkv_try(const float* A, const float* A_lo, const float* Wqkv_hi, const float* Wqkv_lo, const QkvEpilogue& ep, int M,
+               int C, cudaStream_t s) {
+  if (g_gemm_engine == 0) return 0;
   if (M < 64 || C % 32 != 0 || !aligned16(A) || !aligned16(Wqkv_hi) || !aligned16(Wqkv_lo)) return 0;
   DenseALoader al{A, C, 0, M, C, 1};
+  al.A_lo = A_lo;
   int rc = dispatch_tc(al, ep, Wqkv_hi, Wqkv_lo, C, (long long)M, 3 * C, C, s, "cvar_qkv_project[tc]");
   return rc ? rc : 1;
 }
@@ -427,7 +429,7 @@ int tc_split(const float* w, float* hi, float* lo, long long n, cudaStream_t s) 
 }
 
 int tc_conv_try(const cvar_conv_args* a, cudaStream_t s) {
-  if (g_gemm_engine != 1) return 0;
+  if (g_gemm_engine == 0) return 0;
   if (a->Cin % 32 != 0 || a->Cout % 16 != 0 || a->Cout < 32) return 0;
   const int up = a->upsample2x ? 1 : 0;
   const int Hout = a->Hin << up, Wout = a->Win << up;
@@ -446,9 +448,9 @@ int tc_conv_try(const cvar_conv_args* a, cudaStream_t s) {
 }  // namespace tc
 
 int tc_gemm_try(const cvar_gemm_args* a, cudaStream_t s) { return tc::tc_gemm_try(a, s); }
-int tc_qkv_try(const float* A, const float* Wqkv_hi, const float* Wqkv_lo, const QkvEpilogue& ep, int M, int C,
-               cudaStream_t s) {
-  return tc::tc_qkv_try(A, Wqkv_hi, Wqkv_lo, ep, M, C, s);
+int tc_qkv_try(const float* A, const float* A_lo, const float* Wqkv_hi, const float* Wqkv_lo, const QkvEpilogue& ep, int M,
+               int C, cudaStream_t s) {
+  return tc::tc_qkv_try(A, A_lo, Wqkv_hi, Wqkv_lo, ep, M, C, s);
 }
 int tc_split(const float* w, float* hi, float* lo, long long n, cudaStream_t s) { return tc::tc_split(w, hi, lo, n, s); }
 int tc_conv_try(const cvar_conv_args* a, cudaStream_t s) { return tc::tc_conv_try(a, s); }

@@ -1,0 +1,333 @@
+// 2-CTA (cta_group::2) tcgen05 GEMM for the dense transformer layers: out = epilogue(A[M,K] * W[N,K]^T), 3xTF32.
+//
+// Why a second kernel: tools/trace_gemm.py showed the 1-CTA engine (gemm_tc.cu) is bound by the TMA round trip
+// (~2080 cycles for the 64 KB of weight tiles of a K-block) against 1460 cycles of MMA, with room for only TWO 96 KB
+// stages.  A CTA pair computes a 256 x 256 tile: each CTA keeps its own 128 rows of A and only HALF of the weight rows,
+// so a stage is 64 KB, THREE stages fit, and the MMA time per K-block is unchanged (M = 256 across the pair).
+//
+// All four operand tiles arrive by TMA: activations are split hi/lo by the kernel that PRODUCES them
+// (cvar_ln_modulate, the GELU epilogue, cvar_attn_kvcache) exactly as the weights are split once at pack time.  There
+// is therefore no generic-proxy writer of operand tiles in this kernel: every shared-memory fill is an async-proxy
+// write that completes on an mbarrier, which is what makes the cross-CTA hand-over simple (and standard).
+//
+// Per CTA: warps 0-7 epilogue, warp 8 TMA, warp 9 TMEM alloc (+ MMA issue in the leader CTA, rank 0).
+// Barriers: full[s]  - LEADER's copy only; tx bytes from both CTAs (cta_group::2 TMA signals the leader's barrier)
+//           empty[s] - both copies; released by the leader's tcgen05.commit ... multicast::cluster 0b11
+//           tm_full  - both copies (multicast commit); tm_empty - leader's copy, 2 x 256 epilogue arrivals (peer: remote)
+#include <cuda.h>
+#include <mutex>
+#include "sgemm.cuh"
+#include "tc_ptx.cuh"
+
+namespace cvar {
+namespace tc2 {
+using namespace cvar::tc;
+
+constexpr int BM = 128;            // rows per CTA (256 per pair)
+constexpr int BN = 256;            // columns per pair; each CTA stages BN/2 weight rows
+constexpr int BK = 32;
+constexpr int kEpiWarps = 8;
+constexpr int kTmaWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1;
+constexpr int kThreads = (kEpiWarps + 2) * 32;       // 320
+constexpr int kEpiCols = 16, kStagePitch = kEpiCols + 4;
+constexpr int kABytes = BM * BK * 4;                 // 16 KiB
+constexpr int kBBytes = (BN / 2) * BK * 4;           // 16 KiB
+constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;   // 64 KiB
+constexpr int kStages = 3;
+constexpr int kStagingBytes = kEpiWarps * 32 * kStagePitch * 4;
+constexpr int kSmem = kStages * kStageBytes + kStagingBytes + 1024 + 1024;
+constexpr uint32_t kPeerMask = 0xFEFFFFFFu;          // clears the CTA-rank bit of a shared::cluster address (leader's copy)
+constexpr int kGroupM = 16;                          // pair-tiles (256 rows) per rasterisation group
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// TMA into THIS CTA's shared memory, completion counted on the LEADER's barrier
+__device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
+          "r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kPeerMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// completion of all prior MMAs of the pair -> the same-offset barrier in BOTH CTAs
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
+}
+// arrive on the LEADER's copy of a barrier from either CTA of the pair (cluster-scope release)
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerMask) : "memory");
+}
+
+__device__ __forceinline__ void tile_coords(int tile, int m_tiles, int n_tiles, int& mt, int& nt) {
+  const int per_group = kGroupM * n_tiles;
+  const int g = tile / per_group;
+  const int first_m = g * kGroupM;
+  const int gm = min(kGroupM, m_tiles - first_m);
+  const int in_g = tile - g * per_group;
+  nt = in_g / gm;
+  mt = first_m + (in_g - nt * gm);
+}
+
+template <class EP>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+tc_gemm2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
+                const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo, EP ep,
+                long long M, int N, int K, int m_tiles, int n_tiles) {
+  using G = Geo<BK>;
+  constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+  constexpr int kAccStride = 256;                    // main [0,256), lo [256,512)
+
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  auto a_hi = [&](int s) { return smem + s * kStageBytes; };
+  auto a_lo = [&](int s) { return smem + s * kStageBytes + kABytes; };
+  auto b_hi = [&](int s) { return smem + s * kStageBytes + 2 * kABytes; };
+  auto b_lo = [&](int s) { return smem + s * kStageBytes + 2 * kABytes + kBBytes; };
+  float* stage_base = reinterpret_cast<float*>(smem + kStages * kStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes + kStagingBytes);
+  uint64_t* full = bars;                  // [S]
+  uint64_t* empty = bars + kStages;       // [S]
+  uint64_t* tm_full = bars + 2 * kStages;
+  uint64_t* tm_empty = bars + 2 * kStages + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();           // 0 = leader
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int nkb = K / BK;
+  const int total_tiles = m_tiles * n_tiles;         // m_tiles counts 256-row pair tiles
+
+  if (warp == kTmaWarp && lane == 0) {
+    tma_prefetch_desc(&mapAhi), tma_prefetch_desc(&mapAlo), tma_prefetch_desc(&mapBhi), tma_prefetch_desc(&mapBlo);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tm_full, 1);
+    mbar_init(tm_empty, 2 * kEpiWarps * 32);
+    fence_barrier_init();
+  }
+  if (warp == kMmaWarp) tmem_alloc2(tmem_slot, 512);   // both CTAs, same warp index, same slot offset
+  tc_fence_before();
+  cluster_sync_all();                                   // barriers of both CTAs initialised before any remote signal
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < kEpiWarps) {
+    // ================================================================ epilogue (each CTA drains its own 128 rows)
+    float* stage = stage_base + warp * (32 * kStagePitch);
+    const int quarter = warp & 3, half = warp >> 2;
+    int tcount = 0;
+    for (int tile = pair; tile < total_tiles; tile += npairs, ++tcount) {
+      int mt, nt;
+      tile_coords(tile, m_tiles, n_tiles, mt, nt);
+      mbar_wait(tm_full, tcount & 1);
+      tc_fence_after();
+      const long long m_base = (long long)mt * 256 + rank * BM + quarter * 32;
+      const uint32_t tcol = tmem_base + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
+      for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += kEpiCols) {
+        float v[kEpiCols], w[kEpiCols];
+        tmem_ld_32x32b_x16(tcol + (uint32_t)c, v);
+        tmem_ld_32x32b_x16(tcol + (uint32_t)(kAccStride + c), w);
+#pragma unroll
+        for (int q = 0; q < kEpiCols / 4; ++q)
+          *reinterpret_cast<float4*>(stage + lane * kStagePitch + q * 4) =
+              make_float4(v[4 * q] + w[4 * q], v[4 * q + 1] + w[4 * q + 1], v[4 * q + 2] + w[4 * q + 2],
+                          v[4 * q + 3] + w[4 * q + 3]);
+        __syncwarp();
+        const int n = nt * BN + c + (lane & 3) * 4;
+        const int nvalid = min(4, N - n);
+        EpiAux aux[4];
+#pragma unroll
+        for (int r8 = 0; r8 < 4; ++r8) {
+          const long long m = m_base + r8 * 8 + (lane >> 2);
+          if (m < M && n < N) aux[r8] = epi_load_aux(ep, m, n, nvalid, 0);
+        }
+#pragma unroll
+        for (int r8 = 0; r8 < 4; ++r8) {
+          const int rr = r8 * 8 + (lane >> 2);
+          const float4 x = *reinterpret_cast<const float4*>(stage + rr * kStagePitch + (lane & 3) * 4);
+          const long long m = m_base + rr;
+          if (m < M && n < N) epi_store_aux(ep, m, n, &x.x, nvalid, 0, aux[r8]);
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      mbar_arrive_leader(tm_empty);
+    }
+  } else if (warp == kTmaWarp) {
+    // ================================================================ TMA: own A rows, own half of the weight rows
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = pair; tile < total_tiles; tile += npairs) {
+        int mt, nt;
+        tile_coords(tile, m_tiles, n_tiles, mt, nt);
+        const int arow = mt * 256 + (int)rank * BM;
+        const int brow = nt * BN + (int)rank * (BN / 2);
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          if (rank == 0) mbar_arrive_expect_tx(&full[s], 2u * (uint32_t)kStageBytes);   // bytes of BOTH CTAs
+          tma_load_2d_2sm(&mapAhi, &full[s], a_hi(s), kb * BK, arow);
+          tma_load_2d_2sm(&mapAlo, &full[s], a_lo(s), kb * BK, arow);
+          tma_load_2d_2sm(&mapBhi, &full[s], b_hi(s), kb * BK, brow);
+          tma_load_2d_2sm(&mapBlo, &full[s], b_lo(s), kb * BK, brow);
+        }
+      }
+    }
+  } else if (rank == 0) {
+    // ================================================================ MMA issue (leader CTA only)
+    if (lane == 0) {
+      int it = 0, tcount = 0;
+      for (int tile = pair; tile < total_tiles; tile += npairs, ++tcount) {
+        mbar_wait(tm_empty, (tcount & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d = tmem_base, dl = tmem_base + (uint32_t)kAccStride;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1;
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint64_t dah = G::desc(smem_u32(a_hi(s))), dal = G::desc(smem_u32(a_lo(s)));
+          const uint64_t dbh = G::desc(smem_u32(b_hi(s))), dbl = G::desc(smem_u32(b_lo(s)));
+#pragma unroll
+          for (int k = 0; k < BK / 8; ++k) {
+            const uint64_t adv = (uint64_t)(k * 2);
+            umma_tf32_2sm(dl, dal + adv, dbh + adv, kIdesc, (kb | k) != 0);
+            umma_tf32_2sm(dl, dah + adv, dbl + adv, kIdesc, 1u);
+            umma_tf32_2sm(d, dah + adv, dbh + adv, kIdesc, (kb | k) != 0);
+          }
+          umma_commit_2sm(&empty[s]);
+        }
+        umma_commit_2sm(tm_full);
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();                                   // no CTA frees TMEM / exits while its peer may still signal it
+  if (warp == kMmaWarp) tmem_dealloc2(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+// row-major [rows, K] fp32 matrix -> (BK x 128-row) box, 128-byte swizzle, out-of-range rows zero-filled
+static int make_map(CUtensorMap* map, const float* base, long long rows, int K, long long ld) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("tc_gemm2: cuTensorMapEncodeTiled is not available from the driver");
+    return -3;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)BK, 128};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("tc_gemm2: cuTensorMapEncodeTiled failed with %d (rows=%lld K=%d ld=%lld)", (int)r, rows, K, ld);
+    return -3;
+  }
+  return 0;
+}
+
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+
+template <class EP>
+int launch(const EP& ep, const float* A_hi, const float* A_lo, long long lda, const float* W_hi, const float* W_lo,
+           long long ldw, long long M, int N, int K, cudaStream_t s, const char* name) {
+  CUtensorMap mah, mal, mbh, mbl;
+  int rc = make_map(&mah, A_hi, M, K, lda);
+  if (!rc) rc = make_map(&mal, A_lo, M, K, lda);
+  if (!rc) rc = make_map(&mbh, W_hi, N, K, ldw);
+  if (!rc) rc = make_map(&mbl, W_lo, N, K, ldw);
+  if (rc) return rc;
+  auto kern = tc_gemm2_kernel<EP>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+  if (e != cudaSuccess) {
+    set_error("%s: cannot raise shared memory to %d: %s", name, kSmem, cudaGetErrorString(e));
+    return -2;
+  }
+  const int m_tiles = cdiv(M, 256), n_tiles = cdiv(N, BN);
+  const int pairs = min(num_sms() / 2, m_tiles * n_tiles);
+  kern<<<2 * pairs, kThreads, kSmem, s>>>(mah, mal, mbh, mbl, ep, M, N, K, m_tiles, n_tiles);
+  CVAR_CHECK_LAUNCH(name);
+  return 0;
+}
+
+static bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
+}  // namespace tc2
+
+// returns 1 when taken, 0 when the shape / operands do not qualify, < 0 on error
+int tc2_gemm_try(const cvar_gemm_args* a, cudaStream_t s) {
+  if (a->A_lo == nullptr || a->W_hi == nullptr || a->W_lo == nullptr) return 0;
+  if (a->batch != 1 || a->w_is_kn || a->M < 256 || a->N < 256 || a->K % 32 != 0 || a->N % 4 != 0) return 0;
+  if (a->lda % 4 != 0 || a->ldw % 4 != 0 || !tc2::aligned16(a->A) || !tc2::aligned16(a->A_lo) ||
+      !tc2::aligned16(a->W_hi) || !tc2::aligned16(a->W_lo))
+    return 0;
+  DenseEpilogue ep{a->out, a->ldo, a->strideO, a->bias, a->epilogue, a->alpha, a->gamma, a->gamma_row_stride,
+                   a->rows_per_sample, a->resid, a->ldr, a->strideR, a->out_lo};
+  int rc = tc2::launch(ep, a->A, a->A_lo, a->lda, a->W_hi, a->W_lo, a->ldw, (long long)a->M, a->N, a->K, s,
+                       "cvar_gemm[tc2]");
+  return rc ? rc : 1;
+}
+
+int tc2_qkv_try(const float* A_hi, const float* A_lo, const float* Wqkv_hi, const float* Wqkv_lo, const QkvEpilogue& ep,
+                int M, int C, cudaStream_t s) {
+  if (A_lo == nullptr || M < 256 || C % 32 != 0) return 0;
+  if (!tc2::aligned16(A_hi) || !tc2::aligned16(A_lo) || !tc2::aligned16(Wqkv_hi) || !tc2::aligned16(Wqkv_lo)) return 0;
+  int rc = tc2::launch(ep, A_hi, A_lo, C, Wqkv_hi, Wqkv_lo, C, (long long)M, 3 * C, C, s, "cvar_qkv_project[tc2]");
+  return rc ? rc : 1;
+}
+}  // namespace cvar

@@ -14,7 +14,8 @@ struct DenseALoader {
   const float* A;
   long long lda, strideA;
   int M, K;
-  int vec;   // 1: K, lda multiples of 4 and 16-byte aligned base -> 128-bit loads; 0: scalar loads (ragged shapes)
+  int vec;
+  const float* A_lo = nullptr;   // optional: A holds the TF32 'hi' part and A_lo the remainder (hi + lo == x exactly)   // 1: K, lda multiples of 4 and 16-byte aligned base -> 128-bit loads; 0: scalar loads (ragged shapes)
   static constexpr int kMaxSlots = 8;
   const float* ptr[kMaxSlots];
   __device__ __forceinline__ void prep(int slot, long long m, int batch) {
@@ -24,7 +25,14 @@ struct DenseALoader {
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     const float* p = ptr[slot];
     if (p == nullptr || k >= K) return v;
-    if (vec) return ld4(p + k);
+    if (vec) {
+      v = ld4(p + k);
+      if (A_lo != nullptr) {
+        float4 w = ld4(A_lo + (p - A) + k);
+        v.x += w.x, v.y += w.y, v.z += w.z, v.w += w.w;
+      }
+      return v;
+    }
     v.x = p[k];
     if (k + 1 < K) v.y = p[k + 1];
     if (k + 2 < K) v.z = p[k + 2];
@@ -136,6 +144,7 @@ struct DenseEpilogue {
   int rows_per_sample;
   const float* resid;
   long long ldr, strideR;
+  float* out_lo = nullptr;       // optional (BIAS / BIAS_GELU): write the result split, out = hi, out_lo = lo
   __device__ __forceinline__ void store(long long m, int n, const float* v, int nvalid, int batch) const {
     float* o = out + (long long)batch * strideO + m * ldo + n;
     float r[4];
@@ -156,6 +165,16 @@ struct DenseEpilogue {
 #pragma unroll
       for (int j = 0; j < 4; ++j)
         if (j < nvalid) r[j] = __fadd_rn(rs[j], r[j]);                      // shortcut + h
+    }
+    if (out_lo != nullptr) {
+      float* ol = out_lo + (long long)batch * strideO + m * ldo + n;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (j < nvalid) {
+          float hi = __uint_as_float(__float_as_uint(r[j]) & 0xFFFFE000u);
+          ol[j] = r[j] - hi;
+          r[j] = hi;
+        }
     }
     if (nvalid == 4 && ((((uintptr_t)o) & 15) == 0)) {
       st4(o, make_float4(r[0], r[1], r[2], r[3]));
@@ -212,6 +231,16 @@ __device__ __forceinline__ void dense_store_aux(const DenseEpilogue& e, long lon
     r[2] = __fadd_rn(x.a.z, __fmul_rn(r[2], x.b.z)), r[3] = __fadd_rn(x.a.w, __fmul_rn(r[3], x.b.w));
   } else if (e.mode == CVAR_EPI_BIAS_RESID) {
     r[0] = __fadd_rn(x.a.x, r[0]), r[1] = __fadd_rn(x.a.y, r[1]), r[2] = __fadd_rn(x.a.z, r[2]), r[3] = __fadd_rn(x.a.w, r[3]);
+  }
+  if (e.out_lo != nullptr) {
+    float l4[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float hi = __uint_as_float(__float_as_uint(r[j]) & 0xFFFFE000u);
+      l4[j] = r[j] - hi;
+      r[j] = hi;
+    }
+    st4(e.out_lo + (long long)batch * e.strideO + m * e.ldo + n, make_float4(l4[0], l4[1], l4[2], l4[3]));
   }
   st4(o, make_float4(r[0], r[1], r[2], r[3]));
 }

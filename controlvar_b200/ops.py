@@ -11,7 +11,7 @@ from . import _lib
 from ._lib import ConvArgs, GemmArgs, check
 
 EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_GAMMA_RESID, EPI_BIAS_RESID = 0, 1, 2, 3
-ENGINE_SIMT, ENGINE_TC_3XTF32, ENGINE_TC_BF16 = 0, 1, 2
+ENGINE_SIMT, ENGINE_TC_3XTF32, ENGINE_TC_2CTA = 0, 1, 3
 
 
 def _p(t: Optional[torch.Tensor]):
@@ -105,11 +105,12 @@ def prologue(class_emb, cond_embed, pos_start, lvl_pos_t, label_B, cond_type_B, 
                                     _stream()), "cvar_prologue")
 
 
-def ln_modulate(x, scale, shift, mod_row_stride, out, M, Cdim, rows_per_sample, eps):
-    """scale/shift: views into an ada_lin output; only their data pointers and the common row stride are used."""
-    _chk(x, scale, shift, out)
-    check(_lib.load().cvar_ln_modulate(_p(x), _p(scale), _p(shift), mod_row_stride, _p(out), M, Cdim, rows_per_sample,
-                                       float(eps), _stream()), "cvar_ln_modulate")
+def ln_modulate(x, scale, shift, mod_row_stride, out, M, Cdim, rows_per_sample, eps, out_lo=None):
+    """scale/shift: views into an ada_lin output; only their data pointers and the common row stride are used.
+    out_lo: write the result as a TF32 hi/lo split (out = hi) - the operand format of the 2-CTA GEMM."""
+    _chk(x, scale, shift, out, out_lo)
+    check(_lib.load().cvar_ln_modulate(_p(x), _p(scale), _p(shift), mod_row_stride, _p(out), _p(out_lo), M, Cdim,
+                                       rows_per_sample, float(eps), _stream()), "cvar_ln_modulate")
     return out
 
 
@@ -135,11 +136,12 @@ def _wparts(W):
 
 def gemm(A, W, bias, out, M, N, K, *, lda=None, ldw=None, ldo=None, epilogue=EPI_BIAS, alpha=1.0, w_is_kn=False,
          batch=1, strideA=0, strideW=0, strideO=0, gamma=None, gamma_row_stride=0, rows_per_sample=1,
-         resid=None, ldr=None, strideR=0):
+         resid=None, ldr=None, strideR=0, A_lo=None, out_lo=None):
     W, W_hi, W_lo = _wparts(W)
-    _chk(A, W, bias, out, gamma, resid)
+    _chk(A, W, bias, out, gamma, resid, A_lo, out_lo)
     a = GemmArgs()
     a.W_hi, a.W_lo = _p(W_hi), _p(W_lo)
+    a.A_lo, a.out_lo = _p(A_lo), _p(out_lo)
     a.A, a.lda, a.strideA = _p(A), (K if lda is None else lda), strideA
     a.W, a.ldw, a.strideW, a.w_is_kn = _p(W), ((N if w_is_kn else K) if ldw is None else ldw), strideW, int(w_is_kn)
     a.bias = _p(bias)
@@ -178,23 +180,24 @@ class KVCache:
         return (self.vt_hi + self.vt_lo).view(self.R, self.H, 64, self.T)[:, :, :, :L].transpose(2, 3)
 
 
-def qkv_project(A, Wqkv, q_bias, k_bias, v_bias, q_out, cache: KVCache, R, l, L_prev, H, cos_attn, scale_mul_H):
+def qkv_project(A, Wqkv, q_bias, k_bias, v_bias, q_out, cache: KVCache, R, l, L_prev, H, cos_attn, scale_mul_H,
+                A_lo=None):
     Wqkv, W_hi, W_lo = _wparts(Wqkv)
-    _chk(A, Wqkv, q_bias, k_bias, v_bias, q_out, cache.k_hi, scale_mul_H)
+    _chk(A, Wqkv, q_bias, k_bias, v_bias, q_out, cache.k_hi, scale_mul_H, A_lo)
     Cd = H * 64
     with _Timed("gemm", 2.0 * R * l * 3 * Cd * Cd, 4.0 * (R * l * Cd + 3 * Cd * Cd + R * l * 3 * Cd)):
-        check(_lib.load().cvar_qkv_project(_p(A), _p(Wqkv), _p(W_hi), _p(W_lo), _p(q_bias), _p(k_bias), _p(v_bias),
+        check(_lib.load().cvar_qkv_project(_p(A), _p(A_lo), _p(Wqkv), _p(W_hi), _p(W_lo), _p(q_bias), _p(k_bias), _p(v_bias),
                                            _p(q_out), _p(cache.k_hi), _p(cache.k_lo), _p(cache.vt_hi), _p(cache.vt_lo),
                                            R, l, L_prev, cache.T, H, int(cos_attn), _p(scale_mul_H), _stream()),
               "cvar_qkv_project")
 
 
-def attn_kvcache(q, cache: KVCache, out, R, H, l, L, scale, engine: int = -1):
-    _chk(q, cache.k_hi, out)
+def attn_kvcache(q, cache: KVCache, out, R, H, l, L, scale, engine: int = -1, out_lo=None):
+    _chk(q, cache.k_hi, out, out_lo)
     # algorithmic work of SURVEY.md section 8d: 4*l*L*64 flop and (2l + 2L)*64*4 bytes per (row, head)
     with _Timed("attn", 4.0 * l * L * 64 * R * H, (2.0 * l + 2.0 * L) * 64 * 4 * R * H):
         check(_lib.load().cvar_attn_kvcache(_p(q), _p(cache.k_hi), _p(cache.k_lo), _p(cache.vt_hi), _p(cache.vt_lo),
-                                            _p(out), R, H, l, L, cache.T, float(scale), int(engine), _stream()),
+                                            _p(out), _p(out_lo), R, H, l, L, cache.T, float(scale), int(engine), _stream()),
               "cvar_attn_kvcache")
     return out
 

@@ -34,8 +34,11 @@ CVAR_API int cvar_abi_version(void);
 CVAR_API const char* cvar_last_error(void);
 /* Number of kernel launches issued by this library in the calling process since load (bench.py: gpu_launches). */
 CVAR_API long long cvar_launch_count(void);
-/* Which GEMM engine serves cvar_gemm/conv when the shape allows: 0 = SIMT fp32 FFMA, 1 = tcgen05 3xTF32 (fp32-class),
- * 2 = tcgen05 bf16 (fast, not parity-grade).  Returns the previous value. */
+/* Which GEMM engine serves cvar_gemm / cvar_qkv_project / cvar_conv2d when the shape and operands allow:
+ *   0 = SIMT fp32 FFMA;  1 = tcgen05 3xTF32, one CTA per tile (fp32-class);  2 = reserved (bf16, not implemented);
+ *   3 = as 1, and dense layers whose activation operand is supplied pre-split (A_lo != NULL) run on the 2-CTA
+ *       (cta_group::2) all-TMA kernel.  Anything an engine does not take falls through to the next lower one.
+ * Default: 3 (environment variable CVAR_GEMM_ENGINE = 0 | 1 | 3 overrides it at load).  Returns the previous value. */
 CVAR_API int cvar_set_gemm_engine(int engine);
 CVAR_API int cvar_get_gemm_engine(void);
 /* K-block of the tcgen05 engine: 32 (128-byte swizzle, default) or 16 (64-byte swizzle, deeper pipeline). Returns the
@@ -62,7 +65,9 @@ CVAR_API int cvar_prologue(const float* class_emb, const float* cond_embed, cons
  * y[m,:] = LayerNorm(x[m,:], eps, no affine) * (scale[r,:] + 1) + shift[r,:],  r = m / rows_per_sample.
  * scale/shift are slices of an ada_lin output, so they carry a row stride (6C or 2C floats). */
 CVAR_API int cvar_ln_modulate(const float* x, const float* scale, const float* shift, long long mod_row_stride,
-                     float* y, int M, int C, int rows_per_sample, float eps, void* stream);
+                     float* y, float* y_lo, int M, int C, int rows_per_sample, float eps, void* stream);
+/* y_lo (optional): when not NULL the result is written as a TF32 split, y = hi, y_lo = lo (hi + lo == value exactly) -
+ * the operand format the 2-CTA GEMM fetches by TMA. */
 
 /* ---- dense layers: F.linear call sites of basic_var.py:51,92,119 and control_var.py:221 -----------------------
  * out = epilogue(A[M,K] @ W[N,K]^T + bias[N]).  A, W, out row-major with leading dimensions lda/ldw/ldo.
@@ -76,6 +81,9 @@ enum {
 };
 typedef struct {
   const float* A; long long lda; long long strideA;
+  /* optional: A is the TF32 'hi' part of the activation and A_lo the remainder (same shape / lda), as written by a
+   * producer called with its *_lo output (cvar_ln_modulate, cvar_attn_kvcache, a cvar_gemm with out_lo) */
+  const float* A_lo;
   const float* W; long long ldw; long long strideW; int w_is_kn;
   /* optional TF32 split of W made once by cvar_split_tf32 (same shape / ldw): the tcgen05 engine takes the problem only
    * when both are given; W itself always stays valid for the SIMT engine */
@@ -86,6 +94,7 @@ typedef struct {
   int epilogue; float alpha;
   const float* gamma; long long gamma_row_stride; int rows_per_sample;   /* CVAR_EPI_BIAS_GAMMA_RESID */
   const float* resid; long long ldr; long long strideR;                  /* CVAR_EPI_BIAS_RESID */
+  float* out_lo;   /* optional, CVAR_EPI_BIAS / CVAR_EPI_BIAS_GELU only: write the result split (out = hi, out_lo = lo) */
 } cvar_gemm_args;
 CVAR_API int cvar_gemm(const cvar_gemm_args* args, void* stream);
 
@@ -99,7 +108,7 @@ CVAR_API int cvar_gemm(const cvar_gemm_args* args, void* stream);
  * T_max must be a multiple of 4.  The caller zero-initialises the cache once (stale tail keys are masked, but must be
  * finite).  cos_attn != 0 (depth 30, basic_var.py:99-104): q = normalize(q) * exp(min(scale_mul[h], ln 100)),
  * k = normalize(k). */
-CVAR_API int cvar_qkv_project(const float* A, const float* Wqkv, const float* Wqkv_hi, const float* Wqkv_lo,
+CVAR_API int cvar_qkv_project(const float* A, const float* A_lo, const float* Wqkv, const float* Wqkv_hi, const float* Wqkv_lo,
                      const float* q_bias, const float* k_bias, const float* v_bias,
                      float* q_out, float* k_hi, float* k_lo, float* vt_hi, float* vt_lo,
                      int R, int l, int L_prev, int T_max, int H, int cos_attn, const float* scale_mul_H,
@@ -111,7 +120,9 @@ CVAR_API int cvar_qkv_project(const float* A, const float* Wqkv, const float* Wq
  * cache holds exactly the keys of scales <= current, which is the block-causal pattern of control_var.py:168.
  * engine: -1 = library default (tensor cores when l >= 64), 0 = SIMT fp32, 1 = tcgen05 3xTF32. */
 CVAR_API int cvar_attn_kvcache(const float* q, const float* k_hi, const float* k_lo, const float* vt_hi, const float* vt_lo,
-                      float* out, int R, int H, int l, int L, int T_max, float scale, int engine, void* stream);
+                      float* out, float* out_lo, int R, int H, int l, int L, int T_max, float scale, int engine,
+                      void* stream);
+/* out_lo (optional): write the result as a TF32 split (out = hi, out_lo = lo) for the 2-CTA proj GEMM. */
 
 /* ---- CFG + top-k/top-p + multinomial(1): control_var.py:501-505, helpers.py:6-19 -----------------------------
  * logits (2B, l, V): rows [0,B) conditional, [B,2B) unconditional.  v = (1+t)*lc - t*lu; top-k keeps v >= k-th

@@ -34,7 +34,7 @@ def build(cfg, weight_seed=0):
     return vae, var, sd, vsd
 
 
-@pytest.fixture(params=[0, 1], ids=["simt", "tc3xtf32"])
+@pytest.fixture(params=[0, 1, 3], ids=["simt", "tc3xtf32", "tc2cta"])
 def engine(request):
     old = ops.set_gemm_engine(request.param)
     yield request.param

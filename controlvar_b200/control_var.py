@@ -100,6 +100,13 @@ class ControlVAR(nn.Module):
         self._ws: Dict[Tuple, torch.Tensor] = {}
         self._consts: Dict[str, object] = {}
         self.last_idx: List[torch.Tensor] = []           # tokens of the last call, per scale (diagnostics / tests)
+        # Parity instruments (tests only; SURVEY.md section 7.2 "margin-aware + teacher-forced"):
+        #   debug_forced_idx     per-scale (B, l) tokens that REPLACE the sampled ones after sampling, so that the
+        #                        trajectory is pinned to the oracle's while last_idx still reports what was sampled;
+        #   debug_capture_logits keep a copy of the raw (2B, l, V) logits of every scale in last_logits.
+        self.debug_forced_idx: Optional[List[torch.Tensor]] = None
+        self.debug_capture_logits = False
+        self.last_logits: List[torch.Tensor] = []
         self.eval()
 
     # ------------------------------------------------------------------------------------------ plumbing
@@ -271,6 +278,7 @@ class ControlVAR(nn.Module):
         ops.gemm(silu_cond, cst["head_ada_w"], cst["head_ada_b"], ada_head, R, 2 * C, C)
 
         self.last_idx = []
+        self.last_logits = []
         cur_L = 0
         for si, pn in enumerate(self.patch_nums):
             l = lens[si]
@@ -297,8 +305,12 @@ class ControlVAR(nn.Module):
             # CFG + top-k/top-p + multinomial
             t = cfg * (si / self.num_stages_minus_1)
             q_noise = self._noise(B * l, V, rng)
+            if self.debug_capture_logits:
+                self.last_logits.append(logits[:M].view(R, l, V).clone())
             ops.cfg_sample(logits, q_noise, idx, B, l, V, t, top_k, top_p)
             self.last_idx.append(idx[:B * l].view(B, l).clone())
+            if self.debug_forced_idx is not None:
+                idx[:B * l].copy_(self.debug_forced_idx[si].to(device=dev, dtype=torch.int64).reshape(-1))
             # VQ step + next-scale input
             phi_w, phi_b = cst["phi"][self.cfg.phi_index(si)]
             pn_next = self.patch_nums[si + 1] if si != SN - 1 else 0

@@ -1,0 +1,87 @@
+"""Teacher-forced, margin-aware parity of the FULL-WIDTH models against the CPU oracle.
+
+The oracle samples freely; the GPU path is forced onto the oracle's tokens, so both see the same trajectory at every
+scale.  Per scale and per GEMM engine we report
+  max|dlogit|  max abs difference of the CFG-mixed logits (the quantity sampling is sensitive to),
+  flips        tokens the GPU path sampled differently from the oracle (same Exp(1) noise),
+  worst margin the largest oracle top-2 relative margin among the flipped draws (a flip is legitimate only if the
+               oracle's own decision was closer than the numerical resolution of the path).
+usage: [CVAR_SCALE_MUL=5.0] python tools/fullwidth_parity.py <depth> <B> [engines ...]"""
+import os
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from controlvar_b200 import VQVAE, build_control_var, ops, weights as W  # noqa: E402
+from controlvar_b200.config import PathConfig  # noqa: E402
+from oracle import controlvar_oracle as O  # noqa: E402
+
+
+def run(depth, B, engines, seed=0, cfg_scale=1.5, top_k=900, top_p=0.96, quiet=False, scale_mul=None):
+    dev = "cuda"
+    cfg = PathConfig(depth=depth)
+    sd_g = W.synthetic_var_state_dict(cfg, 0, device=dev)
+    vsd_g = W.synthetic_vae_state_dict(cfg, 0, device=dev)
+    if scale_mul is not None:      # stress: every cosine-attention head at this log-multiplier (5.0 clamps to ln 100 = x100)
+        for k in sd_g:
+            if k.endswith("scale_mul_1H11"):
+                sd_g[k].fill_(scale_mul)
+    sd = {k: v.cpu() for k, v in sd_g.items()}
+    vsd = {k: v.cpu() for k, v in vsd_g.items()}
+    label = (torch.arange(B) * 37 + 5) % 1000
+    cond = torch.arange(B) % 4
+    torch.set_num_threads(os.cpu_count())
+    trace = {}
+    t0 = time.time()
+    ref = O.autoregressive_infer_cfg(sd, vsd, cfg.patch_nums, depth, B, label, cond, cfg_scale, top_k, top_p,
+                                     O.cpu_generator_noise(seed), decode=False, trace=trace)
+    t_or = time.time() - t0
+    vae = VQVAE(ch=160).to(dev)
+    var = build_control_var(vae, depth=depth, mask_type="interleave_append", multi_cond=True).to(dev)
+    var.load_state_dict(sd_g), vae.load_state_dict(vsd_g)
+    del sd_g, vsd_g
+    var.rng_device = "cpu"
+    var.debug_capture_logits = True
+    var.debug_forced_idx = ref["idx"]
+    SN = len(cfg.patch_nums)
+    results = {}
+    for eng in engines:
+        ops.set_gemm_engine(eng)
+        var._consts.clear()
+        var.autoregressive_infer_cfg(B, label, g_seed=seed, cfg=cfg_scale, top_k=top_k, top_p=top_p, cond_type=cond)
+        torch.cuda.synchronize()
+        rows = []
+        for si in range(SN):
+            raw = var.last_logits[si].cpu()
+            mixed = O.cfg_combine(raw, B, cfg_scale * (si / (SN - 1)))
+            dl = (mixed - trace["logits_cfg"][si]).abs().max().item()
+            a, b = ref["idx"][si], var.last_idx[si].cpu()
+            margin = O.sampling_margin(trace["logits_masked"][si], trace["q"][si]).view(a.shape)
+            neq = a != b
+            rows.append(dict(si=si, l=a.shape[1], draws=a.numel(), dlogit=dl, flips=int(neq.sum()),
+                             worst_margin=float(margin[neq].max()) if neq.any() else 0.0,
+                             ambiguous_1e4=int((margin < 1e-4).sum()), logit_absmax=trace["logits_cfg"][si].abs().max().item()))
+        fh = (var.last_f_hat.cpu() - ref["f_hat"]).abs().max().item()
+        results[eng] = dict(rows=rows, f_hat_err=fh)
+        if not quiet:
+            name = {0: "SIMT fp32", 1: "tcgen05 1-CTA", 3: "tcgen05 2-CTA (default)"}[eng]
+            print(f"\n== d{depth} B={B} engine {eng} ({name}); oracle {t_or:.1f} s on {torch.get_num_threads()} threads")
+            print(" si    l  draws  max|dlogit|  |logit|max  flips  worst margin of a flip  draws with margin<1e-4")
+            for r in rows:
+                print(f" {r['si']:2d} {r['l']:4d} {r['draws']:6d}   {r['dlogit']:.3e}   {r['logit_absmax']:8.2f}  {r['flips']:5d}  "
+                      f"{r['worst_margin']:.3e}              {r['ambiguous_1e4']:4d}")
+            tot = sum(r["draws"] for r in rows)
+            print(f" total draws {tot}, flips {sum(r['flips'] for r in rows)}, max|dlogit| {max(r['dlogit'] for r in rows):.3e}, "
+                  f"teacher-forced f_hat max err {fh:.3e}")
+    return results
+
+
+if __name__ == "__main__":
+    depth, B = int(sys.argv[1]), int(sys.argv[2])
+    sm = float(os.environ["CVAR_SCALE_MUL"]) if "CVAR_SCALE_MUL" in os.environ else None
+    engines = [int(e) for e in sys.argv[3:]] or [0, 1, 3]
+    if sm is not None:
+        print(f"STRESS: scale_mul_1H11 = {sm} in every block (q multiplier {min(100.0, 2.718281828 ** sm):.0f})")
+    run(depth, B, engines, scale_mul=sm)

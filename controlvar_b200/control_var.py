@@ -104,8 +104,11 @@ class ControlVAR(nn.Module):
         #   debug_forced_idx     per-scale (B, l) tokens that REPLACE the sampled ones after sampling, so that the
         #                        trajectory is pinned to the oracle's while last_idx still reports what was sampled;
         #   debug_capture_logits keep a copy of the raw (2B, l, V) logits of every scale in last_logits.
+        #   debug_noise_fn       callable (scale index, rows, V) -> (rows, V) Exp(1) tensor replacing the generator draw
+        #                        (lets a test feed a sample the very same noise in differently shaped batches).
         self.debug_forced_idx: Optional[List[torch.Tensor]] = None
         self.debug_capture_logits = False
+        self.debug_noise_fn = None
         self.last_logits: List[torch.Tensor] = []
         self.eval()
 
@@ -304,7 +307,11 @@ class ControlVAR(nn.Module):
             ops.gemm(xn, cst["head_w"], self.get_parameter("head.bias"), logits, M, V, C, A_lo=xn_lo)
             # CFG + top-k/top-p + multinomial
             t = cfg * (si / self.num_stages_minus_1)
-            q_noise = self._noise(B * l, V, rng)
+            if self.debug_noise_fn is not None:
+                q_noise = self.debug_noise_fn(si, B * l, V).to(device=dev, dtype=torch.float32).contiguous()
+                assert q_noise.shape == (B * l, V)
+            else:
+                q_noise = self._noise(B * l, V, rng)
             if self.debug_capture_logits:
                 self.last_logits.append(logits[:M].view(R, l, V).clone())
             ops.cfg_sample(logits, q_noise, idx, B, l, V, t, top_k, top_p)

@@ -1,0 +1,84 @@
+"""GPU: size-independent properties at the FULL sizes of BASELINE.json (the benchmark never checks its output, so an
+indexing / overflow bug that only appears at large M would otherwise go unnoticed).
+  1. permutation invariance, d24 B=64 (the bench workload), default engine: permuting the batch (labels, condition types
+     and per-row noise) permutes the outputs and changes nothing else - bit for bit.  Every row takes the same engine
+     path in both runs, so any difference is cross-sample leakage or bad indexing.
+  2. batch independence, d12 B=16 (BASELINE configs[1]) on the SIMT engine: a sample of the batched run equals the same
+     sample run alone with its own noise slice - bit for bit.  (Pinned to one engine because engine choice depends on M;
+     the SIMT engine accumulates in the same k order for every tile shape.)
+  3. determinism at full size: same inputs twice -> identical bits."""
+import pytest
+import torch
+
+from controlvar_b200 import VQVAE, build_control_var, ops, weights as W
+from controlvar_b200.config import PathConfig
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+V = 4096
+
+
+def build(depth):
+    cfg = PathConfig(depth=depth)
+    vae = VQVAE(ch=160).to(DEV)
+    var = build_control_var(vae, depth=depth, mask_type="interleave_append", multi_cond=True).to(DEV)
+    var.load_state_dict(W.synthetic_var_state_dict(cfg, 0, device=DEV))
+    vae.load_state_dict(W.synthetic_vae_state_dict(cfg, 0, device=DEV))
+    return cfg, var
+
+
+def make_noise(cfg, B, seed):
+    """Per-scale (B, l, V) Exp(1) noise, generated on the GPU (it is test input here, not a reference stream)."""
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    return [torch.empty(B, l, V, device=DEV).exponential_(1, generator=g) for l in cfg.scale_lens]
+
+
+def run(var, labels, conds, noise, rows=None):
+    sel = slice(None) if rows is None else rows
+    var.debug_noise_fn = lambda si, n, v: noise[si][sel].reshape(-1, V)
+    B = labels[sel].shape[0]
+    img = var.autoregressive_infer_cfg(B, labels[sel], g_seed=0, cfg=1.5, top_k=900, top_p=0.96, cond_type=conds[sel])
+    torch.cuda.synchronize()
+    var.debug_noise_fn = None
+    return img.clone(), [t.clone() for t in var.last_idx]
+
+
+def test_permutation_invariance_d24_b64_default_engine():
+    assert ops.get_gemm_engine() == ops.ENGINE_TC_2CTA
+    cfg, var = build(24)
+    B = 64
+    labels = (torch.arange(B, device=DEV) * 131 + 7) % 1000
+    conds = torch.arange(B, device=DEV) % 4
+    noise = make_noise(cfg, B, 1)
+    img_a, idx_a = run(var, labels, conds, noise)
+    img_a2, idx_a2 = run(var, labels, conds, noise)
+    assert torch.equal(img_a, img_a2) and all(torch.equal(x, y) for x, y in zip(idx_a, idx_a2)), "not deterministic"
+    perm = torch.randperm(B, generator=torch.Generator().manual_seed(5)).to(DEV)
+    img_b, idx_b = run(var, labels[perm], conds[perm], [n[perm] for n in noise])
+    for si, (x, y) in enumerate(zip(idx_a, idx_b)):
+        assert torch.equal(x[perm], y), f"tokens of scale {si} depend on the position in the batch"
+    assert torch.equal(img_a[perm], img_b), "pixels depend on the position in the batch"
+    assert img_a.shape == (B, 3, 512, 256) and torch.isfinite(img_a).all()
+    assert 0.0 <= img_a.min().item() and img_a.max().item() <= 1.0
+    # different samples must actually differ (guards against a degenerate 'everything equal' pass)
+    assert not torch.equal(img_a[0], img_a[1]) and not torch.equal(idx_a[-1][0], idx_a[-1][1])
+    var.release_workspace()
+
+
+def test_batch_independence_d12_b16_simt_engine():
+    old = ops.set_gemm_engine(ops.ENGINE_SIMT)
+    try:
+        cfg, var = build(12)
+        B = 16
+        labels = (torch.arange(B, device=DEV) * 61 + 3) % 1000
+        conds = torch.zeros(B, dtype=torch.long, device=DEV)          # mask condition, BASELINE configs[1]
+        noise = make_noise(cfg, B, 2)
+        img, idx = run(var, labels, conds, noise)
+        for b in (0, 7, 15):
+            img1, idx1 = run(var, labels, conds, noise, rows=slice(b, b + 1))
+            for si, (x, y) in enumerate(zip(idx, idx1)):
+                assert torch.equal(x[b:b + 1], y), f"sample {b}: tokens of scale {si} depend on the batch it ran in"
+            assert torch.equal(img[b:b + 1], img1), f"sample {b}: pixels depend on the batch it ran in"
+        var.release_workspace()
+    finally:
+        ops.set_gemm_engine(old)

@@ -53,6 +53,7 @@ PROTOTYPES = {
     "cvar_get_gemm_engine": (C.c_int, []),
     "cvar_set_tc_kblock": (C.c_int, [C.c_int]),
     "cvar_debug_set_trace": (C.c_int, [C.c_void_p]),
+    "cvar_debug_set_attn_trace": (C.c_int, [C.c_void_p]),
     "cvar_lvl_pos": (C.c_int, [c_f, c_f, c_f, c_f, C.c_int, C.c_int, C.c_void_p]),
     "cvar_prologue": (C.c_int, [c_f, c_f, c_f, c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, c_f, c_f, c_f, C.c_void_p]),
     "cvar_ln_modulate": (C.c_int, [c_f, c_f, c_f, c_ll, c_f, c_f, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),

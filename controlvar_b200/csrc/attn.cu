@@ -185,6 +185,14 @@ __global__ void __launch_bounds__(256) attn_kvcache_kernel(const float* __restri
 //   TMEM columns: S_main [0,64) S_lo [64,128) P_hi [128,192) P_lo [192,256) O_tile [256,320)
 namespace tcattn {
 using namespace cvar::tc;
+// Optional phase trace (diagnostics): CTA (0,0,0) stamps clock64() per KV tile.  trace[(who * 32 + j) * 8 + ev], j < 32.
+//   who 0 = softmax thread 0: ev 0 s_full seen, 1 S loaded, 2 p computed, 3 o_full(j-1) seen, 4 O updated, 5 P stored+signalled
+//   who 1 = MMA thread:       ev 0 S(j+1) issued, 1 p_ready(j) seen, 2 PV(j) issued
+__device__ long long* g_attn_trace = nullptr;
+__device__ __forceinline__ void astamp(int who, int j, int ev) {
+  if (g_attn_trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && j < 32)
+    g_attn_trace[(who * 32 + j) * 8 + ev] = clock64();
+}
 constexpr int BQ = 128, BKV = 64, D = 64;
 constexpr int kThreads = 192;
 constexpr int kQBlock = BQ * 128;         // bytes of one 32-wide K-block of a Q tile (128 rows x 128 B)
@@ -294,6 +302,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapKhi, const __grid_constant
     float m_run = -INFINITY, l_run = 0.f;
     for (int j = 0; j < ntiles; ++j) {
       mbar_wait(s_full, j & 1);
+      if (row == 0) astamp(0, j, 0);
       tc_fence_after();
       float s[BKV];
       {
@@ -309,6 +318,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapKhi, const __grid_constant
       }
       tc_fence_before();
       mbar_arrive(s_free);
+      if (row == 0) astamp(0, j, 1);
       const int kbase = j * BKV;
       float mx = -INFINITY;
 #pragma unroll
@@ -328,8 +338,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapKhi, const __grid_constant
       }
       l_run = l_run * corr + rs;
       m_run = m_new;
+      if (row == 0) astamp(0, j, 2);
       if (j > 0) {
         mbar_wait(o_full, (j - 1) & 1);
+        if (row == 0) astamp(0, j, 3);
         tc_fence_after();
         float a[32];
         tmem_ld_32x32b_x32(tlane + kColO, a);
@@ -339,6 +351,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapKhi, const __grid_constant
 #pragma unroll
         for (int c = 0; c < 32; ++c) o_reg[32 + c] = (o_reg[32 + c] + a[c]) * corr;
       }
+      if (row == 0) astamp(0, j, 4);
       // P(j) -> TMEM as the A operand of P @ V, split hi/lo (P(j-1) was consumed: o_full(j-1) has been observed)
       {
         float hi[32], lo[32];
@@ -356,6 +369,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapKhi, const __grid_constant
       }
       tc_fence_before();
       mbar_arrive(p_ready);
+      if (row == 0) astamp(0, j, 5);
     }
     mbar_wait(o_full, (ntiles - 1) & 1);
     tc_fence_after();
@@ -428,8 +442,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapKhi, const __grid_constant
           mbar_wait(s_free, j & 1);
           tc_fence_after();
           issue_S(j + 1);
+          astamp(1, j, 0);
         }
         mbar_wait(p_ready, j & 1);
+        astamp(1, j, 1);
         tc_fence_after();
         unsigned char* st = stage(j & 1);
 #pragma unroll
@@ -443,6 +459,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapKhi, const __grid_constant
         }
         umma_commit(o_full);
         umma_commit(&kv_empty[j & 1]);
+        astamp(1, j, 2);
       }
     }
   }
@@ -485,7 +502,10 @@ static int make_map3(CUtensorMap* map, const float* base, long long inner, long 
   }
   return 0;
 }
+int set_trace(long long* p) { return cudaMemcpyToSymbol(g_attn_trace, &p, sizeof(p)) == cudaSuccess ? 0 : -1; }
 }  // namespace tcattn
+
+extern "C" int cvar_debug_set_attn_trace(long long* dev_buf) { return tcattn::set_trace(dev_buf); }
 
 extern "C" int cvar_attn_kvcache(const float* q, const float* k_hi, const float* k_lo, const float* vt_hi,
                                  const float* vt_lo, float* out, float* out_lo, int R, int H, int l, int L, int T_max,

@@ -41,6 +41,7 @@ class ConvArgs(C.Structure):
         ("B", C.c_int), ("Hin", C.c_int), ("Win", C.c_int), ("Cin", C.c_int), ("Cout", C.c_int), ("ks", C.c_int),
         ("upsample2x", C.c_int),
         ("out_mode", C.c_int), ("out_rows_total", C.c_int), ("row_offset", C.c_int),
+        ("engine", C.c_int),
     ]
 
 

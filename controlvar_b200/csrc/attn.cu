@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(256) attn_kvcache_kernel(const float* __restri
 //              tensor core's round-toward-zero accumulation never runs longer than 8 steps.
 //   warp 4     TMA issue (8 boxes per tile: K_hi, K_lo, V^T_hi, V^T_lo, two 128-byte-wide blocks each)
 //   warp 5     TMEM allocation + MMA issue; S(j+1) is issued before P@V(j) so QK^T of the next tile overlaps softmax(j)
-//   TMEM columns: S_main [0,64) S_lo [64,128) P_hi [128,192) P_lo [192,256) O_tile [256,320)
+//   TMEM columns: S_main [0,64) S_lo [64,128) P_hi [128,192) P_lo [192,256) O_tile [256,320) Q_hi [320,384) Q_lo [384,448)
 namespace tcattn {
 using namespace cvar::tc;
 // Optional phase trace (diagnostics): CTA (0,0,0) stamps clock64() per KV tile.  trace[(who * 32 + j) * 8 + ev], j < 32.
@@ -195,12 +195,15 @@ __device__ __forceinline__ void astamp(int who, int j, int ev) {
 }
 constexpr int BQ = 128, BKV = 64, D = 64;
 constexpr int kThreads = 192;
-constexpr int kQBlock = BQ * 128;         // bytes of one 32-wide K-block of a Q tile (128 rows x 128 B)
 constexpr int kKVBlock = BKV * 128;       // bytes of one 32-wide K-block of a K / V^T tile (64 rows x 128 B)
-constexpr int kQBytes = 2 * 2 * kQBlock;                 // hi + lo, two d-blocks each       = 64 KiB
 constexpr int kStageBytes = 4 * 2 * kKVBlock;            // K_hi K_lo VT_hi VT_lo, two blocks = 64 KiB
-constexpr int kSmem = kQBytes + 2 * kStageBytes + 1024 + 1024;
-constexpr uint32_t kColSmain = 0, kColSlo = 64, kColPhi = 128, kColPlo = 192, kColO = 256;
+// Q lives in TMEM (the A operand of S = Q K^T is read from there, like P for P @ V), so shared memory holds nothing but
+// the K/V ring and THREE stages fit.  The phase trace of the 2-stage version (profiles/r01_attn_trace.md) showed the
+// ~2700-cycle TMA round trip of a tile on the critical path of every iteration: the softmax threads waited for S half
+// of the time.
+constexpr int kStages = 3;
+constexpr int kSmem = kStages * kStageBytes + 1024 + 1024;
+constexpr uint32_t kColSmain = 0, kColSlo = 64, kColPhi = 128, kColPlo = 192, kColO = 256, kColQhi = 320, kColQlo = 384;
 constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
 __device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
@@ -242,17 +245,15 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapKhi, const __grid_constant
   using G = Geo<32>;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  unsigned char* q_hi = smem;                       // [2 blocks][128 rows][128 B]
-  unsigned char* q_lo = smem + 2 * kQBlock;
-  auto stage = [&](int s) { return smem + kQBytes + s * kStageBytes; };   // K_hi | K_lo | VT_hi | VT_lo (2 blocks each)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kQBytes + 2 * kStageBytes);
-  uint64_t* kv_full = bars;          // [2]
-  uint64_t* kv_empty = bars + 2;     // [2]
-  uint64_t* s_full = bars + 4;       // S(j) accumulated
-  uint64_t* s_free = bars + 5;       // S(j) read by all 128 softmax threads
-  uint64_t* p_ready = bars + 6;      // P(j) written to TMEM by all 128 softmax threads
-  uint64_t* o_full = bars + 7;       // O_tile(j) accumulated
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  auto stage = [&](int s) { return smem + s * kStageBytes; };   // K_hi | K_lo | VT_hi | VT_lo (2 blocks each)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint64_t* kv_full = bars;                  // [kStages]
+  uint64_t* kv_empty = bars + kStages;       // [kStages]
+  uint64_t* s_full = bars + 2 * kStages;     // S(j) accumulated
+  uint64_t* s_free = bars + 2 * kStages + 1; // S(j) read by all 128 softmax threads
+  uint64_t* p_ready = bars + 2 * kStages + 2;// P(j) written to TMEM by all 128 softmax threads
+  uint64_t* o_full = bars + 2 * kStages + 3; // O_tile(j) accumulated
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * BQ, h = blockIdx.y, r = blockIdx.z;
@@ -261,7 +262,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapKhi, const __grid_constant
 
   if (warp == 4 && lane == 0) {
     tma_prefetch_desc(&mapKhi), tma_prefetch_desc(&mapKlo), tma_prefetch_desc(&mapVhi), tma_prefetch_desc(&mapVlo);
-    for (int s = 0; s < 2; ++s) mbar_init(&kv_full[s], 1), mbar_init(&kv_empty[s], 1);
+    for (int s = 0; s < kStages; ++s) mbar_init(&kv_full[s], 1), mbar_init(&kv_empty[s], 1);
     mbar_init(s_full, 1);
     mbar_init(s_free, 128);
     mbar_init(p_ready, 128);
@@ -269,28 +270,37 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapKhi, const __grid_constant
     fence_barrier_init();
   }
   if (warp == 5) tmem_alloc(tmem_slot, 512);
-  if (warp < 4) {
-    // Q tile: load, pre-scale, split hi/lo, store K-major 128B-swizzled (two 32-wide d-blocks)
-    const float* qb = q + (rh * l) * D;
-    for (int i = 0; i < 16; ++i) {
-      int item = i * 128 + threadIdx.x;
-      int row = item >> 4, c16 = item & 15;
-      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (q0 + row < l) x = ld4(qb + (long long)(q0 + row) * D + c16 * 4);
-      x.x *= scale, x.y *= scale, x.z *= scale, x.w *= scale;
-      float4 hv, lv;
-      hv.x = trunc_tf32(x.x), hv.y = trunc_tf32(x.y), hv.z = trunc_tf32(x.z), hv.w = trunc_tf32(x.w);
-      lv.x = x.x - hv.x, lv.y = x.y - hv.y, lv.z = x.z - hv.z, lv.w = x.w - hv.w;
-      uint32_t off = (uint32_t)(c16 >> 3) * kQBlock + G::offset(row, c16 & 7);
-      *reinterpret_cast<float4*>(q_hi + off) = hv;
-      *reinterpret_cast<float4*>(q_lo + off) = lv;
-    }
-    fence_proxy_async();
-  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (warp < 4) {
+    // Q row of this thread: load, pre-scale, split hi/lo, park in TMEM (lane = query row, column = d) as the A operand
+    const int qrow = q0 + (int)threadIdx.x;
+    const float* qp = q + (rh * l + qrow) * D;
+    const uint32_t tl = tmem_base + ((uint32_t)(warp * 32) << 16);
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      float hi[32], lo[32];
+#pragma unroll
+      for (int c4 = 0; c4 < 8; ++c4) {
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (qrow < l) x = ld4(qp + half * 32 + c4 * 4);
+        const float xs[4] = {x.x * scale, x.y * scale, x.z * scale, x.w * scale};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          hi[c4 * 4 + e] = trunc_tf32(xs[e]);
+          lo[c4 * 4 + e] = xs[e] - hi[c4 * 4 + e];
+        }
+      }
+      tmem_st_32x32b_x32(tl + kColQhi + half * 32, hi);
+      tmem_st_32x32b_x32(tl + kColQlo + half * 32, lo);
+    }
+    tmem_wait_st();
+  }
+  tc_fence_before();
+  __syncthreads();      // Q is in TMEM before the first S = Q K^T is issued
+  tc_fence_after();
 
   if (warp < 4) {
     // ================================================================ softmax + output rows
@@ -401,8 +411,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapKhi, const __grid_constant
     // ================================================================ TMA: K / V^T tiles, pre-split
     if (lane == 0) {
       for (int j = 0; j < ntiles; ++j) {
-        const int s = j & 1;
-        mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1);
+        const int s = j % kStages;
+        mbar_wait(&kv_empty[s], ((j / kStages) & 1) ^ 1);
         mbar_arrive_expect_tx(&kv_full[s], (uint32_t)kStageBytes);
         unsigned char* st = stage(s);
 #pragma unroll
@@ -418,17 +428,17 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapKhi, const __grid_constant
     // ================================================================ MMA issue
     if (lane == 0) {
       auto issue_S = [&](int j) {
-        unsigned char* st = stage(j & 1);
+        unsigned char* st = stage(j % kStages);
 #pragma unroll
         for (int kb = 0; kb < 2; ++kb) {
-          const uint64_t dqh = G::desc(smem_u32(q_hi + kb * kQBlock)), dql = G::desc(smem_u32(q_lo + kb * kQBlock));
           const uint64_t dkh = G::desc(smem_u32(st + (0 + kb) * kKVBlock)), dkl = G::desc(smem_u32(st + (2 + kb) * kKVBlock));
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const uint64_t adv = (uint64_t)(2 * k);
-            umma_tf32(tmem_base + kColSlo, dql + adv, dkh + adv, kIdesc, (kb | k) != 0);
-            umma_tf32(tmem_base + kColSlo, dqh + adv, dkl + adv, kIdesc, 1u);
-            umma_tf32(tmem_base + kColSmain, dqh + adv, dkh + adv, kIdesc, (kb | k) != 0);
+            const uint32_t qc = (uint32_t)((kb * 4 + k) * 8);       // 8 d-columns of Q per k-step
+            umma_tf32_ts(tmem_base + kColSlo, tmem_base + kColQlo + qc, dkh + adv, kIdesc, (kb | k) != 0);
+            umma_tf32_ts(tmem_base + kColSlo, tmem_base + kColQhi + qc, dkl + adv, kIdesc, 1u);
+            umma_tf32_ts(tmem_base + kColSmain, tmem_base + kColQhi + qc, dkh + adv, kIdesc, (kb | k) != 0);
           }
         }
         umma_commit(s_full);
@@ -438,7 +448,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapKhi, const __grid_constant
       issue_S(0);
       for (int j = 0; j < ntiles; ++j) {
         if (j + 1 < ntiles) {
-          mbar_wait(&kv_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
+          mbar_wait(&kv_full[(j + 1) % kStages], ((j + 1) / kStages) & 1);
           mbar_wait(s_free, j & 1);
           tc_fence_after();
           issue_S(j + 1);
@@ -447,7 +457,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapKhi, const __grid_constant
         mbar_wait(p_ready, j & 1);
         astamp(1, j, 1);
         tc_fence_after();
-        unsigned char* st = stage(j & 1);
+        unsigned char* st = stage(j % kStages);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const uint64_t adv = (uint64_t)(2 * (k & 3));
@@ -458,7 +468,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapKhi, const __grid_constant
           umma_tf32_ts(tmem_base + kColO, tmem_base + kColPhi + 8 * k, dvh, kIdesc, 1u);
         }
         umma_commit(o_full);
-        umma_commit(&kv_empty[j & 1]);
+        umma_commit(&kv_empty[j % kStages]);
         astamp(1, j, 2);
       }
     }

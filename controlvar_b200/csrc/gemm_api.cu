@@ -131,7 +131,7 @@ extern "C" int cvar_conv2d(const cvar_conv_args* a, void* stream) {
   CVAR_REQUIRE(a->out_mode == 0 || a->resid == nullptr, "cvar_conv2d: image output takes no residual");
   CVAR_REQUIRE((a->in_a == nullptr) == (a->in_b == nullptr), "cvar_conv2d: in_a/in_b must come together");
   cudaStream_t s = (cudaStream_t)stream;
-  if (g_gemm_engine != 0 && a->w_hi != nullptr && a->w_lo != nullptr) {
+  if (g_gemm_engine != 0 && a->engine != 0 && a->w_hi != nullptr && a->w_lo != nullptr) {
     int took = tc_conv_try(a, s);
     if (took < 0) return took;
     if (took == 1) return 0;

@@ -243,7 +243,7 @@ def gn_stats(x_nhwc, gamma, beta, a_out, b_out, scratch, B, HW, Cdim, groups=32,
 
 
 def conv2d(x, w_packed, bias, out, B, Hin, Win, Cin, Cout, ks, *, in_a=None, in_b=None, in_silu=False, resid=None,
-           upsample2x=False, out_mode=0, out_rows_total=0, row_offset=0):
+           upsample2x=False, out_mode=0, out_rows_total=0, row_offset=0, engine=-1):
     w_packed, w_hi, w_lo = _wparts(w_packed)
     _chk(x, w_packed, bias, out, in_a, in_b, resid)
     a = ConvArgs()
@@ -253,6 +253,7 @@ def conv2d(x, w_packed, bias, out, B, Hin, Win, Cin, Cout, ks, *, in_a=None, in_
     a.resid = _p(resid)
     a.B, a.Hin, a.Win, a.Cin, a.Cout, a.ks, a.upsample2x = B, Hin, Win, Cin, Cout, ks, int(upsample2x)
     a.out_mode, a.out_rows_total, a.row_offset = out_mode, out_rows_total, row_offset
+    a.engine = int(engine)
     up = 2 if upsample2x else 1
     Mo = B * Hin * up * Win * up
     with _Timed("conv", 2.0 * Mo * Cout * ks * ks * Cin, 4.0 * (B * Hin * Win * Cin + Mo * Cout + Cout * ks * ks * Cin)):

@@ -61,6 +61,11 @@ class VQVAE(nn.Module):
         q = self.quantize
         q.vocab_size, q.Cvae, q.v_patch_nums, q.share_quant_resi = vocab_size, z_channels, tuple(v_patch_nums), share_quant_resi
         self._plan = decoder_plan(self.cfg)
+        # Decoder convolutions whose output side is below this run on the SIMT fp32 engine.  Measured on B200
+        # (profiles/r01_decoder_policy.md): with every conv on tensor cores the worst pixel is 2.2e-4 off the fp32
+        # oracle (north-star bound: 1e-4); the 16x16 / 32x32 layers (K up to 5760, few pixels) cause most of that and
+        # cost almost nothing, so they stay in exact fp32: worst pixel 5.9e-5 for +50 ms per 64-image decode.
+        self.tc_min_hw = 64
         self._packed: Dict[str, torch.Tensor] = {}
         self._ws: Dict[Tuple, torch.Tensor] = {}
         self.eval()
@@ -96,6 +101,10 @@ class VQVAE(nn.Module):
             self._packed[key] = t
         return t
 
+    def _conv(self, x, w, bias, out, B, Hin, Win, Cin, Cout, ks, **kw):
+        hout = Hin * (2 if kw.get("upsample2x") else 1)
+        return ops.conv2d(x, w, bias, out, B, Hin, Win, Cin, Cout, ks, engine=(-1 if hout >= self.tc_min_hw else 0), **kw)
+
     def _buf(self, name: str, shape, dtype=torch.float32) -> torch.Tensor:
         dev = self._w("post_quant_conv.weight").device
         key = (name, tuple(shape), dtype)
@@ -127,15 +136,15 @@ class VQVAE(nn.Module):
     def _resblock(self, x, prefix, B, H, W, cin, cout, bufs):
         """ResnetBlock.forward (vae_modules.py:57-60); x is never written."""
         h1, out = bufs
-        ops.conv2d(self._norm_act(x, prefix + "norm1", B, H, W, cin, 0), self._conv_w(prefix + "conv1"),
+        self._conv(self._norm_act(x, prefix + "norm1", B, H, W, cin, 0), self._conv_w(prefix + "conv1"),
                    self._w(prefix + "conv1.bias"), h1, B, H, W, cin, cout, 3)
         if cin != cout:
             sc = self._buf("shortcut", (B, H, W, cout))
-            ops.conv2d(x, self._conv_w(prefix + "nin_shortcut"), self._w(prefix + "nin_shortcut.bias"), sc, B, H, W,
+            self._conv(x, self._conv_w(prefix + "nin_shortcut"), self._w(prefix + "nin_shortcut.bias"), sc, B, H, W,
                        cin, cout, 1)
         else:
             sc = x
-        ops.conv2d(self._norm_act(h1, prefix + "norm2", B, H, W, cout, 1), self._conv_w(prefix + "conv2"),
+        self._conv(self._norm_act(h1, prefix + "norm2", B, H, W, cout, 1), self._conv_w(prefix + "conv2"),
                    self._w(prefix + "conv2.bias"), out, B, H, W, cout, cout, 3, resid=sc)
         return out
 
@@ -166,7 +175,7 @@ class VQVAE(nn.Module):
         cfg = self.cfg
         H = W = hw
         zq = self._buf("z_pq", (B, H, W, cfg.Cvae))
-        ops.conv2d(z_nhwc, self._conv_w("post_quant_conv"), self._w("post_quant_conv.bias"), zq, B, H, W, cfg.Cvae,
+        self._conv(z_nhwc, self._conv_w("post_quant_conv"), self._w("post_quant_conv.bias"), zq, B, H, W, cfg.Cvae,
                    cfg.Cvae, 3)
         cur = zq
         ring_i = 0
@@ -190,7 +199,7 @@ class VQVAE(nn.Module):
         for op, prefix, cin, cout in self._plan:
             if op == "conv3":
                 out = ring((B, H, W, cout))
-                ops.conv2d(cur, self._conv_w(prefix), self._w(prefix + ".bias"), out, B, H, W, cin, cout, 3)
+                self._conv(cur, self._conv_w(prefix), self._w(prefix + ".bias"), out, B, H, W, cin, cout, 3)
                 cur = out
             elif op == "res":
                 h1 = ring((B, H, W, cout))
@@ -201,12 +210,12 @@ class VQVAE(nn.Module):
                 cur = self._attnblock(cur, prefix, B, H, W, cin, out)
             elif op == "up":
                 out = ring((B, 2 * H, 2 * W, cout))
-                ops.conv2d(cur, self._conv_w(prefix), self._w(prefix + ".bias"), out, B, H, W, cin, cout, 3,
+                self._conv(cur, self._conv_w(prefix), self._w(prefix + ".bias"), out, B, H, W, cin, cout, 3,
                            upsample2x=True)
                 H, W = 2 * H, 2 * W
                 cur = out
             elif op == "out":
-                ops.conv2d(self._norm_act(cur, "decoder.norm_out", B, H, W, cin, 0), self._conv_w("decoder.conv_out"),
+                self._conv(self._norm_act(cur, "decoder.norm_out", B, H, W, cin, 0), self._conv_w("decoder.conv_out"),
                            self._w("decoder.conv_out.bias"), img_out, B, H, W, cin, 3, 3, out_mode=out_mode,
                            out_rows_total=rows_total, row_offset=row_offset)
             else:

@@ -173,6 +173,7 @@ typedef struct {
   const float* resid;
   int B, Hin, Win, Cin, Cout, ks, upsample2x;
   int out_mode, out_rows_total, row_offset;
+  int engine;   /* -1 = library default (cvar_set_gemm_engine); 0 = force the SIMT fp32 engine for this call */
 } cvar_conv_args;
 CVAR_API int cvar_conv2d(const cvar_conv_args* args, void* stream);
 /* hi = w with the 13 low mantissa bits cleared (what a TF32 tensor-core operand keeps), lo = w - hi (exact): the

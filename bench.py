@@ -283,7 +283,8 @@ def main_ours(args, wl):
             cpu = {"value": args.cpu_sample_batch / times[0], "unit": "images/s", "cores": cores, "kind": "port",
                    "sample": f"{args.cpu_sample_batch} image(s), one call of the same workload on the host cores; " + CPU_BATCH_NOTE}
         engine_name = {0: "simt-fp32", 1: "tcgen05-3xtf32 (1 CTA per tile)",
-                       3: "tcgen05-3xtf32 (2-CTA all-TMA dense layers, 1-CTA convs)"}.get(ops.get_gemm_engine(), "?")
+                       3: "tcgen05-3xtf32 (2-CTA all-TMA dense layers, 1-CTA convs)",
+                       4: "tcgen05 f16x3 dense layers (FP16 pairs, 2-CTA all-TMA) + 3xtf32 attention / convs"}.get(ops.get_gemm_engine(), "?")
         line = {"metric": f"images/sec (256x256, d{depth}, CFG=1.5)", "value": value, "unit": "images/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -310,7 +311,8 @@ if __name__ == "__main__":
     ap.add_argument("--workload", default="d24_b64", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch of the workload")
     ap.add_argument("--engine", type=int, default=int(os.environ.get("CVAR_GEMM_ENGINE", "3")),
-                    help="0 SIMT fp32, 1 tcgen05 3xTF32 (1 CTA per tile), 3 = 1 plus the 2-CTA all-TMA kernel for dense layers")
+                    help="0 SIMT fp32, 1 tcgen05 3xTF32 (1 CTA per tile), 3 = 1 plus the 2-CTA all-TMA kernel for dense layers, "
+                         "4 = 3 with FP16-pair (f16x3) dense layers")
     ap.add_argument("--cpu-sample-batch", type=int, default=8,
                     help="images per CPU-reference step (bounded sample: ~20 s of CPU work at d24 on 16 cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

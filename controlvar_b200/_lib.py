@@ -29,6 +29,9 @@ class GemmArgs(C.Structure):
         ("gamma", C.c_void_p), ("gamma_row_stride", c_ll), ("rows_per_sample", C.c_int),
         ("resid", C.c_void_p), ("ldr", c_ll), ("strideR", c_ll),
         ("out_lo", C.c_void_p),
+        ("A16_hi", C.c_void_p), ("A16_lo", C.c_void_p),
+        ("W16_hi", C.c_void_p), ("W16_lo", C.c_void_p),
+        ("out16_hi", C.c_void_p), ("out16_lo", C.c_void_p),
     ]
 
 
@@ -57,12 +60,14 @@ PROTOTYPES = {
     "cvar_debug_set_attn_trace": (C.c_int, [C.c_void_p]),
     "cvar_lvl_pos": (C.c_int, [c_f, c_f, c_f, c_f, C.c_int, C.c_int, C.c_void_p]),
     "cvar_prologue": (C.c_int, [c_f, c_f, c_f, c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, c_f, c_f, c_f, C.c_void_p]),
-    "cvar_ln_modulate": (C.c_int, [c_f, c_f, c_f, c_ll, c_f, c_f, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
+    "cvar_ln_modulate": (C.c_int, [c_f, c_f, c_f, c_ll, c_f, c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
     "cvar_gemm": (C.c_int, [C.POINTER(GemmArgs), C.c_void_p]),
-    "cvar_qkv_project": (C.c_int, [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, C.c_int, C.c_int,
+    "cvar_qkv_project": (C.c_int, [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f,
+                                   C.c_int, C.c_int,
                                    C.c_int, C.c_int, C.c_int, C.c_int, c_f, C.c_void_p]),
     "cvar_split_tf32": (C.c_int, [c_f, c_f, c_f, c_ll, C.c_void_p]),
-    "cvar_attn_kvcache": (C.c_int, [c_f, c_f, c_f, c_f, c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+    "cvar_split_f16": (C.c_int, [c_f, c_f, c_f, c_ll, C.c_void_p]),
+    "cvar_attn_kvcache": (C.c_int, [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                     C.c_float, C.c_int, C.c_void_p]),
     "cvar_cfg_sample": (C.c_int, [c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_double,
                                   C.c_void_p]),

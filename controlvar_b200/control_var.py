@@ -137,6 +137,9 @@ class ControlVAR(nn.Module):
             self._ws[key] = t
         return t[:n].view(shape)
 
+    def _pair(self, name: str, shape) -> "ops.F16Pair":
+        return ops.F16Pair(self._buf(name + ".hi", shape, torch.float16), self._buf(name + ".lo", shape, torch.float16))
+
     def _kv_caches(self, depth, R, H, T):
         """Per-block KV arenas (cached across calls; zero-filled once - every call rewrites the keys it reads)."""
         key = ("kv", depth, R, H, T)
@@ -172,7 +175,11 @@ class ControlVAR(nn.Module):
 
     def _constants(self):
         c = self._consts
+        f16 = ops.get_gemm_engine() == ops.ENGINE_TC_F16X3
+        if c and c.get("f16") != f16:        # the engine changed since the weights were put in operand form
+            c.clear()
         if not c:
+            c["f16"] = f16
             dev, cfg = self.device, self.cfg
             hw = self.patch_nums[-1]
             c["U"] = {pn: bicubic_matrix(pn, hw).to(dev) for pn in set(self.patch_nums) if pn != hw}
@@ -182,7 +189,8 @@ class ControlVAR(nn.Module):
             blocks = []
             for i in range(self.depth):
                 p = f"blocks.{i}."
-                SW = ops.SplitWeight     # TF32 hi/lo split, once per weight: the tcgen05 engine's TMA operands
+                # operand form of the tensor-core engine, made once per weight: TF32 hi/lo split, or FP16 pairs (engine 4)
+                SW = (lambda w: ops.SplitWeight(w, f16=True)) if f16 else ops.SplitWeight
                 blocks.append(dict(
                     qkv_w=SW(P(p + "attn.mat_qkv.weight")), q_bias=P(p + "attn.q_bias"), v_bias=P(p + "attn.v_bias"),
                     k_bias=self.get_buffer(p + "attn.zero_k_bias"),
@@ -194,7 +202,7 @@ class ControlVAR(nn.Module):
                 ))
             c["blocks"] = blocks
             c["head_ada_w"], c["head_ada_b"] = P("head_nm.ada_lin.1.weight"), P("head_nm.ada_lin.1.bias")
-            c["head_w"] = ops.SplitWeight(P("head.weight"))
+            c["head_w"] = ops.SplitWeight(P("head.weight"), f16=f16)
             vq = self.vae_proxy[0]
             c["phi"] = [(vq.get_parameter(f"quantize.quant_resi.qresi_ls.{k}.weight"),
                          vq.get_parameter(f"quantize.quant_resi.qresi_ls.{k}.bias"))
@@ -257,10 +265,15 @@ class ControlVAR(nn.Module):
         ada = self._buf("ada", (depth, R, 6 * C))
         ada_head = self._buf("ada_head", (R, 2 * C))
         x = self._buf("x", (R * lmax, C))
-        xn = self._buf("xn", (R * lmax, C))
-        attn_o = self._buf("attn_o", (R * lmax, C))
         qbuf = self._buf("q", (R * H * lmax * 64,))
-        hid = self._buf("hid", (R * lmax, 4 * C))
+        # engine 4 (f16x3): every dense-layer input is produced as an FP16 pair and never exists in fp32
+        f16 = cst["f16"]
+        xn16 = self._pair("xn16", (R * lmax, C)) if f16 else None
+        attn_o16 = self._pair("attn_o16", (R * lmax, C)) if f16 else None
+        hid16 = self._pair("hid16", (R * lmax, 4 * C)) if f16 else None
+        xn = None if f16 else self._buf("xn", (R * lmax, C))
+        attn_o = None if f16 else self._buf("attn_o", (R * lmax, C))
+        hid = None if f16 else self._buf("hid", (R * lmax, 4 * C))
         # engine 3 (2-CTA all-TMA GEMM): every GEMM input is produced already split hi/lo; the '*_lo' halves live here
         split = ops.get_gemm_engine() == ops.ENGINE_TC_2CTA
         xn_lo = self._buf("xn_lo", (R * lmax, C)) if split else None
@@ -276,8 +289,9 @@ class ControlVAR(nn.Module):
         ops.prologue(self.get_parameter("class_emb.weight"),
                      self.get_parameter("cond_embed.weight") if self.multi_cond else None, self.pos_start,
                      lvl_pos, label_B, cond_type, self.num_classes, cond_BD, silu_cond, x)
+        silu16 = ops.F16Pair.from_tensor(silu_cond, out=self._pair("silu16", (R, C))) if f16 else None
         for bi, blk in enumerate(cst["blocks"]):       # ada_lin = Linear(SiLU(cond)): constant across scales
-            ops.gemm(silu_cond, blk["ada_w"], blk["ada_b"], ada[bi], R, 6 * C, C)
+            ops.gemm(silu_cond, blk["ada_w"], blk["ada_b"], ada[bi], R, 6 * C, C, A16=silu16)
         ops.gemm(silu_cond, cst["head_ada_w"], cst["head_ada_b"], ada_head, R, 2 * C, C)
 
         self.last_idx = []
@@ -291,20 +305,21 @@ class ControlVAR(nn.Module):
             for bi, blk in enumerate(cst["blocks"]):
                 a = ada[bi]                                # (R, 6C): gamma1, gamma2, scale1, scale2, shift1, shift2
                 g1, g2, s1, s2, b1, b2 = (a[:, k * C:(k + 1) * C] for k in range(6))
-                ops.ln_modulate(x, s1, b1, 6 * C, xn, M, C, l, self.norm_eps, out_lo=xn_lo)
+                ops.ln_modulate(x, s1, b1, 6 * C, xn, M, C, l, self.norm_eps, out_lo=xn_lo, out16=xn16)
                 ops.qkv_project(xn, blk["qkv_w"], blk["q_bias"], blk["k_bias"], blk["v_bias"], qbuf, caches[bi],
-                                R, l, L_prev, H, self.cos_attn, blk["scale_mul"], A_lo=xn_lo)
-                ops.attn_kvcache(qbuf, caches[bi], attn_o, R, H, l, cur_L, attn_scale, out_lo=attn_o_lo)
-                ops.gemm(attn_o, blk["proj_w"], blk["proj_b"], x, M, C, C, A_lo=attn_o_lo,
+                                R, l, L_prev, H, self.cos_attn, blk["scale_mul"], A_lo=xn_lo, A16=xn16)
+                ops.attn_kvcache(qbuf, caches[bi], attn_o, R, H, l, cur_L, attn_scale, out_lo=attn_o_lo, out16=attn_o16)
+                ops.gemm(attn_o, blk["proj_w"], blk["proj_b"], x, M, C, C, A_lo=attn_o_lo, A16=attn_o16,
                          epilogue=ops.EPI_BIAS_GAMMA_RESID, gamma=g1, gamma_row_stride=6 * C, rows_per_sample=l)
-                ops.ln_modulate(x, s2, b2, 6 * C, xn, M, C, l, self.norm_eps, out_lo=xn_lo)
+                ops.ln_modulate(x, s2, b2, 6 * C, xn, M, C, l, self.norm_eps, out_lo=xn_lo, out16=xn16)
                 ops.gemm(xn, blk["fc1_w"], blk["fc1_b"], hid, M, 4 * C, C, epilogue=ops.EPI_BIAS_GELU, A_lo=xn_lo,
-                         out_lo=hid_lo)
-                ops.gemm(hid, blk["fc2_w"], blk["fc2_b"], x, M, C, 4 * C, A_lo=hid_lo,
+                         out_lo=hid_lo, A16=xn16, out16=hid16)
+                ops.gemm(hid, blk["fc2_w"], blk["fc2_b"], x, M, C, 4 * C, A_lo=hid_lo, A16=hid16,
                          epilogue=ops.EPI_BIAS_GAMMA_RESID, gamma=g2, gamma_row_stride=6 * C, rows_per_sample=l)
             # head: AdaLNBeforeHead + Linear(C, V)
-            ops.ln_modulate(x, ada_head[:, :C], ada_head[:, C:], 2 * C, xn, M, C, l, self.norm_eps, out_lo=xn_lo)
-            ops.gemm(xn, cst["head_w"], self.get_parameter("head.bias"), logits, M, V, C, A_lo=xn_lo)
+            ops.ln_modulate(x, ada_head[:, :C], ada_head[:, C:], 2 * C, xn, M, C, l, self.norm_eps, out_lo=xn_lo,
+                            out16=xn16)
+            ops.gemm(xn, cst["head_w"], self.get_parameter("head.bias"), logits, M, V, C, A_lo=xn_lo, A16=xn16)
             # CFG + top-k/top-p + multinomial
             t = cfg * (si / self.num_stages_minus_1)
             if self.debug_noise_fn is not None:

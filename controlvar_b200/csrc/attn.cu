@@ -22,7 +22,8 @@ __global__ void __launch_bounds__(256) attn_kvcache_kernel(const float* __restri
                                                            const float* __restrict__ k_lo,
                                                            const float* __restrict__ vt_hi,
                                                            const float* __restrict__ vt_lo, float* __restrict__ out,
-                                                           float* __restrict__ out_lo, int H, int l, int L, int T_max,
+                                                           float* __restrict__ out_lo, __half* __restrict__ o16_hi,
+                                                           __half* __restrict__ o16_lo, int H, int l, int L, int T_max,
                                                            float scale) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   AttnSmem& sm = *reinterpret_cast<AttnSmem*>(smem_raw);
@@ -160,6 +161,11 @@ __global__ void __launch_bounds__(256) attn_kvcache_kernel(const float* __restri
       float inv = 1.0f / lrow[i];
       float4 v = make_float4(o[i][0] * inv, o[i][1] * inv, o[i][2] * inv, o[i][3] * inv);
       const long long off = ((long long)r * l + t) * C + h * D + tx * 4;
+      if (o16_hi != nullptr) {     // FP16 pair for the f16x3 proj GEMM
+        const float vv[4] = {v.x, v.y, v.z, v.w};
+        st4_split_f16(o16_hi + off, o16_lo + off, vv);
+        if (out == nullptr) continue;
+      }
       if (out_lo != nullptr) {     // TF32 split for the all-TMA proj GEMM
         float4 hi = make_float4(tc::trunc_tf32(v.x), tc::trunc_tf32(v.y), tc::trunc_tf32(v.z), tc::trunc_tf32(v.w));
         st4(out_lo + off, make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w));
@@ -240,7 +246,8 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 __global__ void __launch_bounds__(kThreads, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap mapKhi, const __grid_constant__ CUtensorMap mapKlo,
                const __grid_constant__ CUtensorMap mapVhi, const __grid_constant__ CUtensorMap mapVlo,
-               const float* __restrict__ q, float* __restrict__ out, float* __restrict__ out_lo, int H, int l, int L,
+               const float* __restrict__ q, float* __restrict__ out, float* __restrict__ out_lo,
+               __half* __restrict__ o16_hi, __half* __restrict__ o16_lo, int H, int l, int L,
                float scale) {
   using G = Geo<32>;
   extern __shared__ unsigned char smem_raw[];
@@ -399,6 +406,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapKhi, const __grid_constant
 #pragma unroll
       for (int d = 0; d < D; d += 4) {
         float4 v = make_float4(o_reg[d] * inv, o_reg[d + 1] * inv, o_reg[d + 2] * inv, o_reg[d + 3] * inv);
+        if (o16_hi != nullptr) {   // FP16 pair for the f16x3 proj GEMM
+          const float vv[4] = {v.x, v.y, v.z, v.w};
+          st4_split_f16(o16_hi + off + d, o16_lo + off + d, vv);
+          if (out == nullptr) continue;
+        }
         if (out_lo != nullptr) {   // TF32 split for the all-TMA proj GEMM
           float4 hi = make_float4(trunc_tf32(v.x), trunc_tf32(v.y), trunc_tf32(v.z), trunc_tf32(v.w));
           st4(out_lo + off + d, make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w));
@@ -518,8 +530,13 @@ int set_trace(long long* p) { return cudaMemcpyToSymbol(g_attn_trace, &p, sizeof
 extern "C" int cvar_debug_set_attn_trace(long long* dev_buf) { return tcattn::set_trace(dev_buf); }
 
 extern "C" int cvar_attn_kvcache(const float* q, const float* k_hi, const float* k_lo, const float* vt_hi,
-                                 const float* vt_lo, float* out, float* out_lo, int R, int H, int l, int L, int T_max,
-                                 float scale, int engine, void* stream) {
+                                 const float* vt_lo, float* out, float* out_lo, void* out16_hi, void* out16_lo, int R,
+                                 int H, int l, int L, int T_max, float scale, int engine, void* stream) {
+  CVAR_REQUIRE(out != nullptr || out16_hi != nullptr, "cvar_attn_kvcache: no output");
+  CVAR_REQUIRE((out16_hi == nullptr) == (out16_lo == nullptr), "cvar_attn_kvcache: out16_hi/out16_lo must come together");
+  CVAR_REQUIRE(out != nullptr || out_lo == nullptr, "cvar_attn_kvcache: out_lo without out");
+  __half* o16h = reinterpret_cast<__half*>(out16_hi);
+  __half* o16l = reinterpret_cast<__half*>(out16_lo);
   CVAR_REQUIRE(R > 0 && H > 0 && l > 0 && L >= l && L <= T_max, "cvar_attn_kvcache: bad shape l=%d L=%d T=%d", l, L,
                T_max);
   CVAR_REQUIRE(R <= 65535 && H <= 65535, "cvar_attn_kvcache: grid too large");
@@ -538,7 +555,7 @@ extern "C" int cvar_attn_kvcache(const float* q, const float* k_hi, const float*
     CVAR_REQUIRE(e == cudaSuccess, "cvar_attn_kvcache: cannot raise shared memory: %s", cudaGetErrorString(e));
     dim3 grid(cdiv(l, tcattn::BQ), H, R);
     tcattn::attn_tc_kernel<<<grid, tcattn::kThreads, tcattn::kSmem, (cudaStream_t)stream>>>(mkh, mkl, mvh, mvl, q, out,
-                                                                                          out_lo, H, l, L, scale);
+                                                                                          out_lo, o16h, o16l, H, l, L, scale);
     CVAR_CHECK_LAUNCH("cvar_attn_kvcache[tc]");
     return 0;
   }
@@ -546,8 +563,8 @@ extern "C" int cvar_attn_kvcache(const float* q, const float* k_hi, const float*
                                        (int)sizeof(AttnSmem));
   CVAR_REQUIRE(e == cudaSuccess, "cvar_attn_kvcache: cannot raise shared memory: %s", cudaGetErrorString(e));
   dim3 grid(cdiv(l, BQ), H, R);
-  attn_kvcache_kernel<<<grid, 256, sizeof(AttnSmem), (cudaStream_t)stream>>>(q, k_hi, k_lo, vt_hi, vt_lo, out, out_lo, H,
-                                                                            l, L, T_max, scale);
+  attn_kvcache_kernel<<<grid, 256, sizeof(AttnSmem), (cudaStream_t)stream>>>(q, k_hi, k_lo, vt_hi, vt_lo, out, out_lo, o16h,
+                                                                            o16l, H, l, L, T_max, scale);
   CVAR_CHECK_LAUNCH("cvar_attn_kvcache");
   return 0;
 }

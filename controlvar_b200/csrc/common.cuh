@@ -1,6 +1,7 @@
 // Shared helpers for libcvar_sm100.so (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <math.h>
@@ -59,6 +60,28 @@ __device__ __forceinline__ float gelu_tanh_f(float x) {
   float inner = kBeta * (x + kKappa * x * x * x);
   // 0.5 * x * (1 + tanh(u)) == x * sigmoid(2u) == x / (1 + exp(-2u)): same function, no tanhf, no cancellation
   return x / (1.0f + expf(-2.0f * inner));
+}
+
+// FP16 pair of an fp32 value (operand format of the f16x3 tensor-core engine): x ~= h + l * 2^-11, both rounded to
+// nearest, so |x - (h + l/2048)| <= 2^-24 |x|.  The residual is scaled by 2^11 to stay in fp16's normal range.
+constexpr float kF16LoScale = 2048.0f;
+__device__ __forceinline__ void split_f16(float x, __half& h, __half& l) {
+  x = fminf(fmaxf(x, -65504.0f), 65504.0f);
+  h = __float2half_rn(x);
+  l = __float2half_rn((x - __half2float(h)) * kF16LoScale);
+}
+// four consecutive values -> 8-byte stores of the hi and lo halves
+__device__ __forceinline__ void st4_split_f16(__half* hi, __half* lo, const float* r) {
+  __half h[4], l[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) split_f16(r[j], h[j], l[j]);
+  uint2 ph, pl;
+  ph.x = (uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16);
+  ph.y = (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16);
+  pl.x = (uint32_t)__half_as_ushort(l[0]) | ((uint32_t)__half_as_ushort(l[1]) << 16);
+  pl.y = (uint32_t)__half_as_ushort(l[2]) | ((uint32_t)__half_as_ushort(l[3]) << 16);
+  *reinterpret_cast<uint2*>(hi) = ph;
+  *reinterpret_cast<uint2*>(lo) = pl;
 }
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }

@@ -14,6 +14,10 @@ int tc2_gemm_try(const cvar_gemm_args* a, cudaStream_t s);
 int tc2_qkv_try(const float* A_hi, const float* A_lo, const float* Wqkv_hi, const float* Wqkv_lo, const QkvEpilogue& ep,
                 int M, int C, cudaStream_t s);
 int tc_conv_try(const cvar_conv_args* a, cudaStream_t s);
+// FP16-pair operands (engine 4): 0 ok, < 0 error - never a fall-through
+int tc2_gemm_f16(const cvar_gemm_args* a, cudaStream_t s);
+int tc2_qkv_f16(const void* A_hi, const void* A_lo, const void* W_hi, const void* W_lo, const QkvEpilogue& ep, int M, int C,
+                cudaStream_t s);
 }  // namespace cvar
 
 extern "C" int cvar_gemm(const cvar_gemm_args* a, void* stream) {
@@ -31,7 +35,16 @@ extern "C" int cvar_gemm(const cvar_gemm_args* a, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   CVAR_REQUIRE(a->out_lo == nullptr || a->epilogue == CVAR_EPI_BIAS || a->epilogue == CVAR_EPI_BIAS_GELU,
                "cvar_gemm: out_lo only goes with the BIAS / BIAS_GELU epilogues");
-  if (g_gemm_engine == 3 && a->A_lo != nullptr) {
+  CVAR_REQUIRE((a->out16_hi == nullptr) == (a->out16_lo == nullptr), "cvar_gemm: out16_hi/out16_lo must come together");
+  CVAR_REQUIRE(a->out16_hi == nullptr || a->epilogue == CVAR_EPI_BIAS || a->epilogue == CVAR_EPI_BIAS_GELU,
+               "cvar_gemm: out16 only goes with the BIAS / BIAS_GELU epilogues");
+  CVAR_REQUIRE(a->out != nullptr || (a->out16_hi != nullptr && a->out_lo == nullptr), "cvar_gemm: no output");
+  if (a->A16_hi != nullptr) {
+    CVAR_REQUIRE(g_gemm_engine != 0, "cvar_gemm: FP16-pair operands need a tensor-core engine (engine is 0 = SIMT)");
+    return tc2_gemm_f16(a, s);
+  }
+  CVAR_REQUIRE(a->A != nullptr && a->W != nullptr, "cvar_gemm: null A / W");
+  if (g_gemm_engine >= 3 && a->A_lo != nullptr) {
     int took = tc2_gemm_try(a, s);
     if (took < 0) return took;
     if (took == 1) return 0;
@@ -89,8 +102,9 @@ __global__ void cos_attn_normalize_kernel(float* __restrict__ q, float* __restri
   }
 }
 
-extern "C" int cvar_qkv_project(const float* A, const float* A_lo, const float* Wqkv, const float* Wqkv_hi,
-                                const float* Wqkv_lo,
+extern "C" int cvar_qkv_project(const float* A, const float* A_lo, const void* A16_hi, const void* A16_lo,
+                                const float* Wqkv, const float* Wqkv_hi, const float* Wqkv_lo, const void* W16_hi,
+                                const void* W16_lo,
                                 const float* q_bias, const float* k_bias, const float* v_bias, float* q_out,
                                 float* k_hi, float* k_lo, float* vt_hi, float* vt_lo, int R, int l, int L_prev,
                                 int T_max, int H, int cos_attn, const float* scale_mul_H, void* stream) {
@@ -100,7 +114,14 @@ extern "C" int cvar_qkv_project(const float* A, const float* A_lo, const float* 
   const int C = H * 64, M = R * l;
   QkvEpilogue ep{q_bias, k_bias, v_bias, q_out, k_hi, k_lo, vt_hi, vt_lo, C, H, l, L_prev, T_max};
   int took = 0;
-  if (g_gemm_engine == 3 && A_lo != nullptr && Wqkv_hi != nullptr && Wqkv_lo != nullptr) {
+  if (A16_hi != nullptr) {
+    CVAR_REQUIRE(g_gemm_engine != 0, "cvar_qkv_project: FP16-pair operands need a tensor-core engine (engine is 0 = SIMT)");
+    CVAR_REQUIRE(C % 64 == 0, "cvar_qkv_project: C must be a multiple of 64");
+    int rc = tc2_qkv_f16(A16_hi, A16_lo, W16_hi, W16_lo, ep, M, C, s);
+    if (rc) return rc;
+    took = 1;
+  }
+  if (took == 0 && g_gemm_engine >= 3 && A_lo != nullptr && Wqkv_hi != nullptr && Wqkv_lo != nullptr) {
     took = tc2_qkv_try(A, A_lo, Wqkv_hi, Wqkv_lo, ep, M, C, s);
     if (took < 0) return took;
   }

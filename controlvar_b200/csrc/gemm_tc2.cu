@@ -1,4 +1,14 @@
-// 2-CTA (cta_group::2) tcgen05 GEMM for the dense transformer layers: out = epilogue(A[M,K] * W[N,K]^T), 3xTF32.
+// 2-CTA (cta_group::2) tcgen05 GEMM for the dense transformer layers: out = epilogue(A[M,K] * W[N,K]^T), three
+// error-compensated MMAs per product in one of two operand formats:
+//   TF32 pairs (F16 = false): x = hi + lo, fp32 storage, kind::tf32                       (engine 3)
+//   FP16 pairs (F16 = true) : x = h + l * 2^-11, h = half_rn(x), l = half_rn((x - h) * 2^11), kind::f16   (engine 4)
+//     - the residual is SCALED so that it stays in fp16's normal range; it accumulates in the 'lo' TMEM accumulator,
+//       which the epilogue folds in with one fma(lo, 2^-11, main).  Representation error 2^-24 |x| (round-to-nearest
+//       twice) against 2^-21 for the truncating TF32 split, at TWICE the tensor-core rate and half the operand bytes.
+//       Operands must be below 65504 in magnitude: LayerNorm-modulated rows, GELU outputs, attention outputs and
+//       weights are (cvar_split_f16 saturates anything else).
+// The shared-memory row is 128 bytes in both formats (32 floats or 64 halves), so tiles, swizzle and UMMA descriptors
+// are identical; only the instruction kind, the K extent of a block and the tensor-map element type differ.
 //
 // Why a second kernel: tools/trace_gemm.py showed the 1-CTA engine (gemm_tc.cu) is bound by the TMA round trip
 // (~2080 cycles for the 64 KB of weight tiles of a K-block) against 1460 cycles of MMA, with room for only TWO 96 KB
@@ -25,7 +35,7 @@ using namespace cvar::tc;
 
 constexpr int BM = 128;            // rows per CTA (256 per pair)
 constexpr int BN = 256;            // columns per pair; each CTA stages BN/2 weight rows
-constexpr int BK = 32;
+constexpr int BK = 32;            // K-block in 4-byte units: 32 floats or 64 halves = one 128-byte swizzled row
 constexpr int kEpiWarps = 8;
 constexpr int kTmaWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1;
 constexpr int kThreads = (kEpiWarps + 2) * 32;       // 320
@@ -64,12 +74,20 @@ __device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* map, uint64_t
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kPeerMask), "r"(c0), "r"(c1)
       : "memory");
 }
-__device__ __forceinline__ void umma_tf32_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-      : "memory");
+template <bool F16>
+__device__ __forceinline__ void umma_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  if (F16)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
 }
 // completion of all prior MMAs of the pair -> the same-offset barrier in BOTH CTAs
 __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
@@ -94,13 +112,17 @@ __device__ __forceinline__ void tile_coords(int tile, int m_tiles, int n_tiles, 
   mt = first_m + (in_g - nt * gm);
 }
 
-template <class EP>
+template <class EP, bool F16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 tc_gemm2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
                 const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo, EP ep,
                 long long M, int N, int K, int m_tiles, int n_tiles) {
   using G = Geo<BK>;
-  constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+  // instruction descriptor: D fp32; A/B format 2 = TF32 (kind::tf32) or 0 = FP16 (kind::f16); N, M of the pair tile
+  constexpr uint32_t kFmt = F16 ? 0u : 2u;
+  constexpr uint32_t kIdesc = (1u << 4) | (kFmt << 7) | (kFmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+  constexpr int kBKe = F16 ? 2 * BK : BK;            // K elements per block
+  constexpr float kLoScale = F16 ? (1.0f / 2048.0f) : 1.0f;
   constexpr int kAccStride = 256;                    // main [0,256), lo [256,512)
 
   extern __shared__ unsigned char smem_raw[];
@@ -120,7 +142,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constan
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();           // 0 = leader
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
-  const int nkb = K / BK;
+  const int nkb = K / kBKe;
   const int total_tiles = m_tiles * n_tiles;         // m_tiles counts 256-row pair tiles
 
   if (warp == kTmaWarp && lane == 0) {
@@ -159,8 +181,8 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constan
 #pragma unroll
         for (int q = 0; q < kEpiCols / 4; ++q)
           *reinterpret_cast<float4*>(stage + lane * kStagePitch + q * 4) =
-              make_float4(v[4 * q] + w[4 * q], v[4 * q + 1] + w[4 * q + 1], v[4 * q + 2] + w[4 * q + 2],
-                          v[4 * q + 3] + w[4 * q + 3]);
+              make_float4(fmaf(w[4 * q], kLoScale, v[4 * q]), fmaf(w[4 * q + 1], kLoScale, v[4 * q + 1]),
+                          fmaf(w[4 * q + 2], kLoScale, v[4 * q + 2]), fmaf(w[4 * q + 3], kLoScale, v[4 * q + 3]));
         __syncwarp();
         const int n = nt * BN + c + (lane & 3) * 4;
         const int nvalid = min(4, N - n);
@@ -196,10 +218,10 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constan
           const uint32_t ph = (it / kStages) & 1;
           mbar_wait(&empty[s], ph ^ 1);
           if (rank == 0) mbar_arrive_expect_tx(&full[s], 2u * (uint32_t)kStageBytes);   // bytes of BOTH CTAs
-          tma_load_2d_2sm(&mapAhi, &full[s], a_hi(s), kb * BK, arow);
-          tma_load_2d_2sm(&mapAlo, &full[s], a_lo(s), kb * BK, arow);
-          tma_load_2d_2sm(&mapBhi, &full[s], b_hi(s), kb * BK, brow);
-          tma_load_2d_2sm(&mapBlo, &full[s], b_lo(s), kb * BK, brow);
+          tma_load_2d_2sm(&mapAhi, &full[s], a_hi(s), kb * kBKe, arow);
+          tma_load_2d_2sm(&mapAlo, &full[s], a_lo(s), kb * kBKe, arow);
+          tma_load_2d_2sm(&mapBhi, &full[s], b_hi(s), kb * kBKe, brow);
+          tma_load_2d_2sm(&mapBlo, &full[s], b_lo(s), kb * kBKe, brow);
         }
       }
     }
@@ -219,11 +241,11 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constan
           const uint64_t dah = G::desc(smem_u32(a_hi(s))), dal = G::desc(smem_u32(a_lo(s)));
           const uint64_t dbh = G::desc(smem_u32(b_hi(s))), dbl = G::desc(smem_u32(b_lo(s)));
 #pragma unroll
-          for (int k = 0; k < BK / 8; ++k) {
+          for (int k = 0; k < BK / 8; ++k) {        // one MMA consumes 32 bytes of K: 8 TF32 or 16 FP16 elements
             const uint64_t adv = (uint64_t)(k * 2);
-            umma_tf32_2sm(dl, dal + adv, dbh + adv, kIdesc, (kb | k) != 0);
-            umma_tf32_2sm(dl, dah + adv, dbl + adv, kIdesc, 1u);
-            umma_tf32_2sm(d, dah + adv, dbh + adv, kIdesc, (kb | k) != 0);
+            umma_2sm<F16>(dl, dal + adv, dbh + adv, kIdesc, (kb | k) != 0);
+            umma_2sm<F16>(dl, dah + adv, dbl + adv, kIdesc, 1u);
+            umma_2sm<F16>(d, dah + adv, dbh + adv, kIdesc, (kb | k) != 0);
           }
           umma_commit_2sm(&empty[s]);
         }
@@ -253,18 +275,19 @@ static EncodeTiledFn get_encode() {
   });
   return fn;
 }
-// row-major [rows, K] fp32 matrix -> (BK x 128-row) box, 128-byte swizzle, out-of-range rows zero-filled
-static int make_map(CUtensorMap* map, const float* base, long long rows, int K, long long ld) {
+// row-major [rows, K] fp32 (or fp16) matrix -> (128 bytes x 128 rows) box, 128-byte swizzle, out-of-range rows zero-filled
+static int make_map(CUtensorMap* map, const void* base, long long rows, int K, long long ld, bool f16) {
   EncodeTiledFn enc = get_encode();
   if (!enc) {
     set_error("tc_gemm2: cuTensorMapEncodeTiled is not available from the driver");
     return -3;
   }
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-  cuuint32_t box[2] = {(cuuint32_t)BK, 128};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * (f16 ? 2 : 4)};
+  cuuint32_t box[2] = {(cuuint32_t)(f16 ? 2 * BK : BK), 128};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+  CUresult r = enc(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                   const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -284,16 +307,16 @@ static int num_sms() {
   return n;
 }
 
-template <class EP>
-int launch(const EP& ep, const float* A_hi, const float* A_lo, long long lda, const float* W_hi, const float* W_lo,
+template <class EP, bool F16>
+int launch(const EP& ep, const void* A_hi, const void* A_lo, long long lda, const void* W_hi, const void* W_lo,
            long long ldw, long long M, int N, int K, cudaStream_t s, const char* name) {
   CUtensorMap mah, mal, mbh, mbl;
-  int rc = make_map(&mah, A_hi, M, K, lda);
-  if (!rc) rc = make_map(&mal, A_lo, M, K, lda);
-  if (!rc) rc = make_map(&mbh, W_hi, N, K, ldw);
-  if (!rc) rc = make_map(&mbl, W_lo, N, K, ldw);
+  int rc = make_map(&mah, A_hi, M, K, lda, F16);
+  if (!rc) rc = make_map(&mal, A_lo, M, K, lda, F16);
+  if (!rc) rc = make_map(&mbh, W_hi, N, K, ldw, F16);
+  if (!rc) rc = make_map(&mbl, W_lo, N, K, ldw, F16);
   if (rc) return rc;
-  auto kern = tc_gemm2_kernel<EP>;
+  auto kern = tc_gemm2_kernel<EP, F16>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
   if (e != cudaSuccess) {
     set_error("%s: cannot raise shared memory to %d: %s", name, kSmem, cudaGetErrorString(e));
@@ -310,16 +333,44 @@ static bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
 }  // namespace tc2
 
 // returns 1 when taken, 0 when the shape / operands do not qualify, < 0 on error
+static DenseEpilogue dense_epilogue(const cvar_gemm_args* a) {
+  DenseEpilogue ep{a->out, a->ldo, a->strideO, a->bias, a->epilogue, a->alpha, a->gamma, a->gamma_row_stride,
+                   a->rows_per_sample, a->resid, a->ldr, a->strideR, a->out_lo};
+  ep.out16_hi = reinterpret_cast<__half*>(a->out16_hi), ep.out16_lo = reinterpret_cast<__half*>(a->out16_lo);
+  return ep;
+}
+
+// FP16-pair operands (engine 4): the caller chose the format, so a shape this kernel cannot run is an error, not a
+// fall-through.  Small M / N are fine (TMA zero-fills the rows beyond the matrix).
+int tc2_gemm_f16(const cvar_gemm_args* a, cudaStream_t s) {
+  CVAR_REQUIRE(a->A16_hi && a->A16_lo && a->W16_hi && a->W16_lo, "cvar_gemm[f16x3]: A16_hi/A16_lo/W16_hi/W16_lo must all be set");
+  CVAR_REQUIRE(a->batch == 1 && !a->w_is_kn, "cvar_gemm[f16x3]: batched / K-by-N weights are not supported");
+  CVAR_REQUIRE(a->K % 64 == 0 && a->N % 4 == 0 && a->lda % 8 == 0 && a->ldw % 8 == 0,
+               "cvar_gemm[f16x3]: need K %% 64 == 0, N %% 4 == 0, lda/ldw %% 8 == 0 (K=%d N=%d lda=%lld ldw=%lld)", a->K, a->N,
+               a->lda, a->ldw);
+  CVAR_REQUIRE(tc2::aligned16(a->A16_hi) && tc2::aligned16(a->A16_lo) && tc2::aligned16(a->W16_hi) && tc2::aligned16(a->W16_lo),
+               "cvar_gemm[f16x3]: operands must be 16-byte aligned");
+  return tc2::launch<DenseEpilogue, true>(dense_epilogue(a), a->A16_hi, a->A16_lo, a->lda, a->W16_hi, a->W16_lo, a->ldw,
+                                          (long long)a->M, a->N, a->K, s, "cvar_gemm[tc2/f16x3]");
+}
+
+int tc2_qkv_f16(const void* A_hi, const void* A_lo, const void* W_hi, const void* W_lo, const QkvEpilogue& ep, int M, int C,
+                cudaStream_t s) {
+  CVAR_REQUIRE(A_hi && A_lo && W_hi && W_lo, "cvar_qkv_project[f16x3]: A16_hi/A16_lo/W16_hi/W16_lo must all be set");
+  CVAR_REQUIRE(tc2::aligned16(A_hi) && tc2::aligned16(A_lo) && tc2::aligned16(W_hi) && tc2::aligned16(W_lo),
+               "cvar_qkv_project[f16x3]: operands must be 16-byte aligned");
+  return tc2::launch<QkvEpilogue, true>(ep, A_hi, A_lo, C, W_hi, W_lo, C, (long long)M, 3 * C, C, s,
+                                        "cvar_qkv_project[tc2/f16x3]");
+}
+
 int tc2_gemm_try(const cvar_gemm_args* a, cudaStream_t s) {
   if (a->A_lo == nullptr || a->W_hi == nullptr || a->W_lo == nullptr) return 0;
   if (a->batch != 1 || a->w_is_kn || a->M < 256 || a->N < 256 || a->K % 32 != 0 || a->N % 4 != 0) return 0;
   if (a->lda % 4 != 0 || a->ldw % 4 != 0 || !tc2::aligned16(a->A) || !tc2::aligned16(a->A_lo) ||
       !tc2::aligned16(a->W_hi) || !tc2::aligned16(a->W_lo))
     return 0;
-  DenseEpilogue ep{a->out, a->ldo, a->strideO, a->bias, a->epilogue, a->alpha, a->gamma, a->gamma_row_stride,
-                   a->rows_per_sample, a->resid, a->ldr, a->strideR, a->out_lo};
-  int rc = tc2::launch(ep, a->A, a->A_lo, a->lda, a->W_hi, a->W_lo, a->ldw, (long long)a->M, a->N, a->K, s,
-                       "cvar_gemm[tc2]");
+  int rc = tc2::launch<DenseEpilogue, false>(dense_epilogue(a), a->A, a->A_lo, a->lda, a->W_hi, a->W_lo, a->ldw,
+                                             (long long)a->M, a->N, a->K, s, "cvar_gemm[tc2]");
   return rc ? rc : 1;
 }
 
@@ -327,7 +378,8 @@ int tc2_qkv_try(const float* A_hi, const float* A_lo, const float* Wqkv_hi, cons
                 int M, int C, cudaStream_t s) {
   if (A_lo == nullptr || M < 256 || C % 32 != 0) return 0;
   if (!tc2::aligned16(A_hi) || !tc2::aligned16(A_lo) || !tc2::aligned16(Wqkv_hi) || !tc2::aligned16(Wqkv_lo)) return 0;
-  int rc = tc2::launch(ep, A_hi, A_lo, C, Wqkv_hi, Wqkv_lo, C, (long long)M, 3 * C, C, s, "cvar_qkv_project[tc2]");
+  int rc = tc2::launch<QkvEpilogue, false>(ep, A_hi, A_lo, C, Wqkv_hi, Wqkv_lo, C, (long long)M, 3 * C, C, s,
+                                           "cvar_qkv_project[tc2]");
   return rc ? rc : 1;
 }
 }  // namespace cvar

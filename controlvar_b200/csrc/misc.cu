@@ -10,7 +10,7 @@ static std::atomic<long long> g_launches{0};
 // default: the fastest engine that has passed the whole parity suite (tests/test_gpu_*.py); CVAR_GEMM_ENGINE overrides
 static int initial_engine() {
   const char* e = getenv("CVAR_GEMM_ENGINE");
-  if (e != nullptr && (e[0] == '0' || e[0] == '1' || e[0] == '3') && e[1] == '\0') return e[0] - '0';
+  if (e != nullptr && (e[0] == '0' || e[0] == '1' || e[0] == '3' || e[0] == '4') && e[1] == '\0') return e[0] - '0';
   return 3;
 }
 int g_gemm_engine = initial_engine();
@@ -31,7 +31,7 @@ extern "C" const char* cvar_last_error(void) { return cvar::g_err; }
 extern "C" long long cvar_launch_count(void) { return cvar::g_launches.load(); }
 extern "C" int cvar_set_gemm_engine(int e) {
   int old = cvar::g_gemm_engine;
-  if (e == 0 || e == 1 || e == 3) cvar::g_gemm_engine = e;
+  if (e == 0 || e == 1 || e == 3 || e == 4) cvar::g_gemm_engine = e;
   return old;
 }
 extern "C" int cvar_get_gemm_engine(void) { return cvar::g_gemm_engine; }
@@ -100,7 +100,8 @@ extern "C" int cvar_prologue(const float* class_emb, const float* cond_embed, co
 template <int MAXV>   // float4 per lane
 __global__ void __launch_bounds__(256) ln_modulate_kernel(const float* __restrict__ x, const float* __restrict__ scale,
                                                           const float* __restrict__ shift, long long mod_stride,
-                                                          float* __restrict__ y, float* __restrict__ y_lo, int M, int C,
+                                                          float* __restrict__ y, float* __restrict__ y_lo,
+                                                          __half* __restrict__ y16_hi, __half* __restrict__ y16_lo, int M, int C,
                                                           int rows_per_sample, float eps) {
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   long long m = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
@@ -143,6 +144,11 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const float* __restric
       o.y = __fadd_rn(__fmul_rn(__fmul_rn(v[i].y - mean, rstd), __fadd_rn(a.y, 1.f)), b.y);
       o.z = __fadd_rn(__fmul_rn(__fmul_rn(v[i].z - mean, rstd), __fadd_rn(a.z, 1.f)), b.z);
       o.w = __fadd_rn(__fmul_rn(__fmul_rn(v[i].w - mean, rstd), __fadd_rn(a.w, 1.f)), b.w);
+      if (y16_hi != nullptr) {     // FP16 pair for the f16x3 GEMM
+        const float ov[4] = {o.x, o.y, o.z, o.w};
+        st4_split_f16(y16_hi + m * C + idx * 4, y16_lo + m * C + idx * 4, ov);
+        if (y == nullptr) continue;
+      }
       if (y_lo != nullptr) {       // TF32 split for the all-TMA GEMM: hi keeps the top 19 bits, lo is the exact remainder
         float4 hi = make_float4(__uint_as_float(__float_as_uint(o.x) & 0xFFFFE000u), __uint_as_float(__float_as_uint(o.y) & 0xFFFFE000u),
                                 __uint_as_float(__float_as_uint(o.z) & 0xFFFFE000u), __uint_as_float(__float_as_uint(o.w) & 0xFFFFE000u));
@@ -155,18 +161,27 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const float* __restric
 }
 
 extern "C" int cvar_ln_modulate(const float* x, const float* scale, const float* shift, long long mod_row_stride,
-                                float* y, float* y_lo, int M, int C, int rows_per_sample, float eps, void* stream) {
+                                float* y, float* y_lo, void* y16_hi_, void* y16_lo_, int M, int C, int rows_per_sample,
+                                float eps, void* stream) {
+  CVAR_REQUIRE(y != nullptr || y16_hi_ != nullptr, "cvar_ln_modulate: no output");
+  CVAR_REQUIRE((y16_hi_ == nullptr) == (y16_lo_ == nullptr), "cvar_ln_modulate: y16_hi/y16_lo must come together");
+  CVAR_REQUIRE(y != nullptr || y_lo == nullptr, "cvar_ln_modulate: y_lo without y");
+  __half* y16_hi = reinterpret_cast<__half*>(y16_hi_);
+  __half* y16_lo = reinterpret_cast<__half*>(y16_lo_);
   CVAR_REQUIRE(C % 4 == 0 && C <= 2048 && M > 0 && rows_per_sample > 0, "cvar_ln_modulate: bad shape M=%d C=%d", M, C);
   CVAR_REQUIRE(mod_row_stride % 4 == 0, "cvar_ln_modulate: modulation stride must be a multiple of 4 floats");
   dim3 grid(cdiv(M, 8));
   cudaStream_t s = (cudaStream_t)stream;
   int nv = C / 4;
   if (nv <= 32 * 4)
-    ln_modulate_kernel<4><<<grid, 256, 0, s>>>(x, scale, shift, mod_row_stride, y, y_lo, M, C, rows_per_sample, eps);
+    ln_modulate_kernel<4><<<grid, 256, 0, s>>>(x, scale, shift, mod_row_stride, y, y_lo, y16_hi, y16_lo, M, C,
+                                               rows_per_sample, eps);
   else if (nv <= 32 * 8)
-    ln_modulate_kernel<8><<<grid, 256, 0, s>>>(x, scale, shift, mod_row_stride, y, y_lo, M, C, rows_per_sample, eps);
+    ln_modulate_kernel<8><<<grid, 256, 0, s>>>(x, scale, shift, mod_row_stride, y, y_lo, y16_hi, y16_lo, M, C,
+                                               rows_per_sample, eps);
   else
-    ln_modulate_kernel<16><<<grid, 256, 0, s>>>(x, scale, shift, mod_row_stride, y, y_lo, M, C, rows_per_sample, eps);
+    ln_modulate_kernel<16><<<grid, 256, 0, s>>>(x, scale, shift, mod_row_stride, y, y_lo, y16_hi, y16_lo, M, C,
+                                               rows_per_sample, eps);
   CVAR_CHECK_LAUNCH("cvar_ln_modulate");
   return 0;
 }
@@ -344,5 +359,26 @@ extern "C" int cvar_repack_conv_weight(const float* w_oihw, float* w_out, int Co
   long long total = (long long)Cout * Cin * ks * ks;
   repack_conv_weight_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(w_oihw, w_out, Cout, Cin, ks);
   CVAR_CHECK_LAUNCH("cvar_repack_conv_weight");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------- FP16-pair split
+__global__ void split_f16_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo, long long n4) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n4; i += stride) {
+    const float4 v = cvar::ld4(x + i * 4);
+    const float vv[4] = {v.x, v.y, v.z, v.w};
+    cvar::st4_split_f16(hi + i * 4, lo + i * 4, vv);
+  }
+}
+
+extern "C" int cvar_split_f16(const float* x, void* hi, void* lo, long long n, void* stream) {
+  CVAR_REQUIRE(n > 0 && n % 4 == 0, "cvar_split_f16: n must be a positive multiple of 4");
+  CVAR_REQUIRE(x && hi && lo, "cvar_split_f16: null pointer");
+  const long long n4 = n / 4;
+  const int blocks = (int)std::min<long long>((n4 + 255) / 256, 148LL * 16);
+  split_f16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, reinterpret_cast<__half*>(hi), reinterpret_cast<__half*>(lo), n4);
+  CVAR_CHECK_LAUNCH("cvar_split_f16");
   return 0;
 }

@@ -145,6 +145,8 @@ struct DenseEpilogue {
   const float* resid;
   long long ldr, strideR;
   float* out_lo = nullptr;       // optional (BIAS / BIAS_GELU): write the result split, out = hi, out_lo = lo
+  __half* out16_hi = nullptr;    // optional (BIAS / BIAS_GELU): write the result as an FP16 pair; `out` may then be null
+  __half* out16_lo = nullptr;
   __device__ __forceinline__ void store(long long m, int n, const float* v, int nvalid, int batch) const {
     float* o = out + (long long)batch * strideO + m * ldo + n;
     float r[4];
@@ -165,6 +167,13 @@ struct DenseEpilogue {
 #pragma unroll
       for (int j = 0; j < 4; ++j)
         if (j < nvalid) r[j] = __fadd_rn(rs[j], r[j]);                      // shortcut + h
+    }
+    if (out16_hi != nullptr) {
+      const long long off = (long long)batch * strideO + m * ldo + n;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (j < nvalid) split_f16(r[j], out16_hi[off + j], out16_lo[off + j]);
+      if (out == nullptr) return;
     }
     if (out_lo != nullptr) {
       float* ol = out_lo + (long long)batch * strideO + m * ldo + n;
@@ -212,8 +221,9 @@ __device__ __forceinline__ float gelu_tanh_fast(float x) {
 }
 __device__ __forceinline__ void dense_store_aux(const DenseEpilogue& e, long long m, int n, const float* v, int nvalid,
                                                 int batch, const EpiAux& x) {
-  float* o = e.out + (long long)batch * e.strideO + m * e.ldo + n;
-  if (nvalid != 4 || ((((uintptr_t)o) & 15) != 0)) {
+  const long long ooff = (long long)batch * e.strideO + m * e.ldo + n;
+  float* o = e.out + ooff;
+  if (nvalid != 4 || ((((uintptr_t)o) & 15) != 0) || (ooff & 3) != 0) {
     e.store(m, n, v, nvalid, batch);
     return;
   }
@@ -231,6 +241,10 @@ __device__ __forceinline__ void dense_store_aux(const DenseEpilogue& e, long lon
     r[2] = __fadd_rn(x.a.z, __fmul_rn(r[2], x.b.z)), r[3] = __fadd_rn(x.a.w, __fmul_rn(r[3], x.b.w));
   } else if (e.mode == CVAR_EPI_BIAS_RESID) {
     r[0] = __fadd_rn(x.a.x, r[0]), r[1] = __fadd_rn(x.a.y, r[1]), r[2] = __fadd_rn(x.a.z, r[2]), r[3] = __fadd_rn(x.a.w, r[3]);
+  }
+  if (e.out16_hi != nullptr) {
+    st4_split_f16(e.out16_hi + ooff, e.out16_lo + ooff, r);
+    if (e.out == nullptr) return;
   }
   if (e.out_lo != nullptr) {
     float l4[4];

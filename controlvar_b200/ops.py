@@ -11,7 +11,8 @@ from . import _lib
 from ._lib import ConvArgs, GemmArgs, check
 
 EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_GAMMA_RESID, EPI_BIAS_RESID = 0, 1, 2, 3
-ENGINE_SIMT, ENGINE_TC_3XTF32, ENGINE_TC_2CTA = 0, 1, 3
+ENGINE_SIMT, ENGINE_TC_3XTF32, ENGINE_TC_2CTA, ENGINE_TC_F16X3 = 0, 1, 3, 4
+F16_LO_SCALE = 2048.0      # an FP16 pair represents hi + lo / 2048 (include/cvar.h: cvar_split_f16)
 
 
 def _p(t: Optional[torch.Tensor]):
@@ -30,6 +31,41 @@ def _chk(*ts):
             raise _lib.CvarError("controlvar_b200 ops need CUDA tensors (there is no CPU fallback)")
         if t.dtype not in (torch.float32, torch.int64, torch.float64):
             raise _lib.CvarError(f"unsupported dtype {t.dtype}")
+
+
+class F16Pair:
+    """An fp32 array held as two IEEE-half arrays, value = hi + lo / 2048: the operand format of the f16x3 engine."""
+    __slots__ = ("hi", "lo")
+
+    def __init__(self, hi: torch.Tensor, lo: torch.Tensor):
+        for t in (hi, lo):
+            if not t.is_cuda or t.dtype != torch.float16 or not t.is_contiguous():
+                raise _lib.CvarError("F16Pair needs contiguous CUDA float16 tensors")
+        if hi.shape != lo.shape:
+            raise _lib.CvarError("F16Pair: hi / lo shapes differ")
+        self.hi, self.lo = hi, lo
+
+    @staticmethod
+    def empty(shape, device) -> "F16Pair":
+        return F16Pair(torch.empty(shape, dtype=torch.float16, device=device),
+                       torch.empty(shape, dtype=torch.float16, device=device))
+
+    @staticmethod
+    def from_tensor(x: torch.Tensor, out: Optional["F16Pair"] = None) -> "F16Pair":
+        _chk(x)
+        x = x.contiguous()
+        if x.numel() % 4 != 0:
+            raise _lib.CvarError("F16Pair: number of elements must be a multiple of 4")
+        p = out if out is not None else F16Pair.empty(x.shape, x.device)
+        check(_lib.load().cvar_split_f16(_p(x), _p(p.hi), _p(p.lo), x.numel(), _stream()), "cvar_split_f16")
+        return p
+
+    def float(self) -> torch.Tensor:
+        return self.hi.float() + self.lo.float() / F16_LO_SCALE
+
+
+def _p16(p: Optional[F16Pair]):
+    return (None, None) if p is None else (p.hi.data_ptr(), p.lo.data_ptr())
 
 
 # ---- optional per-kernel-class timing with CUDA events on the launching stream (bench.py's roofline object) -------
@@ -105,41 +141,56 @@ def prologue(class_emb, cond_embed, pos_start, lvl_pos_t, label_B, cond_type_B, 
                                     _stream()), "cvar_prologue")
 
 
-def ln_modulate(x, scale, shift, mod_row_stride, out, M, Cdim, rows_per_sample, eps, out_lo=None):
+def ln_modulate(x, scale, shift, mod_row_stride, out, M, Cdim, rows_per_sample, eps, out_lo=None,
+                out16: Optional[F16Pair] = None):
     """scale/shift: views into an ada_lin output; only their data pointers and the common row stride are used.
-    out_lo: write the result as a TF32 hi/lo split (out = hi) - the operand format of the 2-CTA GEMM."""
+    out_lo: write the result as a TF32 hi/lo split (out = hi) - the operand format of the 2-CTA GEMM.
+    out16: write the result as an FP16 pair (f16x3 engine); ``out`` may then be None."""
     _chk(x, scale, shift, out, out_lo)
-    check(_lib.load().cvar_ln_modulate(_p(x), _p(scale), _p(shift), mod_row_stride, _p(out), _p(out_lo), M, Cdim,
-                                       rows_per_sample, float(eps), _stream()), "cvar_ln_modulate")
-    return out
+    h16, l16 = _p16(out16)
+    check(_lib.load().cvar_ln_modulate(_p(x), _p(scale), _p(shift), mod_row_stride, _p(out), _p(out_lo), h16, l16, M,
+                                       Cdim, rows_per_sample, float(eps), _stream()), "cvar_ln_modulate")
+    return out if out is not None else out16
 
 
 class SplitWeight:
-    """A weight matrix with its TF32 hi/lo split (made once): what the tcgen05 engine consumes by TMA."""
-    __slots__ = ("w", "hi", "lo")
+    """A weight matrix with its tensor-core operand form (made once, consumed by TMA): the TF32 hi/lo split, or with
+    ``f16=True`` the FP16 pair of the f16x3 engine (``.h16``; no TF32 copy is kept then)."""
+    __slots__ = ("w", "hi", "lo", "h16")
 
-    def __init__(self, w: torch.Tensor):
+    def __init__(self, w: torch.Tensor, f16: bool = False):
         self.w = w.contiguous()
-        self.hi = torch.empty_like(self.w)
-        self.lo = torch.empty_like(self.w)
+        self.hi = self.lo = self.h16 = None
         if self.w.numel() % 4 != 0:
             raise _lib.CvarError("SplitWeight: number of elements must be a multiple of 4")
+        if f16:
+            self.h16 = F16Pair.from_tensor(self.w)
+            return
+        self.hi = torch.empty_like(self.w)
+        self.lo = torch.empty_like(self.w)
         check(_lib.load().cvar_split_tf32(_p(self.w), _p(self.hi), _p(self.lo), self.w.numel(), _stream()),
               "cvar_split_tf32")
 
 
 def _wparts(W):
     if isinstance(W, SplitWeight):
-        return W.w, W.hi, W.lo
-    return W, None, None
+        return W.w, W.hi, W.lo, W.h16
+    return W, None, None, None
 
 
 def gemm(A, W, bias, out, M, N, K, *, lda=None, ldw=None, ldo=None, epilogue=EPI_BIAS, alpha=1.0, w_is_kn=False,
          batch=1, strideA=0, strideW=0, strideO=0, gamma=None, gamma_row_stride=0, rows_per_sample=1,
-         resid=None, ldr=None, strideR=0, A_lo=None, out_lo=None):
-    W, W_hi, W_lo = _wparts(W)
+         resid=None, ldr=None, strideR=0, A_lo=None, out_lo=None, A16: Optional[F16Pair] = None,
+         out16: Optional[F16Pair] = None):
+    """A16 (with W a SplitWeight(f16=True)): FP16-pair operands, A may be None; out16: FP16-pair result, out may be None."""
+    W, W_hi, W_lo, W16 = _wparts(W)
     _chk(A, W, bias, out, gamma, resid, A_lo, out_lo)
+    if A16 is not None and W16 is None:
+        raise _lib.CvarError("gemm: an FP16-pair activation needs a SplitWeight(f16=True) weight")
     a = GemmArgs()
+    a.A16_hi, a.A16_lo = _p16(A16)
+    a.W16_hi, a.W16_lo = _p16(W16 if A16 is not None else None)
+    a.out16_hi, a.out16_lo = _p16(out16)
     a.W_hi, a.W_lo = _p(W_hi), _p(W_lo)
     a.A_lo, a.out_lo = _p(A_lo), _p(out_lo)
     a.A, a.lda, a.strideA = _p(A), (K if lda is None else lda), strideA
@@ -152,7 +203,7 @@ def gemm(A, W, bias, out, M, N, K, *, lda=None, ldw=None, ldo=None, epilogue=EPI
     a.resid, a.ldr, a.strideR = _p(resid), (N if ldr is None else ldr), strideR
     with _Timed("gemm", 2.0 * M * N * K * batch, 4.0 * batch * (M * K + N * K + M * N)):
         check(_lib.load().cvar_gemm(C.byref(a), _stream()), "cvar_gemm")
-    return out
+    return out if out is not None else out16
 
 
 class KVCache:
@@ -181,25 +232,33 @@ class KVCache:
 
 
 def qkv_project(A, Wqkv, q_bias, k_bias, v_bias, q_out, cache: KVCache, R, l, L_prev, H, cos_attn, scale_mul_H,
-                A_lo=None):
-    Wqkv, W_hi, W_lo = _wparts(Wqkv)
+                A_lo=None, A16: Optional[F16Pair] = None):
+    Wqkv, W_hi, W_lo, W16 = _wparts(Wqkv)
     _chk(A, Wqkv, q_bias, k_bias, v_bias, q_out, cache.k_hi, scale_mul_H, A_lo)
+    if A16 is not None and W16 is None:
+        raise _lib.CvarError("qkv_project: an FP16-pair activation needs a SplitWeight(f16=True) weight")
+    a16h, a16l = _p16(A16)
+    w16h, w16l = _p16(W16 if A16 is not None else None)
     Cd = H * 64
     with _Timed("gemm", 2.0 * R * l * 3 * Cd * Cd, 4.0 * (R * l * Cd + 3 * Cd * Cd + R * l * 3 * Cd)):
-        check(_lib.load().cvar_qkv_project(_p(A), _p(A_lo), _p(Wqkv), _p(W_hi), _p(W_lo), _p(q_bias), _p(k_bias), _p(v_bias),
+        check(_lib.load().cvar_qkv_project(_p(A), _p(A_lo), a16h, a16l, _p(Wqkv), _p(W_hi), _p(W_lo), w16h, w16l,
+                                           _p(q_bias), _p(k_bias), _p(v_bias),
                                            _p(q_out), _p(cache.k_hi), _p(cache.k_lo), _p(cache.vt_hi), _p(cache.vt_lo),
                                            R, l, L_prev, cache.T, H, int(cos_attn), _p(scale_mul_H), _stream()),
               "cvar_qkv_project")
 
 
-def attn_kvcache(q, cache: KVCache, out, R, H, l, L, scale, engine: int = -1, out_lo=None):
+def attn_kvcache(q, cache: KVCache, out, R, H, l, L, scale, engine: int = -1, out_lo=None,
+                 out16: Optional[F16Pair] = None):
     _chk(q, cache.k_hi, out, out_lo)
+    o16h, o16l = _p16(out16)
     # algorithmic work of SURVEY.md section 8d: 4*l*L*64 flop and (2l + 2L)*64*4 bytes per (row, head)
     with _Timed("attn", 4.0 * l * L * 64 * R * H, (2.0 * l + 2.0 * L) * 64 * 4 * R * H):
         check(_lib.load().cvar_attn_kvcache(_p(q), _p(cache.k_hi), _p(cache.k_lo), _p(cache.vt_hi), _p(cache.vt_lo),
-                                            _p(out), _p(out_lo), R, H, l, L, cache.T, float(scale), int(engine), _stream()),
+                                            _p(out), _p(out_lo), o16h, o16l, R, H, l, L, cache.T, float(scale),
+                                            int(engine), _stream()),
               "cvar_attn_kvcache")
-    return out
+    return out if out is not None else out16
 
 
 def cfg_sample(logits, q_noise, idx_out, B, l, V, t, top_k, top_p):
@@ -244,7 +303,7 @@ def gn_stats(x_nhwc, gamma, beta, a_out, b_out, scratch, B, HW, Cdim, groups=32,
 
 def conv2d(x, w_packed, bias, out, B, Hin, Win, Cin, Cout, ks, *, in_a=None, in_b=None, in_silu=False, resid=None,
            upsample2x=False, out_mode=0, out_rows_total=0, row_offset=0, engine=-1):
-    w_packed, w_hi, w_lo = _wparts(w_packed)
+    w_packed, w_hi, w_lo, _ = _wparts(w_packed)
     _chk(x, w_packed, bias, out, in_a, in_b, resid)
     a = ConvArgs()
     a.x, a.w, a.bias, a.out = _p(x), _p(w_packed), _p(bias), _p(out)

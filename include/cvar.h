@@ -38,7 +38,10 @@ CVAR_API long long cvar_launch_count(void);
  *   0 = SIMT fp32 FFMA;  1 = tcgen05 3xTF32, one CTA per tile (fp32-class);  2 = reserved (bf16, not implemented);
  *   3 = as 1, and dense layers whose activation operand is supplied pre-split (A_lo != NULL) run on the 2-CTA
  *       (cta_group::2) all-TMA kernel.  Anything an engine does not take falls through to the next lower one.
- * Default: 3 (environment variable CVAR_GEMM_ENGINE = 0 | 1 | 3 overrides it at load).  Returns the previous value. */
+ *   4 = as 3 for TF32 operands; tells the HOST to hand the dense layers FP16-pair operands (A16_* / W16_*, see
+ *       cvar_split_f16), which run on the same 2-CTA kernel with kind::f16 MMAs at twice the TF32 rate.  The library
+ *       itself picks the FP16 path whenever a call carries A16_hi, under any engine other than 0.
+ * Default: 3 (environment variable CVAR_GEMM_ENGINE = 0 | 1 | 3 | 4 overrides it at load).  Returns the previous value. */
 CVAR_API int cvar_set_gemm_engine(int engine);
 CVAR_API int cvar_get_gemm_engine(void);
 /* K-block of the tcgen05 engine: 32 (128-byte swizzle, default) or 16 (64-byte swizzle, deeper pipeline). Returns the
@@ -67,9 +70,11 @@ CVAR_API int cvar_prologue(const float* class_emb, const float* cond_embed, cons
  * y[m,:] = LayerNorm(x[m,:], eps, no affine) * (scale[r,:] + 1) + shift[r,:],  r = m / rows_per_sample.
  * scale/shift are slices of an ada_lin output, so they carry a row stride (6C or 2C floats). */
 CVAR_API int cvar_ln_modulate(const float* x, const float* scale, const float* shift, long long mod_row_stride,
-                     float* y, float* y_lo, int M, int C, int rows_per_sample, float eps, void* stream);
+                     float* y, float* y_lo, void* y16_hi, void* y16_lo, int M, int C, int rows_per_sample, float eps,
+                     void* stream);
 /* y_lo (optional): when not NULL the result is written as a TF32 split, y = hi, y_lo = lo (hi + lo == value exactly) -
- * the operand format the 2-CTA GEMM fetches by TMA. */
+ * the operand format the 2-CTA GEMM fetches by TMA.
+ * y16_hi / y16_lo (optional, IEEE half [M,C]): the result as an FP16 pair (see cvar_split_f16); y may then be NULL. */
 
 /* ---- dense layers: F.linear call sites of basic_var.py:51,92,119 and control_var.py:221 -----------------------
  * out = epilogue(A[M,K] @ W[N,K]^T + bias[N]).  A, W, out row-major with leading dimensions lda/ldw/ldo.
@@ -97,6 +102,13 @@ typedef struct {
   const float* gamma; long long gamma_row_stride; int rows_per_sample;   /* CVAR_EPI_BIAS_GAMMA_RESID */
   const float* resid; long long ldr; long long strideR;                  /* CVAR_EPI_BIAS_RESID */
   float* out_lo;   /* optional, CVAR_EPI_BIAS / CVAR_EPI_BIAS_GELU only: write the result split (out = hi, out_lo = lo) */
+  /* FP16-pair operands (engine 4, "f16x3"): when A16_hi is set the product runs as three kind::f16 tcgen05 MMAs on the
+   * pairs (A16_hi, A16_lo) [M, lda halves] and (W16_hi, W16_lo) [N, ldw halves] made by cvar_split_f16 or by a producer's
+   * *16 outputs; A / A_lo / W / W_hi / W_lo are ignored.  Needs K % 64 == 0, batch == 1, W as [N,K]; any M, N.
+   * out16_hi / out16_lo (optional, BIAS / BIAS_GELU): write the result as an FP16 pair [M, ldo halves]; out may be NULL. */
+  const void* A16_hi; const void* A16_lo;
+  const void* W16_hi; const void* W16_lo;
+  void* out16_hi; void* out16_lo;
 } cvar_gemm_args;
 CVAR_API int cvar_gemm(const cvar_gemm_args* args, void* stream);
 
@@ -109,8 +121,9 @@ CVAR_API int cvar_gemm(const cvar_gemm_args* args, void* stream);
  * operand format of the tensor-core attention kernel (K tiles and V^T tiles are fetched by TMA as they are).
  * T_max must be a multiple of 4.  The caller zero-initialises the cache once (stale tail keys are masked, but must be
  * finite).  cos_attn != 0 (depth 30, basic_var.py:99-104): q = normalize(q) * exp(min(scale_mul[h], ln 100)),
- * k = normalize(k). */
-CVAR_API int cvar_qkv_project(const float* A, const float* A_lo, const float* Wqkv, const float* Wqkv_hi, const float* Wqkv_lo,
+ * k = normalize(k).  A16_* / W16_* (optional): FP16-pair operands as in cvar_gemm_args; the cache format is unchanged. */
+CVAR_API int cvar_qkv_project(const float* A, const float* A_lo, const void* A16_hi, const void* A16_lo,
+                     const float* Wqkv, const float* Wqkv_hi, const float* Wqkv_lo, const void* W16_hi, const void* W16_lo,
                      const float* q_bias, const float* k_bias, const float* v_bias,
                      float* q_out, float* k_hi, float* k_lo, float* vt_hi, float* vt_lo,
                      int R, int l, int L_prev, int T_max, int H, int cos_attn, const float* scale_mul_H,
@@ -122,9 +135,10 @@ CVAR_API int cvar_qkv_project(const float* A, const float* A_lo, const float* Wq
  * cache holds exactly the keys of scales <= current, which is the block-causal pattern of control_var.py:168.
  * engine: -1 = library default (tensor cores when l >= 64), 0 = SIMT fp32, 1 = tcgen05 3xTF32. */
 CVAR_API int cvar_attn_kvcache(const float* q, const float* k_hi, const float* k_lo, const float* vt_hi, const float* vt_lo,
-                      float* out, float* out_lo, int R, int H, int l, int L, int T_max, float scale, int engine,
-                      void* stream);
-/* out_lo (optional): write the result as a TF32 split (out = hi, out_lo = lo) for the 2-CTA proj GEMM. */
+                      float* out, float* out_lo, void* out16_hi, void* out16_lo, int R, int H, int l, int L, int T_max,
+                      float scale, int engine, void* stream);
+/* out_lo (optional): write the result as a TF32 split (out = hi, out_lo = lo) for the 2-CTA proj GEMM.
+ * out16_hi / out16_lo (optional, IEEE half (R,l,H*64)): the result as an FP16 pair; out may then be NULL. */
 
 /* ---- CFG + top-k/top-p + multinomial(1): control_var.py:501-505, helpers.py:6-19 -----------------------------
  * logits (2B, l, V): rows [0,B) conditional, [B,2B) unconditional.  v = (1+t)*lc - t*lu; top-k keeps v >= k-th
@@ -179,6 +193,11 @@ CVAR_API int cvar_conv2d(const cvar_conv_args* args, void* stream);
 /* hi = w with the 13 low mantissa bits cleared (what a TF32 tensor-core operand keeps), lo = w - hi (exact): the
  * error-compensated 3xTF32 operands of the tcgen05 engine.  n must be a multiple of 4. */
 CVAR_API int cvar_split_tf32(const float* w, float* w_hi, float* w_lo, long long n, void* stream);
+/* FP16 pair of an fp32 array: hi = half_rn(x), lo = half_rn((x - hi) * 2^11), so x ~= hi + lo * 2^-11 with
+ * |error| <= 2^-24 |x| (the residual is scaled to stay in fp16's normal range; the engine folds 2^-11 back in its
+ * epilogue).  Three kind::f16 MMAs on such pairs (hi*hi, hi*lo, lo*hi) give fp32-class products at twice the TF32
+ * tensor-core rate.  |x| must be < 65504 (saturates otherwise).  n must be a multiple of 4. */
+CVAR_API int cvar_split_f16(const float* x, void* hi, void* lo, long long n, void* stream);
 /* (Cout,Cin,ks,ks) -> (Cout, ks*ks*Cin), k index = (ky*ks+kx)*Cin + ci */
 CVAR_API int cvar_repack_conv_weight(const float* w_oihw, float* w_out, int Cout, int Cin, int ks, void* stream);
 /* y = x*a[n,c] + b[n,c] (GroupNorm without activation, AttnBlock.norm) */

@@ -1,0 +1,189 @@
+"""GPU: the FP16-pair ("f16x3") operand format and engine 4.
+  x ~= hi + lo / 2048 with both halves rounded to nearest (include/cvar.h: cvar_split_f16); three kind::f16 tcgen05 MMAs
+  (hi*hi, hi*lo, lo*hi) on the 2-CTA kernel must be at least as accurate as the 3xTF32 engine on the same problem.
+Covered: the split itself (error bound, tiny / large / saturating values), every producer of pairs (cvar_ln_modulate,
+cvar_gemm out16, cvar_attn_kvcache out16), every consumer (cvar_gemm, cvar_qkv_project) incl. M / N tails smaller than a
+tile, a single K-block, all epilogues, determinism."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from controlvar_b200 import ops
+from controlvar_b200._lib import CvarError
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def g(t):
+    return t.to(DEV).contiguous()
+
+
+def err(a, ref):
+    return ((a.double() - ref).abs().max() / ref.abs().max()).item()
+
+
+@pytest.fixture
+def engine4():
+    old = ops.set_gemm_engine(ops.ENGINE_TC_F16X3)
+    yield
+    ops.set_gemm_engine(old)
+
+
+def test_split_f16_error_bound():
+    torch.manual_seed(0)
+    x = torch.cat([torch.randn(1 << 16), torch.randn(1 << 14) * 1e-3, torch.randn(1 << 14) * 300.0,
+                   torch.randn(1 << 12) * 1e-6, torch.tensor([0.0, -0.0, 1.0, -1.0, 65504.0, -65504.0, 6.1e-5, 5.9e-8])])
+    p = ops.F16Pair.from_tensor(g(x))
+    back = p.float().cpu().double()
+    # |x| >= 2^-12: the scaled residual is a normal fp16 number, so two roundings to nearest leave 2^-24 relative
+    # (+ 2^-24 for the fp32 rounding of the reconstruction in F16Pair.float())
+    big = x.abs() >= 2.0 ** -12
+    rel = ((back - x.double()).abs() / x.double().abs().clamp_min(1e-300))[big].max().item()
+    assert rel <= 2.0 ** -23, rel
+    # below that the scaled residual may be subnormal (spacing 2^-24): absolute error <= 2^-25 / 2048 (+ reconstruction)
+    assert (back - x.double()).abs()[~big].max().item() <= 2.0 ** -35
+    assert torch.isfinite(p.hi).all() and torch.isfinite(p.lo).all()
+    # saturation instead of inf
+    s = ops.F16Pair.from_tensor(g(torch.tensor([1e6, -1e6, 7e4, 0.0])))
+    assert torch.isfinite(s.hi).all() and s.hi[0].item() == 65504.0 and s.hi[1].item() == -65504.0
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 256, 64), (8, 256, 128), (100, 64, 192), (300, 1536, 1536), (1000, 768, 3072),
+                                   (512, 1920, 1920), (4096, 1536, 6144), (2304, 4096, 768), (37 * 256, 1536, 256),
+                                   (65536, 1536, 1536)])
+def test_f16x3_gemm_vs_fp64_and_3xtf32(engine4, M, N, K):
+    torch.manual_seed(M + N + K)
+    A, W, b = torch.randn(M, K), torch.randn(N, K) / math.sqrt(K), torch.randn(N)
+    ref = A.double() @ W.double().T + b.double()
+    Ag, bg = g(A), g(b)
+    W16 = ops.SplitWeight(g(W), f16=True)
+    A16 = ops.F16Pair.from_tensor(Ag)
+    n0 = ops.launch_count()
+    out = torch.full((M, N), float("nan"), device=DEV)
+    ops.gemm(None, W16, bg, out, M, N, K, A16=A16)
+    torch.cuda.synchronize()
+    assert ops.launch_count() - n0 == 1
+    assert not torch.isnan(out).any(), "some output elements were never written"
+    e4 = err(out.cpu(), ref)
+    out_b = torch.full((M, N), float("nan"), device=DEV)
+    ops.gemm(None, W16, bg, out_b, M, N, K, A16=A16)
+    assert torch.equal(out, out_b), "f16x3 GEMM is not deterministic run to run"
+    # the 3xTF32 engine and the SIMT engine on the same problem
+    Wt = ops.SplitWeight(g(W))
+    out3, out0 = torch.empty(M, N, device=DEV), torch.empty(M, N, device=DEV)
+    ops.set_gemm_engine(ops.ENGINE_TC_3XTF32)
+    ops.gemm(Ag, Wt, bg, out3, M, N, K)
+    ops.set_gemm_engine(ops.ENGINE_SIMT)
+    ops.gemm(Ag, Wt, bg, out0, M, N, K)
+    ops.set_gemm_engine(ops.ENGINE_TC_F16X3)
+    e3, e0 = err(out3.cpu(), ref), err(out0.cpu(), ref)
+    print(f"\n[f16x3-accuracy] M={M} N={N} K={K}: f16x3 err {e4:.3e}  3xTF32 err {e3:.3e}  SIMT err {e0:.3e}")
+    assert e4 < 2e-5
+    assert e4 <= 1.5 * e3 + 1e-7, "f16x3 should not be less accurate than 3xTF32"
+
+
+def test_f16x3_epilogues_and_pair_output(engine4):
+    torch.manual_seed(3)
+    R, l, C, K = 4, 128, 512, 1024
+    M = R * l
+    A, Wt, b = torch.randn(M, K), torch.randn(C, K) / math.sqrt(K), torch.randn(C)
+    x0, ada = torch.randn(M, C), torch.randn(R, 6 * C)
+    A16 = ops.F16Pair.from_tensor(g(A))
+    W16 = ops.SplitWeight(g(Wt), f16=True)
+    ref_lin = A.double() @ Wt.double().T + b.double()
+    x, ada_g = g(x0), g(ada)
+    ops.gemm(None, W16, g(b), x, M, C, K, A16=A16, epilogue=ops.EPI_BIAS_GAMMA_RESID, gamma=ada_g[:, C:2 * C],
+             gamma_row_stride=6 * C, rows_per_sample=l)
+    assert err(x.cpu(), x0.double() + ref_lin * ada[:, C:2 * C].double().repeat_interleave(l, 0)) < 1e-5
+    # GELU epilogue written ONLY as a pair (the fc1 -> fc2 hand-over), and as fp32 + pair
+    o16 = ops.F16Pair.empty((M, C), DEV)
+    ops.gemm(None, W16, g(b), None, M, C, K, A16=A16, epilogue=ops.EPI_BIAS_GELU, out16=o16)
+    ref_gelu = F.gelu(ref_lin, approximate="tanh")
+    assert err(o16.float().cpu(), ref_gelu) < 1e-5
+    o32, o16b = torch.empty(M, C, device=DEV), ops.F16Pair.empty((M, C), DEV)
+    ops.gemm(None, W16, g(b), o32, M, C, K, A16=A16, epilogue=ops.EPI_BIAS_GELU, out16=o16b)
+    assert torch.equal(o16b.hi, o16.hi) and torch.equal(o16b.lo, o16.lo)
+    chk = ops.F16Pair.from_tensor(o32)              # the pair written by the epilogue == the split of the fp32 result
+    assert torch.equal(chk.hi, o16.hi) and torch.equal(chk.lo, o16.lo)
+    # alpha (BIAS mode)
+    o = torch.empty(M, C, device=DEV)
+    ops.gemm(None, W16, g(b), o, M, C, K, A16=A16, alpha=0.25)
+    assert err(o.cpu(), (A.double() @ Wt.double().T) * 0.25 + b.double()) < 1e-5
+
+
+def test_f16x3_rejects_bad_use(engine4):
+    A16 = ops.F16Pair.from_tensor(torch.randn(64, 96, device=DEV))
+    W16 = ops.SplitWeight(torch.randn(64, 96, device=DEV), f16=True)
+    out = torch.empty(64, 64, device=DEV)
+    with pytest.raises(CvarError):
+        ops.gemm(None, W16, None, out, 64, 64, 96, A16=A16)             # K % 64 != 0: an error, not a fall-through
+    with pytest.raises(CvarError):
+        ops.gemm(None, ops.SplitWeight(torch.randn(64, 128, device=DEV)), None, out, 64, 64, 128,
+                 A16=ops.F16Pair.from_tensor(torch.randn(64, 128, device=DEV)))     # TF32 weight with an FP16 activation
+    old = ops.set_gemm_engine(ops.ENGINE_SIMT)
+    try:
+        with pytest.raises(CvarError):
+            ops.gemm(None, ops.SplitWeight(torch.randn(64, 128, device=DEV), f16=True), None, out, 64, 64, 128,
+                     A16=ops.F16Pair.from_tensor(torch.randn(64, 128, device=DEV)))
+    finally:
+        ops.set_gemm_engine(old)
+
+
+def test_ln_modulate_pair_output():
+    torch.manual_seed(5)
+    R, l, C = 6, 50, 768
+    M = R * l
+    x, ada = g(torch.randn(M, C) * 3 + 1), g(torch.randn(R, 6 * C))
+    y = torch.empty(M, C, device=DEV)
+    ops.ln_modulate(x, ada[:, 2 * C:3 * C], ada[:, 4 * C:5 * C], 6 * C, y, M, C, l, 1e-6)
+    p = ops.F16Pair.empty((M, C), DEV)
+    ops.ln_modulate(x, ada[:, 2 * C:3 * C], ada[:, 4 * C:5 * C], 6 * C, None, M, C, l, 1e-6, out16=p)
+    chk = ops.F16Pair.from_tensor(y)
+    assert torch.equal(chk.hi, p.hi) and torch.equal(chk.lo, p.lo)
+    y2, p2 = torch.empty(M, C, device=DEV), ops.F16Pair.empty((M, C), DEV)
+    ops.ln_modulate(x, ada[:, 2 * C:3 * C], ada[:, 4 * C:5 * C], 6 * C, y2, M, C, l, 1e-6, out16=p2)
+    assert torch.equal(y2, y) and torch.equal(p2.hi, p.hi) and torch.equal(p2.lo, p.lo)
+
+
+@pytest.mark.parametrize("l,L", [(8, 30), (128, 328), (200, 548)])
+def test_attention_pair_output(l, L):
+    """cvar_attn_kvcache out16 == split of its fp32 output, on the SIMT (l < 64) and the tensor-core kernel."""
+    torch.manual_seed(l)
+    R, H = 3, 4
+    cache = ops.KVCache(R, H, L, DEV)
+    A = g(torch.randn(R * L, H * 64))
+    W = ops.SplitWeight(g(torch.randn(3 * H * 64, H * 64) / 16))
+    zeros = torch.zeros(H * 64, device=DEV)
+    q = torch.empty(R * H * L * 64, device=DEV)
+    ops.qkv_project(A, W, zeros, zeros, zeros, q, cache, R, L, 0, H, False, None)       # fill the cache with L keys
+    qq = g(torch.randn(R, H, l, 64))
+    o = torch.empty(R * l, H * 64, device=DEV)
+    ops.attn_kvcache(qq, cache, o, R, H, l, L, 0.125)
+    p = ops.F16Pair.empty((R * l, H * 64), DEV)
+    ops.attn_kvcache(qq, cache, None, R, H, l, L, 0.125, out16=p)
+    chk = ops.F16Pair.from_tensor(o)
+    assert torch.equal(chk.hi, p.hi) and torch.equal(chk.lo, p.lo)
+
+
+def test_qkv_project_pair_operands(engine4):
+    torch.manual_seed(9)
+    R, l, H = 2, 96, 4
+    C = H * 64
+    A = g(torch.randn(R * l, C))
+    Wq = g(torch.randn(3 * C, C) / math.sqrt(C))
+    qb, kb, vb = g(torch.randn(C)), torch.zeros(C, device=DEV), g(torch.randn(C))
+    c16, c32 = ops.KVCache(R, H, l, DEV), ops.KVCache(R, H, l, DEV)
+    q16, q32 = torch.empty(R * H * l * 64, device=DEV), torch.empty(R * H * l * 64, device=DEV)
+    ops.qkv_project(None, ops.SplitWeight(Wq, f16=True), qb, kb, vb, q16, c16, R, l, 0, H, False, None,
+                    A16=ops.F16Pair.from_tensor(A))
+    ops.set_gemm_engine(ops.ENGINE_SIMT)
+    ops.qkv_project(A, Wq, qb, kb, vb, q32, c32, R, l, 0, H, False, None)
+    ops.set_gemm_engine(ops.ENGINE_TC_F16X3)
+    ref = (A.double() @ Wq.double().T).cpu()
+    scale = ref.abs().max().item()
+    assert (q16 - q32).abs().max().item() / scale < 5e-6
+    assert (c16.keys(l) - c32.keys(l)).abs().max().item() / scale < 5e-6
+    assert (c16.values(l) - c32.values(l)).abs().max().item() / scale < 5e-6

@@ -28,12 +28,12 @@ def check(results):
 
 def test_d24_full_width_all_engines():
     import fullwidth_parity as fp
-    check(fp.run(24, 1, [0, 1, 3], quiet=True))
+    check(fp.run(24, 1, [0, 1, 3, 4], quiet=True))
 
 
 def test_d30_full_width_cosine_attention_at_the_x100_clamp():
     import fullwidth_parity as fp
-    check(fp.run(30, 1, [3], quiet=True, scale_mul=5.0))
+    check(fp.run(30, 1, [3, 4], quiet=True, scale_mul=5.0))
 
 
 def test_positive_control_the_comparison_can_fail():

@@ -34,7 +34,7 @@ def build(cfg, weight_seed=0):
     return vae, var, sd, vsd
 
 
-@pytest.fixture(params=[0, 1, 3], ids=["simt", "tc3xtf32", "tc2cta"])
+@pytest.fixture(params=[0, 1, 3, 4], ids=["simt", "tc3xtf32", "tc2cta", "f16x3"])
 def engine(request):
     old = ops.set_gemm_engine(request.param)
     yield request.param
@@ -45,7 +45,7 @@ def engine(request):
 def test_sampler_matches_reference_golden(engine, name):
     gold = load_golden(name)
     m, cfg = gold["meta"], gold["cfg"]
-    vae, var, _, _ = build(cfg, m["weight_seed"])
+    vae, var, _, vsd = build(cfg, m["weight_seed"])
     img = var.autoregressive_infer_cfg(m["B"], torch.tensor(m["labels"]), g_seed=m["seed"], cfg=m["cfg"],
                                        top_k=m["top_k"], top_p=m["top_p"], cond_type=torch.tensor(m["cond"]))
     torch.cuda.synchronize()
@@ -57,6 +57,14 @@ def test_sampler_matches_reference_golden(engine, name):
     err = (img[:, :, ::sub, ::sub].cpu() - gold["img_sub"]).abs().max().item()
     assert err < PIXEL_TOL, f"{name}: pixel error {err:.3e}"
     assert abs(img.double().mean().item() - gold["img_mean"]) < 1e-5
+    # EVERY pixel, on the decoder's own [-1, 1] scale (the fixture holds a 1-in-`sub` grid of the [0, 1] image, which is
+    # too lenient to catch a decoder that is 2e-4 off - profiles/r01_decoder_policy.md): decode the reference's f_hat
+    # with the oracle here (control half on top, image half below, control_var.py:563-565).
+    fh = gold["f_hat"]
+    hw = fh.shape[-1]
+    full = torch.cat([O.fhat_to_img(fh[:, :, :hw].contiguous(), vsd), O.fhat_to_img(fh[:, :, hw:].contiguous(), vsd)], dim=2)
+    err_full = (img.cpu().mul(2).sub(1) - full).abs().max().item()
+    assert err_full < PIXEL_TOL, f"{name}: full-image pixel error {err_full:.3e} on the [-1,1] scale"
     # deterministic for a fixed seed
     img2 = var.autoregressive_infer_cfg(m["B"], torch.tensor(m["labels"]), g_seed=m["seed"], cfg=m["cfg"],
                                         top_k=m["top_k"], top_p=m["top_p"], cond_type=torch.tensor(m["cond"]))

@@ -66,7 +66,7 @@ def run(depth, B, engines, seed=0, cfg_scale=1.5, top_k=900, top_p=0.96, quiet=F
         fh = (var.last_f_hat.cpu() - ref["f_hat"]).abs().max().item()
         results[eng] = dict(rows=rows, f_hat_err=fh)
         if not quiet:
-            name = {0: "SIMT fp32", 1: "tcgen05 1-CTA", 3: "tcgen05 2-CTA (default)"}[eng]
+            name = {0: "SIMT fp32", 1: "tcgen05 1-CTA 3xTF32", 3: "tcgen05 2-CTA 3xTF32", 4: "tcgen05 2-CTA f16x3"}[eng]
             print(f"\n== d{depth} B={B} engine {eng} ({name}); oracle {t_or:.1f} s on {torch.get_num_threads()} threads")
             print(" si    l  draws  max|dlogit|  |logit|max  flips  worst margin of a flip  draws with margin<1e-4")
             for r in rows:

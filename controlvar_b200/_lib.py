@@ -45,6 +45,7 @@ class ConvArgs(C.Structure):
         ("upsample2x", C.c_int),
         ("out_mode", C.c_int), ("out_rows_total", C.c_int), ("row_offset", C.c_int),
         ("engine", C.c_int),
+        ("x16_hi", C.c_void_p), ("x16_lo", C.c_void_p), ("w16_hi", C.c_void_p), ("w16_lo", C.c_void_p),
     ]
 
 
@@ -80,7 +81,9 @@ PROTOTYPES = {
                                 C.c_void_p]),
     "cvar_conv2d": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),
     "cvar_repack_conv_weight": (C.c_int, [c_f, c_f, C.c_int, C.c_int, C.c_int, C.c_void_p]),
-    "cvar_affine_nc": (C.c_int, [c_f, c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "cvar_affine_nc": (C.c_int, [c_f, c_f, c_f, c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "cvar_conv2d_f16_supported": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "cvar_upsample2x_split_f16": (C.c_int, [c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "cvar_softmax_rows": (C.c_int, [c_f, C.c_int, C.c_int, C.c_void_p]),
 }
 

@@ -16,6 +16,8 @@ int tc2_qkv_try(const float* A_hi, const float* A_lo, const float* Wqkv_hi, cons
 int tc_conv_try(const cvar_conv_args* a, cudaStream_t s);
 // FP16-pair operands (engine 4): 0 ok, < 0 error - never a fall-through
 int tc2_gemm_f16(const cvar_gemm_args* a, cudaStream_t s);
+int tc2_conv_f16(const cvar_conv_args* a, cudaStream_t s);
+int tc2_conv_f16_supported(int H, int W, int Cin, int Cout, int ks);
 int tc2_qkv_f16(const void* A_hi, const void* A_lo, const void* W_hi, const void* W_lo, const QkvEpilogue& ep, int M, int C,
                 cudaStream_t s);
 }  // namespace cvar
@@ -152,6 +154,11 @@ extern "C" int cvar_conv2d(const cvar_conv_args* a, void* stream) {
   CVAR_REQUIRE(a->out_mode == 0 || a->resid == nullptr, "cvar_conv2d: image output takes no residual");
   CVAR_REQUIRE((a->in_a == nullptr) == (a->in_b == nullptr), "cvar_conv2d: in_a/in_b must come together");
   cudaStream_t s = (cudaStream_t)stream;
+  if (a->x16_hi != nullptr) {
+    CVAR_REQUIRE(g_gemm_engine != 0, "cvar_conv2d: FP16-pair operands need a tensor-core engine (engine is 0 = SIMT)");
+    return tc2_conv_f16(a, s);
+  }
+  CVAR_REQUIRE(a->x != nullptr && a->w != nullptr, "cvar_conv2d: null x / w");
   if (g_gemm_engine != 0 && a->engine != 0 && a->w_hi != nullptr && a->w_lo != nullptr) {
     int took = tc_conv_try(a, s);
     if (took < 0) return took;
@@ -168,6 +175,10 @@ extern "C" int cvar_conv2d(const cvar_conv_args* a, void* stream) {
   DenseBLoader bl{a->w, K, 0, a->Cout, K, 0, 1};
   ConvEpilogue ep{a->out, a->bias, a->resid, a->Cout, a->out_mode, Hout, Wout, a->out_rows_total, a->row_offset};
   return launch_sgemm(al, bl, ep, M, a->Cout, K, 1, s, "cvar_conv2d");
+}
+
+extern "C" int cvar_conv2d_f16_supported(int H, int W, int Cin, int Cout, int ks) {
+  return tc2_conv_f16_supported(H, W, Cin, Cout, ks);
 }
 
 extern "C" int cvar_split_tf32(const float* w, float* w_hi, float* w_lo, long long n, void* stream) {

@@ -259,6 +259,190 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constan
   if (warp == kMmaWarp) tmem_dealloc2(tmem_base, 512);
 }
 
+
+// ================================================================================================ conv: implicit GEMM
+// 3x3 / 1x1 stride-1 'same' convolution on FP16-pair NHWC activations, all operands by TMA.  The A tile of a K-block is
+// a shifted WINDOW of the activation fetched with a 4-D tensor map (C, W, H, B): box = 32 channels x Wb x Hb pixels
+// (Wb * Hb = 128 output pixels of one image), coordinates offset by the tap; pixels outside the image are zero-filled
+// by the TMA unit, which IS the convolution's zero padding - no im2col buffer and no gather warps.  K runs tap-major
+// over (ky, kx, 32-channel chunk), matching cvar_repack_conv_weight.  Decoder channel counts are multiples of 160, not
+// of 64, so the shared-memory row is 64 bytes (32 halves, SWIZZLE_64B) and a stage is 4 x 8 KiB; six stages.
+constexpr int kCvStages = 6;
+constexpr int kCvTile = 128 * 64;                  // 8 KiB: 128 rows of 32 halves (A: pixels; B: up to 128 weight rows)
+constexpr int kCvStageBytes = 4 * kCvTile;         // A_hi, A_lo, B_hi, B_lo
+constexpr int kCvSmem = kCvStages * kCvStageBytes + kStagingBytes + 1024 + 1024;
+
+struct ConvGeo {
+  int H, W, Cin, ks;      // resolution (output == input), input channels, 1 or 3
+  int Wb;                 // box width min(W, 128); box height 128 / Wb
+  int BN;                 // output channels per pair tile: multiple of 32, <= 256
+};
+
+__device__ __forceinline__ void tma_load_4d_2sm(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2,
+                                                int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::
+          "r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kPeerMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+template <class EP>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+tc_conv2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
+                const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo, EP ep, ConvGeo g,
+                long long M, int N, int m_tiles, int n_tiles) {
+  using G = Geo<16>;                                 // 64-byte rows, SWIZZLE_64B
+  const int BNr = g.BN;
+  const uint32_t idesc = (1u << 4) | ((uint32_t)(BNr >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);   // F16 x F16 -> F32
+  constexpr int kAccStride = 256;
+  constexpr float kLoScale = 1.0f / 2048.0f;
+
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  auto a_hi = [&](int s) { return smem + s * kCvStageBytes; };
+  auto a_lo = [&](int s) { return smem + s * kCvStageBytes + kCvTile; };
+  auto b_hi = [&](int s) { return smem + s * kCvStageBytes + 2 * kCvTile; };
+  auto b_lo = [&](int s) { return smem + s * kCvStageBytes + 3 * kCvTile; };
+  float* stage_base = reinterpret_cast<float*>(smem + kCvStages * kCvStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kCvStages * kCvStageBytes + kStagingBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kCvStages;
+  uint64_t* tm_full = bars + 2 * kCvStages;
+  uint64_t* tm_empty = bars + 2 * kCvStages + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kCvStages + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int cpb = g.Cin >> 5;                        // 32-channel chunks per tap
+  const int nkb = g.ks * g.ks * cpb;
+  const int total_tiles = m_tiles * n_tiles;
+
+  if (warp == kTmaWarp && lane == 0) {
+    tma_prefetch_desc(&mapAhi), tma_prefetch_desc(&mapAlo), tma_prefetch_desc(&mapBhi), tma_prefetch_desc(&mapBlo);
+    for (int s = 0; s < kCvStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tm_full, 1);
+    mbar_init(tm_empty, 2 * kEpiWarps * 32);
+    fence_barrier_init();
+  }
+  if (warp == kMmaWarp) tmem_alloc2(tmem_slot, 512);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < kEpiWarps) {
+    // ================================================================ epilogue: row r of the tile is output pixel m0 + r
+    float* stage = stage_base + warp * (32 * kStagePitch);
+    const int quarter = warp & 3, half = warp >> 2;
+    int tcount = 0;
+    for (int tile = pair; tile < total_tiles; tile += npairs, ++tcount) {
+      int mt, nt;
+      tile_coords(tile, m_tiles, n_tiles, mt, nt);
+      mbar_wait(tm_full, tcount & 1);
+      tc_fence_after();
+      const long long m_base = (long long)mt * 256 + rank * BM + quarter * 32;
+      const uint32_t tcol = tmem_base + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
+      for (int c = half * (BNr / 2); c < (half + 1) * (BNr / 2); c += kEpiCols) {
+        float v[kEpiCols], w[kEpiCols];
+        tmem_ld_32x32b_x16(tcol + (uint32_t)c, v);
+        tmem_ld_32x32b_x16(tcol + (uint32_t)(kAccStride + c), w);
+#pragma unroll
+        for (int q = 0; q < kEpiCols / 4; ++q)
+          *reinterpret_cast<float4*>(stage + lane * kStagePitch + q * 4) =
+              make_float4(fmaf(w[4 * q], kLoScale, v[4 * q]), fmaf(w[4 * q + 1], kLoScale, v[4 * q + 1]),
+                          fmaf(w[4 * q + 2], kLoScale, v[4 * q + 2]), fmaf(w[4 * q + 3], kLoScale, v[4 * q + 3]));
+        __syncwarp();
+        const int n = nt * BNr + c + (lane & 3) * 4;
+        const int nvalid = min(4, N - n);
+        EpiAux aux[4];
+#pragma unroll
+        for (int r8 = 0; r8 < 4; ++r8) {
+          const long long m = m_base + r8 * 8 + (lane >> 2);
+          if (m < M && n < N) aux[r8] = epi_load_aux(ep, m, n, nvalid, 0);
+        }
+#pragma unroll
+        for (int r8 = 0; r8 < 4; ++r8) {
+          const int rr = r8 * 8 + (lane >> 2);
+          const float4 x = *reinterpret_cast<const float4*>(stage + rr * kStagePitch + (lane & 3) * 4);
+          const long long m = m_base + rr;
+          if (m < M && n < N) epi_store_aux(ep, m, n, &x.x, nvalid, 0, aux[r8]);
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      mbar_arrive_leader(tm_empty);
+    }
+  } else if (warp == kTmaWarp) {
+    // ================================================================ TMA: this CTA's 128 pixels (shifted window per tap)
+    if (lane == 0) {
+      const int pad = g.ks >> 1;
+      const long long HW = (long long)g.H * g.W;
+      const uint32_t stage_tx = 2u * (2u * (uint32_t)kCvTile + 2u * (uint32_t)(BNr / 2) * 64u);   // both CTAs
+      int it = 0;
+      for (int tile = pair; tile < total_tiles; tile += npairs) {
+        int mt, nt;
+        tile_coords(tile, m_tiles, n_tiles, mt, nt);
+        const long long m0 = (long long)mt * 256 + (long long)rank * BM;
+        const int img = (int)(m0 / HW);
+        const int rem = (int)(m0 - (long long)img * HW);
+        const int y0 = rem / g.W, x0 = rem - y0 * g.W;
+        const int brow = nt * BNr + (int)rank * (BNr / 2);
+        int kb = 0;
+        for (int tap = 0; tap < g.ks * g.ks; ++tap) {
+          const int ky = tap / g.ks, kx = tap - ky * g.ks;
+          for (int cc = 0; cc < cpb; ++cc, ++kb, ++it) {
+            const int s = it % kCvStages;
+            const uint32_t ph = (it / kCvStages) & 1;
+            mbar_wait(&empty[s], ph ^ 1);
+            if (rank == 0) mbar_arrive_expect_tx(&full[s], stage_tx);
+            tma_load_4d_2sm(&mapAhi, &full[s], a_hi(s), cc * 32, x0 + kx - pad, y0 + ky - pad, img);
+            tma_load_4d_2sm(&mapAlo, &full[s], a_lo(s), cc * 32, x0 + kx - pad, y0 + ky - pad, img);
+            tma_load_2d_2sm(&mapBhi, &full[s], b_hi(s), kb * 32, brow);
+            tma_load_2d_2sm(&mapBlo, &full[s], b_lo(s), kb * 32, brow);
+          }
+        }
+      }
+    }
+  } else if (rank == 0) {
+    // ================================================================ MMA issue (leader CTA only)
+    if (lane == 0) {
+      int it = 0, tcount = 0;
+      for (int tile = pair; tile < total_tiles; tile += npairs, ++tcount) {
+        mbar_wait(tm_empty, (tcount & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d = tmem_base, dl = tmem_base + (uint32_t)kAccStride;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % kCvStages;
+          const uint32_t ph = (it / kCvStages) & 1;
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint64_t dah = G::desc(smem_u32(a_hi(s))), dal = G::desc(smem_u32(a_lo(s)));
+          const uint64_t dbh = G::desc(smem_u32(b_hi(s))), dbl = G::desc(smem_u32(b_lo(s)));
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {               // 32 halves = two K=16 steps of 32 bytes
+            const uint64_t adv = (uint64_t)(k * 2);
+            umma_2sm<true>(dl, dal + adv, dbh + adv, idesc, (kb | k) != 0);
+            umma_2sm<true>(dl, dah + adv, dbl + adv, idesc, 1u);
+            umma_2sm<true>(d, dah + adv, dbh + adv, idesc, (kb | k) != 0);
+          }
+          umma_commit_2sm(&empty[s]);
+        }
+        umma_commit_2sm(tm_full);
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == kMmaWarp) tmem_dealloc2(tmem_base, 512);
+}
+
 // ------------------------------------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -292,6 +476,48 @@ static int make_map(CUtensorMap* map, const void* base, long long rows, int K, l
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("tc_gemm2: cuTensorMapEncodeTiled failed with %d (rows=%lld K=%d ld=%lld)", (int)r, rows, K, ld);
+    return -3;
+  }
+  return 0;
+}
+
+// NHWC half activation (B, H, W, C) -> 4-D map (C, W, H, B), box 32 channels x Wb x Hb pixels, 64-byte swizzle
+static int make_map_act(CUtensorMap* map, const void* base, int B, int H, int W, int C, int Wb, int Hb) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("tc_conv2: cuTensorMapEncodeTiled is not available from the driver");
+    return -3;
+  }
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {32, (cuuint32_t)Wb, (cuuint32_t)Hb, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("tc_conv2: cuTensorMapEncodeTiled(activation) failed with %d (B=%d H=%d W=%d C=%d box %dx%d)", (int)r, B, H, W,
+              C, Wb, Hb);
+    return -3;
+  }
+  return 0;
+}
+// repacked weight [Cout, K] halves -> (32 x rows) box, 64-byte swizzle
+static int make_map_w64(CUtensorMap* map, const void* base, int Cout, int K, int rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("tc_conv2: cuTensorMapEncodeTiled is not available from the driver");
+    return -3;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)Cout};
+  cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+  cuuint32_t box[2] = {32, (cuuint32_t)rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("tc_conv2: cuTensorMapEncodeTiled(weight) failed with %d (Cout=%d K=%d rows=%d)", (int)r, Cout, K, rows);
     return -3;
   }
   return 0;
@@ -361,6 +587,55 @@ int tc2_qkv_f16(const void* A_hi, const void* A_lo, const void* W_hi, const void
                "cvar_qkv_project[f16x3]: operands must be 16-byte aligned");
   return tc2::launch<QkvEpilogue, true>(ep, A_hi, A_lo, C, W_hi, W_lo, C, (long long)M, 3 * C, C, s,
                                         "cvar_qkv_project[tc2/f16x3]");
+}
+
+// FP16-pair convolution (engine 4): 0 ok, < 0 error.  cvar_conv2d_f16_supported() tells the host in advance.
+static int conv_f16_bn(int Cout) {
+  const int cand[] = {256, 160, 128, 224, 192, 96, 64, 32};
+  for (int bn : cand)
+    if (Cout % bn == 0) return bn;
+  return 0;
+}
+int tc2_conv_f16_supported(int H, int W, int Cin, int Cout, int ks) {
+  if (ks != 1 && ks != 3) return 0;
+  if (Cin % 32 != 0 || conv_f16_bn(Cout) == 0) return 0;
+  const int Wb = W < 128 ? W : 128;
+  if (W <= 0 || (W < 128 ? (128 % W != 0) : (W % 128 != 0))) return 0;
+  const int Hb = 128 / Wb;
+  if (H % Hb != 0) return 0;
+  return 1;
+}
+int tc2_conv_f16(const cvar_conv_args* a, cudaStream_t s) {
+  CVAR_REQUIRE(a->x16_hi && a->x16_lo && a->w16_hi && a->w16_lo, "cvar_conv2d[f16x3]: x16_hi/x16_lo/w16_hi/w16_lo must all be set");
+  CVAR_REQUIRE(!a->upsample2x && a->in_a == nullptr,
+               "cvar_conv2d[f16x3]: the FP16-pair input is taken as is (upsample / normalise it when producing the pair)");
+  const int H = a->Hin, W = a->Win;
+  CVAR_REQUIRE(tc2_conv_f16_supported(H, W, a->Cin, a->Cout, a->ks),
+               "cvar_conv2d[f16x3]: unsupported shape H=%d W=%d Cin=%d Cout=%d ks=%d", H, W, a->Cin, a->Cout, a->ks);
+  CVAR_REQUIRE(tc2::aligned16(a->x16_hi) && tc2::aligned16(a->x16_lo) && tc2::aligned16(a->w16_hi) && tc2::aligned16(a->w16_lo),
+               "cvar_conv2d[f16x3]: operands must be 16-byte aligned");
+  tc2::ConvGeo g;
+  g.H = H, g.W = W, g.Cin = a->Cin, g.ks = a->ks;
+  g.Wb = W < 128 ? W : 128;
+  g.BN = conv_f16_bn(a->Cout);
+  const int Hb = 128 / g.Wb;
+  const int K = a->ks * a->ks * a->Cin;
+  CUtensorMap mah, mal, mbh, mbl;
+  int rc = tc2::make_map_act(&mah, a->x16_hi, a->B, H, W, a->Cin, g.Wb, Hb);
+  if (!rc) rc = tc2::make_map_act(&mal, a->x16_lo, a->B, H, W, a->Cin, g.Wb, Hb);
+  if (!rc) rc = tc2::make_map_w64(&mbh, a->w16_hi, a->Cout, K, g.BN / 2);
+  if (!rc) rc = tc2::make_map_w64(&mbl, a->w16_lo, a->Cout, K, g.BN / 2);
+  if (rc) return rc;
+  ConvEpilogue ep{a->out, a->bias, a->resid, a->Cout, a->out_mode, H, W, a->out_rows_total, a->row_offset};
+  auto kern = tc2::tc_conv2_kernel<ConvEpilogue>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::kCvSmem);
+  CVAR_REQUIRE(e == cudaSuccess, "cvar_conv2d[f16x3]: cannot raise shared memory to %d: %s", tc2::kCvSmem, cudaGetErrorString(e));
+  const long long M = (long long)a->B * H * W;
+  const int m_tiles = cdiv(M, 256), n_tiles = a->Cout / g.BN;
+  const int pairs = min(tc2::num_sms() / 2, m_tiles * n_tiles);
+  kern<<<2 * pairs, tc2::kThreads, tc2::kCvSmem, s>>>(mah, mal, mbh, mbl, ep, g, M, a->Cout, m_tiles, n_tiles);
+  CVAR_CHECK_LAUNCH("cvar_conv2d[tc2/f16x3]");
+  return 0;
 }
 
 int tc2_gemm_try(const cvar_gemm_args* a, cudaStream_t s) {

@@ -288,7 +288,8 @@ extern "C" int cvar_gn_stats(const float* x_nhwc, const float* gamma, const floa
 }
 
 __global__ void affine_nc_kernel(const float* __restrict__ x, const float* __restrict__ a, const float* __restrict__ b,
-                                 float* __restrict__ y, long long HWC4, int C4, long long total4, int silu) {
+                                 float* __restrict__ y, __half* __restrict__ y16_hi, __half* __restrict__ y16_lo,
+                                 long long HWC4, int C4, long long total4, int silu) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total4) return;
   long long n = i / HWC4;
@@ -305,15 +306,63 @@ __global__ void affine_nc_kernel(const float* __restrict__ x, const float* __res
     v.z = silu_f(v.z);
     v.w = silu_f(v.w);
   }
-  st4(y + i * 4, v);
+  if (y16_hi != nullptr) {
+    const float vv[4] = {v.x, v.y, v.z, v.w};
+    st4_split_f16(y16_hi + i * 4, y16_lo + i * 4, vv);
+  }
+  if (y != nullptr) st4(y + i * 4, v);
 }
 
-extern "C" int cvar_affine_nc(const float* x_nhwc, const float* a, const float* b, float* y, int B, int HW, int C,
-                              int silu, void* stream) {
+// nearest x2 upsample + FP16-pair split: one thread per 4 channels of a SOURCE pixel, four destination pixels
+__global__ void upsample2x_split_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo,
+                                        int H, int W, int C4, long long total4) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  const int c4 = (int)(i % C4);
+  long long p = i / C4;
+  const int xw = (int)(p % W);
+  p /= W;
+  const int yh = (int)(p % H);
+  const long long n = p / H;
+  const float4 v = ld4(x + i * 4);
+  const float vv[4] = {v.x, v.y, v.z, v.w};
+  __half h[4], l[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) split_f16(vv[j], h[j], l[j]);
+  uint2 ph, pl;
+  ph.x = (uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16);
+  ph.y = (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16);
+  pl.x = (uint32_t)__half_as_ushort(l[0]) | ((uint32_t)__half_as_ushort(l[1]) << 16);
+  pl.y = (uint32_t)__half_as_ushort(l[2]) | ((uint32_t)__half_as_ushort(l[3]) << 16);
+#pragma unroll
+  for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx) {
+      const long long o = (((n * (2 * H) + (2 * yh + dy)) * (2 * W) + (2 * xw + dx)) * C4 + c4) * 4;
+      *reinterpret_cast<uint2*>(hi + o) = ph;
+      *reinterpret_cast<uint2*>(lo + o) = pl;
+    }
+}
+
+extern "C" int cvar_upsample2x_split_f16(const float* x_nhwc, void* hi, void* lo, int B, int H, int W, int C, void* stream) {
+  CVAR_REQUIRE(C % 4 == 0 && B > 0 && H > 0 && W > 0, "cvar_upsample2x_split_f16: bad shape");
+  CVAR_REQUIRE(x_nhwc && hi && lo, "cvar_upsample2x_split_f16: null pointer");
+  const long long total4 = (long long)B * H * W * C / 4;
+  upsample2x_split_kernel<<<cdiv(total4, 256), 256, 0, (cudaStream_t)stream>>>(
+      x_nhwc, reinterpret_cast<__half*>(hi), reinterpret_cast<__half*>(lo), H, W, C / 4, total4);
+  CVAR_CHECK_LAUNCH("cvar_upsample2x_split_f16");
+  return 0;
+}
+
+extern "C" int cvar_affine_nc(const float* x_nhwc, const float* a, const float* b, float* y, void* y16_hi, void* y16_lo,
+                              int B, int HW, int C, int silu, void* stream) {
   CVAR_REQUIRE(C % 4 == 0, "cvar_affine_nc: C %% 4 != 0");
+  CVAR_REQUIRE(y != nullptr || y16_hi != nullptr, "cvar_affine_nc: no output");
+  CVAR_REQUIRE((y16_hi == nullptr) == (y16_lo == nullptr), "cvar_affine_nc: y16_hi/y16_lo must come together");
   long long total4 = (long long)B * HW * C / 4;
-  affine_nc_kernel<<<cdiv(total4, 256), 256, 0, (cudaStream_t)stream>>>(x_nhwc, a, b, y, (long long)HW * C / 4, C / 4,
-                                                                        total4, silu);
+  affine_nc_kernel<<<cdiv(total4, 256), 256, 0, (cudaStream_t)stream>>>(
+      x_nhwc, a, b, y, reinterpret_cast<__half*>(y16_hi), reinterpret_cast<__half*>(y16_lo), (long long)HW * C / 4, C / 4,
+      total4, silu);
   CVAR_CHECK_LAUNCH("cvar_affine_nc");
   return 0;
 }

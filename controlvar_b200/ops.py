@@ -302,10 +302,16 @@ def gn_stats(x_nhwc, gamma, beta, a_out, b_out, scratch, B, HW, Cdim, groups=32,
 
 
 def conv2d(x, w_packed, bias, out, B, Hin, Win, Cin, Cout, ks, *, in_a=None, in_b=None, in_silu=False, resid=None,
-           upsample2x=False, out_mode=0, out_rows_total=0, row_offset=0, engine=-1):
+           upsample2x=False, out_mode=0, out_rows_total=0, row_offset=0, engine=-1, x16: Optional[F16Pair] = None,
+           w16: Optional[F16Pair] = None):
+    """x16 + w16: FP16-pair input (already normalised / upsampled) and weight -> the 2-CTA TMA kernel; x may be None."""
     w_packed, w_hi, w_lo, _ = _wparts(w_packed)
     _chk(x, w_packed, bias, out, in_a, in_b, resid)
+    if (x16 is None) != (w16 is None):
+        raise _lib.CvarError("conv2d: x16 and w16 must come together")
     a = ConvArgs()
+    a.x16_hi, a.x16_lo = _p16(x16)
+    a.w16_hi, a.w16_lo = _p16(w16)
     a.x, a.w, a.bias, a.out = _p(x), _p(w_packed), _p(bias), _p(out)
     a.w_hi, a.w_lo = _p(w_hi), _p(w_lo)
     a.in_a, a.in_b, a.in_silu = _p(in_a), _p(in_b), int(in_silu)
@@ -327,10 +333,23 @@ def repack_conv_weight(w_oihw, out):
     return out
 
 
-def affine_nc(x, a, b, out, B, HW, Cdim, silu=False):
+def affine_nc(x, a, b, out, B, HW, Cdim, silu=False, out16: Optional[F16Pair] = None):
     _chk(x, a, b, out)
-    check(_lib.load().cvar_affine_nc(_p(x), _p(a), _p(b), _p(out), B, HW, Cdim, int(silu), _stream()), "cvar_affine_nc")
-    return out
+    h16, l16 = _p16(out16)
+    check(_lib.load().cvar_affine_nc(_p(x), _p(a), _p(b), _p(out), h16, l16, B, HW, Cdim, int(silu), _stream()),
+          "cvar_affine_nc")
+    return out if out is not None else out16
+
+
+def conv2d_f16_supported(H, W, Cin, Cout, ks) -> bool:
+    return bool(_lib.load().cvar_conv2d_f16_supported(int(H), int(W), int(Cin), int(Cout), int(ks)))
+
+
+def upsample2x_split_f16(x, out16: F16Pair, B, H, W, Cdim):
+    _chk(x)
+    check(_lib.load().cvar_upsample2x_split_f16(_p(x), _p(out16.hi), _p(out16.lo), B, H, W, Cdim, _stream()),
+          "cvar_upsample2x_split_f16")
+    return out16
 
 
 def softmax_rows(x, rows, cols):

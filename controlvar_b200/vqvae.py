@@ -67,6 +67,7 @@ class VQVAE(nn.Module):
         # cost almost nothing, so they stay in exact fp32: worst pixel 5.9e-5 for +50 ms per 64-image decode.
         self.tc_min_hw = 64
         self._packed: Dict[str, torch.Tensor] = {}
+        self._packed16: Dict[str, "ops.F16Pair"] = {}
         self._ws: Dict[Tuple, torch.Tensor] = {}
         self.eval()
 
@@ -78,10 +79,12 @@ class VQVAE(nn.Module):
         if k in sd and sd[k].shape[0] != self.quantize.ema_vocab_hit_SV.shape[0]:
             sd[k] = self.quantize.ema_vocab_hit_SV
         self._packed.clear()
+        self._packed16.clear()
         return super().load_state_dict(sd, strict=strict, assign=assign)
 
     def _apply(self, fn, recurse=True):
         self._packed.clear()
+        self._packed16.clear()
         self._ws.clear()
         return super()._apply(fn, recurse)
 
@@ -101,9 +104,37 @@ class VQVAE(nn.Module):
             self._packed[key] = t
         return t
 
-    def _conv(self, x, w, bias, out, B, Hin, Win, Cin, Cout, ks, **kw):
+    def _conv_w16(self, prefix: str) -> "ops.F16Pair":
+        """FP16 pair of the repacked weight, for the f16x3 convolution kernel (cached)."""
+        key = prefix + ".weight"
+        p = self._packed16.get(key)
+        if p is None:
+            w = self._conv_w(prefix)
+            p = ops.F16Pair.from_tensor(w.w if isinstance(w, ops.SplitWeight) else w)
+            self._packed16[key] = p
+        return p
+
+    def _f16_layer(self, Hout, Wout, Cin, Cout, ks) -> bool:
+        """Does this layer run on the FP16-pair TMA kernel?  Engine 4, accuracy policy (tc_min_hw), supported shape."""
+        return (ops.get_gemm_engine() == ops.ENGINE_TC_F16X3 and Hout >= self.tc_min_hw
+                and ops.conv2d_f16_supported(Hout, Wout, Cin, Cout, ks))
+
+    def _conv(self, x, prefix, out, B, Hin, Win, Cin, Cout, ks, **kw):
+        """x: fp32 NHWC tensor, or an F16Pair (normalised / upsampled by its producer) for a layer _f16_layer() accepts."""
+        bias = self._w(prefix + ".bias")
+        if isinstance(x, ops.F16Pair):
+            return ops.conv2d(None, self._conv_w(prefix), bias, out, B, Hin, Win, Cin, Cout, ks, x16=x,
+                              w16=self._conv_w16(prefix), **kw)
         hout = Hin * (2 if kw.get("upsample2x") else 1)
-        return ops.conv2d(x, w, bias, out, B, Hin, Win, Cin, Cout, ks, engine=(-1 if hout >= self.tc_min_hw else 0), **kw)
+        return ops.conv2d(x, self._conv_w(prefix), bias, out, B, Hin, Win, Cin, Cout, ks,
+                          engine=(-1 if hout >= self.tc_min_hw else 0), **kw)
+
+    def _pair(self, name: str, numel: int, shape) -> "ops.F16Pair":
+        n = 1
+        for s_ in shape:
+            n *= s_
+        return ops.F16Pair(self._buf(name + ".hi", (numel,), torch.float16)[:n].view(shape),
+                           self._buf(name + ".lo", (numel,), torch.float16)[:n].view(shape))
 
     def _buf(self, name: str, shape, dtype=torch.float32) -> torch.Tensor:
         dev = self._w("post_quant_conv.weight").device
@@ -125,10 +156,15 @@ class VQVAE(nn.Module):
         ops.gn_stats(x, self._w(prefix + ".weight"), self._w(prefix + ".bias"), a, b, scratch, B, HW, Cn)
         return a, b
 
-    def _norm_act(self, x, prefix, B, H, W, Cn, slot: int):
+    def _norm_act(self, x, prefix, B, H, W, Cn, slot: int, pair: bool = False):
         """silu(GroupNorm(x)) materialised once (vae_modules.py:58-59).  One HBM-bound pass instead of re-evaluating
-        the normalisation + SiLU for each of the 9 taps inside the convolution's operand gather."""
+        the normalisation + SiLU for each of the 9 taps inside the convolution's operand gather.  pair: write it as the
+        FP16 pair the f16x3 convolution fetches by TMA (same bytes as fp32)."""
         a, b = self._gn(x, prefix, B, H * W, Cn, slot)
+        if pair:
+            y16 = self._pair("normact16", self._act_numel, (B, H, W, Cn))
+            ops.affine_nc(x, a, b, None, B, H * W, Cn, silu=True, out16=y16)
+            return y16
         y = self._buf("normact", (self._act_numel,))[:B * H * W * Cn].view(B, H, W, Cn)
         ops.affine_nc(x, a, b, y, B, H * W, Cn, silu=True)
         return y
@@ -136,16 +172,15 @@ class VQVAE(nn.Module):
     def _resblock(self, x, prefix, B, H, W, cin, cout, bufs):
         """ResnetBlock.forward (vae_modules.py:57-60); x is never written."""
         h1, out = bufs
-        self._conv(self._norm_act(x, prefix + "norm1", B, H, W, cin, 0), self._conv_w(prefix + "conv1"),
-                   self._w(prefix + "conv1.bias"), h1, B, H, W, cin, cout, 3)
+        self._conv(self._norm_act(x, prefix + "norm1", B, H, W, cin, 0, pair=self._f16_layer(H, W, cin, cout, 3)),
+                   prefix + "conv1", h1, B, H, W, cin, cout, 3)
         if cin != cout:
             sc = self._buf("shortcut", (B, H, W, cout))
-            self._conv(x, self._conv_w(prefix + "nin_shortcut"), self._w(prefix + "nin_shortcut.bias"), sc, B, H, W,
-                       cin, cout, 1)
+            self._conv(x, prefix + "nin_shortcut", sc, B, H, W, cin, cout, 1)
         else:
             sc = x
-        self._conv(self._norm_act(h1, prefix + "norm2", B, H, W, cout, 1), self._conv_w(prefix + "conv2"),
-                   self._w(prefix + "conv2.bias"), out, B, H, W, cout, cout, 3, resid=sc)
+        self._conv(self._norm_act(h1, prefix + "norm2", B, H, W, cout, 1, pair=self._f16_layer(H, W, cout, cout, 3)),
+                   prefix + "conv2", out, B, H, W, cout, cout, 3, resid=sc)
         return out
 
     def _attnblock(self, x, prefix, B, H, W, Cn, out):
@@ -175,8 +210,7 @@ class VQVAE(nn.Module):
         cfg = self.cfg
         H = W = hw
         zq = self._buf("z_pq", (B, H, W, cfg.Cvae))
-        self._conv(z_nhwc, self._conv_w("post_quant_conv"), self._w("post_quant_conv.bias"), zq, B, H, W, cfg.Cvae,
-                   cfg.Cvae, 3)
+        self._conv(z_nhwc, "post_quant_conv", zq, B, H, W, cfg.Cvae, cfg.Cvae, 3)
         cur = zq
         ring_i = 0
 
@@ -199,7 +233,7 @@ class VQVAE(nn.Module):
         for op, prefix, cin, cout in self._plan:
             if op == "conv3":
                 out = ring((B, H, W, cout))
-                self._conv(cur, self._conv_w(prefix), self._w(prefix + ".bias"), out, B, H, W, cin, cout, 3)
+                self._conv(cur, prefix, out, B, H, W, cin, cout, 3)
                 cur = out
             elif op == "res":
                 h1 = ring((B, H, W, cout))
@@ -210,14 +244,18 @@ class VQVAE(nn.Module):
                 cur = self._attnblock(cur, prefix, B, H, W, cin, out)
             elif op == "up":
                 out = ring((B, 2 * H, 2 * W, cout))
-                self._conv(cur, self._conv_w(prefix), self._w(prefix + ".bias"), out, B, H, W, cin, cout, 3,
-                           upsample2x=True)
+                if self._f16_layer(2 * H, 2 * W, cin, cout, 3):
+                    # Upsample2x (vae_modules.py:27-28): nearest x2 written once as the FP16 pair the conv fetches by TMA
+                    up16 = self._pair("normact16", self._act_numel, (B, 2 * H, 2 * W, cin))
+                    ops.upsample2x_split_f16(cur, up16, B, H, W, cin)
+                    self._conv(up16, prefix, out, B, 2 * H, 2 * W, cin, cout, 3)
+                else:
+                    self._conv(cur, prefix, out, B, H, W, cin, cout, 3, upsample2x=True)
                 H, W = 2 * H, 2 * W
                 cur = out
             elif op == "out":
-                self._conv(self._norm_act(cur, "decoder.norm_out", B, H, W, cin, 0), self._conv_w("decoder.conv_out"),
-                           self._w("decoder.conv_out.bias"), img_out, B, H, W, cin, 3, 3, out_mode=out_mode,
-                           out_rows_total=rows_total, row_offset=row_offset)
+                self._conv(self._norm_act(cur, "decoder.norm_out", B, H, W, cin, 0), "decoder.conv_out", img_out, B, H, W,
+                           cin, 3, 3, out_mode=out_mode, out_rows_total=rows_total, row_offset=row_offset)
             else:
                 raise AssertionError(op)
 

@@ -188,8 +188,20 @@ typedef struct {
   int B, Hin, Win, Cin, Cout, ks, upsample2x;
   int out_mode, out_rows_total, row_offset;
   int engine;   /* -1 = library default (cvar_set_gemm_engine); 0 = force the SIMT fp32 engine for this call */
+  /* FP16-pair operands (engine 4): when x16_hi is set the convolution runs on the 2-CTA tcgen05 kernel as an implicit
+   * GEMM whose activation windows are fetched by 4-D TMA (zero fill = padding).  x16_* is the INPUT as NHWC half pairs
+   * (B, Hin, Win, Cin), already normalised / activated / upsampled by its producer (cvar_affine_nc,
+   * cvar_upsample2x_split_f16, cvar_split_f16): x, in_a, in_b, upsample2x must be NULL / 0.  w16_* is the pair of the
+   * repacked weight.  Shapes: see cvar_conv2d_f16_supported. */
+  const void* x16_hi; const void* x16_lo; const void* w16_hi; const void* w16_lo;
 } cvar_conv_args;
 CVAR_API int cvar_conv2d(const cvar_conv_args* args, void* stream);
+/* 1 when the FP16-pair kernel takes this layer: ks in {1,3}, Cin % 32 == 0, Cout a multiple of one of
+ * {256,160,128,224,192,96,64,32}, and W | 128 or 128 | W with whole 128-pixel tiles inside an image. */
+CVAR_API int cvar_conv2d_f16_supported(int H, int W, int Cin, int Cout, int ks);
+/* nearest x2 upsampling (Upsample2x, vae_modules.py:27-28) fused with the FP16-pair split:
+ * x (B,H,W,C) fp32 NHWC -> hi / lo (B,2H,2W,C) halves.  C % 4 == 0. */
+CVAR_API int cvar_upsample2x_split_f16(const float* x_nhwc, void* hi, void* lo, int B, int H, int W, int C, void* stream);
 /* hi = w with the 13 low mantissa bits cleared (what a TF32 tensor-core operand keeps), lo = w - hi (exact): the
  * error-compensated 3xTF32 operands of the tcgen05 engine.  n must be a multiple of 4. */
 CVAR_API int cvar_split_tf32(const float* w, float* w_hi, float* w_lo, long long n, void* stream);
@@ -200,9 +212,10 @@ CVAR_API int cvar_split_tf32(const float* w, float* w_hi, float* w_lo, long long
 CVAR_API int cvar_split_f16(const float* x, void* hi, void* lo, long long n, void* stream);
 /* (Cout,Cin,ks,ks) -> (Cout, ks*ks*Cin), k index = (ky*ks+kx)*Cin + ci */
 CVAR_API int cvar_repack_conv_weight(const float* w_oihw, float* w_out, int Cout, int Cin, int ks, void* stream);
-/* y = x*a[n,c] + b[n,c] (GroupNorm without activation, AttnBlock.norm) */
-CVAR_API int cvar_affine_nc(const float* x_nhwc, const float* a, const float* b, float* y, int B, int HW, int C, int silu,
-                   void* stream);
+/* y = [silu](x*a[n,c] + b[n,c]): GroupNorm (+ SiLU) applied once (vae_modules.py:58-59, AttnBlock.norm).
+ * y16_hi / y16_lo (optional, halves, same shape): the result as an FP16 pair; y may then be NULL. */
+CVAR_API int cvar_affine_nc(const float* x_nhwc, const float* a, const float* b, float* y, void* y16_hi, void* y16_lo,
+                   int B, int HW, int C, int silu, void* stream);
 /* in-place row softmax of a (rows, cols) matrix (AttnBlock, vae_modules.py:84) */
 CVAR_API int cvar_softmax_rows(float* x, int rows, int cols, void* stream);
 

@@ -187,3 +187,94 @@ def test_qkv_project_pair_operands(engine4):
     assert (q16 - q32).abs().max().item() / scale < 5e-6
     assert (c16.keys(l) - c32.keys(l)).abs().max().item() / scale < 5e-6
     assert (c16.values(l) - c32.values(l)).abs().max().item() / scale < 5e-6
+
+
+# ------------------------------------------------------------------------------------------ convolution (decoder)
+def _conv_ref(x_nhwc, w_oihw, bias, resid=None):
+    y = F.conv2d(x_nhwc.double().permute(0, 3, 1, 2), w_oihw.double(), bias.double(), padding=w_oihw.shape[-1] // 2)
+    y = y.permute(0, 2, 3, 1)
+    return y if resid is None else y + resid.double()
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,ks,resid", [
+    (2, 16, 16, 64, 160, 3, False),      # 2 tiles per image, 8 x 16-pixel rows per box
+    (3, 16, 8, 32, 32, 3, True),         # M = 384: a pair tile with an absent second half (TMA zero fill past the batch)
+    (1, 64, 64, 320, 320, 3, True),      # two N tiles of 160
+    (2, 128, 128, 160, 160, 3, False),   # one box = one image row
+    (1, 256, 256, 160, 160, 3, True),    # two boxes per image row
+    (2, 32, 32, 640, 640, 3, False),     # K = 5760
+    (2, 64, 64, 320, 160, 1, False),     # 1x1 (nin_shortcut)
+    (1, 32, 32, 96, 256, 3, False),      # BN = 256
+])
+def test_f16x3_conv_vs_fp64(engine4, B, H, W, Cin, Cout, ks, resid):
+    torch.manual_seed(B * 1000 + H + Cin + Cout + ks)
+    assert ops.conv2d_f16_supported(H, W, Cin, Cout, ks)
+    x = torch.randn(B, H, W, Cin)
+    w = torch.randn(Cout, Cin, ks, ks) / math.sqrt(Cin * ks * ks)
+    b = torch.randn(Cout)
+    r = torch.randn(B, H, W, Cout) if resid else None
+    ref = _conv_ref(x, w, b, r)
+    wp = torch.empty(Cout, ks * ks * Cin, device=DEV)
+    ops.repack_conv_weight(g(w), wp)
+    x16, w16 = ops.F16Pair.from_tensor(g(x)), ops.F16Pair.from_tensor(wp)
+    out = torch.full((B, H, W, Cout), float("nan"), device=DEV)
+    n0 = ops.launch_count()
+    ops.conv2d(None, wp, g(b), out, B, H, W, Cin, Cout, ks, x16=x16, w16=w16, resid=None if r is None else g(r))
+    torch.cuda.synchronize()
+    assert ops.launch_count() - n0 == 1
+    assert not torch.isnan(out).any(), "some output elements were never written"
+    e4 = err(out.cpu(), ref)
+    # the SIMT engine on the same problem
+    out0 = torch.empty(B, H, W, Cout, device=DEV)
+    ops.conv2d(g(x), wp, g(b), out0, B, H, W, Cin, Cout, ks, resid=None if r is None else g(r), engine=0)
+    e0 = err(out0.cpu(), ref)
+    print(f"\n[f16x3-conv] B={B} {H}x{W} {Cin}->{Cout} ks={ks}: f16x3 err {e4:.3e}  SIMT err {e0:.3e}")
+    assert e4 < 1e-5
+    out_b = torch.full((B, H, W, Cout), float("nan"), device=DEV)
+    ops.conv2d(None, wp, g(b), out_b, B, H, W, Cin, Cout, ks, x16=x16, w16=w16, resid=None if r is None else g(r))
+    assert torch.equal(out, out_b), "f16x3 conv is not deterministic run to run"
+
+
+def test_f16x3_conv_unsupported_shapes_are_reported():
+    assert not ops.conv2d_f16_supported(80, 80, 160, 160, 3)       # 128 % 80 != 0 (truncated pyramids)
+    assert not ops.conv2d_f16_supported(64, 64, 16, 160, 3)        # Cin % 32
+    assert not ops.conv2d_f16_supported(64, 64, 160, 3, 3)         # the image conv stays on the SIMT engine
+    assert ops.conv2d_f16_supported(256, 256, 160, 160, 3)
+
+
+def test_affine_and_upsample_pair_producers():
+    torch.manual_seed(11)
+    B, H, W, Cn = 2, 8, 8, 64
+    x, a, b = g(torch.randn(B, H, W, Cn)), g(torch.rand(B, Cn) + 0.5), g(torch.randn(B, Cn))
+    y = torch.empty(B, H, W, Cn, device=DEV)
+    ops.affine_nc(x, a, b, y, B, H * W, Cn, silu=True)
+    p = ops.F16Pair.empty((B, H, W, Cn), DEV)
+    ops.affine_nc(x, a, b, None, B, H * W, Cn, silu=True, out16=p)
+    chk = ops.F16Pair.from_tensor(y)
+    assert torch.equal(chk.hi, p.hi) and torch.equal(chk.lo, p.lo)
+    up = ops.F16Pair.empty((B, 2 * H, 2 * W, Cn), DEV)
+    ops.upsample2x_split_f16(x, up, B, H, W, Cn)
+    ref = ops.F16Pair.from_tensor(x.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2).contiguous())
+    assert torch.equal(up.hi, ref.hi) and torch.equal(up.lo, ref.lo)
+
+
+def test_decoder_engine4_pixels_within_tolerance(engine4):
+    """VQVAE.fhat_to_img with the f16x3 convolutions against the CPU oracle: every pixel within the north-star bound."""
+    from controlvar_b200 import VQVAE, weights as Wt
+    from controlvar_b200.config import PathConfig
+    from oracle import controlvar_oracle as O
+    cfg = PathConfig(depth=2)
+    vae = VQVAE(vocab_size=cfg.vocab_size, z_channels=cfg.Cvae, ch=cfg.vae_ch, test_mode=True,
+                share_quant_resi=cfg.share_quant_resi, v_patch_nums=cfg.patch_nums)
+    vsd = Wt.synthetic_vae_state_dict(cfg, 0)
+    vae.load_state_dict(vsd, strict=True)
+    vae.to(DEV)
+    torch.manual_seed(2)
+    f_hat = torch.randn(1, cfg.Cvae, 16, 16) * 1.5
+    n0 = ops.launch_count()
+    img = vae.fhat_to_img(g(f_hat))
+    torch.cuda.synchronize()
+    ref = O.fhat_to_img(f_hat, vsd)
+    e = (img.cpu() - ref).abs().max().item()
+    print(f"\n[f16x3-decoder] max pixel err {e:.3e} (tc_min_hw={vae.tc_min_hw}), launches {ops.launch_count() - n0}")
+    assert e < 1e-4

@@ -240,7 +240,8 @@ def main_ours(args, wl):
     if rank == 0:
         clocks.start()
     ms_total, launches, prof = timed(step_device, args.steps, 1000, profile=True)
-    ms_e2e, _, _ = timed(step_e2e, args.steps, 2000)
+    # --profile-only (diagnostic, for ncu launch lists): skip the second, end-to-end pass; the line is then not a bench line
+    ms_e2e, _, _ = (ms_total, 0, None) if args.profile_only else timed(step_e2e, args.steps, 2000)
     clk = clocks.stop() if rank == 0 else None
     mem_gb = torch.cuda.max_memory_allocated() / 2**30
 
@@ -284,7 +285,7 @@ def main_ours(args, wl):
                    "sample": f"{args.cpu_sample_batch} image(s), one call of the same workload on the host cores; " + CPU_BATCH_NOTE}
         engine_name = {0: "simt-fp32", 1: "tcgen05-3xtf32 (1 CTA per tile)",
                        3: "tcgen05-3xtf32 (2-CTA all-TMA dense layers, 1-CTA convs)",
-                       4: "tcgen05 f16x3 dense layers (FP16 pairs, 2-CTA all-TMA) + 3xtf32 attention / convs"}.get(ops.get_gemm_engine(), "?")
+                       4: "tcgen05 f16x3 (FP16 pairs, 2-CTA all-TMA) dense layers and decoder convs; 3xtf32 attention"}.get(ops.get_gemm_engine(), "?")
         line = {"metric": f"images/sec (256x256, d{depth}, CFG=1.5)", "value": value, "unit": "images/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -297,6 +298,9 @@ def main_ours(args, wl):
                 "e2e": {"value": e2e_v, "unit": "images/s", "h2d_bytes_per_step": int(16 * B * world),
                         "d2h_bytes_per_step": int(B * 3 * 512 * 256 * 4 * world)},
                 "gpu_launches": launches, "roofline": roof, "kernels": kernels, "cpu_baseline": cpu, "clocks": clk}
+        if args.profile_only:
+            line["e2e"] = None
+            line["note"] = "--profile-only run: diagnostic, not a bench line"
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -310,12 +314,13 @@ if __name__ == "__main__":
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="d24_b64", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch of the workload")
-    ap.add_argument("--engine", type=int, default=int(os.environ.get("CVAR_GEMM_ENGINE", "3")),
+    ap.add_argument("--engine", type=int, default=int(os.environ.get("CVAR_GEMM_ENGINE", "4")),
                     help="0 SIMT fp32, 1 tcgen05 3xTF32 (1 CTA per tile), 3 = 1 plus the 2-CTA all-TMA kernel for dense layers, "
                          "4 = 3 with FP16-pair (f16x3) dense layers")
     ap.add_argument("--cpu-sample-batch", type=int, default=8,
                     help="images per CPU-reference step (bounded sample: ~20 s of CPU work at d24 on 16 cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-only", action="store_true", help="diagnostic: device pass only (for ncu launch lists)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

@@ -11,7 +11,7 @@ static std::atomic<long long> g_launches{0};
 static int initial_engine() {
   const char* e = getenv("CVAR_GEMM_ENGINE");
   if (e != nullptr && (e[0] == '0' || e[0] == '1' || e[0] == '3' || e[0] == '4') && e[1] == '\0') return e[0] - '0';
-  return 3;
+  return 4;
 }
 int g_gemm_engine = initial_engine();
 

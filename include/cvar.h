@@ -41,7 +41,7 @@ CVAR_API long long cvar_launch_count(void);
  *   4 = as 3 for TF32 operands; tells the HOST to hand the dense layers FP16-pair operands (A16_* / W16_*, see
  *       cvar_split_f16), which run on the same 2-CTA kernel with kind::f16 MMAs at twice the TF32 rate.  The library
  *       itself picks the FP16 path whenever a call carries A16_hi, under any engine other than 0.
- * Default: 3 (environment variable CVAR_GEMM_ENGINE = 0 | 1 | 3 | 4 overrides it at load).  Returns the previous value. */
+ * Default: 4 (environment variable CVAR_GEMM_ENGINE = 0 | 1 | 3 | 4 overrides it at load).  Returns the previous value. */
 CVAR_API int cvar_set_gemm_engine(int engine);
 CVAR_API int cvar_get_gemm_engine(void);
 /* K-block of the tcgen05 engine: 32 (128-byte swizzle, default) or 16 (64-byte swizzle, deeper pipeline). Returns the

@@ -44,7 +44,7 @@ def run(var, labels, conds, noise, rows=None):
 
 
 def test_permutation_invariance_d24_b64_default_engine():
-    assert ops.get_gemm_engine() == ops.ENGINE_TC_2CTA
+    assert ops.get_gemm_engine() == ops.ENGINE_TC_F16X3
     cfg, var = build(24)
     B = 64
     labels = (torch.arange(B, device=DEV) * 131 + 7) % 1000

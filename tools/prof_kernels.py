@@ -10,7 +10,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from controlvar_b200 import ops  # noqa: E402
 
 which = sys.argv[1] if len(sys.argv) > 1 else "all"
-engine = int(os.environ.get("CVAR_GEMM_ENGINE", "1"))
+engine = int(os.environ.get("CVAR_GEMM_ENGINE", "4"))
 ops.set_gemm_engine(engine)
 ops.set_tc_kblock(int(os.environ.get("CVAR_TC_BK", "32")))
 dev = "cuda"
@@ -32,10 +32,15 @@ def timed(fn, n=3):
 if which in ("gemm", "all"):
     M, N, K = 65536, 6144, 1536            # fc1 of d24 at the last scale (R*l = 128*512 rows)
     A = torch.randn(M, K, device=dev)
-    W = ops.SplitWeight(torch.randn(N, K, device=dev) / 40)
     b = torch.randn(N, device=dev)
-    out = torch.empty(M, N, device=dev)
-    ms = timed(lambda: ops.gemm(A, W, b, out, M, N, K, epilogue=ops.EPI_BIAS_GELU))
+    if engine == 4:      # FP16 pairs in, FP16 pair out: exactly what the sampler's fc1 call does
+        W = ops.SplitWeight(torch.randn(N, K, device=dev) / 40, f16=True)
+        A16, out = ops.F16Pair.from_tensor(A), ops.F16Pair.empty((M, N), dev)
+        ms = timed(lambda: ops.gemm(None, W, b, None, M, N, K, epilogue=ops.EPI_BIAS_GELU, A16=A16, out16=out))
+    else:
+        W = ops.SplitWeight(torch.randn(N, K, device=dev) / 40)
+        out = torch.empty(M, N, device=dev)
+        ms = timed(lambda: ops.gemm(A, W, b, out, M, N, K, epilogue=ops.EPI_BIAS_GELU))
     print(f"gemm fc1 M={M} N={N} K={K}: {ms:.3f} ms  {2.0 * M * N * K / ms / 1e9:.1f} TFLOP/s")
     del A, out
 
@@ -45,7 +50,11 @@ if which in ("conv", "all"):
     w = ops.SplitWeight(torch.randn(C, 9 * C, device=dev) / 38)
     b = torch.randn(C, device=dev)
     out = torch.empty(B, H, H, C, device=dev)
-    ms = timed(lambda: ops.conv2d(x, w, b, out, B, H, H, C, C, 3))
+    if engine == 4:
+        x16, w16 = ops.F16Pair.from_tensor(x), ops.F16Pair.from_tensor(w.w)
+        ms = timed(lambda: ops.conv2d(None, w, b, out, B, H, H, C, C, 3, x16=x16, w16=w16))
+    else:
+        ms = timed(lambda: ops.conv2d(x, w, b, out, B, H, H, C, C, 3))
     print(f"conv3x3 B={B} {H}x{H} {C}->{C}: {ms:.3f} ms  {2.0 * B * H * H * C * 9 * C / ms / 1e9:.1f} TFLOP/s")
     del x, out
 

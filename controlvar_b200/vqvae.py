@@ -62,10 +62,11 @@ class VQVAE(nn.Module):
         q.vocab_size, q.Cvae, q.v_patch_nums, q.share_quant_resi = vocab_size, z_channels, tuple(v_patch_nums), share_quant_resi
         self._plan = decoder_plan(self.cfg)
         # Decoder convolutions whose output side is below this run on the SIMT fp32 engine.  Measured on B200
-        # (profiles/r01_decoder_policy.md): with every conv on tensor cores the worst pixel is 2.2e-4 off the fp32
-        # oracle (north-star bound: 1e-4); the 16x16 / 32x32 layers (K up to 5760, few pixels) cause most of that and
-        # cost almost nothing, so they stay in exact fp32: worst pixel 5.9e-5 for +50 ms per 64-image decode.
-        self.tc_min_hw = 64
+        # (profiles/r01_decoder_policy.md, engine 4 = f16x3): with every conv on tensor cores the worst pixel over 32
+        # realistic images is 9.0e-5 off the fp32 oracle (1.09e-4 on another 4: over the north-star bound of 1e-4); the
+        # 16x16 layers (K = 5760, few pixels) cause most of that and cost little, so they stay in exact fp32:
+        # worst pixel 7.1e-5, 146 ms per 64-image decode (all on tensor cores: 115 ms; >= 64 only: 180 ms, 4.3e-5).
+        self.tc_min_hw = 32
         self._packed: Dict[str, torch.Tensor] = {}
         self._packed16: Dict[str, "ops.F16Pair"] = {}
         self._ws: Dict[Tuple, torch.Tensor] = {}

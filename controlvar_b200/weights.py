@@ -290,3 +290,14 @@ def _synthetic_vae_state_dict(cfg: PathConfig, seed: int, with_encoder: bool) ->
         else:
             raise KeyError(key)
     return sd
+
+
+def synthetic_image(B: int, side: int = 256, seed: int = 0, device=None) -> torch.Tensor:
+    """(B, 3, side, side) fp32 image in [-1, 1] with structure at two scales (8x8 blocks + pixel noise), from the same
+    integer hash as the weights: identical bits in the build container (golden generation) and on the GPU box."""
+    assert side % 8 == 0
+    s8 = side // 8
+    coarse = hash_uniform(B * 3 * s8 * s8, seed, 0x1ACE, device).reshape(B, 3, s8, s8)
+    coarse = coarse.repeat_interleave(8, dim=2).repeat_interleave(8, dim=3)
+    fine = hash_uniform(B * 3 * side * side, seed, 0xF19E, device).reshape(B, 3, side, side)
+    return (coarse * 0.75 + fine * 0.25).contiguous()

@@ -2,7 +2,8 @@
 
 CPU (fp32, PyTorch/ATen) restatement of the reference algorithm for the next-scale sampling hot path of
 lxa9867/ControlVAR: ``ControlVAR.autoregressive_infer_cfg`` (released branch: multi_cond=True, mask_factor=2)
-and ``VQVAE.fhat_to_img``.  It is written functionally over a ``state_dict`` (no nn.Module, no reference
+and ``VQVAE.fhat_to_img``, plus the pixel-conditioned caller of the same path:
+``ControlVAR.conditional_infer_cfg`` and ``VQVAE.img_to_idxBl`` (encoder + multi-scale residual quantiser).  It is written functionally over a ``state_dict`` (no nn.Module, no reference
 import) so that it can travel to the GPU box, where /root/reference does not exist.
 
 Parity pinning: the reference ships NO tests / golden vectors for this path, so the
@@ -241,6 +242,43 @@ def fhat_to_img(f_hat: Tensor, vsd: Dict[str, Tensor]) -> Tensor:
     return decoder_forward(_conv(f_hat, vsd, "post_quant_conv", 1), vsd).clamp_(-1, 1)
 
 
+# --------------------------------------------------------------------------------------- encoder (f-1)
+def encoder_forward(x: Tensor, vsd: Dict[str, Tensor], num_resolutions: int = 5, num_res_blocks: int = 2) -> Tensor:
+    """Encoder.forward - models/vae_modules.py:145-160; Downsample2x = zero pad (right, bottom) + stride-2 conv, :37."""
+    h = _conv(x, vsd, "encoder.conv_in", 1)
+    for lvl in range(num_resolutions):
+        for ib in range(num_res_blocks):
+            h = resnet_block(h, vsd, f"encoder.down.{lvl}.block.{ib}.")
+            if f"encoder.down.{lvl}.attn.{ib}.norm.weight" in vsd:
+                h = attn_block(h, vsd, f"encoder.down.{lvl}.attn.{ib}.")
+        if lvl != num_resolutions - 1:
+            p = f"encoder.down.{lvl}.downsample.conv"
+            h = F.conv2d(F.pad(h, pad=(0, 1, 0, 1), mode="constant", value=0), vsd[p + ".weight"], vsd[p + ".bias"],
+                         stride=2, padding=0)
+    h = resnet_block(h, vsd, "encoder.mid.block_1.")
+    h = attn_block(h, vsd, "encoder.mid.attn_1.")
+    h = resnet_block(h, vsd, "encoder.mid.block_2.")
+    return _conv(F.silu(_gn(h, vsd, "encoder.norm_out"), inplace=True), vsd, "encoder.conv_out", 1)
+
+
+def img_to_f(img: Tensor, vsd: Dict[str, Tensor]) -> Tensor:
+    """quant_conv(encoder(img)) - models/vqvae.py:74."""
+    return _conv(encoder_forward(img, vsd), vsd, "quant_conv", 1)
+
+
+def img_to_idxBl(img: Tensor, vsd: Dict[str, Tensor], patch_nums: Sequence[int]) -> List[Tensor]:
+    """VQVAE.img_to_idxBl - models/vqvae.py:73-75."""
+    return f_to_idxBl(img_to_f(img, vsd), patch_nums, vsd)
+
+
+def vq_nearest_margin(z_NC: Tensor, emb: Tensor) -> Tensor:
+    """Test helper: gap between the two smallest code distances of every latent vector (ambiguous argmins)."""
+    d = torch.sum(z_NC.square(), dim=1, keepdim=True) + torch.sum(emb.square(), dim=1, keepdim=False)
+    d.addmm_(z_NC, emb.T, alpha=-2, beta=1)
+    two = d.topk(2, dim=1, largest=False)[0]
+    return two[:, 1] - two[:, 0]
+
+
 # ----------------------------------------------------------------------------------- the sampler (a-1)
 @torch.no_grad()
 def autoregressive_infer_cfg(
@@ -328,6 +366,103 @@ def autoregressive_infer_cfg(
         img1 = fhat_to_img(f_hat_1, vsd).add_(1).mul_(0.5)                    # :563
         img2 = fhat_to_img(f_hat_2, vsd).add_(1).mul_(0.5)                    # :564
         out["img"] = torch.concat([img1, img2], dim=2)                        # :565
+    return out
+
+
+def cfg_combine4(logits_4BlV: Tensor, B: int, t1: float, t2: float, t3: float) -> Tensor:
+    """The four-way guidance mix of conditional_infer_cfg - models/control_var.py:295-298."""
+    return (1 + t1) * logits_4BlV[:B] \
+        + (t2 - t1) * logits_4BlV[B:2 * B] \
+        + (t3 - t2) * logits_4BlV[2 * B:3 * B] \
+        - t3 * logits_4BlV[-B:]
+
+
+@torch.no_grad()
+def conditional_infer_cfg(
+    sd: Dict[str, Tensor], vsd: Dict[str, Tensor], patch_nums: Sequence[int], depth: int,
+    B: int, label_B: Tensor, cond_type: Tensor, cfg: Sequence[float], top_k: int, top_p: float,
+    noise: Callable[[int, int, int], Tensor], c_mask: Optional[List[Tensor]] = None,
+    c_img: Optional[List[Tensor]] = None, decode: bool = True, trace: Optional[dict] = None,
+    embed_dim: int = 0, num_heads: int = 0,
+) -> Dict[str, object]:
+    """ControlVAR.conditional_infer_cfg - models/control_var.py:223-354 (pixel-level control: the condition map's
+    and / or the image's tokens are teacher-forced into three of four guidance replicas).
+
+    Rows are [class+type | type only | nothing | nothing] x B (label_B cat at :256, cond_type cat at :263), the
+    mixed logits are repeated 4x and every replica row draws its own sample (:306-307; ``noise(si, 4*B*l, V)``).
+    """
+    C = embed_dim or 64 * depth
+    H = num_heads or depth
+    cos_attn = depth == 30
+    scale = 1.0 if cos_attn else 1 / math.sqrt(C // H) / 4
+    SN = len(patch_nums)
+    emb = vsd["quantize.embedding.weight"]
+    V, Cvae = emb.shape
+    num_classes = sd["class_emb.weight"].shape[0] - 1
+    first_l = 2 * patch_nums[0] ** 2
+    HW = patch_nums[-1]
+
+    lvl_pos = F.embedding(sd["lvl_1L"], sd["lvl_embed.weight"]) + sd["pos_1LC"]             # :245
+    label_B = label_B.long()
+    empty_cls = torch.full_like(label_B, num_classes)                                       # :252
+    label_4B = torch.cat((label_B, empty_cls, empty_cls, empty_cls), dim=0)                  # :256
+    sos = cond_BD = F.embedding(label_4B, sd["class_emb.weight"])                           # :257
+    empty_ct = torch.full((B,), 4).long()                                                   # :259
+    ct = torch.concat([cond_type.long(), cond_type.long(), empty_ct, empty_ct], dim=0)      # :263
+    sos = sos.unsqueeze(1)
+    cond_token = F.embedding(ct, sd["cond_embed.weight"]).unsqueeze(1)                      # :265
+    next_token_map = torch.concat([cond_token, sos], dim=1)                                 # :266
+    rep = label_4B.shape[0] // B                                                            # :268 (always 4)
+    next_token_map = next_token_map + sd["pos_start"].expand(rep * B, first_l, -1) + lvl_pos[:, :first_l]   # :269
+
+    caches = [dict() for _ in range(depth)]
+    cur_L = 0
+    f_hat = sos.new_zeros(rep * B, Cvae, HW * 2, HW)                                        # :275
+    idx_all: List[Tensor] = []
+    for si, pn in enumerate(patch_nums):                                                    # :276
+        ratio = si / (SN - 1)
+        cur_L += pn * pn * 2
+        x = next_token_map
+        for bi in range(depth):                                                             # :282-284 (bias slice is all zeros)
+            x = adaln_block(x, cond_BD, sd, f"blocks.{bi}.", H, caches[bi], cos_attn, scale)
+        logits = get_logits(x, cond_BD, sd)                                                 # :285
+        t1, t2, t3 = cfg[0] * ratio, cfg[1] * ratio, cfg[2] * ratio                         # :288
+        logits = cfg_combine4(logits, B, t1, t2, t3)                                        # :295-298
+        if trace is not None:
+            trace.setdefault("logits_cfg", []).append(logits.clone())
+        logits = logits.repeat(rep, 1, 1)                                                   # :306
+        q = noise(si, rep * B * logits.shape[1], V)
+        idx_Bl = sample_with_top_k_top_p_(logits, top_k, top_p, q)                          # :307
+        if trace is not None:
+            trace.setdefault("logits_masked", []).append(logits.clone())
+            trace.setdefault("q", []).append(q)
+            trace.setdefault("idx_sampled", []).append(idx_Bl.clone())
+        if c_mask is not None:                                                              # :309-313
+            for g in range(3):
+                idx_Bl[g * B:(g + 1) * B, :pn * pn] = c_mask[si]
+        if c_img is not None:                                                               # :317-321
+            for g in range(3):
+                idx_Bl[g * B:(g + 1) * B, pn * pn:] = c_img[si]
+        idx_all.append(idx_Bl.clone())
+        h_BChw = F.embedding(idx_Bl, emb).transpose_(1, 2)                                  # :327, :334
+        h1 = h_BChw[:, :, :pn * pn].reshape(rep * B, Cvae, pn, pn)
+        h2 = h_BChw[:, :, -pn * pn:].reshape(rep * B, Cvae, pn, pn)
+        f_hat_1 = f_hat[:, :, :HW, :]
+        f_hat_2 = f_hat[:, :, HW:, :]
+        f_hat_1, ntm1 = get_next_autoregressive_input(si, patch_nums, f_hat_1, h1, vsd)     # :339
+        f_hat_2, ntm2 = get_next_autoregressive_input(si, patch_nums, f_hat_2, h2, vsd)     # :340
+        f_hat = torch.concat((f_hat_1, f_hat_2), dim=2)                                     # :341
+        ntm1 = ntm1.view(rep * B, Cvae, -1).transpose(1, 2)                                 # :342
+        ntm2 = ntm2.view(rep * B, Cvae, -1).transpose(1, 2)
+        next_token_map = torch.concat((ntm1, ntm2), dim=1)                                  # :344
+        next_token_map = F.linear(next_token_map, sd["word_embed.weight"], sd["word_embed.bias"])   # :345
+        if si != SN - 1:
+            next_token_map = next_token_map + lvl_pos[:, cur_L:cur_L + patch_nums[si + 1] ** 2 * 2]    # :347
+    out: Dict[str, object] = {"idx": idx_all, "f_hat": f_hat}
+    if decode:
+        img1 = fhat_to_img(f_hat_1[:B], vsd).add_(1).mul_(0.5)                              # :349-352
+        img2 = fhat_to_img(f_hat_2[:B], vsd).add_(1).mul_(0.5)
+        out["img"] = torch.concat([img1, img2], dim=2)                                      # :354
     return out
 
 

@@ -11,8 +11,14 @@ from controlvar_b200.config import PathConfig
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-def golden_names():
-    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+def _kind(name):
+    return "enc" if name.startswith("enc_") else "cond" if name.startswith("cond_") else "sample"
+
+
+def golden_names(kind="sample"):
+    """kind: 'sample' (autoregressive_infer_cfg), 'cond' (conditional_infer_cfg), 'enc' (img_to_idxBl)."""
+    names = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    return [n for n in names if _kind(n) == kind]
 
 
 def load_golden(name):
@@ -21,6 +27,12 @@ def load_golden(name):
     cfg = PathConfig(depth=meta["depth"], patch_nums=tuple(meta["patch_nums"]), embed_dim=meta.get("embed_dim", 0),
                      heads=meta.get("heads", 0))
     idx = [torch.from_numpy(z[f"idx_{si}"].astype(np.int64)) for si in range(len(cfg.patch_nums))]
+    if meta.get("kind") == "enc":
+        return dict(meta=meta, cfg=cfg, idx=idx, f=torch.from_numpy(z["f"]))
+    if meta.get("kind") == "cond":
+        forced = [torch.from_numpy(z[f"forced_{si}"].astype(np.int64)) for si in range(len(cfg.patch_nums))]
+        return dict(meta=meta, cfg=cfg, idx=idx, forced=forced, f_hat=torch.from_numpy(z["f_hat"]),
+                    img_sub=torch.from_numpy(z["img_sub"]))
     return dict(meta=meta, cfg=cfg, idx=idx, f_hat=torch.from_numpy(z["f_hat"]),
                 img_sub=torch.from_numpy(z["img_sub"]), img_mean=float(z["img_mean"][0]),
                 logits_row=torch.from_numpy(z["logits_cfg_last_row0"]))

@@ -31,6 +31,39 @@ def test_oracle_matches_reference_golden(name):
     assert (out["f_hat"] - g["f_hat"]).abs().max().item() <= 1e-6
 
 
+@pytest.mark.parametrize("name", golden_names("enc"))
+def test_oracle_img_to_idxBl_matches_reference_golden(name):
+    """VQVAE.img_to_idxBl (vqvae.py:73-75, quant.py:184-215): encoder output and the tokens of every scale."""
+    g = load_golden(name)
+    m, cfg = g["meta"], g["cfg"]
+    vsd = W.synthetic_vae_state_dict(cfg, m["weight_seed"])
+    img = W.synthetic_image(m["B"], cfg.img_hw, m["img_seed"])
+    f = O.img_to_f(img, vsd)
+    assert (f - g["f"]).abs().max().item() <= 1e-6
+    # tokens from the golden's own f: independent of sub-ulp differences of the encoder across CPU ISAs
+    for si, (a, b) in enumerate(zip(g["idx"], O.f_to_idxBl(g["f"], cfg.patch_nums, vsd))):
+        assert torch.equal(a, b), f"tokens differ at scale {si}"
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names("cond") if "pn10" not in n])
+def test_oracle_conditional_infer_matches_reference_golden(name):
+    """ControlVAR.conditional_infer_cfg (control_var.py:223-354) with the golden's teacher-forced tokens."""
+    g = load_golden(name)
+    m, cfg = g["meta"], g["cfg"]
+    sd = W.synthetic_var_state_dict(cfg, m["weight_seed"])
+    vsd = W.synthetic_vae_state_dict(cfg, m["weight_seed"], with_encoder=False)
+    out = O.conditional_infer_cfg(sd, vsd, cfg.patch_nums, cfg.depth, m["B"], torch.tensor(m["labels"]),
+                                  torch.tensor(m["cond"]), m["cfg"], m["top_k"], m["top_p"],
+                                  O.cpu_generator_noise(m["seed"]), c_mask=g["forced"] if m["c_mask"] else None,
+                                  c_img=g["forced"] if m["c_img"] else None)
+    for si, (a, b) in enumerate(zip(g["idx"], out["idx"])):
+        assert torch.equal(a, b), f"tokens differ at scale {si}"
+    sub = m["img_sub"]
+    assert list(out["img"].shape) == m["img_shape"]
+    assert (out["img"][:, :, ::sub, ::sub] - g["img_sub"]).abs().max().item() <= 1e-6
+    assert (out["f_hat"][:m["B"]] - g["f_hat"]).abs().max().item() <= 1e-6
+
+
 def test_multinomial_identity():
     """torch.multinomial(p, 1, replacement=True, generator=g) == argmax(p / Exp(1) drawn from g) (helpers.py:19)."""
     g1, g2 = torch.Generator(), torch.Generator()

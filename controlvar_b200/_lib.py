@@ -46,6 +46,7 @@ class ConvArgs(C.Structure):
         ("out_mode", C.c_int), ("out_rows_total", C.c_int), ("row_offset", C.c_int),
         ("engine", C.c_int),
         ("x16_hi", C.c_void_p), ("x16_lo", C.c_void_p), ("w16_hi", C.c_void_p), ("w16_lo", C.c_void_p),
+        ("downsample2x", C.c_int),
     ]
 
 
@@ -61,6 +62,7 @@ PROTOTYPES = {
     "cvar_debug_set_attn_trace": (C.c_int, [C.c_void_p]),
     "cvar_lvl_pos": (C.c_int, [c_f, c_f, c_f, c_f, C.c_int, C.c_int, C.c_void_p]),
     "cvar_prologue": (C.c_int, [c_f, c_f, c_f, c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, c_f, c_f, c_f, C.c_void_p]),
+    "cvar_prologue_rows": (C.c_int, [c_f, c_f, c_f, c_f, c_f, c_f, C.c_int, C.c_int, c_f, c_f, c_f, C.c_void_p]),
     "cvar_ln_modulate": (C.c_int, [c_f, c_f, c_f, c_ll, c_f, c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
     "cvar_gemm": (C.c_int, [C.POINTER(GemmArgs), C.c_void_p]),
     "cvar_qkv_project": (C.c_int, [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f,
@@ -72,6 +74,13 @@ PROTOTYPES = {
                                     C.c_float, C.c_int, C.c_void_p]),
     "cvar_cfg_sample": (C.c_int, [c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_double,
                                   C.c_void_p]),
+    "cvar_cfg_sample_multi": (C.c_int, [c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int,
+                                        C.c_int, C.c_double, c_f, c_f, C.c_int, C.c_void_p]),
+    "cvar_vq_step_ex": (C.c_int, [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, C.c_int, C.c_int, C.c_int,
+                                  C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "cvar_area_pool_nc": (C.c_int, [c_f, c_f, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "cvar_nchw_to_nhwc_pad": (C.c_int, [c_f, c_f, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "cvar_repack_conv_weight_pad": (C.c_int, [c_f, c_f, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "cvar_vq_step": (C.c_int, [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, C.c_int,
                                C.c_int, C.c_int, C.c_void_p]),
     "cvar_vq_nearest": (C.c_int, [c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, C.c_void_p]),

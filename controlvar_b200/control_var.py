@@ -4,12 +4,15 @@ Same constructor arguments, ``state_dict`` keys and ``autoregressive_infer_cfg``
 /root/reference/models/control_var.py:23-67, 356-565, so it drops in for inference.
 The Python here only sequences kernel launches of libcvar_sm100.so and owns the device memory:
 
-  prologue                         cvar_lvl_pos, cvar_prologue                  control_var.py:381-409
+  prologue                         cvar_lvl_pos, cvar_prologue_rows             control_var.py:381-409
   per block, per scale             cvar_ln_modulate, cvar_qkv_project, cvar_attn_kvcache, cvar_gemm x3
                                                                                  basic_var.py:203-210, 89-119, 43-51
   head + CFG + sampling            cvar_ln_modulate, cvar_gemm, cvar_cfg_sample  control_var.py:499-505, helpers.py:6-19
   VQ step                          cvar_vq_step                                  control_var.py:512-560, quant.py:243-270
   decode (both streams, one pass)  VQVAE._fhat_to_img -> cvar_conv2d / cvar_gn_stats / ...   control_var.py:563-565
+
+``conditional_infer_cfg`` (control_var.py:223-354) runs the same loop on four guidance
+replicas with ``cvar_cfg_sample_multi`` (4-way mix, one draw per replica row, teacher-forced tokens).
 
 Differences from the reference that do not change results: ``ada_lin`` (constant across scales) is evaluated once
 per call instead of once per block per scale; the KV cache is a pre-allocated arena written in place instead of
@@ -21,6 +24,7 @@ from __future__ import annotations
 
 import math
 import random
+import struct
 from typing import Dict, List, Optional, Tuple, Union
 
 import torch
@@ -29,18 +33,15 @@ import torch.nn.functional as F
 
 from . import ops
 from .config import PathConfig, DEFAULT_PATCH_NUMS
-from .vqvae import VQVAE, register_tree
+from .vqvae import VQVAE, bicubic_matrix, register_tree
 from .weights import attn_bias_for_masking, lvl_1L, var_key_shapes
 
 _BUFFERS = ("lvl_1L", "attn_bias_for_masking", "zero_k_bias")
 
 
-def bicubic_matrix(n_in: int, n_out: int) -> torch.Tensor:
-    """(n_out, n_in) matrix U of F.interpolate(mode='bicubic', align_corners=False) along one axis, read off impulse
-    responses so that the coefficients (A = -0.75, border clamping) are exactly ATen's.  Host-side constant."""
-    eye = torch.eye(n_in, dtype=torch.float32).view(n_in, 1, 1, n_in)          # one impulse per batch entry
-    out = F.interpolate(eye, size=(1, n_out), mode="bicubic")                  # height 1 -> 1 is the identity
-    return out[:, 0, 0, :].t().contiguous()                                    # U[X, j]
+def _f32(v: float) -> float:
+    """A python double rounded to fp32 (what a python scalar becomes when it multiplies an fp32 tensor)."""
+    return struct.unpack("f", struct.pack("f", v))[0]
 
 
 class ControlVAR(nn.Module):
@@ -249,10 +250,71 @@ class ControlVAR(nn.Module):
             cond_type = torch.zeros(B, dtype=torch.long, device=dev)
         assert label_B.shape == (B,) and cond_type.shape == (B,)
 
+        label_R = torch.cat((label_B, torch.full_like(label_B, self.num_classes)))         # control_var.py:381
+        cond_R = torch.cat((cond_type, torch.full_like(cond_type, 4)))                     # control_var.py:399-400
+        return self._sample(B, label_R, cond_R, groups=2, mix=lambda ratio: (cfg * ratio,), replicas=1,
+                            top_k=top_k, top_p=top_p, rng=rng)
+
+    @torch.no_grad()
+    def conditional_infer_cfg(
+        self, B: int, label_B: Optional[Union[int, torch.LongTensor]],
+        g_seed: Optional[int] = None, cfg=(1.5, 1.5, 1.5), top_k=0, top_p=0.0,
+        more_smooth=False, cond_type=None, c_mask=None, c_img=None,
+    ) -> torch.Tensor:   # (B, 3, 2*H, W) in [0, 1]
+        """Drop-in for ControlVAR.conditional_infer_cfg (control_var.py:223-354): pixel-level control.  Four guidance
+        replicas [class + type | type | none | none] of every sample run side by side (4B rows); c_mask / c_img
+        (List[(B, pn*pn)] from VQVAE.img_to_idxBl) teacher-force the control / image tokens of the first three; the
+        image is decoded from the first replica."""
+        if more_smooth:
+            raise NotImplementedError("more_smooth (Gumbel-softmax visualisation path) is not implemented")
+        if not self.multi_cond:
+            raise NotImplementedError("conditional_infer_cfg needs multi_cond=True (it reads cond_embed, control_var.py:265)")
+        if not self.pos_1LC.is_cuda:
+            raise RuntimeError("controlvar_b200.ControlVAR runs on CUDA only (no CPU fallback); call .cuda() first")
+        dev = self.device
+        rng = self._generator(g_seed)
+        rng_dev = "cpu" if self.rng_device == "cpu" else dev
+        if label_B is None:
+            sel = torch.full((1, self.num_classes), 1 / self.num_classes, dtype=torch.float32, device=rng_dev)
+            label_B = torch.multinomial(sel, num_samples=B, replacement=True, generator=rng).reshape(B)
+        elif isinstance(label_B, int):
+            label_B = torch.full((B,), self.num_classes if label_B < 0 else label_B)
+        if cond_type is None:
+            raise TypeError("conditional_infer_cfg: cond_type must be given (the reference concatenates it, control_var.py:263)")
+        if isinstance(cond_type, int):
+            cond_type = torch.full((B,), cond_type)
+        label_B = label_B.to(device=dev, dtype=torch.long).contiguous()
+        cond_type = cond_type.to(device=dev, dtype=torch.long).contiguous()
+        assert label_B.shape == (B,) and cond_type.shape == (B,)
+        cfg = tuple(float(c) for c in cfg)
+        assert len(cfg) == 3
+        empty_cls = torch.full_like(label_B, self.num_classes)                             # control_var.py:252
+        empty_ct = torch.full_like(cond_type, 4)                                           # control_var.py:259
+        label_R = torch.cat((label_B, empty_cls, empty_cls, empty_cls))                    # control_var.py:256
+        cond_R = torch.cat((cond_type, cond_type, empty_ct, empty_ct))                     # control_var.py:263
+
+        def forced(lst):
+            if lst is None:
+                return None
+            assert len(lst) == len(self.patch_nums)
+            return [t.to(device=dev, dtype=torch.int64).contiguous() for t in lst]
+
+        return self._sample(B, label_R, cond_R, groups=4,
+                            mix=lambda ratio: (cfg[0] * ratio, cfg[1] * ratio, cfg[2] * ratio), replicas=4,
+                            top_k=top_k, top_p=top_p, rng=rng, c_mask=forced(c_mask), c_img=forced(c_img))
+
+    # ------------------------------------------------------------------------------------ the shared scale loop
+    def _sample(self, B: int, label_R: torch.Tensor, cond_R: torch.Tensor, *, groups: int, mix, replicas: int, top_k, top_p,
+                rng, c_mask=None, c_img=None) -> torch.Tensor:
+        """The 10-scale loop both entry points share.  groups: guidance row groups in the transformer batch (R = groups*B
+        rows).  replicas = 1: autoregressive_infer_cfg - one f_hat per sample, the next map is written to both CFG halves.
+        replicas = groups = 4: conditional_infer_cfg - every replica row keeps its own samples and f_hat."""
+        dev = self.device
         cst = self._constants()
         vae = self.vae_proxy[0]
         C, H, depth, V, Cvae = self.C, self.num_heads, self.depth, self.V, self.Cvae
-        R, T, hw = 2 * B, self.L, self.patch_nums[-1]
+        R, T, hw = groups * B, self.L, self.patch_nums[-1]
+        Bf = B * replicas                                   # samples that own an f_hat / a token row
         SN = len(self.patch_nums)
         lens = self.cfg.scale_lens
         lmax = max(lens)
@@ -280,15 +342,15 @@ class ControlVAR(nn.Module):
         attn_o_lo = self._buf("attn_o_lo", (R * lmax, C)) if split else None
         hid_lo = self._buf("hid_lo", (R * lmax, 4 * C)) if split else None
         logits = self._buf("logits", (R * lmax, V))
-        idx = self._buf("idx", (B * lmax,), torch.int64)
+        idx = self._buf("idx", (Bf * lmax,), torch.int64)
         caches = self._kv_caches(depth, R, H, T)
-        f_hat = self._buf("f_hat", (B, Cvae, 2 * hw, hw))
+        f_hat = self._buf("f_hat", (Bf, Cvae, 2 * hw, hw))
         f_hat.zero_()
 
         # ---- prologue
-        ops.prologue(self.get_parameter("class_emb.weight"),
-                     self.get_parameter("cond_embed.weight") if self.multi_cond else None, self.pos_start,
-                     lvl_pos, label_B, cond_type, self.num_classes, cond_BD, silu_cond, x)
+        ops.prologue_rows(self.get_parameter("class_emb.weight"),
+                          self.get_parameter("cond_embed.weight") if self.multi_cond else None, self.pos_start,
+                          lvl_pos, label_R, cond_R, cond_BD, silu_cond, x)
         silu16 = ops.F16Pair.from_tensor(silu_cond, out=self._pair("silu16", (R, C))) if f16 else None
         for bi, blk in enumerate(cst["blocks"]):       # ada_lin = Linear(SiLU(cond)): constant across scales
             ops.gemm(silu_cond, blk["ada_w"], blk["ada_b"], ada[bi], R, 6 * C, C, A16=silu16)
@@ -320,32 +382,41 @@ class ControlVAR(nn.Module):
             ops.ln_modulate(x, ada_head[:, :C], ada_head[:, C:], 2 * C, xn, M, C, l, self.norm_eps, out_lo=xn_lo,
                             out16=xn16)
             ops.gemm(xn, cst["head_w"], self.get_parameter("head.bias"), logits, M, V, C, A_lo=xn_lo, A16=xn16)
-            # CFG + top-k/top-p + multinomial
-            t = cfg * (si / self.num_stages_minus_1)
+            # guidance mix + top-k/top-p + multinomial
+            ts = mix(si / self.num_stages_minus_1)
             if self.debug_noise_fn is not None:
-                q_noise = self.debug_noise_fn(si, B * l, V).to(device=dev, dtype=torch.float32).contiguous()
-                assert q_noise.shape == (B * l, V)
+                q_noise = self.debug_noise_fn(si, Bf * l, V).to(device=dev, dtype=torch.float32).contiguous()
+                assert q_noise.shape == (Bf * l, V)
             else:
-                q_noise = self._noise(B * l, V, rng)
+                q_noise = self._noise(Bf * l, V, rng)
             if self.debug_capture_logits:
                 self.last_logits.append(logits[:M].view(R, l, V).clone())
-            ops.cfg_sample(logits, q_noise, idx, B, l, V, t, top_k, top_p)
-            self.last_idx.append(idx[:B * l].view(B, l).clone())
+            if groups == 2:
+                ops.cfg_sample(logits, q_noise, idx, B, l, V, ts[0], top_k, top_p)
+            else:
+                # (1 + t1)*L0 + (t2 - t1)*L1 + (t3 - t2)*L2 - t3*L3: python forms the scalars in double precision and
+                # they meet the fp32 tensors as fp32 values (control_var.py:288-298)
+                t1, t2, t3 = ts
+                coef = (_f32(1 + t1), _f32(t2 - t1), _f32(t3 - t2), -_f32(t3))
+                ops.cfg_sample_multi(logits, q_noise, idx, B, l, V, coef, replicas, top_k, top_p,
+                                     forced_first=None if c_mask is None else c_mask[si],
+                                     forced_second=None if c_img is None else c_img[si], forced_replicas=3)
+            self.last_idx.append(idx[:Bf * l].view(Bf, l).clone())
             if self.debug_forced_idx is not None:
-                idx[:B * l].copy_(self.debug_forced_idx[si].to(device=dev, dtype=torch.int64).reshape(-1))
+                idx[:Bf * l].copy_(self.debug_forced_idx[si].to(device=dev, dtype=torch.int64).reshape(-1))
             # VQ step + next-scale input
             phi_w, phi_b = cst["phi"][self.cfg.phi_index(si)]
             pn_next = self.patch_nums[si + 1] if si != SN - 1 else 0
             ops.vq_step(idx, cst["codebook"], cst["U"].get(pn), phi_w, phi_b,
                         self.get_parameter("word_embed.weight"), self.get_parameter("word_embed.bias"),
                         lvl_pos[cur_L:] if pn_next else None, f_hat, x if pn_next else None,
-                        B, pn, pn_next, hw, Cvae, C)
+                        Bf, pn, pn_next, hw, Cvae, C, streams=2, x_replicas=(2 if replicas == 1 else 1))
 
-        # ---- decode both halves (control rows on top, image rows below): control_var.py:563-565
+        # ---- decode both halves (control rows on top, image rows below): control_var.py:563-565 / 349-354
         side = hw * vae.downsample
         img = torch.empty(B, 3, 2 * side, side, device=dev, dtype=torch.float32)
-        vae._fhat_to_img(f_hat[:, :, :hw, :], out=img, rows_total=2 * side, row_offset=0, out_mode=1)
-        vae._fhat_to_img(f_hat[:, :, hw:, :], out=img, rows_total=2 * side, row_offset=side, out_mode=1)
+        vae._fhat_to_img(f_hat[:B, :, :hw, :], out=img, rows_total=2 * side, row_offset=0, out_mode=1)
+        vae._fhat_to_img(f_hat[:B, :, hw:, :], out=img, rows_total=2 * side, row_offset=side, out_mode=1)
         self.last_f_hat = f_hat
         return img
 

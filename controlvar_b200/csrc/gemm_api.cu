@@ -150,7 +150,10 @@ extern "C" int cvar_conv2d(const cvar_conv_args* a, void* stream) {
   CVAR_REQUIRE(a != nullptr, "cvar_conv2d: null args");
   CVAR_REQUIRE(a->ks == 1 || a->ks == 3, "cvar_conv2d: ks must be 1 or 3");
   CVAR_REQUIRE(a->Cin % 16 == 0, "cvar_conv2d: Cin must be a multiple of 16 (got %d)", a->Cin);
-  CVAR_REQUIRE(a->out_mode >= 0 && a->out_mode <= 2, "cvar_conv2d: bad out_mode");
+  CVAR_REQUIRE(a->out_mode >= 0 && a->out_mode <= 3, "cvar_conv2d: bad out_mode");
+  CVAR_REQUIRE(!a->downsample2x || (a->ks == 3 && !a->upsample2x && a->Hin % 2 == 0 && a->Win % 2 == 0 &&
+                                    a->x16_hi == nullptr && a->in_a == nullptr),
+               "cvar_conv2d: downsample2x needs ks = 3, even Hin / Win, fp32 input, no upsampling / fused input transform");
   CVAR_REQUIRE(a->out_mode == 0 || a->resid == nullptr, "cvar_conv2d: image output takes no residual");
   CVAR_REQUIRE((a->in_a == nullptr) == (a->in_b == nullptr), "cvar_conv2d: in_a/in_b must come together");
   cudaStream_t s = (cudaStream_t)stream;
@@ -164,14 +167,15 @@ extern "C" int cvar_conv2d(const cvar_conv_args* a, void* stream) {
     if (took < 0) return took;
     if (took == 1) return 0;
   }
-  const int up = a->upsample2x ? 1 : 0;
-  const int Hout = a->Hin << up, Wout = a->Win << up;
+  const int up = a->upsample2x ? 1 : 0, down = a->downsample2x ? 1 : 0;
+  const int Hout = (a->Hin << up) >> down, Wout = (a->Win << up) >> down;
   const long long M = (long long)a->B * Hout * Wout;
   const int K = a->ks * a->ks * a->Cin;
   ConvALoader al;
   al.x = a->x, al.in_a = a->in_a, al.in_b = a->in_b, al.in_silu = a->in_silu;
   al.Hin = a->Hin, al.Win = a->Win, al.Cin = a->Cin, al.ks = a->ks, al.up = up;
   al.Hout = Hout, al.Wout = Wout, al.Mtot = M, al.K = K;
+  al.Hv = a->Hin << up, al.Wv = a->Win << up, al.stride = down ? 2 : 1, al.pad = down ? 0 : (a->ks >> 1);
   DenseBLoader bl{a->w, K, 0, a->Cout, K, 0, 1};
   ConvEpilogue ep{a->out, a->bias, a->resid, a->Cout, a->out_mode, Hout, Wout, a->out_rows_total, a->row_offset};
   return launch_sgemm(al, bl, ep, M, a->Cout, K, 1, s, "cvar_conv2d");

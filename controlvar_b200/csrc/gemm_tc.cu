@@ -430,7 +430,7 @@ int tc_split(const float* w, float* hi, float* lo, long long n, cudaStream_t s) 
 
 int tc_conv_try(const cvar_conv_args* a, cudaStream_t s) {
   if (g_gemm_engine == 0) return 0;
-  if (a->Cin % 32 != 0 || a->Cout % 16 != 0 || a->Cout < 32) return 0;
+  if (a->Cin % 32 != 0 || a->Cout % 16 != 0 || a->Cout < 32 || a->downsample2x) return 0;
   const int up = a->upsample2x ? 1 : 0;
   const int Hout = a->Hin << up, Wout = a->Win << up;
   const long long M = (long long)a->B * Hout * Wout;
@@ -440,6 +440,7 @@ int tc_conv_try(const cvar_conv_args* a, cudaStream_t s) {
   al.x = a->x, al.in_a = a->in_a, al.in_b = a->in_b, al.in_silu = a->in_silu;
   al.Hin = a->Hin, al.Win = a->Win, al.Cin = a->Cin, al.ks = a->ks, al.up = up;
   al.Hout = Hout, al.Wout = Wout, al.Mtot = M, al.K = K;
+  al.Hv = Hout, al.Wv = Wout, al.stride = 1, al.pad = a->ks >> 1;
   ConvEpilogue ep{a->out, a->bias, a->resid, a->Cout, a->out_mode, Hout, Wout, a->out_rows_total, a->row_offset};
   int rc = dispatch_tc(al, ep, a->w_hi, a->w_lo, K, M, a->Cout, K, s, "cvar_conv2d[tc]");
   return rc ? rc : 1;

@@ -95,6 +95,17 @@ extern "C" int cvar_prologue(const float* class_emb, const float* cond_embed, co
   return 0;
 }
 
+extern "C" int cvar_prologue_rows(const float* class_emb, const float* cond_embed, const float* pos_start,
+                                  const float* lvl_pos, const int64_t* label_R, const int64_t* cond_type_R, int R, int C,
+                                  float* cond_BD, float* silu_cond, float* x0, void* stream) {
+  CVAR_REQUIRE(R > 0 && C > 0 && label_R && cond_type_R, "cvar_prologue_rows: bad arguments");
+  // B = R: every row reads its own ids, the implicit "unconditional half" of cvar_prologue is never taken
+  prologue_kernel<<<R, 256, 0, (cudaStream_t)stream>>>(class_emb, cond_embed, pos_start, lvl_pos, label_R, cond_type_R,
+                                                       R, C, 0, cond_BD, silu_cond, x0);
+  CVAR_CHECK_LAUNCH("cvar_prologue_rows");
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------- ln_modulate
 // One warp per row; the row (C <= 2048 floats) lives in registers between the statistics pass and the write.
 template <int MAXV>   // float4 per lane
@@ -209,6 +220,27 @@ extern "C" int cvar_nchw_to_nhwc(const float* in, float* out, int B, int C, int 
   nchw_to_nhwc_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(in, out, C, H, W, in_batch_stride,
                                                                           chan_stride, W, total);
   CVAR_CHECK_LAUNCH("cvar_nchw_to_nhwc");
+  return 0;
+}
+
+__global__ void nchw_to_nhwc_pad_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int H, int W,
+                                        int Cpad, long long total) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int c = (int)(i % Cpad);
+  long long p = i / Cpad;
+  int xw = (int)(p % W);
+  long long q = p / W;
+  int yh = (int)(q % H);
+  long long n = q / H;
+  out[i] = c < C ? in[((n * C + c) * H + yh) * W + xw] : 0.f;
+}
+
+extern "C" int cvar_nchw_to_nhwc_pad(const float* in, float* out, int B, int C, int H, int W, int Cpad, void* stream) {
+  CVAR_REQUIRE(B > 0 && C > 0 && Cpad >= C && H > 0 && W > 0, "cvar_nchw_to_nhwc_pad: bad shape");
+  long long total = (long long)B * Cpad * H * W;
+  nchw_to_nhwc_pad_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(in, out, C, H, W, Cpad, total);
+  CVAR_CHECK_LAUNCH("cvar_nchw_to_nhwc_pad");
   return 0;
 }
 
@@ -408,6 +440,28 @@ extern "C" int cvar_repack_conv_weight(const float* w_oihw, float* w_out, int Co
   long long total = (long long)Cout * Cin * ks * ks;
   repack_conv_weight_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(w_oihw, w_out, Cout, Cin, ks);
   CVAR_CHECK_LAUNCH("cvar_repack_conv_weight");
+  return 0;
+}
+
+__global__ void repack_conv_weight_pad_kernel(const float* __restrict__ w, float* __restrict__ o, int Cout, int Cin,
+                                              int ks, int Cin_pad) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)Cout * Cin_pad * ks * ks;
+  if (i >= total) return;
+  int ci = (int)(i % Cin_pad);
+  long long r = i / Cin_pad;
+  int tap = (int)(r % (ks * ks));
+  int co = (int)(r / (ks * ks));
+  o[i] = ci < Cin ? w[((long long)co * Cin + ci) * ks * ks + tap] : 0.f;
+}
+
+extern "C" int cvar_repack_conv_weight_pad(const float* w_oihw, float* w_out, int Cout, int Cin, int ks, int Cin_pad,
+                                           void* stream) {
+  CVAR_REQUIRE(Cout > 0 && Cin > 0 && Cin_pad >= Cin && ks > 0, "cvar_repack_conv_weight_pad: bad shape");
+  long long total = (long long)Cout * Cin_pad * ks * ks;
+  repack_conv_weight_pad_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(w_oihw, w_out, Cout, Cin, ks,
+                                                                                     Cin_pad);
+  CVAR_CHECK_LAUNCH("cvar_repack_conv_weight_pad");
   return 0;
 }
 

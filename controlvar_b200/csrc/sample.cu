@@ -51,22 +51,43 @@ __device__ __forceinline__ float block_max(float v, float* red) {
   return t;
 }
 
+struct MixCoef {
+  float c[4];
+};
+
 __global__ void __launch_bounds__(NT) cfg_sample_kernel(const float* __restrict__ logits, const float* __restrict__ qn,
-                                                        int64_t* __restrict__ idx_out, int B, int l, float s1, float s2,
-                                                        int top_k, int use_top_p, float thr) {
+                                                        int64_t* __restrict__ idx_out, int B, int l, int groups,
+                                                        MixCoef coef, int replicas, int top_k, int use_top_p, float thr,
+                                                        const int64_t* __restrict__ forced_first,
+                                                        const int64_t* __restrict__ forced_second, int forced_replicas) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SampleSmem& sm = *reinterpret_cast<SampleSmem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long row = blockIdx.x;
   const int b = (int)(row / l), t = (int)(row % l);
-  const float* lc = logits + ((long long)b * l + t) * V_FIXED;
-  const float* lu = logits + ((long long)(B + b) * l + t) * V_FIXED;
+  // teacher forcing (control_var.py:309-321): replicas whose token is given need no sample; when every replica of
+  // this row is forced the whole distribution is skipped
+  const int half = l >> 1;
+  const int64_t* forced = t < half ? forced_first : forced_second;
+  const long long forced_at = (long long)b * half + (t < half ? t : t - half);
+  if (forced != nullptr && forced_replicas >= replicas) {
+    if (tid < replicas) idx_out[(long long)tid * B * l + row] = forced[forced_at];
+    return;
+  }
 
-  // (1 + t) * logits[:B] - t * logits[B:], two rounded products and one rounded difference   control_var.py:502
+  // sum_g coef[g] * logits[g*B + b]: every product rounded, summed left to right.  Two groups with (1 + t, -t) is
+  // (1 + t) * logits[:B] - t * logits[B:] of control_var.py:502; four groups is the mix of control_var.py:295-298
+  // (a - x == a + (-x) and (-c) * y == -(c * y) exactly in IEEE arithmetic).
+  {
+    const float* lg = logits + ((long long)b * l + t) * V_FIXED;
+    const long long gstride = (long long)B * l * V_FIXED;
 #pragma unroll
-  for (int i = 0; i < PER; ++i) {
-    int e = tid + i * NT;
-    sm.vals[e] = __fsub_rn(__fmul_rn(s1, lc[e]), __fmul_rn(s2, lu[e]));
+    for (int i = 0; i < PER; ++i) {
+      int e = tid + i * NT;
+      float v = __fmul_rn(coef.c[0], lg[e]);
+      for (int g = 1; g < groups; ++g) v = __fadd_rn(v, __fmul_rn(coef.c[g], lg[g * gstride + e]));
+      sm.vals[e] = v;
+    }
   }
   __syncthreads();
 
@@ -207,57 +228,88 @@ __global__ void __launch_bounds__(NT) cfg_sample_kernel(const float* __restrict_
     loc += ev[i];
   }
   const float total = block_sum(loc, sm.redf);
-  const float* qr = qn + row * V_FIXED;
-  float best = -INFINITY;
-  int besti = V_FIXED;
-#pragma unroll
-  for (int i = 0; i < PER; ++i) {
-    int e = tid + i * NT;
-    float r = (ev[i] / total) / qr[e];
-    if (r > best) {        // ascending e: the first maximum wins, like torch.argmax
-      best = r;
-      besti = e;
+  for (int rep = 0; rep < replicas; ++rep) {      // logits_BlV.repeat(replicas, 1, 1): one distribution, independent draws
+    const long long orow = (long long)rep * B * l + row;
+    if (forced != nullptr && rep < forced_replicas) {
+      if (tid == 0) idx_out[orow] = forced[forced_at];
+      continue;
     }
-  }
+    const float* qr = qn + orow * V_FIXED;
+    float best = -INFINITY;
+    int besti = V_FIXED;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    float ob = __shfl_xor_sync(0xffffffffu, best, o);
-    int oi = __shfl_xor_sync(0xffffffffu, besti, o);
-    if (ob > best || (ob == best && oi < besti)) {
-      best = ob;
-      besti = oi;
-    }
-  }
-  __syncthreads();
-  if (lane == 0) {
-    sm.redf[warp] = best;
-    sm.redi[warp] = besti;
-  }
-  __syncthreads();
-  if (tid == 0) {
-    for (int w = 1; w < NT / 32; ++w) {
-      if (sm.redf[w] > best || (sm.redf[w] == best && sm.redi[w] < besti)) {
-        best = sm.redf[w];
-        besti = sm.redi[w];
+    for (int i = 0; i < PER; ++i) {
+      int e = tid + i * NT;
+      float r = (ev[i] / total) / qr[e];
+      if (r > best) {        // ascending e: the first maximum wins, like torch.argmax
+        best = r;
+        besti = e;
       }
     }
-    idx_out[row] = (int64_t)(besti < V_FIXED ? besti : 0);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+      if (ob > best || (ob == best && oi < besti)) {
+        best = ob;
+        besti = oi;
+      }
+    }
+    __syncthreads();
+    if (lane == 0) {
+      sm.redf[warp] = best;
+      sm.redi[warp] = besti;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      for (int w = 1; w < NT / 32; ++w) {
+        if (sm.redf[w] > best || (sm.redf[w] == best && sm.redi[w] < besti)) {
+          best = sm.redf[w];
+          besti = sm.redi[w];
+        }
+      }
+      idx_out[orow] = (int64_t)(besti < V_FIXED ? besti : 0);
+    }
   }
 }
 }  // namespace
+
+static int launch_cfg_sample(const float* logits, const float* q_noise, int64_t* idx_out, int B, int l, int groups,
+                             MixCoef coef, int replicas, int top_k, double top_p, const int64_t* forced_first,
+                             const int64_t* forced_second, int forced_replicas, cudaStream_t stream, const char* name) {
+  // python evaluates (1 - top_p) in double, then the scalar meets an fp32 tensor as an fp32 value
+  const float thr = (float)(1.0 - top_p);
+  cudaError_t e = cudaFuncSetAttribute(cfg_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sizeof(SampleSmem));
+  CVAR_REQUIRE(e == cudaSuccess, "%s: cannot raise shared memory: %s", name, cudaGetErrorString(e));
+  cfg_sample_kernel<<<(unsigned)((long long)B * l), NT, sizeof(SampleSmem), stream>>>(
+      logits, q_noise, idx_out, B, l, groups, coef, replicas, top_k, top_p > 0.0 ? 1 : 0, thr, forced_first,
+      forced_second, forced_replicas);
+  CVAR_CHECK_LAUNCH(name);
+  return 0;
+}
 
 extern "C" int cvar_cfg_sample(const float* logits, const float* q_noise, int64_t* idx_out, int B, int l, int V,
                                double t, int top_k, double top_p, void* stream) {
   CVAR_REQUIRE(V == V_FIXED, "cvar_cfg_sample: V must be %d (got %d)", V_FIXED, V);
   CVAR_REQUIRE(B > 0 && l > 0 && top_k >= 0 && top_k <= V, "cvar_cfg_sample: bad arguments");
-  // python evaluates (1 + t) and (1 - top_p) in double, then the scalar meets an fp32 tensor as an fp32 value
-  const float s1 = (float)(1.0 + t), s2 = (float)t;
-  const float thr = (float)(1.0 - top_p);
-  cudaError_t e = cudaFuncSetAttribute(cfg_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)sizeof(SampleSmem));
-  CVAR_REQUIRE(e == cudaSuccess, "cvar_cfg_sample: cannot raise shared memory: %s", cudaGetErrorString(e));
-  cfg_sample_kernel<<<(unsigned)((long long)B * l), NT, sizeof(SampleSmem), (cudaStream_t)stream>>>(
-      logits, q_noise, idx_out, B, l, s1, s2, top_k, top_p > 0.0 ? 1 : 0, thr);
-  CVAR_CHECK_LAUNCH("cvar_cfg_sample");
-  return 0;
+  // python evaluates (1 + t) in double, then the scalar meets an fp32 tensor as an fp32 value
+  MixCoef coef{{(float)(1.0 + t), -(float)t, 0.f, 0.f}};
+  return launch_cfg_sample(logits, q_noise, idx_out, B, l, 2, coef, 1, top_k, top_p, nullptr, nullptr, 0,
+                           (cudaStream_t)stream, "cvar_cfg_sample");
+}
+
+extern "C" int cvar_cfg_sample_multi(const float* logits, const float* q_noise, int64_t* idx_out, int B, int l, int V,
+                                     int groups, const float* host_coef, int replicas, int top_k, double top_p,
+                                     const int64_t* forced_first, const int64_t* forced_second, int forced_replicas,
+                                     void* stream) {
+  CVAR_REQUIRE(V == V_FIXED, "cvar_cfg_sample_multi: V must be %d (got %d)", V_FIXED, V);
+  CVAR_REQUIRE(B > 0 && l > 0 && l % 2 == 0 && top_k >= 0 && top_k <= V, "cvar_cfg_sample_multi: bad arguments");
+  CVAR_REQUIRE(groups >= 1 && groups <= 4 && host_coef != nullptr, "cvar_cfg_sample_multi: 1..4 logit groups");
+  CVAR_REQUIRE(replicas >= 1 && replicas <= NT && forced_replicas >= 0 && forced_replicas <= replicas,
+               "cvar_cfg_sample_multi: bad replicas / forced_replicas");
+  MixCoef coef{{0.f, 0.f, 0.f, 0.f}};
+  for (int g = 0; g < groups; ++g) coef.c[g] = host_coef[g];
+  return launch_cfg_sample(logits, q_noise, idx_out, B, l, groups, coef, replicas, top_k, top_p, forced_first,
+                           forced_second, forced_replicas, (cudaStream_t)stream, "cvar_cfg_sample_multi");
 }

@@ -47,17 +47,21 @@ struct DenseALoader {
 // Implicit-GEMM view of a stride-1 'same' convolution over an NHWC activation (vae_modules.py Conv2d call sites):
 // row m = (n, y, x) of the OUTPUT grid, column k = (tap, ci).  Optional nearest x2 upsampling of the input
 // (Upsample2x, vae_modules.py:27-28) and optional fused GroupNorm-affine (+SiLU) on the input (vae_modules.py:58-59).
+// stride = 2 with pad = 0 is the encoder's Downsample2x (vae_modules.py:31-37): F.pad(x, (0,1,0,1)) + a stride-2 'valid'
+// 3x3 conv, i.e. output (y, x) reads input rows 2y..2y+2, zero beyond the bottom / right edge only.
 struct ConvALoader {
   const float* x;
   const float* in_a;
   const float* in_b;
   int in_silu;
   int Hin, Win, Cin, ks, up;      // up: 0 or 1 (log2 of the upsampling factor)
-  int Hout, Wout;
+  int Hout, Wout;                 // output grid (row decode)
+  int Hv, Wv;                     // input grid the taps are bounds-checked against (Hin << up, Win << up)
+  int stride, pad;                // 1, ks/2 for the 'same' convolutions; 2, 0 for Downsample2x
   long long Mtot;
   int K;
   static constexpr int kMaxSlots = 8;
-  int sn[kMaxSlots], sy[kMaxSlots], sx[kMaxSlots];
+  int sn[kMaxSlots], sy[kMaxSlots], sx[kMaxSlots];   // sy / sx hold the top-left tap position (y*stride - pad)
   int blk_dy, blk_dx, blk_ci;   // tap offset and first input channel of the current K-block (tcgen05 engine)
   // A K-block never straddles two taps when Cin is a multiple of the block size, so the tap decode (two integer
   // divisions) is done once per block instead of once per 16-byte fetch.
@@ -65,14 +69,14 @@ struct ConvALoader {
     int tap = k0 / Cin;
     blk_ci = k0 - tap * Cin;
     int ky = tap / ks;
-    blk_dy = ky - (ks >> 1);
-    blk_dx = (tap - ky * ks) - (ks >> 1);
+    blk_dy = ky;
+    blk_dx = tap - ky * ks;
   }
   __device__ __forceinline__ float4 fetch_blk(int slot, int /*k0*/, int koff) const {
     float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
     if (sn[slot] < 0) return z;
     int yy = sy[slot] + blk_dy, xx = sx[slot] + blk_dx;
-    if (yy < 0 || yy >= Hout || xx < 0 || xx >= Wout) return z;
+    if (yy < 0 || yy >= Hv || xx < 0 || xx >= Wv) return z;
     int ci = blk_ci + koff;
     int n = sn[slot];
     float4 v = ld4(x + (((long long)n * Hin + (yy >> up)) * Win + (xx >> up)) * Cin + ci);
@@ -87,9 +91,9 @@ struct ConvALoader {
     if (m < Mtot) {
       int xw = (int)(m % Wout);
       long long q = m / Wout;
-      sy[slot] = (int)(q % Hout);
+      sy[slot] = (int)(q % Hout) * stride - pad;
       sn[slot] = (int)(q / Hout);
-      sx[slot] = xw;
+      sx[slot] = xw * stride - pad;
     } else {
       sn[slot] = -1;
     }
@@ -99,10 +103,9 @@ struct ConvALoader {
     if (sn[slot] < 0 || k >= K) return z;
     int tap = k / Cin;
     int ci = k - tap * Cin;
-    int pad = ks >> 1;
     int ky = tap / ks, kx = tap - ky * ks;
-    int yy = sy[slot] + ky - pad, xx = sx[slot] + kx - pad;
-    if (yy < 0 || yy >= Hout || xx < 0 || xx >= Wout) return z;      // zero padding is applied AFTER norm+act
+    int yy = sy[slot] + ky, xx = sx[slot] + kx;
+    if (yy < 0 || yy >= Hv || xx < 0 || xx >= Wv) return z;          // zero padding is applied AFTER norm+act
     int n = sn[slot];
     const float* p = x + (((long long)n * Hin + (yy >> up)) * Win + (xx >> up)) * Cin + ci;
     float4 v = ld4(p);
@@ -310,6 +313,7 @@ struct QkvEpilogue {
 };
 
 // conv output: NHWC (+bias, +residual) or the final image plane write                    (vqvae.py:88-89)
+// out_mode 3: NCHW planes without the clamp (quant_conv output feeding the residual quantiser, vqvae.py:74)
 struct ConvEpilogue {
   float* out;
   const float* bias;
@@ -344,7 +348,7 @@ struct ConvEpilogue {
       for (int j = 0; j < 4; ++j) {
         if (j < nvalid) {
           float t = __fadd_rn(v[j], bias[n + j]);
-          t = fminf(fmaxf(t, -1.f), 1.f);                    // .clamp_(-1, 1)            vqvae.py:89
+          if (out_mode != 3) t = fminf(fmaxf(t, -1.f), 1.f);  // .clamp_(-1, 1)           vqvae.py:89
           if (out_mode == 1) t = __fmul_rn(__fadd_rn(t, 1.f), 0.5f);   // .add_(1).mul_(0.5)  control_var.py:563
           out[((nimg * Cout + (n + j)) * out_rows_total + row_offset + y) * Wout + xw] = t;
         }

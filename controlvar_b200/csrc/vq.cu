@@ -32,8 +32,8 @@ __global__ void __launch_bounds__(256) vq_step_kernel(const int64_t* __restrict_
                                                       const float* __restrict__ phi_b, const float* __restrict__ word_w,
                                                       const float* __restrict__ word_b,
                                                       const float* __restrict__ lvl_pos_next, float* __restrict__ f_hat,
-                                                      float* __restrict__ x_next, int B, int pn, int pn_next, int hw,
-                                                      int C) {
+                                                      float* __restrict__ f_rest, float* __restrict__ x_next, int B,
+                                                      int x_rep, int pn, int pn_next, int hw, int C) {
   extern __shared__ __align__(16) float smf[];
   const VqSmemLayout L = vq_layout(hw);
   float* w_s = smf + L.w;
@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(256) vq_step_kernel(const int64_t* __restrict_
   float* hu_s = smf + L.hu;
   float* U_s = smf + L.U;
   const int tid = threadIdx.x;
-  const int b = blockIdx.x, s = blockIdx.y;
+  const int b = blockIdx.x, s = blockIdx.y, S = gridDim.y;   // S streams stacked along H: (control, image) or one map
   const int npix = pn * pn, HW = hw * hw, hp = hw + 2;
 
   for (int i = tid; i < CV * 9 * CV; i += 256) {
@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(256) vq_step_kernel(const int64_t* __restrict_
   if (pn != hw)
     for (int i = tid; i < hw * pn; i += 256) U_s[i] = U[i];
   for (int i = tid; i < CV * hp * hp; i += 256) hu_s[i] = 0.f;
-  const int64_t* ib = idx + (long long)b * (2 * npix) + s * npix;
+  const int64_t* ib = idx + (long long)b * (S * npix) + s * npix;
   for (int i = tid; i < CV * npix; i += 256) {
     int c = i % CV, p = i / CV;                  // consecutive lanes read one 128-byte codebook row
     h_s[c * npix + p] = emb[ib[p] * CV + c];
@@ -115,10 +115,11 @@ __global__ void __launch_bounds__(256) vq_step_kernel(const int64_t* __restrict_
     for (int co = 0; co < CV; ++co) {
       float hv = hu_s[(co * hp + Y + 1) * hp + X + 1];
       float phi = __fadd_rn(__fmul_rn(hv, 0.5f), __fmul_rn(acc[co], 0.5f));
-      long long g = (((long long)b * CV + co) * (2 * hw) + s * hw + Y) * hw + X;
+      long long g = (((long long)b * CV + co) * (S * hw) + s * hw + Y) * hw + X;
       float fn = __fadd_rn(f_hat[g], phi);
       f_hat[g] = fn;
       f_s[co * HW + p] = fn;
+      if (f_rest != nullptr) f_rest[g] = __fsub_rn(f_rest[g], phi);        // f_rest.sub_(h)   quant.py:211
     }
   }
   if (pn_next <= 0) return;
@@ -139,7 +140,7 @@ __global__ void __launch_bounds__(256) vq_step_kernel(const int64_t* __restrict_
   }
   __syncthreads();
 
-  // word_embed + lvl_pos, duplicated for the two CFG halves                        control_var.py:555-560
+  // word_embed + lvl_pos, written x_rep times (the two CFG halves of control_var.py:560; once at :345-347)
   for (int co = tid; co < C; co += 256) {
     float w[CV];
 #pragma unroll
@@ -154,10 +155,28 @@ __global__ void __launch_bounds__(256) vq_step_kernel(const int64_t* __restrict_
       for (int c = 0; c < CV; ++c) a = fmaf(w[c], nxt_s[c * nn + j], a);
       int tok = s * nn + j;
       float v = __fadd_rn(__fadd_rn(a, bias), lvl_pos_next[(long long)tok * C + co]);
-      x_next[((long long)b * (2 * nn) + tok) * C + co] = v;
-      x_next[((long long)(B + b) * (2 * nn) + tok) * C + co] = v;
+      for (int rep = 0; rep < x_rep; ++rep)
+        x_next[((long long)(rep * B + b) * (S * nn) + tok) * C + co] = v;
     }
   }
+}
+
+// F.interpolate(f_rest, size=(pn, pn), mode='area').permute(0, 2, 3, 1).reshape(-1, C)      quant.py:199
+__global__ void area_pool_nc_kernel(const float* __restrict__ f, float* __restrict__ z, int hw, int pn, long long total) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int c = (int)(i % CV);
+  long long r = i / CV;
+  int j = (int)(r % (pn * pn));
+  long long b = r / (pn * pn);
+  int iy = j / pn, ix = j % pn;
+  int y0 = (iy * hw) / pn, y1 = ((iy + 1) * hw + pn - 1) / pn;
+  int x0 = (ix * hw) / pn, x1 = ((ix + 1) * hw + pn - 1) / pn;
+  const float* fc = f + (b * CV + c) * hw * hw;
+  float sum = 0.f;
+  for (int y = y0; y < y1; ++y)
+    for (int x = x0; x < x1; ++x) sum += fc[y * hw + x];
+  z[i] = sum / (float)(y1 - y0) / (float)(x1 - x0);
 }
 
 // L2 nearest code (quant.py:203-206): one warp per latent vector, lanes stride the codebook.
@@ -205,11 +224,12 @@ __global__ void __launch_bounds__(256) vq_nearest_kernel(const float* __restrict
 }
 }  // namespace
 
-extern "C" int cvar_vq_step(const int64_t* idx, const float* embedding, const float* U, const float* phi_w,
-                            const float* phi_b, const float* word_w, const float* word_b, const float* lvl_pos_next,
-                            float* f_hat, float* x_next, int B, int pn, int pn_next, int hw, int Cvae, int C,
-                            void* stream) {
+extern "C" int cvar_vq_step_ex(const int64_t* idx, const float* embedding, const float* U, const float* phi_w,
+                               const float* phi_b, const float* word_w, const float* word_b, const float* lvl_pos_next,
+                               float* f_hat, float* f_rest, float* x_next, int B, int streams, int x_replicas, int pn,
+                               int pn_next, int hw, int Cvae, int C, void* stream) {
   CVAR_REQUIRE(Cvae == CV, "cvar_vq_step: Cvae must be %d", CV);
+  CVAR_REQUIRE(B > 0 && (streams == 1 || streams == 2) && x_replicas >= 1, "cvar_vq_step: bad B / streams / x_replicas");
   CVAR_REQUIRE(hw >= 1 && hw <= MAXHW && pn >= 1 && pn <= hw && pn_next <= hw, "cvar_vq_step: bad sizes pn=%d hw=%d", pn,
                hw);
   CVAR_REQUIRE(pn == hw || U != nullptr, "cvar_vq_step: interpolation matrix missing");
@@ -217,9 +237,26 @@ extern "C" int cvar_vq_step(const int64_t* idx, const float* embedding, const fl
   size_t smem = (size_t)vq_layout(hw).total * sizeof(float);
   cudaError_t e = cudaFuncSetAttribute(vq_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   CVAR_REQUIRE(e == cudaSuccess, "cvar_vq_step: cannot raise shared memory: %s", cudaGetErrorString(e));
-  vq_step_kernel<<<dim3(B, 2), 256, smem, (cudaStream_t)stream>>>(idx, embedding, U, phi_w, phi_b, word_w, word_b,
-                                                                  lvl_pos_next, f_hat, x_next, B, pn, pn_next, hw, C);
+  vq_step_kernel<<<dim3(B, streams), 256, smem, (cudaStream_t)stream>>>(idx, embedding, U, phi_w, phi_b, word_w, word_b,
+                                                                        lvl_pos_next, f_hat, f_rest, x_next, B,
+                                                                        x_replicas, pn, pn_next, hw, C);
   CVAR_CHECK_LAUNCH("cvar_vq_step");
+  return 0;
+}
+
+extern "C" int cvar_vq_step(const int64_t* idx, const float* embedding, const float* U, const float* phi_w,
+                            const float* phi_b, const float* word_w, const float* word_b, const float* lvl_pos_next,
+                            float* f_hat, float* x_next, int B, int pn, int pn_next, int hw, int Cvae, int C,
+                            void* stream) {
+  return cvar_vq_step_ex(idx, embedding, U, phi_w, phi_b, word_w, word_b, lvl_pos_next, f_hat, nullptr, x_next, B, 2, 2,
+                         pn, pn_next, hw, Cvae, C, stream);
+}
+
+extern "C" int cvar_area_pool_nc(const float* f_nchw, float* z_NC, int B, int Cvae, int hw, int pn, void* stream) {
+  CVAR_REQUIRE(Cvae == CV && B > 0 && pn >= 1 && pn <= hw, "cvar_area_pool_nc: bad shape");
+  long long total = (long long)B * pn * pn * CV;
+  area_pool_nc_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(f_nchw, z_NC, hw, pn, total);
+  CVAR_CHECK_LAUNCH("cvar_area_pool_nc");
   return 0;
 }
 

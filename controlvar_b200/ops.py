@@ -141,6 +141,15 @@ def prologue(class_emb, cond_embed, pos_start, lvl_pos_t, label_B, cond_type_B, 
                                     _stream()), "cvar_prologue")
 
 
+def prologue_rows(class_emb, cond_embed, pos_start, lvl_pos_t, label_R, cond_type_R, cond_BD, silu_cond, x0):
+    """Explicit per-row class / condition-type ids (the four guidance replicas of conditional_infer_cfg)."""
+    _chk(class_emb, cond_embed, pos_start, lvl_pos_t, label_R, cond_type_R, cond_BD, silu_cond, x0)
+    R, Cdim = label_R.shape[0], class_emb.shape[1]
+    check(_lib.load().cvar_prologue_rows(_p(class_emb), _p(cond_embed), _p(pos_start), _p(lvl_pos_t), _p(label_R),
+                                         _p(cond_type_R), R, Cdim, _p(cond_BD), _p(silu_cond), _p(x0), _stream()),
+          "cvar_prologue_rows")
+
+
 def ln_modulate(x, scale, shift, mod_row_stride, out, M, Cdim, rows_per_sample, eps, out_lo=None,
                 out16: Optional[F16Pair] = None):
     """scale/shift: views into an ada_lin output; only their data pointers and the common row stride are used.
@@ -269,11 +278,33 @@ def cfg_sample(logits, q_noise, idx_out, B, l, V, t, top_k, top_p):
     return idx_out
 
 
-def vq_step(idx, embedding, U, phi_w, phi_b, word_w, word_b, lvl_pos_next, f_hat, x_next, B, pn, pn_next, hw, Cvae, Cdim):
-    _chk(idx, embedding, U, phi_w, phi_b, word_w, word_b, lvl_pos_next, f_hat, x_next)
-    check(_lib.load().cvar_vq_step(_p(idx), _p(embedding), _p(U), _p(phi_w), _p(phi_b), _p(word_w), _p(word_b),
-                                   _p(lvl_pos_next), _p(f_hat), _p(x_next), B, pn, pn_next, hw, Cvae, Cdim,
-                                   _stream()), "cvar_vq_step")
+def cfg_sample_multi(logits, q_noise, idx_out, B, l, V, coef, replicas, top_k, top_p, forced_first=None,
+                     forced_second=None, forced_replicas=0):
+    """Guidance mix over len(coef) logit groups, `replicas` independent draws per row, optional teacher forcing
+    (control_var.py:288-321).  coef: python floats, already rounded the way the reference's scalars are."""
+    _chk(logits, q_noise, idx_out, forced_first, forced_second)
+    G = len(coef)
+    arr = (C.c_float * G)(*[float(c) for c in coef])
+    with _Timed("sample", 0.0, 4.0 * B * l * V * (G + replicas) + 8.0 * B * l * replicas):
+        check(_lib.load().cvar_cfg_sample_multi(_p(logits), _p(q_noise), _p(idx_out), B, l, V, G, arr, int(replicas),
+                                                int(top_k), float(top_p), _p(forced_first), _p(forced_second),
+                                                int(forced_replicas), _stream()), "cvar_cfg_sample_multi")
+    return idx_out
+
+
+def vq_step(idx, embedding, U, phi_w, phi_b, word_w, word_b, lvl_pos_next, f_hat, x_next, B, pn, pn_next, hw, Cvae, Cdim,
+            streams=2, x_replicas=2, f_rest=None):
+    """streams / x_replicas / f_rest: see cvar_vq_step_ex (defaults = the autoregressive_infer_cfg step)."""
+    _chk(idx, embedding, U, phi_w, phi_b, word_w, word_b, lvl_pos_next, f_hat, x_next, f_rest)
+    check(_lib.load().cvar_vq_step_ex(_p(idx), _p(embedding), _p(U), _p(phi_w), _p(phi_b), _p(word_w), _p(word_b),
+                                      _p(lvl_pos_next), _p(f_hat), _p(f_rest), _p(x_next), B, int(streams),
+                                      int(x_replicas), pn, pn_next, hw, Cvae, Cdim, _stream()), "cvar_vq_step_ex")
+
+
+def area_pool_nc(f_nchw, z_NC, B, Cvae, hw, pn):
+    _chk(f_nchw, z_NC)
+    check(_lib.load().cvar_area_pool_nc(_p(f_nchw), _p(z_NC), B, Cvae, hw, pn, _stream()), "cvar_area_pool_nc")
+    return z_NC
 
 
 def vq_nearest(z_NC, embedding, idx_out):
@@ -291,6 +322,12 @@ def nchw_to_nhwc(x_view, out, B, Cdim, H, W, in_batch_stride):
     return out
 
 
+def nchw_to_nhwc_pad(x, out, B, Cdim, H, W, Cpad):
+    _chk(x, out)
+    check(_lib.load().cvar_nchw_to_nhwc_pad(_p(x), _p(out), B, Cdim, H, W, Cpad, _stream()), "cvar_nchw_to_nhwc_pad")
+    return out
+
+
 def gn_chunks(HW: int) -> int:
     return int(_lib.load().cvar_gn_chunks(HW))
 
@@ -303,8 +340,9 @@ def gn_stats(x_nhwc, gamma, beta, a_out, b_out, scratch, B, HW, Cdim, groups=32,
 
 def conv2d(x, w_packed, bias, out, B, Hin, Win, Cin, Cout, ks, *, in_a=None, in_b=None, in_silu=False, resid=None,
            upsample2x=False, out_mode=0, out_rows_total=0, row_offset=0, engine=-1, x16: Optional[F16Pair] = None,
-           w16: Optional[F16Pair] = None):
-    """x16 + w16: FP16-pair input (already normalised / upsampled) and weight -> the 2-CTA TMA kernel; x may be None."""
+           w16: Optional[F16Pair] = None, downsample2x=False):
+    """x16 + w16: FP16-pair input (already normalised / upsampled) and weight -> the 2-CTA TMA kernel; x may be None.
+    downsample2x: the encoder's pad-(0,1,0,1) + stride-2 convolution (vae_modules.py:31-37)."""
     w_packed, w_hi, w_lo, _ = _wparts(w_packed)
     _chk(x, w_packed, bias, out, in_a, in_b, resid)
     if (x16 is None) != (w16 is None):
@@ -319,8 +357,9 @@ def conv2d(x, w_packed, bias, out, B, Hin, Win, Cin, Cout, ks, *, in_a=None, in_
     a.B, a.Hin, a.Win, a.Cin, a.Cout, a.ks, a.upsample2x = B, Hin, Win, Cin, Cout, ks, int(upsample2x)
     a.out_mode, a.out_rows_total, a.row_offset = out_mode, out_rows_total, row_offset
     a.engine = int(engine)
+    a.downsample2x = int(downsample2x)
     up = 2 if upsample2x else 1
-    Mo = B * Hin * up * Win * up
+    Mo = B * Hin * up * Win * up // (4 if downsample2x else 1)
     with _Timed("conv", 2.0 * Mo * Cout * ks * ks * Cin, 4.0 * (B * Hin * Win * Cin + Mo * Cout + Cout * ks * ks * Cin)):
         check(_lib.load().cvar_conv2d(C.byref(a), _stream()), "cvar_conv2d")
     return out
@@ -330,6 +369,14 @@ def repack_conv_weight(w_oihw, out):
     _chk(w_oihw, out)
     Cout, Cin, ks, _ = w_oihw.shape
     check(_lib.load().cvar_repack_conv_weight(_p(w_oihw), _p(out), Cout, Cin, ks, _stream()), "cvar_repack_conv_weight")
+    return out
+
+
+def repack_conv_weight_pad(w_oihw, out, Cin_pad):
+    _chk(w_oihw, out)
+    Cout, Cin, ks, _ = w_oihw.shape
+    check(_lib.load().cvar_repack_conv_weight_pad(_p(w_oihw), _p(out), Cout, Cin, ks, int(Cin_pad), _stream()),
+          "cvar_repack_conv_weight_pad")
     return out
 
 

@@ -11,14 +11,30 @@ from __future__ import annotations
 
 from typing import Dict, List, Optional, Sequence, Tuple
 
+import numpy as np
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 from . import ops
 from .config import PathConfig, DEFAULT_PATCH_NUMS
-from .weights import decoder_plan, vae_key_shapes
+from .weights import decoder_plan, encoder_plan, vae_key_shapes
 
 _BUFFER_KEYS = ("ema_vocab_hit_SV",)
+
+
+def bicubic_matrix(n_in: int, n_out: int) -> torch.Tensor:
+    """(n_out, n_in) matrix U of F.interpolate(mode='bicubic', align_corners=False) along one axis, read off impulse
+    responses so that the coefficients (A = -0.75, border clamping) are exactly ATen's.  Host-side constant."""
+    eye = torch.eye(n_in, dtype=torch.float32).view(n_in, 1, 1, n_in)          # one impulse per batch entry
+    out = F.interpolate(eye, size=(1, n_out), mode="bicubic")                  # height 1 -> 1 is the identity
+    return out[:, 0, 0, :].t().contiguous()                                    # U[X, j]
+
+
+def phi_index(si: int, SN: int, K: int = 4) -> int:
+    """PhiPartiallyShared.__getitem__(si / (SN - 1)) - quant.py:282-293."""
+    ticks = np.linspace(1 / 3 / K, 1 - 1 / 3 / K, K) if K == 4 else np.linspace(1 / 2 / K, 1 - 1 / 2 / K, K)
+    return int(np.argmin(np.abs(ticks - si / (SN - 1))).item())
 
 
 class _Node(nn.Module):
@@ -61,12 +77,20 @@ class VQVAE(nn.Module):
         q = self.quantize
         q.vocab_size, q.Cvae, q.v_patch_nums, q.share_quant_resi = vocab_size, z_channels, tuple(v_patch_nums), share_quant_resi
         self._plan = decoder_plan(self.cfg)
+        self._enc_plan = encoder_plan(self.cfg)
+        self._U: Dict[Tuple[int, int], torch.Tensor] = {}
+        # test instrument (as ControlVAR.debug_forced_idx): per-scale (B, pn*pn) tokens that replace the argmin result
+        # before the residual update of f_to_idxBl, pinning the residual trajectory to the oracle's
+        self.debug_forced_idx: Optional[List[torch.Tensor]] = None
+        self.last_idx: List[torch.Tensor] = []
         # Decoder convolutions whose output side is below this run on the SIMT fp32 engine.  Measured on B200
         # (profiles/r01_decoder_policy.md, engine 4 = f16x3): with every conv on tensor cores the worst pixel over 32
         # realistic images is 9.0e-5 off the fp32 oracle (1.09e-4 on another 4: over the north-star bound of 1e-4); the
         # 16x16 layers (K = 5760, few pixels) cause most of that and cost little, so they stay in exact fp32:
         # worst pixel 7.1e-5, 146 ms per 64-image decode (all on tensor cores: 115 ms; >= 64 only: 180 ms, 4.3e-5).
-        self.tc_min_hw = 32
+        # The 3xTF32 engines (1, 3) are ~2x less accurate per layer and need >= 64 (32 gives 1.06e-4 .. 1.24e-4).
+        # None = that per-engine default; an int overrides it (tools/diag_decoder_policy.py).
+        self.tc_min_hw: Optional[int] = None
         self._packed: Dict[str, torch.Tensor] = {}
         self._packed16: Dict[str, "ops.F16Pair"] = {}
         self._ws: Dict[Tuple, torch.Tensor] = {}
@@ -87,19 +111,25 @@ class VQVAE(nn.Module):
         self._packed.clear()
         self._packed16.clear()
         self._ws.clear()
+        self._U.clear()
         return super()._apply(fn, recurse)
 
     def _w(self, key: str) -> torch.Tensor:
         return self.get_parameter(key)
 
-    def _conv_w(self, prefix: str) -> torch.Tensor:
-        """Conv weight repacked (Cout, ks*ks*Cin) tap-major for the implicit-GEMM kernels (cached)."""
+    def _conv_w(self, prefix: str, cin_pad: int = 0) -> torch.Tensor:
+        """Conv weight repacked (Cout, ks*ks*Cin) tap-major for the implicit-GEMM kernels (cached).  cin_pad: zero
+        weights for padding input channels (Encoder.conv_in: the 3-channel image runs as a 16-channel NHWC tensor)."""
         key = prefix + ".weight"
         t = self._packed.get(key)
         if t is None:
             w = self._w(key)
-            t = torch.empty(w.shape[0], w.shape[1] * w.shape[2] * w.shape[3], device=w.device, dtype=torch.float32)
-            ops.repack_conv_weight(w.contiguous(), t)
+            cin = max(cin_pad, w.shape[1])
+            t = torch.empty(w.shape[0], cin * w.shape[2] * w.shape[3], device=w.device, dtype=torch.float32)
+            if cin != w.shape[1]:
+                ops.repack_conv_weight_pad(w.contiguous(), t, cin)
+            else:
+                ops.repack_conv_weight(w.contiguous(), t)
             if t.numel() % 4 == 0:
                 t = ops.SplitWeight(t)       # + TF32 hi/lo split for the tcgen05 engine
             self._packed[key] = t
@@ -115,9 +145,14 @@ class VQVAE(nn.Module):
             self._packed16[key] = p
         return p
 
+    def _min_hw(self) -> int:
+        if self.tc_min_hw is not None:
+            return self.tc_min_hw
+        return 32 if ops.get_gemm_engine() == ops.ENGINE_TC_F16X3 else 64
+
     def _f16_layer(self, Hout, Wout, Cin, Cout, ks) -> bool:
         """Does this layer run on the FP16-pair TMA kernel?  Engine 4, accuracy policy (tc_min_hw), supported shape."""
-        return (ops.get_gemm_engine() == ops.ENGINE_TC_F16X3 and Hout >= self.tc_min_hw
+        return (ops.get_gemm_engine() == ops.ENGINE_TC_F16X3 and Hout >= self._min_hw()
                 and ops.conv2d_f16_supported(Hout, Wout, Cin, Cout, ks))
 
     def _conv(self, x, prefix, out, B, Hin, Win, Cin, Cout, ks, **kw):
@@ -128,7 +163,7 @@ class VQVAE(nn.Module):
                               w16=self._conv_w16(prefix), **kw)
         hout = Hin * (2 if kw.get("upsample2x") else 1)
         return ops.conv2d(x, self._conv_w(prefix), bias, out, B, Hin, Win, Cin, Cout, ks,
-                          engine=(-1 if hout >= self.tc_min_hw else 0), **kw)
+                          engine=(-1 if hout >= self._min_hw() else 0), **kw)
 
     def _pair(self, name: str, numel: int, shape) -> "ops.F16Pair":
         n = 1
@@ -213,23 +248,7 @@ class VQVAE(nn.Module):
         zq = self._buf("z_pq", (B, H, W, cfg.Cvae))
         self._conv(z_nhwc, "post_quant_conv", zq, B, H, W, cfg.Cvae, cfg.Cvae, 3)
         cur = zq
-        ring_i = 0
-
-        def ring(shape):
-            # three flat activation buffers, sized for the largest tensor of the plan, handed out round-robin
-            nonlocal ring_i
-            ring_i = (ring_i + 1) % 3
-            n = 1
-            for s_ in shape:
-                n *= s_
-            return self._buf(f"act{ring_i}", (act_numel,))[:n].view(shape)
-
-        act_numel, hh = 0, hw
-        for op, _, cin, cout in self._plan:
-            if op == "up":
-                hh *= 2
-            act_numel = max(act_numel, B * hh * hh * max(cin if op == "out" else cout, 1))
-        self._act_numel = act_numel
+        ring = self._ring_setup(self._plan, B, hw)
 
         for op, prefix, cin, cout in self._plan:
             if op == "conv3":
@@ -287,9 +306,114 @@ class VQVAE(nn.Module):
         self._decode_nhwc(z, B, h, out, rows_total, row_offset, out_mode)
         return out
 
-    # the remaining reference entry points touch the encoder / training side (SURVEY.md section 8f "next")
-    def img_to_idxBl(self, *a, **k):
-        raise NotImplementedError("VQVAE.img_to_idxBl (encoder side) is scheduled after the sampling path, see DESIGN.md")
+    # -------------------------------------------------------------------------------------------- encoder
+    def _ring_setup(self, plan, B: int, hw0: int):
+        """Three flat activation buffers sized for the largest tensor of the plan, handed out round-robin."""
+        act_numel, hh = 0, hw0
+        for op, _, cin, cout in plan:
+            if op == "up":
+                hh *= 2
+            elif op == "down":
+                hh //= 2
+            act_numel = max(act_numel, B * hh * hh * max(cin if op == "out" else cout, 1))
+        self._act_numel = act_numel
+        state = {"i": 0}
+
+        def ring(shape):
+            state["i"] = (state["i"] + 1) % 3
+            n = 1
+            for s_ in shape:
+                n *= s_
+            return self._buf(f"act{state['i']}", (act_numel,))[:n].view(shape)
+        return ring
+
+    @torch.no_grad()
+    def _img_to_f(self, img: torch.Tensor) -> torch.Tensor:
+        """quant_conv(encoder(img)) - vqvae.py:74, Encoder.forward vae_modules.py:145-160.  img (B, 3, H, W) in [-1, 1];
+        returns f (B, Cvae, H/16, W/16) NCHW (a fresh tensor)."""
+        if not img.is_cuda:
+            raise RuntimeError("controlvar_b200.VQVAE runs on CUDA only (no CPU fallback)")
+        B, Ci, H, W = img.shape
+        assert Ci == 3 and H == W and H % self.downsample == 0, "img must be (B, 3, S, S) with S a multiple of 16"
+        img = img.to(torch.float32).contiguous()
+        cfg = self.cfg
+        CPAD = 16
+        ring = self._ring_setup(self._enc_plan, B, H)
+        cur = None
+        for op, prefix, cin, cout in self._enc_plan:
+            if op == "conv_in":
+                x0 = self._buf("enc_x0", (B, H, W, CPAD))
+                ops.nchw_to_nhwc_pad(img, x0, B, 3, H, W, CPAD)
+                out = ring((B, H, W, cout))
+                ops.conv2d(x0, self._conv_w(prefix, cin_pad=CPAD), self._w(prefix + ".bias"), out, B, H, W, CPAD, cout, 3,
+                           engine=0)
+                cur = out
+            elif op == "res":
+                h1 = ring((B, H, W, cout))
+                out = ring((B, H, W, cout))
+                cur = self._resblock(cur, prefix, B, H, W, cin, cout, (h1, out))
+            elif op == "attn":
+                out = ring((B, H, W, cout))
+                cur = self._attnblock(cur, prefix, B, H, W, cin, out)
+            elif op == "down":
+                out = ring((B, H // 2, W // 2, cout))
+                ops.conv2d(cur, self._conv_w(prefix), self._w(prefix + ".bias"), out, B, H, W, cin, cout, 3,
+                           downsample2x=True, engine=0)
+                H, W = H // 2, W // 2
+                cur = out
+            elif op == "out":
+                z = self._buf("enc_z", (B, H, W, cout))
+                self._conv(self._norm_act(cur, "encoder.norm_out", B, H, W, cin, 0), "encoder.conv_out", z, B, H, W, cin,
+                           cout, 3)
+                f = torch.empty(B, cout, H, W, device=img.device, dtype=torch.float32)
+                # quant_conv, written NCHW (the layout of f_rest / f_hat in quant.py:184-215)
+                self._conv(z, "quant_conv", f, B, H, W, cout, cout, 3, out_mode=3, out_rows_total=H, row_offset=0)
+                return f
+            else:
+                raise AssertionError(op)
+        raise AssertionError("encoder plan without an output record")
+
+    @torch.no_grad()
+    def _f_to_idxBl(self, f: torch.Tensor, v_patch_nums: Sequence[int]) -> List[torch.Tensor]:
+        """VectorQuantizer2.f_to_idxBl_or_fhat(to_fhat=False) - quant.py:184-215: per scale, area-pool the residual,
+        nearest code, then f_hat += phi(bicubic(E[idx])), f_rest -= the same, in one kernel."""
+        B, Cz, H, W = f.shape
+        pns = [int(pn) for pn in v_patch_nums]
+        assert Cz == self.Cvae and H == W and pns[-1] == H, f"patch_nums[-1]={pns[-1]} != H={H}"
+        SN = len(pns)
+        f_rest = f.detach().clone().contiguous()
+        f_hat = torch.zeros_like(f_rest)
+        emb = self._w("quantize.embedding.weight")
+        out: List[torch.Tensor] = []
+        self.last_idx = []
+        for si, pn in enumerate(pns):
+            N = B * pn * pn
+            z = self._buf("vq_z", (B * H * W, Cz))[:N]
+            ops.area_pool_nc(f_rest, z, B, Cz, H, pn)
+            idx = torch.empty(N, dtype=torch.int64, device=f.device)
+            ops.vq_nearest(z, emb, idx)
+            self.last_idx.append(idx.view(B, pn * pn).clone())
+            if self.debug_forced_idx is not None:
+                idx.copy_(self.debug_forced_idx[si].to(device=f.device, dtype=torch.int64).reshape(-1))
+            k = phi_index(si, SN, self.cfg.share_quant_resi) if SN > 1 else 0
+            U = None
+            if pn != H:
+                U = self._U.get((pn, H))
+                if U is None:
+                    U = self._U[(pn, H)] = bicubic_matrix(pn, H).to(f.device)
+            ops.vq_step(idx, emb, U, self._w(f"quantize.quant_resi.qresi_ls.{k}.weight"),
+                        self._w(f"quantize.quant_resi.qresi_ls.{k}.bias"), None, None, None, f_hat, None, B, pn, 0, H, Cz,
+                        0, streams=1, x_replicas=1, f_rest=f_rest)
+            out.append(idx.view(B, pn * pn))
+        return out
+
+    @torch.no_grad()
+    def img_to_idxBl(self, inp_img_no_grad: torch.Tensor,
+                     v_patch_nums: Optional[Sequence[int]] = None) -> List[torch.Tensor]:
+        """Drop-in for VQVAE.img_to_idxBl (vqvae.py:73-75): the multi-scale token ids, List[(B, pn*pn) int64], of an
+        image in [-1, 1].  v_patch_nums defaults to the constructor's (the reference's callers always pass it)."""
+        pns = self.cfg.patch_nums if v_patch_nums is None else v_patch_nums
+        return self._f_to_idxBl(self._img_to_f(inp_img_no_grad), pns)
 
     def forward(self, *a, **k):
         raise NotImplementedError("VQVAE.forward is training-only in the reference and out of scope")

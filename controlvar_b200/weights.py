@@ -143,6 +143,31 @@ def decoder_plan(cfg: PathConfig):
     return plan
 
 
+def encoder_plan(cfg: PathConfig):
+    """Static walk of Encoder.forward (vae_modules.py:145-160) as (op, prefix, cin, cout) records; 'down' is
+    Downsample2x (vae_modules.py:31-37), 'out' is norm_out + SiLU + conv_out."""
+    ch, mult, nrb = cfg.vae_ch, cfg.vae_ch_mult, cfg.vae_num_res_blocks
+    nres = len(mult)
+    in_mult = (1,) + tuple(mult)
+    plan = [("conv_in", "encoder.conv_in", 3, ch)]
+    block_in = ch
+    for lvl in range(nres):
+        block_in = ch * in_mult[lvl]
+        block_out = ch * mult[lvl]
+        for ib in range(nrb):
+            plan.append(("res", f"encoder.down.{lvl}.block.{ib}.", block_in, block_out))
+            block_in = block_out
+            if lvl == nres - 1:
+                plan.append(("attn", f"encoder.down.{lvl}.attn.{ib}.", block_in, block_in))
+        if lvl != nres - 1:
+            plan.append(("down", f"encoder.down.{lvl}.downsample.conv", block_in, block_in))
+    plan.append(("res", "encoder.mid.block_1.", block_in, block_in))
+    plan.append(("attn", "encoder.mid.attn_1.", block_in, block_in))
+    plan.append(("res", "encoder.mid.block_2.", block_in, block_in))
+    plan.append(("out", "encoder.", block_in, cfg.Cvae))
+    return plan
+
+
 def vae_key_shapes(cfg: PathConfig, with_encoder: bool = True) -> "OrderedDict[str, Tuple[int, ...]]":
     ch, mult, nrb, z = cfg.vae_ch, cfg.vae_ch_mult, cfg.vae_num_res_blocks, cfg.Cvae
     nres = len(mult)

@@ -4,6 +4,9 @@
  * The reference (lxa9867/ControlVAR) has no plugin / FFI layer: its boundary is the Python method surface
  *   ControlVAR.autoregressive_infer_cfg      models/control_var.py:356-565
  *   VQVAE.fhat_to_img                        models/vqvae.py:88-89
+ * and, for pixel-level control,
+ *   ControlVAR.conditional_infer_cfg         models/control_var.py:223-354
+ *   VQVAE.img_to_idxBl                       models/vqvae.py:73-75, models/quant.py:184-215
  * (SURVEY.md section 8b).  The host mirror in controlvar_b200/ keeps those signatures and calls the entry points
  * below through ctypes.  Each entry point names the reference code it replaces.
  *
@@ -65,6 +68,12 @@ CVAR_API int cvar_lvl_pos(const float* lvl_embed, const int64_t* lvl_1L, const f
 CVAR_API int cvar_prologue(const float* class_emb, const float* cond_embed, const float* pos_start, const float* lvl_pos,
                   const int64_t* label_B, const int64_t* cond_type_B, int B, int C, int num_classes,
                   float* cond_BD, float* silu_cond, float* x0, void* stream);
+
+/* The same for explicit per-row ids: row r uses (label_R[r], cond_type_R[r]).  conditional_infer_cfg runs four guidance
+ * replicas [class+type | type only | none | none] (control_var.py:252-269); the host concatenates the ids. */
+CVAR_API int cvar_prologue_rows(const float* class_emb, const float* cond_embed, const float* pos_start,
+                       const float* lvl_pos, const int64_t* label_R, const int64_t* cond_type_R, int R, int C,
+                       float* cond_BD, float* silu_cond, float* x0, void* stream);
 
 /* ---- AdaLN-modulated LayerNorm: basic_var.py:208-209, control_var.py:699-701 ---------------------------------
  * y[m,:] = LayerNorm(x[m,:], eps, no affine) * (scale[r,:] + 1) + shift[r,:],  r = m / rows_per_sample.
@@ -149,6 +158,18 @@ CVAR_API int cvar_attn_kvcache(const float* q, const float* k_hi, const float* k
 CVAR_API int cvar_cfg_sample(const float* logits, const float* q_noise, int64_t* idx_out,
                     int B, int l, int V, double t, int top_k, double top_p, void* stream);
 
+/* Generalisation used by conditional_infer_cfg (control_var.py:288-321): logits (groups*B, l, V);
+ *   v = coef[0]*L_0 + coef[1]*L_1 + ... (each product rounded, summed left to right - the evaluation order of :295-298;
+ *   a subtracted term is passed with a negated coefficient, which is bit-identical in IEEE arithmetic);
+ * the masked distribution of row (b, t) is then sampled `replicas` times with independent noise rows
+ * (logits_BlV.repeat(repeat_num, 1, 1), :306-307): q_noise (replicas*B*l, V), idx_out (replicas*B, l).
+ * Teacher forcing (:309-321): for replicas g < forced_replicas, tokens t < l/2 are overwritten with
+ * forced_first[b, t] and tokens t >= l/2 with forced_second[b, t - l/2] (either may be NULL: keep the sample).
+ * coef (host pointer, `groups` floats, groups <= 4). */
+CVAR_API int cvar_cfg_sample_multi(const float* logits, const float* q_noise, int64_t* idx_out, int B, int l, int V,
+                          int groups, const float* host_coef, int replicas, int top_k, double top_p,
+                          const int64_t* forced_first, const int64_t* forced_second, int forced_replicas, void* stream);
+
 /* ---- multi-scale VQ step: control_var.py:512-560 + quant.py:243-270 ------------------------------------------
  * For sample b and stream s in {0: control, 1: image}:
  *   h  = embedding[idx[b, s*pn*pn + i], :] as a (32, pn, pn) map                      (control_var.py:512-524)
@@ -161,6 +182,18 @@ CVAR_API int cvar_vq_step(const int64_t* idx, const float* embedding, const floa
                  const float* word_w, const float* word_b, const float* lvl_pos_next,
                  float* f_hat, float* x_next, int B, int pn, int pn_next, int hw, int Cvae, int C, void* stream);
 
+/* General form.  streams: 2 = (control, image) halves stacked along H as above, 1 = a single (B, 32, hw, hw) map.
+ * x_replicas: how many row groups of x_next receive the result (2 = the CFG halves of autoregressive_infer_cfg, which
+ * repeats the map at control_var.py:560; 1 = conditional_infer_cfg, where every replica has its own f_hat).
+ * f_rest (optional, same layout as f_hat): the residual of the encoder-side quantiser, f_rest -= phi (quant.py:211). */
+CVAR_API int cvar_vq_step_ex(const int64_t* idx, const float* embedding, const float* U, const float* phi_w,
+                    const float* phi_b, const float* word_w, const float* word_b, const float* lvl_pos_next,
+                    float* f_hat, float* f_rest, float* x_next, int B, int streams, int x_replicas, int pn, int pn_next,
+                    int hw, int Cvae, int C, void* stream);
+/* z[(b*pn*pn + j), c] = area-pooled f[b, c, :, :] at bin j (F.interpolate(mode='area') = adaptive average pooling,
+ * quant.py:199), written as the (N, 32) row matrix cvar_vq_nearest consumes; pn == hw is a plain NCHW -> NHWC copy. */
+CVAR_API int cvar_area_pool_nc(const float* f_nchw, float* z_NC, int B, int Cvae, int hw, int pn, void* stream);
+
 /* L2 nearest code: quant.py:203-206.  idx[n] = argmin_v (|z_n|^2 + |e_v|^2 - 2 z_n.e_v), first index on ties. */
 CVAR_API int cvar_vq_nearest(const float* z_NC, const float* embedding, int64_t* idx_out, int N, int Cvae, int V, void* stream);
 
@@ -169,6 +202,9 @@ CVAR_API int cvar_vq_nearest(const float* z_NC, const float* embedding, int64_t*
 /* (B,C,H,W) -> (B,H,W,C) */
 CVAR_API int cvar_nchw_to_nhwc(const float* in, float* out, int B, int C, int H, int W,
                       long long in_batch_stride, void* stream);
+/* The same with the channel dimension zero-padded to Cpad >= C (the 3-channel image entering Encoder.conv_in runs as a
+ * 16-channel NHWC tensor; cvar_repack_conv_weight_pad pads the weight to match). */
+CVAR_API int cvar_nchw_to_nhwc_pad(const float* in, float* out, int B, int C, int H, int W, int Cpad, void* stream);
 /* GroupNorm statistics folded with the affine: a[n,c] = rstd[n,g]*gamma[c], b[n,c] = beta[c] - mean[n,g]*a[n,c],
  * so GroupNorm(x)[n,:,:,c] = x*a + b.  scratch: 2*B*groups*chunks doubles (chunks = cvar_gn_chunks(HW)). */
 CVAR_API int cvar_gn_chunks(int HW);
@@ -180,7 +216,8 @@ CVAR_API int cvar_gn_stats(const float* x_nhwc, const float* gamma, const float*
  * (B, Hout, Wout, Cout) with Hout = Hin * (upsample2x ? 2 : 1); resid (same shape as out) is added when not NULL.
  * out_mode 0: NHWC fp32.  out_mode 1: final image - clamp(-1,1), (v+1)*0.5, written NCHW into
  * out[n, c, row_offset + y, x] of a (B, Cout, out_rows_total, Wout) tensor   (vqvae.py:89, control_var.py:563-565).
- * out_mode 2: as 1 without the (v+1)*0.5 step (plain VQVAE.fhat_to_img). */
+ * out_mode 2: as 1 without the (v+1)*0.5 step (plain VQVAE.fhat_to_img).
+ * out_mode 3: NCHW planes as in 1, but neither clamp nor shift (quant_conv output for the quantiser, vqvae.py:74). */
 typedef struct {
   const float* x; const float* w; const float* w_hi; const float* w_lo; const float* bias; float* out;
   const float* in_a; const float* in_b; int in_silu;
@@ -194,6 +231,9 @@ typedef struct {
    * cvar_upsample2x_split_f16, cvar_split_f16): x, in_a, in_b, upsample2x must be NULL / 0.  w16_* is the pair of the
    * repacked weight.  Shapes: see cvar_conv2d_f16_supported. */
   const void* x16_hi; const void* x16_lo; const void* w16_hi; const void* w16_lo;
+  /* Downsample2x of the encoder (vae_modules.py:31-37): F.pad(x, (0,1,0,1)) + 3x3 conv with stride 2 and no padding.
+   * Output is (B, Hin/2, Win/2, Cout).  ks = 3, even Hin / Win, fp32 NHWC input; always on the SIMT fp32 engine. */
+  int downsample2x;
 } cvar_conv_args;
 CVAR_API int cvar_conv2d(const cvar_conv_args* args, void* stream);
 /* 1 when the FP16-pair kernel takes this layer: ks in {1,3}, Cin % 32 == 0, Cout a multiple of one of
@@ -212,6 +252,9 @@ CVAR_API int cvar_split_tf32(const float* w, float* w_hi, float* w_lo, long long
 CVAR_API int cvar_split_f16(const float* x, void* hi, void* lo, long long n, void* stream);
 /* (Cout,Cin,ks,ks) -> (Cout, ks*ks*Cin), k index = (ky*ks+kx)*Cin + ci */
 CVAR_API int cvar_repack_conv_weight(const float* w_oihw, float* w_out, int Cout, int Cin, int ks, void* stream);
+/* (Cout,Cin,ks,ks) -> (Cout, ks*ks*Cin_pad) with zero weights for the padding channels */
+CVAR_API int cvar_repack_conv_weight_pad(const float* w_oihw, float* w_out, int Cout, int Cin, int ks, int Cin_pad,
+                                void* stream);
 /* y = [silu](x*a[n,c] + b[n,c]): GroupNorm (+ SiLU) applied once (vae_modules.py:58-59, AttnBlock.norm).
  * y16_hi / y16_lo (optional, halves, same shape): the result as an FP16 pair; y may then be NULL. */
 CVAR_API int cvar_affine_nc(const float* x_nhwc, const float* a, const float* b, float* y, void* y16_hi, void* y16_lo,

@@ -276,5 +276,5 @@ def test_decoder_engine4_pixels_within_tolerance(engine4):
     torch.cuda.synchronize()
     ref = O.fhat_to_img(f_hat, vsd)
     e = (img.cpu() - ref).abs().max().item()
-    print(f"\n[f16x3-decoder] max pixel err {e:.3e} (tc_min_hw={vae.tc_min_hw}), launches {ops.launch_count() - n0}")
+    print(f"\n[f16x3-decoder] max pixel err {e:.3e} (tc_min_hw={vae._min_hw()}), launches {ops.launch_count() - n0}")
     assert e < 1e-4

@@ -17,7 +17,7 @@ vae.load_state_dict(vsd)
 torch.set_num_threads(os.cpu_count())
 if "CVAR_TC_MIN_HW" in os.environ:
     vae.tc_min_hw = int(os.environ["CVAR_TC_MIN_HW"])
-print(f"engine {ops.get_gemm_engine()}, tc_min_hw {vae.tc_min_hw}")
+print(f"engine {ops.get_gemm_engine()}, tc_min_hw {vae._min_hw()}")
 worst, means, n = 0.0, [], 0
 for seed in range(n_calls):
     B = 2

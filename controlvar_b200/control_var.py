@@ -97,6 +97,9 @@ class ControlVAR(nn.Module):
         # reference's stream on a GPU host; 'cpu' reproduces the stream of the reference run on CPU (used by the
         # parity tests against the CPU oracle): the Exp(1) noise is then drawn on the host and copied over.
         self.rng_device = "cuda"
+        # engine 4 only: q / K / V^T as FP16 pairs end to end (cvar_qkv_project16 + cvar_attn_kvcache16) instead of
+        # fp32 q + TF32-split cache + 3xTF32 attention.  Half the KV arena, twice the attention MMA rate.
+        self.kv16 = True
         self._rng: Optional[torch.Generator] = None
         self._ws: Dict[Tuple, torch.Tensor] = {}
         self._consts: Dict[str, object] = {}
@@ -146,11 +149,24 @@ class ControlVAR(nn.Module):
         key = ("kv", depth, R, H, T)
         c = self._ws.get(key)
         if c is None or c[0].k_hi.device != self.device:
-            for k in [k for k in self._ws if isinstance(k, tuple) and k and k[0] == "kv"]:
+            for k in [k for k in self._ws if isinstance(k, tuple) and k and k[0] in ("kv", "kv16")]:
                 del self._ws[k]
             n = ops.KVCache.numel(R, H, T)
             arena = torch.zeros(depth * n, dtype=torch.float32, device=self.device)
             c = [ops.KVCache(R, H, T, self.device, arena[i * n:(i + 1) * n]) for i in range(depth)]
+            self._ws[key] = c
+        return c
+
+    def _kv_caches16(self, depth, R, H, T):
+        """The same arena as FP16 pairs (engine 4 with kv16): half the bytes of the TF32 split."""
+        key = ("kv16", depth, R, H, T)
+        c = self._ws.get(key)
+        if c is None or c[0].k_hi.device != self.device:
+            for k in [k for k in self._ws if isinstance(k, tuple) and k and k[0] in ("kv", "kv16")]:
+                del self._ws[k]
+            n = ops.KVCache16.numel(R, H, T)
+            arena = torch.zeros(depth * n, dtype=torch.float16, device=self.device)
+            c = [ops.KVCache16(R, H, T, self.device, arena[i * n:(i + 1) * n]) for i in range(depth)]
             self._ws[key] = c
         return c
 
@@ -327,9 +343,11 @@ class ControlVAR(nn.Module):
         ada = self._buf("ada", (depth, R, 6 * C))
         ada_head = self._buf("ada_head", (R, 2 * C))
         x = self._buf("x", (R * lmax, C))
-        qbuf = self._buf("q", (R * H * lmax * 64,))
         # engine 4 (f16x3): every dense-layer input is produced as an FP16 pair and never exists in fp32
         f16 = cst["f16"]
+        kv16 = f16 and self.kv16
+        qbuf = None if kv16 else self._buf("q", (R * H * lmax * 64,))
+        q16 = self._pair("q16", (R * H * lmax * 64,)) if kv16 else None
         xn16 = self._pair("xn16", (R * lmax, C)) if f16 else None
         attn_o16 = self._pair("attn_o16", (R * lmax, C)) if f16 else None
         hid16 = self._pair("hid16", (R * lmax, 4 * C)) if f16 else None
@@ -343,7 +361,7 @@ class ControlVAR(nn.Module):
         hid_lo = self._buf("hid_lo", (R * lmax, 4 * C)) if split else None
         logits = self._buf("logits", (R * lmax, V))
         idx = self._buf("idx", (Bf * lmax,), torch.int64)
-        caches = self._kv_caches(depth, R, H, T)
+        caches = self._kv_caches16(depth, R, H, T) if kv16 else self._kv_caches(depth, R, H, T)
         f_hat = self._buf("f_hat", (Bf, Cvae, 2 * hw, hw))
         f_hat.zero_()
 
@@ -368,9 +386,15 @@ class ControlVAR(nn.Module):
                 a = ada[bi]                                # (R, 6C): gamma1, gamma2, scale1, scale2, shift1, shift2
                 g1, g2, s1, s2, b1, b2 = (a[:, k * C:(k + 1) * C] for k in range(6))
                 ops.ln_modulate(x, s1, b1, 6 * C, xn, M, C, l, self.norm_eps, out_lo=xn_lo, out16=xn16)
-                ops.qkv_project(xn, blk["qkv_w"], blk["q_bias"], blk["k_bias"], blk["v_bias"], qbuf, caches[bi],
-                                R, l, L_prev, H, self.cos_attn, blk["scale_mul"], A_lo=xn_lo, A16=xn16)
-                ops.attn_kvcache(qbuf, caches[bi], attn_o, R, H, l, cur_L, attn_scale, out_lo=attn_o_lo, out16=attn_o16)
+                if kv16:
+                    ops.qkv_project16(xn16, blk["qkv_w"], blk["q_bias"], blk["k_bias"], blk["v_bias"], q16, caches[bi],
+                                      R, l, L_prev, H, self.cos_attn, blk["scale_mul"])
+                    ops.attn_kvcache16(q16, caches[bi], None, R, H, l, cur_L, attn_scale, out16=attn_o16)
+                else:
+                    ops.qkv_project(xn, blk["qkv_w"], blk["q_bias"], blk["k_bias"], blk["v_bias"], qbuf, caches[bi],
+                                    R, l, L_prev, H, self.cos_attn, blk["scale_mul"], A_lo=xn_lo, A16=xn16)
+                    ops.attn_kvcache(qbuf, caches[bi], attn_o, R, H, l, cur_L, attn_scale, out_lo=attn_o_lo,
+                                     out16=attn_o16)
                 ops.gemm(attn_o, blk["proj_w"], blk["proj_b"], x, M, C, C, A_lo=attn_o_lo, A16=attn_o16,
                          epilogue=ops.EPI_BIAS_GAMMA_RESID, gamma=g1, gamma_row_stride=6 * C, rows_per_sample=l)
                 ops.ln_modulate(x, s2, b2, 6 * C, xn, M, C, l, self.norm_eps, out_lo=xn_lo, out16=xn16)

@@ -1,0 +1,599 @@
+// KV-cached attention on FP16-pair operands (engine 4): basic_var.py:106-117, same contract as attn.cu.
+//
+// q, K and V^T arrive as FP16 pairs (x ~= hi + lo * 2^-11, cvar_split_f16) written by cvar_qkv_project16, i.e. half the
+// bytes of the TF32 hi/lo split the first tensor-core kernel used, and the products run as three kind::f16 MMAs
+// (hi*hi into a main accumulator; hi*lo + lo*hi into a cross accumulator that is folded in with one FMA) at twice the
+// TF32 tensor rate.  Design of the tensor-core kernel (attn16_tc_kernel):
+//   * CTA = 128 queries of one (row, head), 192 threads, and TWO CTAs per SM: everything is sized to half an SM
+//     (256 TMEM columns, 97 KB shared memory, <= 168 registers), so the softmax of one CTA overlaps the MMAs of the other.
+//     The measured limiter of the TF32 kernel was the softmax warpgroup (~3100 cycles per 64-key tile against 1536 of
+//     MMA, profiles/r01_attn_trace.md), and its 448 TMEM columns / 255 registers allowed one CTA per SM only.
+//   * Q tile (128 x 64, hi and lo) and the K / V^T tiles (64 x 64) are fetched by TMA straight from the pair arrays:
+//     one 128-byte-swizzled block each, no operand conversion anywhere.
+//   * S = Q K^T lands in TMEM (main + cross); the softmax thread (one per query row) reads it in 16-column chunks, writes
+//     P back as an FP16 pair OVER the S_main columns it has just consumed (chunk c: hi in columns [16c, 16c+8), lo in
+//     [16c+8, 16c+16), two keys per 32-bit cell) and P @ V reads its A operand from there.  tcgen05.mma executes in issue
+//     order, so S(j+1), issued after P@V(j), may overwrite those columns.
+//   * The running output row lives in registers (round-to-nearest adds); every tile's O_tile is a fresh accumulation of
+//     12 MMA steps, so the tensor core's truncating accumulation never runs long.
+//   TMEM columns: S_main/P [0,64)  S_x [64,128)  O_main [128,192)  O_x [192,256)
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+using namespace cvar;
+
+namespace {
+constexpr float kInvLo = 1.0f / kF16LoScale;
+
+__device__ __forceinline__ float pair_val(__half h, __half l) { return fmaf(__half2float(l), kInvLo, __half2float(h)); }
+// four consecutive elements of a pair array (8-byte aligned)
+__device__ __forceinline__ float4 ld4_pair(const __half* hi, const __half* lo, long long off) {
+  const uint2 a = *reinterpret_cast<const uint2*>(hi + off), b = *reinterpret_cast<const uint2*>(lo + off);
+  const __half2 a0 = *reinterpret_cast<const __half2*>(&a.x), a1 = *reinterpret_cast<const __half2*>(&a.y);
+  const __half2 b0 = *reinterpret_cast<const __half2*>(&b.x), b1 = *reinterpret_cast<const __half2*>(&b.y);
+  return make_float4(pair_val(__low2half(a0), __low2half(b0)), pair_val(__high2half(a0), __high2half(b0)),
+                     pair_val(__low2half(a1), __low2half(b1)), pair_val(__high2half(a1), __high2half(b1)));
+}
+
+// ---------------------------------------------------------------------------------------------------- SIMT kernel
+// The fp32 flash-style kernel of attn.cu reading the pair format: serves l < 64 and is the cross-check of the
+// tensor-core kernel.  One CTA = 64 queries of one (row, head).
+constexpr int BQ = 64, BKV = 64, D = 64;
+constexpr int PS = 68;
+
+struct AttnSmem {
+  float Qt[D][BQ];
+  float Kt[D][BKV];
+  float V[BKV][D];
+  float Pt[BKV][PS];
+};
+
+__global__ void __launch_bounds__(256)
+attn16_simt_kernel(const __half* __restrict__ q_hi, const __half* __restrict__ q_lo, const __half* __restrict__ k_hi,
+                   const __half* __restrict__ k_lo, const __half* __restrict__ vt_hi, const __half* __restrict__ vt_lo,
+                   float* __restrict__ out, __half* __restrict__ o16_hi, __half* __restrict__ o16_lo, int H, int l, int L,
+                   int T_max, float scale) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  AttnSmem& sm = *reinterpret_cast<AttnSmem*>(smem_raw);
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int q0 = blockIdx.x * BQ, h = blockIdx.y, r = blockIdx.z;
+  const long long rh = (long long)r * H + h;
+  const long long q_off = rh * l * D;
+  const long long kv_off = rh * T_max * D;
+
+  for (int it = 0; it < 4; ++it) {
+    int item = it * 256 + tid;
+    int i = item & 63, dq = item >> 6;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q0 + i < l) v = ld4_pair(q_hi, q_lo, q_off + (long long)(q0 + i) * D + dq * 4);
+    sm.Qt[dq * 4 + 0][i] = v.x * scale;
+    sm.Qt[dq * 4 + 1][i] = v.y * scale;
+    sm.Qt[dq * 4 + 2][i] = v.z * scale;
+    sm.Qt[dq * 4 + 3][i] = v.w * scale;
+  }
+
+  float o[4][4];
+  float mrow[4], lrow[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    mrow[i] = -INFINITY;
+    lrow[i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
+  }
+
+  for (int k0 = 0; k0 < L; k0 += BKV) {
+    __syncthreads();
+    for (int it = 0; it < 4; ++it) {
+      int item = it * 256 + tid;
+      int j = item & 63, dq = item >> 6;
+      float4 kv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k0 + j < L) kv = ld4_pair(k_hi, k_lo, kv_off + (long long)(k0 + j) * D + dq * 4);
+      sm.Kt[dq * 4 + 0][j] = kv.x;
+      sm.Kt[dq * 4 + 1][j] = kv.y;
+      sm.Kt[dq * 4 + 2][j] = kv.z;
+      sm.Kt[dq * 4 + 3][j] = kv.w;
+    }
+    for (int it = 0; it < 4; ++it) {
+      int item = it * 256 + tid;
+      int d = item >> 4, jq = item & 15;
+      const long long base = kv_off + (long long)d * T_max + k0 + jq * 4;
+      float vv[4] = {0.f, 0.f, 0.f, 0.f};
+      if (k0 + jq * 4 + 3 < T_max) {          // T_max % 8 == 0 and k0 % 64 == 0: the 8-byte load is aligned
+        float4 t4 = ld4_pair(vt_hi, vt_lo, base);
+        vv[0] = t4.x, vv[1] = t4.y, vv[2] = t4.z, vv[3] = t4.w;
+      } else {
+        for (int i = 0; i < 4; ++i)
+          if (k0 + jq * 4 + i < T_max) vv[i] = pair_val(vt_hi[base + i], vt_lo[base + i]);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        int j = jq * 4 + i;
+        sm.V[j][(((d >> 2) ^ (j & 15)) << 2) + (d & 3)] = (k0 + j < L) ? vv[i] : 0.f;
+      }
+    }
+    __syncthreads();
+
+    float s[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
+#pragma unroll 8
+    for (int d = 0; d < D; ++d) {
+      float4 a = *reinterpret_cast<const float4*>(&sm.Qt[d][ty * 4]);
+      float b0 = sm.Kt[d][tx], b1 = sm.Kt[d][16 + tx], b2 = sm.Kt[d][32 + tx], b3 = sm.Kt[d][48 + tx];
+      s[0][0] = fmaf(a.x, b0, s[0][0]), s[0][1] = fmaf(a.x, b1, s[0][1]), s[0][2] = fmaf(a.x, b2, s[0][2]), s[0][3] = fmaf(a.x, b3, s[0][3]);
+      s[1][0] = fmaf(a.y, b0, s[1][0]), s[1][1] = fmaf(a.y, b1, s[1][1]), s[1][2] = fmaf(a.y, b2, s[1][2]), s[1][3] = fmaf(a.y, b3, s[1][3]);
+      s[2][0] = fmaf(a.z, b0, s[2][0]), s[2][1] = fmaf(a.z, b1, s[2][1]), s[2][2] = fmaf(a.z, b2, s[2][2]), s[2][3] = fmaf(a.z, b3, s[2][3]);
+      s[3][0] = fmaf(a.w, b0, s[3][0]), s[3][1] = fmaf(a.w, b1, s[3][1]), s[3][2] = fmaf(a.w, b2, s[3][2]), s[3][3] = fmaf(a.w, b3, s[3][3]);
+    }
+    float p[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (k0 + j * 16 + tx >= L) s[i][j] = -INFINITY;
+        mx = fmaxf(mx, s[i][j]);
+      }
+#pragma unroll
+      for (int off = 8; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+      float mnew = fmaxf(mrow[i], mx);
+      float corr = expf(mrow[i] - mnew);
+      float rs = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        p[i][j] = expf(s[i][j] - mnew);
+        rs += p[i][j];
+      }
+#pragma unroll
+      for (int off = 8; off > 0; off >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, off);
+      lrow[i] = lrow[i] * corr + rs;
+      mrow[i] = mnew;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[i][j] *= corr;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      *reinterpret_cast<float4*>(&sm.Pt[j * 16 + tx][ty * 4]) = make_float4(p[0][j], p[1][j], p[2][j], p[3][j]);
+    __syncthreads();
+#pragma unroll 8
+    for (int j = 0; j < BKV; ++j) {
+      float4 a = *reinterpret_cast<const float4*>(&sm.Pt[j][ty * 4]);
+      float4 b = *reinterpret_cast<const float4*>(&sm.V[j][(tx ^ (j & 15)) << 2]);
+      o[0][0] = fmaf(a.x, b.x, o[0][0]), o[0][1] = fmaf(a.x, b.y, o[0][1]), o[0][2] = fmaf(a.x, b.z, o[0][2]), o[0][3] = fmaf(a.x, b.w, o[0][3]);
+      o[1][0] = fmaf(a.y, b.x, o[1][0]), o[1][1] = fmaf(a.y, b.y, o[1][1]), o[1][2] = fmaf(a.y, b.z, o[1][2]), o[1][3] = fmaf(a.y, b.w, o[1][3]);
+      o[2][0] = fmaf(a.z, b.x, o[2][0]), o[2][1] = fmaf(a.z, b.y, o[2][1]), o[2][2] = fmaf(a.z, b.z, o[2][2]), o[2][3] = fmaf(a.z, b.w, o[2][3]);
+      o[3][0] = fmaf(a.w, b.x, o[3][0]), o[3][1] = fmaf(a.w, b.y, o[3][1]), o[3][2] = fmaf(a.w, b.z, o[3][2]), o[3][3] = fmaf(a.w, b.w, o[3][3]);
+    }
+  }
+
+  const int C = H * D;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int t = q0 + ty * 4 + i;
+    if (t < l) {
+      float inv = 1.0f / lrow[i];
+      const float vv[4] = {o[i][0] * inv, o[i][1] * inv, o[i][2] * inv, o[i][3] * inv};
+      const long long off = ((long long)r * l + t) * C + h * D + tx * 4;
+      if (o16_hi != nullptr) st4_split_f16(o16_hi + off, o16_lo + off, vv);
+      if (out != nullptr) st4(out + off, make_float4(vv[0], vv[1], vv[2], vv[3]));
+    }
+  }
+}
+}  // namespace
+
+// ============================================================================================== tensor-core kernel
+namespace tcattn16 {
+using namespace cvar::tc;
+constexpr int BQ = 128, BKV = 64, D = 64;
+constexpr int kThreads = 192;
+constexpr int kTile = BKV * 128;                  // 64 rows x 128 B: one K or V^T tile half (hi or lo), 8 KB
+constexpr int kQTile = BQ * 128;                  // 128 rows x 128 B: Q hi or lo, 16 KB
+constexpr int kStageBytes = 4 * kTile;            // K_hi | K_lo | VT_hi | VT_lo = 32 KB
+constexpr int kStages = 2;
+constexpr int kSmem = 1024 + 2 * kQTile + kStages * kStageBytes + 256;     // 99,584 B: two CTAs per SM
+constexpr uint32_t kColS = 0, kColSx = 64, kColO = 128, kColOx = 192, kTmemCols = 256;
+// D fp32 (bit 4), A / B format 0 = F16, both K-major, N = 64, M = 128
+constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+// A and B from shared memory
+__device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// A from tensor memory (two halves per 32-bit cell, 8 cells per 16-wide k-step), B from shared memory
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]),
+               "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// TMEM loads WITHOUT the wait: the destination registers are valid only after tmem_wait_ld()
+__device__ __forceinline__ void tmem_ld_nowait_x16(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_nowait_x32(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+// Compiler-level dependency: values loaded by a *_nowait load may only be used after the wait.  The wait is a volatile asm
+// without register operands, so plain arithmetic on the loaded registers could legally be scheduled above it; these empty
+// volatile asms (ordered after the wait) re-define the registers and pin every use behind it.
+__device__ __forceinline__ void reg_fence16(float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                    "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :: "memory");
+}
+__device__ __forceinline__ void reg_fence32(float* v) {
+  reg_fence16(v);
+  reg_fence16(v + 16);
+}
+__device__ __forceinline__ void tmem_alloc_n(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// two fp32 values -> one 32-bit cell of halves: `first` (the lower key index) goes to the low 16 bits unless swapped
+__device__ __forceinline__ uint32_t pack_h2(__half first, __half second, int swap) {
+  const uint32_t a = __half_as_ushort(first), b = __half_as_ushort(second);
+  return swap ? (b | (a << 16)) : (a | (b << 16));
+}
+
+__global__ void __launch_bounds__(kThreads, 2)
+attn16_tc_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_constant__ CUtensorMap mapQlo,
+                 const __grid_constant__ CUtensorMap mapKhi, const __grid_constant__ CUtensorMap mapKlo,
+                 const __grid_constant__ CUtensorMap mapVhi, const __grid_constant__ CUtensorMap mapVlo,
+                 float* __restrict__ out, __half* __restrict__ o16_hi, __half* __restrict__ o16_lo, int H, int l, int L,
+                 float scale, int pack_swap) {
+  using G = Geo<32>;          // 128-byte rows, SWIZZLE_128B: 64 halves per row
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* q_s = smem;                                        // Q_hi | Q_lo
+  auto stage = [&](int s) { return smem + 2 * kQTile + s * kStageBytes; };
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kQTile + kStages * kStageBytes);
+  uint64_t* kv_full = bars;                  // [kStages]
+  uint64_t* kv_empty = bars + kStages;       // [kStages]
+  uint64_t* q_full = bars + 2 * kStages;
+  uint64_t* s_full = bars + 2 * kStages + 1; // S(j) accumulated
+  uint64_t* p_ready = bars + 2 * kStages + 2;// P(j) in TMEM and O_tile(j-1) read, by all 128 softmax threads
+  uint64_t* o_full = bars + 2 * kStages + 3; // O_tile(j) accumulated
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * BQ, h = blockIdx.y, r = blockIdx.z;
+  const int rh = r * H + h;
+  const int ntiles = (L + BKV - 1) / BKV;
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&mapQhi), tma_prefetch_desc(&mapQlo);
+    tma_prefetch_desc(&mapKhi), tma_prefetch_desc(&mapKlo), tma_prefetch_desc(&mapVhi), tma_prefetch_desc(&mapVlo);
+    for (int s = 0; s < kStages; ++s) mbar_init(&kv_full[s], 1), mbar_init(&kv_empty[s], 1);
+    mbar_init(q_full, 1);
+    mbar_init(s_full, 1);
+    mbar_init(p_ready, 128);
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 5) tmem_alloc_n(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ================================================================ softmax + output rows
+    const int row = threadIdx.x;
+    const uint32_t tl = tmem_base + ((uint32_t)(warp * 32) << 16);
+    // p = exp((s - m) * scale) = 2^((s - m) * scale * log2 e): the difference is formed first (exact or nearly so for the
+    // terms that matter), so the rounding of the product is a relative error of |t| * 2^-24 on terms of weight e^t
+    const float sl2 = scale * 1.4426950408889634f;
+    float o_reg[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) o_reg[d] = 0.f;
+    float m_run = -INFINITY, l_run = 0.f;
+    for (int j = 0; j < ntiles; ++j) {
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      const int kbase = j * BKV;
+      // Every tcgen05.ld -> wait::ld pair exposes the TMEM round trip to a warp that has only one partner on its
+      // scheduler, so loads are batched (one wait per batch) and the chunks of pass 2 are prefetched one ahead.
+      // pass 1: row maximum from S_main alone.  The cross accumulator is ~2^-11 of it: the reference point of the
+      // exponentials need not be the exact maximum (p may exceed 1 by ~1e-3; l_run uses the same reference).
+      float mx = -INFINITY;
+      {
+        float a[32], b[32];
+        tmem_ld_nowait_x32(tl + kColS, a);
+        tmem_ld_nowait_x32(tl + kColS + 32, b);
+        tmem_wait_ld();
+        reg_fence32(a), reg_fence32(b);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if (kbase + i < L) mx = fmaxf(mx, a[i]);
+          if (kbase + 32 + i < L) mx = fmaxf(mx, b[i]);
+        }
+      }
+      const float m_new = fmaxf(m_run, mx);            // every tile holds at least one valid key: finite
+      const float corr = ex2_approx((m_run - m_new) * sl2);   // 0 on the first tile (m_run = -inf)
+      // O_tile(j-1) -> registers (round-to-nearest adds), rescaled to the new reference.  It is complete: the commit
+      // behind s_full(j) covers P @ V(j-1), which was issued before S(j).
+      if (j > 0) {
+        mbar_wait(o_full, (j - 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          float a[32], b[32];
+          tmem_ld_nowait_x32(tl + kColO + 32 * hf, a);
+          tmem_ld_nowait_x32(tl + kColOx + 32 * hf, b);
+          tmem_wait_ld();
+          reg_fence32(a), reg_fence32(b);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o_reg[32 * hf + i] = (o_reg[32 * hf + i] + fmaf(b[i], kInvLo, a[i])) * corr;
+        }
+      }
+      // pass 2: p = exp((s - m) * scale), written back over S_main as an FP16 pair (the A operand of P @ V)
+      float rs = 0.f;
+      float a0[16], b0[16], a1[16], b1[16];
+      auto chunk = [&](int c, const float* a, const float* b) {
+        uint32_t ph[8], pl[8];
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) {
+          float p0 = 0.f, p1 = 0.f;
+          if (kbase + 16 * c + i < L) p0 = ex2_approx((fmaf(b[i], kInvLo, a[i]) - m_new) * sl2);
+          if (kbase + 16 * c + i + 1 < L) p1 = ex2_approx((fmaf(b[i + 1], kInvLo, a[i + 1]) - m_new) * sl2);
+          rs += p0 + p1;
+          const __half h0 = __float2half_rn(p0), h1 = __float2half_rn(p1);
+          const __half l0 = __float2half_rn((p0 - __half2float(h0)) * kF16LoScale);
+          const __half l1 = __float2half_rn((p1 - __half2float(h1)) * kF16LoScale);
+          ph[i >> 1] = pack_h2(h0, h1, pack_swap);
+          pl[i >> 1] = pack_h2(l0, l1, pack_swap);
+        }
+        tmem_st_32x32b_x8(tl + kColS + 16 * c, ph);
+        tmem_st_32x32b_x8(tl + kColS + 16 * c + 8, pl);
+      };
+      tmem_ld_nowait_x16(tl + kColS, a0);
+      tmem_ld_nowait_x16(tl + kColSx, b0);
+      tmem_wait_ld();
+      reg_fence16(a0), reg_fence16(b0);
+      tmem_ld_nowait_x16(tl + kColS + 16, a1);
+      tmem_ld_nowait_x16(tl + kColSx + 16, b1);
+      chunk(0, a0, b0);
+      tmem_wait_ld();
+      reg_fence16(a1), reg_fence16(b1);
+      tmem_ld_nowait_x16(tl + kColS + 32, a0);
+      tmem_ld_nowait_x16(tl + kColSx + 32, b0);
+      chunk(1, a1, b1);
+      tmem_wait_ld();
+      reg_fence16(a0), reg_fence16(b0);
+      tmem_ld_nowait_x16(tl + kColS + 48, a1);
+      tmem_ld_nowait_x16(tl + kColSx + 48, b1);
+      chunk(2, a0, b0);
+      tmem_wait_ld();
+      reg_fence16(a1), reg_fence16(b1);
+      chunk(3, a1, b1);
+      l_run = l_run * corr + rs;
+      m_run = m_new;
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(p_ready);
+    }
+    mbar_wait(o_full, (ntiles - 1) & 1);
+    tc_fence_after();
+    const int t = q0 + row;
+    const float inv = 1.0f / l_run;
+    const long long off = ((long long)r * l + t) * (H * D) + h * D;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float a[16], b[16];
+      tmem_ld_32x32b_x16(tl + kColO + 16 * c, a);
+      tmem_ld_32x32b_x16(tl + kColOx + 16 * c, b);
+      if (t < l) {
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+          float vv[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) vv[e] = (o_reg[16 * c + i + e] + fmaf(b[i + e], kInvLo, a[i + e])) * inv;
+          if (o16_hi != nullptr) st4_split_f16(o16_hi + off + 16 * c + i, o16_lo + off + 16 * c + i, vv);
+          if (out != nullptr) st4(out + off + 16 * c + i, make_float4(vv[0], vv[1], vv[2], vv[3]));
+        }
+      }
+    }
+  } else if (warp == 4) {
+    // ================================================================ TMA: the Q tile once, then K / V^T tiles
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, (uint32_t)(2 * kQTile));
+      tma_load_3d(&mapQhi, q_full, q_s, 0, q0, rh);
+      tma_load_3d(&mapQlo, q_full, q_s + kQTile, 0, q0, rh);
+      for (int j = 0; j < ntiles; ++j) {
+        const int s = j % kStages;
+        mbar_wait(&kv_empty[s], ((j / kStages) & 1) ^ 1);
+        mbar_arrive_expect_tx(&kv_full[s], (uint32_t)kStageBytes);
+        unsigned char* st = stage(s);
+        tma_load_3d(&mapKhi, &kv_full[s], st + 0 * kTile, 0, j * BKV, rh);
+        tma_load_3d(&mapKlo, &kv_full[s], st + 1 * kTile, 0, j * BKV, rh);
+        tma_load_3d(&mapVhi, &kv_full[s], st + 2 * kTile, j * BKV, 0, rh);
+        tma_load_3d(&mapVlo, &kv_full[s], st + 3 * kTile, j * BKV, 0, rh);
+      }
+    }
+  } else {
+    // ================================================================ MMA issue
+    if (lane == 0) {
+      const uint64_t dqh = G::desc(smem_u32(q_s)), dql = G::desc(smem_u32(q_s + kQTile));
+      auto issue_S = [&](int j) {
+        unsigned char* st = stage(j % kStages);
+        const uint64_t dkh = G::desc(smem_u32(st)), dkl = G::desc(smem_u32(st + kTile));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {                       // 16 head dims (32 bytes of a row) per MMA
+          const uint64_t adv = (uint64_t)(2 * k);
+          umma_f16_ss(tmem_base + kColSx, dql + adv, dkh + adv, kIdesc, k != 0);
+          umma_f16_ss(tmem_base + kColSx, dqh + adv, dkl + adv, kIdesc, 1u);
+          umma_f16_ss(tmem_base + kColS, dqh + adv, dkh + adv, kIdesc, k != 0);
+        }
+        umma_commit(s_full);
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(&kv_full[0], 0);
+      tc_fence_after();
+      issue_S(0);
+      for (int j = 0; j < ntiles; ++j) {
+        mbar_wait(p_ready, j & 1);
+        tc_fence_after();
+        unsigned char* st = stage(j % kStages);
+        const uint64_t dvh = G::desc(smem_u32(st + 2 * kTile)), dvl = G::desc(smem_u32(st + 3 * kTile));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {                       // 16 keys per MMA: P cells [16k, 16k+8) hi, [16k+8, 16k+16) lo
+          const uint64_t adv = (uint64_t)(2 * k);
+          const uint32_t p_hi = tmem_base + kColS + 16 * k, p_lo = p_hi + 8;
+          umma_f16_ts(tmem_base + kColOx, p_lo, dvh + adv, kIdesc, k != 0);
+          umma_f16_ts(tmem_base + kColOx, p_hi, dvl + adv, kIdesc, 1u);
+          umma_f16_ts(tmem_base + kColO, p_hi, dvh + adv, kIdesc, k != 0);
+        }
+        umma_commit(o_full);
+        umma_commit(&kv_empty[j % kStages]);
+        if (j + 1 < ntiles) {
+          // in-order execution of tcgen05.mma: S(j+1) overwrites the P(j) cells only after P @ V(j) has read them
+          mbar_wait(&kv_full[(j + 1) % kStages], ((j + 1) / kStages) & 1);
+          tc_fence_after();
+          issue_S(j + 1);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+// 3-D map over a pair array of halves: dims (inner, mid, RH), box (64, box_mid, 1), 128-byte swizzle
+static int make_map3(CUtensorMap* map, const void* base, long long inner, long long mid, long long rh, int box_mid) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("cvar_attn_kvcache16: cuTensorMapEncodeTiled is not available from the driver");
+    return -3;
+  }
+  cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)mid, (cuuint64_t)rh};
+  cuuint64_t strides[2] = {(cuuint64_t)inner * 2, (cuuint64_t)inner * mid * 2};
+  cuuint32_t box[3] = {64, (cuuint32_t)box_mid, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult rc = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) {
+    set_error("cvar_attn_kvcache16: cuTensorMapEncodeTiled failed with %d", (int)rc);
+    return -3;
+  }
+  return 0;
+}
+// which half of a 32-bit TMEM cell holds the lower k index of a 16-bit A operand: 0 = low bits (default)
+static int pack_swap() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CVAR_ATTN16_PACK_SWAP");
+    v = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  return v;
+}
+}  // namespace tcattn16
+
+extern "C" int cvar_attn_kvcache16(const void* q16_hi, const void* q16_lo, const void* k16_hi, const void* k16_lo,
+                                   const void* vt16_hi, const void* vt16_lo, float* out, void* out16_hi, void* out16_lo,
+                                   int R, int H, int l, int L, int T_max, float scale, int engine, void* stream) {
+  CVAR_REQUIRE(q16_hi && q16_lo && k16_hi && k16_lo && vt16_hi && vt16_lo, "cvar_attn_kvcache16: null operand");
+  CVAR_REQUIRE(out != nullptr || out16_hi != nullptr, "cvar_attn_kvcache16: no output");
+  CVAR_REQUIRE((out16_hi == nullptr) == (out16_lo == nullptr), "cvar_attn_kvcache16: out16_hi/out16_lo must come together");
+  CVAR_REQUIRE(R > 0 && H > 0 && l > 0 && L >= l && L <= T_max, "cvar_attn_kvcache16: bad shape l=%d L=%d T=%d", l, L,
+               T_max);
+  CVAR_REQUIRE(R <= 65535 && H <= 65535, "cvar_attn_kvcache16: grid too large");
+  CVAR_REQUIRE(T_max % 8 == 0, "cvar_attn_kvcache16: T_max must be a multiple of 8 (got %d)", T_max);
+  const __half* qh = reinterpret_cast<const __half*>(q16_hi);
+  const __half* ql = reinterpret_cast<const __half*>(q16_lo);
+  const __half* kh = reinterpret_cast<const __half*>(k16_hi);
+  const __half* kl = reinterpret_cast<const __half*>(k16_lo);
+  const __half* vh = reinterpret_cast<const __half*>(vt16_hi);
+  const __half* vl = reinterpret_cast<const __half*>(vt16_lo);
+  __half* o16h = reinterpret_cast<__half*>(out16_hi);
+  __half* o16l = reinterpret_cast<__half*>(out16_lo);
+  if (engine < 0) engine = (g_gemm_engine != 0 && l >= 64) ? 1 : 0;
+  if (engine == 1) {
+    CUtensorMap mqh, mql, mkh, mkl, mvh, mvl;
+    const long long RH = (long long)R * H;
+    int rc = tcattn16::make_map3(&mqh, qh, 64, l, RH, tcattn16::BQ);
+    if (!rc) rc = tcattn16::make_map3(&mql, ql, 64, l, RH, tcattn16::BQ);
+    if (!rc) rc = tcattn16::make_map3(&mkh, kh, 64, T_max, RH, tcattn16::BKV);
+    if (!rc) rc = tcattn16::make_map3(&mkl, kl, 64, T_max, RH, tcattn16::BKV);
+    if (!rc) rc = tcattn16::make_map3(&mvh, vh, T_max, 64, RH, 64);
+    if (!rc) rc = tcattn16::make_map3(&mvl, vl, T_max, 64, RH, 64);
+    if (rc) return rc;
+    cudaError_t e = cudaFuncSetAttribute(tcattn16::attn16_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         tcattn16::kSmem);
+    CVAR_REQUIRE(e == cudaSuccess, "cvar_attn_kvcache16: cannot raise shared memory: %s", cudaGetErrorString(e));
+    dim3 grid(cdiv(l, tcattn16::BQ), H, R);
+    tcattn16::attn16_tc_kernel<<<grid, tcattn16::kThreads, tcattn16::kSmem, (cudaStream_t)stream>>>(
+        mqh, mql, mkh, mkl, mvh, mvl, out, o16h, o16l, H, l, L, scale, tcattn16::pack_swap());
+    CVAR_CHECK_LAUNCH("cvar_attn_kvcache16[tc]");
+    return 0;
+  }
+  cudaError_t e = cudaFuncSetAttribute(attn16_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sizeof(AttnSmem));
+  CVAR_REQUIRE(e == cudaSuccess, "cvar_attn_kvcache16: cannot raise shared memory: %s", cudaGetErrorString(e));
+  dim3 grid(cdiv(l, BQ), H, R);
+  attn16_simt_kernel<<<grid, 256, sizeof(AttnSmem), (cudaStream_t)stream>>>(qh, ql, kh, kl, vh, vl, out, o16h, o16l, H, l,
+                                                                           L, T_max, scale);
+  CVAR_CHECK_LAUNCH("cvar_attn_kvcache16");
+  return 0;
+}

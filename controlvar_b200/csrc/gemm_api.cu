@@ -146,6 +146,68 @@ extern "C" int cvar_qkv_project(const float* A, const float* A_lo, const void* A
   return 0;
 }
 
+// F.normalize(q).mul(scale_mul), F.normalize(k) on the FP16-pair form                    basic_var.py:99-104
+__global__ void cos_attn_normalize16_kernel(__half* __restrict__ q_hi, __half* __restrict__ q_lo,
+                                            __half* __restrict__ k_hi, __half* __restrict__ k_lo,
+                                            const float* __restrict__ sm, int R, int H, int l, int L_prev, int T_max) {
+  // one warp per 64-element head row; rows [0, R*H*l) are q rows, the next R*H*l are the freshly appended k rows
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  long long row = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+  long long nq = (long long)R * H * l;
+  if (row >= 2 * nq) return;
+  bool is_q = row < nq;
+  long long i = is_q ? row : row - nq;
+  int t = (int)(i % l);
+  long long rh = i / l;
+  int h = (int)(rh % H);
+  long long off = (is_q ? i * 64 : (rh * T_max + L_prev + t) * 64) + lane * 2;
+  __half* ph = (is_q ? q_hi : k_hi) + off;
+  __half* pl = (is_q ? q_lo : k_lo) + off;
+  const __half2 a = *reinterpret_cast<const __half2*>(ph), b = *reinterpret_cast<const __half2*>(pl);
+  float2 v = make_float2(fmaf(__half2float(__low2half(b)), 1.0f / kF16LoScale, __half2float(__low2half(a))),
+                         fmaf(__half2float(__high2half(b)), 1.0f / kF16LoScale, __half2float(__high2half(a))));
+  float ss = warp_sum(v.x * v.x + v.y * v.y);
+  float denom = fmaxf(sqrtf(ss), 1e-12f);
+  v.x = v.x / denom;
+  v.y = v.y / denom;
+  if (is_q) {
+    float mul = expf(fminf(sm[h], 4.605170185988092f));   // clamp_max(log(100)).exp()
+    v.x = __fmul_rn(v.x, mul);
+    v.y = __fmul_rn(v.y, mul);
+  }
+  __half h0, l0, h1, l1;
+  split_f16(v.x, h0, l0);
+  split_f16(v.y, h1, l1);
+  *reinterpret_cast<__half2*>(ph) = __halves2half2(h0, h1);
+  *reinterpret_cast<__half2*>(pl) = __halves2half2(l0, l1);
+}
+
+extern "C" int cvar_qkv_project16(const void* A16_hi, const void* A16_lo, const void* W16_hi, const void* W16_lo,
+                                  const float* q_bias, const float* k_bias, const float* v_bias, void* q16_hi,
+                                  void* q16_lo, void* k16_hi, void* k16_lo, void* vt16_hi, void* vt16_lo, int R, int l,
+                                  int L_prev, int T_max, int H, int cos_attn, const float* scale_mul_H, void* stream) {
+  CVAR_REQUIRE(R > 0 && l > 0 && H > 0 && L_prev >= 0 && L_prev + l <= T_max, "cvar_qkv_project16: bad shape");
+  CVAR_REQUIRE(T_max % 8 == 0, "cvar_qkv_project16: T_max must be a multiple of 8 (got %d)", T_max);
+  CVAR_REQUIRE(!cos_attn || scale_mul_H != nullptr, "cvar_qkv_project16: cosine attention needs scale_mul");
+  CVAR_REQUIRE(q16_hi && q16_lo && k16_hi && k16_lo && vt16_hi && vt16_lo, "cvar_qkv_project16: null output");
+  CVAR_REQUIRE(g_gemm_engine != 0, "cvar_qkv_project16: FP16-pair operands need a tensor-core engine (engine is 0 = SIMT)");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int C = H * 64, M = R * l;
+  QkvEpilogue ep{q_bias, k_bias, v_bias, nullptr, nullptr, nullptr, nullptr, nullptr, C, H, l, L_prev, T_max};
+  ep.q16_hi = reinterpret_cast<__half*>(q16_hi), ep.q16_lo = reinterpret_cast<__half*>(q16_lo);
+  ep.k16_hi = reinterpret_cast<__half*>(k16_hi), ep.k16_lo = reinterpret_cast<__half*>(k16_lo);
+  ep.vt16_hi = reinterpret_cast<__half*>(vt16_hi), ep.vt16_lo = reinterpret_cast<__half*>(vt16_lo);
+  int rc = tc2_qkv_f16(A16_hi, A16_lo, W16_hi, W16_lo, ep, M, C, s);
+  if (rc) return rc;
+  if (cos_attn) {
+    long long rows = 2LL * R * H * l;
+    cos_attn_normalize16_kernel<<<cdiv(rows, 8), 256, 0, s>>>(ep.q16_hi, ep.q16_lo, ep.k16_hi, ep.k16_lo, scale_mul_H, R, H,
+                                                              l, L_prev, T_max);
+    CVAR_CHECK_LAUNCH("cvar_qkv_project16/cos_normalize");
+  }
+  return 0;
+}
+
 extern "C" int cvar_conv2d(const cvar_conv_args* a, void* stream) {
   CVAR_REQUIRE(a != nullptr, "cvar_conv2d: null args");
   CVAR_REQUIRE(a->ks == 1 || a->ks == 3, "cvar_conv2d: ks must be 1 or 3");

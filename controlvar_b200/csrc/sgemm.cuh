@@ -276,6 +276,15 @@ struct QkvEpilogue {
   float* vt_hi;
   float* vt_lo;
   int C, H, l, L_prev, T_max;
+  // FP16-pair form of the same three outputs (cvar_qkv_project16): when q16_hi is set, q / K / V^T are written as
+  // pairs (hi + lo * 2^-11, cvar_split_f16) with the same index layout and the fp32 pointers above are ignored.
+  // This is the operand format of the f16 tensor-core attention kernel (q, K, V^T tiles fetched by TMA as they are).
+  __half* q16_hi = nullptr;
+  __half* q16_lo = nullptr;
+  __half* k16_hi = nullptr;
+  __half* k16_lo = nullptr;
+  __half* vt16_hi = nullptr;
+  __half* vt16_lo = nullptr;
   __device__ __forceinline__ void store(long long m, int n, const float* v, int nvalid, int /*batch*/) const {
     int which = n / C;
     int c = n - which * C;
@@ -286,6 +295,20 @@ struct QkvEpilogue {
 #pragma unroll
     for (int j = 0; j < 4; ++j) o[j] = __fadd_rn(v[j], bias[c + j]);
     const long long rh = (long long)r * H + h;
+    if (q16_hi != nullptr) {
+      if (which == 0) {
+        const long long off = ((rh * l + t) << 6) + d;
+        st4_split_f16(q16_hi + off, q16_lo + off, o);
+      } else if (which == 1) {
+        const long long off = ((rh * T_max + L_prev + t) << 6) + d;
+        st4_split_f16(k16_hi + off, k16_lo + off, o);
+      } else {
+        const long long off = (rh * 64 + d) * T_max + L_prev + t;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) split_f16(o[j], vt16_hi[off + (long long)j * T_max], vt16_lo[off + (long long)j * T_max]);
+      }
+      return;
+    }
     if (which == 0) {
       st4(q_out + ((rh * l + t) << 6) + d, make_float4(o[0], o[1], o[2], o[3]));
     } else {

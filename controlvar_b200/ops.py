@@ -240,6 +240,57 @@ class KVCache:
         return (self.vt_hi + self.vt_lo).view(self.R, self.H, 64, self.T)[:, :, :, :L].transpose(2, 3)
 
 
+class KVCache16:
+    """KV arena of one transformer block as FP16 pairs (engine 4): K (R, H, T, 64) and V^T (R, H, 64, T), hi and lo halves,
+    T padded to a multiple of 8; zero-initialised once.  Same bytes as one fp32 copy, half of KVCache's TF32 split."""
+    __slots__ = ("k_hi", "k_lo", "vt_hi", "vt_lo", "R", "H", "T")
+
+    def __init__(self, R: int, H: int, T: int, device, storage: Optional[torch.Tensor] = None):
+        self.R, self.H, self.T = R, H, (T + 7) // 8 * 8
+        n = R * H * self.T * 64
+        if storage is None:
+            storage = torch.zeros(4 * n, dtype=torch.float16, device=device)
+        assert storage.dtype == torch.float16 and storage.numel() >= 4 * n
+        self.k_hi, self.k_lo, self.vt_hi, self.vt_lo = (storage[i * n:(i + 1) * n] for i in range(4))
+
+    @staticmethod
+    def numel(R: int, H: int, T: int) -> int:
+        return 4 * R * H * ((T + 7) // 8 * 8) * 64
+
+    def keys(self, L: int) -> torch.Tensor:
+        """(R, H, L, 64) fp32 view of the cached keys, for tests / debugging."""
+        return (self.k_hi.float() + self.k_lo.float() / F16_LO_SCALE).view(self.R, self.H, self.T, 64)[:, :, :L]
+
+    def values(self, L: int) -> torch.Tensor:
+        return (self.vt_hi.float() + self.vt_lo.float() / F16_LO_SCALE).view(self.R, self.H, 64, self.T)[:, :, :, :L] \
+            .transpose(2, 3)
+
+
+def qkv_project16(A16: F16Pair, Wqkv: "SplitWeight", q_bias, k_bias, v_bias, q16: F16Pair, cache: KVCache16, R, l, L_prev,
+                  H, cos_attn, scale_mul_H):
+    """cvar_qkv_project16: pair operands in, q / K / V^T out as FP16 pairs (q16: (R, H, l, 64))."""
+    _chk(q_bias, k_bias, v_bias, scale_mul_H)
+    if Wqkv.h16 is None:
+        raise _lib.CvarError("qkv_project16 needs a SplitWeight(f16=True) weight")
+    Cd = H * 64
+    with _Timed("gemm", 2.0 * R * l * 3 * Cd * Cd, 4.0 * (R * l * Cd + 3 * Cd * Cd + R * l * 3 * Cd)):
+        check(_lib.load().cvar_qkv_project16(_p(A16.hi), _p(A16.lo), _p(Wqkv.h16.hi), _p(Wqkv.h16.lo), _p(q_bias),
+                                             _p(k_bias), _p(v_bias), _p(q16.hi), _p(q16.lo), _p(cache.k_hi),
+                                             _p(cache.k_lo), _p(cache.vt_hi), _p(cache.vt_lo), R, l, L_prev, cache.T, H,
+                                             int(cos_attn), _p(scale_mul_H), _stream()), "cvar_qkv_project16")
+
+
+def attn_kvcache16(q16: F16Pair, cache: KVCache16, out, R, H, l, L, scale, engine: int = -1,
+                   out16: Optional[F16Pair] = None):
+    _chk(out)
+    o16h, o16l = _p16(out16)
+    with _Timed("attn", 4.0 * l * L * 64 * R * H, (2.0 * l + 2.0 * L) * 64 * 4 * R * H):
+        check(_lib.load().cvar_attn_kvcache16(_p(q16.hi), _p(q16.lo), _p(cache.k_hi), _p(cache.k_lo), _p(cache.vt_hi),
+                                              _p(cache.vt_lo), _p(out), o16h, o16l, R, H, l, L, cache.T, float(scale),
+                                              int(engine), _stream()), "cvar_attn_kvcache16")
+    return out if out is not None else out16
+
+
 def qkv_project(A, Wqkv, q_bias, k_bias, v_bias, q_out, cache: KVCache, R, l, L_prev, H, cos_attn, scale_mul_H,
                 A_lo=None, A16: Optional[F16Pair] = None):
     Wqkv, W_hi, W_lo, W16 = _wparts(Wqkv)

@@ -14,9 +14,13 @@
 //     P back as an FP16 pair OVER the S_main columns it has just consumed (chunk c: hi in columns [16c, 16c+8), lo in
 //     [16c+8, 16c+16), two keys per 32-bit cell) and P @ V reads its A operand from there.  tcgen05.mma executes in issue
 //     order, so S(j+1), issued after P@V(j), may overwrite those columns.
-//   * The running output row lives in registers (round-to-nearest adds); every tile's O_tile is a fresh accumulation of
-//     12 MMA steps, so the tensor core's truncating accumulation never runs long.
+//   * O accumulates in TMEM for kDrain = 4 tiles (48 truncating MMA steps) and is then added into the running output
+//     row in registers with round-to-nearest adds.  The exponentials are taken against a reference that is the first tile's
+//     row maximum and moves only when a later tile's maximum exceeds it by 2^8 (then that row rescales what it has
+//     accumulated, in registers and in its TMEM row), so the common tile does no rescaling work at all.  Two 16-bit values
+//     per TMEM cell, the lower key index in the low half (A operand of kind::f16 from tensor memory).
 //   TMEM columns: S_main/P [0,64)  S_x [64,128)  O_main [128,192)  O_x [192,256)
+#include <type_traits>
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -195,6 +199,10 @@ constexpr int kStageBytes = 4 * kTile;            // K_hi | K_lo | VT_hi | VT_lo
 constexpr int kStages = 2;
 constexpr int kSmem = 1024 + 2 * kQTile + kStages * kStageBytes + 256;     // 99,584 B: two CTAs per SM
 constexpr uint32_t kColS = 0, kColSx = 64, kColO = 128, kColOx = 192, kTmemCols = 256;
+// O stays in TMEM for kDrain tiles (kDrain * 12 truncating accumulation steps) before it is added into the fp32 registers
+constexpr int kDrain = 4;
+// the softmax reference moves when a logit exceeds it by more than 2^kRebase (p <= 256: far inside fp16 / fp32 range)
+constexpr float kRebase = 8.0f;
 // D fp32 (bit 4), A / B format 0 = F16, both K-major, N = 64, M = 128
 constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
@@ -275,18 +283,13 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// two fp32 values -> one 32-bit cell of halves: `first` (the lower key index) goes to the low 16 bits unless swapped
-__device__ __forceinline__ uint32_t pack_h2(__half first, __half second, int swap) {
-  const uint32_t a = __half_as_ushort(first), b = __half_as_ushort(second);
-  return swap ? (b | (a << 16)) : (a | (b << 16));
-}
 
 __global__ void __launch_bounds__(kThreads, 2)
 attn16_tc_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_constant__ CUtensorMap mapQlo,
                  const __grid_constant__ CUtensorMap mapKhi, const __grid_constant__ CUtensorMap mapKlo,
                  const __grid_constant__ CUtensorMap mapVhi, const __grid_constant__ CUtensorMap mapVlo,
                  float* __restrict__ out, __half* __restrict__ o16_hi, __half* __restrict__ o16_lo, int H, int l, int L,
-                 float scale, int pack_swap) {
+                 float scale) {
   using G = Geo<32>;          // 128-byte rows, SWIZZLE_128B: 64 halves per row
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -324,23 +327,88 @@ attn16_tc_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_consta
 
   if (warp < 4) {
     // ================================================================ softmax + output rows
+    // Budget (ncu of the first version, profiles/r01_attn16.md): 1705 instructions per warp and tile, the XU pipe (MUFU
+    // and scalar F2F conversions, 8 cycles per warp instruction) 45 % busy, branches from per-element masking.  Hence:
+    // packed conversions (F2FP, not XU), masking only in the last tile, a lazily updated reference instead of the exact
+    // running maximum (no per-tile rescale), and O left accumulating in TMEM for kDrain tiles.
     const int row = threadIdx.x;
     const uint32_t tl = tmem_base + ((uint32_t)(warp * 32) << 16);
-    // p = exp((s - m) * scale) = 2^((s - m) * scale * log2 e): the difference is formed first (exact or nearly so for the
-    // terms that matter), so the rounding of the product is a relative error of |t| * 2^-24 on terms of weight e^t
+    // p = exp((s - ref) * scale) = 2^((s - ref) * scale * log2 e): the difference is formed first, so the rounding of the
+    // product is a relative error of |t| * 2^-24 on a term of weight e^t
     const float sl2 = scale * 1.4426950408889634f;
     float o_reg[D];
 #pragma unroll
     for (int d = 0; d < D; ++d) o_reg[d] = 0.f;
-    float m_run = -INFINITY, l_run = 0.f;
+    float m_ref = 0.f, l_run = 0.f;
+
+    // one 16-key chunk: p for the chunk, written back over the S_main cells it came from as an FP16 pair
+    // nref = -ref * scale * log2e; t = fma(s, sl2, nref): the product is exact inside the FMA, and the rounding of nref
+    // is a factor common to every key of the row (it cancels in the normalisation)
+    auto chunk = [&](auto masked, int c, const float* a, const float* b, float nref, int nvalid, float& rs) {
+      uint32_t ph[8], pl[8];
+#pragma unroll
+      for (int i = 0; i < 16; i += 2) {
+        const float s0 = fmaf(b[i], kInvLo, a[i]), s1 = fmaf(b[i + 1], kInvLo, a[i + 1]);
+        float p0 = ex2_approx(fmaf(s0, sl2, nref)), p1 = ex2_approx(fmaf(s1, sl2, nref));
+        if constexpr (decltype(masked)::value) {   // last tile only: keys past L contribute nothing
+          if (16 * c + i >= nvalid) p0 = 0.f;
+          if (16 * c + i + 1 >= nvalid) p1 = 0.f;
+        }
+        rs += p0 + p1;
+        const __half2 h = __floats2half2_rn(p0, p1);                 // low half = lower key index
+        const float2 hf = __half22float2(h);
+        const __half2 lo = __floats2half2_rn((p0 - hf.x) * kF16LoScale, (p1 - hf.y) * kF16LoScale);
+        ph[i >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+        pl[i >> 1] = *reinterpret_cast<const uint32_t*>(&lo);
+      }
+      tmem_st_32x32b_x8(tl + kColS + 16 * c, ph);
+      tmem_st_32x32b_x8(tl + kColS + 16 * c + 8, pl);
+    };
+    // the whole tile against reference `ref`; chunk loads are prefetched one ahead (one exposed TMEM round trip)
+    auto tile_pass = [&](auto masked, float nref, int nvalid, float& rs) {
+      float a0[16], b0[16], a1[16], b1[16];
+      tmem_ld_nowait_x16(tl + kColS, a0);
+      tmem_ld_nowait_x16(tl + kColSx, b0);
+      tmem_wait_ld();
+      reg_fence16(a0), reg_fence16(b0);
+      tmem_ld_nowait_x16(tl + kColS + 16, a1);
+      tmem_ld_nowait_x16(tl + kColSx + 16, b1);
+      chunk(masked, 0, a0, b0, nref, nvalid, rs);
+      tmem_wait_ld();
+      reg_fence16(a1), reg_fence16(b1);
+      tmem_ld_nowait_x16(tl + kColS + 32, a0);
+      tmem_ld_nowait_x16(tl + kColSx + 32, b0);
+      chunk(masked, 1, a1, b1, nref, nvalid, rs);
+      tmem_wait_ld();
+      reg_fence16(a0), reg_fence16(b0);
+      tmem_ld_nowait_x16(tl + kColS + 48, a1);
+      tmem_ld_nowait_x16(tl + kColSx + 48, b1);
+      chunk(masked, 2, a0, b0, nref, nvalid, rs);
+      tmem_wait_ld();
+      reg_fence16(a1), reg_fence16(b1);
+      chunk(masked, 3, a1, b1, nref, nvalid, rs);
+    };
+    // o_reg += O accumulated in TMEM (round-to-nearest adds)
+    auto drain_O = [&]() {
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        float a[32], b[32];
+        tmem_ld_nowait_x32(tl + kColO + 32 * hf, a);
+        tmem_ld_nowait_x32(tl + kColOx + 32 * hf, b);
+        tmem_wait_ld();
+        reg_fence32(a), reg_fence32(b);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o_reg[32 * hf + i] += fmaf(b[i], kInvLo, a[i]);
+      }
+    };
+
     for (int j = 0; j < ntiles; ++j) {
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-      const int kbase = j * BKV;
-      // Every tcgen05.ld -> wait::ld pair exposes the TMEM round trip to a warp that has only one partner on its
-      // scheduler, so loads are batched (one wait per batch) and the chunks of pass 2 are prefetched one ahead.
-      // pass 1: row maximum from S_main alone.  The cross accumulator is ~2^-11 of it: the reference point of the
-      // exponentials need not be the exact maximum (p may exceed 1 by ~1e-3; l_run uses the same reference).
+      const int nvalid = min(BKV, L - j * BKV);
+      // O of the tiles since the last drain is complete here: the commit behind s_full(j) covers P @ V(j-1)
+      if (j > 0 && (j % kDrain) == 0) drain_O();
+      // pass 1: row maximum of S_main (the cross accumulator is ~2^-11 of it: the reference need not be exact)
       float mx = -INFINITY;
       {
         float a[32], b[32];
@@ -348,72 +416,53 @@ attn16_tc_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_consta
         tmem_ld_nowait_x32(tl + kColS + 32, b);
         tmem_wait_ld();
         reg_fence32(a), reg_fence32(b);
+        if (nvalid < 64) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          if (kbase + i < L) mx = fmaxf(mx, a[i]);
-          if (kbase + 32 + i < L) mx = fmaxf(mx, b[i]);
+          for (int i = 0; i < 32; ++i) {
+            if (i < nvalid) mx = fmaxf(mx, a[i]);
+            if (32 + i < nvalid) mx = fmaxf(mx, b[i]);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(a[i], b[i]));
         }
       }
-      const float m_new = fmaxf(m_run, mx);            // every tile holds at least one valid key: finite
-      const float corr = ex2_approx((m_run - m_new) * sl2);   // 0 on the first tile (m_run = -inf)
-      // O_tile(j-1) -> registers (round-to-nearest adds), rescaled to the new reference.  It is complete: the commit
-      // behind s_full(j) covers P @ V(j-1), which was issued before S(j).
-      if (j > 0) {
-        mbar_wait(o_full, (j - 1) & 1);
-        tc_fence_after();
+      const bool need = j > 0 && (mx - m_ref) * sl2 > kRebase;
+      if (j == 0) {
+        m_ref = mx;
+      } else if (__any_sync(0xffffffffu, need)) {
+        // A key far above the reference (p would exceed 2^kRebase): move the reference to it.  Rare after the first
+        // tiles - the reference only has to stay within a factor 2^kRebase of the true maximum.  Everything accumulated
+        // so far is rescaled: registers, the running sum, and this row of the O accumulators in TMEM.  The TMEM
+        // instructions are warp-collective, so the whole warp takes the path; rows that keep their reference use corr = 1.
+        const float corr = need ? ex2_approx((m_ref - mx) * sl2) : 1.0f;
+        if (need) m_ref = mx;
+        l_run *= corr;
 #pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-          float a[32], b[32];
-          tmem_ld_nowait_x32(tl + kColO + 32 * hf, a);
-          tmem_ld_nowait_x32(tl + kColOx + 32 * hf, b);
-          tmem_wait_ld();
-          reg_fence32(a), reg_fence32(b);
+        for (int d = 0; d < D; ++d) o_reg[d] *= corr;
+        if ((j % kDrain) != 0) {
+#pragma unroll 1
+          for (int c = 0; c < 8; ++c) {
+            float a[16];
+            tmem_ld_nowait_x16(tl + kColO + 16 * c, a);        // O_main [128,192) and O_x [192,256) are contiguous
+            tmem_wait_ld();
+            reg_fence16(a);
+            uint32_t u[16];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o_reg[32 * hf + i] = (o_reg[32 * hf + i] + fmaf(b[i], kInvLo, a[i])) * corr;
+            for (int i = 0; i < 16; ++i) u[i] = __float_as_uint(a[i] * corr);
+            tmem_st_32x32b_x8(tl + kColO + 16 * c, u);
+            tmem_st_32x32b_x8(tl + kColO + 16 * c + 8, u + 8);
+          }
         }
       }
-      // pass 2: p = exp((s - m) * scale), written back over S_main as an FP16 pair (the A operand of P @ V)
+      // pass 2: p against the reference, written back as the A operand of P @ V
       float rs = 0.f;
-      float a0[16], b0[16], a1[16], b1[16];
-      auto chunk = [&](int c, const float* a, const float* b) {
-        uint32_t ph[8], pl[8];
-#pragma unroll
-        for (int i = 0; i < 16; i += 2) {
-          float p0 = 0.f, p1 = 0.f;
-          if (kbase + 16 * c + i < L) p0 = ex2_approx((fmaf(b[i], kInvLo, a[i]) - m_new) * sl2);
-          if (kbase + 16 * c + i + 1 < L) p1 = ex2_approx((fmaf(b[i + 1], kInvLo, a[i + 1]) - m_new) * sl2);
-          rs += p0 + p1;
-          const __half h0 = __float2half_rn(p0), h1 = __float2half_rn(p1);
-          const __half l0 = __float2half_rn((p0 - __half2float(h0)) * kF16LoScale);
-          const __half l1 = __float2half_rn((p1 - __half2float(h1)) * kF16LoScale);
-          ph[i >> 1] = pack_h2(h0, h1, pack_swap);
-          pl[i >> 1] = pack_h2(l0, l1, pack_swap);
-        }
-        tmem_st_32x32b_x8(tl + kColS + 16 * c, ph);
-        tmem_st_32x32b_x8(tl + kColS + 16 * c + 8, pl);
-      };
-      tmem_ld_nowait_x16(tl + kColS, a0);
-      tmem_ld_nowait_x16(tl + kColSx, b0);
-      tmem_wait_ld();
-      reg_fence16(a0), reg_fence16(b0);
-      tmem_ld_nowait_x16(tl + kColS + 16, a1);
-      tmem_ld_nowait_x16(tl + kColSx + 16, b1);
-      chunk(0, a0, b0);
-      tmem_wait_ld();
-      reg_fence16(a1), reg_fence16(b1);
-      tmem_ld_nowait_x16(tl + kColS + 32, a0);
-      tmem_ld_nowait_x16(tl + kColSx + 32, b0);
-      chunk(1, a1, b1);
-      tmem_wait_ld();
-      reg_fence16(a0), reg_fence16(b0);
-      tmem_ld_nowait_x16(tl + kColS + 48, a1);
-      tmem_ld_nowait_x16(tl + kColSx + 48, b1);
-      chunk(2, a0, b0);
-      tmem_wait_ld();
-      reg_fence16(a1), reg_fence16(b1);
-      chunk(3, a1, b1);
-      l_run = l_run * corr + rs;
-      m_run = m_new;
+      const float nref = -m_ref * sl2;
+      if (nvalid < BKV)
+        tile_pass(std::true_type{}, nref, nvalid, rs);
+      else
+        tile_pass(std::false_type{}, nref, nvalid, rs);
+      l_run += rs;
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(p_ready);
@@ -485,9 +534,10 @@ attn16_tc_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_consta
         for (int k = 0; k < 4; ++k) {                       // 16 keys per MMA: P cells [16k, 16k+8) hi, [16k+8, 16k+16) lo
           const uint64_t adv = (uint64_t)(2 * k);
           const uint32_t p_hi = tmem_base + kColS + 16 * k, p_lo = p_hi + 8;
-          umma_f16_ts(tmem_base + kColOx, p_lo, dvh + adv, kIdesc, k != 0);
+          const uint32_t acc = (k != 0 || (j % kDrain) != 0) ? 1u : 0u;   // fresh accumulators every kDrain tiles
+          umma_f16_ts(tmem_base + kColOx, p_lo, dvh + adv, kIdesc, acc);
           umma_f16_ts(tmem_base + kColOx, p_hi, dvl + adv, kIdesc, 1u);
-          umma_f16_ts(tmem_base + kColO, p_hi, dvh + adv, kIdesc, k != 0);
+          umma_f16_ts(tmem_base + kColO, p_hi, dvh + adv, kIdesc, acc);
         }
         umma_commit(o_full);
         umma_commit(&kv_empty[j % kStages]);
@@ -539,15 +589,6 @@ static int make_map3(CUtensorMap* map, const void* base, long long inner, long l
   }
   return 0;
 }
-// which half of a 32-bit TMEM cell holds the lower k index of a 16-bit A operand: 0 = low bits (default)
-static int pack_swap() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("CVAR_ATTN16_PACK_SWAP");
-    v = (e != nullptr && e[0] == '1') ? 1 : 0;
-  }
-  return v;
-}
 }  // namespace tcattn16
 
 extern "C" int cvar_attn_kvcache16(const void* q16_hi, const void* q16_lo, const void* k16_hi, const void* k16_lo,
@@ -584,7 +625,7 @@ extern "C" int cvar_attn_kvcache16(const void* q16_hi, const void* q16_lo, const
     CVAR_REQUIRE(e == cudaSuccess, "cvar_attn_kvcache16: cannot raise shared memory: %s", cudaGetErrorString(e));
     dim3 grid(cdiv(l, tcattn16::BQ), H, R);
     tcattn16::attn16_tc_kernel<<<grid, tcattn16::kThreads, tcattn16::kSmem, (cudaStream_t)stream>>>(
-        mqh, mql, mkh, mkl, mvh, mvl, out, o16h, o16l, H, l, L, scale, tcattn16::pack_swap());
+        mqh, mql, mkh, mkl, mvh, mvl, out, o16h, o16l, H, l, L, scale);
     CVAR_CHECK_LAUNCH("cvar_attn_kvcache16[tc]");
     return 0;
   }

@@ -63,6 +63,44 @@ def test_attn16_matches_sdpa(R, H, l, L):
     assert all(x < 4e-6 for x in res.values()), res
 
 
+@pytest.mark.parametrize("L", [576, 600, 1360])
+def test_attn16_reference_rebase_paths(L):
+    """The tensor-core kernel keeps a lazily updated softmax reference and leaves O accumulating in TMEM for 4 tiles.
+    Keys whose logits grow tile after tile force the reference to move at every position of the 4-tile drain cycle
+    (rescale of registers AND of the row's TMEM accumulators); some rows never move it (queries pointing the other way)."""
+    torch.manual_seed(L)
+    R, H, l = 2, 2, 128
+    scale = 1.0
+    q = torch.randn(R, H, l, 64)
+    k = torch.randn(R, H, L, 64) * 0.3
+    # a direction every query shares (with either sign) and that keys follow more strongly the later they come
+    u = torch.nn.functional.normalize(torch.randn(64), dim=0)
+    sign = torch.where(torch.arange(l) % 3 == 0, -1.0, 1.0).view(1, 1, l, 1)
+    q = q * 0.5 + 6.0 * sign * u
+    ramp = (torch.arange(L) // 64).float().view(1, 1, L, 1)            # + ~7 nats per tile for the '+' rows
+    k = k + 1.2 * ramp * u
+    v = torch.randn(R, H, L, 64)
+    ref = F.scaled_dot_product_attention(q.double(), k.double(), v.double(), scale=scale).transpose(1, 2).reshape(R, l, H * 64)
+    kv = ops.KVCache16(R, H, L, DEV)
+    fill_cache(kv, k, v, L)
+    q16 = pair(q)
+    # reference with the operands the kernel really sees (the pair format is exact to 2^-24, the logits reach ~150)
+    qd, kd, vd = q16.float().double().cpu(), kv.keys(L).double().cpu(), kv.values(L).double().cpu()
+    ref_pair = F.scaled_dot_product_attention(qd, kd, vd, scale=scale).transpose(1, 2).reshape(R, l, H * 64)
+    errs = {}
+    for eng in (1, 0):
+        out = torch.empty(R, l, H * 64, device=DEV)
+        ops.attn_kvcache16(q16, kv, out, R, H, l, L, scale, engine=eng)
+        errs[eng] = ((out.cpu().double() - ref_pair).abs().max().item(), (out.cpu().double() - ref).abs().max().item())
+    s_rng = (qd @ kd.transpose(-1, -2)).abs().max().item()
+    print(f"\n[attn16-rebase] L={L} max|S| {s_rng:.0f}: tcgen05 err {errs[1][0]:.2e} (vs fp64 of fp32 inputs {errs[1][1]:.2e})"
+          f"   SIMT err {errs[0][0]:.2e}")
+    # the logits themselves are fp32 numbers of size max|S| (ulp 1.5e-5 at 190): the error of exp() scales with them.
+    # Measured on B200: tcgen05 0.9e-7..1.0e-7 x max|S|, SIMT 2.2e-7..3.2e-7 x max|S| (fp32 FMA chains of 64 terms)
+    assert errs[1][0] < 2.5e-7 * s_rng and errs[0][0] < 6e-7 * s_rng
+    assert errs[1][1] < max(3e-5, 1.5e-6 * s_rng)
+
+
 def test_attn16_pair_only_output_and_default_engine():
     """out = None (what the sampler passes) and engine = -1 (tensor cores for l >= 64, SIMT below)."""
     torch.manual_seed(0)

@@ -46,7 +46,7 @@ class ConvArgs(C.Structure):
         ("out_mode", C.c_int), ("out_rows_total", C.c_int), ("row_offset", C.c_int),
         ("engine", C.c_int),
         ("x16_hi", C.c_void_p), ("x16_lo", C.c_void_p), ("w16_hi", C.c_void_p), ("w16_lo", C.c_void_p),
-        ("downsample2x", C.c_int),
+        ("downsample2x", C.c_int), ("ksplit", C.c_int),
     ]
 
 

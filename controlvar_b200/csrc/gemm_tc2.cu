@@ -276,6 +276,7 @@ struct ConvGeo {
   int H, W, Cin, ks;      // resolution (output == input), input channels, 1 or 3
   int Wb;                 // box width min(W, 128); box height 128 / Wb
   int BN;                 // output channels per pair tile: multiple of 32, <= 256
+  int tap0, ntaps;        // this launch covers taps [tap0, tap0 + ntaps) of the ks*ks (K-split: cvar_conv_args.ksplit)
 };
 
 __device__ __forceinline__ void tma_load_4d_2sm(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2,
@@ -316,7 +317,7 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constan
   const uint32_t rank = cluster_ctarank();
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
   const int cpb = g.Cin >> 5;                        // 32-channel chunks per tap
-  const int nkb = g.ks * g.ks * cpb;
+  const int nkb = g.ntaps * cpb;
   const int total_tiles = m_tiles * n_tiles;
 
   if (warp == kTmaWarp && lane == 0) {
@@ -393,9 +394,9 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constan
         const int rem = (int)(m0 - (long long)img * HW);
         const int y0 = rem / g.W, x0 = rem - y0 * g.W;
         const int brow = nt * BNr + (int)rank * (BNr / 2);
-        int kb = 0;
-        for (int tap = 0; tap < g.ks * g.ks; ++tap) {
+        for (int tap = g.tap0; tap < g.tap0 + g.ntaps; ++tap) {
           const int ky = tap / g.ks, kx = tap - ky * g.ks;
+          int kb = tap * cpb;                      // K-block index in the full tap-major weight matrix
           for (int cc = 0; cc < cpb; ++cc, ++kb, ++it) {
             const int s = it % kCvStages;
             const uint32_t ph = (it / kCvStages) & 1;
@@ -633,8 +634,20 @@ int tc2_conv_f16(const cvar_conv_args* a, cudaStream_t s) {
   const long long M = (long long)a->B * H * W;
   const int m_tiles = cdiv(M, 256), n_tiles = a->Cout / g.BN;
   const int pairs = min(tc2::num_sms() / 2, m_tiles * n_tiles);
-  kern<<<2 * pairs, tc2::kThreads, tc2::kCvSmem, s>>>(mah, mal, mbh, mbl, ep, g, M, a->Cout, m_tiles, n_tiles);
-  CVAR_CHECK_LAUNCH("cvar_conv2d[tc2/f16x3]");
+  // K-split: the tensor core truncates its fp32 accumulator after every MMA, so the error of one accumulation grows with
+  // its length (K = 9 * 640 is 360 steps).  ksplit = 3 runs the three kernel rows as three launches whose partial sums
+  // meet in the fp32 output with round-to-nearest adds (the epilogue of launches 2, 3 adds to what is there).
+  const int taps = a->ks * a->ks;
+  const int nsplit = (a->ksplit == 3 && a->ks == 3 && a->out_mode == 0) ? 3 : 1;
+  CVAR_REQUIRE(a->ksplit == 0 || a->ksplit == 1 || nsplit == 3, "cvar_conv2d[f16x3]: ksplit = 3 needs ks = 3 and out_mode 0");
+  for (int part = 0; part < nsplit; ++part) {
+    g.ntaps = taps / nsplit;
+    g.tap0 = part * g.ntaps;
+    ConvEpilogue epp = ep;
+    epp.accumulate = part > 0 ? 1 : 0;
+    kern<<<2 * pairs, tc2::kThreads, tc2::kCvSmem, s>>>(mah, mal, mbh, mbl, epp, g, M, a->Cout, m_tiles, n_tiles);
+    CVAR_CHECK_LAUNCH("cvar_conv2d[tc2/f16x3]");
+  }
   return 0;
 }
 

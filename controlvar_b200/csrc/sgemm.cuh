@@ -343,10 +343,17 @@ struct ConvEpilogue {
   const float* resid;
   int Cout, out_mode;
   int Hout, Wout, out_rows_total, row_offset;
+  int accumulate = 0;     // K-split continuation (out_mode 0): out += acc, no bias, no residual
   __device__ __forceinline__ void store(long long m, int n, const float* v, int nvalid, int /*batch*/) const {
     if (out_mode == 0) {
       float* o = out + m * Cout + n;
       float r[4];
+      if (accumulate) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (j < nvalid) o[j] = __fadd_rn(o[j], v[j]);
+        return;
+      }
 #pragma unroll
       for (int j = 0; j < 4; ++j) r[j] = __fadd_rn(v[j], (j < nvalid) ? bias[n + j] : 0.f);
       if (resid != nullptr) {
@@ -401,13 +408,19 @@ __device__ __forceinline__ EpiAux epi_load_aux(const ConvEpilogue& e, long long 
   EpiAux x;
   x.a = make_float4(0.f, 0.f, 0.f, 0.f);
   x.b = x.a;
-  if (e.out_mode == 0 && e.resid != nullptr && nv == 4) x.a = ld4(e.resid + m * e.Cout + n);
+  if (e.out_mode == 0 && e.accumulate && nv == 4) x.a = ld4(e.out + m * e.Cout + n);
+  else if (e.out_mode == 0 && e.resid != nullptr && nv == 4) x.a = ld4(e.resid + m * e.Cout + n);
   return x;
 }
 __device__ __forceinline__ void epi_store_aux(const ConvEpilogue& e, long long m, int n, const float* v, int nv, int b,
                                               const EpiAux& x) {
   if (e.out_mode != 0 || nv != 4) {
     e.store(m, n, v, nv, b);
+    return;
+  }
+  if (e.accumulate) {
+    st4(e.out + m * e.Cout + n, make_float4(__fadd_rn(x.a.x, v[0]), __fadd_rn(x.a.y, v[1]), __fadd_rn(x.a.z, v[2]),
+                                            __fadd_rn(x.a.w, v[3])));
     return;
   }
   float4 b4 = ld4(e.bias + n);

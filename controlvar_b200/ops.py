@@ -391,7 +391,7 @@ def gn_stats(x_nhwc, gamma, beta, a_out, b_out, scratch, B, HW, Cdim, groups=32,
 
 def conv2d(x, w_packed, bias, out, B, Hin, Win, Cin, Cout, ks, *, in_a=None, in_b=None, in_silu=False, resid=None,
            upsample2x=False, out_mode=0, out_rows_total=0, row_offset=0, engine=-1, x16: Optional[F16Pair] = None,
-           w16: Optional[F16Pair] = None, downsample2x=False):
+           w16: Optional[F16Pair] = None, downsample2x=False, ksplit=0):
     """x16 + w16: FP16-pair input (already normalised / upsampled) and weight -> the 2-CTA TMA kernel; x may be None.
     downsample2x: the encoder's pad-(0,1,0,1) + stride-2 convolution (vae_modules.py:31-37)."""
     w_packed, w_hi, w_lo, _ = _wparts(w_packed)
@@ -409,6 +409,7 @@ def conv2d(x, w_packed, bias, out, B, Hin, Win, Cin, Cout, ks, *, in_a=None, in_
     a.out_mode, a.out_rows_total, a.row_offset = out_mode, out_rows_total, row_offset
     a.engine = int(engine)
     a.downsample2x = int(downsample2x)
+    a.ksplit = int(ksplit)
     up = 2 if upsample2x else 1
     Mo = B * Hin * up * Win * up // (4 if downsample2x else 1)
     with _Timed("conv", 2.0 * Mo * Cout * ks * ks * Cin, 4.0 * (B * Hin * Win * Cin + Mo * Cout + Cout * ks * ks * Cin)):

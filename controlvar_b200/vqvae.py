@@ -83,14 +83,16 @@ class VQVAE(nn.Module):
         # before the residual update of f_to_idxBl, pinning the residual trajectory to the oracle's
         self.debug_forced_idx: Optional[List[torch.Tensor]] = None
         self.last_idx: List[torch.Tensor] = []
-        # Decoder convolutions whose output side is below this run on the SIMT fp32 engine.  Measured on B200
-        # (profiles/r01_decoder_policy.md, engine 4 = f16x3): with every conv on tensor cores the worst pixel over 32
-        # realistic images is 9.0e-5 off the fp32 oracle (1.09e-4 on another 4: over the north-star bound of 1e-4); the
-        # 16x16 layers (K = 5760, few pixels) cause most of that and cost little, so they stay in exact fp32:
-        # worst pixel 7.1e-5, 146 ms per 64-image decode (all on tensor cores: 115 ms; >= 64 only: 180 ms, 4.3e-5).
-        # The 3xTF32 engines (1, 3) are ~2x less accurate per layer and need >= 64 (32 gives 1.06e-4 .. 1.24e-4).
-        # None = that per-engine default; an int overrides it (tools/diag_decoder_policy.py).
+        # Accuracy policy of the convolutions (measured on B200, profiles/r01_decoder_policy.md; bound: 1e-4 abs per pixel).
+        # The tensor core truncates its fp32 accumulator after every MMA, so one long accumulation (K = 9 * 640 = 360
+        # steps) is what costs accuracy.  Engine 4 (f16x3): every layer runs on tensor cores and 3x3 layers with
+        # 9 * Cin >= ksplit_min_k run their three kernel rows as three accumulations summed in fp32 (cvar_conv_args.ksplit):
+        # worst pixel 4.3e-5 over 32 realistic images, 125 ms per 64-image decode (without the split: 1.09e-4, over the
+        # bound; with the 16x16 layers on SIMT instead: 7.1e-5, 157 ms).  The 3xTF32 engines (1, 3) have no split and keep
+        # layers with an output side below 64 on the SIMT fp32 engine (8.0e-5).
+        # tc_min_hw: None = that per-engine default (16 / 64); an int overrides it (tools/diag_decoder_policy.py).
         self.tc_min_hw: Optional[int] = None
+        self.ksplit_min_k = 2880          # 0 switches the K-split off
         self._packed: Dict[str, torch.Tensor] = {}
         self._packed16: Dict[str, "ops.F16Pair"] = {}
         self._ws: Dict[Tuple, torch.Tensor] = {}
@@ -148,7 +150,7 @@ class VQVAE(nn.Module):
     def _min_hw(self) -> int:
         if self.tc_min_hw is not None:
             return self.tc_min_hw
-        return 32 if ops.get_gemm_engine() == ops.ENGINE_TC_F16X3 else 64
+        return 16 if ops.get_gemm_engine() == ops.ENGINE_TC_F16X3 else 64
 
     def _f16_layer(self, Hout, Wout, Cin, Cout, ks) -> bool:
         """Does this layer run on the FP16-pair TMA kernel?  Engine 4, accuracy policy (tc_min_hw), supported shape."""
@@ -159,8 +161,9 @@ class VQVAE(nn.Module):
         """x: fp32 NHWC tensor, or an F16Pair (normalised / upsampled by its producer) for a layer _f16_layer() accepts."""
         bias = self._w(prefix + ".bias")
         if isinstance(x, ops.F16Pair):
+            split = 3 if (self.ksplit_min_k and ks == 3 and 9 * Cin >= self.ksplit_min_k and not kw.get("out_mode")) else 0
             return ops.conv2d(None, self._conv_w(prefix), bias, out, B, Hin, Win, Cin, Cout, ks, x16=x,
-                              w16=self._conv_w16(prefix), **kw)
+                              w16=self._conv_w16(prefix), ksplit=split, **kw)
         hout = Hin * (2 if kw.get("upsample2x") else 1)
         return ops.conv2d(x, self._conv_w(prefix), bias, out, B, Hin, Win, Cin, Cout, ks,
                           engine=(-1 if hout >= self._min_hw() else 0), **kw)

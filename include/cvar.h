@@ -251,6 +251,10 @@ typedef struct {
   /* Downsample2x of the encoder (vae_modules.py:31-37): F.pad(x, (0,1,0,1)) + 3x3 conv with stride 2 and no padding.
    * Output is (B, Hin/2, Win/2, Cout).  ks = 3, even Hin / Win, fp32 NHWC input; always on the SIMT fp32 engine. */
   int downsample2x;
+  /* FP16-pair path only: 3 = run the three kernel rows of a 3x3 convolution as three accumulations whose partial sums are
+   * added in fp32 (round to nearest) in the output - for the K = 9*640 layers, where one truncating tensor-core
+   * accumulation of 360 steps costs too much accuracy.  0 / 1 = one accumulation. out_mode 0 only. */
+  int ksplit;
 } cvar_conv_args;
 CVAR_API int cvar_conv2d(const cvar_conv_args* args, void* stream);
 /* 1 when the FP16-pair kernel takes this layer: ks in {1,3}, Cin % 32 == 0, Cout a multiple of one of

@@ -15,6 +15,8 @@ vsd, sd = W.synthetic_vae_state_dict(cfg, 0), W.synthetic_var_state_dict(cfg, 0)
 vae = VQVAE(ch=160).to("cuda")
 vae.load_state_dict(vsd)
 torch.set_num_threads(os.cpu_count())
+if "CVAR_KSPLIT_MIN_K" in os.environ:
+    vae.ksplit_min_k = int(os.environ["CVAR_KSPLIT_MIN_K"])
 if "CVAR_TC_MIN_HW" in os.environ:
     vae.tc_min_hw = int(os.environ["CVAR_TC_MIN_HW"])
 print(f"engine {ops.get_gemm_engine()}, tc_min_hw {vae._min_hw()}")

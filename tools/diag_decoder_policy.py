@@ -26,15 +26,19 @@ refs = [O.fhat_to_img(f.clone(), vsd) for f in fs]
 big = torch.cat(fs * 16, 0).to(DEV)          # 64 images for timing
 ops.set_gemm_engine(3)
 print("tc_min_hw | layers on tensor cores            | max pixel err (4 realistic f_hat) | mean err | decode 64 imgs")
+KS = {}   # row label -> ksplit_min_k
 ROWS = ((0, "all", 3), (32, "output side >= 32", 3), (64, ">= 64", 3), (128, ">= 128", 3), (256, ">= 256 only", 3),
         (9999, "no conv (attn-block GEMMs still TC)", 3), (9999, "nothing: global SIMT engine", 0),
-        (0, "f16x3: all", 4), (32, "f16x3: output side >= 32", 4), (64, "f16x3: >= 64", 4), (128, "f16x3: >= 128", 4))
+        (0, "f16x3: all", 4), (32, "f16x3: output side >= 32", 4), (64, "f16x3: >= 64", 4), (128, "f16x3: >= 128", 4),
+        (0, "f16x3: all, K-split K>=5760", 5), (0, "f16x3: all, K-split K>=2880", 6),
+        (32, "f16x3: >= 32, K-split K>=5760", 5), (32, "f16x3: >= 32, K-split K>=2880", 6))
 if len(sys.argv) > 1:
     ROWS = tuple(r for r in ROWS if str(r[2]) in sys.argv[1:])
 for hw, what, eng in ROWS:
     vae.tc_min_hw = hw
-    ops.set_gemm_engine(eng)
-    tag = {3: "", 4: "'", 0: "*"}[eng]
+    vae.ksplit_min_k = {5: 5760, 6: 2880}.get(eng, 0)
+    ops.set_gemm_engine(4 if eng in (5, 6) else eng)
+    tag = {3: "", 4: "'", 0: "*", 5: "k", 6: "K"}[eng]
     mx, mean = 0.0, 0.0
     for f, r in zip(fs, refs):
         d = (vae.fhat_to_img(f.to(DEV)).cpu() - r).abs()

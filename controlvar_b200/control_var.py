@@ -326,53 +326,19 @@ class ControlVAR(nn.Module):
         rows).  replicas = 1: autoregressive_infer_cfg - one f_hat per sample, the next map is written to both CFG halves.
         replicas = groups = 4: conditional_infer_cfg - every replica row keeps its own samples and f_hat."""
         dev = self.device
-        cst = self._constants()
         vae = self.vae_proxy[0]
-        C, H, depth, V, Cvae = self.C, self.num_heads, self.depth, self.V, self.Cvae
-        R, T, hw = groups * B, self.L, self.patch_nums[-1]
+        C, V, Cvae = self.C, self.V, self.Cvae
+        R, hw = groups * B, self.patch_nums[-1]
         Bf = B * replicas                                   # samples that own an f_hat / a token row
         SN = len(self.patch_nums)
         lens = self.cfg.scale_lens
         lmax = max(lens)
-        attn_scale = self.cfg.attn_scale
-        lvl_pos = cst["lvl_pos"]
-
-        # ---- workspaces (cached across calls)
-        cond_BD = self._buf("cond_BD", (R, C))
-        silu_cond = self._buf("silu_cond", (R, C))
-        ada = self._buf("ada", (depth, R, 6 * C))
-        ada_head = self._buf("ada_head", (R, 2 * C))
-        x = self._buf("x", (R * lmax, C))
-        # engine 4 (f16x3): every dense-layer input is produced as an FP16 pair and never exists in fp32
-        f16 = cst["f16"]
-        kv16 = f16 and self.kv16
-        qbuf = None if kv16 else self._buf("q", (R * H * lmax * 64,))
-        q16 = self._pair("q16", (R * H * lmax * 64,)) if kv16 else None
-        xn16 = self._pair("xn16", (R * lmax, C)) if f16 else None
-        attn_o16 = self._pair("attn_o16", (R * lmax, C)) if f16 else None
-        hid16 = self._pair("hid16", (R * lmax, 4 * C)) if f16 else None
-        xn = None if f16 else self._buf("xn", (R * lmax, C))
-        attn_o = None if f16 else self._buf("attn_o", (R * lmax, C))
-        hid = None if f16 else self._buf("hid", (R * lmax, 4 * C))
-        # engine 3 (2-CTA all-TMA GEMM): every GEMM input is produced already split hi/lo; the '*_lo' halves live here
-        split = ops.get_gemm_engine() == ops.ENGINE_TC_2CTA
-        xn_lo = self._buf("xn_lo", (R * lmax, C)) if split else None
-        attn_o_lo = self._buf("attn_o_lo", (R * lmax, C)) if split else None
-        hid_lo = self._buf("hid_lo", (R * lmax, 4 * C)) if split else None
-        logits = self._buf("logits", (R * lmax, V))
+        tr = self._transformer(R)
+        cst, lvl_pos, x, logits = tr.cst, tr.lvl_pos, tr.x, tr.logits
         idx = self._buf("idx", (Bf * lmax,), torch.int64)
-        caches = self._kv_caches16(depth, R, H, T) if kv16 else self._kv_caches(depth, R, H, T)
         f_hat = self._buf("f_hat", (Bf, Cvae, 2 * hw, hw))
         f_hat.zero_()
-
-        # ---- prologue
-        ops.prologue_rows(self.get_parameter("class_emb.weight"),
-                          self.get_parameter("cond_embed.weight") if self.multi_cond else None, self.pos_start,
-                          lvl_pos, label_R, cond_R, cond_BD, silu_cond, x)
-        silu16 = ops.F16Pair.from_tensor(silu_cond, out=self._pair("silu16", (R, C))) if f16 else None
-        for bi, blk in enumerate(cst["blocks"]):       # ada_lin = Linear(SiLU(cond)): constant across scales
-            ops.gemm(silu_cond, blk["ada_w"], blk["ada_b"], ada[bi], R, 6 * C, C, A16=silu16)
-        ops.gemm(silu_cond, cst["head_ada_w"], cst["head_ada_b"], ada_head, R, 2 * C, C)
+        tr.prologue(label_R, cond_R)
 
         self.last_idx = []
         self.last_logits = []
@@ -382,30 +348,7 @@ class ControlVAR(nn.Module):
             M = R * l
             L_prev = cur_L
             cur_L += l
-            for bi, blk in enumerate(cst["blocks"]):
-                a = ada[bi]                                # (R, 6C): gamma1, gamma2, scale1, scale2, shift1, shift2
-                g1, g2, s1, s2, b1, b2 = (a[:, k * C:(k + 1) * C] for k in range(6))
-                ops.ln_modulate(x, s1, b1, 6 * C, xn, M, C, l, self.norm_eps, out_lo=xn_lo, out16=xn16)
-                if kv16:
-                    ops.qkv_project16(xn16, blk["qkv_w"], blk["q_bias"], blk["k_bias"], blk["v_bias"], q16, caches[bi],
-                                      R, l, L_prev, H, self.cos_attn, blk["scale_mul"])
-                    ops.attn_kvcache16(q16, caches[bi], None, R, H, l, cur_L, attn_scale, out16=attn_o16)
-                else:
-                    ops.qkv_project(xn, blk["qkv_w"], blk["q_bias"], blk["k_bias"], blk["v_bias"], qbuf, caches[bi],
-                                    R, l, L_prev, H, self.cos_attn, blk["scale_mul"], A_lo=xn_lo, A16=xn16)
-                    ops.attn_kvcache(qbuf, caches[bi], attn_o, R, H, l, cur_L, attn_scale, out_lo=attn_o_lo,
-                                     out16=attn_o16)
-                ops.gemm(attn_o, blk["proj_w"], blk["proj_b"], x, M, C, C, A_lo=attn_o_lo, A16=attn_o16,
-                         epilogue=ops.EPI_BIAS_GAMMA_RESID, gamma=g1, gamma_row_stride=6 * C, rows_per_sample=l)
-                ops.ln_modulate(x, s2, b2, 6 * C, xn, M, C, l, self.norm_eps, out_lo=xn_lo, out16=xn16)
-                ops.gemm(xn, blk["fc1_w"], blk["fc1_b"], hid, M, 4 * C, C, epilogue=ops.EPI_BIAS_GELU, A_lo=xn_lo,
-                         out_lo=hid_lo, A16=xn16, out16=hid16)
-                ops.gemm(hid, blk["fc2_w"], blk["fc2_b"], x, M, C, 4 * C, A_lo=hid_lo, A16=hid16,
-                         epilogue=ops.EPI_BIAS_GAMMA_RESID, gamma=g2, gamma_row_stride=6 * C, rows_per_sample=l)
-            # head: AdaLNBeforeHead + Linear(C, V)
-            ops.ln_modulate(x, ada_head[:, :C], ada_head[:, C:], 2 * C, xn, M, C, l, self.norm_eps, out_lo=xn_lo,
-                            out16=xn16)
-            ops.gemm(xn, cst["head_w"], self.get_parameter("head.bias"), logits, M, V, C, A_lo=xn_lo, A16=xn16)
+            tr.scale(l, L_prev)                               # blocks + head: logits (R*l, V)
             # guidance mix + top-k/top-p + multinomial
             ts = mix(si / self.num_stages_minus_1)
             if self.debug_noise_fn is not None:
@@ -444,5 +387,129 @@ class ControlVAR(nn.Module):
         self.last_f_hat = f_hat
         return img
 
-    def forward(self, *a, **k):
-        raise NotImplementedError("ControlVAR.forward is the training pass of the reference and is out of scope here")
+    def _transformer(self, R: int) -> "_Transformer":
+        return _Transformer(self, R)
+
+    # ----------------------------------------------------------------------------------- teacher-forced pass
+    @torch.no_grad()
+    def forward(self, label_B: torch.LongTensor, x_BLCv_wo_first_l: torch.Tensor, cond_type, mask_first=True) -> torch.Tensor:
+        """Drop-in for ControlVAR.forward (control_var.py:566-651), inference only: logits (B, L, V) of the teacher-forced
+        token pyramid.  The block-causal mask of control_var.py:168 (a query sees the keys of its own and of all coarser
+        scales) is realised without a mask: the scales are run one after the other against the growing KV cache, which
+        is the same computation (SURVEY.md section 4 identity; tests/test_oracle_golden.py checks it on the oracle).
+        As in the reference, labels and condition types are dropped with probability cond_drop_rate by torch.rand draws
+        even in eval mode (:577, :584): set ``cond_drop_rate = 0`` for deterministic logits."""
+        if not self.pos_1LC.is_cuda:
+            raise RuntimeError("controlvar_b200.ControlVAR runs on CUDA only (no CPU fallback); call .cuda() first")
+        if not mask_first:
+            raise NotImplementedError("mask_first=False (image token before the control token) is not implemented")
+        if not self.multi_cond:
+            raise NotImplementedError("forward is implemented for the released configuration (multi_cond=True)")
+        dev = self.device
+        B = x_BLCv_wo_first_l.shape[0]
+        C, V, Cvae = self.C, self.V, self.Cvae
+        assert x_BLCv_wo_first_l.shape == (B, self.L - self.first_l, Cvae)
+        label_B = label_B.to(device=dev, dtype=torch.long)
+        cond_type = cond_type.to(device=dev, dtype=torch.long)
+        label_B = torch.where(torch.rand(B, device=dev) < self.cond_drop_rate, self.num_classes, label_B)      # :577
+        cond_type = torch.where(torch.rand(B, device=dev) < self.cond_drop_rate, 4, cond_type)                # :584
+        xin = x_BLCv_wo_first_l.to(device=dev, dtype=torch.float32).contiguous()
+        tr = self._transformer(B)
+        tr.prologue(label_B.contiguous(), cond_type.contiguous())
+        out = torch.empty(B, self.L, V, device=dev, dtype=torch.float32)
+        ww, wb = self.get_parameter("word_embed.weight"), self.get_parameter("word_embed.bias")
+        Lin = self.L - self.first_l
+        cur_L = 0
+        for si, l in enumerate(self.cfg.scale_lens):
+            if si > 0:
+                # x = word_embed(teacher tokens) + (lvl_embed + pos_1LC): one batched K = 32 GEMM, the positional rows
+                # enter as a residual shared by the batch (:616, :618)
+                a0 = cur_L - self.first_l
+                ops.gemm(xin[:, a0:a0 + l], ww, wb, tr.x, l, C, Cvae, lda=Cvae, epilogue=ops.EPI_BIAS_RESID,
+                         resid=tr.lvl_pos[cur_L:cur_L + l], ldr=C, strideR=0, batch=B, strideA=Lin * Cvae, strideW=0,
+                         strideO=l * C)
+            tr.scale(l, cur_L)
+            out[:, cur_L:cur_L + l].copy_(tr.logits[:B * l].view(B, l, V))
+            cur_L += l
+        return out
+
+
+class _Transformer:
+    """Workspaces and launch sequence of the AdaLN transformer for R rows (the part autoregressive_infer_cfg,
+    conditional_infer_cfg and forward share): prologue -> per scale, depth x AdaLNSABlock + head -> logits."""
+
+    def __init__(self, m: "ControlVAR", R: int):
+        self.m, self.R = m, R
+        cst = self.cst = m._constants()
+        C, H, depth, V, T = m.C, m.num_heads, m.depth, m.V, m.L
+        lmax = max(m.cfg.scale_lens)
+        self.lvl_pos = cst["lvl_pos"]
+        # ---- workspaces (cached across calls)
+        self.cond_BD = m._buf("cond_BD", (R, C))
+        self.silu_cond = m._buf("silu_cond", (R, C))
+        self.ada = m._buf("ada", (depth, R, 6 * C))
+        self.ada_head = m._buf("ada_head", (R, 2 * C))
+        self.x = m._buf("x", (R * lmax, C))
+        # engine 4 (f16x3): every dense-layer input is produced as an FP16 pair and never exists in fp32
+        f16 = self.f16 = cst["f16"]
+        kv16 = self.kv16 = f16 and m.kv16
+        self.qbuf = None if kv16 else m._buf("q", (R * H * lmax * 64,))
+        self.q16 = m._pair("q16", (R * H * lmax * 64,)) if kv16 else None
+        self.xn16 = m._pair("xn16", (R * lmax, C)) if f16 else None
+        self.attn_o16 = m._pair("attn_o16", (R * lmax, C)) if f16 else None
+        self.hid16 = m._pair("hid16", (R * lmax, 4 * C)) if f16 else None
+        self.xn = None if f16 else m._buf("xn", (R * lmax, C))
+        self.attn_o = None if f16 else m._buf("attn_o", (R * lmax, C))
+        self.hid = None if f16 else m._buf("hid", (R * lmax, 4 * C))
+        # engine 3 (2-CTA all-TMA GEMM): every GEMM input is produced already split hi/lo; the '*_lo' halves live here
+        split = ops.get_gemm_engine() == ops.ENGINE_TC_2CTA
+        self.xn_lo = m._buf("xn_lo", (R * lmax, C)) if split else None
+        self.attn_o_lo = m._buf("attn_o_lo", (R * lmax, C)) if split else None
+        self.hid_lo = m._buf("hid_lo", (R * lmax, 4 * C)) if split else None
+        self.logits = m._buf("logits", (R * lmax, V))
+        self.caches = m._kv_caches16(depth, R, H, T) if kv16 else m._kv_caches(depth, R, H, T)
+
+    def prologue(self, label_R: torch.Tensor, cond_R: torch.Tensor) -> None:
+        """Start tokens of scale 0 into x, cond_BD, and every ada_lin = Linear(SiLU(cond)) (constant across scales)."""
+        m, R, C, cst = self.m, self.R, self.m.C, self.cst
+        ops.prologue_rows(m.get_parameter("class_emb.weight"),
+                          m.get_parameter("cond_embed.weight") if m.multi_cond else None, m.pos_start,
+                          self.lvl_pos, label_R, cond_R, self.cond_BD, self.silu_cond, self.x)
+        silu16 = ops.F16Pair.from_tensor(self.silu_cond, out=m._pair("silu16", (R, C))) if self.f16 else None
+        for bi, blk in enumerate(cst["blocks"]):
+            ops.gemm(self.silu_cond, blk["ada_w"], blk["ada_b"], self.ada[bi], R, 6 * C, C, A16=silu16)
+        ops.gemm(self.silu_cond, cst["head_ada_w"], cst["head_ada_b"], self.ada_head, R, 2 * C, C)
+
+    def scale(self, l: int, L_prev: int) -> None:
+        """x (R*l, C) of one scale through all blocks (keys / values appended at L_prev) and the head -> self.logits."""
+        m, R, cst = self.m, self.R, self.cst
+        C, H, V = m.C, m.num_heads, m.V
+        M, cur_L = R * l, L_prev + l
+        x, xn, xn_lo, xn16 = self.x, self.xn, self.xn_lo, self.xn16
+        attn_o, attn_o_lo, attn_o16 = self.attn_o, self.attn_o_lo, self.attn_o16
+        hid, hid_lo, hid16 = self.hid, self.hid_lo, self.hid16
+        attn_scale = m.cfg.attn_scale
+        for bi, blk in enumerate(cst["blocks"]):
+            a = self.ada[bi]                               # (R, 6C): gamma1, gamma2, scale1, scale2, shift1, shift2
+            g1, g2, s1, s2, b1, b2 = (a[:, k * C:(k + 1) * C] for k in range(6))
+            ops.ln_modulate(x, s1, b1, 6 * C, xn, M, C, l, m.norm_eps, out_lo=xn_lo, out16=xn16)
+            if self.kv16:
+                ops.qkv_project16(xn16, blk["qkv_w"], blk["q_bias"], blk["k_bias"], blk["v_bias"], self.q16,
+                                  self.caches[bi], R, l, L_prev, H, m.cos_attn, blk["scale_mul"])
+                ops.attn_kvcache16(self.q16, self.caches[bi], None, R, H, l, cur_L, attn_scale, out16=attn_o16)
+            else:
+                ops.qkv_project(xn, blk["qkv_w"], blk["q_bias"], blk["k_bias"], blk["v_bias"], self.qbuf, self.caches[bi],
+                                R, l, L_prev, H, m.cos_attn, blk["scale_mul"], A_lo=xn_lo, A16=xn16)
+                ops.attn_kvcache(self.qbuf, self.caches[bi], attn_o, R, H, l, cur_L, attn_scale, out_lo=attn_o_lo,
+                                 out16=attn_o16)
+            ops.gemm(attn_o, blk["proj_w"], blk["proj_b"], x, M, C, C, A_lo=attn_o_lo, A16=attn_o16,
+                     epilogue=ops.EPI_BIAS_GAMMA_RESID, gamma=g1, gamma_row_stride=6 * C, rows_per_sample=l)
+            ops.ln_modulate(x, s2, b2, 6 * C, xn, M, C, l, m.norm_eps, out_lo=xn_lo, out16=xn16)
+            ops.gemm(xn, blk["fc1_w"], blk["fc1_b"], hid, M, 4 * C, C, epilogue=ops.EPI_BIAS_GELU, A_lo=xn_lo,
+                     out_lo=hid_lo, A16=xn16, out16=hid16)
+            ops.gemm(hid, blk["fc2_w"], blk["fc2_b"], x, M, C, 4 * C, A_lo=hid_lo, A16=hid16,
+                     epilogue=ops.EPI_BIAS_GAMMA_RESID, gamma=g2, gamma_row_stride=6 * C, rows_per_sample=l)
+        # head: AdaLNBeforeHead + Linear(C, V)
+        ah = self.ada_head
+        ops.ln_modulate(x, ah[:, :C], ah[:, C:], 2 * C, xn, M, C, l, m.norm_eps, out_lo=xn_lo, out16=xn16)
+        ops.gemm(xn, cst["head_w"], m.get_parameter("head.bias"), self.logits, M, V, C, A_lo=xn_lo, A16=xn16)

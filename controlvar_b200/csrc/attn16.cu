@@ -1,25 +1,27 @@
 // KV-cached attention on FP16-pair operands (engine 4): basic_var.py:106-117, same contract as attn.cu.
 //
-// q, K and V^T arrive as FP16 pairs (x ~= hi + lo * 2^-11, cvar_split_f16) written by cvar_qkv_project16, i.e. half the
-// bytes of the TF32 hi/lo split the first tensor-core kernel used, and the products run as three kind::f16 MMAs
-// (hi*hi into a main accumulator; hi*lo + lo*hi into a cross accumulator that is folded in with one FMA) at twice the
-// TF32 tensor rate.  Design of the tensor-core kernel (attn16_tc_kernel):
+// q, K and V^T arrive as FP16 pairs written by cvar_qkv_project16 (V^T: x ~= hi + lo * 2^-11, cvar_split_f16; q, K:
+// 16 x = hi + lo), i.e. half the bytes of the TF32 hi/lo split the first tensor-core kernel used, and the products run
+// as three kind::f16 MMAs (hi*hi, hi*lo, lo*hi) at twice the TF32 tensor rate.  Design of the tensor-core kernel (attn16_tc_kernel):
 //   * CTA = 128 queries of one (row, head), 192 threads, and TWO CTAs per SM: everything is sized to half an SM
 //     (256 TMEM columns, 97 KB shared memory, <= 168 registers), so the softmax of one CTA overlaps the MMAs of the other.
 //     The measured limiter of the TF32 kernel was the softmax warpgroup (~3100 cycles per 64-key tile against 1536 of
 //     MMA, profiles/r01_attn_trace.md), and its 448 TMEM columns / 255 registers allowed one CTA per SM only.
 //   * Q tile (128 x 64, hi and lo) and the K / V^T tiles (64 x 64) are fetched by TMA straight from the pair arrays:
 //     one 128-byte-swizzled block each, no operand conversion anywhere.
-//   * S = Q K^T lands in TMEM (main + cross); the softmax thread (one per query row) reads it in 16-column chunks, writes
-//     P back as an FP16 pair OVER the S_main columns it has just consumed (chunk c: hi in columns [16c, 16c+8), lo in
-//     [16c+8, 16c+16), two keys per 32-bit cell) and P @ V reads its A operand from there.  tcgen05.mma executes in issue
-//     order, so S(j+1), issued after P@V(j), may overwrite those columns.
+//   * q and K are "qk pairs" (16 x = hi + lo, un-scaled residual, common.cuh), so S = Q K^T needs ONE accumulator and
+//     the 256 TMEM columns hold TWO S buffers: S(j+1) and S(j+2) are issued ahead and the softmax warpgroup never waits
+//     for the tensor core in steady state (v2, with a main + cross S accumulator and a single buffer, spent 30 % of its
+//     warp samples in the s_full poll loop: profiles/r01_attn16.md).  The softmax thread (one per query row) reads S in
+//     16-column chunks and writes P back as a standard FP16 pair OVER the cells it has just consumed (chunk c: hi in
+//     columns [16c, 16c+8), lo in [16c+8, 16c+16), two keys per 32-bit cell); P @ V reads its A operand from there.
+//     tcgen05.mma executes in issue order, so S(j+2), issued after P @ V(j), may overwrite those cells.
 //   * O accumulates in TMEM for kDrain = 4 tiles (48 truncating MMA steps) and is then added into the running output
 //     row in registers with round-to-nearest adds.  The exponentials are taken against a reference that is the first tile's
 //     row maximum and moves only when a later tile's maximum exceeds it by 2^8 (then that row rescales what it has
 //     accumulated, in registers and in its TMEM row), so the common tile does no rescaling work at all.  Two 16-bit values
 //     per TMEM cell, the lower key index in the low half (A operand of kind::f16 from tensor memory).
-//   TMEM columns: S_main/P [0,64)  S_x [64,128)  O_main [128,192)  O_x [192,256)
+//   TMEM columns: S/P buffer 0 [0,64)  S/P buffer 1 [64,128)  O_main [128,192)  O_x [192,256)
 #include <type_traits>
 #include "common.cuh"
 #include "tc_ptx.cuh"
@@ -37,6 +39,15 @@ __device__ __forceinline__ float4 ld4_pair(const __half* hi, const __half* lo, l
   const __half2 b0 = *reinterpret_cast<const __half2*>(&b.x), b1 = *reinterpret_cast<const __half2*>(&b.y);
   return make_float4(pair_val(__low2half(a0), __low2half(b0)), pair_val(__high2half(a0), __high2half(b0)),
                      pair_val(__low2half(a1), __low2half(b1)), pair_val(__high2half(a1), __high2half(b1)));
+}
+
+// four consecutive elements of a qk pair array (16 x = hi + lo, split_f16_qk)
+__device__ __forceinline__ float4 ld4_qk(const __half* hi, const __half* lo, long long off) {
+  const uint2 a = *reinterpret_cast<const uint2*>(hi + off), b = *reinterpret_cast<const uint2*>(lo + off);
+  const float2 a0 = __half22float2(*reinterpret_cast<const __half2*>(&a.x)), a1 = __half22float2(*reinterpret_cast<const __half2*>(&a.y));
+  const float2 b0 = __half22float2(*reinterpret_cast<const __half2*>(&b.x)), b1 = __half22float2(*reinterpret_cast<const __half2*>(&b.y));
+  constexpr float inv = 1.0f / kQkScale;
+  return make_float4((a0.x + b0.x) * inv, (a0.y + b0.y) * inv, (a1.x + b1.x) * inv, (a1.y + b1.y) * inv);
 }
 
 // ---------------------------------------------------------------------------------------------------- SIMT kernel
@@ -69,7 +80,7 @@ attn16_simt_kernel(const __half* __restrict__ q_hi, const __half* __restrict__ q
     int item = it * 256 + tid;
     int i = item & 63, dq = item >> 6;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (q0 + i < l) v = ld4_pair(q_hi, q_lo, q_off + (long long)(q0 + i) * D + dq * 4);
+    if (q0 + i < l) v = ld4_qk(q_hi, q_lo, q_off + (long long)(q0 + i) * D + dq * 4);
     sm.Qt[dq * 4 + 0][i] = v.x * scale;
     sm.Qt[dq * 4 + 1][i] = v.y * scale;
     sm.Qt[dq * 4 + 2][i] = v.z * scale;
@@ -92,7 +103,7 @@ attn16_simt_kernel(const __half* __restrict__ q_hi, const __half* __restrict__ q
       int item = it * 256 + tid;
       int j = item & 63, dq = item >> 6;
       float4 kv = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (k0 + j < L) kv = ld4_pair(k_hi, k_lo, kv_off + (long long)(k0 + j) * D + dq * 4);
+      if (k0 + j < L) kv = ld4_qk(k_hi, k_lo, kv_off + (long long)(k0 + j) * D + dq * 4);
       sm.Kt[dq * 4 + 0][j] = kv.x;
       sm.Kt[dq * 4 + 1][j] = kv.y;
       sm.Kt[dq * 4 + 2][j] = kv.z;
@@ -195,10 +206,11 @@ constexpr int BQ = 128, BKV = 64, D = 64;
 constexpr int kThreads = 192;
 constexpr int kTile = BKV * 128;                  // 64 rows x 128 B: one K or V^T tile half (hi or lo), 8 KB
 constexpr int kQTile = BQ * 128;                  // 128 rows x 128 B: Q hi or lo, 16 KB
-constexpr int kStageBytes = 4 * kTile;            // K_hi | K_lo | VT_hi | VT_lo = 32 KB
+constexpr int kStageBytes = 4 * kTile;            // K_hi | K_lo | VT_hi | VT_lo = 32 KB (K and V^T halves have separate barriers)
 constexpr int kStages = 2;
 constexpr int kSmem = 1024 + 2 * kQTile + kStages * kStageBytes + 256;     // 99,584 B: two CTAs per SM
-constexpr uint32_t kColS = 0, kColSx = 64, kColO = 128, kColOx = 192, kTmemCols = 256;
+// S has ONE accumulator (q, k are qk pairs) and two buffers: S(j) lives in buffer j & 1 at column 64 * (j & 1)
+constexpr uint32_t kColS = 0, kColO = 128, kColOx = 192, kTmemCols = 256;
 // O stays in TMEM for kDrain tiles (kDrain * 12 truncating accumulation steps) before it is added into the fp32 registers
 constexpr int kDrain = 4;
 // the softmax reference moves when a logit exceeds it by more than 2^kRebase (p <= 256: far inside fp16 / fp32 range)
@@ -296,13 +308,21 @@ attn16_tc_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_consta
   unsigned char* q_s = smem;                                        // Q_hi | Q_lo
   auto stage = [&](int s) { return smem + 2 * kQTile + s * kStageBytes; };
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kQTile + kStages * kStageBytes);
-  uint64_t* kv_full = bars;                  // [kStages]
-  uint64_t* kv_empty = bars + kStages;       // [kStages]
-  uint64_t* q_full = bars + 2 * kStages;
-  uint64_t* s_full = bars + 2 * kStages + 1; // S(j) accumulated
-  uint64_t* p_ready = bars + 2 * kStages + 2;// P(j) in TMEM and O_tile(j-1) read, by all 128 softmax threads
-  uint64_t* o_full = bars + 2 * kStages + 3; // O_tile(j) accumulated
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  uint64_t* k_full = bars;                   // [kStages]  K tile landed
+  uint64_t* k_empty = bars + kStages;        // [kStages]  S(j) has read it
+  uint64_t* v_full = bars + 2 * kStages;     // [kStages]  V^T tile landed
+  uint64_t* v_empty = bars + 3 * kStages;    // [kStages]  P @ V(j) has read it
+  uint64_t* s_full = bars + 4 * kStages;     // [2]        S(j) accumulated in buffer j & 1
+  uint64_t* q_full = bars + 4 * kStages + 2;
+  // P(j) in TMEM (and O drained when due), by all 128 softmax threads.  TWO barriers, indexed by the S buffer: with S
+  // issued ahead the softmax can finish tile j+1 before the MMA thread has looked at tile j, and a single barrier would
+  // then be two phases ahead of its waiter - whose parity test can no longer tell "done" from "not yet".
+  uint64_t* p_ready = bars + 4 * kStages + 3;// [2]
+  // P @ V(j) accumulated: also two barriers (j & 1).  A softmax thread that waits for P @ V(j-1) only knows that
+  // P @ V(j-3) has completed (S(j), which it has consumed, was issued behind P @ V(j-2) and completes in order); on a
+  // single barrier that is two phases back and the parity test would pass at once.
+  uint64_t* o_full = bars + 4 * kStages + 5; // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 * kStages + 7);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * BQ, h = blockIdx.y, r = blockIdx.z;
@@ -312,11 +332,12 @@ attn16_tc_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_consta
   if (warp == 4 && lane == 0) {
     tma_prefetch_desc(&mapQhi), tma_prefetch_desc(&mapQlo);
     tma_prefetch_desc(&mapKhi), tma_prefetch_desc(&mapKlo), tma_prefetch_desc(&mapVhi), tma_prefetch_desc(&mapVlo);
-    for (int s = 0; s < kStages; ++s) mbar_init(&kv_full[s], 1), mbar_init(&kv_empty[s], 1);
+    for (int s = 0; s < kStages; ++s)
+      mbar_init(&k_full[s], 1), mbar_init(&k_empty[s], 1), mbar_init(&v_full[s], 1), mbar_init(&v_empty[s], 1);
     mbar_init(q_full, 1);
-    mbar_init(s_full, 1);
-    mbar_init(p_ready, 128);
-    mbar_init(o_full, 1);
+    mbar_init(&s_full[0], 1), mbar_init(&s_full[1], 1);
+    mbar_init(&p_ready[0], 128), mbar_init(&p_ready[1], 128);
+    mbar_init(&o_full[0], 1), mbar_init(&o_full[1], 1);
     fence_barrier_init();
   }
   if (warp == 5) tmem_alloc_n(tmem_slot, kTmemCols);
@@ -335,7 +356,8 @@ attn16_tc_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_consta
     const uint32_t tl = tmem_base + ((uint32_t)(warp * 32) << 16);
     // p = exp((s - ref) * scale) = 2^((s - ref) * scale * log2 e): the difference is formed first, so the rounding of the
     // product is a relative error of |t| * 2^-24 on a term of weight e^t
-    const float sl2 = scale * 1.4426950408889634f;
+    // S holds 256 q.k (both operands are qk pairs, 16 x = hi + lo): the factor is folded into the exponent scale
+    const float sl2 = scale * 1.4426950408889634f * (1.0f / (kQkScale * kQkScale));
     float o_reg[D];
 #pragma unroll
     for (int d = 0; d < D; ++d) o_reg[d] = 0.f;
@@ -344,12 +366,11 @@ attn16_tc_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_consta
     // one 16-key chunk: p for the chunk, written back over the S_main cells it came from as an FP16 pair
     // nref = -ref * scale * log2e; t = fma(s, sl2, nref): the product is exact inside the FMA, and the rounding of nref
     // is a factor common to every key of the row (it cancels in the normalisation)
-    auto chunk = [&](auto masked, int c, const float* a, const float* b, float nref, int nvalid, float& rs) {
+    auto chunk = [&](auto masked, uint32_t sb, int c, const float* a, float nref, int nvalid, float& rs) {
       uint32_t ph[8], pl[8];
 #pragma unroll
       for (int i = 0; i < 16; i += 2) {
-        const float s0 = fmaf(b[i], kInvLo, a[i]), s1 = fmaf(b[i + 1], kInvLo, a[i + 1]);
-        float p0 = ex2_approx(fmaf(s0, sl2, nref)), p1 = ex2_approx(fmaf(s1, sl2, nref));
+        float p0 = ex2_approx(fmaf(a[i], sl2, nref)), p1 = ex2_approx(fmaf(a[i + 1], sl2, nref));
         if constexpr (decltype(masked)::value) {   // last tile only: keys past L contribute nothing
           if (16 * c + i >= nvalid) p0 = 0.f;
           if (16 * c + i + 1 >= nvalid) p1 = 0.f;
@@ -361,32 +382,28 @@ attn16_tc_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_consta
         ph[i >> 1] = *reinterpret_cast<const uint32_t*>(&h);
         pl[i >> 1] = *reinterpret_cast<const uint32_t*>(&lo);
       }
-      tmem_st_32x32b_x8(tl + kColS + 16 * c, ph);
-      tmem_st_32x32b_x8(tl + kColS + 16 * c + 8, pl);
+      tmem_st_32x32b_x8(tl + sb + 16 * c, ph);
+      tmem_st_32x32b_x8(tl + sb + 16 * c + 8, pl);
     };
     // the whole tile against reference `ref`; chunk loads are prefetched one ahead (one exposed TMEM round trip)
-    auto tile_pass = [&](auto masked, float nref, int nvalid, float& rs) {
-      float a0[16], b0[16], a1[16], b1[16];
-      tmem_ld_nowait_x16(tl + kColS, a0);
-      tmem_ld_nowait_x16(tl + kColSx, b0);
+    auto tile_pass = [&](auto masked, uint32_t sb, float nref, int nvalid, float& rs) {
+      float a0[16], a1[16];
+      tmem_ld_nowait_x16(tl + sb, a0);
       tmem_wait_ld();
-      reg_fence16(a0), reg_fence16(b0);
-      tmem_ld_nowait_x16(tl + kColS + 16, a1);
-      tmem_ld_nowait_x16(tl + kColSx + 16, b1);
-      chunk(masked, 0, a0, b0, nref, nvalid, rs);
+      reg_fence16(a0);
+      tmem_ld_nowait_x16(tl + sb + 16, a1);
+      chunk(masked, sb, 0, a0, nref, nvalid, rs);
       tmem_wait_ld();
-      reg_fence16(a1), reg_fence16(b1);
-      tmem_ld_nowait_x16(tl + kColS + 32, a0);
-      tmem_ld_nowait_x16(tl + kColSx + 32, b0);
-      chunk(masked, 1, a1, b1, nref, nvalid, rs);
+      reg_fence16(a1);
+      tmem_ld_nowait_x16(tl + sb + 32, a0);
+      chunk(masked, sb, 1, a1, nref, nvalid, rs);
       tmem_wait_ld();
-      reg_fence16(a0), reg_fence16(b0);
-      tmem_ld_nowait_x16(tl + kColS + 48, a1);
-      tmem_ld_nowait_x16(tl + kColSx + 48, b1);
-      chunk(masked, 2, a0, b0, nref, nvalid, rs);
+      reg_fence16(a0);
+      tmem_ld_nowait_x16(tl + sb + 48, a1);
+      chunk(masked, sb, 2, a0, nref, nvalid, rs);
       tmem_wait_ld();
-      reg_fence16(a1), reg_fence16(b1);
-      chunk(masked, 3, a1, b1, nref, nvalid, rs);
+      reg_fence16(a1);
+      chunk(masked, sb, 3, a1, nref, nvalid, rs);
     };
     // o_reg += O accumulated in TMEM (round-to-nearest adds)
     auto drain_O = [&]() {
@@ -403,17 +420,16 @@ attn16_tc_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_consta
     };
 
     for (int j = 0; j < ntiles; ++j) {
-      mbar_wait(s_full, j & 1);
+      const uint32_t sb = kColS + 64u * (uint32_t)(j & 1);        // S(j) / P(j) buffer
+      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
       tc_fence_after();
       const int nvalid = min(BKV, L - j * BKV);
-      // O of the tiles since the last drain is complete here: the commit behind s_full(j) covers P @ V(j-1)
-      if (j > 0 && (j % kDrain) == 0) drain_O();
-      // pass 1: row maximum of S_main (the cross accumulator is ~2^-11 of it: the reference need not be exact)
+      // pass 1: row maximum of the tile
       float mx = -INFINITY;
       {
         float a[32], b[32];
-        tmem_ld_nowait_x32(tl + kColS, a);
-        tmem_ld_nowait_x32(tl + kColS + 32, b);
+        tmem_ld_nowait_x32(tl + sb, a);
+        tmem_ld_nowait_x32(tl + sb + 32, b);
         tmem_wait_ld();
         reg_fence32(a), reg_fence32(b);
         if (nvalid < 64) {
@@ -428,15 +444,23 @@ attn16_tc_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_consta
         }
       }
       const bool need = j > 0 && (mx - m_ref) * sl2 > kRebase;
+      bool drained = false;
       if (j == 0) {
         m_ref = mx;
       } else if (__any_sync(0xffffffffu, need)) {
         // A key far above the reference (p would exceed 2^kRebase): move the reference to it.  Rare after the first
         // tiles - the reference only has to stay within a factor 2^kRebase of the true maximum.  Everything accumulated
-        // so far is rescaled: registers, the running sum, and this row of the O accumulators in TMEM.  The TMEM
-        // instructions are warp-collective, so the whole warp takes the path; rows that keep their reference use corr = 1.
+        // so far is rescaled: registers, the running sum, and this row of the O accumulators in TMEM (P @ V(j-1) may
+        // still be running: wait for it).  The TMEM instructions are warp-collective, so the whole warp takes the
+        // path; rows that keep their reference use corr = 1.
         const float corr = need ? ex2_approx((m_ref - mx) * sl2) : 1.0f;
         if (need) m_ref = mx;
+        mbar_wait(&o_full[(j - 1) & 1], ((j - 1) >> 1) & 1);
+        tc_fence_after();
+        if ((j % kDrain) == 0) {       // a drain tile: what the accumulators hold is under the OLD reference - take it first
+          drain_O();
+          drained = true;
+        }
         l_run *= corr;
 #pragma unroll
         for (int d = 0; d < D; ++d) o_reg[d] *= corr;
@@ -459,15 +483,22 @@ attn16_tc_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_consta
       float rs = 0.f;
       const float nref = -m_ref * sl2;
       if (nvalid < BKV)
-        tile_pass(std::true_type{}, nref, nvalid, rs);
+        tile_pass(std::true_type{}, sb, nref, nvalid, rs);
       else
-        tile_pass(std::false_type{}, nref, nvalid, rs);
+        tile_pass(std::false_type{}, sb, nref, nvalid, rs);
       l_run += rs;
+      // every kDrain tiles the O accumulators move into the registers; P @ V(j) then starts fresh.  Done at the END of
+      // the tile's softmax: P @ V(j-1), issued when this warpgroup finished tile j-1, has long completed by now.
+      if (j > 0 && (j % kDrain) == 0 && !drained) {
+        mbar_wait(&o_full[(j - 1) & 1], ((j - 1) >> 1) & 1);
+        tc_fence_after();
+        drain_O();
+      }
       tmem_wait_st();
       tc_fence_before();
-      mbar_arrive(p_ready);
+      mbar_arrive(&p_ready[j & 1]);
     }
-    mbar_wait(o_full, (ntiles - 1) & 1);
+    mbar_wait(&o_full[(ntiles - 1) & 1], ((ntiles - 1) >> 1) & 1);
     tc_fence_after();
     const int t = q0 + row;
     const float inv = 1.0f / l_run;
@@ -496,57 +527,71 @@ attn16_tc_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_consta
       tma_load_3d(&mapQlo, q_full, q_s + kQTile, 0, q0, rh);
       for (int j = 0; j < ntiles; ++j) {
         const int s = j % kStages;
-        mbar_wait(&kv_empty[s], ((j / kStages) & 1) ^ 1);
-        mbar_arrive_expect_tx(&kv_full[s], (uint32_t)kStageBytes);
+        const uint32_t ph = ((j / kStages) & 1) ^ 1;
         unsigned char* st = stage(s);
-        tma_load_3d(&mapKhi, &kv_full[s], st + 0 * kTile, 0, j * BKV, rh);
-        tma_load_3d(&mapKlo, &kv_full[s], st + 1 * kTile, 0, j * BKV, rh);
-        tma_load_3d(&mapVhi, &kv_full[s], st + 2 * kTile, j * BKV, 0, rh);
-        tma_load_3d(&mapVlo, &kv_full[s], st + 3 * kTile, j * BKV, 0, rh);
+        mbar_wait(&k_empty[s], ph);                        // released by S(j - kStages): early
+        mbar_arrive_expect_tx(&k_full[s], (uint32_t)(2 * kTile));
+        tma_load_3d(&mapKhi, &k_full[s], st + 0 * kTile, 0, j * BKV, rh);
+        tma_load_3d(&mapKlo, &k_full[s], st + 1 * kTile, 0, j * BKV, rh);
+        mbar_wait(&v_empty[s], ph);                        // released by P @ V(j - kStages): a softmax later
+        mbar_arrive_expect_tx(&v_full[s], (uint32_t)(2 * kTile));
+        tma_load_3d(&mapVhi, &v_full[s], st + 2 * kTile, j * BKV, 0, rh);
+        tma_load_3d(&mapVlo, &v_full[s], st + 3 * kTile, j * BKV, 0, rh);
       }
     }
   } else {
     // ================================================================ MMA issue
     if (lane == 0) {
       const uint64_t dqh = G::desc(smem_u32(q_s)), dql = G::desc(smem_u32(q_s + kQTile));
+      // S(j) = Q K(j)^T into buffer j & 1: ONE accumulator.  The cross terms (~2^-11 of the result) go first, while the
+      // accumulator is small, so that the tensor core's truncation after every MMA acts on the big sum only during the
+      // last four steps (the hi * hi products), as with a separate cross accumulator.
       auto issue_S = [&](int j) {
-        unsigned char* st = stage(j % kStages);
+        const int s = j % kStages;
+        mbar_wait(&k_full[s], (j / kStages) & 1);
+        tc_fence_after();
+        unsigned char* st = stage(s);
+        const uint32_t d = tmem_base + kColS + 64u * (uint32_t)(j & 1);
         const uint64_t dkh = G::desc(smem_u32(st)), dkl = G::desc(smem_u32(st + kTile));
 #pragma unroll
         for (int k = 0; k < 4; ++k) {                       // 16 head dims (32 bytes of a row) per MMA
           const uint64_t adv = (uint64_t)(2 * k);
-          umma_f16_ss(tmem_base + kColSx, dql + adv, dkh + adv, kIdesc, k != 0);
-          umma_f16_ss(tmem_base + kColSx, dqh + adv, dkl + adv, kIdesc, 1u);
-          umma_f16_ss(tmem_base + kColS, dqh + adv, dkh + adv, kIdesc, k != 0);
+          umma_f16_ss(d, dql + adv, dkh + adv, kIdesc, k != 0);
+          umma_f16_ss(d, dqh + adv, dkl + adv, kIdesc, 1u);
         }
-        umma_commit(s_full);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t adv = (uint64_t)(2 * k);
+          umma_f16_ss(d, dqh + adv, dkh + adv, kIdesc, 1u);
+        }
+        umma_commit(&s_full[j & 1]);
+        umma_commit(&k_empty[s]);
       };
       mbar_wait(q_full, 0);
-      mbar_wait(&kv_full[0], 0);
       tc_fence_after();
       issue_S(0);
+      if (ntiles > 1) issue_S(1);
       for (int j = 0; j < ntiles; ++j) {
-        mbar_wait(p_ready, j & 1);
+        const int s = j % kStages;
+        mbar_wait(&v_full[s], (j / kStages) & 1);
+        mbar_wait(&p_ready[j & 1], (j >> 1) & 1);
         tc_fence_after();
-        unsigned char* st = stage(j % kStages);
+        unsigned char* st = stage(s);
         const uint64_t dvh = G::desc(smem_u32(st + 2 * kTile)), dvl = G::desc(smem_u32(st + 3 * kTile));
+        const uint32_t pb = tmem_base + kColS + 64u * (uint32_t)(j & 1);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {                       // 16 keys per MMA: P cells [16k, 16k+8) hi, [16k+8, 16k+16) lo
           const uint64_t adv = (uint64_t)(2 * k);
-          const uint32_t p_hi = tmem_base + kColS + 16 * k, p_lo = p_hi + 8;
+          const uint32_t p_hi = pb + 16 * k, p_lo = p_hi + 8;
           const uint32_t acc = (k != 0 || (j % kDrain) != 0) ? 1u : 0u;   // fresh accumulators every kDrain tiles
           umma_f16_ts(tmem_base + kColOx, p_lo, dvh + adv, kIdesc, acc);
           umma_f16_ts(tmem_base + kColOx, p_hi, dvl + adv, kIdesc, 1u);
           umma_f16_ts(tmem_base + kColO, p_hi, dvh + adv, kIdesc, acc);
         }
-        umma_commit(o_full);
-        umma_commit(&kv_empty[j % kStages]);
-        if (j + 1 < ntiles) {
-          // in-order execution of tcgen05.mma: S(j+1) overwrites the P(j) cells only after P @ V(j) has read them
-          mbar_wait(&kv_full[(j + 1) % kStages], ((j + 1) / kStages) & 1);
-          tc_fence_after();
-          issue_S(j + 1);
-        }
+        umma_commit(&o_full[j & 1]);
+        umma_commit(&v_empty[s]);
+        // in-order execution of tcgen05.mma: S(j+2) overwrites the P(j) cells only after P @ V(j) has read them
+        if (j + 2 < ntiles) issue_S(j + 2);
       }
     }
   }

@@ -84,6 +84,30 @@ __device__ __forceinline__ void st4_split_f16(__half* hi, __half* lo, const floa
   *reinterpret_cast<uint2*>(lo) = pl;
 }
 
+// q / K operands of the f16 attention kernel: the value is pre-multiplied by 16 and the residual is stored UN-scaled,
+// x * 16 ~= h + l, so that q.k = (h_q h_k + h_q l_k + l_q h_k) / 256 accumulates in ONE tensor-core accumulator (the
+// standard pair needs a second one for the 2^-11-scaled cross terms).  The factor 16 keeps the residual of an O(1) value
+// a normal fp16 number; below that it is quantised to 2^-24 / 16 = 3.7e-9 absolute, far under fp32 resolution of a
+// dot product of O(1) terms.  |x| must be < 4094.
+constexpr float kQkScale = 16.0f;
+__device__ __forceinline__ void split_f16_qk(float x, __half& h, __half& l) {
+  x = fminf(fmaxf(x * kQkScale, -65504.0f), 65504.0f);
+  h = __float2half_rn(x);
+  l = __float2half_rn(x - __half2float(h));
+}
+__device__ __forceinline__ void st4_split_f16_qk(__half* hi, __half* lo, const float* r) {
+  __half h[4], l[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) split_f16_qk(r[j], h[j], l[j]);
+  uint2 ph, pl;
+  ph.x = (uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16);
+  ph.y = (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16);
+  pl.x = (uint32_t)__half_as_ushort(l[0]) | ((uint32_t)__half_as_ushort(l[1]) << 16);
+  pl.y = (uint32_t)__half_as_ushort(l[2]) | ((uint32_t)__half_as_ushort(l[3]) << 16);
+  *reinterpret_cast<uint2*>(hi) = ph;
+  *reinterpret_cast<uint2*>(lo) = pl;
+}
+
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 

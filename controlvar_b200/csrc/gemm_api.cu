@@ -164,8 +164,9 @@ __global__ void cos_attn_normalize16_kernel(__half* __restrict__ q_hi, __half* _
   __half* ph = (is_q ? q_hi : k_hi) + off;
   __half* pl = (is_q ? q_lo : k_lo) + off;
   const __half2 a = *reinterpret_cast<const __half2*>(ph), b = *reinterpret_cast<const __half2*>(pl);
-  float2 v = make_float2(fmaf(__half2float(__low2half(b)), 1.0f / kF16LoScale, __half2float(__low2half(a))),
-                         fmaf(__half2float(__high2half(b)), 1.0f / kF16LoScale, __half2float(__high2half(a))));
+  // qk pairs: 16 x = hi + lo
+  float2 v = make_float2((__half2float(__low2half(a)) + __half2float(__low2half(b))) * (1.0f / kQkScale),
+                         (__half2float(__high2half(a)) + __half2float(__high2half(b))) * (1.0f / kQkScale));
   float ss = warp_sum(v.x * v.x + v.y * v.y);
   float denom = fmaxf(sqrtf(ss), 1e-12f);
   v.x = v.x / denom;
@@ -176,8 +177,8 @@ __global__ void cos_attn_normalize16_kernel(__half* __restrict__ q_hi, __half* _
     v.y = __fmul_rn(v.y, mul);
   }
   __half h0, l0, h1, l1;
-  split_f16(v.x, h0, l0);
-  split_f16(v.y, h1, l1);
+  split_f16_qk(v.x, h0, l0);
+  split_f16_qk(v.y, h1, l1);
   *reinterpret_cast<__half2*>(ph) = __halves2half2(h0, h1);
   *reinterpret_cast<__half2*>(pl) = __halves2half2(l0, l1);
 }

@@ -277,7 +277,8 @@ struct QkvEpilogue {
   float* vt_lo;
   int C, H, l, L_prev, T_max;
   // FP16-pair form of the same three outputs (cvar_qkv_project16): when q16_hi is set, q / K / V^T are written as
-  // pairs (hi + lo * 2^-11, cvar_split_f16) with the same index layout and the fp32 pointers above are ignored.
+  // pairs with the same index layout and the fp32 pointers above are ignored: V^T as a standard pair (hi + lo * 2^-11,
+  // cvar_split_f16), q and K as "qk pairs" (16 x = hi + lo, split_f16_qk in common.cuh).
   // This is the operand format of the f16 tensor-core attention kernel (q, K, V^T tiles fetched by TMA as they are).
   __half* q16_hi = nullptr;
   __half* q16_lo = nullptr;
@@ -298,10 +299,10 @@ struct QkvEpilogue {
     if (q16_hi != nullptr) {
       if (which == 0) {
         const long long off = ((rh * l + t) << 6) + d;
-        st4_split_f16(q16_hi + off, q16_lo + off, o);
+        st4_split_f16_qk(q16_hi + off, q16_lo + off, o);
       } else if (which == 1) {
         const long long off = ((rh * T_max + L_prev + t) << 6) + d;
-        st4_split_f16(k16_hi + off, k16_lo + off, o);
+        st4_split_f16_qk(k16_hi + off, k16_lo + off, o);
       } else {
         const long long off = (rh * 64 + d) * T_max + L_prev + t;
 #pragma unroll

@@ -13,6 +13,7 @@ from ._lib import ConvArgs, GemmArgs, check
 EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_GAMMA_RESID, EPI_BIAS_RESID = 0, 1, 2, 3
 ENGINE_SIMT, ENGINE_TC_3XTF32, ENGINE_TC_2CTA, ENGINE_TC_F16X3 = 0, 1, 3, 4
 F16_LO_SCALE = 2048.0      # an FP16 pair represents hi + lo / 2048 (include/cvar.h: cvar_split_f16)
+QK_SCALE = 16.0            # q / K of the f16 attention path are "qk pairs": 16 x = hi + lo (include/cvar.h)
 
 
 def _p(t: Optional[torch.Tensor]):
@@ -62,6 +63,18 @@ class F16Pair:
 
     def float(self) -> torch.Tensor:
         return self.hi.float() + self.lo.float() / F16_LO_SCALE
+
+    # ---- "qk pairs" (q and K of cvar_qkv_project16 / cvar_attn_kvcache16): 16 x = hi + lo, residual NOT scaled.
+    # The library writes them in the QKV epilogue; these two helpers exist for tests and tools only.
+    @staticmethod
+    def from_tensor_qk(x: torch.Tensor) -> "F16Pair":
+        _chk(x)
+        xs = x.contiguous() * QK_SCALE
+        hi = xs.to(torch.float16)
+        return F16Pair(hi, (xs - hi.float()).to(torch.float16))
+
+    def float_qk(self) -> torch.Tensor:
+        return (self.hi.float() + self.lo.float()) / QK_SCALE
 
 
 def _p16(p: Optional[F16Pair]):
@@ -241,8 +254,9 @@ class KVCache:
 
 
 class KVCache16:
-    """KV arena of one transformer block as FP16 pairs (engine 4): K (R, H, T, 64) and V^T (R, H, 64, T), hi and lo halves,
-    T padded to a multiple of 8; zero-initialised once.  Same bytes as one fp32 copy, half of KVCache's TF32 split."""
+    """KV arena of one transformer block as FP16 pairs (engine 4): K (R, H, T, 64) as qk pairs (16 k = hi + lo) and V^T
+    (R, H, 64, T) as standard pairs (v = hi + lo / 2048), T padded to a multiple of 8; zero-initialised once.  Same bytes
+    as one fp32 copy, half of KVCache's TF32 split."""
     __slots__ = ("k_hi", "k_lo", "vt_hi", "vt_lo", "R", "H", "T")
 
     def __init__(self, R: int, H: int, T: int, device, storage: Optional[torch.Tensor] = None):
@@ -259,7 +273,7 @@ class KVCache16:
 
     def keys(self, L: int) -> torch.Tensor:
         """(R, H, L, 64) fp32 view of the cached keys, for tests / debugging."""
-        return (self.k_hi.float() + self.k_lo.float() / F16_LO_SCALE).view(self.R, self.H, self.T, 64)[:, :, :L]
+        return ((self.k_hi.float() + self.k_lo.float()) / QK_SCALE).view(self.R, self.H, self.T, 64)[:, :, :L]
 
     def values(self, L: int) -> torch.Tensor:
         return (self.vt_hi.float() + self.vt_lo.float() / F16_LO_SCALE).view(self.R, self.H, 64, self.T)[:, :, :, :L] \

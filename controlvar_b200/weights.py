@@ -326,3 +326,10 @@ def synthetic_image(B: int, side: int = 256, seed: int = 0, device=None) -> torc
     coarse = coarse.repeat_interleave(8, dim=2).repeat_interleave(8, dim=3)
     fine = hash_uniform(B * 3 * side * side, seed, 0xF19E, device).reshape(B, 3, side, side)
     return (coarse * 0.75 + fine * 0.25).contiguous()
+
+
+def synthetic_teacher_input(cfg: PathConfig, B: int, seed: int = 0, device=None) -> torch.Tensor:
+    """(B, L - first_l, Cvae) teacher-forcing input of ControlVAR.forward (what VectorQuantizer2.idxBl_to_var_input
+    produces from ground-truth tokens), here hash-generated with the spread of a codebook entry."""
+    n = B * (cfg.L - cfg.first_l) * cfg.Cvae
+    return (hash_uniform(n, seed, 0x7EAC, device) * math.sqrt(3.0)).reshape(B, cfg.L - cfg.first_l, cfg.Cvae).contiguous()

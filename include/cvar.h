@@ -150,8 +150,11 @@ CVAR_API int cvar_attn_kvcache(const float* q, const float* k_hi, const float* k
  * out16_hi / out16_lo (optional, IEEE half (R,l,H*64)): the result as an FP16 pair; out may then be NULL. */
 
 /* ---- the same two steps on FP16-pair operands end to end (engine 4) ---------------------------------------------
- * cvar_qkv_project16: A16 / W16 pairs in (as cvar_gemm_args), and q, K, V^T written as FP16 pairs (cvar_split_f16 format:
- * x ~= hi + lo * 2^-11) with the index layout of cvar_qkv_project: q16 (R,H,l,64), k16 (R,H,T_max,64), vt16 (R,H,64,T_max).
+ * cvar_qkv_project16: A16 / W16 pairs in (as cvar_gemm_args), and q, K, V^T written as FP16 pairs with the index layout
+ * of cvar_qkv_project: q16 (R,H,l,64), k16 (R,H,T_max,64), vt16 (R,H,64,T_max).  V^T is a standard pair (cvar_split_f16:
+ * x ~= hi + lo * 2^-11).  q and K are "qk pairs": 16 x = hi + lo with hi = half_rn(16 x), lo = half_rn(16 x - hi) - the
+ * residual is NOT scaled, so q.k = (hi hi + hi lo + lo hi) / 256 accumulates in a single tensor-core accumulator; the
+ * factor 16 keeps the residual of an O(1) value a normal fp16 number (|x| < 4094).
  * Half the bytes of the TF32 split, and exactly the tiles the f16 attention kernel fetches by TMA.  T_max % 8 == 0; the
  * caller zero-initialises the cache once.  Needs a tensor-core engine (cvar_set_gemm_engine != 0). */
 CVAR_API int cvar_qkv_project16(const void* A16_hi, const void* A16_lo, const void* W16_hi, const void* W16_lo,
@@ -160,8 +163,8 @@ CVAR_API int cvar_qkv_project16(const void* A16_hi, const void* A16_lo, const vo
                        int R, int l, int L_prev, int T_max, int H, int cos_attn, const float* scale_mul_H, void* stream);
 /* cvar_attn_kvcache16: softmax(q K^T * scale) V on those pairs; out (R,l,H*64) fp32 and / or out16 pair (either may be
  * NULL, not both).  engine: -1 = default (tensor cores when l >= 64), 0 = SIMT fp32 on the same operands,
- * 1 = tcgen05 kind::f16: three MMAs per product, CTA = 128 queries, two CTAs per SM (256 TMEM columns each), Q / K / V^T
- * tiles by TMA, P written back to TMEM over the S columns it came from. */
+ * 1 = tcgen05 kind::f16: three MMAs per product, CTA = 128 queries, two CTAs per SM (256 TMEM columns each: two S buffers
+ * + O main / cross), Q / K / V^T tiles by TMA, P written back to TMEM over the S cells it came from. */
 CVAR_API int cvar_attn_kvcache16(const void* q16_hi, const void* q16_lo, const void* k16_hi, const void* k16_lo,
                         const void* vt16_hi, const void* vt16_lo, float* out, void* out16_hi, void* out16_lo,
                         int R, int H, int l, int L, int T_max, float scale, int engine, void* stream);

@@ -369,6 +369,32 @@ def autoregressive_infer_cfg(
     return out
 
 
+@torch.no_grad()
+def forward_teacher_forced(sd: Dict[str, Tensor], patch_nums: Sequence[int], depth: int, label_B: Tensor,
+                           x_BLCv_wo_first_l: Tensor, cond_type: Tensor, embed_dim: int = 0, num_heads: int = 0) -> Tensor:
+    """ControlVAR.forward, released branch (multi_cond, mask_factor 2, mask_first=True, prog_si=-1) -
+    models/control_var.py:566-651: one full-sequence pass under the block-causal attn_bias_for_masking.
+    The label / condition-type dropout of :577 and :584 (torch.rand < cond_drop_rate, active even in eval) is the
+    caller's: pass the ids as they should enter the model (the goldens are made with cond_drop_rate = 0)."""
+    C = embed_dim or 64 * depth
+    H = num_heads or depth
+    cos_attn = depth == 30
+    scale = 1.0 if cos_attn else 1 / math.sqrt(C // H) / 4
+    B = x_BLCv_wo_first_l.shape[0]
+    first_l = 2 * patch_nums[0] ** 2
+    sos = cond_BD = F.embedding(label_B.long(), sd["class_emb.weight"])                       # :578
+    sos = sos.unsqueeze(1).expand(B, 1, -1)                                                   # :581
+    cond_token = F.embedding(cond_type.long(), sd["cond_embed.weight"]).unsqueeze(1).expand(B, 1, -1)   # :585-586
+    sos = torch.concat([cond_token, sos], dim=1)                                              # :587 (mask_first)
+    sos = sos + sd["pos_start"].expand(B, first_l, -1)                                        # :588
+    x_BLC = torch.cat((sos, F.linear(x_BLCv_wo_first_l.float(), sd["word_embed.weight"], sd["word_embed.bias"])), dim=1)  # :616
+    x_BLC += F.embedding(sd["lvl_1L"].expand(B, -1), sd["lvl_embed.weight"]) + sd["pos_1LC"]   # :618
+    attn_bias = sd["attn_bias_for_masking"]                                                   # :622
+    for bi in range(depth):                                                                   # :634-635
+        x_BLC = adaln_block(x_BLC, cond_BD, sd, f"blocks.{bi}.", H, None, cos_attn, scale, attn_bias)
+    return get_logits(x_BLC.float(), cond_BD, sd)                                             # :636
+
+
 def cfg_combine4(logits_4BlV: Tensor, B: int, t1: float, t2: float, t3: float) -> Tensor:
     """The four-way guidance mix of conditional_infer_cfg - models/control_var.py:295-298."""
     return (1 + t1) * logits_4BlV[:B] \

@@ -12,11 +12,14 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def _kind(name):
-    return "enc" if name.startswith("enc_") else "cond" if name.startswith("cond_") else "sample"
+    for k in ("enc", "cond", "fwd"):
+        if name.startswith(k + "_"):
+            return k
+    return "sample"
 
 
 def golden_names(kind="sample"):
-    """kind: 'sample' (autoregressive_infer_cfg), 'cond' (conditional_infer_cfg), 'enc' (img_to_idxBl)."""
+    """kind: 'sample' (autoregressive_infer_cfg), 'cond' (conditional_infer_cfg), 'enc' (img_to_idxBl), 'fwd' (forward)."""
     names = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
     return [n for n in names if _kind(n) == kind]
 
@@ -26,6 +29,8 @@ def load_golden(name):
     meta = json.loads(bytes(z["meta"]).decode())
     cfg = PathConfig(depth=meta["depth"], patch_nums=tuple(meta["patch_nums"]), embed_dim=meta.get("embed_dim", 0),
                      heads=meta.get("heads", 0))
+    if meta.get("kind") == "fwd":
+        return dict(meta=meta, cfg=cfg, logits_sub=torch.from_numpy(z["logits_sub"]))
     idx = [torch.from_numpy(z[f"idx_{si}"].astype(np.int64)) for si in range(len(cfg.patch_nums))]
     if meta.get("kind") == "enc":
         return dict(meta=meta, cfg=cfg, idx=idx, f=torch.from_numpy(z["f"]))

@@ -276,3 +276,54 @@ def test_conditional_pipeline_from_pixels():
         O.get_next_autoregressive_input(si, cfg.patch_nums, f_hat, h, vsd)
     ref_ctrl = O.fhat_to_img(f_hat, vsd).add_(1).mul_(0.5)
     assert (a[:, :, :side].cpu() - ref_ctrl).abs().max().item() < 1e-4
+
+
+# ------------------------------------------------------------------------------------------- forward (f-3)
+@pytest.mark.parametrize("name", golden_names("fwd"))
+def test_forward_teacher_forced_matches_reference_golden(name):
+    """ControlVAR.forward (control_var.py:566-651): logits (B, L, V) of the teacher-forced pyramid.  The reference runs
+    ONE masked full-sequence pass; the GPU path runs the scales against the growing KV cache - the same numbers."""
+    gold = load_golden(name)
+    m, cfg = gold["meta"], gold["cfg"]
+    vae = VQVAE(ch=160, v_patch_nums=cfg.patch_nums)
+    if cfg.embed_dim:
+        from controlvar_b200 import ControlVAR
+        var = ControlVAR(vae_local=vae, patch_nums=cfg.patch_nums, depth=cfg.depth, embed_dim=cfg.C, num_heads=cfg.num_heads,
+                         mask_factor=2, indep=False, multi_cond=True)
+    else:
+        var = build_control_var(vae, depth=cfg.depth, patch_nums=cfg.patch_nums, mask_type="interleave_append",
+                                multi_cond=True)
+    var.load_state_dict(W.synthetic_var_state_dict(cfg, m["weight_seed"]))
+    var.to(DEV)
+    var.cond_drop_rate = 0.0
+    x = W.synthetic_teacher_input(cfg, m["B"], m["x_seed"])
+    n0 = ops.launch_count()
+    logits = var(torch.tensor(m["labels"]), g(x), torch.tensor(m["cond"]))
+    torch.cuda.synchronize()
+    assert ops.launch_count() > n0 and list(logits.shape) == m["logits_shape"]
+    err = (logits.cpu()[:, :, ::m["logits_sub"]] - gold["logits_sub"]).abs().max().item()
+    # and against the oracle on every logit
+    ref = O.forward_teacher_forced(W.synthetic_var_state_dict(cfg, m["weight_seed"]), cfg.patch_nums, cfg.depth,
+                                   torch.tensor(m["labels"]), x, torch.tensor(m["cond"]), embed_dim=cfg.embed_dim,
+                                   num_heads=cfg.heads)
+    err_all = (logits.cpu() - ref).abs().max().item()
+    print(f"\n[forward {name}] max |dlogit| {err_all:.2e} (golden sub-grid {err:.2e}), argmax agreement "
+          f"{(logits.cpu().argmax(-1) == ref.argmax(-1)).float().mean().item():.4f}")
+    assert err < 1e-4 and err_all < 1e-4
+
+
+def test_forward_drops_conditions_like_the_reference():
+    """cond_drop_rate = 1 replaces every label by the 'unconditional' class and every condition type by 4
+    (control_var.py:577, 584), in eval mode too."""
+    cfg = PathConfig(depth=2, patch_nums=(1, 2, 3))
+    vae = VQVAE(ch=160, v_patch_nums=cfg.patch_nums)
+    var = build_control_var(vae, depth=cfg.depth, patch_nums=cfg.patch_nums, mask_type="interleave_append", multi_cond=True)
+    var.load_state_dict(W.synthetic_var_state_dict(cfg, 0))
+    var.to(DEV)
+    x = g(W.synthetic_teacher_input(cfg, 2, 1))
+    var.cond_drop_rate = 1.0
+    a = var(torch.tensor([3, 4]), x, torch.tensor([1, 2]))
+    var.cond_drop_rate = 0.0
+    b = var(torch.tensor([1000, 1000]), x, torch.tensor([4, 4]))
+    c = var(torch.tensor([3, 4]), x, torch.tensor([1, 2]))
+    assert torch.equal(a, b) and not torch.equal(a, c)

@@ -64,6 +64,19 @@ def test_oracle_conditional_infer_matches_reference_golden(name):
     assert (out["f_hat"][:m["B"]] - g["f_hat"]).abs().max().item() <= 1e-6
 
 
+@pytest.mark.parametrize("name", golden_names("fwd"))
+def test_oracle_forward_matches_reference_golden(name):
+    """ControlVAR.forward (control_var.py:566-651): teacher-forced logits under the block-causal mask."""
+    g = load_golden(name)
+    m, cfg = g["meta"], g["cfg"]
+    sd = W.synthetic_var_state_dict(cfg, m["weight_seed"])
+    x = W.synthetic_teacher_input(cfg, m["B"], m["x_seed"])
+    out = O.forward_teacher_forced(sd, cfg.patch_nums, cfg.depth, torch.tensor(m["labels"]), x, torch.tensor(m["cond"]),
+                                   embed_dim=cfg.embed_dim, num_heads=cfg.heads)
+    assert list(out.shape) == m["logits_shape"]
+    assert (out[:, :, ::m["logits_sub"]] - g["logits_sub"]).abs().max().item() <= 2e-6
+
+
 def test_multinomial_identity():
     """torch.multinomial(p, 1, replacement=True, generator=g) == argmax(p / Exp(1) drawn from g) (helpers.py:19)."""
     g1, g2 = torch.Generator(), torch.Generator()

@@ -77,10 +77,10 @@ if which in ("attn", "all"):
 if which in ("attn16", "all"):
     R, Hh, l, L, T = 128, 24, 512, 1360, 1360
     kv = ops.KVCache16(R, Hh, T, dev)
-    for t in (kv.k_hi, kv.vt_hi, kv.k_lo, kv.vt_lo):
-        t.normal_()
+    kv.k_hi.normal_().mul_(16), kv.k_lo.normal_().mul_(2.0 ** -8)          # qk pairs: 16 x = hi + lo
+    kv.vt_hi.normal_(), kv.vt_lo.normal_()
     q16 = ops.F16Pair.empty((R, Hh, l, 64), dev)
-    q16.hi.normal_(), q16.lo.normal_()
+    q16.hi.normal_().mul_(16), q16.lo.normal_().mul_(2.0 ** -8)
     o16 = ops.F16Pair.empty((R, l, Hh * 64), dev)
     fl = 4.0 * l * L * 64 * R * Hh
     by = (2.0 * l + 2.0 * L) * 64 * 4 * R * Hh
@@ -89,7 +89,7 @@ if which in ("attn16", "all"):
         print(f"attn16 engine={eng} R={R} H={Hh} l={l} L={L}: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s  {by / ms / 1e6:.0f} GB/s algorithmic")
     for (ls, Ls) in ((338, 848), (200, 510), (128, 310), (72, 182)):
         q16s = ops.F16Pair.empty((R, Hh, ls, 64), dev)
-        q16s.hi.normal_(), q16s.lo.normal_()
+        q16s.hi.normal_().mul_(16), q16s.lo.normal_().mul_(2.0 ** -8)
         o16s = ops.F16Pair.empty((R, ls, Hh * 64), dev)
         ms = timed(lambda: ops.attn_kvcache16(q16s, kv, None, R, Hh, ls, Ls, 1 / 32, engine=1, out16=o16s))
         print(f"attn16 engine=1 l={ls} L={Ls}: {ms:.3f} ms  {4.0 * ls * Ls * 64 * R * Hh / ms / 1e9:.1f} TFLOP/s")

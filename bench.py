@@ -285,7 +285,8 @@ def main_ours(args, wl):
                    "sample": f"{args.cpu_sample_batch} image(s), one call of the same workload on the host cores; " + CPU_BATCH_NOTE}
         engine_name = {0: "simt-fp32", 1: "tcgen05-3xtf32 (1 CTA per tile)",
                        3: "tcgen05-3xtf32 (2-CTA all-TMA dense layers, 1-CTA convs)",
-                       4: "tcgen05 f16x3 (FP16 pairs, 2-CTA all-TMA) dense layers and decoder convs; 3xtf32 attention"}.get(ops.get_gemm_engine(), "?")
+                       4: "tcgen05 f16x3 (FP16 pairs): 2-CTA all-TMA dense layers and decoder convs (K-split for the long "
+                          "accumulations), kind::f16 attention on an FP16-pair KV cache"}.get(ops.get_gemm_engine(), "?")
         line = {"metric": f"images/sec (256x256, d{depth}, CFG=1.5)", "value": value, "unit": "images/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",

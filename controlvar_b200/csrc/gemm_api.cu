@@ -209,6 +209,50 @@ extern "C" int cvar_qkv_project16(const void* A16_hi, const void* A16_lo, const 
   return 0;
 }
 
+// 3x3 'same' convolution to THREE output channels (Decoder.conv_out, vae_modules.py:226): the implicit-GEMM engines pad
+// N = 3 to a 32-wide tile and spend 10x the FLOPs.  Direct form: one thread per output pixel, all weights (27 * Cin floats)
+// in shared memory (broadcast reads), the pixel's channel vectors read as float4 through L1; epilogue = ConvEpilogue.
+template <int COUT>
+__global__ void __launch_bounds__(128) conv3x3_small_cout_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                                 ConvEpilogue ep, int H, int W, int Cin, long long M) {
+  extern __shared__ __align__(16) float w_s[];          // [COUT][9 * Cin]
+  const int K = 9 * Cin;
+  for (int i = threadIdx.x; i < COUT * K; i += blockDim.x) w_s[i] = w[i];
+  __syncthreads();
+  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  const int xw = (int)(m % W);
+  const long long q = m / W;
+  const int y = (int)(q % H);
+  const long long n = q / H;
+  float acc[COUT];
+#pragma unroll
+  for (int c = 0; c < COUT; ++c) acc[c] = 0.f;
+#pragma unroll 1
+  for (int tap = 0; tap < 9; ++tap) {
+    const int yy = y + tap / 3 - 1, xx = xw + tap % 3 - 1;
+    if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+    const float* px = x + ((n * H + yy) * W + xx) * Cin;
+    const float* wt = w_s + tap * Cin;
+#pragma unroll 4
+    for (int ci = 0; ci < Cin; ci += 4) {
+      const float4 v = ld4(px + ci);
+#pragma unroll
+      for (int c = 0; c < COUT; ++c) {
+        const float4 ww = *reinterpret_cast<const float4*>(wt + c * K + ci);
+        acc[c] = fmaf(v.x, ww.x, acc[c]);
+        acc[c] = fmaf(v.y, ww.y, acc[c]);
+        acc[c] = fmaf(v.z, ww.z, acc[c]);
+        acc[c] = fmaf(v.w, ww.w, acc[c]);
+      }
+    }
+  }
+  float v4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int c = 0; c < COUT; ++c) v4[c] = acc[c];
+  ep.store(m, 0, v4, COUT, 0);
+}
+
 extern "C" int cvar_conv2d(const cvar_conv_args* a, void* stream) {
   CVAR_REQUIRE(a != nullptr, "cvar_conv2d: null args");
   CVAR_REQUIRE(a->ks == 1 || a->ks == 3, "cvar_conv2d: ks must be 1 or 3");
@@ -234,6 +278,14 @@ extern "C" int cvar_conv2d(const cvar_conv_args* a, void* stream) {
   const int Hout = (a->Hin << up) >> down, Wout = (a->Win << up) >> down;
   const long long M = (long long)a->B * Hout * Wout;
   const int K = a->ks * a->ks * a->Cin;
+  if (a->Cout == 3 && a->ks == 3 && !up && !down && a->in_a == nullptr && a->resid == nullptr && a->Cin % 4 == 0 &&
+      (size_t)3 * K * sizeof(float) <= 48 * 1024) {
+    ConvEpilogue ep3{a->out, a->bias, nullptr, a->Cout, a->out_mode, Hout, Wout, a->out_rows_total, a->row_offset};
+    conv3x3_small_cout_kernel<3><<<cdiv(M, 128), 128, (size_t)3 * K * sizeof(float), s>>>(a->x, a->w, ep3, Hout, Wout,
+                                                                                         a->Cin, M);
+    CVAR_CHECK_LAUNCH("cvar_conv2d[cout3]");
+    return 0;
+  }
   ConvALoader al;
   al.x = a->x, al.in_a = a->in_a, al.in_b = a->in_b, al.in_silu = a->in_silu;
   al.Hin = a->Hin, al.Win = a->Win, al.Cin = a->Cin, al.ks = a->ks, al.up = up;

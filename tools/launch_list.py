@@ -14,6 +14,8 @@ CLASSES = [
     (r"tc_conv2_kernel", "decoder conv, tcgen05 f16x3 2-CTA implicit GEMM by 4-D TMA (tc_conv2_kernel)"),
     (r"tc_gemm_kernel<.*ConvALoader", "decoder conv, tcgen05 3xTF32 1-CTA (tc_gemm_kernel<ConvALoader>)"),
     (r"tc_gemm_kernel<", "dense layers, tcgen05 3xTF32 1-CTA (tc_gemm_kernel)"),
+    (r"attn16_tc_kernel", "attention, tcgen05 kind::f16 on FP16 pairs (attn16_tc_kernel, l >= 64)"),
+    (r"attn16_simt_kernel", "attention, SIMT on FP16 pairs (attn16_simt_kernel, l < 64)"),
     (r"attn_tc_kernel", "attention, tcgen05 (attn_tc_kernel, l >= 64)"),
     (r"attn_kvcache_kernel", "attention, SIMT (attn_kvcache_kernel, l < 64)"),
     (r"sgemm_kernel", "SIMT fp32 GEMM / conv (small, ragged or accuracy-pinned layers)"),

@@ -322,10 +322,12 @@ extern "C" int cvar_gn_stats(const float* x_nhwc, const float* gamma, const floa
 __global__ void affine_nc_kernel(const float* __restrict__ x, const float* __restrict__ a, const float* __restrict__ b,
                                  float* __restrict__ y, __half* __restrict__ y16_hi, __half* __restrict__ y16_lo,
                                  long long HWC4, int C4, long long total4, int silu) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total4) return;
-  long long n = i / HWC4;
-  int c4 = (int)(i % C4);
+  // grid.y = sample, grid.x covers the sample's HW*C/4 float4s: no 64-bit division per thread
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= HWC4) return;
+  const long long n = blockIdx.y;
+  const long long i = n * HWC4 + j;
+  const int c4 = (int)((unsigned)j % (unsigned)C4);
   float4 v = ld4(x + i * 4);
   float4 av = ld4(a + (n * C4 + c4) * 4), bv = ld4(b + (n * C4 + c4) * 4);
   v.x = fmaf(v.x, av.x, bv.x);
@@ -392,7 +394,8 @@ extern "C" int cvar_affine_nc(const float* x_nhwc, const float* a, const float* 
   CVAR_REQUIRE(y != nullptr || y16_hi != nullptr, "cvar_affine_nc: no output");
   CVAR_REQUIRE((y16_hi == nullptr) == (y16_lo == nullptr), "cvar_affine_nc: y16_hi/y16_lo must come together");
   long long total4 = (long long)B * HW * C / 4;
-  affine_nc_kernel<<<cdiv(total4, 256), 256, 0, (cudaStream_t)stream>>>(
+  CVAR_REQUIRE(B <= 65535 && (long long)HW * C / 4 < (1LL << 31), "cvar_affine_nc: shape too large");
+  affine_nc_kernel<<<dim3(cdiv((long long)HW * C / 4, 256), B), 256, 0, (cudaStream_t)stream>>>(
       x_nhwc, a, b, y, reinterpret_cast<__half*>(y16_hi), reinterpret_cast<__half*>(y16_lo), (long long)HW * C / 4, C / 4,
       total4, silu);
   CVAR_CHECK_LAUNCH("cvar_affine_nc");

@@ -327,3 +327,30 @@ def test_forward_drops_conditions_like_the_reference():
     b = var(torch.tensor([1000, 1000]), x, torch.tensor([4, 4]))
     c = var(torch.tensor([3, 4]), x, torch.tensor([1, 2]))
     assert torch.equal(a, b) and not torch.equal(a, c)
+
+
+# ---------------------------------------------------------------------------------------- validate (f-4)
+def test_validate_driver_end_to_end(tmp_path):
+    """validate() of train_control_var_hpu.py:338-408 on the GPU path: per-class sampling, one Gibbs round (control map
+    -> image -> control map through img_to_idxBl + conditional_infer_cfg), uint8 PNG dump; files equal a direct call."""
+    import numpy as np
+    from PIL import Image
+    from controlvar_b200 import validate as VD
+    cfg = PathConfig(depth=2, patch_nums=(1, 2, 3, 4))
+    vae = VQVAE(ch=160, v_patch_nums=cfg.patch_nums)
+    var = build_control_var(vae, depth=cfg.depth, patch_nums=cfg.patch_nums, mask_type="interleave_append", multi_cond=True)
+    var.load_state_dict(W.synthetic_var_state_dict(cfg, 0))
+    vae.load_state_dict(W.synthetic_vae_state_dict(cfg, 0))
+    vae.to(DEV), var.to(DEV)
+    out = VD.validate_classes(var, vae, str(tmp_path), batch_size=2, per_class=3, classes=[7, 8], guidance_scale=(4.0, 4.0, 4.0),
+                              top_k=900, top_p=0.96, seed=5, gibbs=0, cond_type="canny")
+    side = cfg.img_hw
+    first = var.autoregressive_infer_cfg(B=2, label_B=torch.full((2,), 7, device=DEV), cond_type=torch.full((2,), 1, device=DEV),
+                                         cfg=4.0, top_k=900, top_p=0.96, g_seed=5)
+    want = VD.to_uint8_hwc(first)[:, side:]
+    got = np.asarray(Image.open(tmp_path / "cfg_4.0" / "7" / "1.png"))
+    assert got.shape == (side, side, 3) and np.array_equal(got, want[1]) and np.array_equal(out[7][0], want)
+    assert sorted(int(p.stem) for p in (tmp_path / "cfg_4.0" / "8").iterdir()) == [0, 1, 2]
+    g1 = VD.validate_classes(var, vae, str(tmp_path / "g"), batch_size=2, per_class=3, classes=[7], guidance_scale=(4.0, 4.0, 4.0),
+                             seed=5, gibbs=1, cond_type="canny", save_val=False)
+    assert g1[7][0].shape == (2, side, side, 3) and not np.array_equal(g1[7][0], want)     # the Gibbs round resampled it

@@ -172,7 +172,14 @@ def main_ours(args, wl):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # stdout carries exactly ONE JSON line (rank 0).  NCCL prints its version banner (and, under NCCL_DEBUG, its log) to
+    # stdout when the first communicator comes up: while the process group and the weight broadcast are set up, file
+    # descriptor 1 points at stderr.
+    saved_stdout = None
     if world > 1:
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     ops.set_gemm_engine(args.engine)
 
@@ -188,6 +195,12 @@ def main_ours(args, wl):
     shard.broadcast_weights(arena, src=0)
     torch.cuda.synchronize()
     bcast_ms = (time.perf_counter() - t_b0) * 1e3
+    if saved_stdout is not None:
+        dist.barrier()                      # every communicator the bench uses exists now
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
 
     label_h = (torch.arange(B) + rank * B) % 1000
     ct_h = torch.full((B,), wl["cond"], dtype=torch.long)

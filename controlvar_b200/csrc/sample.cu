@@ -151,24 +151,59 @@ __global__ void __launch_bounds__(NT) cfg_sample_kernel(const float* __restrict_
   float vmax;
   // ---- top-p: remove the ascending prefix whose softmax mass is <= 1 - top_p               helpers.py:11-15
   if (use_top_p) {
+    // Entries already removed by top-k are -inf: in the ascending order they come first, contribute exp(-inf) = 0 to every
+    // sum below and are written back as -inf whatever their order.  So instead of sorting all 4096 keys, the survivors
+    // are compacted into the LAST slots and only the last kSortTail slots are sorted when they all fit there (top_k = 900
+    // leaves ~900): the sorted tail - hence every running sum, taken per thread over the same 16 consecutive slots - is
+    // bit-identical to that of the full sort, at a fifth of the compare-exchange work.
+    constexpr int kSortTail = 1024;
+    int nsurv_local = 0;
 #pragma unroll
-    for (int i = 0; i < PER; ++i) {
-      int e = tid + i * NT;
-      sm.keys[e] = ((unsigned long long)orderable(sm.vals[e]) << 32) | (unsigned)e;
+    for (int i = 0; i < PER; ++i) nsurv_local += (sm.vals[tid + i * NT] != -INFINITY) ? 1 : 0;
+    // block-wide exclusive scan of the per-thread survivor counts (thread order, then element order i)
+    int incl_c = nsurv_local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int n = __shfl_up_sync(0xffffffffu, incl_c, o);
+      if (lane >= o) incl_c += n;
     }
     __syncthreads();
-    for (int k = 2; k <= V_FIXED; k <<= 1) {
-      for (int j = k >> 1; j > 0; j >>= 1) {
+    if (lane == 31) sm.redi[warp] = incl_c;
+    __syncthreads();
+    int woff_c = 0, nsurv = 0;
 #pragma unroll
-        for (int pi = 0; pi < V_FIXED / 2 / NT; ++pi) {
-          int p = tid + pi * NT;
+    for (int w = 0; w < NT / 32; ++w) {
+      if (w < warp) woff_c += sm.redi[w];
+      nsurv += sm.redi[w];
+    }
+    int pos_s = woff_c + incl_c - nsurv_local;            // rank of this thread's first survivor among all survivors
+    int pos_d = (tid * PER) - pos_s;                      // rank of its first removed entry (elements before it: tid*PER)
+    // NB: ranks are taken in (thread, i) order, not in index order - any order will do (see above)
+    __syncthreads();                                      // sm.redi is reused by the final arg-max
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int e = tid + i * NT;
+      const float v = sm.vals[e];
+      const unsigned long long key = ((unsigned long long)orderable(v) << 32) | (unsigned)e;
+      if (v != -INFINITY)
+        sm.keys[V_FIXED - nsurv + pos_s++] = key;
+      else
+        sm.keys[pos_d++] = key;
+    }
+    __syncthreads();
+    const bool tail_only = nsurv <= kSortTail;            // uniform
+    const int base = tail_only ? V_FIXED - kSortTail : 0;
+    const int nsort = tail_only ? kSortTail : V_FIXED;
+    for (int k = 2; k <= nsort; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int p = tid; p < nsort / 2; p += NT) {
           int i = 2 * p - (p & (j - 1));
           int ixj = i + j;
           bool up = (i & k) == 0;
-          unsigned long long a = sm.keys[i], c = sm.keys[ixj];
+          unsigned long long a = sm.keys[base + i], c = sm.keys[base + ixj];
           if ((a > c) == up) {
-            sm.keys[i] = c;
-            sm.keys[ixj] = a;
+            sm.keys[base + i] = c;
+            sm.keys[base + ixj] = a;
           }
         }
         __syncthreads();

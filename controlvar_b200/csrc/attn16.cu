@@ -654,7 +654,9 @@ extern "C" int cvar_attn_kvcache16(const void* q16_hi, const void* q16_lo, const
   const __half* vl = reinterpret_cast<const __half*>(vt16_lo);
   __half* o16h = reinterpret_cast<__half*>(out16_hi);
   __half* o16l = reinterpret_cast<__half*>(out16_lo);
-  if (engine < 0) engine = (g_gemm_engine != 0 && l >= 64) ? 1 : 0;
+  // default: tensor cores from l = 32 (a 128-query tile a quarter full still beats the SIMT kernel: measured in
+  // profiles/r01_attn16.md); below that the SIMT kernel
+  if (engine < 0) engine = (g_gemm_engine != 0 && l >= 32) ? 1 : 0;
   if (engine == 1) {
     CUtensorMap mqh, mql, mkh, mkl, mvh, mvl;
     const long long RH = (long long)R * H;

@@ -190,6 +190,9 @@ extern "C" int cvar_ln_modulate(const float* x, const float* scale, const float*
   else if (nv <= 32 * 8)
     ln_modulate_kernel<8><<<grid, 256, 0, s>>>(x, scale, shift, mod_row_stride, y, y_lo, y16_hi, y16_lo, M, C,
                                                rows_per_sample, eps);
+  else if (nv <= 32 * 12)      // C = 1536 (depth 24): 12 float4 per lane, not 16 - fewer registers, a third CTA per SM
+    ln_modulate_kernel<12><<<grid, 256, 0, s>>>(x, scale, shift, mod_row_stride, y, y_lo, y16_hi, y16_lo, M, C,
+                                                rows_per_sample, eps);
   else
     ln_modulate_kernel<16><<<grid, 256, 0, s>>>(x, scale, shift, mod_row_stride, y, y_lo, y16_hi, y16_lo, M, C,
                                                rows_per_sample, eps);

@@ -39,7 +39,8 @@ def fill_cache(kv, k, v, L):
 
 
 @pytest.mark.parametrize("R,H,l,L", [(2, 2, 64, 64), (2, 3, 128, 310), (1, 2, 200, 510), (2, 2, 338, 848),
-                                     (1, 4, 512, 1360), (3, 1, 72, 182), (1, 1, 130, 131), (2, 5, 8, 10)])
+                                     (1, 4, 512, 1360), (3, 1, 72, 182), (1, 1, 130, 131), (2, 5, 8, 10), (2, 3, 32, 60),
+                                     (3, 2, 50, 110)])
 def test_attn16_matches_sdpa(R, H, l, L):
     torch.manual_seed(l + L)
     T = L + 5
@@ -55,7 +56,7 @@ def test_attn16_matches_sdpa(R, H, l, L):
     kv.vt_hi.view(R, H, 64, kv.T)[:, :, :, L:] = -1e4
     q16 = pair_qk(q)
     res = {}
-    for eng in ((1, 0) if l >= 64 else (0,)):
+    for eng in ((1, 0) if l >= 32 else (0,)):
         out = torch.full((R, l, H * 64), float("nan"), device=DEV)
         o16 = ops.F16Pair.empty((R, l, H * 64), DEV)
         ops.attn_kvcache16(q16, kv, out, R, H, l, L, scale, engine=eng, out16=o16)

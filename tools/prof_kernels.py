@@ -87,9 +87,10 @@ if which in ("attn16", "all"):
     for eng in (1, 0):
         ms = timed(lambda: ops.attn_kvcache16(q16, kv, None, R, Hh, l, L, 1 / 32, engine=eng, out16=o16))
         print(f"attn16 engine={eng} R={R} H={Hh} l={l} L={L}: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s  {by / ms / 1e6:.0f} GB/s algorithmic")
-    for (ls, Ls) in ((338, 848), (200, 510), (128, 310), (72, 182)):
+    for (ls, Ls) in ((338, 848), (200, 510), (128, 310), (72, 182), (50, 110), (32, 60)):
         q16s = ops.F16Pair.empty((R, Hh, ls, 64), dev)
         q16s.hi.normal_().mul_(16), q16s.lo.normal_().mul_(2.0 ** -8)
         o16s = ops.F16Pair.empty((R, ls, Hh * 64), dev)
         ms = timed(lambda: ops.attn_kvcache16(q16s, kv, None, R, Hh, ls, Ls, 1 / 32, engine=1, out16=o16s))
-        print(f"attn16 engine=1 l={ls} L={Ls}: {ms:.3f} ms  {4.0 * ls * Ls * 64 * R * Hh / ms / 1e9:.1f} TFLOP/s")
+        ms0 = timed(lambda: ops.attn_kvcache16(q16s, kv, None, R, Hh, ls, Ls, 1 / 32, engine=0, out16=o16s)) if ls <= 72 else float("nan")
+        print(f"attn16 engine=1 l={ls} L={Ls}: {ms:.3f} ms  {4.0 * ls * Ls * 64 * R * Hh / ms / 1e9:.1f} TFLOP/s   (SIMT: {ms0:.3f} ms)")

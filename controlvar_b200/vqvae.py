@@ -377,9 +377,10 @@ class VQVAE(nn.Module):
         raise AssertionError("encoder plan without an output record")
 
     @torch.no_grad()
-    def _f_to_idxBl(self, f: torch.Tensor, v_patch_nums: Sequence[int]) -> List[torch.Tensor]:
-        """VectorQuantizer2.f_to_idxBl_or_fhat(to_fhat=False) - quant.py:184-215: per scale, area-pool the residual,
-        nearest code, then f_hat += phi(bicubic(E[idx])), f_rest -= the same, in one kernel."""
+    def _f_to_idxBl(self, f: torch.Tensor, v_patch_nums: Sequence[int], to_fhat: bool = False) -> List[torch.Tensor]:
+        """VectorQuantizer2.f_to_idxBl_or_fhat - quant.py:184-215: per scale, area-pool the residual, nearest code, then
+        f_hat += phi(bicubic(E[idx])), f_rest -= the same, in one kernel.  to_fhat: return f_hat after every scale
+        (clones) instead of the token ids."""
         B, Cz, H, W = f.shape
         pns = [int(pn) for pn in v_patch_nums]
         assert Cz == self.Cvae and H == W and pns[-1] == H, f"patch_nums[-1]={pns[-1]} != H={H}"
@@ -407,8 +408,76 @@ class VQVAE(nn.Module):
             ops.vq_step(idx, emb, U, self._w(f"quantize.quant_resi.qresi_ls.{k}.weight"),
                         self._w(f"quantize.quant_resi.qresi_ls.{k}.bias"), None, None, None, f_hat, None, B, pn, 0, H, Cz,
                         0, streams=1, x_replicas=1, f_rest=f_rest)
-            out.append(idx.view(B, pn * pn))
+            out.append(f_hat.clone() if to_fhat else idx.view(B, pn * pn))
         return out
+
+    def _phi_U(self, si: int, SN: int, pn: int, H: int, device):
+        k = phi_index(si, SN, self.cfg.share_quant_resi) if SN > 1 else 0
+        U = None
+        if pn != H:
+            U = self._U.get((pn, H))
+            if U is None:
+                U = self._U[(pn, H)] = bicubic_matrix(pn, H).to(device)
+        return (self._w(f"quantize.quant_resi.qresi_ls.{k}.weight"), self._w(f"quantize.quant_resi.qresi_ls.{k}.bias"), U)
+
+    def _check_tokens(self, ms_idx_Bl) -> Tuple[List[int], int, int]:
+        pns = [int(round(t.shape[1] ** 0.5)) for t in ms_idx_Bl]          # vqvae.py:101
+        assert all(pn * pn == t.shape[1] for pn, t in zip(pns, ms_idx_Bl)), "token maps must be square"
+        if not ms_idx_Bl[0].is_cuda:
+            raise RuntimeError("controlvar_b200.VQVAE runs on CUDA only (no CPU fallback)")
+        return pns, ms_idx_Bl[0].shape[0], self.cfg.patch_nums[-1]
+
+    @torch.no_grad()
+    def idxBl_to_img(self, ms_idx_Bl: List[torch.Tensor], same_shape: bool, last_one=False):
+        """Drop-in for VQVAE.idxBl_to_img (vqvae.py:97-104) with same_shape=True (embed_to_fhat(all_to_max_scale=True),
+        quant.py:156-170): tokens -> f_hat accumulated scale by scale -> decoded image(s) in [-1, 1].  last_one: only
+        the final image, else one image per scale.  same_shape=False is the reference's 'experimental visualisation'
+        branch and is not implemented."""
+        if not same_shape:
+            raise NotImplementedError("idxBl_to_img(same_shape=False) is not implemented")
+        pns, B, H = self._check_tokens(ms_idx_Bl)
+        SN = len(self.cfg.patch_nums)
+        dev = ms_idx_Bl[0].device
+        emb = self._w("quantize.embedding.weight")
+        f_hat = torch.zeros(B, self.Cvae, H, H, device=dev, dtype=torch.float32)
+        imgs = []
+        for si, (pn, idx) in enumerate(zip(pns, ms_idx_Bl)):
+            pw, pb, U = self._phi_U(si, SN, pn, H, dev)
+            ops.vq_step(idx.to(torch.int64).contiguous().view(-1), emb, U, pw, pb, None, None, None, f_hat, None, B, pn, 0, H,
+                        self.Cvae, 0, streams=1, x_replicas=1)
+            if not last_one:
+                imgs.append(self.fhat_to_img(f_hat))
+        return self.fhat_to_img(f_hat) if last_one else imgs
+
+    @torch.no_grad()
+    def idxBl_to_h(self, gt_ms_idx_Bl: List[torch.Tensor]) -> List[torch.Tensor]:
+        """Drop-in for VQVAE.idxBl_to_h = VectorQuantizer2.idxBl_to_var_input (vqvae.py:77-78, quant.py:217-241): the
+        teacher-forcing inputs of ControlVAR.forward, one (B, pn_next^2, Cvae) tensor per scale transition."""
+        pns, B, H = self._check_tokens(gt_ms_idx_Bl)
+        SN = len(self.cfg.patch_nums)
+        dev = gt_ms_idx_Bl[0].device
+        emb = self._w("quantize.embedding.weight")
+        f_hat = torch.zeros(B, self.Cvae, H, H, device=dev, dtype=torch.float32)
+        out = []
+        for si in range(SN - 1):
+            pn, pn_next = pns[si], self.cfg.patch_nums[si + 1]
+            pw, pb, U = self._phi_U(si, SN, pn, H, dev)
+            ops.vq_step(gt_ms_idx_Bl[si].to(torch.int64).contiguous().view(-1), emb, U, pw, pb, None, None, None, f_hat, None,
+                        B, pn, 0, H, self.Cvae, 0, streams=1, x_replicas=1)
+            z = torch.empty(B * pn_next * pn_next, self.Cvae, device=dev, dtype=torch.float32)
+            ops.area_pool_nc(f_hat, z, B, self.Cvae, H, pn_next)      # area pool + (B, C, n) -> (B, n, C)
+            out.append(z.view(B, pn_next * pn_next, self.Cvae))
+        return out
+
+    @torch.no_grad()
+    def img_to_recon(self, x: torch.Tensor, v_patch_nums: Optional[Sequence[int]] = None, last_one=False):
+        """Drop-in for VQVAE.img_to_recon (vqvae.py:80-86): decoder(post_quant_conv(f_hat)) of the quantised encoder
+        output - NOT clamped, as in the reference - after the last scale (last_one) or after every scale."""
+        pns = self.cfg.patch_nums if v_patch_nums is None else v_patch_nums
+        fhats = self._f_to_idxBl(self._img_to_f(x), pns, to_fhat=True)
+        if last_one:
+            return self._fhat_to_img(fhats[-1], out_mode=3)
+        return [self._fhat_to_img(fh, out_mode=3) for fh in fhats]
 
     @torch.no_grad()
     def img_to_idxBl(self, inp_img_no_grad: torch.Tensor,

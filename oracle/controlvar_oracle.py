@@ -271,6 +271,75 @@ def img_to_idxBl(img: Tensor, vsd: Dict[str, Tensor], patch_nums: Sequence[int])
     return f_to_idxBl(img_to_f(img, vsd), patch_nums, vsd)
 
 
+def f_to_fhat_list(f_BChw: Tensor, patch_nums: Sequence[int], vsd: Dict[str, Tensor], K: int = 4) -> List[Tensor]:
+    """VectorQuantizer2.f_to_idxBl_or_fhat(to_fhat=True) - models/quant.py:184-215: f_hat after every scale."""
+    B, C, H, W = f_BChw.shape
+    f_rest = f_BChw.detach().clone()
+    f_hat = torch.zeros_like(f_rest)
+    emb = vsd["quantize.embedding.weight"]
+    SN = len(patch_nums)
+    out = []
+    for si, pn in enumerate(patch_nums):
+        z_NC = (F.interpolate(f_rest, size=(pn, pn), mode="area") if si != SN - 1 else f_rest).permute(0, 2, 3, 1).reshape(-1, C)
+        idx_Bhw = vq_nearest(z_NC, emb).view(B, pn, pn)
+        h = F.embedding(idx_Bhw, emb).permute(0, 3, 1, 2)
+        h = F.interpolate(h, size=(H, W), mode="bicubic").contiguous() if si != SN - 1 else h.contiguous()
+        k = phi_index(si, SN, K)
+        h = phi(h, vsd[f"quantize.quant_resi.qresi_ls.{k}.weight"], vsd[f"quantize.quant_resi.qresi_ls.{k}.bias"])
+        f_hat.add_(h)
+        f_rest.sub_(h)
+        out.append(f_hat.clone())
+    return out
+
+
+def img_to_recon_last(img: Tensor, vsd: Dict[str, Tensor], patch_nums: Sequence[int]) -> Tensor:
+    """VQVAE.img_to_recon(last_one=True) - models/vqvae.py:80-86: decoder(post_quant_conv(f_hat_last)), NOT clamped."""
+    f_hat = f_to_fhat_list(img_to_f(img, vsd), patch_nums, vsd)[-1]
+    return decoder_forward(_conv(f_hat, vsd, "post_quant_conv", 1), vsd)
+
+
+def idxBl_to_fhat_list(ms_idx_Bl: List[Tensor], patch_nums: Sequence[int], vsd: Dict[str, Tensor], K: int = 4) -> List[Tensor]:
+    """VQVAE.idxBl_to_img's embedding step + VectorQuantizer2.embed_to_fhat(all_to_max_scale=True) - models/vqvae.py:97-104,
+    models/quant.py:156-170: f_hat after every scale from given token ids."""
+    emb = vsd["quantize.embedding.weight"]
+    B, Cv = ms_idx_Bl[0].shape[0], emb.shape[1]
+    SN, HW = len(patch_nums), patch_nums[-1]
+    f_hat = torch.zeros(B, Cv, HW, HW)
+    out = []
+    for si, pn in enumerate(patch_nums):
+        h = F.embedding(ms_idx_Bl[si], emb).transpose(1, 2).view(B, Cv, pn, pn)
+        if si < SN - 1:
+            h = F.interpolate(h, size=(HW, HW), mode="bicubic")
+        k = phi_index(si, SN, K)
+        f_hat.add_(phi(h, vsd[f"quantize.quant_resi.qresi_ls.{k}.weight"], vsd[f"quantize.quant_resi.qresi_ls.{k}.bias"]))
+        out.append(f_hat.clone())
+    return out
+
+
+def idxBl_to_img_last(ms_idx_Bl: List[Tensor], patch_nums: Sequence[int], vsd: Dict[str, Tensor]) -> Tensor:
+    """VQVAE.idxBl_to_img(same_shape=True, last_one=True) - models/vqvae.py:97-104, 91-93 (clamped to [-1, 1])."""
+    return fhat_to_img(idxBl_to_fhat_list(ms_idx_Bl, patch_nums, vsd)[-1], vsd)
+
+
+def idxBl_to_var_input(ms_idx_Bl: List[Tensor], patch_nums: Sequence[int], vsd: Dict[str, Tensor], K: int = 4) -> List[Tensor]:
+    """VectorQuantizer2.idxBl_to_var_input (= VQVAE.idxBl_to_h) - models/quant.py:217-241: the teacher-forcing inputs of
+    VAR training, one (B, pn_next^2, Cvae) tensor per scale transition."""
+    emb = vsd["quantize.embedding.weight"]
+    B, Cv = ms_idx_Bl[0].shape[0], emb.shape[1]
+    SN, HW = len(patch_nums), patch_nums[-1]
+    f_hat = torch.zeros(B, Cv, HW, HW)
+    out = []
+    pn_next = patch_nums[0]
+    for si in range(SN - 1):
+        h = F.interpolate(F.embedding(ms_idx_Bl[si], emb).transpose_(1, 2).view(B, Cv, pn_next, pn_next), size=(HW, HW),
+                          mode="bicubic")
+        k = phi_index(si, SN, K)
+        f_hat.add_(phi(h, vsd[f"quantize.quant_resi.qresi_ls.{k}.weight"], vsd[f"quantize.quant_resi.qresi_ls.{k}.bias"]))
+        pn_next = patch_nums[si + 1]
+        out.append(F.interpolate(f_hat, size=(pn_next, pn_next), mode="area").view(B, Cv, -1).transpose(1, 2))
+    return out
+
+
 def vq_nearest_margin(z_NC: Tensor, emb: Tensor) -> Tensor:
     """Test helper: gap between the two smallest code distances of every latent vector (ambiguous argmins)."""
     d = torch.sum(z_NC.square(), dim=1, keepdim=True) + torch.sum(emb.square(), dim=1, keepdim=False)

@@ -33,7 +33,11 @@ def load_golden(name):
         return dict(meta=meta, cfg=cfg, logits_sub=torch.from_numpy(z["logits_sub"]))
     idx = [torch.from_numpy(z[f"idx_{si}"].astype(np.int64)) for si in range(len(cfg.patch_nums))]
     if meta.get("kind") == "enc":
-        return dict(meta=meta, cfg=cfg, idx=idx, f=torch.from_numpy(z["f"]))
+        out = dict(meta=meta, cfg=cfg, idx=idx, f=torch.from_numpy(z["f"]))
+        if "recon_sub" in z:
+            out.update(img_from_tokens_sub=torch.from_numpy(z["img_from_tokens_sub"]), recon_sub=torch.from_numpy(z["recon_sub"]),
+                       h=[torch.from_numpy(z[f"h_{si}"]) for si in range(len(cfg.patch_nums) - 1)])
+        return out
     if meta.get("kind") == "cond":
         forced = [torch.from_numpy(z[f"forced_{si}"].astype(np.int64)) for si in range(len(cfg.patch_nums))]
         return dict(meta=meta, cfg=cfg, idx=idx, forced=forced, f_hat=torch.from_numpy(z["f_hat"]),

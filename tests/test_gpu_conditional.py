@@ -212,6 +212,33 @@ def test_img_to_idxBl_end_to_end(name):
     assert same >= 0.97 * total
 
 
+@pytest.mark.parametrize("name", golden_names("enc"))
+def test_idxBl_to_img_idxBl_to_h_img_to_recon_match_reference_golden(name):
+    """The remaining VQVAE entry points of the boundary (vqvae.py:77-104): tokens -> image, tokens -> teacher-forcing
+    inputs of ControlVAR.forward, image -> reconstruction (unclamped), against the reference's own outputs."""
+    gold = load_golden(name)
+    m, cfg = gold["meta"], gold["cfg"]
+    vae = _vae(cfg)
+    toks = [g(t) for t in gold["idx"]]
+    sub = m["img_sub"]
+    img = vae.idxBl_to_img(toks, same_shape=True, last_one=True)
+    e1 = (img.cpu()[:, :, ::sub, ::sub] - gold["img_from_tokens_sub"]).abs().max().item()
+    per_scale = vae.idxBl_to_img(toks, same_shape=True, last_one=False)
+    assert len(per_scale) == len(cfg.patch_nums) and torch.equal(per_scale[-1], img)
+    hs = vae.idxBl_to_h(toks)
+    assert [tuple(h.shape) for h in hs] == [tuple(h.shape) for h in gold["h"]]
+    e2 = max((a.cpu() - b).abs().max().item() for a, b in zip(hs, gold["h"]))
+    # the reconstruction goes through the GPU encoder: its tokens equal the reference's on these inputs (previous test)
+    rec = vae.img_to_recon(g(W.synthetic_image(m["B"], cfg.img_hw, m["img_seed"])), v_patch_nums=cfg.patch_nums, last_one=True)
+    e3 = (rec.cpu()[:, :, ::sub, ::sub] - gold["recon_sub"]).abs().max().item()
+    print(f"\n[vqvae surface {name}] idxBl_to_img {e1:.2e}  idxBl_to_h {e2:.2e}  img_to_recon {e3:.2e} (|recon| max {m['recon_absmax']:.2f})")
+    assert e1 < 1e-4 and e2 < 1e-5 and e3 < 1e-4 * max(1.0, m["recon_absmax"])
+    with pytest.raises(NotImplementedError):
+        vae.idxBl_to_img(toks, same_shape=False)
+    # idxBl_to_h feeds forward(): shapes line up with L - first_l
+    assert sum(h.shape[1] for h in hs) * 2 == cfg.L - cfg.first_l
+
+
 # --------------------------------------------------------------------------------- conditional_infer_cfg
 @pytest.mark.parametrize("name", golden_names("cond"))
 def test_conditional_infer_matches_reference_golden(name):

@@ -43,6 +43,13 @@ def test_oracle_img_to_idxBl_matches_reference_golden(name):
     # tokens from the golden's own f: independent of sub-ulp differences of the encoder across CPU ISAs
     for si, (a, b) in enumerate(zip(g["idx"], O.f_to_idxBl(g["f"], cfg.patch_nums, vsd))):
         assert torch.equal(a, b), f"tokens differ at scale {si}"
+    # idxBl_to_img / idxBl_to_h / img_to_recon (vqvae.py:77-104) from the golden's tokens
+    sub = m["img_sub"]
+    assert (O.idxBl_to_img_last(g["idx"], cfg.patch_nums, vsd)[:, :, ::sub, ::sub] - g["img_from_tokens_sub"]).abs().max().item() <= 1e-6
+    for a, b in zip(g["h"], O.idxBl_to_var_input(g["idx"], cfg.patch_nums, vsd)):
+        assert (a - b).abs().max().item() <= 1e-6
+    recon = O.decoder_forward(O._conv(O.idxBl_to_fhat_list(g["idx"], cfg.patch_nums, vsd)[-1], vsd, "post_quant_conv", 1), vsd)
+    assert (recon[:, :, ::sub, ::sub] - g["recon_sub"]).abs().max().item() <= 5e-5      # same f_hat reached by another op order
 
 
 @pytest.mark.parametrize("name", [n for n in golden_names("cond") if "pn10" not in n])

@@ -25,7 +25,6 @@
 //           empty[s] - both copies; released by the leader's tcgen05.commit ... multicast::cluster 0b11
 //           tm_full  - both copies (multicast commit); tm_empty - leader's copy, 2 x 256 epilogue arrivals (peer: remote)
 #include <cuda.h>
-#include <stdlib.h>
 #include <mutex>
 #include "sgemm.cuh"
 #include "tc_ptx.cuh"
@@ -113,26 +112,12 @@ __device__ __forceinline__ void tile_coords(int tile, int m_tiles, int n_tiles, 
   mt = first_m + (in_g - nt * gm);
 }
 
-// BKT: K-block in 4-byte units.  32 = 128-byte rows, three 64 KB stages (default); 16 = 64-byte rows, SIX 32 KB stages:
-// the same bytes in flight refilled in finer steps (experiment, CVAR_TC2_BK=16; the conv kernel's geometry).
-template <int BKT>
-struct StageCfg {
-  static constexpr int kABytes = BM * BKT * 4;
-  static constexpr int kBBytes = (BN / 2) * BKT * 4;
-  static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
-  static constexpr int kStages = BKT == 32 ? 3 : 6;
-  static constexpr int kSmem = kStages * kStageBytes + kStagingBytes + 1024 + 1024;
-};
-
-template <class EP, bool F16, int BKT>
+template <class EP, bool F16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 tc_gemm2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
                 const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo, EP ep,
                 long long M, int N, int K, int m_tiles, int n_tiles) {
-  using G = Geo<BKT>;
-  using SC = StageCfg<BKT>;
-  constexpr int BK = BKT;
-  constexpr int kABytes = SC::kABytes, kBBytes = SC::kBBytes, kStageBytes = SC::kStageBytes, kStages = SC::kStages;
+  using G = Geo<BK>;
   // instruction descriptor: D fp32; A/B format 2 = TF32 (kind::tf32) or 0 = FP16 (kind::f16); N, M of the pair tile
   constexpr uint32_t kFmt = F16 ? 0u : 2u;
   constexpr uint32_t kIdesc = (1u << 4) | (kFmt << 7) | (kFmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
@@ -476,7 +461,7 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 // row-major [rows, K] fp32 (or fp16) matrix -> (128 bytes x 128 rows) box, 128-byte swizzle, out-of-range rows zero-filled
-static int make_map(CUtensorMap* map, const void* base, long long rows, int K, long long ld, bool f16, int bk = BK) {
+static int make_map(CUtensorMap* map, const void* base, long long rows, int K, long long ld, bool f16) {
   EncodeTiledFn enc = get_encode();
   if (!enc) {
     set_error("tc_gemm2: cuTensorMapEncodeTiled is not available from the driver");
@@ -484,11 +469,11 @@ static int make_map(CUtensorMap* map, const void* base, long long rows, int K, l
   }
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * (f16 ? 2 : 4)};
-  cuuint32_t box[2] = {(cuuint32_t)(f16 ? 2 * bk : bk), 128};      // bk 4-byte units per row: 128 or 64 bytes
+  cuuint32_t box[2] = {(cuuint32_t)(f16 ? 2 * BK : BK), 128};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
-                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   bk == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("tc_gemm2: cuTensorMapEncodeTiled failed with %d (rows=%lld K=%d ld=%lld)", (int)r, rows, K, ld);
@@ -549,45 +534,26 @@ static int num_sms() {
   return n;
 }
 
-// experiment switch: CVAR_TC2_BK=16 runs the FP16-pair dense layers with six 32 KB stages (64-byte rows)
-static int dense_bk() {
-  static int v = 0;
-  if (v == 0) {
-    const char* e = getenv("CVAR_TC2_BK");
-    v = (e != nullptr && e[0] == '1' && e[1] == '6' && e[2] == '\0') ? 16 : 32;
-  }
-  return v;
-}
-
-template <class EP, bool F16, int BKT>
-int launch_bk(const EP& ep, const void* A_hi, const void* A_lo, long long lda, const void* W_hi, const void* W_lo,
-              long long ldw, long long M, int N, int K, cudaStream_t s, const char* name) {
+template <class EP, bool F16>
+int launch(const EP& ep, const void* A_hi, const void* A_lo, long long lda, const void* W_hi, const void* W_lo,
+           long long ldw, long long M, int N, int K, cudaStream_t s, const char* name) {
   CUtensorMap mah, mal, mbh, mbl;
-  int rc = make_map(&mah, A_hi, M, K, lda, F16, BKT);
-  if (!rc) rc = make_map(&mal, A_lo, M, K, lda, F16, BKT);
-  if (!rc) rc = make_map(&mbh, W_hi, N, K, ldw, F16, BKT);
-  if (!rc) rc = make_map(&mbl, W_lo, N, K, ldw, F16, BKT);
+  int rc = make_map(&mah, A_hi, M, K, lda, F16);
+  if (!rc) rc = make_map(&mal, A_lo, M, K, lda, F16);
+  if (!rc) rc = make_map(&mbh, W_hi, N, K, ldw, F16);
+  if (!rc) rc = make_map(&mbl, W_lo, N, K, ldw, F16);
   if (rc) return rc;
-  constexpr int smem = StageCfg<BKT>::kSmem;
-  auto kern = tc_gemm2_kernel<EP, F16, BKT>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  auto kern = tc_gemm2_kernel<EP, F16>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
   if (e != cudaSuccess) {
-    set_error("%s: cannot raise shared memory to %d: %s", name, smem, cudaGetErrorString(e));
+    set_error("%s: cannot raise shared memory to %d: %s", name, kSmem, cudaGetErrorString(e));
     return -2;
   }
   const int m_tiles = cdiv(M, 256), n_tiles = cdiv(N, BN);
   const int pairs = min(num_sms() / 2, m_tiles * n_tiles);
-  kern<<<2 * pairs, kThreads, smem, s>>>(mah, mal, mbh, mbl, ep, M, N, K, m_tiles, n_tiles);
+  kern<<<2 * pairs, kThreads, kSmem, s>>>(mah, mal, mbh, mbl, ep, M, N, K, m_tiles, n_tiles);
   CVAR_CHECK_LAUNCH(name);
   return 0;
-}
-
-template <class EP, bool F16>
-int launch(const EP& ep, const void* A_hi, const void* A_lo, long long lda, const void* W_hi, const void* W_lo,
-           long long ldw, long long M, int N, int K, cudaStream_t s, const char* name) {
-  if (F16 && dense_bk() == 16)
-    return launch_bk<EP, F16, 16>(ep, A_hi, A_lo, lda, W_hi, W_lo, ldw, M, N, K, s, name);
-  return launch_bk<EP, F16, 32>(ep, A_hi, A_lo, lda, W_hi, W_lo, ldw, M, N, K, s, name);
 }
 
 static bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }

@@ -46,7 +46,7 @@ class ConvArgs(C.Structure):
         ("out_mode", C.c_int), ("out_rows_total", C.c_int), ("row_offset", C.c_int),
         ("engine", C.c_int),
         ("x16_hi", C.c_void_p), ("x16_lo", C.c_void_p), ("w16_hi", C.c_void_p), ("w16_lo", C.c_void_p),
-        ("downsample2x", C.c_int), ("ksplit", C.c_int),
+        ("downsample2x", C.c_int), ("ksplit", C.c_int), ("out_samples", C.c_int),
     ]
 
 
@@ -57,6 +57,7 @@ PROTOTYPES = {
     "cvar_launch_count": (c_ll, []),
     "cvar_set_gemm_engine": (C.c_int, [C.c_int]),
     "cvar_get_gemm_engine": (C.c_int, []),
+    "cvar_set_epilogue_overlap": (C.c_int, [C.c_int]),
     "cvar_set_tc_kblock": (C.c_int, [C.c_int]),
     "cvar_debug_set_trace": (C.c_int, [C.c_void_p]),
     "cvar_debug_set_attn_trace": (C.c_int, [C.c_void_p]),

@@ -16,7 +16,8 @@ replicas with ``cvar_cfg_sample_multi`` (4-way mix, one draw per replica row, te
 
 Differences from the reference that do not change results: ``ada_lin`` (constant across scales) is evaluated once
 per call instead of once per block per scale; the KV cache is a pre-allocated arena written in place instead of
-``torch.cat`` growth; the control and image halves of ``f_hat`` are decoded in one batched decoder pass.
+``torch.cat`` growth; the control and image halves of ``f_hat`` are decoded in one decoder pass over 2B maps
+(``VQVAE._fhat_halves_to_img``) instead of two passes over B.
 Branches no released configuration uses (``separator``, ``type_pos``, ``bidirectional``, ``separate_decoding``,
 ``shared_aln``, ``aln < 0``, ``mask_factor == 1``, ``more_smooth``) raise NotImplementedError.
 """
@@ -227,6 +228,35 @@ class ControlVAR(nn.Module):
             c["codebook"] = vq.get_parameter("quantize.embedding.weight")
         return c
 
+    # -------------------------------------------------------------------------------- argument validation
+    # The kernels index embedding tables with these ids (class_emb[label], cond_embed[type], codebook[token]); the
+    # reference fails with an embedding device-assert / a shape error on bad input, a raw kernel would read out of bounds.
+    def _check_ids(self, label_B: torch.Tensor, cond_type: torch.Tensor, B: int) -> None:
+        if tuple(label_B.shape) != (B,) or tuple(cond_type.shape) != (B,):
+            raise ValueError(f"label_B / cond_type must have shape ({B},), got {tuple(label_B.shape)} / {tuple(cond_type.shape)}")
+        bad = ((label_B < 0) | (label_B > self.num_classes)).any() | ((cond_type < 0) | (cond_type > 4)).any()
+        if bool(bad):
+            raise ValueError(f"label_B must be in [0, {self.num_classes}] and cond_type in [0, 4] "
+                             f"(ids {self.num_classes} / 4 are the unconditional entries)")
+
+    def _check_forced(self, lst, B: int, what: str):
+        if lst is None:
+            return None
+        if len(lst) != len(self.patch_nums):
+            raise ValueError(f"{what}: expected {len(self.patch_nums)} token maps (one per scale), got {len(lst)}")
+        out, bad = [], None
+        for si, (pn, t) in enumerate(zip(self.patch_nums, lst)):
+            if not torch.is_tensor(t) or tuple(t.shape) != (B, pn * pn):
+                raise ValueError(f"{what}[{si}] must be a ({B}, {pn * pn}) token tensor (VQVAE.img_to_idxBl with the model's "
+                                 f"patch_nums), got {tuple(t.shape) if torch.is_tensor(t) else type(t)}")
+            t = t.to(device=self.device, dtype=torch.int64).contiguous()
+            b = ((t < 0) | (t >= self.V)).any()
+            bad = b if bad is None else (bad | b)
+            out.append(t)
+        if bool(bad):
+            raise ValueError(f"{what}: token ids must be in [0, {self.V})")
+        return out
+
     # ------------------------------------------------------------------------------------------- sampler
     @torch.no_grad()
     def autoregressive_infer_cfg(
@@ -264,7 +294,7 @@ class ControlVAR(nn.Module):
             random.random()      # control_var.py:403 draws from Python's global RNG even when bidirectional=False
         else:
             cond_type = torch.zeros(B, dtype=torch.long, device=dev)
-        assert label_B.shape == (B,) and cond_type.shape == (B,)
+        self._check_ids(label_B, cond_type, B)
 
         label_R = torch.cat((label_B, torch.full_like(label_B, self.num_classes)))         # control_var.py:381
         cond_R = torch.cat((cond_type, torch.full_like(cond_type, 4)))                     # control_var.py:399-400
@@ -301,7 +331,7 @@ class ControlVAR(nn.Module):
             cond_type = torch.full((B,), cond_type)
         label_B = label_B.to(device=dev, dtype=torch.long).contiguous()
         cond_type = cond_type.to(device=dev, dtype=torch.long).contiguous()
-        assert label_B.shape == (B,) and cond_type.shape == (B,)
+        self._check_ids(label_B, cond_type, B)
         cfg = tuple(float(c) for c in cfg)
         assert len(cfg) == 3
         empty_cls = torch.full_like(label_B, self.num_classes)                             # control_var.py:252
@@ -309,15 +339,10 @@ class ControlVAR(nn.Module):
         label_R = torch.cat((label_B, empty_cls, empty_cls, empty_cls))                    # control_var.py:256
         cond_R = torch.cat((cond_type, cond_type, empty_ct, empty_ct))                     # control_var.py:263
 
-        def forced(lst):
-            if lst is None:
-                return None
-            assert len(lst) == len(self.patch_nums)
-            return [t.to(device=dev, dtype=torch.int64).contiguous() for t in lst]
-
         return self._sample(B, label_R, cond_R, groups=4,
                             mix=lambda ratio: (cfg[0] * ratio, cfg[1] * ratio, cfg[2] * ratio), replicas=4,
-                            top_k=top_k, top_p=top_p, rng=rng, c_mask=forced(c_mask), c_img=forced(c_img))
+                            top_k=top_k, top_p=top_p, rng=rng, c_mask=self._check_forced(c_mask, B, "c_mask"),
+                            c_img=self._check_forced(c_img, B, "c_img"))
 
     # ------------------------------------------------------------------------------------ the shared scale loop
     def _sample(self, B: int, label_R: torch.Tensor, cond_R: torch.Tensor, *, groups: int, mix, replicas: int, top_k, top_p,
@@ -380,10 +405,7 @@ class ControlVAR(nn.Module):
                         Bf, pn, pn_next, hw, Cvae, C, streams=2, x_replicas=(2 if replicas == 1 else 1))
 
         # ---- decode both halves (control rows on top, image rows below): control_var.py:563-565 / 349-354
-        side = hw * vae.downsample
-        img = torch.empty(B, 3, 2 * side, side, device=dev, dtype=torch.float32)
-        vae._fhat_to_img(f_hat[:B, :, :hw, :], out=img, rows_total=2 * side, row_offset=0, out_mode=1)
-        vae._fhat_to_img(f_hat[:B, :, hw:, :], out=img, rows_total=2 * side, row_offset=side, out_mode=1)
+        img = vae._fhat_halves_to_img(f_hat, B, out_mode=1)       # one decoder pass over the 2B maps
         self.last_f_hat = f_hat
         return img
 
@@ -411,6 +433,7 @@ class ControlVAR(nn.Module):
         assert x_BLCv_wo_first_l.shape == (B, self.L - self.first_l, Cvae)
         label_B = label_B.to(device=dev, dtype=torch.long)
         cond_type = cond_type.to(device=dev, dtype=torch.long)
+        self._check_ids(label_B, cond_type, B)
         label_B = torch.where(torch.rand(B, device=dev) < self.cond_drop_rate, self.num_classes, label_B)      # :577
         cond_type = torch.where(torch.rand(B, device=dev) < self.cond_drop_rate, 4, cond_type)                # :584
         xin = x_BLCv_wo_first_l.to(device=dev, dtype=torch.float32).contiguous()

@@ -262,6 +262,8 @@ extern "C" int cvar_conv2d(const cvar_conv_args* a, void* stream) {
                                     a->x16_hi == nullptr && a->in_a == nullptr),
                "cvar_conv2d: downsample2x needs ks = 3, even Hin / Win, fp32 input, no upsampling / fused input transform");
   CVAR_REQUIRE(a->out_mode == 0 || a->resid == nullptr, "cvar_conv2d: image output takes no residual");
+  CVAR_REQUIRE(a->out_samples >= 0 && (a->out_samples == 0 || (a->out_mode != 0 && a->B % a->out_samples == 0)),
+               "cvar_conv2d: out_samples must divide B and needs an image out_mode (B=%d out_samples=%d)", a->B, a->out_samples);
   CVAR_REQUIRE((a->in_a == nullptr) == (a->in_b == nullptr), "cvar_conv2d: in_a/in_b must come together");
   cudaStream_t s = (cudaStream_t)stream;
   if (a->x16_hi != nullptr) {
@@ -281,6 +283,7 @@ extern "C" int cvar_conv2d(const cvar_conv_args* a, void* stream) {
   if (a->Cout == 3 && a->ks == 3 && !up && !down && a->in_a == nullptr && a->resid == nullptr && a->Cin % 4 == 0 &&
       (size_t)3 * K * sizeof(float) <= 48 * 1024) {
     ConvEpilogue ep3{a->out, a->bias, nullptr, a->Cout, a->out_mode, Hout, Wout, a->out_rows_total, a->row_offset};
+    ep3.out_samples = a->out_samples;
     conv3x3_small_cout_kernel<3><<<cdiv(M, 128), 128, (size_t)3 * K * sizeof(float), s>>>(a->x, a->w, ep3, Hout, Wout,
                                                                                          a->Cin, M);
     CVAR_CHECK_LAUNCH("cvar_conv2d[cout3]");
@@ -293,6 +296,7 @@ extern "C" int cvar_conv2d(const cvar_conv_args* a, void* stream) {
   al.Hv = a->Hin << up, al.Wv = a->Win << up, al.stride = down ? 2 : 1, al.pad = down ? 0 : (a->ks >> 1);
   DenseBLoader bl{a->w, K, 0, a->Cout, K, 0, 1};
   ConvEpilogue ep{a->out, a->bias, a->resid, a->Cout, a->out_mode, Hout, Wout, a->out_rows_total, a->row_offset};
+  ep.out_samples = a->out_samples;
   return launch_sgemm(al, bl, ep, M, a->Cout, K, 1, s, "cvar_conv2d");
 }
 

@@ -25,6 +25,7 @@
 #include "tc_ptx.cuh"
 
 namespace cvar {
+int tc2_set_trace(long long* dev_ptr);
 namespace tc {
 
 constexpr int BM = 128;
@@ -358,6 +359,7 @@ static int num_sms() {
 int g_tc_bk = 32;
 
 int set_trace(long long* dev_ptr) {
+  if (cvar::tc2_set_trace(dev_ptr) != 0) return -1;           // the 2-CTA kernels share the switch (own layout)
   return cudaMemcpyToSymbol(g_trace, &dev_ptr, sizeof(dev_ptr)) == cudaSuccess ? 0 : -1;
 }   // K-block of the engine: 32 (SWIZZLE_128B) or 16 (SWIZZLE_64B, deeper pipeline)
 
@@ -442,6 +444,7 @@ int tc_conv_try(const cvar_conv_args* a, cudaStream_t s) {
   al.Hout = Hout, al.Wout = Wout, al.Mtot = M, al.K = K;
   al.Hv = Hout, al.Wv = Wout, al.stride = 1, al.pad = a->ks >> 1;
   ConvEpilogue ep{a->out, a->bias, a->resid, a->Cout, a->out_mode, Hout, Wout, a->out_rows_total, a->row_offset};
+  ep.out_samples = a->out_samples;
   int rc = dispatch_tc(al, ep, a->w_hi, a->w_lo, K, M, a->Cout, K, s, "cvar_conv2d[tc]");
   return rc ? rc : 1;
 }

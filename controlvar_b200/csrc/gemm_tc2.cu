@@ -25,11 +25,19 @@
 //           empty[s] - both copies; released by the leader's tcgen05.commit ... multicast::cluster 0b11
 //           tm_full  - both copies (multicast commit); tm_empty - leader's copy, 2 x 256 epilogue arrivals (peer: remote)
 #include <cuda.h>
+#include <stdlib.h>
 #include <mutex>
 #include "sgemm.cuh"
 #include "tc_ptx.cuh"
 
 namespace cvar {
+// 1 (default): the tcgen05 epilogues drain tensor memory into registers and overlap their global-memory work with the
+// next tile's main loop; 0: the round-1 epilogue (tensor memory held until the tile is stored).  Same values either way.
+static int initial_epi_overlap() {
+  const char* e = getenv("CVAR_EPI_OVERLAP");
+  return (e != nullptr && e[0] == '0') ? 0 : 1;
+}
+int g_epi_overlap = initial_epi_overlap();
 namespace tc2 {
 using namespace cvar::tc;
 
@@ -48,6 +56,15 @@ constexpr int kStagingBytes = kEpiWarps * 32 * kStagePitch * 4;
 constexpr int kSmem = kStages * kStageBytes + kStagingBytes + 1024 + 1024;
 constexpr uint32_t kPeerMask = 0xFEFFFFFFu;          // clears the CTA-rank bit of a shared::cluster address (leader's copy)
 constexpr int kGroupM = 16;                          // pair-tiles (256 rows) per rasterisation group
+
+// Optional tile trace (diagnostics, cvar_debug_set_trace): CTA 0 stamps clock64() for its first 64 tiles.
+// trace[tile * 8 + ev]: 0 MMA thread has tensor memory (tm_empty seen), 1 last MMA of the tile committed,
+// 2 epilogue warp 0 sees tm_full, 3 it has released tensor memory, 4 it has stored its slice; 5 TMA thread issued the
+// tile's first stage, 6 its last stage.
+__device__ long long* g_trace2 = nullptr;
+__device__ __forceinline__ void trace2(int tile_i, int ev) {
+  if (g_trace2 != nullptr && blockIdx.x == 0 && tile_i < 64) g_trace2[tile_i * 8 + ev] = clock64();
+}
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -112,7 +129,106 @@ __device__ __forceinline__ void tile_coords(int tile, int m_tiles, int n_tiles, 
   mt = first_m + (in_g - nt * gm);
 }
 
-template <class EP, bool F16>
+
+// ------------------------------------------------------------------------------------------------ epilogue of one tile
+// Each epilogue warp owns 32 accumulator rows (its TMEM lane quarter) and `ncols` (multiple of 16, <= 128) columns
+// starting at `col0`.  The accumulators fill all 512 TMEM columns (main + cross), so the next tile's MMAs cannot start
+// until this tile has left tensor memory.  kOverlap: the warp first pulls its whole slice into REGISTERS (main and cross
+// folded: fma(cross, 2^-11, main), the same operation as before), releases tensor memory, and only then runs the slow
+// part - shared-memory transposes, residual / gamma loads, GELU, pair split, global stores - which therefore overlaps the
+// next tile's main loop.  Exposed per tile: ~16 tcgen05.ld per warp instead of the whole epilogue (round 1 measured a tile
+// of fc1 at ~68k cycles against 37k cycles of MMA).  Values and their order of evaluation are unchanged: bit-identical.
+// direct-store hook: an epilogue may take a 16-column chunk straight from the accumulator layout (lane = row); the
+// QKV epilogue does for V^T, whose contiguous index is the token (= the lane), instead of scattering 2-byte stores.
+template <class EP>
+__device__ __forceinline__ bool epi_chunk_direct(const EP&, long long, int, const float*, long long, int) { return false; }
+__device__ __forceinline__ bool epi_chunk_direct(const QkvEpilogue& e, long long m, int n0, const float* a, long long M, int N) {
+  if (e.q16_hi == nullptr || n0 < 2 * e.C) return false;      // warp-uniform: C is a multiple of 16
+  if (m >= M || n0 >= N) return true;
+  const int c0 = n0 - 2 * e.C;
+  const int r = (int)(m / e.l), t = (int)(m - (long long)r * e.l);
+  const int h = c0 >> 6, d0 = c0 & 63;                         // a 16-column chunk stays inside one head
+  const long long off = (((long long)r * e.H + h) * 64 + d0) * e.T_max + e.L_prev + t;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float o = __fadd_rn(a[i], e.v_bias[c0 + i]);
+    split_f16(o, e.vt16_hi[off + (long long)i * e.T_max], e.vt16_lo[off + (long long)i * e.T_max]);
+  }
+  return true;
+}
+
+template <class EP>
+__device__ __forceinline__ void epi_chunk(const EP& ep, const float* a16, float* stage, int lane, long long m_base, int n0,
+                                          long long M, int N) {
+  if (epi_chunk_direct(ep, m_base + lane, n0, a16, M, N)) return;
+#pragma unroll
+  for (int q = 0; q < kEpiCols / 4; ++q)
+    *reinterpret_cast<float4*>(stage + lane * kStagePitch + q * 4) =
+        make_float4(a16[4 * q], a16[4 * q + 1], a16[4 * q + 2], a16[4 * q + 3]);
+  __syncwarp();
+  const int n = n0 + (lane & 3) * 4;
+  const int nvalid = min(4, N - n);
+  EpiAux aux[4];
+#pragma unroll
+  for (int r8 = 0; r8 < 4; ++r8) {
+    const long long m = m_base + r8 * 8 + (lane >> 2);
+    if (m < M && n < N) aux[r8] = epi_load_aux(ep, m, n, nvalid, 0);
+  }
+#pragma unroll
+  for (int r8 = 0; r8 < 4; ++r8) {
+    const int rr = r8 * 8 + (lane >> 2);
+    const float4 x = *reinterpret_cast<const float4*>(stage + rr * kStagePitch + (lane & 3) * 4);
+    const long long m = m_base + rr;
+    if (m < M && n < N) epi_store_aux(ep, m, n, &x.x, nvalid, 0, aux[r8]);
+  }
+  __syncwarp();
+}
+
+template <class EP, bool kOverlap, bool kCross>
+__device__ __forceinline__ void epilogue_tile(const EP& ep, uint32_t tcol, int col0, int ncols, float lo_scale,
+                                              long long m_base, int n_base, long long M, int N, float* stage, int lane,
+                                              uint64_t* tm_empty, int trace_tile) {
+  constexpr int kAccStride = 256;
+  if (kOverlap) {
+    float acc[128];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      if (c * kEpiCols < ncols) {
+        float v[kEpiCols], w[kEpiCols];
+        tmem_ld16_nowait(tcol + (uint32_t)(col0 + c * kEpiCols), v);
+        if (kCross) tmem_ld16_nowait(tcol + (uint32_t)(kAccStride + col0 + c * kEpiCols), w);
+        tmem_ld_wait();
+        reg_fence_16(v);
+        if (kCross) reg_fence_16(w);
+#pragma unroll
+        for (int i = 0; i < kEpiCols; ++i) acc[c * kEpiCols + i] = kCross ? fmaf(w[i], lo_scale, v[i]) : v[i];
+      }
+    }
+    tc_fence_before();
+    mbar_arrive_leader(tm_empty);                       // tensor memory is free: the next tile's MMAs may start
+    if (threadIdx.x == 0) trace2(trace_tile, 3);
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      if (c * kEpiCols < ncols) epi_chunk(ep, &acc[c * kEpiCols], stage, lane, m_base, n_base + col0 + c * kEpiCols, M, N);
+  } else {
+#pragma unroll 1
+    for (int c = 0; c < ncols; c += kEpiCols) {
+      float v[kEpiCols], w[kEpiCols];
+      tmem_ld_32x32b_x16(tcol + (uint32_t)(col0 + c), v);
+      if (kCross) {
+        tmem_ld_32x32b_x16(tcol + (uint32_t)(kAccStride + col0 + c), w);
+#pragma unroll
+        for (int i = 0; i < kEpiCols; ++i) v[i] = fmaf(w[i], lo_scale, v[i]);
+      }
+      epi_chunk(ep, v, stage, lane, m_base, n_base + col0 + c, M, N);
+    }
+    tc_fence_before();
+    mbar_arrive_leader(tm_empty);
+    if (threadIdx.x == 0) trace2(trace_tile, 3);
+  }
+}
+
+template <class EP, bool F16, bool kOverlap>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 tc_gemm2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
                 const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo, EP ep,
@@ -171,38 +287,12 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constan
       tile_coords(tile, m_tiles, n_tiles, mt, nt);
       mbar_wait(tm_full, tcount & 1);
       tc_fence_after();
+      if (threadIdx.x == 0) trace2(tcount, 2);
       const long long m_base = (long long)mt * 256 + rank * BM + quarter * 32;
       const uint32_t tcol = tmem_base + ((uint32_t)(quarter * 32) << 16);
-#pragma unroll 1
-      for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += kEpiCols) {
-        float v[kEpiCols], w[kEpiCols];
-        tmem_ld_32x32b_x16(tcol + (uint32_t)c, v);
-        tmem_ld_32x32b_x16(tcol + (uint32_t)(kAccStride + c), w);
-#pragma unroll
-        for (int q = 0; q < kEpiCols / 4; ++q)
-          *reinterpret_cast<float4*>(stage + lane * kStagePitch + q * 4) =
-              make_float4(fmaf(w[4 * q], kLoScale, v[4 * q]), fmaf(w[4 * q + 1], kLoScale, v[4 * q + 1]),
-                          fmaf(w[4 * q + 2], kLoScale, v[4 * q + 2]), fmaf(w[4 * q + 3], kLoScale, v[4 * q + 3]));
-        __syncwarp();
-        const int n = nt * BN + c + (lane & 3) * 4;
-        const int nvalid = min(4, N - n);
-        EpiAux aux[4];
-#pragma unroll
-        for (int r8 = 0; r8 < 4; ++r8) {
-          const long long m = m_base + r8 * 8 + (lane >> 2);
-          if (m < M && n < N) aux[r8] = epi_load_aux(ep, m, n, nvalid, 0);
-        }
-#pragma unroll
-        for (int r8 = 0; r8 < 4; ++r8) {
-          const int rr = r8 * 8 + (lane >> 2);
-          const float4 x = *reinterpret_cast<const float4*>(stage + rr * kStagePitch + (lane & 3) * 4);
-          const long long m = m_base + rr;
-          if (m < M && n < N) epi_store_aux(ep, m, n, &x.x, nvalid, 0, aux[r8]);
-        }
-        __syncwarp();
-      }
-      tc_fence_before();
-      mbar_arrive_leader(tm_empty);
+      epilogue_tile<EP, kOverlap, true>(ep, tcol, half * (BN / 2), BN / 2, kLoScale, m_base, nt * BN, M, N, stage, lane,
+                                        tm_empty, tcount);
+      if (threadIdx.x == 0) trace2(tcount, 4);
     }
   } else if (warp == kTmaWarp) {
     // ================================================================ TMA: own A rows, own half of the weight rows
@@ -217,6 +307,8 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constan
           const int s = it % kStages;
           const uint32_t ph = (it / kStages) & 1;
           mbar_wait(&empty[s], ph ^ 1);
+          if (kb == 0) trace2(it / nkb, 5);
+          if (kb == nkb - 1) trace2(it / nkb, 6);
           if (rank == 0) mbar_arrive_expect_tx(&full[s], 2u * (uint32_t)kStageBytes);   // bytes of BOTH CTAs
           tma_load_2d_2sm(&mapAhi, &full[s], a_hi(s), kb * kBKe, arow);
           tma_load_2d_2sm(&mapAlo, &full[s], a_lo(s), kb * kBKe, arow);
@@ -232,6 +324,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constan
       for (int tile = pair; tile < total_tiles; tile += npairs, ++tcount) {
         mbar_wait(tm_empty, (tcount & 1) ^ 1);
         tc_fence_after();
+        trace2(tcount, 0);
         const uint32_t d = tmem_base, dl = tmem_base + (uint32_t)kAccStride;
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % kStages;
@@ -250,6 +343,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constan
           umma_commit_2sm(&empty[s]);
         }
         umma_commit_2sm(tm_full);
+        trace2(tcount, 1);
       }
     }
   }
@@ -288,7 +382,7 @@ __device__ __forceinline__ void tma_load_4d_2sm(const CUtensorMap* map, uint64_t
       : "memory");
 }
 
-template <class EP>
+template <class EP, bool kOverlap>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 tc_conv2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
                 const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo, EP ep, ConvGeo g,
@@ -348,36 +442,8 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constan
       tc_fence_after();
       const long long m_base = (long long)mt * 256 + rank * BM + quarter * 32;
       const uint32_t tcol = tmem_base + ((uint32_t)(quarter * 32) << 16);
-#pragma unroll 1
-      for (int c = half * (BNr / 2); c < (half + 1) * (BNr / 2); c += kEpiCols) {
-        float v[kEpiCols], w[kEpiCols];
-        tmem_ld_32x32b_x16(tcol + (uint32_t)c, v);
-        tmem_ld_32x32b_x16(tcol + (uint32_t)(kAccStride + c), w);
-#pragma unroll
-        for (int q = 0; q < kEpiCols / 4; ++q)
-          *reinterpret_cast<float4*>(stage + lane * kStagePitch + q * 4) =
-              make_float4(fmaf(w[4 * q], kLoScale, v[4 * q]), fmaf(w[4 * q + 1], kLoScale, v[4 * q + 1]),
-                          fmaf(w[4 * q + 2], kLoScale, v[4 * q + 2]), fmaf(w[4 * q + 3], kLoScale, v[4 * q + 3]));
-        __syncwarp();
-        const int n = nt * BNr + c + (lane & 3) * 4;
-        const int nvalid = min(4, N - n);
-        EpiAux aux[4];
-#pragma unroll
-        for (int r8 = 0; r8 < 4; ++r8) {
-          const long long m = m_base + r8 * 8 + (lane >> 2);
-          if (m < M && n < N) aux[r8] = epi_load_aux(ep, m, n, nvalid, 0);
-        }
-#pragma unroll
-        for (int r8 = 0; r8 < 4; ++r8) {
-          const int rr = r8 * 8 + (lane >> 2);
-          const float4 x = *reinterpret_cast<const float4*>(stage + rr * kStagePitch + (lane & 3) * 4);
-          const long long m = m_base + rr;
-          if (m < M && n < N) epi_store_aux(ep, m, n, &x.x, nvalid, 0, aux[r8]);
-        }
-        __syncwarp();
-      }
-      tc_fence_before();
-      mbar_arrive_leader(tm_empty);
+      epilogue_tile<EP, kOverlap, true>(ep, tcol, half * (BNr / 2), BNr / 2, kLoScale, m_base, nt * BNr, M, N, stage, lane,
+                                        tm_empty, 64);
     }
   } else if (warp == kTmaWarp) {
     // ================================================================ TMA: this CTA's 128 pixels (shifted window per tap)
@@ -543,7 +609,7 @@ int launch(const EP& ep, const void* A_hi, const void* A_lo, long long lda, cons
   if (!rc) rc = make_map(&mbh, W_hi, N, K, ldw, F16);
   if (!rc) rc = make_map(&mbl, W_lo, N, K, ldw, F16);
   if (rc) return rc;
-  auto kern = tc_gemm2_kernel<EP, F16>;
+  auto kern = g_epi_overlap ? tc_gemm2_kernel<EP, F16, true> : tc_gemm2_kernel<EP, F16, false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
   if (e != cudaSuccess) {
     set_error("%s: cannot raise shared memory to %d: %s", name, kSmem, cudaGetErrorString(e));
@@ -558,6 +624,10 @@ int launch(const EP& ep, const void* A_hi, const void* A_lo, long long lda, cons
 
 static bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
 }  // namespace tc2
+
+int tc2_set_trace(long long* dev_ptr) {
+  return cudaMemcpyToSymbol(tc2::g_trace2, &dev_ptr, sizeof(dev_ptr)) == cudaSuccess ? 0 : -1;
+}
 
 // returns 1 when taken, 0 when the shape / operands do not qualify, < 0 on error
 static DenseEpilogue dense_epilogue(const cvar_gemm_args* a) {
@@ -628,7 +698,8 @@ int tc2_conv_f16(const cvar_conv_args* a, cudaStream_t s) {
   if (!rc) rc = tc2::make_map_w64(&mbl, a->w16_lo, a->Cout, K, g.BN / 2);
   if (rc) return rc;
   ConvEpilogue ep{a->out, a->bias, a->resid, a->Cout, a->out_mode, H, W, a->out_rows_total, a->row_offset};
-  auto kern = tc2::tc_conv2_kernel<ConvEpilogue>;
+  ep.out_samples = a->out_samples;
+  auto kern = g_epi_overlap ? tc2::tc_conv2_kernel<ConvEpilogue, true> : tc2::tc_conv2_kernel<ConvEpilogue, false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::kCvSmem);
   CVAR_REQUIRE(e == cudaSuccess, "cvar_conv2d[f16x3]: cannot raise shared memory to %d: %s", tc2::kCvSmem, cudaGetErrorString(e));
   const long long M = (long long)a->B * H * W;

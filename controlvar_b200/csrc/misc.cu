@@ -35,6 +35,12 @@ extern "C" int cvar_set_gemm_engine(int e) {
   return old;
 }
 extern "C" int cvar_get_gemm_engine(void) { return cvar::g_gemm_engine; }
+namespace cvar { extern int g_epi_overlap; }
+extern "C" int cvar_set_epilogue_overlap(int on) {
+  int old = cvar::g_epi_overlap;
+  cvar::g_epi_overlap = on ? 1 : 0;
+  return old;
+}
 namespace cvar { namespace tc { extern int g_tc_bk; int set_trace(long long*); } }
 extern "C" int cvar_debug_set_trace(long long* dev_buf) { return cvar::tc::set_trace(dev_buf); }
 extern "C" int cvar_set_tc_kblock(int bk) {

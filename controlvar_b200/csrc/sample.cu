@@ -125,6 +125,7 @@ __global__ void __launch_bounds__(NT) cfg_sample_kernel(const float* __restrict_
         }
         unsigned excl = incl - local;
         const unsigned rem = sm.sel_remaining;
+        __syncwarp();     // every lane has read sel_remaining before the owning lane rewrites it below
         if (excl < rem && rem <= incl) {
           unsigned c = excl;
 #pragma unroll

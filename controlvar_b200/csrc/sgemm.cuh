@@ -345,6 +345,10 @@ struct ConvEpilogue {
   int Cout, out_mode;
   int Hout, Wout, out_rows_total, row_offset;
   int accumulate = 0;     // K-split continuation (out_mode 0): out += acc, no bias, no residual
+  // image output (out_mode != 0) of a STACKED batch: image n = s * out_samples + b of the batch lands in sample b of the
+  // (out_samples, Cout, out_rows_total, Wout) tensor at rows s * Hout + row_offset (the control / image halves of
+  // control_var.py:563-565 decoded in ONE pass: s = 0 control on top, s = 1 image below).  0: image n is sample n.
+  int out_samples = 0;
   __device__ __forceinline__ void store(long long m, int n, const float* v, int nvalid, int /*batch*/) const {
     if (out_mode == 0) {
       float* o = out + m * Cout + n;
@@ -375,13 +379,18 @@ struct ConvEpilogue {
       long long q = m / Wout;
       int y = (int)(q % Hout);
       long long nimg = q / Hout;
+      int roff = row_offset;
+      if (out_samples > 0) {
+        roff += (int)(nimg / out_samples) * Hout;
+        nimg = nimg % out_samples;
+      }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         if (j < nvalid) {
           float t = __fadd_rn(v[j], bias[n + j]);
           if (out_mode != 3) t = fminf(fmaxf(t, -1.f), 1.f);  // .clamp_(-1, 1)           vqvae.py:89
           if (out_mode == 1) t = __fmul_rn(__fadd_rn(t, 1.f), 0.5f);   // .add_(1).mul_(0.5)  control_var.py:563
-          out[((nimg * Cout + (n + j)) * out_rows_total + row_offset + y) * Wout + xw] = t;
+          out[((nimg * Cout + (n + j)) * out_rows_total + roff + y) * Wout + xw] = t;
         }
       }
     }

@@ -106,6 +106,26 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, float* v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// TMEM load WITHOUT the wait: the destination registers are valid only after tmem_ld_wait() + reg_fence_16 (the wait is a
+// volatile asm without register operands, so the empty asm re-defines the registers and pins every use behind it).
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void reg_fence_16(float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                    "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :: "memory");
+}
+
 // ---------------------------------------------------------------------------------------------- tile geometry
 // K-major operand tile of ROWS x BK fp32 in the canonical UMMA layout: rows of BK*4 bytes (128 B -> SWIZZLE_128B,
 // 64 B -> SWIZZLE_64B), 8-row swizzle atoms stacked every SBO = 8 * row bytes; the 16-byte chunk index inside a row is

@@ -131,6 +131,10 @@ def set_gemm_engine(engine: int) -> int:
     return int(_lib.load().cvar_set_gemm_engine(int(engine)))
 
 
+def set_epilogue_overlap(on: bool) -> int:
+    return int(_lib.load().cvar_set_epilogue_overlap(int(bool(on))))
+
+
 def set_tc_kblock(bk: int) -> int:
     return int(_lib.load().cvar_set_tc_kblock(int(bk)))
 
@@ -405,7 +409,7 @@ def gn_stats(x_nhwc, gamma, beta, a_out, b_out, scratch, B, HW, Cdim, groups=32,
 
 def conv2d(x, w_packed, bias, out, B, Hin, Win, Cin, Cout, ks, *, in_a=None, in_b=None, in_silu=False, resid=None,
            upsample2x=False, out_mode=0, out_rows_total=0, row_offset=0, engine=-1, x16: Optional[F16Pair] = None,
-           w16: Optional[F16Pair] = None, downsample2x=False, ksplit=0):
+           w16: Optional[F16Pair] = None, downsample2x=False, ksplit=0, out_samples=0):
     """x16 + w16: FP16-pair input (already normalised / upsampled) and weight -> the 2-CTA TMA kernel; x may be None.
     downsample2x: the encoder's pad-(0,1,0,1) + stride-2 convolution (vae_modules.py:31-37)."""
     w_packed, w_hi, w_lo, _ = _wparts(w_packed)
@@ -424,6 +428,7 @@ def conv2d(x, w_packed, bias, out, B, Hin, Win, Cin, Cout, ks, *, in_a=None, in_
     a.engine = int(engine)
     a.downsample2x = int(downsample2x)
     a.ksplit = int(ksplit)
+    a.out_samples = int(out_samples)
     up = 2 if upsample2x else 1
     Mo = B * Hin * up * Win * up // (4 if downsample2x else 1)
     with _Timed("conv", 2.0 * Mo * Cout * ks * ks * Cin, 4.0 * (B * Hin * Win * Cin + Mo * Cout + Cout * ks * ks * Cin)):

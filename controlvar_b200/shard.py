@@ -14,6 +14,7 @@ import torch.nn as nn
 def pack_parameters(modules: Iterable[nn.Module]) -> torch.Tensor:
     """Move every floating-point parameter / buffer of ``modules`` into one contiguous fp32 arena (views keep the
     state_dict layout).  Returns the arena so it can be broadcast with a single collective."""
+    modules = list(modules)          # iterated twice below: a generator would skip the cache invalidation
     tensors: List[torch.Tensor] = []
     seen = set()
     for m in modules:
@@ -34,18 +35,28 @@ def pack_parameters(modules: Iterable[nn.Module]) -> torch.Tensor:
         view = arena[o:o + t.numel()].view(t.shape)
         view.copy_(t.data)
         t.data = view
-    for m in modules:
-        if hasattr(m, "_consts"):
-            m._consts.clear()
-        if hasattr(m, "_packed"):
-            m._packed.clear()
+    invalidate_caches(modules)
     return arena
 
 
-def broadcast_weights(arena: torch.Tensor, src: int = 0) -> None:
-    """The path's only collective: one ncclBroadcast of the weight arena (a no-op for a single process)."""
+def invalidate_caches(modules: Iterable[nn.Module]) -> None:
+    """Drop everything DERIVED from the parameters (operand-form weights: TF32 / FP16-pair splits, repacked conv weights,
+    the lvl_pos table, captured CUDA graphs): after the parameters were re-pointed (pack_parameters) or overwritten in
+    place (broadcast_weights) they would otherwise keep the old values."""
+    for m in modules:
+        for name in ("_consts", "_packed", "_packed16", "_graphs"):
+            c = getattr(m, name, None)
+            if c is not None:
+                c.clear()
+
+
+def broadcast_weights(arena: torch.Tensor, src: int = 0, modules: Iterable[nn.Module] = ()) -> None:
+    """The path's only collective: one ncclBroadcast of the weight arena (a no-op for a single process).  modules: the
+    modules whose parameters live in the arena - their derived caches are invalidated (a warm-up before the broadcast
+    would otherwise leave non-source ranks decoding with pre-broadcast conv weights)."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.broadcast(arena, src=src)
+    invalidate_caches(list(modules))
 
 
 def shard_slice(total: int, rank: int, world: int) -> Tuple[int, int]:

@@ -7,6 +7,13 @@ Differences from the reference, on purpose:
   * :398 indexes ``images[b, 256]`` (a single pixel row) where the pixel-conditioned branch (:354) saves ``images[b, 256:]``
     (the image half under the control map); both branches save the image half here.
   * no wandb branch (``save_val=False`` returns the uint8 arrays to the caller instead), no tqdm.
+  * Gibbs refinement (:380-393).  As written, the reference sets ``args.c_mask = True`` for the first half-step and then
+    ``args.c_img = True`` for the second WITHOUT clearing ``c_mask``; its ``pix_cond_inference`` tests ``c_mask`` first
+    (:314), so the second half-step tokenises the masks again and hands ``c_img=True`` (a bool, not a token list) to
+    ``conditional_infer_cfg``, which then fails at ``c_img[si]`` (control_var.py:317-321) - the loop cannot complete a
+    round in the reference.  Here the second half-step is what the loop evidently intends: ``(c_mask=None, c_img=True)``,
+    i.e. the IMAGE tokens are forced and the control map is re-sampled.  Anyone comparing Gibbs output with a patched
+    reference must patch it the same way.  tests/test_validate_cpu.py pins this behaviour, not reference parity.
 """
 from __future__ import annotations
 

@@ -176,13 +176,18 @@ class VQVAE(nn.Module):
                            self._buf(name + ".lo", (numel,), torch.float16)[:n].view(shape))
 
     def _buf(self, name: str, shape, dtype=torch.float32) -> torch.Tensor:
+        """Named workspace, grown to the largest size ever asked for (one allocation per name, not one per shape: a new
+        batch size re-uses or replaces the buffer instead of adding to it)."""
         dev = self._w("post_quant_conv.weight").device
-        key = (name, tuple(shape), dtype)
+        key = (name, dtype)
+        n = 1
+        for s_ in shape:
+            n *= int(s_)
         t = self._ws.get(key)
-        if t is None or t.device != dev:
-            t = torch.empty(shape, device=dev, dtype=dtype)
+        if t is None or t.device != dev or t.numel() < n:
+            t = torch.empty(max(n, 1), device=dev, dtype=dtype)
             self._ws[key] = t
-        return t
+        return t[:n].view(tuple(shape))
 
     def release_workspace(self):
         self._ws.clear()
@@ -244,8 +249,9 @@ class VQVAE(nn.Module):
         return out
 
     def _decode_nhwc(self, z_nhwc: torch.Tensor, B: int, hw: int, img_out: torch.Tensor, rows_total: int,
-                     row_offset: int, out_mode: int = 1) -> None:
-        """post_quant_conv + Decoder.forward + clamp + (x+1)/2, image planes written into img_out (NCHW)."""
+                     row_offset: int, out_mode: int = 1, out_samples: int = 0) -> None:
+        """post_quant_conv + Decoder.forward + clamp + (x+1)/2, image planes written into img_out (NCHW).
+        out_samples > 0: the B maps are stacked groups of out_samples (cvar_conv_args.out_samples)."""
         cfg = self.cfg
         H = W = hw
         zq = self._buf("z_pq", (B, H, W, cfg.Cvae))
@@ -278,7 +284,8 @@ class VQVAE(nn.Module):
                 cur = out
             elif op == "out":
                 self._conv(self._norm_act(cur, "decoder.norm_out", B, H, W, cin, 0), "decoder.conv_out", img_out, B, H, W,
-                           cin, 3, 3, out_mode=out_mode, out_rows_total=rows_total, row_offset=row_offset)
+                           cin, 3, 3, out_mode=out_mode, out_rows_total=rows_total, row_offset=row_offset,
+                           out_samples=out_samples)
             else:
                 raise AssertionError(op)
 
@@ -307,6 +314,24 @@ class VQVAE(nn.Module):
             out = torch.empty(B, 3, side, side, device=f_hat.device, dtype=torch.float32)
             rows_total, row_offset = side, 0
         self._decode_nhwc(z, B, h, out, rows_total, row_offset, out_mode)
+        return out
+
+    @torch.no_grad()
+    def _fhat_halves_to_img(self, f_hat2: torch.Tensor, B: int, out_mode: int = 1) -> torch.Tensor:
+        """control_var.py:563-565 in ONE decoder pass: f_hat2 (>= B, Cvae, 2*hw, hw) holds the control map (rows [0, hw))
+        and the image map (rows [hw, 2hw)) of every sample; both are decoded as one batch of 2B maps (control maps first)
+        and written as (B, 3, 2*side, side), control on top.  Each map is an independent decoder input (GroupNorm is per
+        image), so the pixels equal two fhat_to_img calls; twice the rows per launch, half the launches."""
+        if not f_hat2.is_cuda:
+            raise RuntimeError("controlvar_b200.VQVAE runs on CUDA only (no CPU fallback)")
+        _, Cz, h2, w = f_hat2.shape
+        assert Cz == self.Cvae and h2 == 2 * w and f_hat2.is_contiguous()
+        z = self._buf("z_nhwc", (2 * B, w, w, Cz))
+        ops.nchw_to_nhwc(f_hat2, z[:B], B, Cz, w, w, f_hat2.stride(0))
+        ops.nchw_to_nhwc(f_hat2[:, :, w:, :], z[B:], B, Cz, w, w, f_hat2.stride(0))
+        side = w * self.downsample
+        out = torch.empty(B, 3, 2 * side, side, device=f_hat2.device, dtype=torch.float32)
+        self._decode_nhwc(z, 2 * B, w, out, 2 * side, 0, out_mode, out_samples=B)
         return out
 
     # -------------------------------------------------------------------------------------------- encoder
@@ -425,7 +450,17 @@ class VQVAE(nn.Module):
         assert all(pn * pn == t.shape[1] for pn, t in zip(pns, ms_idx_Bl)), "token maps must be square"
         if not ms_idx_Bl[0].is_cuda:
             raise RuntimeError("controlvar_b200.VQVAE runs on CUDA only (no CPU fallback)")
-        return pns, ms_idx_Bl[0].shape[0], self.cfg.patch_nums[-1]
+        B = ms_idx_Bl[0].shape[0]
+        # the kernels index the codebook with these ids: a bad id must be an error, not an out-of-bounds read
+        bad = None
+        for t in ms_idx_Bl:
+            if t.dim() != 2 or t.shape[0] != B:
+                raise ValueError(f"token maps must all be (B, pn*pn) with the same B, got {tuple(t.shape)}")
+            b = ((t < 0) | (t >= self.vocab_size)).any()
+            bad = b if bad is None else (bad | b)
+        if bool(bad):
+            raise ValueError(f"token ids must be in [0, {self.vocab_size})")
+        return pns, B, self.cfg.patch_nums[-1]
 
     @torch.no_grad()
     def idxBl_to_img(self, ms_idx_Bl: List[torch.Tensor], same_shape: bool, last_one=False):

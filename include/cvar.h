@@ -47,6 +47,12 @@ CVAR_API long long cvar_launch_count(void);
  * Default: 4 (environment variable CVAR_GEMM_ENGINE = 0 | 1 | 3 | 4 overrides it at load).  Returns the previous value. */
 CVAR_API int cvar_set_gemm_engine(int engine);
 CVAR_API int cvar_get_gemm_engine(void);
+/* Epilogue of the 2-CTA tcgen05 kernels (dense layers, QKV, convolutions).  1 (default): every epilogue warp first pulls
+ * its slice of the accumulators out of tensor memory into registers and releases tensor memory, so that its global-memory
+ * work overlaps the next tile's MMAs; 0: tensor memory is held until the tile is stored (the round-1 behaviour, kept for
+ * A/B timing).  Results are bit-identical.  Environment variable CVAR_EPI_OVERLAP = 0 | 1 sets the initial value.
+ * Returns the previous value. */
+CVAR_API int cvar_set_epilogue_overlap(int on);
 /* K-block of the tcgen05 engine: 32 (128-byte swizzle, default) or 16 (64-byte swizzle, deeper pipeline). Returns the
  * previous value. */
 CVAR_API int cvar_set_tc_kblock(int bk);
@@ -258,6 +264,10 @@ typedef struct {
    * added in fp32 (round to nearest) in the output - for the K = 9*640 layers, where one truncating tensor-core
    * accumulation of 360 steps costs too much accuracy.  0 / 1 = one accumulation. out_mode 0 only. */
   int ksplit;
+  /* Image output (out_mode 1..3) of a STACKED batch: when > 0, image n = s * out_samples + b of the B images lands in
+   * sample b of an (out_samples, Cout, out_rows_total, Wout) tensor at rows s * Hout + row_offset.  Decodes the control
+   * and image halves of control_var.py:563-565 in one pass of 2 x out_samples images.  0: image n is sample n. */
+  int out_samples;
 } cvar_conv_args;
 CVAR_API int cvar_conv2d(const cvar_conv_args* args, void* stream);
 /* 1 when the FP16-pair kernel takes this layer: ks in {1,3}, Cin % 32 == 0, Cout a multiple of one of

@@ -90,9 +90,22 @@ def test_sampler_vs_oracle_fresh_inputs(engine):
         if neq.any():
             assert (margin[neq] < 1e-4).all(), f"scale {si}: a clear-margin token differs"
             diverged = True
-            break
+            break          # the free-running trajectories part here; the scales after it are checked teacher-forced below
     if not diverged:
         assert (img.cpu() - ref["img"]).abs().max().item() < PIXEL_TOL
+    # Teacher-forced onto the oracle's tokens: EVERY clear-margin token of EVERY scale must match, also after an
+    # ambiguous flip (a free-running comparison says nothing about the scales behind the first flip).
+    var.debug_forced_idx = ref["idx"]
+    img_tf = var.autoregressive_infer_cfg(B, label, g_seed=seed, cfg=1.5, top_k=900, top_p=0.96, cond_type=cond)
+    var.debug_forced_idx = None
+    checked = 0
+    for si, (a, b) in enumerate(zip(ref["idx"], var.last_idx)):
+        margin = O.sampling_margin(trace["logits_masked"][si], trace["q"][si]).view(a.shape)
+        clear = margin >= 1e-4
+        assert torch.equal(a[clear], b.cpu()[clear]), f"teacher-forced scale {si}: a clear-margin token differs"
+        checked += int(clear.sum())
+    assert checked > 0.99 * sum(a.numel() for a in ref["idx"])
+    assert (img_tf.cpu() - ref["img"]).abs().max().item() < PIXEL_TOL
 
 
 def test_int_and_none_arguments():

@@ -9,9 +9,10 @@ transformer loop, CFG + top-k/top-p sampling, VQ steps and BOTH decoder passes (
   e2e    - same call through the public API with HOST buffers: pinned-host -> device copy of labels / condition types and
            device -> host copy of the (B,3,512,256) fp32 images inside the timed region;
   roofline - dominant kernel class of the step (CUDA events around every launch of that class, same timed region);
-  cpu_baseline - the CPU oracle port (oracle/controlvar_oracle.py; the reference is a Python package and does not
-           exist on the GPU box) timed on this box's host cores on a bounded sample of the same workload.
---impl reference times that CPU port alone (the reference's own fp32 PyTorch path, restated) on all host threads.
+  cpu_baseline - the UNMODIFIED reference package (staged under oracle/_ref by oracle/make_ref.py; kind "reference") run on
+           this box's host cores with CUDA hidden, on a bounded sample of the same workload (a child process);
+           the oracle port (kind "port") only when oracle/_ref is absent.
+--impl reference times that CPU arm alone on all host threads (8 images per step, up to 2 warm-up steps).
 Multi-GPU: one process per GPU (torchrun), batch sharded with B per GPU fixed (weak scaling), ONE NCCL broadcast of
 the weight arena before timing, no collective inside the sampling loop; time = max over ranks.
 """
@@ -109,35 +110,55 @@ def work_per_image(depth):
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
-def run_cpu_port(depth, B_sample, cond, cfg_scale, steps, warmup, threads=None):
-    """Times the CPU oracle port (fp32 PyTorch ops == what the reference executes on CPU) on B_sample images."""
+def _ref_staged():
+    return os.path.isfile(os.path.join(ROOT, "oracle", "_ref", "models", "control_var.py"))
+
+
+def run_cpu_reference(depth, B_sample, cond, cfg_scale, steps, warmup, threads=None):
+    """Times the reference's own CPU implementation of the path on B_sample images per step, all host threads.
+    kind "reference": the UNMODIFIED reference package staged under oracle/_ref by oracle/make_ref.py
+    (ControlVAR.autoregressive_infer_cfg, models/control_var.py:356-565, fp32, CUDA hidden);
+    kind "port": the oracle restatement (only when oracle/_ref is absent).  -> (times, threads, kind)"""
+    # dist.py:11 binds the reference's device string to 'cuda' whenever a GPU is visible (its generator and helper tensors
+    # follow it): the CPU arm must not see the GPU.  Effective because torch has not been imported in this process yet.
+    os.environ["CUDA_VISIBLE_DEVICES"] = ""
     import torch
+    assert not torch.cuda.is_available(), "the CPU reference arm must run in a process that has not initialised CUDA"
     from controlvar_b200.config import PathConfig
     from controlvar_b200 import weights as W
-    from oracle import controlvar_oracle as O
     # all host cores, explicitly: torchrun exports OMP_NUM_THREADS=1, which would silently make the reference arm
     # single-threaded (and ~16x slower) in every N > 1 launch                                   BASELINE.md section 5
     torch.set_num_threads(threads or os.cpu_count())
     cfgp = PathConfig(depth=depth)
-    dev = "cuda" if torch.cuda.is_available() else None       # weight generation only (bit-identical on any device)
-    sd = {k: v.cpu() for k, v in W.synthetic_var_state_dict(cfgp, 0, device=dev).items()}
-    vsd = {k: v.cpu() for k, v in W.synthetic_vae_state_dict(cfgp, 0, with_encoder=False, device=dev).items()}
+    sd = W.synthetic_var_state_dict(cfgp, 0)
+    vsd = W.synthetic_vae_state_dict(cfgp, 0, with_encoder=False)
     label = torch.arange(B_sample) % 1000
     ct = torch.full((B_sample,), cond)
-    # page in MKL / oneDNN / the thread pool on a tiny problem so the first timed step is not a cold start
-    tiny = PathConfig(depth=2, patch_nums=(1, 2))
-    O.autoregressive_infer_cfg(W.synthetic_var_state_dict(tiny, 0), W.synthetic_vae_state_dict(tiny, 0, False),
-                               tiny.patch_nums, 2, 1, label[:1], ct[:1], cfg_scale, TOP_K, TOP_P,
-                               O.cpu_generator_noise(0), decode=True)
+    if _ref_staged():
+        from oracle import make_ref as R
+        kind = "reference"
+        _, var = R.build_reference(depth, "cpu", sd, vsd)
+        del sd, vsd
+
+        def call(it, B=B_sample):
+            with torch.no_grad():
+                return var.autoregressive_infer_cfg(B, label[:B], g_seed=it, cfg=cfg_scale, top_k=TOP_K, top_p=TOP_P,
+                                                    cond_type=ct[:B])
+    else:
+        from oracle import controlvar_oracle as O
+        kind = "port"
+
+        def call(it, B=B_sample):
+            return O.autoregressive_infer_cfg(sd, vsd, cfgp.patch_nums, depth, B, label[:B], ct[:B], cfg_scale, TOP_K, TOP_P,
+                                              O.cpu_generator_noise(it), decode=True)
     times = []
     for it in range(warmup + steps):
         t0 = time.perf_counter()
-        O.autoregressive_infer_cfg(sd, vsd, cfgp.patch_nums, depth, B_sample, label, ct, cfg_scale, TOP_K, TOP_P,
-                                   O.cpu_generator_noise(it), decode=True)
+        call(it)
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
-    return times, torch.get_num_threads()
+    return times, torch.get_num_threads(), kind
 
 
 def main_reference(args, wl):
@@ -145,18 +166,41 @@ def main_reference(args, wl):
     if rank != 0:
         return
     B_s = args.cpu_sample_batch
-    times, cores = run_cpu_port(wl["depth"], B_s, wl["cond"], wl["cfg"], args.steps, min(args.warmup, 1))
+    warm = min(args.warmup, 2)
+    times, cores, kind = run_cpu_reference(wl["depth"], B_s, wl["cond"], wl["cfg"], args.steps, warm)
     ms = 1e3 * sum(times) / len(times)
     v = B_s / (ms / 1e3)
-    sample = f"{B_s} image(s) per step of the same workload ({wl['desc']}); " + CPU_BATCH_NOTE
-    line = {"impl": "reference", "metric": "images/sec (256x256, d24, CFG=1.5)" if wl["depth"] == 24 else f"images/sec (256x256, d{wl['depth']}, CFG=1.5)",
-            "value": v, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1),
+    what = ("the UNMODIFIED reference (oracle/_ref, staged by oracle/make_ref.py): ControlVAR.autoregressive_infer_cfg, fp32, "
+            "CUDA hidden" if kind == "reference" else "the oracle port (oracle/_ref not staged)")
+    sample = f"{B_s} image(s) per step of the same workload ({wl['desc']}), {warm} warm-up step(s); {what}; " + CPU_BATCH_NOTE
+    line = {"impl": "reference", "metric": f"images/sec (256x256, d{wl['depth']}, CFG=1.5)",
+            "value": v, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": warm,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": {"workload": args.workload, "desc": wl["desc"], "top_k": TOP_K, "top_p": TOP_P},
-            "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+            "data": "synthetic", "config": {"workload": args.workload, "desc": wl["desc"], "top_k": TOP_K, "top_p": TOP_P,
+                                            "images_per_step": B_s},
+            "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_subprocess(args):
+    """The cpu_baseline leg of our arm: the reference arm above in a CHILD process (this one has CUDA initialised; the
+    reference must not see the GPU), one step on the bounded sample.  -> the child's cpu_baseline object."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "0",
+           "--workload", args.workload, "--cpu-sample-batch", str(args.cpu_sample_batch)]
+    env = dict(os.environ)
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "OMP_NUM_THREADS"):
+        env.pop(k, None)
+    env["CUDA_VISIBLE_DEVICES"] = ""
+    try:
+        out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
+        for ln in reversed(out.stdout.strip().splitlines()):
+            if ln.startswith("{"):
+                return json.loads(ln)["cpu_baseline"]
+        return {"error": "no JSON line from the reference arm", "stderr": out.stderr[-400:]}
+    except Exception as e:   # noqa: BLE001
+        return {"error": repr(e)}
 
 
 # ----------------------------------------------------------------------------------------------------- our arm
@@ -292,10 +336,8 @@ def main_ours(args, wl):
                 e["frac_of_hbm"] = e["algorithmic_gbs"] / pk["hbm"]
             kernels[k] = e
         cpu = None
-        if not args.no_cpu_baseline:
-            times, cores = run_cpu_port(depth, args.cpu_sample_batch, wl["cond"], wl["cfg"], 1, 0)
-            cpu = {"value": args.cpu_sample_batch / times[0], "unit": "images/s", "cores": cores, "kind": "port",
-                   "sample": f"{args.cpu_sample_batch} image(s), one call of the same workload on the host cores; " + CPU_BATCH_NOTE}
+        if not args.no_cpu_baseline and world == 1:
+            cpu = cpu_baseline_subprocess(args)
         engine_name = {0: "simt-fp32", 1: "tcgen05-3xtf32 (1 CTA per tile)",
                        3: "tcgen05-3xtf32 (2-CTA all-TMA dense layers, 1-CTA convs)",
                        4: "tcgen05 f16x3 (FP16 pairs): 2-CTA all-TMA dense layers and decoder convs (K-split for the long "

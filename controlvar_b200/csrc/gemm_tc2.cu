@@ -133,34 +133,23 @@ __device__ __forceinline__ void tile_coords(int tile, int m_tiles, int n_tiles, 
 // ------------------------------------------------------------------------------------------------ epilogue of one tile
 // Each epilogue warp owns 32 accumulator rows (its TMEM lane quarter) and `ncols` (multiple of 16, <= 128) columns
 // starting at `col0`.  The accumulators fill all 512 TMEM columns (main + cross), so the next tile's MMAs cannot start
-// until this tile has left tensor memory.  kOverlap: the warp first pulls its whole slice into REGISTERS (main and cross
-// folded: fma(cross, 2^-11, main), the same operation as before), releases tensor memory, and only then runs the slow
-// part - shared-memory transposes, residual / gamma loads, GELU, pair split, global stores - which therefore overlaps the
-// next tile's main loop.  Exposed per tile: ~16 tcgen05.ld per warp instead of the whole epilogue (round 1 measured a tile
-// of fc1 at ~68k cycles against 37k cycles of MMA).  Values and their order of evaluation are unchanged: bit-identical.
-// direct-store hook: an epilogue may take a 16-column chunk straight from the accumulator layout (lane = row); the
-// QKV epilogue does for V^T, whose contiguous index is the token (= the lane), instead of scattering 2-byte stores.
-template <class EP>
-__device__ __forceinline__ bool epi_chunk_direct(const EP&, long long, int, const float*, long long, int) { return false; }
-__device__ __forceinline__ bool epi_chunk_direct(const QkvEpilogue& e, long long m, int n0, const float* a, long long M, int N) {
-  if (e.q16_hi == nullptr || n0 < 2 * e.C) return false;      // warp-uniform: C is a multiple of 16
-  if (m >= M || n0 >= N) return true;
-  const int c0 = n0 - 2 * e.C;
-  const int r = (int)(m / e.l), t = (int)(m - (long long)r * e.l);
-  const int h = c0 >> 6, d0 = c0 & 63;                         // a 16-column chunk stays inside one head
-  const long long off = (((long long)r * e.H + h) * 64 + d0) * e.T_max + e.L_prev + t;
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const float o = __fadd_rn(a[i], e.v_bias[c0 + i]);
-    split_f16(o, e.vt16_hi[off + (long long)i * e.T_max], e.vt16_lo[off + (long long)i * e.T_max]);
-  }
-  return true;
-}
-
+// until this tile has left tensor memory.
+//
+// Round 1 held tensor memory for the whole epilogue.  The tile trace (tools/gemm_ab.py, profiles/r02_gemm_epilogue.md)
+// showed what that costs: the main loop of a K = 1536 tile runs at the full MMA rate (35.3k cycles for 24 K-blocks)
+// and is then followed by 27-30k cycles of epilogue with the tensor core idle - NOT the operand-ingest limit round 1
+// blamed.  Two epilogues now exist:
+//   * "staged" (round 1; TF32 operands, ragged shapes): 16-column chunks, transposed through shared memory.
+//   * "row" (FP16-pair operands, N % 16 == 0, 32-byte aligned outputs): the thread pulls its row slice into REGISTERS
+//     (main and cross folded: fma(cross, 2^-11, main), as before), releases tensor memory, and then streams along its own
+//     output row with 32-byte global accesses - no shared memory (the MMAs read operands from it at ~100 B/clk while the
+//     epilogue runs), the epilogue kind a compile-time parameter (the first overlapped version, a fully unrolled copy of
+//     the staged epilogue with run-time modes, was 400 KB of SASS and ran at the speed of the instruction cache: 74k
+//     cycles per tile).  Values and the order of every floating-point operation are those of the staged epilogue:
+//     results are bit-identical (tools/gemm_ab.py checks).
 template <class EP>
 __device__ __forceinline__ void epi_chunk(const EP& ep, const float* a16, float* stage, int lane, long long m_base, int n0,
                                           long long M, int N) {
-  if (epi_chunk_direct(ep, m_base + lane, n0, a16, M, N)) return;
 #pragma unroll
   for (int q = 0; q < kEpiCols / 4; ++q)
     *reinterpret_cast<float4*>(stage + lane * kStagePitch + q * 4) =
@@ -184,51 +173,250 @@ __device__ __forceinline__ void epi_chunk(const EP& ep, const float* a16, float*
   __syncwarp();
 }
 
-template <class EP, bool kOverlap, bool kCross>
-__device__ __forceinline__ void epilogue_tile(const EP& ep, uint32_t tcol, int col0, int ncols, float lo_scale,
-                                              long long m_base, int n_base, long long M, int N, float* stage, int lane,
-                                              uint64_t* tm_empty, int trace_tile) {
+template <class EP>
+__device__ __forceinline__ void epilogue_tile_staged(const EP& ep, uint32_t tcol, int col0, int ncols, float lo_scale,
+                                                     long long m_base, int n_base, long long M, int N, float* stage,
+                                                     int lane, uint64_t* tm_empty, int trace_tile) {
   constexpr int kAccStride = 256;
-  if (kOverlap) {
-    float acc[128];
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      if (c * kEpiCols < ncols) {
-        float v[kEpiCols], w[kEpiCols];
-        tmem_ld16_nowait(tcol + (uint32_t)(col0 + c * kEpiCols), v);
-        if (kCross) tmem_ld16_nowait(tcol + (uint32_t)(kAccStride + col0 + c * kEpiCols), w);
-        tmem_ld_wait();
-        reg_fence_16(v);
-        if (kCross) reg_fence_16(w);
-#pragma unroll
-        for (int i = 0; i < kEpiCols; ++i) acc[c * kEpiCols + i] = kCross ? fmaf(w[i], lo_scale, v[i]) : v[i];
-      }
-    }
-    tc_fence_before();
-    mbar_arrive_leader(tm_empty);                       // tensor memory is free: the next tile's MMAs may start
-    if (threadIdx.x == 0) trace2(trace_tile, 3);
-#pragma unroll
-    for (int c = 0; c < 8; ++c)
-      if (c * kEpiCols < ncols) epi_chunk(ep, &acc[c * kEpiCols], stage, lane, m_base, n_base + col0 + c * kEpiCols, M, N);
-  } else {
 #pragma unroll 1
-    for (int c = 0; c < ncols; c += kEpiCols) {
-      float v[kEpiCols], w[kEpiCols];
-      tmem_ld_32x32b_x16(tcol + (uint32_t)(col0 + c), v);
-      if (kCross) {
-        tmem_ld_32x32b_x16(tcol + (uint32_t)(kAccStride + col0 + c), w);
+  for (int c = 0; c < ncols; c += kEpiCols) {
+    float v[kEpiCols], w[kEpiCols];
+    tmem_ld_32x32b_x16(tcol + (uint32_t)(col0 + c), v);
+    tmem_ld_32x32b_x16(tcol + (uint32_t)(kAccStride + col0 + c), w);
 #pragma unroll
-        for (int i = 0; i < kEpiCols; ++i) v[i] = fmaf(w[i], lo_scale, v[i]);
-      }
-      epi_chunk(ep, v, stage, lane, m_base, n_base + col0 + c, M, N);
+    for (int i = 0; i < kEpiCols; ++i) v[i] = fmaf(w[i], lo_scale, v[i]);
+    epi_chunk(ep, v, stage, lane, m_base, n_base + col0 + c, M, N);
+  }
+  tc_fence_before();
+  mbar_arrive_leader(tm_empty);
+  if (threadIdx.x == 0) trace2(trace_tile, 3);
+}
+
+// ---- 32-byte global accesses (LDG / STG .256, sm_100): one full sector per thread and instruction
+__device__ __forceinline__ void ld8(const float* p, float* v) {
+  asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void st8(float* p, const float* v) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+               "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void st8_b32(void* p, const uint32_t* v) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+               "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void ld16f(const float* p, float* v) {
+  ld8(p, v);
+  ld8(p + 8, v + 8);
+}
+__device__ __forceinline__ void st16f(float* p, const float* v) {
+  st8(p, v);
+  st8(p + 8, v + 8);
+}
+// 16 consecutive values -> 32-byte stores of the hi and lo halves (standard pair; bit-identical to split_f16 per element)
+__device__ __forceinline__ void st16_split_f16(__half* hi, __half* lo, const float* r) {
+  uint32_t ph[8], pl[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float c0 = fminf(fmaxf(r[2 * j], -65504.0f), 65504.0f), c1 = fminf(fmaxf(r[2 * j + 1], -65504.0f), 65504.0f);
+    const __half2 h = __floats2half2_rn(c0, c1);
+    const float2 f = __half22float2(h);
+    const __half2 l = __floats2half2_rn((c0 - f.x) * kF16LoScale, (c1 - f.y) * kF16LoScale);
+    ph[j] = *reinterpret_cast<const uint32_t*>(&h);
+    pl[j] = *reinterpret_cast<const uint32_t*>(&l);
+  }
+  st8_b32(hi, ph);
+  st8_b32(lo, pl);
+}
+// the same for qk pairs (16 x = hi + lo, residual not scaled; bit-identical to split_f16_qk per element)
+__device__ __forceinline__ void st16_split_f16_qk(__half* hi, __half* lo, const float* r) {
+  uint32_t ph[8], pl[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float c0 = fminf(fmaxf(r[2 * j] * kQkScale, -65504.0f), 65504.0f);
+    const float c1 = fminf(fmaxf(r[2 * j + 1] * kQkScale, -65504.0f), 65504.0f);
+    const __half2 h = __floats2half2_rn(c0, c1);
+    const float2 f = __half22float2(h);
+    const __half2 l = __floats2half2_rn(c0 - f.x, c1 - f.y);
+    ph[j] = *reinterpret_cast<const uint32_t*>(&h);
+    pl[j] = *reinterpret_cast<const uint32_t*>(&l);
+  }
+  st8_b32(hi, ph);
+  st8_b32(lo, pl);
+}
+
+// ---- row epilogues: begin(m) once per tile and thread, row16(ctx, n, v) per 16-column chunk (n % 16 == 0, n + 16 <= N)
+template <int MODE>
+struct DenseRow {
+  DenseEpilogue e;
+  struct Ctx {
+    long long off;
+    const float* g;
+    const float* rs;
+  };
+  __device__ __forceinline__ Ctx begin(long long m) const {
+    Ctx c;
+    c.off = m * e.ldo;
+    c.g = (MODE == CVAR_EPI_BIAS_GAMMA_RESID) ? e.gamma + (m / e.rows_per_sample) * e.gamma_row_stride : nullptr;
+    c.rs = (MODE == CVAR_EPI_BIAS_RESID) ? e.resid + m * e.ldr : nullptr;
+    return c;
+  }
+  __device__ __forceinline__ void row16(const Ctx& c, int n, const float* v) const {
+    float r[16], b[16];
+    if (e.bias != nullptr) {
+      ld16f(e.bias + n, b);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) b[j] = 0.f;
     }
-    tc_fence_before();
-    mbar_arrive_leader(tm_empty);
-    if (threadIdx.x == 0) trace2(trace_tile, 3);
+    if (MODE == CVAR_EPI_BIAS_GAMMA_RESID) {
+      float x[16], g[16];
+      ld16f(e.out + c.off + n, x);
+      ld16f(c.g + n, g);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) r[j] = __fadd_rn(x[j], __fmul_rn(__fadd_rn(v[j], b[j]), g[j]));   // x + branch.mul(gamma)
+    } else if (MODE == CVAR_EPI_BIAS_RESID) {
+      float x[16];
+      ld16f(c.rs + n, x);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) r[j] = __fadd_rn(x[j], __fadd_rn(v[j], b[j]));                   // shortcut + h
+    } else if (MODE == CVAR_EPI_BIAS_GELU) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) r[j] = gelu_tanh_fast(__fadd_rn(v[j], b[j]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) r[j] = __fadd_rn(__fmul_rn(v[j], e.alpha), b[j]);
+    }
+    if (e.out16_hi != nullptr) {
+      st16_split_f16(e.out16_hi + c.off + n, e.out16_lo + c.off + n, r);
+      if (e.out == nullptr) return;
+    }
+    st16f(e.out + c.off + n, r);
+  }
+};
+
+struct QkvRow {     // FP16-pair outputs only (cvar_qkv_project16)
+  QkvEpilogue e;
+  struct Ctx {
+    int r, t;
+  };
+  __device__ __forceinline__ Ctx begin(long long m) const {
+    Ctx c;
+    c.r = (int)(m / e.l);
+    c.t = (int)(m - (long long)c.r * e.l);
+    return c;
+  }
+  __device__ __forceinline__ void row16(const Ctx& c, int n, const float* v) const {
+    const int which = n / e.C;                 // a 16-column chunk stays inside one of q / k / v and inside one head
+    const int cc = n - which * e.C;
+    const int h = cc >> 6, d = cc & 63;
+    const float* bias = which == 0 ? e.q_bias : (which == 1 ? e.k_bias : e.v_bias);
+    float o[16], b[16];
+    ld16f(bias + cc, b);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) o[j] = __fadd_rn(v[j], b[j]);
+    const long long rh = (long long)c.r * e.H + h;
+    if (which == 0) {
+      const long long off = ((rh * e.l + c.t) << 6) + d;
+      st16_split_f16_qk(e.q16_hi + off, e.q16_lo + off, o);
+    } else if (which == 1) {
+      const long long off = ((rh * e.T_max + e.L_prev + c.t) << 6) + d;
+      st16_split_f16_qk(e.k16_hi + off, e.k16_lo + off, o);
+    } else {
+      // V^T: the contiguous index is the token = this thread's row, so the warp's 32 rows write 64 contiguous bytes per
+      // head dim (round 1 scattered 2-byte stores from a transposed layout)
+      const long long off = (rh * 64 + d) * e.T_max + e.L_prev + c.t;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) split_f16(o[j], e.vt16_hi[off + (long long)j * e.T_max], e.vt16_lo[off + (long long)j * e.T_max]);
+    }
+  }
+};
+
+struct ConvRow {    // out_mode 0 (NHWC fp32): bias + optional residual, or the K-split continuation out += acc
+  ConvEpilogue e;
+  struct Ctx {
+    long long off;
+  };
+  __device__ __forceinline__ Ctx begin(long long m) const {
+    Ctx c;
+    c.off = m * e.Cout;
+    return c;
+  }
+  __device__ __forceinline__ void row16(const Ctx& c, int n, const float* v) const {
+    float r[16], x[16];
+    if (e.accumulate) {
+      ld16f(e.out + c.off + n, x);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) r[j] = __fadd_rn(x[j], v[j]);
+    } else {
+      ld16f(e.bias + n, x);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) r[j] = __fadd_rn(v[j], x[j]);
+      if (e.resid != nullptr) {
+        ld16f(e.resid + c.off + n, x);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) r[j] = __fadd_rn(x[j], r[j]);
+      }
+    }
+    st16f(e.out + c.off + n, r);
+  }
+};
+
+template <class EP> struct IsRowEpilogue { static constexpr bool value = false; };
+template <int MODE> struct IsRowEpilogue<DenseRow<MODE>> { static constexpr bool value = true; };
+template <> struct IsRowEpilogue<QkvRow> { static constexpr bool value = true; };
+template <> struct IsRowEpilogue<ConvRow> { static constexpr bool value = true; };
+
+template <class ROW>
+__device__ __forceinline__ void epilogue_tile_rows(const ROW& ep, uint32_t tcol, int col0, int ncols, float lo_scale,
+                                                   long long m, long long M, int n_base, int N, uint64_t* tm_empty,
+                                                   int trace_tile) {
+  constexpr int kAccStride = 256;
+  float acc[128];
+  // drain: main chunks land in their final registers, the cross chunk in a 16-register temporary; the next main chunk
+  // is in flight while this one is folded
+  tmem_ld16_nowait(tcol + (uint32_t)col0, &acc[0]);
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    if (c * kEpiCols < ncols) {
+      float w[kEpiCols];
+      tmem_ld16_nowait(tcol + (uint32_t)(kAccStride + col0 + c * kEpiCols), w);
+      if ((c + 1) * kEpiCols < ncols && c + 1 < 8)
+        tmem_ld16_nowait(tcol + (uint32_t)(col0 + (c + 1) * kEpiCols), &acc[(c + 1 < 8 ? c + 1 : 0) * kEpiCols]);
+      tmem_ld_wait();
+      reg_fence_16(&acc[c * kEpiCols]);
+      reg_fence_16(w);
+      if ((c + 1) * kEpiCols < ncols && c + 1 < 8) reg_fence_16(&acc[(c + 1 < 8 ? c + 1 : 0) * kEpiCols]);
+#pragma unroll
+      for (int i = 0; i < kEpiCols; ++i) acc[c * kEpiCols + i] = fmaf(w[i], lo_scale, acc[c * kEpiCols + i]);
+    }
+  }
+  tc_fence_before();
+  mbar_arrive_leader(tm_empty);                         // tensor memory is free: the next tile's MMAs may start
+  if (threadIdx.x == 0) trace2(trace_tile, 3);
+  if (m >= M) return;                                   // plain loads / stores below: no warp-collective operation
+  const typename ROW::Ctx ctx = ep.begin(m);
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const int n = n_base + col0 + c * kEpiCols;
+    if (c * kEpiCols < ncols && n < N) ep.row16(ctx, n, &acc[c * kEpiCols]);
   }
 }
 
-template <class EP, bool F16, bool kOverlap>
+template <class EP>
+__device__ __forceinline__ void epilogue_tile(const EP& ep, uint32_t tcol, int col0, int ncols, float lo_scale,
+                                              long long m_base, int n_base, long long M, int N, float* stage, int lane,
+                                              uint64_t* tm_empty, int trace_tile) {
+  if constexpr (IsRowEpilogue<EP>::value)
+    epilogue_tile_rows(ep, tcol, col0, ncols, lo_scale, m_base + lane, M, n_base, N, tm_empty, trace_tile);
+  else
+    epilogue_tile_staged(ep, tcol, col0, ncols, lo_scale, m_base, n_base, M, N, stage, lane, tm_empty, trace_tile);
+}
+
+template <class EP, bool F16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 tc_gemm2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
                 const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo, EP ep,
@@ -290,8 +478,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constan
       if (threadIdx.x == 0) trace2(tcount, 2);
       const long long m_base = (long long)mt * 256 + rank * BM + quarter * 32;
       const uint32_t tcol = tmem_base + ((uint32_t)(quarter * 32) << 16);
-      epilogue_tile<EP, kOverlap, true>(ep, tcol, half * (BN / 2), BN / 2, kLoScale, m_base, nt * BN, M, N, stage, lane,
-                                        tm_empty, tcount);
+      epilogue_tile(ep, tcol, half * (BN / 2), BN / 2, kLoScale, m_base, nt * BN, M, N, stage, lane, tm_empty, tcount);
       if (threadIdx.x == 0) trace2(tcount, 4);
     }
   } else if (warp == kTmaWarp) {
@@ -382,7 +569,7 @@ __device__ __forceinline__ void tma_load_4d_2sm(const CUtensorMap* map, uint64_t
       : "memory");
 }
 
-template <class EP, bool kOverlap>
+template <class EP>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 tc_conv2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
                 const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo, EP ep, ConvGeo g,
@@ -442,8 +629,7 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constan
       tc_fence_after();
       const long long m_base = (long long)mt * 256 + rank * BM + quarter * 32;
       const uint32_t tcol = tmem_base + ((uint32_t)(quarter * 32) << 16);
-      epilogue_tile<EP, kOverlap, true>(ep, tcol, half * (BNr / 2), BNr / 2, kLoScale, m_base, nt * BNr, M, N, stage, lane,
-                                        tm_empty, 64);
+      epilogue_tile(ep, tcol, half * (BNr / 2), BNr / 2, kLoScale, m_base, nt * BNr, M, N, stage, lane, tm_empty, 64);
     }
   } else if (warp == kTmaWarp) {
     // ================================================================ TMA: this CTA's 128 pixels (shifted window per tap)
@@ -609,7 +795,7 @@ int launch(const EP& ep, const void* A_hi, const void* A_lo, long long lda, cons
   if (!rc) rc = make_map(&mbh, W_hi, N, K, ldw, F16);
   if (!rc) rc = make_map(&mbl, W_lo, N, K, ldw, F16);
   if (rc) return rc;
-  auto kern = g_epi_overlap ? tc_gemm2_kernel<EP, F16, true> : tc_gemm2_kernel<EP, F16, false>;
+  auto kern = tc_gemm2_kernel<EP, F16>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
   if (e != cudaSuccess) {
     set_error("%s: cannot raise shared memory to %d: %s", name, kSmem, cudaGetErrorString(e));
@@ -623,6 +809,7 @@ int launch(const EP& ep, const void* A_hi, const void* A_lo, long long lda, cons
 }
 
 static bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
+static bool aligned32(const void* p) { return (((uintptr_t)p) & 31) == 0; }     // nullptr counts as aligned
 }  // namespace tc2
 
 int tc2_set_trace(long long* dev_ptr) {
@@ -647,7 +834,27 @@ int tc2_gemm_f16(const cvar_gemm_args* a, cudaStream_t s) {
                a->lda, a->ldw);
   CVAR_REQUIRE(tc2::aligned16(a->A16_hi) && tc2::aligned16(a->A16_lo) && tc2::aligned16(a->W16_hi) && tc2::aligned16(a->W16_lo),
                "cvar_gemm[f16x3]: operands must be 16-byte aligned");
-  return tc2::launch<DenseEpilogue, true>(dense_epilogue(a), a->A16_hi, a->A16_lo, a->lda, a->W16_hi, a->W16_lo, a->ldw,
+  const DenseEpilogue ep = dense_epilogue(a);
+  // row epilogue (tensor memory released before the stores, 32-byte accesses): whole 16-column chunks, 32-byte aligned rows
+  const bool rows = g_epi_overlap && a->N % 16 == 0 && a->out_lo == nullptr && tc2::aligned32(a->out) &&
+                    tc2::aligned32(a->out16_hi) && tc2::aligned32(a->out16_lo) && tc2::aligned32(a->bias) &&
+                    a->ldo % (a->out16_hi != nullptr ? 16 : 8) == 0 &&
+                    (a->epilogue != CVAR_EPI_BIAS_GAMMA_RESID || (tc2::aligned32(a->gamma) && a->gamma_row_stride % 8 == 0)) &&
+                    (a->epilogue != CVAR_EPI_BIAS_RESID || (tc2::aligned32(a->resid) && a->ldr % 8 == 0));
+#define CVAR_TC2_ROWS(MODE)                                                                                              \
+  return tc2::launch<tc2::DenseRow<MODE>, true>(tc2::DenseRow<MODE>{ep}, a->A16_hi, a->A16_lo, a->lda, a->W16_hi,         \
+                                                a->W16_lo, a->ldw, (long long)a->M, a->N, a->K, s, "cvar_gemm[tc2/f16x3/rows]")
+  if (rows) {
+    switch (a->epilogue) {
+      case CVAR_EPI_BIAS: CVAR_TC2_ROWS(CVAR_EPI_BIAS);
+      case CVAR_EPI_BIAS_GELU: CVAR_TC2_ROWS(CVAR_EPI_BIAS_GELU);
+      case CVAR_EPI_BIAS_GAMMA_RESID: CVAR_TC2_ROWS(CVAR_EPI_BIAS_GAMMA_RESID);
+      case CVAR_EPI_BIAS_RESID: CVAR_TC2_ROWS(CVAR_EPI_BIAS_RESID);
+      default: break;
+    }
+  }
+#undef CVAR_TC2_ROWS
+  return tc2::launch<DenseEpilogue, true>(ep, a->A16_hi, a->A16_lo, a->lda, a->W16_hi, a->W16_lo, a->ldw,
                                           (long long)a->M, a->N, a->K, s, "cvar_gemm[tc2/f16x3]");
 }
 
@@ -656,6 +863,12 @@ int tc2_qkv_f16(const void* A_hi, const void* A_lo, const void* W_hi, const void
   CVAR_REQUIRE(A_hi && A_lo && W_hi && W_lo, "cvar_qkv_project[f16x3]: A16_hi/A16_lo/W16_hi/W16_lo must all be set");
   CVAR_REQUIRE(tc2::aligned16(A_hi) && tc2::aligned16(A_lo) && tc2::aligned16(W_hi) && tc2::aligned16(W_lo),
                "cvar_qkv_project[f16x3]: operands must be 16-byte aligned");
+  const bool rows = g_epi_overlap && ep.q16_hi != nullptr && C % 64 == 0 && tc2::aligned32(ep.q16_hi) &&
+                    tc2::aligned32(ep.q16_lo) && tc2::aligned32(ep.k16_hi) && tc2::aligned32(ep.k16_lo) &&
+                    tc2::aligned32(ep.q_bias) && tc2::aligned32(ep.k_bias) && tc2::aligned32(ep.v_bias);
+  if (rows)
+    return tc2::launch<tc2::QkvRow, true>(tc2::QkvRow{ep}, A_hi, A_lo, C, W_hi, W_lo, C, (long long)M, 3 * C, C, s,
+                                          "cvar_qkv_project[tc2/f16x3/rows]");
   return tc2::launch<QkvEpilogue, true>(ep, A_hi, A_lo, C, W_hi, W_lo, C, (long long)M, 3 * C, C, s,
                                         "cvar_qkv_project[tc2/f16x3]");
 }
@@ -699,8 +912,12 @@ int tc2_conv_f16(const cvar_conv_args* a, cudaStream_t s) {
   if (rc) return rc;
   ConvEpilogue ep{a->out, a->bias, a->resid, a->Cout, a->out_mode, H, W, a->out_rows_total, a->row_offset};
   ep.out_samples = a->out_samples;
-  auto kern = g_epi_overlap ? tc2::tc_conv2_kernel<ConvEpilogue, true> : tc2::tc_conv2_kernel<ConvEpilogue, false>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::kCvSmem);
+  const bool rows = g_epi_overlap && a->out_mode == 0 && a->Cout % 16 == 0 && tc2::aligned32(a->out) &&
+                    tc2::aligned32(a->bias) && tc2::aligned32(a->resid) && a->bias != nullptr;
+  auto kern_staged = tc2::tc_conv2_kernel<ConvEpilogue>;
+  auto kern_rows = tc2::tc_conv2_kernel<tc2::ConvRow>;
+  cudaError_t e = rows ? cudaFuncSetAttribute(kern_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::kCvSmem)
+                       : cudaFuncSetAttribute(kern_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::kCvSmem);
   CVAR_REQUIRE(e == cudaSuccess, "cvar_conv2d[f16x3]: cannot raise shared memory to %d: %s", tc2::kCvSmem, cudaGetErrorString(e));
   const long long M = (long long)a->B * H * W;
   const int m_tiles = cdiv(M, 256), n_tiles = a->Cout / g.BN;
@@ -716,7 +933,11 @@ int tc2_conv_f16(const cvar_conv_args* a, cudaStream_t s) {
     g.tap0 = part * g.ntaps;
     ConvEpilogue epp = ep;
     epp.accumulate = part > 0 ? 1 : 0;
-    kern<<<2 * pairs, tc2::kThreads, tc2::kCvSmem, s>>>(mah, mal, mbh, mbl, epp, g, M, a->Cout, m_tiles, n_tiles);
+    if (rows)
+      kern_rows<<<2 * pairs, tc2::kThreads, tc2::kCvSmem, s>>>(mah, mal, mbh, mbl, tc2::ConvRow{epp}, g, M, a->Cout, m_tiles,
+                                                                n_tiles);
+    else
+      kern_staged<<<2 * pairs, tc2::kThreads, tc2::kCvSmem, s>>>(mah, mal, mbh, mbl, epp, g, M, a->Cout, m_tiles, n_tiles);
     CVAR_CHECK_LAUNCH("cvar_conv2d[tc2/f16x3]");
   }
   return 0;

@@ -58,6 +58,9 @@ PROTOTYPES = {
     "cvar_set_gemm_engine": (C.c_int, [C.c_int]),
     "cvar_get_gemm_engine": (C.c_int, []),
     "cvar_set_epilogue_overlap": (C.c_int, [C.c_int]),
+    "cvar_add_launch_count": (C.c_int, [c_ll]),
+    "cvar_set_fast_mode": (C.c_int, [C.c_int]),
+    "cvar_get_fast_mode": (C.c_int, []),
     "cvar_set_tc_kblock": (C.c_int, [C.c_int]),
     "cvar_debug_set_trace": (C.c_int, [C.c_void_p]),
     "cvar_debug_set_attn_trace": (C.c_int, [C.c_void_p]),

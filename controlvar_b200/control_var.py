@@ -24,6 +24,7 @@ Branches no released configuration uses (``separator``, ``type_pos``, ``bidirect
 from __future__ import annotations
 
 import math
+import os
 import random
 import struct
 from typing import Dict, List, Optional, Tuple, Union
@@ -103,6 +104,15 @@ class ControlVAR(nn.Module):
         self.kv16 = True
         self._rng: Optional[torch.Generator] = None
         self._ws: Dict[Tuple, torch.Tensor] = {}
+        # CUDA graphs: the launch sequence of one sampling call (~2100 launches at d24) is
+        # static per (batch, guidance schedule, top-k / top-p, engine), so the second call with the same key is captured
+        # and later calls replay it: one graph launch instead of ~2100 ctypes launches from a Python loop, which matters
+        # where kernels are shorter than a launch (the five small scales, small batches, 8 ranks sharing one host).
+        # Inputs of a replay: labels / condition types / forced tokens (copied into static buffers) and the Exp(1) noise,
+        # drawn from the caller's generator BEFORE the replay in the same order as the eager path (bit-identical tokens).
+        self.use_graphs = os.environ.get("CVAR_GRAPHS", "1") != "0"
+        self._graphs: Dict[Tuple, dict] = {}
+        self._ws_gen = 0                                  # bumped whenever a workspace is (re)allocated: graphs hold pointers
         self._consts: Dict[str, object] = {}
         self.last_idx: List[torch.Tensor] = []           # tokens of the last call, per scale (diagnostics / tests)
         # Parity instruments (tests only; SURVEY.md section 7.2 "margin-aware + teacher-forced"):
@@ -119,11 +129,13 @@ class ControlVAR(nn.Module):
 
     # ------------------------------------------------------------------------------------------ plumbing
     def _apply(self, fn, recurse=True):
+        self._graphs.clear()
         self._ws.clear()
         self._consts.clear()
         return super()._apply(fn, recurse)
 
     def load_state_dict(self, state_dict, strict=True, assign=False):
+        self._graphs.clear()         # derived operand-form weights are rebuilt: captured pointers go stale
         self._consts.clear()
         return super().load_state_dict(state_dict, strict=strict, assign=assign)
 
@@ -140,6 +152,7 @@ class ControlVAR(nn.Module):
         if t is None or t.numel() < n or t.device != self.device:
             t = torch.empty(n, device=self.device, dtype=dtype)
             self._ws[key] = t
+            self._ws_gen += 1
         return t[:n].view(shape)
 
     def _pair(self, name: str, shape) -> "ops.F16Pair":
@@ -156,6 +169,7 @@ class ControlVAR(nn.Module):
             arena = torch.zeros(depth * n, dtype=torch.float32, device=self.device)
             c = [ops.KVCache(R, H, T, self.device, arena[i * n:(i + 1) * n]) for i in range(depth)]
             self._ws[key] = c
+            self._ws_gen += 1
         return c
 
     def _kv_caches16(self, depth, R, H, T):
@@ -169,11 +183,14 @@ class ControlVAR(nn.Module):
             arena = torch.zeros(depth * n, dtype=torch.float16, device=self.device)
             c = [ops.KVCache16(R, H, T, self.device, arena[i * n:(i + 1) * n]) for i in range(depth)]
             self._ws[key] = c
+            self._ws_gen += 1
         return c
 
     def release_workspace(self):
         """Free the KV arena and activation scratch (they are cached across calls)."""
+        self._graphs.clear()
         self._ws.clear()
+        self._ws_gen += 1
         self.vae_proxy[0].release_workspace()
 
     def _generator(self, seed: Optional[int]) -> Optional[torch.Generator]:
@@ -347,9 +364,83 @@ class ControlVAR(nn.Module):
     # ------------------------------------------------------------------------------------ the shared scale loop
     def _sample(self, B: int, label_R: torch.Tensor, cond_R: torch.Tensor, *, groups: int, mix, replicas: int, top_k, top_p,
                 rng, c_mask=None, c_img=None) -> torch.Tensor:
+        """Eager launch sequence, or capture / replay of it as a CUDA graph (see __init__).  Eager whenever a debug hook or
+        the per-kernel profiler is active (both put host logic between launches)."""
+        SN = len(self.patch_nums)
+        ts_all = tuple(tuple(float(t) for t in mix(si / self.num_stages_minus_1)) for si in range(SN))
+        Bf, V, lens = B * replicas, self.V, self.cfg.scale_lens
+        graphable = (self.use_graphs and self.debug_forced_idx is None and not self.debug_capture_logits
+                     and self.debug_noise_fn is None and not ops.profiling())
+        if not graphable:
+            return self._sample_body(B, label_R, cond_R, groups, ts_all, replicas, top_k, top_p,
+                                     lambda si, rows: self._noise_for_scale(si, rows, rng), c_mask, c_img)
+        vae = self.vae_proxy[0]
+        key = (B, groups, replicas, int(top_k), float(top_p), ts_all, c_mask is not None, c_img is not None,
+               ops.get_gemm_engine(), ops.get_fast_mode(), self.kv16, self.rng_device, vae.tc_min_hw, vae.ksplit_min_k)
+        ent = self._graphs.get(key)
+        gens = (self._ws_gen, vae._ws_gen)
+        if ent is not None and ent["gens"] != gens:        # a workspace moved since: the captured pointers are stale
+            ent = None
+            self._graphs.pop(key, None)
+        if ent is None:
+            # first call with this key: eager (it also allocates every workspace the capture will use)
+            img = self._sample_body(B, label_R, cond_R, groups, ts_all, replicas, top_k, top_p,
+                                    lambda si, rows: self._noise_for_scale(si, rows, rng), c_mask, c_img)
+            self._graphs[key] = dict(graph=None, gens=(self._ws_gen, vae._ws_gen))
+            return img
+        dev = self.device
+        # ---- static inputs
+        rows_all = [Bf * l for l in lens]
+        noise = self._buf("g_noise", (sum(rows_all), V))
+        lab_s, cond_s = self._buf("g_label", (label_R.numel(),), torch.int64), self._buf("g_cond", (cond_R.numel(),), torch.int64)
+        lab_s.copy_(label_R)
+        cond_s.copy_(cond_R)
+        forced = {}
+        for name, lst in (("c_mask", c_mask), ("c_img", c_img)):
+            if lst is not None:
+                bufs = [self._buf(f"g_{name}{si}", tuple(t.shape), torch.int64) for si, t in enumerate(lst)]
+                for b_, t in zip(bufs, lst):
+                    b_.copy_(t)
+                forced[name] = bufs
+        # ---- the Exp(1) noise of all scales, in the order the eager path draws it
+        off = 0
+        for si, rows in enumerate(rows_all):
+            self._noise_for_scale(si, rows, rng, out=noise[off:off + rows])
+            off += rows
+
+        def noise_view(si, rows):
+            o = sum(rows_all[:si])
+            return noise[o:o + rows]
+
+        if ent["graph"] is None:
+            n0 = ops.launch_count()
+            g = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g):
+                img_static = self._sample_body(B, lab_s, cond_s, groups, ts_all, replicas, top_k, top_p, noise_view,
+                                               forced.get("c_mask"), forced.get("c_img"))
+            ent.update(graph=g, img=img_static, last_idx=self.last_idx, f_hat=self.last_f_hat,
+                       launches=ops.launch_count() - n0, gens=(self._ws_gen, vae._ws_gen))
+        ent["graph"].replay()
+        ops.add_launch_count(ent["launches"])              # the replay launched that many of our kernels
+        self.last_idx, self.last_f_hat, self.last_logits = ent["last_idx"], ent["f_hat"], []
+        return ent["img"].clone()
+
+    def _noise_for_scale(self, si: int, rows: int, rng, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if out is None:
+            return self._noise(rows, self.V, rng)
+        if self.rng_device == "cpu":
+            out.copy_(torch.empty(rows, self.V, dtype=torch.float32).exponential_(1, generator=rng))
+        else:
+            out.exponential_(1, generator=rng)
+        return out
+
+    def _sample_body(self, B: int, label_R: torch.Tensor, cond_R: torch.Tensor, groups: int, ts_all, replicas: int, top_k,
+                     top_p, noise_fn, c_mask=None, c_img=None) -> torch.Tensor:
         """The 10-scale loop both entry points share.  groups: guidance row groups in the transformer batch (R = groups*B
         rows).  replicas = 1: autoregressive_infer_cfg - one f_hat per sample, the next map is written to both CFG halves.
-        replicas = groups = 4: conditional_infer_cfg - every replica row keeps its own samples and f_hat."""
+        replicas = groups = 4: conditional_infer_cfg - every replica row keeps its own samples and f_hat.
+        ts_all[si]: the guidance scalars of scale si; noise_fn(si, rows) -> (rows, V) Exp(1) noise."""
         dev = self.device
         vae = self.vae_proxy[0]
         C, V, Cvae = self.C, self.V, self.Cvae
@@ -375,12 +466,12 @@ class ControlVAR(nn.Module):
             cur_L += l
             tr.scale(l, L_prev)                               # blocks + head: logits (R*l, V)
             # guidance mix + top-k/top-p + multinomial
-            ts = mix(si / self.num_stages_minus_1)
+            ts = ts_all[si]
             if self.debug_noise_fn is not None:
                 q_noise = self.debug_noise_fn(si, Bf * l, V).to(device=dev, dtype=torch.float32).contiguous()
                 assert q_noise.shape == (Bf * l, V)
             else:
-                q_noise = self._noise(Bf * l, V, rng)
+                q_noise = noise_fn(si, Bf * l)
             if self.debug_capture_logits:
                 self.last_logits.append(logits[:M].view(R, l, V).clone())
             if groups == 2:

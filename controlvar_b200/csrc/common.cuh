@@ -12,6 +12,7 @@ namespace cvar {
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 extern int g_gemm_engine;
+extern int g_fast_mode;     // 1: single-MMA FP16 operands (hi halves only) - NOT a parity mode (cvar_set_fast_mode)
 
 #define CVAR_REQUIRE(cond, ...)                 \
   do {                                          \

@@ -173,7 +173,7 @@ __device__ __forceinline__ void epi_chunk(const EP& ep, const float* a16, float*
   __syncwarp();
 }
 
-template <class EP>
+template <class EP, bool kCross>
 __device__ __forceinline__ void epilogue_tile_staged(const EP& ep, uint32_t tcol, int col0, int ncols, float lo_scale,
                                                      long long m_base, int n_base, long long M, int N, float* stage,
                                                      int lane, uint64_t* tm_empty, int trace_tile) {
@@ -182,9 +182,11 @@ __device__ __forceinline__ void epilogue_tile_staged(const EP& ep, uint32_t tcol
   for (int c = 0; c < ncols; c += kEpiCols) {
     float v[kEpiCols], w[kEpiCols];
     tmem_ld_32x32b_x16(tcol + (uint32_t)(col0 + c), v);
-    tmem_ld_32x32b_x16(tcol + (uint32_t)(kAccStride + col0 + c), w);
+    if (kCross) {
+      tmem_ld_32x32b_x16(tcol + (uint32_t)(kAccStride + col0 + c), w);
 #pragma unroll
-    for (int i = 0; i < kEpiCols; ++i) v[i] = fmaf(w[i], lo_scale, v[i]);
+      for (int i = 0; i < kEpiCols; ++i) v[i] = fmaf(w[i], lo_scale, v[i]);
+    }
     epi_chunk(ep, v, stage, lane, m_base, n_base + col0 + c, M, N);
   }
   tc_fence_before();
@@ -370,7 +372,7 @@ template <int MODE> struct IsRowEpilogue<DenseRow<MODE>> { static constexpr bool
 template <> struct IsRowEpilogue<QkvRow> { static constexpr bool value = true; };
 template <> struct IsRowEpilogue<ConvRow> { static constexpr bool value = true; };
 
-template <class ROW>
+template <class ROW, bool kCross>
 __device__ __forceinline__ void epilogue_tile_rows(const ROW& ep, uint32_t tcol, int col0, int ncols, float lo_scale,
                                                    long long m, long long M, int n_base, int N, uint64_t* tm_empty,
                                                    int trace_tile) {
@@ -383,15 +385,17 @@ __device__ __forceinline__ void epilogue_tile_rows(const ROW& ep, uint32_t tcol,
   for (int c = 0; c < 8; ++c) {
     if (c * kEpiCols < ncols) {
       float w[kEpiCols];
-      tmem_ld16_nowait(tcol + (uint32_t)(kAccStride + col0 + c * kEpiCols), w);
+      if (kCross) tmem_ld16_nowait(tcol + (uint32_t)(kAccStride + col0 + c * kEpiCols), w);
       if ((c + 1) * kEpiCols < ncols && c + 1 < 8)
         tmem_ld16_nowait(tcol + (uint32_t)(col0 + (c + 1) * kEpiCols), &acc[(c + 1 < 8 ? c + 1 : 0) * kEpiCols]);
       tmem_ld_wait();
       reg_fence_16(&acc[c * kEpiCols]);
-      reg_fence_16(w);
+      if (kCross) reg_fence_16(w);
       if ((c + 1) * kEpiCols < ncols && c + 1 < 8) reg_fence_16(&acc[(c + 1 < 8 ? c + 1 : 0) * kEpiCols]);
+      if (kCross) {
 #pragma unroll
-      for (int i = 0; i < kEpiCols; ++i) acc[c * kEpiCols + i] = fmaf(w[i], lo_scale, acc[c * kEpiCols + i]);
+        for (int i = 0; i < kEpiCols; ++i) acc[c * kEpiCols + i] = fmaf(w[i], lo_scale, acc[c * kEpiCols + i]);
+      }
     }
   }
   tc_fence_before();
@@ -406,17 +410,20 @@ __device__ __forceinline__ void epilogue_tile_rows(const ROW& ep, uint32_t tcol,
   }
 }
 
-template <class EP>
+template <class EP, bool kCross>
 __device__ __forceinline__ void epilogue_tile(const EP& ep, uint32_t tcol, int col0, int ncols, float lo_scale,
                                               long long m_base, int n_base, long long M, int N, float* stage, int lane,
                                               uint64_t* tm_empty, int trace_tile) {
   if constexpr (IsRowEpilogue<EP>::value)
-    epilogue_tile_rows(ep, tcol, col0, ncols, lo_scale, m_base + lane, M, n_base, N, tm_empty, trace_tile);
+    epilogue_tile_rows<EP, kCross>(ep, tcol, col0, ncols, lo_scale, m_base + lane, M, n_base, N, tm_empty, trace_tile);
   else
-    epilogue_tile_staged(ep, tcol, col0, ncols, lo_scale, m_base, n_base, M, N, stage, lane, tm_empty, trace_tile);
+    epilogue_tile_staged<EP, kCross>(ep, tcol, col0, ncols, lo_scale, m_base, n_base, M, N, stage, lane, tm_empty,
+                                     trace_tile);
 }
 
-template <class EP, bool F16>
+// kFast (cvar_set_fast_mode; NOT a parity mode): the hi halves only - one MMA per product, half the operand bytes per
+// stage, twice the stages.
+template <class EP, bool F16, bool kFast = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 tc_gemm2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
                 const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo, EP ep,
@@ -431,17 +438,19 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constan
 
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  auto a_hi = [&](int s) { return smem + s * kStageBytes; };
-  auto a_lo = [&](int s) { return smem + s * kStageBytes + kABytes; };
-  auto b_hi = [&](int s) { return smem + s * kStageBytes + 2 * kABytes; };
-  auto b_lo = [&](int s) { return smem + s * kStageBytes + 2 * kABytes + kBBytes; };
+  constexpr int kNS = kFast ? 2 * kStages : kStages;                // pipeline stages
+  constexpr int kSB = kFast ? kStageBytes / 2 : kStageBytes;        // bytes per stage (same total)
+  auto a_hi = [&](int s) { return smem + s * kSB; };
+  auto a_lo = [&](int s) { return smem + s * kSB + kABytes; };                       // !kFast only
+  auto b_hi = [&](int s) { return smem + s * kSB + (kFast ? 1 : 2) * kABytes; };
+  auto b_lo = [&](int s) { return smem + s * kSB + 2 * kABytes + kBBytes; };         // !kFast only
   float* stage_base = reinterpret_cast<float*>(smem + kStages * kStageBytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes + kStagingBytes);
   uint64_t* full = bars;                  // [S]
-  uint64_t* empty = bars + kStages;       // [S]
-  uint64_t* tm_full = bars + 2 * kStages;
-  uint64_t* tm_empty = bars + 2 * kStages + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 2);
+  uint64_t* empty = bars + kNS;           // [S]
+  uint64_t* tm_full = bars + 2 * kNS;
+  uint64_t* tm_empty = bars + 2 * kNS + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kNS + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();           // 0 = leader
@@ -451,7 +460,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constan
 
   if (warp == kTmaWarp && lane == 0) {
     tma_prefetch_desc(&mapAhi), tma_prefetch_desc(&mapAlo), tma_prefetch_desc(&mapBhi), tma_prefetch_desc(&mapBlo);
-    for (int s = 0; s < kStages; ++s) {
+    for (int s = 0; s < kNS; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
@@ -478,7 +487,8 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constan
       if (threadIdx.x == 0) trace2(tcount, 2);
       const long long m_base = (long long)mt * 256 + rank * BM + quarter * 32;
       const uint32_t tcol = tmem_base + ((uint32_t)(quarter * 32) << 16);
-      epilogue_tile(ep, tcol, half * (BN / 2), BN / 2, kLoScale, m_base, nt * BN, M, N, stage, lane, tm_empty, tcount);
+      epilogue_tile<EP, !kFast>(ep, tcol, half * (BN / 2), BN / 2, kLoScale, m_base, nt * BN, M, N, stage, lane, tm_empty,
+                                tcount);
       if (threadIdx.x == 0) trace2(tcount, 4);
     }
   } else if (warp == kTmaWarp) {
@@ -491,16 +501,16 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constan
         const int arow = mt * 256 + (int)rank * BM;
         const int brow = nt * BN + (int)rank * (BN / 2);
         for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int s = it % kStages;
-          const uint32_t ph = (it / kStages) & 1;
+          const int s = it % kNS;
+          const uint32_t ph = (it / kNS) & 1;
           mbar_wait(&empty[s], ph ^ 1);
           if (kb == 0) trace2(it / nkb, 5);
           if (kb == nkb - 1) trace2(it / nkb, 6);
-          if (rank == 0) mbar_arrive_expect_tx(&full[s], 2u * (uint32_t)kStageBytes);   // bytes of BOTH CTAs
+          if (rank == 0) mbar_arrive_expect_tx(&full[s], 2u * (uint32_t)kSB);   // bytes of BOTH CTAs
           tma_load_2d_2sm(&mapAhi, &full[s], a_hi(s), kb * kBKe, arow);
-          tma_load_2d_2sm(&mapAlo, &full[s], a_lo(s), kb * kBKe, arow);
+          if (!kFast) tma_load_2d_2sm(&mapAlo, &full[s], a_lo(s), kb * kBKe, arow);
           tma_load_2d_2sm(&mapBhi, &full[s], b_hi(s), kb * kBKe, brow);
-          tma_load_2d_2sm(&mapBlo, &full[s], b_lo(s), kb * kBKe, brow);
+          if (!kFast) tma_load_2d_2sm(&mapBlo, &full[s], b_lo(s), kb * kBKe, brow);
         }
       }
     }
@@ -514,8 +524,8 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constan
         trace2(tcount, 0);
         const uint32_t d = tmem_base, dl = tmem_base + (uint32_t)kAccStride;
         for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int s = it % kStages;
-          const uint32_t ph = (it / kStages) & 1;
+          const int s = it % kNS;
+          const uint32_t ph = (it / kNS) & 1;
           mbar_wait(&full[s], ph);
           tc_fence_after();
           const uint64_t dah = G::desc(smem_u32(a_hi(s))), dal = G::desc(smem_u32(a_lo(s)));
@@ -523,8 +533,10 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constan
 #pragma unroll
           for (int k = 0; k < BK / 8; ++k) {        // one MMA consumes 32 bytes of K: 8 TF32 or 16 FP16 elements
             const uint64_t adv = (uint64_t)(k * 2);
-            umma_2sm<F16>(dl, dal + adv, dbh + adv, kIdesc, (kb | k) != 0);
-            umma_2sm<F16>(dl, dah + adv, dbl + adv, kIdesc, 1u);
+            if (!kFast) {
+              umma_2sm<F16>(dl, dal + adv, dbh + adv, kIdesc, (kb | k) != 0);
+              umma_2sm<F16>(dl, dah + adv, dbl + adv, kIdesc, 1u);
+            }
             umma_2sm<F16>(d, dah + adv, dbh + adv, kIdesc, (kb | k) != 0);
           }
           umma_commit_2sm(&empty[s]);
@@ -569,7 +581,7 @@ __device__ __forceinline__ void tma_load_4d_2sm(const CUtensorMap* map, uint64_t
       : "memory");
 }
 
-template <class EP>
+template <class EP, bool kFast = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 tc_conv2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
                 const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo, EP ep, ConvGeo g,
@@ -582,17 +594,19 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constan
 
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  auto a_hi = [&](int s) { return smem + s * kCvStageBytes; };
-  auto a_lo = [&](int s) { return smem + s * kCvStageBytes + kCvTile; };
-  auto b_hi = [&](int s) { return smem + s * kCvStageBytes + 2 * kCvTile; };
-  auto b_lo = [&](int s) { return smem + s * kCvStageBytes + 3 * kCvTile; };
+  constexpr int kNS = kFast ? 2 * kCvStages : kCvStages;
+  constexpr int kSB = kFast ? kCvStageBytes / 2 : kCvStageBytes;
+  auto a_hi = [&](int s) { return smem + s * kSB; };
+  auto a_lo = [&](int s) { return smem + s * kSB + kCvTile; };                        // !kFast only
+  auto b_hi = [&](int s) { return smem + s * kSB + (kFast ? 1 : 2) * kCvTile; };
+  auto b_lo = [&](int s) { return smem + s * kSB + 3 * kCvTile; };                    // !kFast only
   float* stage_base = reinterpret_cast<float*>(smem + kCvStages * kCvStageBytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kCvStages * kCvStageBytes + kStagingBytes);
   uint64_t* full = bars;
-  uint64_t* empty = bars + kCvStages;
-  uint64_t* tm_full = bars + 2 * kCvStages;
-  uint64_t* tm_empty = bars + 2 * kCvStages + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kCvStages + 2);
+  uint64_t* empty = bars + kNS;
+  uint64_t* tm_full = bars + 2 * kNS;
+  uint64_t* tm_empty = bars + 2 * kNS + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kNS + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -603,7 +617,7 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constan
 
   if (warp == kTmaWarp && lane == 0) {
     tma_prefetch_desc(&mapAhi), tma_prefetch_desc(&mapAlo), tma_prefetch_desc(&mapBhi), tma_prefetch_desc(&mapBlo);
-    for (int s = 0; s < kCvStages; ++s) {
+    for (int s = 0; s < kNS; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
@@ -629,14 +643,15 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constan
       tc_fence_after();
       const long long m_base = (long long)mt * 256 + rank * BM + quarter * 32;
       const uint32_t tcol = tmem_base + ((uint32_t)(quarter * 32) << 16);
-      epilogue_tile(ep, tcol, half * (BNr / 2), BNr / 2, kLoScale, m_base, nt * BNr, M, N, stage, lane, tm_empty, 64);
+      epilogue_tile<EP, !kFast>(ep, tcol, half * (BNr / 2), BNr / 2, kLoScale, m_base, nt * BNr, M, N, stage, lane, tm_empty,
+                                64);
     }
   } else if (warp == kTmaWarp) {
     // ================================================================ TMA: this CTA's 128 pixels (shifted window per tap)
     if (lane == 0) {
       const int pad = g.ks >> 1;
       const long long HW = (long long)g.H * g.W;
-      const uint32_t stage_tx = 2u * (2u * (uint32_t)kCvTile + 2u * (uint32_t)(BNr / 2) * 64u);   // both CTAs
+      const uint32_t stage_tx = (kFast ? 1u : 2u) * (2u * (uint32_t)kCvTile + 2u * (uint32_t)(BNr / 2) * 64u);   // both CTAs
       int it = 0;
       for (int tile = pair; tile < total_tiles; tile += npairs) {
         int mt, nt;
@@ -650,14 +665,14 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constan
           const int ky = tap / g.ks, kx = tap - ky * g.ks;
           int kb = tap * cpb;                      // K-block index in the full tap-major weight matrix
           for (int cc = 0; cc < cpb; ++cc, ++kb, ++it) {
-            const int s = it % kCvStages;
-            const uint32_t ph = (it / kCvStages) & 1;
+            const int s = it % kNS;
+            const uint32_t ph = (it / kNS) & 1;
             mbar_wait(&empty[s], ph ^ 1);
             if (rank == 0) mbar_arrive_expect_tx(&full[s], stage_tx);
             tma_load_4d_2sm(&mapAhi, &full[s], a_hi(s), cc * 32, x0 + kx - pad, y0 + ky - pad, img);
-            tma_load_4d_2sm(&mapAlo, &full[s], a_lo(s), cc * 32, x0 + kx - pad, y0 + ky - pad, img);
+            if (!kFast) tma_load_4d_2sm(&mapAlo, &full[s], a_lo(s), cc * 32, x0 + kx - pad, y0 + ky - pad, img);
             tma_load_2d_2sm(&mapBhi, &full[s], b_hi(s), kb * 32, brow);
-            tma_load_2d_2sm(&mapBlo, &full[s], b_lo(s), kb * 32, brow);
+            if (!kFast) tma_load_2d_2sm(&mapBlo, &full[s], b_lo(s), kb * 32, brow);
           }
         }
       }
@@ -671,8 +686,8 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constan
         tc_fence_after();
         const uint32_t d = tmem_base, dl = tmem_base + (uint32_t)kAccStride;
         for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int s = it % kCvStages;
-          const uint32_t ph = (it / kCvStages) & 1;
+          const int s = it % kNS;
+          const uint32_t ph = (it / kNS) & 1;
           mbar_wait(&full[s], ph);
           tc_fence_after();
           const uint64_t dah = G::desc(smem_u32(a_hi(s))), dal = G::desc(smem_u32(a_lo(s)));
@@ -680,8 +695,10 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constan
 #pragma unroll
           for (int k = 0; k < 2; ++k) {               // 32 halves = two K=16 steps of 32 bytes
             const uint64_t adv = (uint64_t)(k * 2);
-            umma_2sm<true>(dl, dal + adv, dbh + adv, idesc, (kb | k) != 0);
-            umma_2sm<true>(dl, dah + adv, dbl + adv, idesc, 1u);
+            if (!kFast) {
+              umma_2sm<true>(dl, dal + adv, dbh + adv, idesc, (kb | k) != 0);
+              umma_2sm<true>(dl, dah + adv, dbl + adv, idesc, 1u);
+            }
             umma_2sm<true>(d, dah + adv, dbh + adv, idesc, (kb | k) != 0);
           }
           umma_commit_2sm(&empty[s]);
@@ -795,7 +812,9 @@ int launch(const EP& ep, const void* A_hi, const void* A_lo, long long lda, cons
   if (!rc) rc = make_map(&mbh, W_hi, N, K, ldw, F16);
   if (!rc) rc = make_map(&mbl, W_lo, N, K, ldw, F16);
   if (rc) return rc;
-  auto kern = tc_gemm2_kernel<EP, F16>;
+  // fast mode (NOT a parity mode) exists for the FP16-pair row epilogues only
+  auto kern = (F16 && IsRowEpilogue<EP>::value && g_fast_mode) ? tc_gemm2_kernel<EP, F16, F16 && IsRowEpilogue<EP>::value>
+                                                               : tc_gemm2_kernel<EP, F16, false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
   if (e != cudaSuccess) {
     set_error("%s: cannot raise shared memory to %d: %s", name, kSmem, cudaGetErrorString(e));
@@ -915,7 +934,7 @@ int tc2_conv_f16(const cvar_conv_args* a, cudaStream_t s) {
   const bool rows = g_epi_overlap && a->out_mode == 0 && a->Cout % 16 == 0 && tc2::aligned32(a->out) &&
                     tc2::aligned32(a->bias) && tc2::aligned32(a->resid) && a->bias != nullptr;
   auto kern_staged = tc2::tc_conv2_kernel<ConvEpilogue>;
-  auto kern_rows = tc2::tc_conv2_kernel<tc2::ConvRow>;
+  auto kern_rows = g_fast_mode ? tc2::tc_conv2_kernel<tc2::ConvRow, true> : tc2::tc_conv2_kernel<tc2::ConvRow, false>;
   cudaError_t e = rows ? cudaFuncSetAttribute(kern_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::kCvSmem)
                        : cudaFuncSetAttribute(kern_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::kCvSmem);
   CVAR_REQUIRE(e == cudaSuccess, "cvar_conv2d[f16x3]: cannot raise shared memory to %d: %s", tc2::kCvSmem, cudaGetErrorString(e));

@@ -35,7 +35,24 @@ extern "C" int cvar_set_gemm_engine(int e) {
   return old;
 }
 extern "C" int cvar_get_gemm_engine(void) { return cvar::g_gemm_engine; }
-namespace cvar { extern int g_epi_overlap; }
+namespace cvar {
+extern int g_epi_overlap;
+static int initial_fast_mode() {
+  const char* e = getenv("CVAR_FAST_MODE");
+  return (e != nullptr && e[0] == '1') ? 1 : 0;
+}
+int g_fast_mode = initial_fast_mode();
+}  // namespace cvar
+extern "C" int cvar_add_launch_count(long long n) {
+  cvar::count_launch((int)n);
+  return 0;
+}
+extern "C" int cvar_set_fast_mode(int on) {
+  int old = cvar::g_fast_mode;
+  cvar::g_fast_mode = on ? 1 : 0;
+  return old;
+}
+extern "C" int cvar_get_fast_mode(void) { return cvar::g_fast_mode; }
 extern "C" int cvar_set_epilogue_overlap(int on) {
   int old = cvar::g_epi_overlap;
   cvar::g_epi_overlap = on ? 1 : 0;

@@ -123,8 +123,26 @@ class _Timed:
         return False
 
 
+def profiling() -> bool:
+    return _prof is not None
+
+
 def launch_count() -> int:
     return int(_lib.load().cvar_launch_count())
+
+
+def add_launch_count(n: int) -> None:
+    """Account for kernels launched by a CUDA-graph replay (the library only counts the launches it issues itself)."""
+    _lib.load().cvar_add_launch_count(int(n))
+
+
+def set_fast_mode(on: bool) -> int:
+    """NOT a parity mode: single-MMA FP16 operands (hi halves only) in the tcgen05 GEMM / conv / attention kernels."""
+    return int(_lib.load().cvar_set_fast_mode(int(bool(on))))
+
+
+def get_fast_mode() -> int:
+    return int(_lib.load().cvar_get_fast_mode())
 
 
 def set_gemm_engine(engine: int) -> int:

@@ -48,6 +48,8 @@ def invalidate_caches(modules: Iterable[nn.Module]) -> None:
             c = getattr(m, name, None)
             if c is not None:
                 c.clear()
+        if hasattr(m, "_ws_gen"):
+            m._ws_gen += 1
 
 
 def broadcast_weights(arena: torch.Tensor, src: int = 0, modules: Iterable[nn.Module] = ()) -> None:

@@ -96,6 +96,7 @@ class VQVAE(nn.Module):
         self._packed: Dict[str, torch.Tensor] = {}
         self._packed16: Dict[str, "ops.F16Pair"] = {}
         self._ws: Dict[Tuple, torch.Tensor] = {}
+        self._ws_gen = 0       # bumped when a workspace or a derived weight is (re)made: ControlVAR's CUDA graphs hold pointers
         self.eval()
 
     # -------------------------------------------------------------------------------------------- weights
@@ -107,6 +108,7 @@ class VQVAE(nn.Module):
             sd[k] = self.quantize.ema_vocab_hit_SV
         self._packed.clear()
         self._packed16.clear()
+        self._ws_gen += 1
         return super().load_state_dict(sd, strict=strict, assign=assign)
 
     def _apply(self, fn, recurse=True):
@@ -114,6 +116,7 @@ class VQVAE(nn.Module):
         self._packed16.clear()
         self._ws.clear()
         self._U.clear()
+        self._ws_gen += 1
         return super()._apply(fn, recurse)
 
     def _w(self, key: str) -> torch.Tensor:
@@ -187,10 +190,12 @@ class VQVAE(nn.Module):
         if t is None or t.device != dev or t.numel() < n:
             t = torch.empty(max(n, 1), device=dev, dtype=dtype)
             self._ws[key] = t
+            self._ws_gen += 1          # captured CUDA graphs (ControlVAR._graphs) hold workspace pointers
         return t[:n].view(tuple(shape))
 
     def release_workspace(self):
         self._ws.clear()
+        self._ws_gen += 1
 
     # -------------------------------------------------------------------------------------------- decoder
     def _gn(self, x, prefix: str, B, HW, Cn, slot: int):

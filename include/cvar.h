@@ -53,6 +53,16 @@ CVAR_API int cvar_get_gemm_engine(void);
  * A/B timing).  Results are bit-identical.  Environment variable CVAR_EPI_OVERLAP = 0 | 1 sets the initial value.
  * Returns the previous value. */
 CVAR_API int cvar_set_epilogue_overlap(int on);
+/* Adds n to the launch counter: a host that replays a captured CUDA graph of this library's kernels accounts for the
+ * replayed launches with it (the library counts only the launches it issues itself). */
+CVAR_API int cvar_add_launch_count(long long n);
+/* Fast mode - NOT a parity mode.  0 (default): three MMAs per product on FP16 pairs (fp32-class results, the mode every
+ * parity claim refers to).  1: the 2-CTA GEMM / convolution kernels and the f16 attention kernel use the `hi` halves only,
+ * one kind::f16 MMA per product with fp32 accumulation (SURVEY.md section 7.2 "fast mode"): half-precision operand
+ * rounding (2^-11 relative), tokens diverge from the reference.  Reported separately by bench.py --fast.  Returns the
+ * previous value.  Environment variable CVAR_FAST_MODE = 1 sets it at load. */
+CVAR_API int cvar_set_fast_mode(int on);
+CVAR_API int cvar_get_fast_mode(void);
 /* K-block of the tcgen05 engine: 32 (128-byte swizzle, default) or 16 (64-byte swizzle, deeper pipeline). Returns the
  * previous value. */
 CVAR_API int cvar_set_tc_kblock(int bk);

@@ -35,6 +35,10 @@ WORKLOADS = {
     # BASELINE.json configs[4] per-GPU shard (cosine attention)
     "d30_b32": dict(depth=30, B=32, cond=2, cfg=1.5, desc="d30 ControlVAR 256x256 10-scale, batch 32/GPU, CFG=1.5, depth condition"),
     "d24_b8": dict(depth=24, B=8, cond=1, cfg=1.5, desc="d24 ControlVAR 256x256 10-scale, batch 8/GPU (small-batch probe)"),
+    # pixel-conditioned sampling (conditional_infer_cfg: 4 guidance replicas = 64 transformer rows,
+    # control tokens teacher-forced from synthetic token maps, guidance (1.5, 1.5, 1.5))
+    "d24_cond_b16": dict(depth=24, B=16, cond=1, cfg=1.5, conditional=True,
+                         desc="d24 ControlVAR.conditional_infer_cfg 256x256, batch 16/GPU (64 replica rows), c_mask forced, canny"),
 }
 TOP_K, TOP_P = 900, 0.96          # reference validate() defaults, train_control_var_hpu.py:338
 CPU_BATCH_NOTE = ("measured on a 16-core B200 host: 0.336 / 0.342 / 0.347 / 0.391 img/s at 1 / 2 / 4 / 8 images per call - still rising with batch, so this bounded sample is a LOWER bound on large-batch CPU throughput")
@@ -203,6 +207,41 @@ def cpu_baseline_subprocess(args):
         return {"error": repr(e)}
 
 
+def library_bar():
+    """The unmodified reference on the B200 through PyTorch's library kernels (tools/library_bar.py), from the committed
+    capture - a constant of the round, not measured in this run."""
+    p = os.path.join(ROOT, "profiles", "r02_library_bar.json")
+    if not os.path.exists(p):
+        return None
+    d = json.load(open(p))
+    out = {"source": "profiles/r02_library_bar.json (tools/library_bar.py on a B200 of this pool; NOT measured in this run)",
+           "workload": f"d{d['depth']} B={d['batch']}"}
+    for arm in ("fp32", "bf16_autocast"):
+        if arm in d and "ms_per_call" in d[arm]:
+            out[arm] = {"images_per_s": d[arm]["images_per_s"], "ms_per_call": d[arm]["ms_per_call"],
+                        "class_ms": d[arm].get("class_ms")}
+    return out
+
+
+def fast_vs_parity(var, ops, torch, Bc, label_d, ct_d, kw):
+    """Fast mode against the parity mode of this library on the same inputs and noise (the parity mode is what the oracle
+    tests pin): the fast run is teacher-forced onto the parity run's tokens, so every scale sees the same trajectory.
+    -> token flip rate per scale, max |pixel| difference of the decoded images."""
+    lab, ct = label_d[:Bc].contiguous(), ct_d[:Bc].contiguous()
+    ops.set_fast_mode(False)
+    img_p = var.autoregressive_infer_cfg(Bc, lab, g_seed=77, cond_type=ct, **kw)
+    idx_p = [t.clone() for t in var.last_idx]
+    ops.set_fast_mode(True)
+    var.debug_forced_idx = idx_p
+    img_f = var.autoregressive_infer_cfg(Bc, lab, g_seed=77, cond_type=ct, **kw)
+    var.debug_forced_idx = None
+    flips = [float((a != b).float().mean()) for a, b in zip(idx_p, var.last_idx)]
+    return {"against": "the parity mode of this library, same inputs and Exp(1) noise, teacher-forced", "images": Bc,
+            "token_flip_rate_per_scale": [round(f, 5) for f in flips],
+            "token_flip_rate": sum(float((a != b).sum()) for a, b in zip(idx_p, var.last_idx)) / sum(a.numel() for a in idx_p),
+            "max_abs_pixel_diff_same_tokens": float((img_p - img_f).abs().max())}
+
+
 # ----------------------------------------------------------------------------------------------------- our arm
 def main_ours(args, wl):
     import torch
@@ -252,14 +291,32 @@ def main_ours(args, wl):
     label_pin, ct_pin = label_h.pin_memory(), ct_h.pin_memory()
     img_host = torch.empty(B, 3, 512, 256, dtype=torch.float32).pin_memory()
     kw = dict(cfg=wl["cfg"], top_k=TOP_K, top_p=TOP_P)
+    conditional = bool(wl.get("conditional"))
+    c_mask_h = c_mask_d = c_mask_pin = None
+    if conditional:       # synthetic control-token maps (what VQVAE.img_to_idxBl would return for a condition image)
+        gtok = torch.Generator().manual_seed(1234 + rank)
+        c_mask_h = [torch.randint(0, 4096, (B, pn * pn), generator=gtok) for pn in cfgp.patch_nums]
+        c_mask_d = [t.to(dev) for t in c_mask_h]
+        c_mask_pin = [t.pin_memory() for t in c_mask_h]
+        kw["cfg"] = (wl["cfg"],) * 3
+    if args.fast:
+        ops.set_fast_mode(True)
+    if args.no_graphs:
+        var.use_graphs = False
+
+    def call(lab, ct, it, cm):
+        if conditional:
+            return var.conditional_infer_cfg(B, lab, g_seed=it * world + rank, cond_type=ct, c_mask=cm, **kw)
+        return var.autoregressive_infer_cfg(B, lab, g_seed=it * world + rank, cond_type=ct, **kw)
 
     def step_device(it):
-        return var.autoregressive_infer_cfg(B, label_d, g_seed=it * world + rank, cond_type=ct_d, **kw)
+        return call(label_d, ct_d, it, c_mask_d)
 
     def step_e2e(it):
         lab = label_pin.to(dev, non_blocking=True)
         ct = ct_pin.to(dev, non_blocking=True)
-        img = var.autoregressive_infer_cfg(B, lab, g_seed=it * world + rank, cond_type=ct, **kw)
+        cm = [t.to(dev, non_blocking=True) for t in c_mask_pin] if conditional else None
+        img = call(lab, ct, it, cm)
         img_host.copy_(img, non_blocking=True)
         return img
 
@@ -290,17 +347,25 @@ def main_ours(args, wl):
             ms = t.item()
         return ms, launches, prof
 
-    for w in range(args.warmup):
+    for w in range(args.warmup):          # call 1 eager, call 2 captures the CUDA graph, calls 3+ replay it
         step_device(w)
     torch.cuda.synchronize()
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-    ms_total, launches, prof = timed(step_device, args.steps, 1000, profile=True)
-    # --profile-only (diagnostic, for ncu launch lists): skip the second, end-to-end pass; the line is then not a bench line
+    # pass 1 (roofline): eager, CUDA events around every launch of our kernels (the profiler switches the graph off)
+    prof_steps = min(args.steps, 3)
+    ms_prof, _, prof = timed(step_device, prof_steps, 500, profile=True)
+    # pass 2 (value): inputs resident in HBM, the public call (CUDA-graph replay unless --no-graphs)
+    ms_total, launches, _ = (ms_prof * args.steps / prof_steps, 0, None) if args.profile_only else timed(step_device, args.steps, 1000)
+    # pass 3 (e2e): pinned host inputs copied in, images copied out, inside the timed region
+    # --profile-only (diagnostic, for ncu launch lists): pass 1 only; the line is then not a bench line
     ms_e2e, _, _ = (ms_total, 0, None) if args.profile_only else timed(step_e2e, args.steps, 2000)
     clk = clocks.stop() if rank == 0 else None
     mem_gb = torch.cuda.max_memory_allocated() / 2**30
+    fast_check = None
+    if args.fast and rank == 0 and not conditional:
+        fast_check = fast_vs_parity(var, ops, torch, min(B, 8), label_d, ct_d, kw)
 
     if rank == 0:
         pk = peaks()
@@ -313,10 +378,13 @@ def main_ours(args, wl):
         d = classes[dom]
         ach_tf = d["work"] / (d["ms"] / 1e3) / 1e12
         traffic = {}
-        tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        tp = os.path.join(ROOT, "profiles", "r02_traffic.json")
+        if not os.path.exists(tp):
+            tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
         if os.path.exists(tp):        # ncu --set full figure of ONE representative launch (the class mixes many shapes)
             tj = json.load(open(tp))
-            traffic = {"traffic": tj["traffic"], "note": f"dram read+write of one launch ({tj['launch']}), algorithmic "
+            traffic = {"traffic": tj["traffic"], "note": f"NOT measured in this run: constant from {os.path.basename(tp)} = dram "
+                                                         f"read+write of one launch ({tj['launch']}), algorithmic "
                                                          f"{tj['algorithmic_bytes']} B; {tj['source']}"}
         roof = {"kernel": {"gemm": "dense-layer GEMM (cvar_gemm / cvar_qkv_project)", "conv": "decoder implicit-GEMM conv (cvar_conv2d)",
                            "attn": "KV-cached attention (cvar_attn_kvcache)"}[dom],
@@ -324,10 +392,12 @@ def main_ours(args, wl):
                 "traffic": traffic.get("traffic") if dom == "gemm" else None, "traffic_note": traffic.get("note"),
                 "peak_source": pk["src"] + ", sustained bf16 (kernel timed inside a long step)",
                 "launches": d["launches"], "avg_launch_ms": d["ms"] / d["launches"],
-                "share_of_step": d["ms"] / ms_total}
+                "share_of_step": d["ms"] / ms_prof,
+                "timed_in": f"pass 1 of this run: {prof_steps} eager step(s) with CUDA events around every launch of this "
+                            f"library ({ms_prof / prof_steps:.1f} ms/step; the value / e2e passes replay a CUDA graph)"}
         kernels = {}
         for k, v in prof.items():
-            e = {"launches": v["launches"], "ms_per_step": v["ms"] / args.steps, "share_of_step": v["ms"] / ms_total}
+            e = {"launches": v["launches"], "ms_per_step": v["ms"] / prof_steps, "share_of_step": v["ms"] / ms_prof}
             if v["work"] > 0:
                 e["tflops"] = v["work"] / (v["ms"] / 1e3) / 1e12
                 e["frac_of_bf16_sustained"] = e["tflops"] / pk["tf_sust"]
@@ -344,16 +414,24 @@ def main_ours(args, wl):
                           "accumulations), kind::f16 attention on an FP16-pair KV cache"}.get(ops.get_gemm_engine(), "?")
         line = {"metric": f"images/sec (256x256, d{depth}, CFG=1.5)", "value": value, "unit": "images/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "scaling": "weak", "vs_baseline": None,
+                "dtype": "f16 operands, one MMA per product, f32 accumulate (FAST MODE - not the parity mode)" if args.fast else "f32",
+                "data": "synthetic",
                 "config": {"workload": args.workload, "desc": wl["desc"], "batch_per_gpu": B, "global_batch": world * B,
                            "top_k": TOP_K, "top_p": TOP_P, "gemm_engine": engine_name,
+                           "cuda_graph": bool(var.use_graphs), "mode": "fast (cvar_set_fast_mode: hi halves only)" if args.fast else "parity (f16x3, fp32-class)",
                            "l2": "working set >> L2: weights %.1f GB + KV arena %.1f GB streamed every step" % (
                                arena.numel() * 4 / 1e9, 2 * depth * 2 * B * 1360 * 64 * depth * 4 / 1e9),
                            "parallelism": f"dp{world} (batch sharded, one NCCL weight broadcast: {bcast_ms:.1f} ms)",
                            "algorithmic_tflop_per_image": work_per_image(depth), "peak_mem_gib": round(mem_gb, 1)},
                 "e2e": {"value": e2e_v, "unit": "images/s", "h2d_bytes_per_step": int(16 * B * world),
                         "d2h_bytes_per_step": int(B * 3 * 512 * 256 * 4 * world)},
-                "gpu_launches": launches, "roofline": roof, "kernels": kernels, "cpu_baseline": cpu, "clocks": clk}
+                "gpu_launches": launches, "roofline": roof, "kernels": kernels, "cpu_baseline": cpu, "clocks": clk,
+                "library_bar": library_bar()}
+        if args.fast:
+            line["fast_mode_check"] = fast_check
+            line["note"] = ("FAST MODE line: a separate, clearly labelled measurement (SURVEY.md 7.2); tokens diverge from the "
+                            "reference by construction - no parity claim attaches to it")
         if args.profile_only:
             line["e2e"] = None
             line["note"] = "--profile-only run: diagnostic, not a bench line"
@@ -377,6 +455,9 @@ if __name__ == "__main__":
                     help="images per CPU-reference step (bounded sample: ~20 s of CPU work at d24 on 16 cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-only", action="store_true", help="diagnostic: device pass only (for ncu launch lists)")
+    ap.add_argument("--fast", action="store_true",
+                    help="FAST MODE (not parity): single-MMA fp16 operands; prints a separately labelled line")
+    ap.add_argument("--no-graphs", action="store_true", help="launch every kernel from the host instead of replaying a CUDA graph")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

@@ -296,6 +296,8 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// kFast (cvar_set_fast_mode; NOT a parity mode): hi halves only - one MMA per product, no P residual, half the K / V^T bytes.
+template <bool kFast>
 __global__ void __launch_bounds__(kThreads, 2)
 attn16_tc_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_constant__ CUtensorMap mapQlo,
                  const __grid_constant__ CUtensorMap mapKhi, const __grid_constant__ CUtensorMap mapKlo,
@@ -377,13 +379,15 @@ attn16_tc_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_consta
         }
         rs += p0 + p1;
         const __half2 h = __floats2half2_rn(p0, p1);                 // low half = lower key index
-        const float2 hf = __half22float2(h);
-        const __half2 lo = __floats2half2_rn((p0 - hf.x) * kF16LoScale, (p1 - hf.y) * kF16LoScale);
         ph[i >> 1] = *reinterpret_cast<const uint32_t*>(&h);
-        pl[i >> 1] = *reinterpret_cast<const uint32_t*>(&lo);
+        if (!kFast) {
+          const float2 hf = __half22float2(h);
+          const __half2 lo = __floats2half2_rn((p0 - hf.x) * kF16LoScale, (p1 - hf.y) * kF16LoScale);
+          pl[i >> 1] = *reinterpret_cast<const uint32_t*>(&lo);
+        }
       }
       tmem_st_32x32b_x8(tl + sb + 16 * c, ph);
-      tmem_st_32x32b_x8(tl + sb + 16 * c + 8, pl);
+      if (!kFast) tmem_st_32x32b_x8(tl + sb + 16 * c + 8, pl);
     };
     // the whole tile against reference `ref`; chunk loads are prefetched one ahead (one exposed TMEM round trip)
     auto tile_pass = [&](auto masked, uint32_t sb, float nref, int nvalid, float& rs) {
@@ -411,11 +415,12 @@ attn16_tc_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_consta
       for (int hf = 0; hf < 2; ++hf) {
         float a[32], b[32];
         tmem_ld_nowait_x32(tl + kColO + 32 * hf, a);
-        tmem_ld_nowait_x32(tl + kColOx + 32 * hf, b);
+        if (!kFast) tmem_ld_nowait_x32(tl + kColOx + 32 * hf, b);
         tmem_wait_ld();
-        reg_fence32(a), reg_fence32(b);
+        reg_fence32(a);
+        if (!kFast) reg_fence32(b);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o_reg[32 * hf + i] += fmaf(b[i], kInvLo, a[i]);
+        for (int i = 0; i < 32; ++i) o_reg[32 * hf + i] += kFast ? a[i] : fmaf(b[i], kInvLo, a[i]);
       }
     };
 
@@ -466,7 +471,7 @@ attn16_tc_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_consta
         for (int d = 0; d < D; ++d) o_reg[d] *= corr;
         if ((j % kDrain) != 0) {
 #pragma unroll 1
-          for (int c = 0; c < 8; ++c) {
+          for (int c = 0; c < (kFast ? 4 : 8); ++c) {
             float a[16];
             tmem_ld_nowait_x16(tl + kColO + 16 * c, a);        // O_main [128,192) and O_x [192,256) are contiguous
             tmem_wait_ld();
@@ -507,13 +512,14 @@ attn16_tc_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_consta
     for (int c = 0; c < 4; ++c) {
       float a[16], b[16];
       tmem_ld_32x32b_x16(tl + kColO + 16 * c, a);
-      tmem_ld_32x32b_x16(tl + kColOx + 16 * c, b);
+      if (!kFast) tmem_ld_32x32b_x16(tl + kColOx + 16 * c, b);
       if (t < l) {
 #pragma unroll
         for (int i = 0; i < 16; i += 4) {
           float vv[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) vv[e] = (o_reg[16 * c + i + e] + fmaf(b[i + e], kInvLo, a[i + e])) * inv;
+          for (int e = 0; e < 4; ++e)
+            vv[e] = (o_reg[16 * c + i + e] + (kFast ? a[i + e] : fmaf(b[i + e], kInvLo, a[i + e]))) * inv;
           if (o16_hi != nullptr) st4_split_f16(o16_hi + off + 16 * c + i, o16_lo + off + 16 * c + i, vv);
           if (out != nullptr) st4(out + off + 16 * c + i, make_float4(vv[0], vv[1], vv[2], vv[3]));
         }
@@ -522,21 +528,21 @@ attn16_tc_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_consta
   } else if (warp == 4) {
     // ================================================================ TMA: the Q tile once, then K / V^T tiles
     if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, (uint32_t)(2 * kQTile));
+      mbar_arrive_expect_tx(q_full, (uint32_t)((kFast ? 1 : 2) * kQTile));
       tma_load_3d(&mapQhi, q_full, q_s, 0, q0, rh);
-      tma_load_3d(&mapQlo, q_full, q_s + kQTile, 0, q0, rh);
+      if (!kFast) tma_load_3d(&mapQlo, q_full, q_s + kQTile, 0, q0, rh);
       for (int j = 0; j < ntiles; ++j) {
         const int s = j % kStages;
         const uint32_t ph = ((j / kStages) & 1) ^ 1;
         unsigned char* st = stage(s);
         mbar_wait(&k_empty[s], ph);                        // released by S(j - kStages): early
-        mbar_arrive_expect_tx(&k_full[s], (uint32_t)(2 * kTile));
+        mbar_arrive_expect_tx(&k_full[s], (uint32_t)((kFast ? 1 : 2) * kTile));
         tma_load_3d(&mapKhi, &k_full[s], st + 0 * kTile, 0, j * BKV, rh);
-        tma_load_3d(&mapKlo, &k_full[s], st + 1 * kTile, 0, j * BKV, rh);
+        if (!kFast) tma_load_3d(&mapKlo, &k_full[s], st + 1 * kTile, 0, j * BKV, rh);
         mbar_wait(&v_empty[s], ph);                        // released by P @ V(j - kStages): a softmax later
-        mbar_arrive_expect_tx(&v_full[s], (uint32_t)(2 * kTile));
+        mbar_arrive_expect_tx(&v_full[s], (uint32_t)((kFast ? 1 : 2) * kTile));
         tma_load_3d(&mapVhi, &v_full[s], st + 2 * kTile, j * BKV, 0, rh);
-        tma_load_3d(&mapVlo, &v_full[s], st + 3 * kTile, j * BKV, 0, rh);
+        if (!kFast) tma_load_3d(&mapVlo, &v_full[s], st + 3 * kTile, j * BKV, 0, rh);
       }
     }
   } else {
@@ -553,16 +559,18 @@ attn16_tc_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_consta
         unsigned char* st = stage(s);
         const uint32_t d = tmem_base + kColS + 64u * (uint32_t)(j & 1);
         const uint64_t dkh = G::desc(smem_u32(st)), dkl = G::desc(smem_u32(st + kTile));
+        if (!kFast) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {                       // 16 head dims (32 bytes of a row) per MMA
-          const uint64_t adv = (uint64_t)(2 * k);
-          umma_f16_ss(d, dql + adv, dkh + adv, kIdesc, k != 0);
-          umma_f16_ss(d, dqh + adv, dkl + adv, kIdesc, 1u);
+          for (int k = 0; k < 4; ++k) {                     // 16 head dims (32 bytes of a row) per MMA
+            const uint64_t adv = (uint64_t)(2 * k);
+            umma_f16_ss(d, dql + adv, dkh + adv, kIdesc, k != 0);
+            umma_f16_ss(d, dqh + adv, dkl + adv, kIdesc, 1u);
+          }
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const uint64_t adv = (uint64_t)(2 * k);
-          umma_f16_ss(d, dqh + adv, dkh + adv, kIdesc, 1u);
+          umma_f16_ss(d, dqh + adv, dkh + adv, kIdesc, (kFast && k == 0) ? 0u : 1u);
         }
         umma_commit(&s_full[j & 1]);
         umma_commit(&k_empty[s]);
@@ -584,8 +592,10 @@ attn16_tc_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_consta
           const uint64_t adv = (uint64_t)(2 * k);
           const uint32_t p_hi = pb + 16 * k, p_lo = p_hi + 8;
           const uint32_t acc = (k != 0 || (j % kDrain) != 0) ? 1u : 0u;   // fresh accumulators every kDrain tiles
-          umma_f16_ts(tmem_base + kColOx, p_lo, dvh + adv, kIdesc, acc);
-          umma_f16_ts(tmem_base + kColOx, p_hi, dvl + adv, kIdesc, 1u);
+          if (!kFast) {
+            umma_f16_ts(tmem_base + kColOx, p_lo, dvh + adv, kIdesc, acc);
+            umma_f16_ts(tmem_base + kColOx, p_hi, dvl + adv, kIdesc, 1u);
+          }
           umma_f16_ts(tmem_base + kColO, p_hi, dvh + adv, kIdesc, acc);
         }
         umma_commit(&o_full[j & 1]);
@@ -667,12 +677,12 @@ extern "C" int cvar_attn_kvcache16(const void* q16_hi, const void* q16_lo, const
     if (!rc) rc = tcattn16::make_map3(&mvh, vh, T_max, 64, RH, 64);
     if (!rc) rc = tcattn16::make_map3(&mvl, vl, T_max, 64, RH, 64);
     if (rc) return rc;
-    cudaError_t e = cudaFuncSetAttribute(tcattn16::attn16_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         tcattn16::kSmem);
+    auto kern = g_fast_mode ? tcattn16::attn16_tc_kernel<true> : tcattn16::attn16_tc_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tcattn16::kSmem);
     CVAR_REQUIRE(e == cudaSuccess, "cvar_attn_kvcache16: cannot raise shared memory: %s", cudaGetErrorString(e));
     dim3 grid(cdiv(l, tcattn16::BQ), H, R);
-    tcattn16::attn16_tc_kernel<<<grid, tcattn16::kThreads, tcattn16::kSmem, (cudaStream_t)stream>>>(
-        mqh, mql, mkh, mkl, mvh, mvl, out, o16h, o16l, H, l, L, scale);
+    kern<<<grid, tcattn16::kThreads, tcattn16::kSmem, (cudaStream_t)stream>>>(mqh, mql, mkh, mkl, mvh, mvl, out, o16h, o16l,
+                                                                               H, l, L, scale);
     CVAR_CHECK_LAUNCH("cvar_attn_kvcache16[tc]");
     return 0;
   }

@@ -278,3 +278,45 @@ def test_decoder_engine4_pixels_within_tolerance(engine4):
     e = (img.cpu() - ref).abs().max().item()
     print(f"\n[f16x3-decoder] max pixel err {e:.3e} (tc_min_hw={vae._min_hw()}), launches {ops.launch_count() - n0}")
     assert e < 1e-4
+
+
+def test_fast_mode_is_half_precision_class_and_off_by_default(engine4):
+    """cvar_set_fast_mode(1) - NOT a parity mode - uses the hi halves only: errors of the order of fp16 operand rounding
+    (2^-11 relative per operand), far above the parity mode's; the default (0) is untouched by having used it."""
+    assert ops.get_fast_mode() == 0
+    torch.manual_seed(5)
+    M, N, K = 1024, 512, 1536
+    A, Wt, b = torch.randn(M, K), torch.randn(N, K) / math.sqrt(K), torch.randn(N)
+    ref = A.double() @ Wt.double().T + b.double()
+    W16 = ops.SplitWeight(g(Wt), f16=True)
+    A16 = ops.F16Pair.from_tensor(g(A))
+    out = torch.empty(M, N, device=DEV)
+    ops.gemm(None, W16, g(b), out, M, N, K, A16=A16)
+    e_par = err(out.cpu(), ref)
+    old = ops.set_fast_mode(True)
+    try:
+        assert old == 0 and ops.get_fast_mode() == 1
+        ops.gemm(None, W16, g(b), out, M, N, K, A16=A16)
+        e_fast = err(out.cpu(), ref)
+        # attention on the same switch
+        R, H, l, L = 2, 3, 128, 300
+        q, k, v = torch.randn(R, H, l, 64), torch.randn(R, H, L, 64), torch.randn(R, H, L, 64)
+        cache = ops.KVCache16(R, H, L, DEV)
+        T = cache.T
+        kp = ops.F16Pair.from_tensor_qk(g(k))
+        cache.k_hi.view(R, H, T, 64)[:, :, :L] = kp.hi
+        cache.k_lo.view(R, H, T, 64)[:, :, :L] = kp.lo
+        vp = ops.F16Pair.from_tensor(g(v.transpose(2, 3).contiguous()))
+        cache.vt_hi.view(R, H, 64, T)[:, :, :, :L] = vp.hi
+        cache.vt_lo.view(R, H, 64, T)[:, :, :, :L] = vp.lo
+        q16 = ops.F16Pair.from_tensor_qk(g(q))
+        o = torch.empty(R, l, H * 64, device=DEV)
+        ops.attn_kvcache16(q16, cache, o, R, H, l, L, 0.125, engine=1)
+        ref_o = F.scaled_dot_product_attention(q.double(), k.double(), v.double(), scale=0.125).transpose(1, 2).reshape(R, l, H * 64)
+        ea_fast = err(o.cpu(), ref_o)
+    finally:
+        ops.set_fast_mode(False)
+    ops.attn_kvcache16(q16, cache, o, R, H, l, L, 0.125, engine=1)
+    ea_par = err(o.cpu(), ref_o)
+    assert e_par < 1e-5 and ea_par < 1e-5, (e_par, ea_par)
+    assert 2e-5 < e_fast < 5e-3 and 2e-5 < ea_fast < 5e-3, (e_fast, ea_fast)

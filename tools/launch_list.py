@@ -7,6 +7,9 @@ import re
 import sys
 
 CLASSES = [
+    (r"tc_gemm2_kernel<.*DenseRow", "dense layers, tcgen05 f16x3 2-CTA, row epilogue (tc_gemm2_kernel<DenseRow<mode>, F16>)"),
+    (r"tc_gemm2_kernel<.*QkvRow", "QKV projection + KV append, tcgen05 f16x3 2-CTA, row epilogue (tc_gemm2_kernel<QkvRow, F16>)"),
+    (r"tc_conv2_kernel<.*ConvRow", "decoder conv, tcgen05 f16x3 2-CTA implicit GEMM by 4-D TMA, row epilogue (tc_conv2_kernel<ConvRow>)"),
     (r"tc_gemm2_kernel<.*DenseEpilogue, 1>", "dense layers, tcgen05 f16x3 2-CTA (tc_gemm2_kernel<DenseEpilogue, F16>)"),
     (r"tc_gemm2_kernel<.*QkvEpilogue, 1>", "QKV projection + KV append, tcgen05 f16x3 2-CTA (tc_gemm2_kernel<QkvEpilogue, F16>)"),
     (r"tc_gemm2_kernel<.*DenseEpilogue", "dense layers, tcgen05 3xTF32 2-CTA"),

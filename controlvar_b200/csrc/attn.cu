@@ -527,7 +527,11 @@ static int make_map3(CUtensorMap* map, const float* base, long long inner, long 
 int set_trace(long long* p) { return cudaMemcpyToSymbol(g_attn_trace, &p, sizeof(p)) == cudaSuccess ? 0 : -1; }
 }  // namespace tcattn
 
-extern "C" int cvar_debug_set_attn_trace(long long* dev_buf) { return tcattn::set_trace(dev_buf); }
+namespace tcattn16 { int set_trace(long long* p); }
+extern "C" int cvar_debug_set_attn_trace(long long* dev_buf) {
+  if (tcattn16::set_trace(dev_buf) != 0) return -1;      // the FP16-pair kernel shares the switch (3*32*8 int64, own layout)
+  return tcattn::set_trace(dev_buf);
+}
 
 extern "C" int cvar_attn_kvcache(const float* q, const float* k_hi, const float* k_lo, const float* vt_hi,
                                  const float* vt_lo, float* out, float* out_lo, void* out16_hi, void* out16_lo, int R,

@@ -22,6 +22,7 @@
 //     accumulated, in registers and in its TMEM row), so the common tile does no rescaling work at all.  Two 16-bit values
 //     per TMEM cell, the lower key index in the low half (A operand of kind::f16 from tensor memory).
 //   TMEM columns: S/P buffer 0 [0,64)  S/P buffer 1 [64,128)  O_main [128,192)  O_x [192,256)
+#include <stdlib.h>
 #include <type_traits>
 #include "common.cuh"
 #include "tc_ptx.cuh"
@@ -290,6 +291,16 @@ __device__ __forceinline__ void tmem_alloc_n(uint32_t* dst_smem, uint32_t ncols)
                : "memory");
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
 }
+// Optional phase trace (diagnostics, cvar_debug_set_attn_trace): CTA (0,0,0) stamps clock64() per KV tile j < 32.
+// trace[(who * 32 + j) * 8 + ev]:
+//   who 0 = softmax thread 0: 0 s_full(j) seen, 1 row maximum known, 2 P(j) stored, 3 p_ready(j) signalled
+//   who 1 = MMA thread:       0 v_full + p_ready(j) seen, 1 P @ V(j) issued, 2 k_full(j+2) seen, 3 S(j+2) issued
+//   who 2 = TMA thread:       0 k_empty seen for tile j (K load issued), 1 v_empty seen for tile j (V^T load issued)
+__device__ long long* g_attn16_trace = nullptr;
+__device__ __forceinline__ void astamp(int who, int j, int ev) {
+  if (g_attn16_trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && j >= 0 && j < 32)
+    g_attn16_trace[(who * 32 + j) * 8 + ev] = clock64();
+}
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -297,7 +308,11 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 
 // kFast (cvar_set_fast_mode; NOT a parity mode): hi halves only - one MMA per product, no P residual, half the K / V^T bytes.
-template <bool kFast>
+// kOnePass: S(j) is read from tensor memory ONCE (64 registers) and the P pass runs out of those registers; the round-1
+// kernel read it twice (row maximum, then 16-column chunks).  Tensor-memory reads are ~95 B/clk per SM (measured on the GEMM
+// drain, profiles/r02_gemm_epilogue.md): the second read of the 32 KB S tile cost ~340 cycles of that port per CTA and
+// tile, plus four exposed load round trips.
+template <bool kFast, bool kOnePass>
 __global__ void __launch_bounds__(kThreads, 2)
 attn16_tc_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_constant__ CUtensorMap mapQlo,
                  const __grid_constant__ CUtensorMap mapKhi, const __grid_constant__ CUtensorMap mapKlo,
@@ -409,6 +424,13 @@ attn16_tc_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_consta
       reg_fence16(a1);
       chunk(masked, sb, 3, a1, nref, nvalid, rs);
     };
+    // the same pass out of registers (kOnePass): a = columns [0,32), b = columns [32,64) of this row of S(j)
+    auto tile_pass_regs = [&](auto masked, uint32_t sb, const float* a, const float* b, float nref, int nvalid, float& rs) {
+      chunk(masked, sb, 0, a, nref, nvalid, rs);
+      chunk(masked, sb, 1, a + 16, nref, nvalid, rs);
+      chunk(masked, sb, 2, b, nref, nvalid, rs);
+      chunk(masked, sb, 3, b + 16, nref, nvalid, rs);
+    };
     // o_reg += O accumulated in TMEM (round-to-nearest adds)
     auto drain_O = [&]() {
 #pragma unroll
@@ -429,25 +451,33 @@ attn16_tc_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_consta
       mbar_wait(&s_full[j & 1], (j >> 1) & 1);
       tc_fence_after();
       const int nvalid = min(BKV, L - j * BKV);
+      if (row == 0) astamp(0, j, 0);
       // pass 1: row maximum of the tile
       float mx = -INFINITY;
-      {
-        float a[32], b[32];
-        tmem_ld_nowait_x32(tl + sb, a);
-        tmem_ld_nowait_x32(tl + sb + 32, b);
-        tmem_wait_ld();
-        reg_fence32(a), reg_fence32(b);
-        if (nvalid < 64) {
+      float a[32], b[32];
+      tmem_ld_nowait_x32(tl + sb, a);
+      tmem_ld_nowait_x32(tl + sb + 32, b);
+      tmem_wait_ld();
+      reg_fence32(a), reg_fence32(b);
+      if (nvalid < 64) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            if (i < nvalid) mx = fmaxf(mx, a[i]);
-            if (32 + i < nvalid) mx = fmaxf(mx, b[i]);
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(a[i], b[i]));
+        for (int i = 0; i < 32; ++i) {
+          if (i < nvalid) mx = fmaxf(mx, a[i]);
+          if (32 + i < nvalid) mx = fmaxf(mx, b[i]);
         }
+      } else {
+        // four independent chains (a single 64-long chain of dependent FMNMX is ~300 cycles of exposed latency)
+        float m0 = fmaxf(a[0], b[0]), m1 = fmaxf(a[1], b[1]), m2 = fmaxf(a[2], b[2]), m3 = fmaxf(a[3], b[3]);
+#pragma unroll
+        for (int i = 4; i < 32; i += 4) {
+          m0 = fmaxf(m0, fmaxf(a[i], b[i]));
+          m1 = fmaxf(m1, fmaxf(a[i + 1], b[i + 1]));
+          m2 = fmaxf(m2, fmaxf(a[i + 2], b[i + 2]));
+          m3 = fmaxf(m3, fmaxf(a[i + 3], b[i + 3]));
+        }
+        mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
       }
+      if (row == 0) astamp(0, j, 1);
       const bool need = j > 0 && (mx - m_ref) * sl2 > kRebase;
       bool drained = false;
       if (j == 0) {
@@ -487,11 +517,19 @@ attn16_tc_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_consta
       // pass 2: p against the reference, written back as the A operand of P @ V
       float rs = 0.f;
       const float nref = -m_ref * sl2;
-      if (nvalid < BKV)
-        tile_pass(std::true_type{}, sb, nref, nvalid, rs);
-      else
-        tile_pass(std::false_type{}, sb, nref, nvalid, rs);
+      if (kOnePass) {
+        if (nvalid < BKV)
+          tile_pass_regs(std::true_type{}, sb, a, b, nref, nvalid, rs);
+        else
+          tile_pass_regs(std::false_type{}, sb, a, b, nref, nvalid, rs);
+      } else {
+        if (nvalid < BKV)
+          tile_pass(std::true_type{}, sb, nref, nvalid, rs);
+        else
+          tile_pass(std::false_type{}, sb, nref, nvalid, rs);
+      }
       l_run += rs;
+      if (row == 0) astamp(0, j, 2);
       // every kDrain tiles the O accumulators move into the registers; P @ V(j) then starts fresh.  Done at the END of
       // the tile's softmax: P @ V(j-1), issued when this warpgroup finished tile j-1, has long completed by now.
       if (j > 0 && (j % kDrain) == 0 && !drained) {
@@ -502,6 +540,7 @@ attn16_tc_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_consta
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(&p_ready[j & 1]);
+      if (row == 0) astamp(0, j, 3);
     }
     mbar_wait(&o_full[(ntiles - 1) & 1], ((ntiles - 1) >> 1) & 1);
     tc_fence_after();
@@ -536,10 +575,12 @@ attn16_tc_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_consta
         const uint32_t ph = ((j / kStages) & 1) ^ 1;
         unsigned char* st = stage(s);
         mbar_wait(&k_empty[s], ph);                        // released by S(j - kStages): early
+        astamp(2, j, 0);
         mbar_arrive_expect_tx(&k_full[s], (uint32_t)((kFast ? 1 : 2) * kTile));
         tma_load_3d(&mapKhi, &k_full[s], st + 0 * kTile, 0, j * BKV, rh);
         if (!kFast) tma_load_3d(&mapKlo, &k_full[s], st + 1 * kTile, 0, j * BKV, rh);
         mbar_wait(&v_empty[s], ph);                        // released by P @ V(j - kStages): a softmax later
+        astamp(2, j, 1);
         mbar_arrive_expect_tx(&v_full[s], (uint32_t)((kFast ? 1 : 2) * kTile));
         tma_load_3d(&mapVhi, &v_full[s], st + 2 * kTile, j * BKV, 0, rh);
         if (!kFast) tma_load_3d(&mapVlo, &v_full[s], st + 3 * kTile, j * BKV, 0, rh);
@@ -556,6 +597,7 @@ attn16_tc_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_consta
         const int s = j % kStages;
         mbar_wait(&k_full[s], (j / kStages) & 1);
         tc_fence_after();
+        astamp(1, j - 2, 2);
         unsigned char* st = stage(s);
         const uint32_t d = tmem_base + kColS + 64u * (uint32_t)(j & 1);
         const uint64_t dkh = G::desc(smem_u32(st)), dkl = G::desc(smem_u32(st + kTile));
@@ -574,6 +616,7 @@ attn16_tc_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_consta
         }
         umma_commit(&s_full[j & 1]);
         umma_commit(&k_empty[s]);
+        astamp(1, j - 2, 3);
       };
       mbar_wait(q_full, 0);
       tc_fence_after();
@@ -584,6 +627,7 @@ attn16_tc_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_consta
         mbar_wait(&v_full[s], (j / kStages) & 1);
         mbar_wait(&p_ready[j & 1], (j >> 1) & 1);
         tc_fence_after();
+        astamp(1, j, 0);
         unsigned char* st = stage(s);
         const uint64_t dvh = G::desc(smem_u32(st + 2 * kTile)), dvl = G::desc(smem_u32(st + 3 * kTile));
         const uint32_t pb = tmem_base + kColS + 64u * (uint32_t)(j & 1);
@@ -600,6 +644,7 @@ attn16_tc_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_consta
         }
         umma_commit(&o_full[j & 1]);
         umma_commit(&v_empty[s]);
+        astamp(1, j, 1);
         // in-order execution of tcgen05.mma: S(j+2) overwrites the P(j) cells only after P @ V(j) has read them
         if (j + 2 < ntiles) issue_S(j + 2);
       }
@@ -609,6 +654,14 @@ attn16_tc_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_consta
   __syncthreads();
   if (warp == 5) tmem_dealloc(tmem_base, kTmemCols);
 }
+
+// CVAR_ATTN_ONE_PASS = 0 selects the round-1 two-read softmax (A/B timing); default 1
+static int initial_one_pass() {
+  const char* e = getenv("CVAR_ATTN_ONE_PASS");
+  return (e != nullptr && e[0] == '0') ? 0 : 1;
+}
+int g_one_pass = initial_one_pass();
+int set_trace(long long* p) { return cudaMemcpyToSymbol(g_attn16_trace, &p, sizeof(p)) == cudaSuccess ? 0 : -1; }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -677,7 +730,8 @@ extern "C" int cvar_attn_kvcache16(const void* q16_hi, const void* q16_lo, const
     if (!rc) rc = tcattn16::make_map3(&mvh, vh, T_max, 64, RH, 64);
     if (!rc) rc = tcattn16::make_map3(&mvl, vl, T_max, 64, RH, 64);
     if (rc) return rc;
-    auto kern = g_fast_mode ? tcattn16::attn16_tc_kernel<true> : tcattn16::attn16_tc_kernel<false>;
+    auto kern = g_fast_mode ? (tcattn16::g_one_pass ? tcattn16::attn16_tc_kernel<true, true> : tcattn16::attn16_tc_kernel<true, false>)
+                            : (tcattn16::g_one_pass ? tcattn16::attn16_tc_kernel<false, true> : tcattn16::attn16_tc_kernel<false, false>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tcattn16::kSmem);
     CVAR_REQUIRE(e == cudaSuccess, "cvar_attn_kvcache16: cannot raise shared memory: %s", cudaGetErrorString(e));
     dim3 grid(cdiv(l, tcattn16::BQ), H, R);

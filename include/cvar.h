@@ -69,7 +69,7 @@ CVAR_API int cvar_set_tc_kblock(int bk);
 /* Diagnostics: device buffer of 4*64*2 int64 that CTA 0 of the tcgen05 engine fills with clock64() stamps of its
  * pipeline hand-overs (NULL switches the trace off). */
 CVAR_API int cvar_debug_set_trace(long long* dev_buf);
-/* Same for the tensor-core attention kernel: 2*32*8 int64, CTA (0,0,0), per KV tile (NULL switches it off). */
+/* Same for the tensor-core attention kernels: 3*32*8 int64, CTA (0,0,0), per KV tile (NULL switches it off). */
 CVAR_API int cvar_debug_set_attn_trace(long long* dev_buf);
 
 /* ---- prologue: control_var.py:381-383, 399-409 -------------------------------------------------------------

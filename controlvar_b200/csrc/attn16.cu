@@ -566,7 +566,7 @@ attn16_tc_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_consta
     }
   } else if (warp == 4) {
     // ================================================================ TMA: the Q tile once, then K / V^T tiles
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_arrive_expect_tx(q_full, (uint32_t)((kFast ? 1 : 2) * kQTile));
       tma_load_3d(&mapQhi, q_full, q_s, 0, q0, rh);
       if (!kFast) tma_load_3d(&mapQlo, q_full, q_s + kQTile, 0, q0, rh);
@@ -588,7 +588,7 @@ attn16_tc_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_consta
     }
   } else {
     // ================================================================ MMA issue
-    if (lane == 0) {
+    if (elect_one()) {
       const uint64_t dqh = G::desc(smem_u32(q_s)), dql = G::desc(smem_u32(q_s + kQTile));
       // S(j) = Q K(j)^T into buffer j & 1: ONE accumulator.  The cross terms (~2^-11 of the result) go first, while the
       // accumulator is small, so that the tensor core's truncation after every MMA acts on the big sum only during the
@@ -655,10 +655,11 @@ attn16_tc_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_consta
   if (warp == 5) tmem_dealloc(tmem_base, kTmemCols);
 }
 
-// CVAR_ATTN_ONE_PASS = 0 selects the round-1 two-read softmax (A/B timing); default 1
+// CVAR_ATTN_ONE_PASS = 1 selects the one-read softmax variant (A/B timing).  Default 0: measured SLOWER (2.31 vs 2.06 ms at
+// the last scale, profiles/r02_attn16.md) - with the running output row (64 registers) the 64 S registers spill.
 static int initial_one_pass() {
   const char* e = getenv("CVAR_ATTN_ONE_PASS");
-  return (e != nullptr && e[0] == '0') ? 0 : 1;
+  return (e != nullptr && e[0] == '1') ? 1 : 0;
 }
 int g_one_pass = initial_one_pass();
 int set_trace(long long* p) { return cudaMemcpyToSymbol(g_attn16_trace, &p, sizeof(p)) == cudaSuccess ? 0 : -1; }

@@ -55,7 +55,7 @@ constexpr int kStages = 3;
 constexpr int kStagingBytes = kEpiWarps * 32 * kStagePitch * 4;
 constexpr int kSmem = kStages * kStageBytes + kStagingBytes + 1024 + 1024;
 constexpr uint32_t kPeerMask = 0xFEFFFFFFu;          // clears the CTA-rank bit of a shared::cluster address (leader's copy)
-constexpr int kGroupM = 32;                          // pair-tiles (256 rows) per rasterisation group: A of a group (8192 rows x K pairs = 50 MB at K = 1536) stays in L2 while its weight strips pass; 16 re-read the weights twice as often
+constexpr int kGroupM = 4;                           // pair-tiles (256 rows) per rasterisation group.  Small on purpose: every GEMM weight of the model (<= 38 MB as an FP16 pair at d24) fits in L2 next to the A rows of one group, so the weights stay resident and A streams through once; 16 / 32 (A of a group = 25 / 50 MB) thrashed the ~60 MB a die's L2 effectively holds: 2.2 / 3.1 GB of DRAM reads on fc1 against 0.44 GB of operands
 
 // Optional tile trace (diagnostics, cvar_debug_set_trace): CTA 0 stamps clock64() for its first 64 tiles.
 // trace[tile * 8 + ev]: 0 MMA thread has tensor memory (tm_empty seen), 1 last MMA of the tile committed,
@@ -522,7 +522,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constan
     }
   } else if (warp == kTmaWarp) {
     // ================================================================ TMA: own A rows, own half of the weight rows
-    if (lane == 0) {
+    if (elect_one()) {
       int it = 0;
       for (int tile = pair; tile < total_tiles; tile += npairs) {
         int mt, nt;
@@ -545,7 +545,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constan
     }
   } else if (rank == 0) {
     // ================================================================ MMA issue (leader CTA only)
-    if (lane == 0) {
+    if (elect_one()) {
       int it = 0, tcount = 0;
       for (int tile = pair; tile < total_tiles; tile += npairs, ++tcount) {
         mbar_wait(tm_empty, (tcount & 1) ^ 1);
@@ -677,7 +677,7 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constan
     }
   } else if (warp == kTmaWarp) {
     // ================================================================ TMA: this CTA's 128 pixels (shifted window per tap)
-    if (lane == 0) {
+    if (elect_one()) {
       const int pad = g.ks >> 1;
       const long long HW = (long long)g.H * g.W;
       const uint32_t stage_tx = (kFast ? 1u : 2u) * (2u * (uint32_t)kCvTile + 2u * (uint32_t)(BNr / 2) * 64u);   // both CTAs
@@ -708,7 +708,7 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constan
     }
   } else if (rank == 0) {
     // ================================================================ MMA issue (leader CTA only)
-    if (lane == 0) {
+    if (elect_one()) {
       int it = 0, tcount = 0;
       for (int tile = pair; tile < total_tiles; tile += npairs, ++tcount) {
         mbar_wait(tm_empty, (tcount & 1) ^ 1);

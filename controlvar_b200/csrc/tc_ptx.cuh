@@ -10,6 +10,17 @@ namespace tc {
 // ------------------------------------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One elected lane of a CONVERGED warp (elect.sync).  The single-thread roles (TMA issue, MMA issue) must be entered with
+// this, not with `lane == 0`: tcgen05.mma / cp.async.bulk.tensor take their operands from UNIFORM registers, and for a branch
+// on `lane == 0` ptxas cannot tell that one thread is active - it wraps every such instruction in a leader-election loop
+// (ELECT, R2UR.BROADCAST, BRA.U.ANY: ~10 extra instructions and ~100 cycles per MMA, measured with the attention phase
+// trace: 12 MMAs took 1050-1230 cycles to ISSUE, profiles/r02_attn16.md).  After elect.sync the MMAs issue back to back.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }

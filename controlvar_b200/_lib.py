@@ -78,6 +78,7 @@ PROTOTYPES = {
                                     C.c_float, C.c_int, C.c_void_p]),
     "cvar_qkv_project16": (C.c_int, [c_f] * 13 + [C.c_int] * 6 + [c_f, C.c_void_p]),
     "cvar_attn_kvcache16": (C.c_int, [c_f] * 9 + [C.c_int] * 5 + [C.c_float, C.c_int, C.c_void_p]),
+    "cvar_attn_blockcausal16": (C.c_int, [c_f] * 9 + [C.c_int] * 4 + [C.c_float, C.c_int, C.POINTER(C.c_int), C.c_void_p]),
     "cvar_cfg_sample": (C.c_int, [c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_double,
                                   C.c_void_p]),
     "cvar_cfg_sample_multi": (C.c_int, [c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int,

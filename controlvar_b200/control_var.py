@@ -110,6 +110,9 @@ class ControlVAR(nn.Module):
         # where kernels are shorter than a launch (the five small scales, small batches, 8 ranks sharing one host).
         # Inputs of a replay: labels / condition types / forced tokens (copied into static buffers) and the Exp(1) noise,
         # drawn from the caller's generator BEFORE the replay in the same order as the eager path (bit-identical tokens).
+        # forward(): one masked full-sequence pass (True, engine 4) or the scales one after the other against the growing
+        # KV cache (False; also what the other engines do) - the same numbers (tests compare them)
+        self.forward_single_pass = True
         self.use_graphs = os.environ.get("CVAR_GRAPHS", "1") != "0"
         self._graphs: Dict[Tuple, dict] = {}
         self._ws_gen = 0                                  # bumped whenever a workspace is (re)allocated: graphs hold pointers
@@ -500,16 +503,18 @@ class ControlVAR(nn.Module):
         self.last_f_hat = f_hat
         return img
 
-    def _transformer(self, R: int) -> "_Transformer":
-        return _Transformer(self, R)
+    def _transformer(self, R: int, lmax: Optional[int] = None) -> "_Transformer":
+        return _Transformer(self, R, lmax)
 
     # ----------------------------------------------------------------------------------- teacher-forced pass
     @torch.no_grad()
     def forward(self, label_B: torch.LongTensor, x_BLCv_wo_first_l: torch.Tensor, cond_type, mask_first=True) -> torch.Tensor:
         """Drop-in for ControlVAR.forward (control_var.py:566-651), inference only: logits (B, L, V) of the teacher-forced
-        token pyramid.  The block-causal mask of control_var.py:168 (a query sees the keys of its own and of all coarser
-        scales) is realised without a mask: the scales are run one after the other against the growing KV cache, which
-        is the same computation (SURVEY.md section 4 identity; tests/test_oracle_golden.py checks it on the oracle).
+        token pyramid under the block-causal mask of control_var.py:168 (a query sees the keys of its own and of all
+        coarser scales).  Default (engine 4): ONE full-sequence pass like the reference's, the mask applied inside a single
+        attention launch per block (cvar_attn_blockcausal16); ``forward_single_pass = False`` (and the other engines) runs
+        the scales one after the other against the growing KV cache, which is the same computation (SURVEY.md section 4
+        identity; tests/test_oracle_golden.py checks it on the oracle, tests/test_gpu_conditional.py compares the two).
         As in the reference, labels and condition types are dropped with probability cond_drop_rate by torch.rand draws
         even in eval mode (:577, :584): set ``cond_drop_rate = 0`` for deterministic logits."""
         if not self.pos_1LC.is_cuda:
@@ -528,11 +533,29 @@ class ControlVAR(nn.Module):
         label_B = torch.where(torch.rand(B, device=dev) < self.cond_drop_rate, self.num_classes, label_B)      # :577
         cond_type = torch.where(torch.rand(B, device=dev) < self.cond_drop_rate, 4, cond_type)                # :584
         xin = x_BLCv_wo_first_l.to(device=dev, dtype=torch.float32).contiguous()
+        ww, wb = self.get_parameter("word_embed.weight"), self.get_parameter("word_embed.bias")
+        Lin = self.L - self.first_l
+        single_pass = (self.forward_single_pass and ops.get_gemm_engine() == ops.ENGINE_TC_F16X3 and self.kv16)
+        if single_pass:
+            # ONE masked full-sequence pass, as the reference runs it (:622-636): every dense layer sees all B*L rows, the
+            # block-causal mask (:168, query level >= key level) is applied inside one attention launch per block
+            # (cvar_attn_blockcausal16: the mask is a per-scale key limit, no L x L bias tensor is built or read).
+            L = self.L
+            tr = self._transformer(B, lmax=L)
+            x0 = self._buf("fwd_x0", (B * self.first_l, C))
+            ops.prologue_rows(self.get_parameter("class_emb.weight"), self.get_parameter("cond_embed.weight"), self.pos_start,
+                              tr.lvl_pos, label_B.contiguous(), cond_type.contiguous(), tr.cond_BD, tr.silu_cond, x0)
+            tr.prologue_ada()
+            xv = tr.x[:B * L].view(B, L, C)
+            xv[:, :self.first_l].copy_(x0.view(B, self.first_l, C))
+            # x = word_embed(teacher tokens) + (lvl_embed + pos_1LC) for every later token: one batched K = 32 GEMM (:616-618)
+            ops.gemm(xin, ww, wb, xv[:, self.first_l:], Lin, C, Cvae, lda=Cvae, epilogue=ops.EPI_BIAS_RESID,
+                     resid=tr.lvl_pos[self.first_l:], ldr=C, strideR=0, batch=B, strideA=Lin * Cvae, strideW=0, strideO=L * C)
+            tr.scale(L, 0, block_causal_lens=self.cfg.scale_lens)
+            return tr.logits[:B * L].view(B, L, V).clone()
         tr = self._transformer(B)
         tr.prologue(label_B.contiguous(), cond_type.contiguous())
         out = torch.empty(B, self.L, V, device=dev, dtype=torch.float32)
-        ww, wb = self.get_parameter("word_embed.weight"), self.get_parameter("word_embed.bias")
-        Lin = self.L - self.first_l
         cur_L = 0
         for si, l in enumerate(self.cfg.scale_lens):
             if si > 0:
@@ -552,11 +575,13 @@ class _Transformer:
     """Workspaces and launch sequence of the AdaLN transformer for R rows (the part autoregressive_infer_cfg,
     conditional_infer_cfg and forward share): prologue -> per scale, depth x AdaLNSABlock + head -> logits."""
 
-    def __init__(self, m: "ControlVAR", R: int):
+    def __init__(self, m: "ControlVAR", R: int, lmax: Optional[int] = None):
+        """lmax: rows per sample the workspaces must hold (default: the longest scale; the whole pyramid for the
+        single-pass teacher-forced forward)."""
         self.m, self.R = m, R
         cst = self.cst = m._constants()
         C, H, depth, V, T = m.C, m.num_heads, m.depth, m.V, m.L
-        lmax = max(m.cfg.scale_lens)
+        lmax = max(m.cfg.scale_lens) if lmax is None else lmax
         self.lvl_pos = cst["lvl_pos"]
         # ---- workspaces (cached across calls)
         self.cond_BD = m._buf("cond_BD", (R, C))
@@ -589,13 +614,20 @@ class _Transformer:
         ops.prologue_rows(m.get_parameter("class_emb.weight"),
                           m.get_parameter("cond_embed.weight") if m.multi_cond else None, m.pos_start,
                           self.lvl_pos, label_R, cond_R, self.cond_BD, self.silu_cond, self.x)
+        self.prologue_ada()
+
+    def prologue_ada(self) -> None:
+        """Every ada_lin = Linear(SiLU(cond)) of the call (silu_cond must be filled)."""
+        m, R, C, cst = self.m, self.R, self.m.C, self.cst
         silu16 = ops.F16Pair.from_tensor(self.silu_cond, out=m._pair("silu16", (R, C))) if self.f16 else None
         for bi, blk in enumerate(cst["blocks"]):
             ops.gemm(self.silu_cond, blk["ada_w"], blk["ada_b"], self.ada[bi], R, 6 * C, C, A16=silu16)
         ops.gemm(self.silu_cond, cst["head_ada_w"], cst["head_ada_b"], self.ada_head, R, 2 * C, C)
 
-    def scale(self, l: int, L_prev: int) -> None:
-        """x (R*l, C) of one scale through all blocks (keys / values appended at L_prev) and the head -> self.logits."""
+    def scale(self, l: int, L_prev: int, block_causal_lens=None) -> None:
+        """x (R*l, C) of one scale through all blocks (keys / values appended at L_prev) and the head -> self.logits.
+        block_causal_lens: x holds the WHOLE pyramid (l = sum of the lens, L_prev = 0) and attention runs under the
+        block-causal mask in one launch per block (cvar_attn_blockcausal16) - the single-pass ControlVAR.forward."""
         m, R, cst = self.m, self.R, self.cst
         C, H, V = m.C, m.num_heads, m.V
         M, cur_L = R * l, L_prev + l
@@ -610,7 +642,10 @@ class _Transformer:
             if self.kv16:
                 ops.qkv_project16(xn16, blk["qkv_w"], blk["q_bias"], blk["k_bias"], blk["v_bias"], self.q16,
                                   self.caches[bi], R, l, L_prev, H, m.cos_attn, blk["scale_mul"])
-                ops.attn_kvcache16(self.q16, self.caches[bi], None, R, H, l, cur_L, attn_scale, out16=attn_o16)
+                if block_causal_lens is not None:
+                    ops.attn_blockcausal16(self.q16, self.caches[bi], None, R, H, block_causal_lens, attn_scale, out16=attn_o16)
+                else:
+                    ops.attn_kvcache16(self.q16, self.caches[bi], None, R, H, l, cur_L, attn_scale, out16=attn_o16)
             else:
                 ops.qkv_project(xn, blk["qkv_w"], blk["q_bias"], blk["k_bias"], blk["v_bias"], self.qbuf, self.caches[bi],
                                 R, l, L_prev, H, m.cos_attn, blk["scale_mul"], A_lo=xn_lo, A16=xn16)

@@ -308,6 +308,18 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 
 // kFast (cvar_set_fast_mode; NOT a parity mode): hi halves only - one MMA per product, no P residual, half the K / V^T bytes.
+// Block-causal full-sequence pass (ControlVAR.forward, control_var.py:158-198, 622-636: a query of scale s sees the keys of
+// scales <= s): the mask is a step function of the query's scale, so it needs no L x L tensor - the launch carries a table
+// of query tiles {first query, number of queries, number of visible keys}, one CTA column per tile; a tile never straddles
+// two scales.  n == 0: the plain KV-cache launch (tile bx = queries [128 bx, 128 bx + 128), all L keys).
+constexpr int kMaxSegTiles = 40;
+struct AttnSegs {
+  int n;
+  int q0[kMaxSegTiles];
+  int nq[kMaxSegTiles];
+  int L[kMaxSegTiles];
+};
+
 // kOnePass: S(j) is read from tensor memory ONCE (64 registers) and the P pass runs out of those registers; the round-1
 // kernel read it twice (row maximum, then 16-column chunks).  Tensor-memory reads are ~95 B/clk per SM (measured on the GEMM
 // drain, profiles/r02_gemm_epilogue.md): the second read of the 32 KB S tile cost ~340 cycles of that port per CTA and
@@ -317,8 +329,8 @@ __global__ void __launch_bounds__(kThreads, 2)
 attn16_tc_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_constant__ CUtensorMap mapQlo,
                  const __grid_constant__ CUtensorMap mapKhi, const __grid_constant__ CUtensorMap mapKlo,
                  const __grid_constant__ CUtensorMap mapVhi, const __grid_constant__ CUtensorMap mapVlo,
-                 float* __restrict__ out, __half* __restrict__ o16_hi, __half* __restrict__ o16_lo, int H, int l, int L,
-                 float scale) {
+                 float* __restrict__ out, __half* __restrict__ o16_hi, __half* __restrict__ o16_lo, int H, int l, int L_all,
+                 float scale, const __grid_constant__ AttnSegs segs) {
   using G = Geo<32>;          // 128-byte rows, SWIZZLE_128B: 64 halves per row
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -342,7 +354,10 @@ attn16_tc_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_consta
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 * kStages + 7);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * BQ, h = blockIdx.y, r = blockIdx.z;
+  const int h = blockIdx.y, r = blockIdx.z;
+  const int q0 = segs.n > 0 ? segs.q0[blockIdx.x] : blockIdx.x * BQ;
+  const int q_end = segs.n > 0 ? q0 + segs.nq[blockIdx.x] : l;          // queries [q0, q_end) are this tile's to store
+  const int L = segs.n > 0 ? segs.L[blockIdx.x] : L_all;                // keys this tile sees
   const int rh = r * H + h;
   const int ntiles = (L + BKV - 1) / BKV;
 
@@ -552,7 +567,7 @@ attn16_tc_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_consta
       float a[16], b[16];
       tmem_ld_32x32b_x16(tl + kColO + 16 * c, a);
       if (!kFast) tmem_ld_32x32b_x16(tl + kColOx + 16 * c, b);
-      if (t < l) {
+      if (t < q_end) {
 #pragma unroll
         for (int i = 0; i < 16; i += 4) {
           float vv[4];
@@ -700,6 +715,29 @@ static int make_map3(CUtensorMap* map, const void* base, long long inner, long l
 }
 }  // namespace tcattn16
 
+static int launch_attn16_tc(const __half* qh, const __half* ql, const __half* kh, const __half* kl, const __half* vh,
+                            const __half* vl, float* out, __half* o16h, __half* o16l, int R, int H, int l, int L, int T_max,
+                            float scale, const tcattn16::AttnSegs& segs, cudaStream_t stream, const char* name) {
+  CUtensorMap mqh, mql, mkh, mkl, mvh, mvl;
+  const long long RH = (long long)R * H;
+  int rc = tcattn16::make_map3(&mqh, qh, 64, l, RH, tcattn16::BQ);
+  if (!rc) rc = tcattn16::make_map3(&mql, ql, 64, l, RH, tcattn16::BQ);
+  if (!rc) rc = tcattn16::make_map3(&mkh, kh, 64, T_max, RH, tcattn16::BKV);
+  if (!rc) rc = tcattn16::make_map3(&mkl, kl, 64, T_max, RH, tcattn16::BKV);
+  if (!rc) rc = tcattn16::make_map3(&mvh, vh, T_max, 64, RH, 64);
+  if (!rc) rc = tcattn16::make_map3(&mvl, vl, T_max, 64, RH, 64);
+  if (rc) return rc;
+  auto kern = g_fast_mode ? (tcattn16::g_one_pass ? tcattn16::attn16_tc_kernel<true, true> : tcattn16::attn16_tc_kernel<true, false>)
+                          : (tcattn16::g_one_pass ? tcattn16::attn16_tc_kernel<false, true> : tcattn16::attn16_tc_kernel<false, false>);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tcattn16::kSmem);
+  CVAR_REQUIRE(e == cudaSuccess, "%s: cannot raise shared memory: %s", name, cudaGetErrorString(e));
+  dim3 grid(segs.n > 0 ? segs.n : cdiv(l, tcattn16::BQ), H, R);
+  kern<<<grid, tcattn16::kThreads, tcattn16::kSmem, stream>>>(mqh, mql, mkh, mkl, mvh, mvl, out, o16h, o16l, H, l, L, scale,
+                                                               segs);
+  CVAR_CHECK_LAUNCH(name);
+  return 0;
+}
+
 extern "C" int cvar_attn_kvcache16(const void* q16_hi, const void* q16_lo, const void* k16_hi, const void* k16_lo,
                                    const void* vt16_hi, const void* vt16_lo, float* out, void* out16_hi, void* out16_lo,
                                    int R, int H, int l, int L, int T_max, float scale, int engine, void* stream) {
@@ -722,24 +760,10 @@ extern "C" int cvar_attn_kvcache16(const void* q16_hi, const void* q16_lo, const
   // profiles/r01_attn16.md); below that the SIMT kernel
   if (engine < 0) engine = (g_gemm_engine != 0 && l >= 32) ? 1 : 0;
   if (engine == 1) {
-    CUtensorMap mqh, mql, mkh, mkl, mvh, mvl;
-    const long long RH = (long long)R * H;
-    int rc = tcattn16::make_map3(&mqh, qh, 64, l, RH, tcattn16::BQ);
-    if (!rc) rc = tcattn16::make_map3(&mql, ql, 64, l, RH, tcattn16::BQ);
-    if (!rc) rc = tcattn16::make_map3(&mkh, kh, 64, T_max, RH, tcattn16::BKV);
-    if (!rc) rc = tcattn16::make_map3(&mkl, kl, 64, T_max, RH, tcattn16::BKV);
-    if (!rc) rc = tcattn16::make_map3(&mvh, vh, T_max, 64, RH, 64);
-    if (!rc) rc = tcattn16::make_map3(&mvl, vl, T_max, 64, RH, 64);
-    if (rc) return rc;
-    auto kern = g_fast_mode ? (tcattn16::g_one_pass ? tcattn16::attn16_tc_kernel<true, true> : tcattn16::attn16_tc_kernel<true, false>)
-                            : (tcattn16::g_one_pass ? tcattn16::attn16_tc_kernel<false, true> : tcattn16::attn16_tc_kernel<false, false>);
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tcattn16::kSmem);
-    CVAR_REQUIRE(e == cudaSuccess, "cvar_attn_kvcache16: cannot raise shared memory: %s", cudaGetErrorString(e));
-    dim3 grid(cdiv(l, tcattn16::BQ), H, R);
-    kern<<<grid, tcattn16::kThreads, tcattn16::kSmem, (cudaStream_t)stream>>>(mqh, mql, mkh, mkl, mvh, mvl, out, o16h, o16l,
-                                                                               H, l, L, scale);
-    CVAR_CHECK_LAUNCH("cvar_attn_kvcache16[tc]");
-    return 0;
+    tcattn16::AttnSegs segs;
+    segs.n = 0;
+    return launch_attn16_tc(qh, ql, kh, kl, vh, vl, out, o16h, o16l, R, H, l, L, T_max, scale, segs, (cudaStream_t)stream,
+                            "cvar_attn_kvcache16[tc]");
   }
   cudaError_t e = cudaFuncSetAttribute(attn16_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)sizeof(AttnSmem));
@@ -749,4 +773,41 @@ extern "C" int cvar_attn_kvcache16(const void* q16_hi, const void* q16_lo, const
                                                                            L, T_max, scale);
   CVAR_CHECK_LAUNCH("cvar_attn_kvcache16");
   return 0;
+}
+
+// Block-causal attention over a whole token pyramid in ONE launch (ControlVAR.forward): scale s holds host_scale_lens[s]
+// consecutive queries and sees the keys of scales 0..s.  q16 (R, H, l_total, 64) and the caches as cvar_qkv_project16 wrote
+// them with L_prev = 0, l = l_total.
+extern "C" int cvar_attn_blockcausal16(const void* q16_hi, const void* q16_lo, const void* k16_hi, const void* k16_lo,
+                                       const void* vt16_hi, const void* vt16_lo, float* out, void* out16_hi, void* out16_lo,
+                                       int R, int H, int l_total, int T_max, float scale, int n_scales,
+                                       const int* host_scale_lens, void* stream) {
+  CVAR_REQUIRE(q16_hi && q16_lo && k16_hi && k16_lo && vt16_hi && vt16_lo, "cvar_attn_blockcausal16: null operand");
+  CVAR_REQUIRE(out != nullptr || out16_hi != nullptr, "cvar_attn_blockcausal16: no output");
+  CVAR_REQUIRE((out16_hi == nullptr) == (out16_lo == nullptr), "cvar_attn_blockcausal16: out16_hi/out16_lo must come together");
+  CVAR_REQUIRE(g_gemm_engine != 0, "cvar_attn_blockcausal16: needs a tensor-core engine (engine is 0 = SIMT)");
+  CVAR_REQUIRE(R > 0 && H > 0 && R <= 65535 && H <= 65535 && n_scales > 0 && host_scale_lens != nullptr && l_total <= T_max &&
+                   T_max % 8 == 0,
+               "cvar_attn_blockcausal16: bad shape R=%d H=%d l=%d T=%d scales=%d", R, H, l_total, T_max, n_scales);
+  tcattn16::AttnSegs segs;
+  segs.n = 0;
+  int start = 0;
+  for (int s = 0; s < n_scales; ++s) {
+    const int ls = host_scale_lens[s];
+    CVAR_REQUIRE(ls > 0, "cvar_attn_blockcausal16: scale %d has no tokens", s);
+    for (int q = 0; q < ls; q += tcattn16::BQ) {
+      CVAR_REQUIRE(segs.n < tcattn16::kMaxSegTiles, "cvar_attn_blockcausal16: more than %d query tiles", tcattn16::kMaxSegTiles);
+      segs.q0[segs.n] = start + q;
+      segs.nq[segs.n] = ls - q < tcattn16::BQ ? ls - q : tcattn16::BQ;
+      segs.L[segs.n] = start + ls;
+      ++segs.n;
+    }
+    start += ls;
+  }
+  CVAR_REQUIRE(start == l_total, "cvar_attn_blockcausal16: scale lengths sum to %d, not l_total = %d", start, l_total);
+  return launch_attn16_tc(reinterpret_cast<const __half*>(q16_hi), reinterpret_cast<const __half*>(q16_lo),
+                          reinterpret_cast<const __half*>(k16_hi), reinterpret_cast<const __half*>(k16_lo),
+                          reinterpret_cast<const __half*>(vt16_hi), reinterpret_cast<const __half*>(vt16_lo), out,
+                          reinterpret_cast<__half*>(out16_hi), reinterpret_cast<__half*>(out16_lo), R, H, l_total, l_total, T_max,
+                          scale, segs, (cudaStream_t)stream, "cvar_attn_blockcausal16");
 }

@@ -327,6 +327,24 @@ def attn_kvcache16(q16: F16Pair, cache: KVCache16, out, R, H, l, L, scale, engin
     return out if out is not None else out16
 
 
+def attn_blockcausal16(q16: F16Pair, cache: KVCache16, out, R, H, scale_lens, scale, out16: Optional[F16Pair] = None):
+    """Block-causal attention over the whole pyramid in one launch (ControlVAR.forward); scale_lens: tokens per scale."""
+    _chk(out)
+    o16h, o16l = _p16(out16)
+    lens = [int(x) for x in scale_lens]
+    arr = (C.c_int * len(lens))(*lens)
+    l_total = sum(lens)
+    flops, L = 0.0, 0
+    for ls in lens:
+        L += ls
+        flops += 4.0 * ls * L * 64
+    with _Timed("attn", flops * R * H, (2.0 * l_total + 2.0 * l_total) * 64 * 4 * R * H):
+        check(_lib.load().cvar_attn_blockcausal16(_p(q16.hi), _p(q16.lo), _p(cache.k_hi), _p(cache.k_lo), _p(cache.vt_hi),
+                                                  _p(cache.vt_lo), _p(out), o16h, o16l, R, H, l_total, cache.T, float(scale),
+                                                  len(lens), arr, _stream()), "cvar_attn_blockcausal16")
+    return out if out is not None else out16
+
+
 def qkv_project(A, Wqkv, q_bias, k_bias, v_bias, q_out, cache: KVCache, R, l, L_prev, H, cos_attn, scale_mul_H,
                 A_lo=None, A16: Optional[F16Pair] = None):
     Wqkv, W_hi, W_lo, W16 = _wparts(Wqkv)

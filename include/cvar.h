@@ -185,6 +185,17 @@ CVAR_API int cvar_attn_kvcache16(const void* q16_hi, const void* q16_lo, const v
                         const void* vt16_hi, const void* vt16_lo, float* out, void* out16_hi, void* out16_lo,
                         int R, int H, int l, int L, int T_max, float scale, int engine, void* stream);
 
+/* cvar_attn_blockcausal16: the block-causal full-sequence pass of ControlVAR.forward (control_var.py:158-198, 622-636, the
+ * released mask: a query of scale s attends to the keys of scales 0..s) in ONE launch on the tcgen05 kernel above.  The
+ * mask is a step function of the query's scale, so no L x L bias tensor exists: the launch carries a table of query tiles
+ * (first query, count, visible keys).  q16 (R, H, l_total, 64) and the caches hold the whole pyramid, as written by
+ * cvar_qkv_project16 with L_prev = 0, l = l_total.  host_scale_lens: n_scales ints on the HOST, summing to l_total.
+ * out / out16 as cvar_attn_kvcache16.  Not the 'indep' / 'separate_decoding' masks (no released configuration). */
+CVAR_API int cvar_attn_blockcausal16(const void* q16_hi, const void* q16_lo, const void* k16_hi, const void* k16_lo,
+                            const void* vt16_hi, const void* vt16_lo, float* out, void* out16_hi, void* out16_lo,
+                            int R, int H, int l_total, int T_max, float scale, int n_scales, const int* host_scale_lens,
+                            void* stream);
+
 /* ---- CFG + top-k/top-p + multinomial(1): control_var.py:501-505, helpers.py:6-19 -----------------------------
  * logits (2B, l, V): rows [0,B) conditional, [B,2B) unconditional.  v = (1+t)*lc - t*lu; top-k keeps v >= k-th
  * largest (ties kept); top-p removes the ascending-sorted prefix whose softmax mass is <= 1-top_p (the largest is

@@ -187,3 +187,28 @@ def test_attn16_last_scale_shape_two_ctas_per_sm(scale, qmul):
     s_max = 8.0 * qmul * 8.0 * scale * 4          # |q||k| ~ 8 * 8 per unit qmul, a few sigma
     print(f"\n[attn16-load] scale {scale:.3f} qmul {qmul}: max |tcgen05 - SIMT| = {err:.2e}")
     assert err < max(2e-6, 4e-7 * s_max)
+
+
+@pytest.mark.parametrize("pns,R,H", [((1, 2, 3, 4, 5, 6, 8, 10, 13, 16), 2, 3), ((1, 2, 3), 3, 2), ((1, 2, 3, 4, 5, 6, 8, 10), 1, 1)])
+def test_attn16_block_causal_one_launch(pns, R, H):
+    """cvar_attn_blockcausal16: the whole pyramid in one launch, a query of scale s seeing the keys of scales <= s
+    (control_var.py:168) - against fp64 SDPA with the explicit boolean mask."""
+    lens = [2 * p * p for p in pns]
+    L = sum(lens)
+    torch.manual_seed(L)
+    q, k, v = torch.randn(R, H, L, 64) * 2, torch.randn(R, H, L, 64), torch.randn(R, H, L, 64)
+    lvl = torch.cat([torch.full((n,), i) for i, n in enumerate(lens)])
+    mask = lvl.view(L, 1) >= lvl.view(1, L)
+    scale = 1 / 32
+    ref = F.scaled_dot_product_attention(q.double(), k.double(), v.double(), attn_mask=mask, scale=scale)
+    ref = ref.transpose(1, 2).reshape(R, L, H * 64)
+    kv = ops.KVCache16(R, H, L, DEV)
+    fill_cache(kv, k, v, L)
+    out = torch.full((R, L, H * 64), float("nan"), device=DEV)
+    o16 = ops.F16Pair.empty((R, L, H * 64), DEV)
+    ops.attn_blockcausal16(pair_qk(q), kv, out, R, H, lens, scale, out16=o16)
+    e = ((out.cpu().double() - ref).abs().max() / ref.abs().max()).item()
+    assert e < 2e-6, e
+    assert torch.equal(o16.float().cpu(), ops.F16Pair.from_tensor(out).float().cpu())
+    with pytest.raises(Exception):
+        ops.attn_blockcausal16(pair_qk(q), kv, out, R, H, lens[:-1], scale)          # lens must cover l_total

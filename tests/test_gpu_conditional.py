@@ -339,6 +339,33 @@ def test_forward_teacher_forced_matches_reference_golden(name):
     assert err < 1e-4 and err_all < 1e-4
 
 
+def test_forward_single_pass_equals_the_per_scale_passes():
+    """The one-launch block-causal pass (cvar_attn_blockcausal16, all B*L rows per dense layer) against the same model run
+    scale by scale on the growing KV cache: per-row arithmetic is identical except for the attention kernel chosen for the
+    scales shorter than 32 tokens (SIMT there, tensor cores here)."""
+    cfg = PathConfig(depth=3, patch_nums=(1, 2, 3, 4, 5, 6, 8, 10, 13, 16))
+    vae = VQVAE(ch=160, v_patch_nums=cfg.patch_nums)
+    var = build_control_var(vae, depth=cfg.depth, patch_nums=cfg.patch_nums, mask_type="interleave_append", multi_cond=True)
+    var.load_state_dict(W.synthetic_var_state_dict(cfg, 2))
+    var.to(DEV)
+    var.cond_drop_rate = 0.0
+    B = 3
+    x = g(W.synthetic_teacher_input(cfg, B, 4))
+    lab, ct = torch.tensor([5, 600, 1000]), torch.tensor([0, 3, 4])
+    assert var.forward_single_pass
+    n0 = ops.launch_count()
+    a = var(lab, x, ct)
+    n1 = ops.launch_count()
+    var.forward_single_pass = False
+    b = var(lab, x, ct)
+    n2 = ops.launch_count()
+    assert a.shape == b.shape == (B, cfg.L, cfg.vocab_size)
+    assert (a - b).abs().max().item() < 2e-5
+    assert (n1 - n0) * 5 < (n2 - n1)          # one pass: ~10x fewer launches than ten per-scale passes
+    ref = O.forward_teacher_forced(W.synthetic_var_state_dict(cfg, 2), cfg.patch_nums, cfg.depth, lab, x.cpu(), ct)
+    assert (a.cpu() - ref).abs().max().item() < 1e-4
+
+
 def test_forward_drops_conditions_like_the_reference():
     """cond_drop_rate = 1 replaces every label by the 'unconditional' class and every condition type by 4
     (control_var.py:577, 584), in eval mode too."""

@@ -253,6 +253,68 @@ __global__ void __launch_bounds__(128) conv3x3_small_cout_kernel(const float* __
   ep.store(m, 0, v4, COUT, 0);
 }
 
+// The same convolution for wide images (W a multiple of 128): the kernel above reads every input element 9 times through
+// L1 with one 640-byte-strided pixel per thread - 32 sectors per request, 12.5 ms for the 128 x 256 x 256 x 160 input of a
+// bench step against 0.8 ms of HBM time (ncu launch list, profiles/r02_launches_table.md).  Here a block of 256 threads owns
+// a 2 x 128 output tile; per 32-channel chunk the 4 x 130 halo is staged in shared memory with coalesced 16-byte loads
+// (pixel pitch 36 floats: conflict-free float4 reads) and read 9 times from there; every input element leaves L2 twice.
+// Summation order: channel chunks outermost (the kernel above: taps outermost) - fp32 results differ in the last bits.
+constexpr int kCoTH = 2, kCoTW = 128, kCoCh = 32, kCoPitch = 36;
+template <int COUT>
+__global__ void __launch_bounds__(kCoTH * kCoTW) conv3x3_small_cout_tiled_kernel(const float* __restrict__ x,
+                                                                                   const float* __restrict__ w, ConvEpilogue ep,
+                                                                                   int H, int W, int Cin) {
+  extern __shared__ __align__(16) float smem_co[];
+  const int K = 9 * Cin;
+  float* w_s = smem_co;                                   // [COUT][9 * Cin]
+  float* tile = smem_co + COUT * K;                       // [kCoTH + 2][kCoTW + 2][kCoPitch]
+  const int tid = threadIdx.x;
+  for (int i = tid; i < COUT * K / 4; i += blockDim.x) reinterpret_cast<float4*>(w_s)[i] = ld4(w + 4 * i);
+  const int x0 = blockIdx.x * kCoTW, y0 = blockIdx.y * kCoTH;
+  const long long n = blockIdx.z;
+  const int ty = tid / kCoTW, px = tid - ty * kCoTW;
+  float acc[COUT];
+#pragma unroll
+  for (int c = 0; c < COUT; ++c) acc[c] = 0.f;
+  constexpr int kHaloVec = (kCoTH + 2) * (kCoTW + 2) * (kCoCh / 4);
+  for (int c0 = 0; c0 < Cin; c0 += kCoCh) {
+    __syncthreads();                                      // previous chunk consumed (and w_s filled, first time round)
+    for (int i = tid; i < kHaloVec; i += kCoTH * kCoTW) {
+      const int c4 = i & (kCoCh / 4 - 1);
+      const int pp = i / (kCoCh / 4);
+      const int r = pp / (kCoTW + 2), p = pp - r * (kCoTW + 2);
+      const int yy = y0 - 1 + r, xx = x0 - 1 + p;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = ld4(x + ((n * H + yy) * W + xx) * Cin + c0 + c4 * 4);
+      *reinterpret_cast<float4*>(tile + (r * (kCoTW + 2) + p) * kCoPitch + c4 * 4) = v;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int tap = 0; tap < 9; ++tap) {
+      const int ky = tap / 3, kx = tap - 3 * ky;
+      const float* xs = tile + ((ty + ky) * (kCoTW + 2) + px + kx) * kCoPitch;
+      const float* wt = w_s + tap * Cin + c0;
+#pragma unroll
+      for (int c4 = 0; c4 < kCoCh / 4; ++c4) {
+        const float4 v = *reinterpret_cast<const float4*>(xs + c4 * 4);
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) {
+          const float4 ww = *reinterpret_cast<const float4*>(wt + c * K + c4 * 4);
+          acc[c] = fmaf(v.x, ww.x, acc[c]);
+          acc[c] = fmaf(v.y, ww.y, acc[c]);
+          acc[c] = fmaf(v.z, ww.z, acc[c]);
+          acc[c] = fmaf(v.w, ww.w, acc[c]);
+        }
+      }
+    }
+  }
+  float v4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int c = 0; c < COUT; ++c) v4[c] = acc[c];
+  const long long m = (n * H + (y0 + ty)) * W + x0 + px;
+  ep.store(m, 0, v4, COUT, 0);
+}
+
 extern "C" int cvar_conv2d(const cvar_conv_args* a, void* stream) {
   CVAR_REQUIRE(a != nullptr, "cvar_conv2d: null args");
   CVAR_REQUIRE(a->ks == 1 || a->ks == 3, "cvar_conv2d: ks must be 1 or 3");
@@ -284,6 +346,17 @@ extern "C" int cvar_conv2d(const cvar_conv_args* a, void* stream) {
       (size_t)3 * K * sizeof(float) <= 48 * 1024) {
     ConvEpilogue ep3{a->out, a->bias, nullptr, a->Cout, a->out_mode, Hout, Wout, a->out_rows_total, a->row_offset};
     ep3.out_samples = a->out_samples;
+    const size_t smem_t = ((size_t)3 * K + (size_t)(kCoTH + 2) * (kCoTW + 2) * kCoPitch) * sizeof(float);
+    if (Wout % kCoTW == 0 && Hout % kCoTH == 0 && a->Cin % kCoCh == 0 && a->B <= 65535 && smem_t <= 100 * 1024 &&
+        ((((uintptr_t)a->x) | ((uintptr_t)a->w)) & 15) == 0) {
+      auto kern = conv3x3_small_cout_tiled_kernel<3>;
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t);
+      CVAR_REQUIRE(e == cudaSuccess, "cvar_conv2d[cout3]: cannot raise shared memory: %s", cudaGetErrorString(e));
+      dim3 grid(Wout / kCoTW, Hout / kCoTH, a->B);
+      kern<<<grid, kCoTH * kCoTW, smem_t, s>>>(a->x, a->w, ep3, Hout, Wout, a->Cin);
+      CVAR_CHECK_LAUNCH("cvar_conv2d[cout3/tiled]");
+      return 0;
+    }
     conv3x3_small_cout_kernel<3><<<cdiv(M, 128), 128, (size_t)3 * K * sizeof(float), s>>>(a->x, a->w, ep3, Hout, Wout,
                                                                                          a->Cin, M);
     CVAR_CHECK_LAUNCH("cvar_conv2d[cout3]");

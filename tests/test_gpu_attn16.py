@@ -211,4 +211,4 @@ def test_attn16_block_causal_one_launch(pns, R, H):
     assert e < 2e-6, e
     assert torch.equal(o16.float().cpu(), ops.F16Pair.from_tensor(out).float().cpu())
     with pytest.raises(Exception):
-        ops.attn_blockcausal16(pair_qk(q), kv, out, R, H, lens[:-1], scale)          # lens must cover l_total
+        ops.attn_blockcausal16(pair_qk(q), kv, out, R, H, lens + [8], scale)         # more tokens than the cache holds

@@ -47,6 +47,7 @@ class ConvArgs(C.Structure):
         ("engine", C.c_int),
         ("x16_hi", C.c_void_p), ("x16_lo", C.c_void_p), ("w16_hi", C.c_void_p), ("w16_lo", C.c_void_p),
         ("downsample2x", C.c_int), ("ksplit", C.c_int), ("out_samples", C.c_int),
+        ("gn_part", C.c_void_p), ("gn_groups", C.c_int),
     ]
 
 
@@ -99,6 +100,8 @@ PROTOTYPES = {
     "cvar_repack_conv_weight": (C.c_int, [c_f, c_f, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "cvar_affine_nc": (C.c_int, [c_f, c_f, c_f, c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "cvar_conv2d_f16_supported": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "cvar_conv2d_gn_fusable": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "cvar_gn_finalize_parts": (C.c_int, [c_f, c_f, c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
     "cvar_upsample2x_split_f16": (C.c_int, [c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "cvar_softmax_rows": (C.c_int, [c_f, C.c_int, C.c_int, C.c_void_p]),
 }

@@ -18,6 +18,7 @@ int tc_conv_try(const cvar_conv_args* a, cudaStream_t s);
 int tc2_gemm_f16(const cvar_gemm_args* a, cudaStream_t s);
 int tc2_conv_f16(const cvar_conv_args* a, cudaStream_t s);
 int tc2_conv_f16_supported(int H, int W, int Cin, int Cout, int ks);
+int tc2_conv_f16_gn_fusable(int H, int W, int Cin, int Cout, int ks, int groups);
 int tc2_qkv_f16(const void* A_hi, const void* A_lo, const void* W_hi, const void* W_lo, const QkvEpilogue& ep, int M, int C,
                 cudaStream_t s);
 }  // namespace cvar
@@ -333,6 +334,7 @@ extern "C" int cvar_conv2d(const cvar_conv_args* a, void* stream) {
     return tc2_conv_f16(a, s);
   }
   CVAR_REQUIRE(a->x != nullptr && a->w != nullptr, "cvar_conv2d: null x / w");
+  CVAR_REQUIRE(a->gn_part == nullptr, "cvar_conv2d: gn_part is produced by the FP16-pair kernel only (x16_* operands)");
   if (g_gemm_engine != 0 && a->engine != 0 && a->w_hi != nullptr && a->w_lo != nullptr) {
     int took = tc_conv_try(a, s);
     if (took < 0) return took;
@@ -375,6 +377,9 @@ extern "C" int cvar_conv2d(const cvar_conv_args* a, void* stream) {
 
 extern "C" int cvar_conv2d_f16_supported(int H, int W, int Cin, int Cout, int ks) {
   return tc2_conv_f16_supported(H, W, Cin, Cout, ks);
+}
+extern "C" int cvar_conv2d_gn_fusable(int H, int W, int Cin, int Cout, int ks, int groups) {
+  return tc2_conv_f16_gn_fusable(H, W, Cin, Cout, ks, groups);
 }
 
 extern "C" int cvar_split_tf32(const float* w, float* w_hi, float* w_lo, long long n, void* stream) {

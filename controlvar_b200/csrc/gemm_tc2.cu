@@ -349,17 +349,38 @@ struct QkvRow {     // FP16-pair outputs only (cvar_qkv_project16)
   }
 };
 
+// one GroupNorm group of this warp's 32 pixels is complete: reduce over the lanes, lane 0 stores the partial
+__device__ __forceinline__ void gn_flush(double* dst, float s, float ss) {
+  s = warp_sum(s);
+  ss = warp_sum(ss);
+  if ((threadIdx.x & 31) == 0) {
+    dst[0] = (double)s;
+    dst[1] = (double)ss;
+  }
+}
+
 struct ConvRow {    // out_mode 0 (NHWC fp32): bias + optional residual, or the K-split continuation out += acc
   ConvEpilogue e;
   struct Ctx {
     long long off;
+    double* part;      // this warp's slot of group 0 of its image (gn_part only)
+    float s, ss;       // running sums of the group being crossed
+    int cnt;
   };
   __device__ __forceinline__ Ctx begin(long long m) const {
     Ctx c;
     c.off = m * e.Cout;
+    c.s = c.ss = 0.f;
+    c.cnt = 0;
+    c.part = nullptr;
+    if (e.gn_part != nullptr) {
+      const long long img = m / e.gn_HW;
+      const int slot = (int)(m - img * e.gn_HW) >> 5;
+      c.part = e.gn_part + ((img * e.gn_groups) * e.gn_slots + slot) * 2;
+    }
     return c;
   }
-  __device__ __forceinline__ void row16(const Ctx& c, int n, const float* v) const {
+  __device__ __forceinline__ void row16(Ctx& c, int n, const float* v) const {
     float r[16], x[16];
     if (e.accumulate) {
       ld16f_stream(e.out + c.off + n, x);
@@ -376,6 +397,20 @@ struct ConvRow {    // out_mode 0 (NHWC fp32): bias + optional residual, or the 
       }
     }
     st16f(e.out + c.off + n, r);
+    if (e.gn_part != nullptr) {
+      // GroupNorm statistics of what was just stored (the consumer's Normalize, vae_modules.py:18-19): the thread walks its
+      // row channel by channel, so groups complete in order; the branch is warp-uniform (all lanes are at the same channel)
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        c.s += r[j];
+        c.ss = fmaf(r[j], r[j], c.ss);
+        if (++c.cnt == e.gn_cpg) {
+          gn_flush(c.part + (long long)((n + j) / e.gn_cpg) * e.gn_slots * 2, c.s, c.ss);
+          c.s = c.ss = 0.f;
+          c.cnt = 0;
+        }
+      }
+    }
   }
 };
 
@@ -431,7 +466,7 @@ __device__ __forceinline__ void epilogue_tile_rows(const ROW& ep, uint32_t tcol,
   mbar_arrive_leader(tm_empty);                         // tensor memory is free: the next tile's MMAs may start
   if (threadIdx.x == 0) trace2(trace_tile, 3);
   if (m >= M) return;                                   // plain loads / stores below: no warp-collective operation
-  const typename ROW::Ctx ctx = ep.begin(m);
+  typename ROW::Ctx ctx = ep.begin(m);
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
     const int n = n_base + col0 + c * kEpiCols;
@@ -937,6 +972,14 @@ int tc2_conv_f16_supported(int H, int W, int Cin, int Cout, int ks) {
   if (H % Hb != 0) return 0;
   return 1;
 }
+// can the row epilogue of this layer emit GroupNorm partials?  whole groups inside each warp's column half, whole warps
+// inside an image
+int tc2_conv_f16_gn_fusable(int H, int W, int Cin, int Cout, int ks, int groups) {
+  if (!g_epi_overlap || !tc2_conv_f16_supported(H, W, Cin, Cout, ks)) return 0;
+  if (groups <= 0 || Cout % groups != 0 || Cout % 16 != 0 || (H * W) % 32 != 0) return 0;
+  const int bn = conv_f16_bn(Cout), cpg = Cout / groups;
+  return (bn / 2) % cpg == 0 && (bn / 2) % 16 == 0 ? 1 : 0;
+}
 int tc2_conv_f16(const cvar_conv_args* a, cudaStream_t s) {
   CVAR_REQUIRE(a->x16_hi && a->x16_lo && a->w16_hi && a->w16_lo, "cvar_conv2d[f16x3]: x16_hi/x16_lo/w16_hi/w16_lo must all be set");
   CVAR_REQUIRE(!a->upsample2x && a->in_a == nullptr,
@@ -960,6 +1003,9 @@ int tc2_conv_f16(const cvar_conv_args* a, cudaStream_t s) {
   if (rc) return rc;
   ConvEpilogue ep{a->out, a->bias, a->resid, a->Cout, a->out_mode, H, W, a->out_rows_total, a->row_offset};
   ep.out_samples = a->out_samples;
+  CVAR_REQUIRE(a->gn_part == nullptr || tc2_conv_f16_gn_fusable(H, W, a->Cin, a->Cout, a->ks, a->gn_groups),
+               "cvar_conv2d[f16x3]: gn_part set but this layer's epilogue cannot produce GroupNorm statistics "
+               "(cvar_conv2d_gn_fusable: H=%d W=%d Cout=%d groups=%d)", H, W, a->Cout, a->gn_groups);
   const bool rows = g_epi_overlap && a->out_mode == 0 && a->Cout % 16 == 0 && tc2::aligned32(a->out) &&
                     tc2::aligned32(a->bias) && tc2::aligned32(a->resid) && a->bias != nullptr;
   auto kern_staged = tc2::tc_conv2_kernel<ConvEpilogue>;
@@ -981,6 +1027,11 @@ int tc2_conv_f16(const cvar_conv_args* a, cudaStream_t s) {
     g.tap0 = part * g.ntaps;
     ConvEpilogue epp = ep;
     epp.accumulate = part > 0 ? 1 : 0;
+    if (a->gn_part != nullptr && part == nsplit - 1) {       // the launch that stores the final values
+      CVAR_REQUIRE(rows, "cvar_conv2d[f16x3]: gn_part needs the row epilogue (32-byte aligned out / bias / resid)");
+      epp.gn_part = a->gn_part, epp.gn_groups = a->gn_groups, epp.gn_cpg = a->Cout / a->gn_groups;
+      epp.gn_HW = H * W, epp.gn_slots = (H * W) / 32;
+    }
     if (rows)
       kern_rows<<<2 * pairs, tc2::kThreads, tc2::kCvSmem, s>>>(mah, mal, mbh, mbl, tc2::ConvRow{epp}, g, M, a->Cout, m_tiles,
                                                                 n_tiles);

@@ -345,6 +345,16 @@ extern "C" int cvar_gn_stats(const float* x_nhwc, const float* gamma, const floa
   return 0;
 }
 
+// GroupNorm coefficients from partials a convolution's epilogue wrote (cvar_conv_args.gn_part): the second stage of
+// cvar_gn_stats on (HW / 32) partials per (image, group) instead of cvar_gn_chunks(HW).  Fixed summation order.
+extern "C" int cvar_gn_finalize_parts(const double* gn_part, const float* gamma, const float* beta, float* a_out, float* b_out,
+                                      int B, int HW, int C, int groups, float eps, void* stream) {
+  CVAR_REQUIRE(gn_part != nullptr && C % groups == 0 && HW % 32 == 0 && B > 0, "cvar_gn_finalize_parts: bad shape HW=%d C=%d", HW, C);
+  gn_finalize_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(gn_part, gamma, beta, a_out, b_out, HW, C, groups, HW / 32, eps);
+  CVAR_CHECK_LAUNCH("cvar_gn_finalize_parts");
+  return 0;
+}
+
 __global__ void affine_nc_kernel(const float* __restrict__ x, const float* __restrict__ a, const float* __restrict__ b,
                                  float* __restrict__ y, __half* __restrict__ y16_hi, __half* __restrict__ y16_lo,
                                  long long HWC4, int C4, long long total4, int silu) {

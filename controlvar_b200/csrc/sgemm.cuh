@@ -349,6 +349,11 @@ struct ConvEpilogue {
   // (out_samples, Cout, out_rows_total, Wout) tensor at rows s * Hout + row_offset (the control / image halves of
   // control_var.py:563-565 decoded in ONE pass: s = 0 control on top, s = 1 image below).  0: image n is sample n.
   int out_samples = 0;
+  // GroupNorm statistics of the OUTPUT from the epilogue (row epilogue of the 2-CTA kernel only; cvar_conv_args.gn_part):
+  // every epilogue warp writes (sum, sum of squares) of its 32 pixels x one group as two doubles to
+  // gn_part[((image * gn_groups + group) * gn_slots + slot) * 2], slot = (pixel index in the image) / 32.
+  double* gn_part = nullptr;
+  int gn_groups = 0, gn_cpg = 0, gn_slots = 0, gn_HW = 0;
   __device__ __forceinline__ void store(long long m, int n, const float* v, int nvalid, int /*batch*/) const {
     if (out_mode == 0) {
       float* o = out + m * Cout + n;

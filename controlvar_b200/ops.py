@@ -445,7 +445,7 @@ def gn_stats(x_nhwc, gamma, beta, a_out, b_out, scratch, B, HW, Cdim, groups=32,
 
 def conv2d(x, w_packed, bias, out, B, Hin, Win, Cin, Cout, ks, *, in_a=None, in_b=None, in_silu=False, resid=None,
            upsample2x=False, out_mode=0, out_rows_total=0, row_offset=0, engine=-1, x16: Optional[F16Pair] = None,
-           w16: Optional[F16Pair] = None, downsample2x=False, ksplit=0, out_samples=0):
+           w16: Optional[F16Pair] = None, downsample2x=False, ksplit=0, out_samples=0, gn_part=None, gn_groups=32):
     """x16 + w16: FP16-pair input (already normalised / upsampled) and weight -> the 2-CTA TMA kernel; x may be None.
     downsample2x: the encoder's pad-(0,1,0,1) + stride-2 convolution (vae_modules.py:31-37)."""
     w_packed, w_hi, w_lo, _ = _wparts(w_packed)
@@ -465,6 +465,7 @@ def conv2d(x, w_packed, bias, out, B, Hin, Win, Cin, Cout, ks, *, in_a=None, in_
     a.downsample2x = int(downsample2x)
     a.ksplit = int(ksplit)
     a.out_samples = int(out_samples)
+    a.gn_part, a.gn_groups = _p(gn_part), (int(gn_groups) if gn_part is not None else 0)
     up = 2 if upsample2x else 1
     Mo = B * Hin * up * Win * up // (4 if downsample2x else 1)
     with _Timed("conv", 2.0 * Mo * Cout * ks * ks * Cin, 4.0 * (B * Hin * Win * Cin + Mo * Cout + Cout * ks * ks * Cin)):
@@ -493,6 +494,16 @@ def affine_nc(x, a, b, out, B, HW, Cdim, silu=False, out16: Optional[F16Pair] = 
     check(_lib.load().cvar_affine_nc(_p(x), _p(a), _p(b), _p(out), h16, l16, B, HW, Cdim, int(silu), _stream()),
           "cvar_affine_nc")
     return out if out is not None else out16
+
+
+def conv2d_gn_fusable(H, W, Cin, Cout, ks, groups=32) -> bool:
+    return bool(_lib.load().cvar_conv2d_gn_fusable(int(H), int(W), int(Cin), int(Cout), int(ks), int(groups)))
+
+
+def gn_finalize_parts(gn_part, gamma, beta, a_out, b_out, B, HW, Cdim, groups=32, eps=1e-6):
+    _chk(gn_part, gamma, beta, a_out, b_out)
+    check(_lib.load().cvar_gn_finalize_parts(_p(gn_part), _p(gamma), _p(beta), _p(a_out), _p(b_out), B, HW, Cdim, groups,
+                                             float(eps), _stream()), "cvar_gn_finalize_parts")
 
 
 def conv2d_f16_supported(H, W, Cin, Cout, ks) -> bool:

@@ -96,6 +96,8 @@ class VQVAE(nn.Module):
         self._packed: Dict[str, torch.Tensor] = {}
         self._packed16: Dict[str, "ops.F16Pair"] = {}
         self._ws: Dict[Tuple, torch.Tensor] = {}
+        self._pending_stats: Dict[int, tuple] = {}   # data_ptr of a conv output -> (GroupNorm partials, B, HW, C)
+        self.fuse_gn_stats = True                     # GroupNorm statistics from the producing conv's epilogue
         self._ws_gen = 0       # bumped when a workspace or a derived weight is (re)made: ControlVAR's CUDA graphs hold pointers
         self.eval()
 
@@ -163,10 +165,18 @@ class VQVAE(nn.Module):
     def _conv(self, x, prefix, out, B, Hin, Win, Cin, Cout, ks, **kw):
         """x: fp32 NHWC tensor, or an F16Pair (normalised / upsampled by its producer) for a layer _f16_layer() accepts."""
         bias = self._w(prefix + ".bias")
+        self._pending_stats.pop(out.data_ptr(), None)
+        stats_role = kw.pop("stats_role", None)
         if isinstance(x, ops.F16Pair):
             split = 3 if (self.ksplit_min_k and ks == 3 and 9 * Cin >= self.ksplit_min_k and not kw.get("out_mode")) else 0
+            part = None
+            if (stats_role is not None and self.fuse_gn_stats and not kw.get("out_mode")
+                    and ops.conv2d_gn_fusable(Hin, Win, Cin, Cout, ks)):
+                # the consumer of this output is a GroupNorm: its statistics come out of this conv's epilogue
+                part = self._buf("gn_part_" + stats_role, (2 * B * 32 * (Hin * Win // 32),), torch.float64)
+                self._pending_stats[out.data_ptr()] = (part, B, Hin * Win, Cout)
             return ops.conv2d(None, self._conv_w(prefix), bias, out, B, Hin, Win, Cin, Cout, ks, x16=x,
-                              w16=self._conv_w16(prefix), ksplit=split, **kw)
+                              w16=self._conv_w16(prefix), ksplit=split, gn_part=part, **kw)
         hout = Hin * (2 if kw.get("upsample2x") else 1)
         return ops.conv2d(x, self._conv_w(prefix), bias, out, B, Hin, Win, Cin, Cout, ks,
                           engine=(-1 if hout >= self._min_hw() else 0), **kw)
@@ -201,6 +211,11 @@ class VQVAE(nn.Module):
     def _gn(self, x, prefix: str, B, HW, Cn, slot: int):
         a = self._buf(f"gn_a{slot}", (B, Cn))
         b = self._buf(f"gn_b{slot}", (B, Cn))
+        pend = self._pending_stats.pop(x.data_ptr(), None)
+        if pend is not None and pend[1:] == (B, HW, Cn):
+            # partial sums written by the epilogue of the convolution that produced x (cvar_conv_args.gn_part)
+            ops.gn_finalize_parts(pend[0], self._w(prefix + ".weight"), self._w(prefix + ".bias"), a, b, B, HW, Cn)
+            return a, b
         scratch = self._buf("gn_scratch", (2 * B * 32 * ops.gn_chunks(HW),), torch.float64)
         ops.gn_stats(x, self._w(prefix + ".weight"), self._w(prefix + ".bias"), a, b, scratch, B, HW, Cn)
         return a, b
@@ -222,14 +237,14 @@ class VQVAE(nn.Module):
         """ResnetBlock.forward (vae_modules.py:57-60); x is never written."""
         h1, out = bufs
         self._conv(self._norm_act(x, prefix + "norm1", B, H, W, cin, 0, pair=self._f16_layer(H, W, cin, cout, 3)),
-                   prefix + "conv1", h1, B, H, W, cin, cout, 3)
+                   prefix + "conv1", h1, B, H, W, cin, cout, 3, stats_role="h")
         if cin != cout:
             sc = self._buf("shortcut", (B, H, W, cout))
             self._conv(x, prefix + "nin_shortcut", sc, B, H, W, cin, cout, 1)
         else:
             sc = x
         self._conv(self._norm_act(h1, prefix + "norm2", B, H, W, cout, 1, pair=self._f16_layer(H, W, cout, cout, 3)),
-                   prefix + "conv2", out, B, H, W, cout, cout, 3, resid=sc)
+                   prefix + "conv2", out, B, H, W, cout, cout, 3, resid=sc, stats_role="o")
         return out
 
     def _attnblock(self, x, prefix, B, H, W, Cn, out):
@@ -282,7 +297,7 @@ class VQVAE(nn.Module):
                     # Upsample2x (vae_modules.py:27-28): nearest x2 written once as the FP16 pair the conv fetches by TMA
                     up16 = self._pair("normact16", self._act_numel, (B, 2 * H, 2 * W, cin))
                     ops.upsample2x_split_f16(cur, up16, B, H, W, cin)
-                    self._conv(up16, prefix, out, B, 2 * H, 2 * W, cin, cout, 3)
+                    self._conv(up16, prefix, out, B, 2 * H, 2 * W, cin, cout, 3, stats_role="o")
                 else:
                     self._conv(cur, prefix, out, B, H, W, cin, cout, 3, upsample2x=True)
                 H, W = 2 * H, 2 * W
@@ -357,7 +372,9 @@ class VQVAE(nn.Module):
             n = 1
             for s_ in shape:
                 n *= s_
-            return self._buf(f"act{state['i']}", (act_numel,))[:n].view(shape)
+            t = self._buf(f"act{state['i']}", (act_numel,))[:n].view(shape)
+            self._pending_stats.pop(t.data_ptr(), None)       # the buffer is about to be overwritten
+            return t
         return ring
 
     @torch.no_grad()

@@ -289,11 +289,21 @@ typedef struct {
    * sample b of an (out_samples, Cout, out_rows_total, Wout) tensor at rows s * Hout + row_offset.  Decodes the control
    * and image halves of control_var.py:563-565 in one pass of 2 x out_samples images.  0: image n is sample n. */
   int out_samples;
+  /* FP16-pair path, out_mode 0: GroupNorm statistics of the OUTPUT, produced by the epilogue (saves the read pass of
+   * cvar_gn_stats over the activation).  gn_part: 2 * B * gn_groups * (Hout*Wout/32) doubles - per image, group and
+   * 32-pixel slot the (sum, sum of squares) of the stored values; feed it to cvar_gn_finalize_parts.  Only for layers
+   * cvar_conv2d_gn_fusable() accepts (an error otherwise: never silently skipped).  NULL: off. */
+  double* gn_part; int gn_groups;
 } cvar_conv_args;
 CVAR_API int cvar_conv2d(const cvar_conv_args* args, void* stream);
 /* 1 when the FP16-pair kernel takes this layer: ks in {1,3}, Cin % 32 == 0, Cout a multiple of one of
  * {256,160,128,224,192,96,64,32}, and W | 128 or 128 | W with whole 128-pixel tiles inside an image. */
 CVAR_API int cvar_conv2d_f16_supported(int H, int W, int Cin, int Cout, int ks);
+/* 1 when the FP16-pair kernel can emit GroupNorm partials for this layer (cvar_conv_args.gn_part). */
+CVAR_API int cvar_conv2d_gn_fusable(int H, int W, int Cin, int Cout, int ks, int groups);
+/* a[n,c], b[n,c] as cvar_gn_stats, from the partials a convolution wrote into gn_part (B images of HW pixels, C channels). */
+CVAR_API int cvar_gn_finalize_parts(const double* gn_part, const float* gamma, const float* beta, float* a_out, float* b_out,
+                           int B, int HW, int C, int groups, float eps, void* stream);
 /* nearest x2 upsampling (Upsample2x, vae_modules.py:27-28) fused with the FP16-pair split:
  * x (B,H,W,C) fp32 NHWC -> hi / lo (B,2H,2W,C) halves.  C % 4 == 0. */
 CVAR_API int cvar_upsample2x_split_f16(const float* x_nhwc, void* hi, void* lo, int B, int H, int W, int C, void* stream);

@@ -235,6 +235,50 @@ def test_f16x3_conv_vs_fp64(engine4, B, H, W, Cin, Cout, ks, resid):
     assert torch.equal(out, out_b), "f16x3 conv is not deterministic run to run"
 
 
+@pytest.mark.parametrize("B,H,W,Cin,Cout,ksplit,resid", [
+    (2, 128, 128, 160, 160, 0, True),    # 5 channels per group, 16 groups per column half
+    (1, 64, 64, 320, 320, 0, False),     # 10 per group, two N tiles
+    (2, 32, 32, 640, 640, 3, True),      # 20 per group, K-split: the statistics come from the last of the three launches
+    (3, 16, 16, 64, 160, 0, False),      # 256-pixel images: M = 768 = three pair tiles, one per image
+])
+def test_f16x3_conv_groupnorm_statistics_from_the_epilogue(engine4, B, H, W, Cin, Cout, ksplit, resid):
+    """cvar_conv_args.gn_part: GroupNorm(32) coefficients from the partial sums the conv epilogue writes must equal the ones
+    cvar_gn_stats computes by reading the stored activation (vae_modules.py:18-19), and the output must not change."""
+    torch.manual_seed(H + Cin + Cout)
+    assert ops.conv2d_gn_fusable(H, W, Cin, Cout, 3)
+    x = torch.randn(B, H, W, Cin)
+    w = torch.randn(Cout, Cin, 3, 3) / math.sqrt(Cin * 9)
+    b = torch.randn(Cout) + 0.5
+    r = g(torch.randn(B, H, W, Cout)) if resid else None
+    gamma, beta = g(torch.randn(Cout)), g(torch.randn(Cout))
+    wp = torch.empty(Cout, 9 * Cin, device=DEV)
+    ops.repack_conv_weight(g(w), wp)
+    x16, w16 = ops.F16Pair.from_tensor(g(x)), ops.F16Pair.from_tensor(wp)
+    out_ref = torch.empty(B, H, W, Cout, device=DEV)
+    ops.conv2d(None, wp, g(b), out_ref, B, H, W, Cin, Cout, 3, x16=x16, w16=w16, resid=r, ksplit=ksplit)
+    out = torch.empty(B, H, W, Cout, device=DEV)
+    part = torch.full((2 * B * 32 * (H * W // 32),), float("nan"), dtype=torch.float64, device=DEV)
+    ops.conv2d(None, wp, g(b), out, B, H, W, Cin, Cout, 3, x16=x16, w16=w16, resid=r, ksplit=ksplit, gn_part=part)
+    assert torch.equal(out, out_ref)
+    assert not torch.isnan(part).any(), "some partial slots were never written"
+    a1, b1 = torch.empty(B, Cout, device=DEV), torch.empty(B, Cout, device=DEV)
+    ops.gn_finalize_parts(part, gamma, beta, a1, b1, B, H * W, Cout)
+    a0, b0 = torch.empty(B, Cout, device=DEV), torch.empty(B, Cout, device=DEV)
+    scratch = torch.empty(2 * B * 32 * ops.gn_chunks(H * W), dtype=torch.float64, device=DEV)
+    ops.gn_stats(out, gamma, beta, a0, b0, scratch, B, H * W, Cout)
+    ea = ((a1 - a0).abs().max() / a0.abs().max()).item()
+    eb = ((b1 - b0).abs().max() / b0.abs().max()).item()
+    # fp32 partial sums over 32 pixels x one group, fp64 from there on: ~1e-7 relative
+    assert ea < 2e-6 and eb < 2e-6, (ea, eb)
+    # and against torch's GroupNorm on the stored activation
+    y = F.group_norm(out.permute(0, 3, 1, 2).double().cpu(), 32, gamma.double().cpu(), beta.double().cpu(), 1e-6)
+    y1 = out.double().cpu() * a1.double().cpu()[:, None, None, :] + b1.double().cpu()[:, None, None, :]
+    assert (y1.permute(0, 3, 1, 2) - y).abs().max().item() < 2e-5
+    assert not ops.conv2d_gn_fusable(32, 32, 96, 256, 3) or True      # shape query never raises
+    with pytest.raises(CvarError):      # fp32 input path cannot produce them: an error, not a silent skip
+        ops.conv2d(g(x), wp, g(b), out, B, H, W, Cin, Cout, 3, gn_part=part)
+
+
 def test_f16x3_conv_unsupported_shapes_are_reported():
     assert not ops.conv2d_f16_supported(80, 80, 160, 160, 3)       # 128 % 80 != 0 (truncated pyramids)
     assert not ops.conv2d_f16_supported(64, 64, 16, 160, 3)        # Cin % 32

@@ -278,7 +278,7 @@ struct DenseRow {
     c.rs = (MODE == CVAR_EPI_BIAS_RESID) ? e.resid + m * e.ldr : nullptr;
     return c;
   }
-  __device__ __forceinline__ void row16(const Ctx& c, int n, const float* v) const {
+  __device__ __forceinline__ void row16(const Ctx& c, int n, const float* v, int /*lc*/) const {
     float r[16], b[16];
     if (e.bias != nullptr) {
       ld16f(e.bias + n, b);
@@ -323,7 +323,7 @@ struct QkvRow {     // FP16-pair outputs only (cvar_qkv_project16)
     c.t = (int)(m - (long long)c.r * e.l);
     return c;
   }
-  __device__ __forceinline__ void row16(const Ctx& c, int n, const float* v) const {
+  __device__ __forceinline__ void row16(const Ctx& c, int n, const float* v, int /*lc*/) const {
     const int which = n / e.C;                 // a 16-column chunk stays inside one of q / k / v and inside one head
     const int cc = n - which * e.C;
     const int h = cc >> 6, d = cc & 63;
@@ -359,28 +359,32 @@ __device__ __forceinline__ void gn_flush(double* dst, float s, float ss) {
   }
 }
 
-struct ConvRow {    // out_mode 0 (NHWC fp32): bias + optional residual, or the K-split continuation out += acc
+// out_mode 0 (NHWC fp32): bias + optional residual, or the K-split continuation out += acc.
+// CPG > 0: also the GroupNorm statistics of the stored values (cvar_conv_args.gn_part), CPG = channels per group, a
+// compile-time constant so that the group boundaries inside the thread's row are static (a run-time counter version cost
+// the convolution 6 %: 128 compare-and-branch sites and their spills, also when the statistics were off).
+template <int CPG>
+struct ConvRow {
   ConvEpilogue e;
   struct Ctx {
     long long off;
-    double* part;      // this warp's slot of group 0 of its image (gn_part only)
+    double* part;      // this warp's slot of group 0 of its image (CPG > 0)
     float s, ss;       // running sums of the group being crossed
-    int cnt;
   };
   __device__ __forceinline__ Ctx begin(long long m) const {
     Ctx c;
     c.off = m * e.Cout;
     c.s = c.ss = 0.f;
-    c.cnt = 0;
     c.part = nullptr;
-    if (e.gn_part != nullptr) {
+    if (CPG > 0) {
       const long long img = m / e.gn_HW;
       const int slot = (int)(m - img * e.gn_HW) >> 5;
       c.part = e.gn_part + ((img * e.gn_groups) * e.gn_slots + slot) * 2;
     }
     return c;
   }
-  __device__ __forceinline__ void row16(Ctx& c, int n, const float* v) const {
+  // lc: column of v[0] inside the thread's slice (a literal after unrolling); the slice starts on a group boundary
+  __device__ __forceinline__ void row16(Ctx& c, int n, const float* v, int lc) const {
     float r[16], x[16];
     if (e.accumulate) {
       ld16f_stream(e.out + c.off + n, x);
@@ -397,17 +401,16 @@ struct ConvRow {    // out_mode 0 (NHWC fp32): bias + optional residual, or the 
       }
     }
     st16f(e.out + c.off + n, r);
-    if (e.gn_part != nullptr) {
-      // GroupNorm statistics of what was just stored (the consumer's Normalize, vae_modules.py:18-19): the thread walks its
-      // row channel by channel, so groups complete in order; the branch is warp-uniform (all lanes are at the same channel)
+    if (CPG > 0) {
+      // GroupNorm statistics of what was just stored (the consumer's Normalize, vae_modules.py:18-19); every lane is at
+      // the same channel, so the flush (a warp reduction) is warp-uniform
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         c.s += r[j];
         c.ss = fmaf(r[j], r[j], c.ss);
-        if (++c.cnt == e.gn_cpg) {
-          gn_flush(c.part + (long long)((n + j) / e.gn_cpg) * e.gn_slots * 2, c.s, c.ss);
+        if ((lc + j + 1) % (CPG > 0 ? CPG : 1) == 0) {
+          gn_flush(c.part + (long long)((n + j) / (CPG > 0 ? CPG : 1)) * e.gn_slots * 2, c.s, c.ss);
           c.s = c.ss = 0.f;
-          c.cnt = 0;
         }
       }
     }
@@ -417,7 +420,7 @@ struct ConvRow {    // out_mode 0 (NHWC fp32): bias + optional residual, or the 
 template <class EP> struct IsRowEpilogue { static constexpr bool value = false; };
 template <int MODE> struct IsRowEpilogue<DenseRow<MODE>> { static constexpr bool value = true; };
 template <> struct IsRowEpilogue<QkvRow> { static constexpr bool value = true; };
-template <> struct IsRowEpilogue<ConvRow> { static constexpr bool value = true; };
+template <int CPG> struct IsRowEpilogue<ConvRow<CPG>> { static constexpr bool value = true; };
 
 template <class ROW, bool kCross>
 __device__ __forceinline__ void epilogue_tile_rows(const ROW& ep, uint32_t tcol, int col0, int ncols, float lo_scale,
@@ -470,7 +473,7 @@ __device__ __forceinline__ void epilogue_tile_rows(const ROW& ep, uint32_t tcol,
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
     const int n = n_base + col0 + c * kEpiCols;
-    if (c * kEpiCols < ncols && n < N) ep.row16(ctx, n, &acc[c * kEpiCols]);
+    if (c * kEpiCols < ncols && n < N) ep.row16(ctx, n, &acc[c * kEpiCols], c * kEpiCols);
   }
 }
 
@@ -978,6 +981,7 @@ int tc2_conv_f16_gn_fusable(int H, int W, int Cin, int Cout, int ks, int groups)
   if (!g_epi_overlap || !tc2_conv_f16_supported(H, W, Cin, Cout, ks)) return 0;
   if (groups <= 0 || Cout % groups != 0 || Cout % 16 != 0 || (H * W) % 32 != 0) return 0;
   const int bn = conv_f16_bn(Cout), cpg = Cout / groups;
+  if (cpg != 5 && cpg != 10 && cpg != 20) return 0;          // the instantiated group sizes: 160 / 320 / 640 channels
   return (bn / 2) % cpg == 0 && (bn / 2) % 16 == 0 ? 1 : 0;
 }
 int tc2_conv_f16(const cvar_conv_args* a, cudaStream_t s) {
@@ -1009,9 +1013,16 @@ int tc2_conv_f16(const cvar_conv_args* a, cudaStream_t s) {
   const bool rows = g_epi_overlap && a->out_mode == 0 && a->Cout % 16 == 0 && tc2::aligned32(a->out) &&
                     tc2::aligned32(a->bias) && tc2::aligned32(a->resid) && a->bias != nullptr;
   auto kern_staged = tc2::tc_conv2_kernel<ConvEpilogue>;
-  auto kern_rows = g_fast_mode ? tc2::tc_conv2_kernel<tc2::ConvRow, true> : tc2::tc_conv2_kernel<tc2::ConvRow, false>;
-  cudaError_t e = rows ? cudaFuncSetAttribute(kern_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::kCvSmem)
-                       : cudaFuncSetAttribute(kern_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::kCvSmem);
+  auto kern_rows = g_fast_mode ? tc2::tc_conv2_kernel<tc2::ConvRow<0>, true> : tc2::tc_conv2_kernel<tc2::ConvRow<0>, false>;
+  auto kern_gn5 = g_fast_mode ? tc2::tc_conv2_kernel<tc2::ConvRow<5>, true> : tc2::tc_conv2_kernel<tc2::ConvRow<5>, false>;
+  auto kern_gn10 = g_fast_mode ? tc2::tc_conv2_kernel<tc2::ConvRow<10>, true> : tc2::tc_conv2_kernel<tc2::ConvRow<10>, false>;
+  auto kern_gn20 = g_fast_mode ? tc2::tc_conv2_kernel<tc2::ConvRow<20>, true> : tc2::tc_conv2_kernel<tc2::ConvRow<20>, false>;
+  const int cpg = a->gn_part != nullptr ? a->Cout / a->gn_groups : 0;
+  cudaError_t e = cudaFuncSetAttribute(kern_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::kCvSmem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(kern_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::kCvSmem);
+  if (e == cudaSuccess && cpg == 5) e = cudaFuncSetAttribute(kern_gn5, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::kCvSmem);
+  if (e == cudaSuccess && cpg == 10) e = cudaFuncSetAttribute(kern_gn10, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::kCvSmem);
+  if (e == cudaSuccess && cpg == 20) e = cudaFuncSetAttribute(kern_gn20, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::kCvSmem);
   CVAR_REQUIRE(e == cudaSuccess, "cvar_conv2d[f16x3]: cannot raise shared memory to %d: %s", tc2::kCvSmem, cudaGetErrorString(e));
   const long long M = (long long)a->B * H * W;
   const int m_tiles = cdiv(M, 256), n_tiles = a->Cout / g.BN;
@@ -1032,8 +1043,17 @@ int tc2_conv_f16(const cvar_conv_args* a, cudaStream_t s) {
       epp.gn_part = a->gn_part, epp.gn_groups = a->gn_groups, epp.gn_cpg = a->Cout / a->gn_groups;
       epp.gn_HW = H * W, epp.gn_slots = (H * W) / 32;
     }
-    if (rows)
-      kern_rows<<<2 * pairs, tc2::kThreads, tc2::kCvSmem, s>>>(mah, mal, mbh, mbl, tc2::ConvRow{epp}, g, M, a->Cout, m_tiles,
+    if (rows && epp.gn_part != nullptr && cpg == 5)
+      kern_gn5<<<2 * pairs, tc2::kThreads, tc2::kCvSmem, s>>>(mah, mal, mbh, mbl, tc2::ConvRow<5>{epp}, g, M, a->Cout, m_tiles,
+                                                               n_tiles);
+    else if (rows && epp.gn_part != nullptr && cpg == 10)
+      kern_gn10<<<2 * pairs, tc2::kThreads, tc2::kCvSmem, s>>>(mah, mal, mbh, mbl, tc2::ConvRow<10>{epp}, g, M, a->Cout, m_tiles,
+                                                                n_tiles);
+    else if (rows && epp.gn_part != nullptr && cpg == 20)
+      kern_gn20<<<2 * pairs, tc2::kThreads, tc2::kCvSmem, s>>>(mah, mal, mbh, mbl, tc2::ConvRow<20>{epp}, g, M, a->Cout, m_tiles,
+                                                                n_tiles);
+    else if (rows)
+      kern_rows<<<2 * pairs, tc2::kThreads, tc2::kCvSmem, s>>>(mah, mal, mbh, mbl, tc2::ConvRow<0>{epp}, g, M, a->Cout, m_tiles,
                                                                 n_tiles);
     else
       kern_staged<<<2 * pairs, tc2::kThreads, tc2::kCvSmem, s>>>(mah, mal, mbh, mbl, epp, g, M, a->Cout, m_tiles, n_tiles);

@@ -756,9 +756,10 @@ extern "C" int cvar_attn_kvcache16(const void* q16_hi, const void* q16_lo, const
   const __half* vl = reinterpret_cast<const __half*>(vt16_lo);
   __half* o16h = reinterpret_cast<__half*>(out16_hi);
   __half* o16l = reinterpret_cast<__half*>(out16_lo);
-  // default: tensor cores from l = 32 (a 128-query tile a quarter full still beats the SIMT kernel: measured in
-  // profiles/r01_attn16.md); below that the SIMT kernel
-  if (engine < 0) engine = (g_gemm_engine != 0 && l >= 32) ? 1 : 0;
+  // default: tensor cores for every scale.  A 128-query tile that is mostly empty still beats the SIMT kernel (l = 32:
+  // 0.076 vs 0.17 ms per layer, l = 18 / 8 / 2: ~0.07 vs ~0.13 ms, profiles/r02_attn16.md), and the block-causal pass
+  // runs the short scales on the same kernel anyway.
+  if (engine < 0) engine = (g_gemm_engine != 0) ? 1 : 0;
   if (engine == 1) {
     tcattn16::AttnSegs segs;
     segs.n = 0;

@@ -178,7 +178,7 @@ CVAR_API int cvar_qkv_project16(const void* A16_hi, const void* A16_lo, const vo
                        void* q16_hi, void* q16_lo, void* k16_hi, void* k16_lo, void* vt16_hi, void* vt16_lo,
                        int R, int l, int L_prev, int T_max, int H, int cos_attn, const float* scale_mul_H, void* stream);
 /* cvar_attn_kvcache16: softmax(q K^T * scale) V on those pairs; out (R,l,H*64) fp32 and / or out16 pair (either may be
- * NULL, not both).  engine: -1 = default (tensor cores when l >= 32), 0 = SIMT fp32 on the same operands,
+ * NULL, not both).  engine: -1 = default (tensor cores unless the library engine is 0), 0 = SIMT fp32 on the same operands,
  * 1 = tcgen05 kind::f16: three MMAs per product, CTA = 128 queries, two CTAs per SM (256 TMEM columns each: two S buffers
  * + O main / cross), Q / K / V^T tiles by TMA, P written back to TMEM over the S cells it came from. */
 CVAR_API int cvar_attn_kvcache16(const void* q16_hi, const void* q16_lo, const void* k16_hi, const void* k16_lo,

@@ -56,7 +56,7 @@ def test_attn16_matches_sdpa(R, H, l, L):
     kv.vt_hi.view(R, H, 64, kv.T)[:, :, :, L:] = -1e4
     q16 = pair_qk(q)
     res = {}
-    for eng in ((1, 0) if l >= 32 else (0,)):
+    for eng in (1, 0):
         out = torch.full((R, l, H * 64), float("nan"), device=DEV)
         o16 = ops.F16Pair.empty((R, l, H * 64), DEV)
         ops.attn_kvcache16(q16, kv, out, R, H, l, L, scale, engine=eng, out16=o16)

@@ -41,7 +41,7 @@ WORKLOADS = {
                          desc="d24 ControlVAR.conditional_infer_cfg 256x256, batch 16/GPU (64 replica rows), c_mask forced, canny"),
 }
 TOP_K, TOP_P = 900, 0.96          # reference validate() defaults, train_control_var_hpu.py:338
-CPU_BATCH_NOTE = ("measured on a 16-core B200 host: 0.336 / 0.342 / 0.347 / 0.391 img/s at 1 / 2 / 4 / 8 images per call - still rising with batch, so this bounded sample is a LOWER bound on large-batch CPU throughput")
+CPU_BATCH_NOTE = ("round 1 measured the oracle port on a 16-core B200 host at 0.336 / 0.342 / 0.347 / 0.391 img/s for 1 / 2 / 4 / 8 images per call - still rising with batch, so this bounded sample is a LOWER bound on large-batch CPU throughput")
 
 
 def peaks():
@@ -275,7 +275,7 @@ def main_ours(args, wl):
         vae.load_state_dict(W.synthetic_vae_state_dict(cfgp, 0, device=dev))
     arena = shard.pack_parameters([var, vae])
     t_b0 = time.perf_counter()
-    shard.broadcast_weights(arena, src=0)
+    shard.broadcast_weights(arena, src=0, modules=[var, vae])
     torch.cuda.synchronize()
     bcast_ms = (time.perf_counter() - t_b0) * 1e3
     if saved_stdout is not None:

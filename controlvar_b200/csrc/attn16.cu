@@ -670,314 +670,6 @@ attn16_tc_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_consta
   if (warp == 5) tmem_dealloc(tmem_base, kTmemCols);
 }
 
-// ================================================================================================ split-row kernel
-// attn16_tc8_kernel: the same CTA (128 queries of one (row, head), two CTAs per SM, the same TMA / MMA protocol and
-// tensor-memory layout) with EIGHT softmax warps instead of four: warp w serves TMEM lane quarter w & 3 and column half
-// w >> 2, so a query row is shared by two threads - each takes 32 of the 64 keys of a tile and 32 of the 64 head dims of
-// the output row.  Why (profiles/r02_attn16.md): after the MMA-issue fix the kernel is bound by the softmax warps - 2 150
-// cycles of dependent work per tile and CTA at an issue rate of 0.2-0.3 per warp, two softmax warps per scheduler.  Twice
-// the warps hide twice the latency, and a half row (32 S values + 32 output dims) fits in registers next to each other, so
-// S is read from tensor memory ONCE (the one-read variant of the four-warp kernel spills: 64 + 64 registers).
-// The two threads of a row exchange their half-row maxima through shared memory (one 64-thread named barrier per tile) and
-// then take identical decisions (reference update, rescale); the row sum is split and joined once at the end.
-constexpr int kThreads8 = 320;
-constexpr int kSmem8 = kSmem + 2 * 2 * BQ * 4;      // + the half-row maxima, double-buffered by tile parity
-
-__device__ __forceinline__ void bar_sync_pair(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
-
-template <bool kFast>
-__global__ void __launch_bounds__(kThreads8, 2)
-attn16_tc8_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_constant__ CUtensorMap mapQlo,
-                  const __grid_constant__ CUtensorMap mapKhi, const __grid_constant__ CUtensorMap mapKlo,
-                  const __grid_constant__ CUtensorMap mapVhi, const __grid_constant__ CUtensorMap mapVlo,
-                  float* __restrict__ out, __half* __restrict__ o16_hi, __half* __restrict__ o16_lo, int H, int l, int L_all,
-                  float scale, const __grid_constant__ AttnSegs segs) {
-  using G = Geo<32>;
-  extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  unsigned char* q_s = smem;
-  auto stage = [&](int s) { return smem + 2 * kQTile + s * kStageBytes; };
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kQTile + kStages * kStageBytes);
-  uint64_t* k_full = bars;
-  uint64_t* k_empty = bars + kStages;
-  uint64_t* v_full = bars + 2 * kStages;
-  uint64_t* v_empty = bars + 3 * kStages;
-  uint64_t* s_full = bars + 4 * kStages;     // [2]
-  uint64_t* q_full = bars + 4 * kStages + 2;
-  uint64_t* p_ready = bars + 4 * kStages + 3;// [2]  256 arrivals
-  uint64_t* o_full = bars + 4 * kStages + 5; // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 * kStages + 7);
-  float* xchg = reinterpret_cast<float*>(smem + 2 * kQTile + kStages * kStageBytes + 256);   // [2 parity][2 half][128 rows]
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int h = blockIdx.y, r = blockIdx.z;
-  const int q0 = segs.n > 0 ? segs.q0[blockIdx.x] : blockIdx.x * BQ;
-  const int q_end = segs.n > 0 ? q0 + segs.nq[blockIdx.x] : l;
-  const int L = segs.n > 0 ? segs.L[blockIdx.x] : L_all;
-  const int rh = r * H + h;
-  const int ntiles = (L + BKV - 1) / BKV;
-
-  if (warp == 8 && lane == 0) {
-    tma_prefetch_desc(&mapQhi), tma_prefetch_desc(&mapQlo);
-    tma_prefetch_desc(&mapKhi), tma_prefetch_desc(&mapKlo), tma_prefetch_desc(&mapVhi), tma_prefetch_desc(&mapVlo);
-    for (int s = 0; s < kStages; ++s)
-      mbar_init(&k_full[s], 1), mbar_init(&k_empty[s], 1), mbar_init(&v_full[s], 1), mbar_init(&v_empty[s], 1);
-    mbar_init(q_full, 1);
-    mbar_init(&s_full[0], 1), mbar_init(&s_full[1], 1);
-    mbar_init(&p_ready[0], 256), mbar_init(&p_ready[1], 256);
-    mbar_init(&o_full[0], 1), mbar_init(&o_full[1], 1);
-    fence_barrier_init();
-  }
-  if (warp == 9) tmem_alloc_n(tmem_slot, kTmemCols);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp < 8) {
-    // ================================================================ softmax + output: half a row per thread
-    const int qtr = warp & 3, hf = warp >> 2;
-    const int row = qtr * 32 + lane;
-    const uint32_t tl = tmem_base + ((uint32_t)(qtr * 32) << 16);
-    const uint32_t colS = 32u * (uint32_t)hf;                    // this thread's columns of an S buffer / of O
-    const float sl2 = scale * 1.4426950408889634f * (1.0f / (kQkScale * kQkScale));
-    float o_reg[32];
-#pragma unroll
-    for (int d = 0; d < 32; ++d) o_reg[d] = 0.f;
-    float m_ref = 0.f, l_half = 0.f;
-
-    auto drain_O = [&]() {
-      float a[32], b[32];
-      tmem_ld_nowait_x32(tl + kColO + colS, a);
-      if (!kFast) tmem_ld_nowait_x32(tl + kColOx + colS, b);
-      tmem_wait_ld();
-      reg_fence32(a);
-      if (!kFast) reg_fence32(b);
-#pragma unroll
-      for (int i = 0; i < 32; ++i) o_reg[i] += kFast ? a[i] : fmaf(b[i], kInvLo, a[i]);
-    };
-
-    for (int j = 0; j < ntiles; ++j) {
-      const uint32_t sb = kColS + 64u * (uint32_t)(j & 1);
-      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
-      tc_fence_after();
-      if (threadIdx.x == 0) astamp(0, j, 0);
-      const int nvalid = min(BKV, L - j * BKV) - 32 * hf;         // valid keys among this thread's 32 (may be <= 0)
-      float sv[32];
-      tmem_ld_nowait_x32(tl + sb + colS, sv);
-      tmem_wait_ld();
-      reg_fence32(sv);
-      float mx;
-      if (nvalid < 32) {
-        mx = -INFINITY;
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (i < nvalid) mx = fmaxf(mx, sv[i]);
-      } else {
-        float m0 = fmaxf(sv[0], sv[4]), m1 = fmaxf(sv[1], sv[5]), m2 = fmaxf(sv[2], sv[6]), m3 = fmaxf(sv[3], sv[7]);
-#pragma unroll
-        for (int i = 8; i < 32; i += 4) {
-          m0 = fmaxf(m0, sv[i]), m1 = fmaxf(m1, sv[i + 1]), m2 = fmaxf(m2, sv[i + 2]), m3 = fmaxf(m3, sv[i + 3]);
-        }
-        mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-      }
-      // the row maximum of the tile = max over both halves: exchange through shared memory (buffer j & 1: the partner
-      // has read buffer j & 1 of tile j - 2 before it arrived at the barrier of tile j - 1, which this thread has passed)
-      float* xb = xchg + (j & 1) * 2 * BQ;
-      xb[hf * BQ + row] = mx;
-      bar_sync_pair(1 + qtr);
-      mx = fmaxf(mx, xb[(hf ^ 1) * BQ + row]);
-      if (threadIdx.x == 0) astamp(0, j, 1);
-
-      const bool need = j > 0 && (mx - m_ref) * sl2 > kRebase;
-      bool drained = false;
-      if (j == 0) {
-        m_ref = mx;
-      } else if (__any_sync(0xffffffffu, need)) {
-        // as in the four-warp kernel; both threads of a row see the same maximum and take the same path, each on its own
-        // 32 output dims
-        const float corr = need ? ex2_approx((m_ref - mx) * sl2) : 1.0f;
-        if (need) m_ref = mx;
-        mbar_wait(&o_full[(j - 1) & 1], ((j - 1) >> 1) & 1);
-        tc_fence_after();
-        if ((j % kDrain) == 0) {
-          drain_O();
-          drained = true;
-        }
-        l_half *= corr;
-#pragma unroll
-        for (int d = 0; d < 32; ++d) o_reg[d] *= corr;
-        if ((j % kDrain) != 0) {
-#pragma unroll 1
-          for (int acc = 0; acc < (kFast ? 1 : 2); ++acc) {
-            const uint32_t base = tl + (acc == 0 ? kColO : kColOx) + colS;
-#pragma unroll 1
-            for (int c = 0; c < 2; ++c) {
-              float a[16];
-              tmem_ld_nowait_x16(base + 16 * c, a);
-              tmem_wait_ld();
-              reg_fence16(a);
-              uint32_t u[16];
-#pragma unroll
-              for (int i = 0; i < 16; ++i) u[i] = __float_as_uint(a[i] * corr);
-              tmem_st_32x32b_x8(base + 16 * c, u);
-              tmem_st_32x32b_x8(base + 16 * c + 8, u + 8);
-            }
-          }
-        }
-      }
-      // p for this thread's two 16-key chunks, out of the registers; P(j) goes back over the S cells it came from
-      float rs = 0.f;
-      const float nref = -m_ref * sl2;
-#pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        uint32_t ph[8], pl[8];
-#pragma unroll
-        for (int i = 0; i < 16; i += 2) {
-          float p0 = ex2_approx(fmaf(sv[16 * cc + i], sl2, nref)), p1 = ex2_approx(fmaf(sv[16 * cc + i + 1], sl2, nref));
-          if (nvalid < 32) {
-            if (16 * cc + i >= nvalid) p0 = 0.f;
-            if (16 * cc + i + 1 >= nvalid) p1 = 0.f;
-          }
-          rs += p0 + p1;
-          const __half2 hh = __floats2half2_rn(p0, p1);
-          ph[i >> 1] = *reinterpret_cast<const uint32_t*>(&hh);
-          if (!kFast) {
-            const float2 hfv = __half22float2(hh);
-            const __half2 lo = __floats2half2_rn((p0 - hfv.x) * kF16LoScale, (p1 - hfv.y) * kF16LoScale);
-            pl[i >> 1] = *reinterpret_cast<const uint32_t*>(&lo);
-          }
-        }
-        const uint32_t cell = tl + sb + colS + 16 * cc;
-        tmem_st_32x32b_x8(cell, ph);
-        if (!kFast) tmem_st_32x32b_x8(cell + 8, pl);
-      }
-      l_half += rs;
-      if (threadIdx.x == 0) astamp(0, j, 2);
-      if (j > 0 && (j % kDrain) == 0 && !drained) {
-        mbar_wait(&o_full[(j - 1) & 1], ((j - 1) >> 1) & 1);
-        tc_fence_after();
-        drain_O();
-      }
-      tmem_wait_st();
-      tc_fence_before();
-      mbar_arrive(&p_ready[j & 1]);
-      if (threadIdx.x == 0) astamp(0, j, 3);
-    }
-    mbar_wait(&o_full[(ntiles - 1) & 1], ((ntiles - 1) >> 1) & 1);
-    tc_fence_after();
-    // join the two halves of the row sum (the maxima buffers are free: every tile's exchange is behind us after one more
-    // pair barrier)
-    bar_sync_pair(1 + qtr);
-    xchg[hf * BQ + row] = l_half;
-    bar_sync_pair(1 + qtr);
-    const float inv = 1.0f / (l_half + xchg[(hf ^ 1) * BQ + row]);
-    const int t = q0 + row;
-    const long long off = ((long long)r * l + t) * (H * D) + h * D + 32 * hf;
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      float a[16], b[16];
-      tmem_ld_32x32b_x16(tl + kColO + colS + 16 * c, a);
-      if (!kFast) tmem_ld_32x32b_x16(tl + kColOx + colS + 16 * c, b);
-      if (t < q_end) {
-#pragma unroll
-        for (int i = 0; i < 16; i += 4) {
-          float vv[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e)
-            vv[e] = (o_reg[16 * c + i + e] + (kFast ? a[i + e] : fmaf(b[i + e], kInvLo, a[i + e]))) * inv;
-          if (o16_hi != nullptr) st4_split_f16(o16_hi + off + 16 * c + i, o16_lo + off + 16 * c + i, vv);
-          if (out != nullptr) st4(out + off + 16 * c + i, make_float4(vv[0], vv[1], vv[2], vv[3]));
-        }
-      }
-    }
-  } else if (warp == 8) {
-    // ================================================================ TMA (as attn16_tc_kernel)
-    if (elect_one()) {
-      mbar_arrive_expect_tx(q_full, (uint32_t)((kFast ? 1 : 2) * kQTile));
-      tma_load_3d(&mapQhi, q_full, q_s, 0, q0, rh);
-      if (!kFast) tma_load_3d(&mapQlo, q_full, q_s + kQTile, 0, q0, rh);
-      for (int j = 0; j < ntiles; ++j) {
-        const int s = j % kStages;
-        const uint32_t ph = ((j / kStages) & 1) ^ 1;
-        unsigned char* st = stage(s);
-        mbar_wait(&k_empty[s], ph);
-        astamp(2, j, 0);
-        mbar_arrive_expect_tx(&k_full[s], (uint32_t)((kFast ? 1 : 2) * kTile));
-        tma_load_3d(&mapKhi, &k_full[s], st + 0 * kTile, 0, j * BKV, rh);
-        if (!kFast) tma_load_3d(&mapKlo, &k_full[s], st + 1 * kTile, 0, j * BKV, rh);
-        mbar_wait(&v_empty[s], ph);
-        astamp(2, j, 1);
-        mbar_arrive_expect_tx(&v_full[s], (uint32_t)((kFast ? 1 : 2) * kTile));
-        tma_load_3d(&mapVhi, &v_full[s], st + 2 * kTile, j * BKV, 0, rh);
-        if (!kFast) tma_load_3d(&mapVlo, &v_full[s], st + 3 * kTile, j * BKV, 0, rh);
-      }
-    }
-  } else {
-    // ================================================================ MMA issue (as attn16_tc_kernel)
-    if (elect_one()) {
-      const uint64_t dqh = G::desc(smem_u32(q_s)), dql = G::desc(smem_u32(q_s + kQTile));
-      auto issue_S = [&](int j) {
-        const int s = j % kStages;
-        mbar_wait(&k_full[s], (j / kStages) & 1);
-        tc_fence_after();
-        astamp(1, j - 2, 2);
-        unsigned char* st = stage(s);
-        const uint32_t d = tmem_base + kColS + 64u * (uint32_t)(j & 1);
-        const uint64_t dkh = G::desc(smem_u32(st)), dkl = G::desc(smem_u32(st + kTile));
-        if (!kFast) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t adv = (uint64_t)(2 * k);
-            umma_f16_ss(d, dql + adv, dkh + adv, kIdesc, k != 0);
-            umma_f16_ss(d, dqh + adv, dkl + adv, kIdesc, 1u);
-          }
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint64_t adv = (uint64_t)(2 * k);
-          umma_f16_ss(d, dqh + adv, dkh + adv, kIdesc, (kFast && k == 0) ? 0u : 1u);
-        }
-        umma_commit(&s_full[j & 1]);
-        umma_commit(&k_empty[s]);
-        astamp(1, j - 2, 3);
-      };
-      mbar_wait(q_full, 0);
-      tc_fence_after();
-      issue_S(0);
-      if (ntiles > 1) issue_S(1);
-      for (int j = 0; j < ntiles; ++j) {
-        const int s = j % kStages;
-        mbar_wait(&v_full[s], (j / kStages) & 1);
-        mbar_wait(&p_ready[j & 1], (j >> 1) & 1);
-        tc_fence_after();
-        astamp(1, j, 0);
-        unsigned char* st = stage(s);
-        const uint64_t dvh = G::desc(smem_u32(st + 2 * kTile)), dvl = G::desc(smem_u32(st + 3 * kTile));
-        const uint32_t pb = tmem_base + kColS + 64u * (uint32_t)(j & 1);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint64_t adv = (uint64_t)(2 * k);
-          const uint32_t p_hi = pb + 16 * k, p_lo = p_hi + 8;
-          const uint32_t acc = (k != 0 || (j % kDrain) != 0) ? 1u : 0u;
-          if (!kFast) {
-            umma_f16_ts(tmem_base + kColOx, p_lo, dvh + adv, kIdesc, acc);
-            umma_f16_ts(tmem_base + kColOx, p_hi, dvl + adv, kIdesc, 1u);
-          }
-          umma_f16_ts(tmem_base + kColO, p_hi, dvh + adv, kIdesc, acc);
-        }
-        umma_commit(&o_full[j & 1]);
-        umma_commit(&v_empty[s]);
-        astamp(1, j, 1);
-        if (j + 2 < ntiles) issue_S(j + 2);
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 9) tmem_dealloc(tmem_base, kTmemCols);
-}
-
 // CVAR_ATTN_ONE_PASS = 1 selects the one-read softmax variant (A/B timing).  Default 0: measured SLOWER (2.31 vs 2.06 ms at
 // the last scale, profiles/r02_attn16.md) - with the running output row (64 registers) the 64 S registers spill.
 static int initial_one_pass() {
@@ -985,12 +677,6 @@ static int initial_one_pass() {
   return (e != nullptr && e[0] == '1') ? 1 : 0;
 }
 int g_one_pass = initial_one_pass();
-// CVAR_ATTN_WARPS = 4 selects the four-softmax-warp kernel (attn16_tc_kernel); default 8 (attn16_tc8_kernel)
-static int initial_split_rows() {
-  const char* e = getenv("CVAR_ATTN_WARPS");
-  return (e != nullptr && e[0] == '4') ? 0 : 1;
-}
-int g_split_rows = initial_split_rows();
 int set_trace(long long* p) { return cudaMemcpyToSymbol(g_attn16_trace, &p, sizeof(p)) == cudaSuccess ? 0 : -1; }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -1041,20 +727,11 @@ static int launch_attn16_tc(const __half* qh, const __half* ql, const __half* kh
   if (!rc) rc = tcattn16::make_map3(&mvh, vh, T_max, 64, RH, 64);
   if (!rc) rc = tcattn16::make_map3(&mvl, vl, T_max, 64, RH, 64);
   if (rc) return rc;
-  dim3 grid(segs.n > 0 ? segs.n : cdiv(l, tcattn16::BQ), H, R);
-  if (tcattn16::g_split_rows) {
-    auto kern8 = g_fast_mode ? tcattn16::attn16_tc8_kernel<true> : tcattn16::attn16_tc8_kernel<false>;
-    cudaError_t e8 = cudaFuncSetAttribute(kern8, cudaFuncAttributeMaxDynamicSharedMemorySize, tcattn16::kSmem8);
-    CVAR_REQUIRE(e8 == cudaSuccess, "%s: cannot raise shared memory: %s", name, cudaGetErrorString(e8));
-    kern8<<<grid, tcattn16::kThreads8, tcattn16::kSmem8, stream>>>(mqh, mql, mkh, mkl, mvh, mvl, out, o16h, o16l, H, l, L,
-                                                                    scale, segs);
-    CVAR_CHECK_LAUNCH(name);
-    return 0;
-  }
   auto kern = g_fast_mode ? (tcattn16::g_one_pass ? tcattn16::attn16_tc_kernel<true, true> : tcattn16::attn16_tc_kernel<true, false>)
                           : (tcattn16::g_one_pass ? tcattn16::attn16_tc_kernel<false, true> : tcattn16::attn16_tc_kernel<false, false>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tcattn16::kSmem);
   CVAR_REQUIRE(e == cudaSuccess, "%s: cannot raise shared memory: %s", name, cudaGetErrorString(e));
+  dim3 grid(segs.n > 0 ? segs.n : cdiv(l, tcattn16::BQ), H, R);
   kern<<<grid, tcattn16::kThreads, tcattn16::kSmem, stream>>>(mqh, mql, mkh, mkl, mvh, mvl, out, o16h, o16l, H, l, L, scale,
                                                                segs);
   CVAR_CHECK_LAUNCH(name);

@@ -138,3 +138,41 @@ def test_cuda_generator_path_is_deterministic():
                                      cond_type=torch.tensor([1, 2, 3]))
     assert torch.equal(a, b)
     assert ops.launch_count() - n0 > 100
+
+
+def test_bad_ids_and_token_maps_are_rejected_before_any_launch():
+    """The kernels index class_emb / cond_embed / the codebook with user-supplied ids: out-of-range ids and token maps of
+    the wrong shape must raise on the host (the reference fails with an embedding assert / a shape error), never reach a
+    kernel."""
+    from controlvar_b200.config import PathConfig
+    cfg = PathConfig(depth=2, patch_nums=(1, 2, 3))
+    vae, var, _, _ = build(cfg)
+    ok_l, ok_c = torch.tensor([1, 2]), torch.tensor([0, 3])
+    n0 = ops.launch_count()
+    with pytest.raises(ValueError):
+        var.autoregressive_infer_cfg(2, torch.tensor([1, 1001]), g_seed=0, cond_type=ok_c)          # label > num_classes
+    with pytest.raises(ValueError):
+        var.autoregressive_infer_cfg(2, torch.tensor([-1, 5]), g_seed=0, cond_type=ok_c)            # negative label tensor
+    with pytest.raises(ValueError):
+        var.autoregressive_infer_cfg(2, ok_l, g_seed=0, cond_type=torch.tensor([0, 5]))             # condition type > 4
+    with pytest.raises(ValueError):
+        var.autoregressive_infer_cfg(2, torch.tensor([1, 2, 3]), g_seed=0, cond_type=ok_c)          # wrong length
+    toks = [torch.zeros(2, pn * pn, dtype=torch.long, device=DEV) for pn in cfg.patch_nums]
+    bad_shape = [t.clone() for t in toks]
+    bad_shape[1] = torch.zeros(2, 9, dtype=torch.long, device=DEV)                                  # 3x3 tokens at the 2x2 scale
+    with pytest.raises(ValueError):
+        var.conditional_infer_cfg(2, ok_l, g_seed=0, cond_type=ok_c, c_mask=bad_shape)
+    bad_val = [t.clone() for t in toks]
+    bad_val[2][0, 0] = 4096
+    with pytest.raises(ValueError):
+        var.conditional_infer_cfg(2, ok_l, g_seed=0, cond_type=ok_c, c_mask=bad_val)
+    with pytest.raises(ValueError):
+        var.conditional_infer_cfg(2, ok_l, g_seed=0, cond_type=ok_c, c_img=toks[:2])                # a scale missing
+    with pytest.raises(ValueError):
+        vae.idxBl_to_img(bad_val, same_shape=True, last_one=True)
+    with pytest.raises(ValueError):
+        vae.idxBl_to_h([t.clone().fill_(-1) for t in toks])
+    assert ops.launch_count() == n0, "a rejected call must not have launched anything"
+    # the unconditional ids themselves are legal
+    img = var.autoregressive_infer_cfg(2, torch.tensor([1000, 0]), g_seed=0, cond_type=torch.tensor([4, 0]))
+    assert img.shape == (2, 3, 96, 48)

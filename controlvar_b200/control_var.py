@@ -239,7 +239,8 @@ class ControlVAR(nn.Module):
                     scale_mul=P(p + "attn.scale_mul_1H11").reshape(-1).contiguous() if self.cos_attn else None,
                 ))
             c["blocks"] = blocks
-            c["head_ada_w"], c["head_ada_b"] = P("head_nm.ada_lin.1.weight"), P("head_nm.ada_lin.1.bias")
+            c["head_ada_w"] = ops.SplitWeight(P("head_nm.ada_lin.1.weight"), f16=True) if f16 else P("head_nm.ada_lin.1.weight")
+            c["head_ada_b"] = P("head_nm.ada_lin.1.bias")
             c["head_w"] = ops.SplitWeight(P("head.weight"), f16=f16)
             vq = self.vae_proxy[0]
             c["phi"] = [(vq.get_parameter(f"quantize.quant_resi.qresi_ls.{k}.weight"),
@@ -622,7 +623,7 @@ class _Transformer:
         silu16 = ops.F16Pair.from_tensor(self.silu_cond, out=m._pair("silu16", (R, C))) if self.f16 else None
         for bi, blk in enumerate(cst["blocks"]):
             ops.gemm(self.silu_cond, blk["ada_w"], blk["ada_b"], self.ada[bi], R, 6 * C, C, A16=silu16)
-        ops.gemm(self.silu_cond, cst["head_ada_w"], cst["head_ada_b"], self.ada_head, R, 2 * C, C)
+        ops.gemm(self.silu_cond, cst["head_ada_w"], cst["head_ada_b"], self.ada_head, R, 2 * C, C, A16=silu16)
 
     def scale(self, l: int, L_prev: int, block_causal_lens=None) -> None:
         """x (R*l, C) of one scale through all blocks (keys / values appended at L_prev) and the head -> self.logits.

@@ -152,6 +152,16 @@ class VQVAE(nn.Module):
             self._packed16[key] = p
         return p
 
+    def _gemm_w16(self, prefix: str) -> "ops.SplitWeight":
+        """A 1x1 conv weight (AttnBlock q / k / v / proj_out) as the FP16-pair GEMM weight of the f16x3 engine (cached)."""
+        key = prefix + ".weight/gemm16"
+        w = self._packed.get(key)
+        if w is None:
+            base = self._conv_w(prefix)
+            w = ops.SplitWeight(base.w if isinstance(base, ops.SplitWeight) else base, f16=True)
+            self._packed[key] = w
+        return w
+
     def _min_hw(self) -> int:
         if self.tc_min_hw is not None:
             return self.tc_min_hw
@@ -251,10 +261,16 @@ class VQVAE(nn.Module):
         """AttnBlock.forward (vae_modules.py:73-92) on NHWC: single head over HW positions."""
         HW = H * W
         a, b = self._gn(x, prefix + "norm", B, HW, Cn, 0)
-        xn = self._buf("attn_xn", (B, HW, Cn))
-        ops.affine_nc(x, a, b, xn, B, HW, Cn, silu=False)
+        f16 = ops.get_gemm_engine() == ops.ENGINE_TC_F16X3 and Cn % 64 == 0
         qkv = self._buf("attn_qkv", (B, HW, 3 * Cn))
-        ops.gemm(xn, self._conv_w(prefix + "qkv"), self._w(prefix + "qkv.bias"), qkv, B * HW, 3 * Cn, Cn)
+        if f16:       # the dense layers of the block on the f16x3 2-CTA kernel, like the transformer's (round 1: 3xTF32 1-CTA)
+            xn16 = self._pair("attn_xn16", B * HW * Cn, (B * HW, Cn))
+            ops.affine_nc(x, a, b, None, B, HW, Cn, silu=False, out16=xn16)
+            ops.gemm(None, self._gemm_w16(prefix + "qkv"), self._w(prefix + "qkv.bias"), qkv, B * HW, 3 * Cn, Cn, A16=xn16)
+        else:
+            xn = self._buf("attn_xn", (B, HW, Cn))
+            ops.affine_nc(x, a, b, xn, B, HW, Cn, silu=False)
+            ops.gemm(xn, self._conv_w(prefix + "qkv"), self._w(prefix + "qkv.bias"), qkv, B * HW, 3 * Cn, Cn)
         S = self._buf("attn_S", (B, HW, HW))
         # w = bmm(q, k).mul_(C ** -0.5)
         ops.gemm(qkv, qkv[:, :, Cn:], None, S, HW, HW, Cn, lda=3 * Cn, ldw=3 * Cn, ldo=HW, alpha=int(Cn) ** (-0.5),
@@ -264,8 +280,13 @@ class VQVAE(nn.Module):
         # h[i, c] = sum_j P[i, j] v[j, c]
         ops.gemm(S, qkv[:, :, 2 * Cn:], None, hbuf, HW, Cn, HW, lda=HW, ldw=3 * Cn, ldo=Cn, w_is_kn=True, batch=B,
                  strideA=HW * HW, strideW=HW * 3 * Cn, strideO=HW * Cn)
-        ops.gemm(hbuf, self._conv_w(prefix + "proj_out"), self._w(prefix + "proj_out.bias"), out, B * HW, Cn, Cn,
-                 epilogue=ops.EPI_BIAS_RESID, resid=x)
+        if f16:
+            h16 = ops.F16Pair.from_tensor(hbuf, out=self._pair("attn_h16", B * HW * Cn, (B, HW, Cn)))
+            ops.gemm(None, self._gemm_w16(prefix + "proj_out"), self._w(prefix + "proj_out.bias"), out, B * HW, Cn, Cn,
+                     epilogue=ops.EPI_BIAS_RESID, resid=x, A16=h16)
+        else:
+            ops.gemm(hbuf, self._conv_w(prefix + "proj_out"), self._w(prefix + "proj_out.bias"), out, B * HW, Cn, Cn,
+                     epilogue=ops.EPI_BIAS_RESID, resid=x)
         return out
 
     def _decode_nhwc(self, z_nhwc: torch.Tensor, B: int, hw: int, img_out: torch.Tensor, rows_total: int,
@@ -275,14 +296,22 @@ class VQVAE(nn.Module):
         cfg = self.cfg
         H = W = hw
         zq = self._buf("z_pq", (B, H, W, cfg.Cvae))
-        self._conv(z_nhwc, "post_quant_conv", zq, B, H, W, cfg.Cvae, cfg.Cvae, 3)
+        if self._f16_layer(H, W, cfg.Cvae, cfg.Cvae, 3):
+            z16 = ops.F16Pair.from_tensor(z_nhwc, out=self._pair("z_in16", B * H * W * cfg.Cvae, (B, H, W, cfg.Cvae)))
+            self._conv(z16, "post_quant_conv", zq, B, H, W, cfg.Cvae, cfg.Cvae, 3)
+        else:
+            self._conv(z_nhwc, "post_quant_conv", zq, B, H, W, cfg.Cvae, cfg.Cvae, 3)
         cur = zq
         ring = self._ring_setup(self._plan, B, hw)
 
         for op, prefix, cin, cout in self._plan:
             if op == "conv3":
                 out = ring((B, H, W, cout))
-                self._conv(cur, prefix, out, B, H, W, cin, cout, 3)
+                if self._f16_layer(H, W, cin, cout, 3):
+                    c16 = ops.F16Pair.from_tensor(cur, out=self._pair("z_pq16", B * H * W * cin, (B, H, W, cin)))
+                    self._conv(c16, prefix, out, B, H, W, cin, cout, 3, stats_role="o")
+                else:
+                    self._conv(cur, prefix, out, B, H, W, cin, cout, 3)
                 cur = out
             elif op == "res":
                 h1 = ring((B, H, W, cout))

@@ -83,18 +83,6 @@ __device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t ncols) 
 __device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
-// L2 eviction-priority hints for TMA loads (the fixed policy encodings createpolicy would produce)
-constexpr uint64_t kL2EvictFirst = 0x12F0000000000000ull, kL2EvictLast = 0x14F0000000000000ull;
-// the same load with an L2 cache hint: weights EVICT_LAST (every GEMM weight of the model fits in L2 and is re-read by every
-// group of row tiles), activations EVICT_FIRST (a row tile is re-read only while its group is in flight)
-__device__ __forceinline__ void tma_load_2d_2sm_hint(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1,
-                                                     uint64_t policy) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;" ::
-          "r"(smem_u32(dst)),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kPeerMask), "r"(c0), "r"(c1), "l"(policy)
-      : "memory");
-}
 // TMA into THIS CTA's shared memory, completion counted on the LEADER's barrier
 __device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
   asm volatile(
@@ -586,10 +574,10 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constan
           if (kb == 0) trace2(it / nkb, 5);
           if (kb == nkb - 1) trace2(it / nkb, 6);
           if (rank == 0) mbar_arrive_expect_tx(&full[s], 2u * (uint32_t)kSB);   // bytes of BOTH CTAs
-          tma_load_2d_2sm_hint(&mapAhi, &full[s], a_hi(s), kb * kBKe, arow, kL2EvictFirst);
-          if (!kFast) tma_load_2d_2sm_hint(&mapAlo, &full[s], a_lo(s), kb * kBKe, arow, kL2EvictFirst);
-          tma_load_2d_2sm_hint(&mapBhi, &full[s], b_hi(s), kb * kBKe, brow, kL2EvictLast);
-          if (!kFast) tma_load_2d_2sm_hint(&mapBlo, &full[s], b_lo(s), kb * kBKe, brow, kL2EvictLast);
+          tma_load_2d_2sm(&mapAhi, &full[s], a_hi(s), kb * kBKe, arow);
+          if (!kFast) tma_load_2d_2sm(&mapAlo, &full[s], a_lo(s), kb * kBKe, arow);
+          tma_load_2d_2sm(&mapBhi, &full[s], b_hi(s), kb * kBKe, brow);
+          if (!kFast) tma_load_2d_2sm(&mapBlo, &full[s], b_lo(s), kb * kBKe, brow);
         }
       }
     }

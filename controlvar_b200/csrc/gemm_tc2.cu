@@ -55,7 +55,13 @@ constexpr int kStages = 3;
 constexpr int kStagingBytes = kEpiWarps * 32 * kStagePitch * 4;
 constexpr int kSmem = kStages * kStageBytes + kStagingBytes + 1024 + 1024;
 constexpr uint32_t kPeerMask = 0xFEFFFFFFu;          // clears the CTA-rank bit of a shared::cluster address (leader's copy)
-constexpr int kGroupM = 4;                           // pair-tiles (256 rows) per rasterisation group.  Small on purpose: every GEMM weight of the model (<= 38 MB as an FP16 pair at d24) fits in L2 next to the A rows of one group, so the weights stay resident and A streams through once; 16 / 32 (A of a group = 25 / 50 MB) thrashed the ~60 MB a die's L2 effectively holds: 2.2 / 3.1 GB of DRAM reads on fc1 against 0.44 GB of operands
+static int initial_group_m() {
+  const char* e = getenv("CVAR_GROUP_M");
+  int v = e ? atoi(e) : 4;
+  return v >= 1 && v <= 64 ? v : 4;
+}
+int g_group_m = initial_group_m();      // CVAR_GROUP_M: A/B of the rasterisation group (diagnostic)
+// default 4:                           // pair-tiles (256 rows) per rasterisation group.  Small on purpose: every GEMM weight of the model (<= 38 MB as an FP16 pair at d24) fits in L2 next to the A rows of one group, so the weights stay resident and A streams through once; 16 / 32 (A of a group = 25 / 50 MB) thrashed the ~60 MB a die's L2 effectively holds: 2.2 / 3.1 GB of DRAM reads on fc1 against 0.44 GB of operands
 
 // Optional tile trace (diagnostics, cvar_debug_set_trace): CTA 0 stamps clock64() for its first 64 tiles.
 // trace[tile * 8 + ev]: 0 MMA thread has tensor memory (tm_empty seen), 1 last MMA of the tile committed,
@@ -119,7 +125,7 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerMask) : "memory");
 }
 
-__device__ __forceinline__ void tile_coords(int tile, int m_tiles, int n_tiles, int& mt, int& nt) {
+__device__ __forceinline__ void tile_coords(int tile, int m_tiles, int n_tiles, int kGroupM, int& mt, int& nt) {
   const int per_group = kGroupM * n_tiles;
   const int g = tile / per_group;
   const int first_m = g * kGroupM;
@@ -494,7 +500,7 @@ template <class EP, bool F16, bool kFast = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 tc_gemm2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
                 const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo, EP ep,
-                long long M, int N, int K, int m_tiles, int n_tiles) {
+                long long M, int N, int K, int m_tiles, int n_tiles, int group_m) {
   using G = Geo<BK>;
   // instruction descriptor: D fp32; A/B format 2 = TF32 (kind::tf32) or 0 = FP16 (kind::f16); N, M of the pair tile
   constexpr uint32_t kFmt = F16 ? 0u : 2u;
@@ -548,7 +554,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constan
     int tcount = 0;
     for (int tile = pair; tile < total_tiles; tile += npairs, ++tcount) {
       int mt, nt;
-      tile_coords(tile, m_tiles, n_tiles, mt, nt);
+      tile_coords(tile, m_tiles, n_tiles, group_m, mt, nt);
       mbar_wait(tm_full, tcount & 1);
       tc_fence_after();
       if (threadIdx.x == 0) trace2(tcount, 2);
@@ -564,7 +570,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constan
       int it = 0;
       for (int tile = pair; tile < total_tiles; tile += npairs) {
         int mt, nt;
-        tile_coords(tile, m_tiles, n_tiles, mt, nt);
+        tile_coords(tile, m_tiles, n_tiles, group_m, mt, nt);
         const int arow = mt * 256 + (int)rank * BM;
         const int brow = nt * BN + (int)rank * (BN / 2);
         for (int kb = 0; kb < nkb; ++kb, ++it) {
@@ -652,7 +658,7 @@ template <class EP, bool kFast = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 tc_conv2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
                 const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo, EP ep, ConvGeo g,
-                long long M, int N, int m_tiles, int n_tiles) {
+                long long M, int N, int m_tiles, int n_tiles, int group_m) {
   using G = Geo<16>;                                 // 64-byte rows, SWIZZLE_64B
   const int BNr = g.BN;
   const uint32_t idesc = (1u << 4) | ((uint32_t)(BNr >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);   // F16 x F16 -> F32
@@ -705,7 +711,7 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constan
     int tcount = 0;
     for (int tile = pair; tile < total_tiles; tile += npairs, ++tcount) {
       int mt, nt;
-      tile_coords(tile, m_tiles, n_tiles, mt, nt);
+      tile_coords(tile, m_tiles, n_tiles, group_m, mt, nt);
       mbar_wait(tm_full, tcount & 1);
       tc_fence_after();
       const long long m_base = (long long)mt * 256 + rank * BM + quarter * 32;
@@ -722,7 +728,7 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constan
       int it = 0;
       for (int tile = pair; tile < total_tiles; tile += npairs) {
         int mt, nt;
-        tile_coords(tile, m_tiles, n_tiles, mt, nt);
+        tile_coords(tile, m_tiles, n_tiles, group_m, mt, nt);
         const long long m0 = (long long)mt * 256 + (long long)rank * BM;
         const int img = (int)(m0 / HW);
         const int rem = (int)(m0 - (long long)img * HW);
@@ -889,7 +895,7 @@ int launch(const EP& ep, const void* A_hi, const void* A_lo, long long lda, cons
   }
   const int m_tiles = cdiv(M, 256), n_tiles = cdiv(N, BN);
   const int pairs = min(num_sms() / 2, m_tiles * n_tiles);
-  kern<<<2 * pairs, kThreads, kSmem, s>>>(mah, mal, mbh, mbl, ep, M, N, K, m_tiles, n_tiles);
+  kern<<<2 * pairs, kThreads, kSmem, s>>>(mah, mal, mbh, mbl, ep, M, N, K, m_tiles, n_tiles, g_group_m);
   CVAR_CHECK_LAUNCH(name);
   return 0;
 }
@@ -1045,18 +1051,18 @@ int tc2_conv_f16(const cvar_conv_args* a, cudaStream_t s) {
     }
     if (rows && epp.gn_part != nullptr && cpg == 5)
       kern_gn5<<<2 * pairs, tc2::kThreads, tc2::kCvSmem, s>>>(mah, mal, mbh, mbl, tc2::ConvRow<5>{epp}, g, M, a->Cout, m_tiles,
-                                                               n_tiles);
+                                                               n_tiles, tc2::g_group_m);
     else if (rows && epp.gn_part != nullptr && cpg == 10)
       kern_gn10<<<2 * pairs, tc2::kThreads, tc2::kCvSmem, s>>>(mah, mal, mbh, mbl, tc2::ConvRow<10>{epp}, g, M, a->Cout, m_tiles,
-                                                                n_tiles);
+                                                                n_tiles, tc2::g_group_m);
     else if (rows && epp.gn_part != nullptr && cpg == 20)
       kern_gn20<<<2 * pairs, tc2::kThreads, tc2::kCvSmem, s>>>(mah, mal, mbh, mbl, tc2::ConvRow<20>{epp}, g, M, a->Cout, m_tiles,
-                                                                n_tiles);
+                                                                n_tiles, tc2::g_group_m);
     else if (rows)
       kern_rows<<<2 * pairs, tc2::kThreads, tc2::kCvSmem, s>>>(mah, mal, mbh, mbl, tc2::ConvRow<0>{epp}, g, M, a->Cout, m_tiles,
-                                                                n_tiles);
+                                                                n_tiles, tc2::g_group_m);
     else
-      kern_staged<<<2 * pairs, tc2::kThreads, tc2::kCvSmem, s>>>(mah, mal, mbh, mbl, epp, g, M, a->Cout, m_tiles, n_tiles);
+      kern_staged<<<2 * pairs, tc2::kThreads, tc2::kCvSmem, s>>>(mah, mal, mbh, mbl, epp, g, M, a->Cout, m_tiles, n_tiles, tc2::g_group_m);
     CVAR_CHECK_LAUNCH("cvar_conv2d[tc2/f16x3]");
   }
   return 0;

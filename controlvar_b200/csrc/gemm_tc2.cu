@@ -714,10 +714,12 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constan
       tile_coords(tile, m_tiles, n_tiles, group_m, mt, nt);
       mbar_wait(tm_full, tcount & 1);
       tc_fence_after();
+      if (threadIdx.x == 0) trace2(tcount, 2);
       const long long m_base = (long long)mt * 256 + rank * BM + quarter * 32;
       const uint32_t tcol = tmem_base + ((uint32_t)(quarter * 32) << 16);
       epilogue_tile<EP, !kFast>(ep, tcol, half * (BNr / 2), BNr / 2, kLoScale, m_base, nt * BNr, M, N, stage, lane, tm_empty,
-                                64);
+                                tcount);
+      if (threadIdx.x == 0) trace2(tcount, 4);
     }
   } else if (warp == kTmaWarp) {
     // ================================================================ TMA: this CTA's 128 pixels (shifted window per tap)
@@ -757,6 +759,7 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constan
       for (int tile = pair; tile < total_tiles; tile += npairs, ++tcount) {
         mbar_wait(tm_empty, (tcount & 1) ^ 1);
         tc_fence_after();
+        trace2(tcount, 0);
         const uint32_t d = tmem_base, dl = tmem_base + (uint32_t)kAccStride;
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % kNS;
@@ -777,6 +780,7 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constan
           umma_commit_2sm(&empty[s]);
         }
         umma_commit_2sm(tm_full);
+        trace2(tcount, 1);
       }
     }
   }

@@ -428,37 +428,40 @@ template <int MODE> struct IsRowEpilogue<DenseRow<MODE>> { static constexpr bool
 template <> struct IsRowEpilogue<QkvRow> { static constexpr bool value = true; };
 template <int CPG> struct IsRowEpilogue<ConvRow<CPG>> { static constexpr bool value = true; };
 
-template <class ROW, bool kCross>
+// kChunks: 16-column chunks the thread's slice can have (8 = 128 columns: a 256-wide tile; 5 = 80 columns: the 160-wide
+// tiles of the decoder).  A compile-time bound: with a run-time one the register array is sized for 128 columns whatever
+// the tile, and the 160-wide convolution kernel spilled its accumulators during the drain.
+template <class ROW, bool kCross, int kChunks>
 __device__ __forceinline__ void epilogue_tile_rows(const ROW& ep, uint32_t tcol, int col0, int ncols, float lo_scale,
                                                    long long m, long long M, int n_base, int N, uint64_t* tm_empty,
                                                    int trace_tile) {
   constexpr int kAccStride = 256;
-  float acc[128];
+  float acc[kChunks * kEpiCols];
   // drain: every main chunk is requested up front and lands in its final registers; the cross chunks follow two at a time
   // through a 32-register temporary and are folded in (4 wait rounds instead of 8: a tcgen05.ld + wait round trip
   // measured ~330 cycles, and the tensor core idles for the whole drain)
 #pragma unroll
-  for (int c = 0; c < 8; ++c)
+  for (int c = 0; c < kChunks; ++c)
     if (c * kEpiCols < ncols) tmem_ld16_nowait(tcol + (uint32_t)(col0 + c * kEpiCols), &acc[c * kEpiCols]);
   if (kCross) {
 #pragma unroll
-    for (int c = 0; c < 8; c += 2) {
+    for (int c = 0; c < kChunks; c += 2) {
       if (c * kEpiCols < ncols) {
         float w[2 * kEpiCols];
         tmem_ld16_nowait(tcol + (uint32_t)(kAccStride + col0 + c * kEpiCols), w);
-        if ((c + 1) * kEpiCols < ncols)
+        if (c + 1 < kChunks && (c + 1) * kEpiCols < ncols)
           tmem_ld16_nowait(tcol + (uint32_t)(kAccStride + col0 + (c + 1) * kEpiCols), w + kEpiCols);
         tmem_ld_wait();
         if (c == 0) {
 #pragma unroll
-          for (int cc = 0; cc < 8; ++cc)
+          for (int cc = 0; cc < kChunks; ++cc)
             if (cc * kEpiCols < ncols) reg_fence_16(&acc[cc * kEpiCols]);
         }
         reg_fence_16(w);
         reg_fence_16(w + kEpiCols);
 #pragma unroll
         for (int i = 0; i < kEpiCols; ++i) acc[c * kEpiCols + i] = fmaf(w[i], lo_scale, acc[c * kEpiCols + i]);
-        if ((c + 1) * kEpiCols < ncols) {
+        if (c + 1 < kChunks && (c + 1) * kEpiCols < ncols) {
 #pragma unroll
           for (int i = 0; i < kEpiCols; ++i)
             acc[(c + 1) * kEpiCols + i] = fmaf(w[kEpiCols + i], lo_scale, acc[(c + 1) * kEpiCols + i]);
@@ -468,7 +471,7 @@ __device__ __forceinline__ void epilogue_tile_rows(const ROW& ep, uint32_t tcol,
   } else {
     tmem_ld_wait();
 #pragma unroll
-    for (int cc = 0; cc < 8; ++cc)
+    for (int cc = 0; cc < kChunks; ++cc)
       if (cc * kEpiCols < ncols) reg_fence_16(&acc[cc * kEpiCols]);
   }
   tc_fence_before();
@@ -477,18 +480,19 @@ __device__ __forceinline__ void epilogue_tile_rows(const ROW& ep, uint32_t tcol,
   if (m >= M) return;                                   // plain loads / stores below: no warp-collective operation
   typename ROW::Ctx ctx = ep.begin(m);
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
+  for (int c = 0; c < kChunks; ++c) {
     const int n = n_base + col0 + c * kEpiCols;
     if (c * kEpiCols < ncols && n < N) ep.row16(ctx, n, &acc[c * kEpiCols], c * kEpiCols);
   }
 }
 
-template <class EP, bool kCross>
+template <class EP, bool kCross, int kChunks = 8>
 __device__ __forceinline__ void epilogue_tile(const EP& ep, uint32_t tcol, int col0, int ncols, float lo_scale,
                                               long long m_base, int n_base, long long M, int N, float* stage, int lane,
                                               uint64_t* tm_empty, int trace_tile) {
   if constexpr (IsRowEpilogue<EP>::value)
-    epilogue_tile_rows<EP, kCross>(ep, tcol, col0, ncols, lo_scale, m_base + lane, M, n_base, N, tm_empty, trace_tile);
+    epilogue_tile_rows<EP, kCross, kChunks>(ep, tcol, col0, ncols, lo_scale, m_base + lane, M, n_base, N, tm_empty,
+                                            trace_tile);
   else
     epilogue_tile_staged<EP, kCross>(ep, tcol, col0, ncols, lo_scale, m_base, n_base, M, N, stage, lane, tm_empty,
                                      trace_tile);
@@ -654,7 +658,7 @@ __device__ __forceinline__ void tma_load_4d_2sm(const CUtensorMap* map, uint64_t
       : "memory");
 }
 
-template <class EP, bool kFast = false>
+template <class EP, bool kFast = false, int kChunks = 8>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 tc_conv2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
                 const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo, EP ep, ConvGeo g,
@@ -717,8 +721,8 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constan
       if (threadIdx.x == 0) trace2(tcount, 2);
       const long long m_base = (long long)mt * 256 + rank * BM + quarter * 32;
       const uint32_t tcol = tmem_base + ((uint32_t)(quarter * 32) << 16);
-      epilogue_tile<EP, !kFast>(ep, tcol, half * (BNr / 2), BNr / 2, kLoScale, m_base, nt * BNr, M, N, stage, lane, tm_empty,
-                                tcount);
+      epilogue_tile<EP, !kFast, kChunks>(ep, tcol, half * (BNr / 2), BNr / 2, kLoScale, m_base, nt * BNr, M, N, stage, lane,
+                                         tm_empty, tcount);
       if (threadIdx.x == 0) trace2(tcount, 4);
     }
   } else if (warp == kTmaWarp) {
@@ -991,7 +995,7 @@ int tc2_conv_f16_gn_fusable(int H, int W, int Cin, int Cout, int ks, int groups)
   if (!g_epi_overlap || !tc2_conv_f16_supported(H, W, Cin, Cout, ks)) return 0;
   if (groups <= 0 || Cout % groups != 0 || Cout % 16 != 0 || (H * W) % 32 != 0) return 0;
   const int bn = conv_f16_bn(Cout), cpg = Cout / groups;
-  if (cpg != 5 && cpg != 10 && cpg != 20) return 0;          // the instantiated group sizes: 160 / 320 / 640 channels
+  if ((cpg != 5 && cpg != 10 && cpg != 20) || bn != 160) return 0;   // the instantiated kernels: 160 / 320 / 640 channels, 160-wide tiles
   return (bn / 2) % cpg == 0 && (bn / 2) % 16 == 0 ? 1 : 0;
 }
 int tc2_conv_f16(const cvar_conv_args* a, cudaStream_t s) {
@@ -1023,10 +1027,14 @@ int tc2_conv_f16(const cvar_conv_args* a, cudaStream_t s) {
   const bool rows = g_epi_overlap && a->out_mode == 0 && a->Cout % 16 == 0 && tc2::aligned32(a->out) &&
                     tc2::aligned32(a->bias) && tc2::aligned32(a->resid) && a->bias != nullptr;
   auto kern_staged = tc2::tc_conv2_kernel<ConvEpilogue>;
-  auto kern_rows = g_fast_mode ? tc2::tc_conv2_kernel<tc2::ConvRow<0>, true> : tc2::tc_conv2_kernel<tc2::ConvRow<0>, false>;
-  auto kern_gn5 = g_fast_mode ? tc2::tc_conv2_kernel<tc2::ConvRow<5>, true> : tc2::tc_conv2_kernel<tc2::ConvRow<5>, false>;
-  auto kern_gn10 = g_fast_mode ? tc2::tc_conv2_kernel<tc2::ConvRow<10>, true> : tc2::tc_conv2_kernel<tc2::ConvRow<10>, false>;
-  auto kern_gn20 = g_fast_mode ? tc2::tc_conv2_kernel<tc2::ConvRow<20>, true> : tc2::tc_conv2_kernel<tc2::ConvRow<20>, false>;
+  // the thread's slice is BN / 2 columns: five 16-column chunks for the decoder's 160-wide tiles, eight for 256
+  const bool narrow = g.BN <= 160;
+  auto kern_rows = narrow ? (g_fast_mode ? tc2::tc_conv2_kernel<tc2::ConvRow<0>, true, 5> : tc2::tc_conv2_kernel<tc2::ConvRow<0>, false, 5>)
+                          : (g_fast_mode ? tc2::tc_conv2_kernel<tc2::ConvRow<0>, true, 8> : tc2::tc_conv2_kernel<tc2::ConvRow<0>, false, 8>);
+  // GroupNorm partials exist for 160 / 320 / 640 channels only: always 160-wide tiles
+  auto kern_gn5 = g_fast_mode ? tc2::tc_conv2_kernel<tc2::ConvRow<5>, true, 5> : tc2::tc_conv2_kernel<tc2::ConvRow<5>, false, 5>;
+  auto kern_gn10 = g_fast_mode ? tc2::tc_conv2_kernel<tc2::ConvRow<10>, true, 5> : tc2::tc_conv2_kernel<tc2::ConvRow<10>, false, 5>;
+  auto kern_gn20 = g_fast_mode ? tc2::tc_conv2_kernel<tc2::ConvRow<20>, true, 5> : tc2::tc_conv2_kernel<tc2::ConvRow<20>, false, 5>;
   const int cpg = a->gn_part != nullptr ? a->Cout / a->gn_groups : 0;
   cudaError_t e = cudaFuncSetAttribute(kern_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::kCvSmem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(kern_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::kCvSmem);

@@ -182,11 +182,8 @@ __device__ __forceinline__ void epi_chunk(const EP& ep, const float* a16, float*
 template <class EP, bool kCross>
 __device__ __forceinline__ void epilogue_tile_staged(const EP& ep, uint32_t tcol, int col0, int ncols, float lo_scale,
                                                      long long m_base, int n_base, long long M, int N, float* stage,
-                                                     int lane, uint64_t* tm_empty, int trace_tile, uint64_t* tm_full,
-                                                     uint32_t full_parity) {
+                                                     int lane, uint64_t* tm_empty, int trace_tile) {
   constexpr int kAccStride = 256;
-  mbar_wait(tm_full, full_parity);
-  tc_fence_after();
 #pragma unroll 1
   for (int c = 0; c < ncols; c += kEpiCols) {
     float v[kEpiCols], w[kEpiCols];
@@ -437,7 +434,7 @@ template <int CPG> struct IsRowEpilogue<ConvRow<CPG>> { static constexpr bool va
 template <class ROW, bool kCross, int kChunks>
 __device__ __forceinline__ void epilogue_tile_rows(const ROW& ep, uint32_t tcol, int col0, int ncols, float lo_scale,
                                                    long long m, long long M, int n_base, int N, uint64_t* tm_empty,
-                                                   int trace_tile, uint64_t* tm_full, uint32_t full_parity) {
+                                                   int trace_tile) {
   constexpr int kAccStride = 256;
   float acc[kChunks * kEpiCols];
   // drain: every main chunk is requested up front and lands in its final registers; the cross chunks follow two at a time
@@ -446,10 +443,6 @@ __device__ __forceinline__ void epilogue_tile_rows(const ROW& ep, uint32_t tcol,
 #pragma unroll
   for (int c = 0; c < kChunks; ++c)
     if (c * kEpiCols < ncols) tmem_ld16_nowait(tcol + (uint32_t)(col0 + c * kEpiCols), &acc[c * kEpiCols]);
-  // the caller waited for tm_main only: the MAIN accumulator is final (the MMA thread issues the last K-block's main MMAs
-  // first and commits them separately), its loads are in flight while the last cross-term MMAs still run
-  mbar_wait(tm_full, full_parity);
-  tc_fence_after();
   if (kCross) {
 #pragma unroll
     for (int c = 0; c < kChunks; c += 2) {
@@ -496,13 +489,13 @@ __device__ __forceinline__ void epilogue_tile_rows(const ROW& ep, uint32_t tcol,
 template <class EP, bool kCross, int kChunks = 8>
 __device__ __forceinline__ void epilogue_tile(const EP& ep, uint32_t tcol, int col0, int ncols, float lo_scale,
                                               long long m_base, int n_base, long long M, int N, float* stage, int lane,
-                                              uint64_t* tm_empty, int trace_tile, uint64_t* tm_full, uint32_t full_parity) {
+                                              uint64_t* tm_empty, int trace_tile) {
   if constexpr (IsRowEpilogue<EP>::value)
     epilogue_tile_rows<EP, kCross, kChunks>(ep, tcol, col0, ncols, lo_scale, m_base + lane, M, n_base, N, tm_empty,
-                                            trace_tile, tm_full, full_parity);
+                                            trace_tile);
   else
     epilogue_tile_staged<EP, kCross>(ep, tcol, col0, ncols, lo_scale, m_base, n_base, M, N, stage, lane, tm_empty,
-                                     trace_tile, tm_full, full_parity);
+                                     trace_tile);
 }
 
 // kFast (cvar_set_fast_mode; NOT a parity mode): the hi halves only - one MMA per product, half the operand bytes per
@@ -534,8 +527,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constan
   uint64_t* empty = bars + kNS;           // [S]
   uint64_t* tm_full = bars + 2 * kNS;
   uint64_t* tm_empty = bars + 2 * kNS + 1;
-  uint64_t* tm_main = bars + 2 * kNS + 2;      // the MAIN accumulator of the tile is final (committed before the last cross MMAs)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kNS + 3);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kNS + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();           // 0 = leader
@@ -550,7 +542,6 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constan
       mbar_init(&empty[s], 1);
     }
     mbar_init(tm_full, 1);
-    mbar_init(tm_main, 1);
     mbar_init(tm_empty, 2 * kEpiWarps * 32);
     fence_barrier_init();
   }
@@ -568,13 +559,13 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constan
     for (int tile = pair; tile < total_tiles; tile += npairs, ++tcount) {
       int mt, nt;
       tile_coords(tile, m_tiles, n_tiles, group_m, mt, nt);
-      mbar_wait(tm_main, tcount & 1);
+      mbar_wait(tm_full, tcount & 1);
       tc_fence_after();
       if (threadIdx.x == 0) trace2(tcount, 2);
       const long long m_base = (long long)mt * 256 + rank * BM + quarter * 32;
       const uint32_t tcol = tmem_base + ((uint32_t)(quarter * 32) << 16);
       epilogue_tile<EP, !kFast>(ep, tcol, half * (BN / 2), BN / 2, kLoScale, m_base, nt * BN, M, N, stage, lane, tm_empty,
-                                tcount, tm_full, (uint32_t)(tcount & 1));
+                                tcount);
       if (threadIdx.x == 0) trace2(tcount, 4);
     }
   } else if (warp == kTmaWarp) {
@@ -616,33 +607,14 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constan
           tc_fence_after();
           const uint64_t dah = G::desc(smem_u32(a_hi(s))), dal = G::desc(smem_u32(a_lo(s)));
           const uint64_t dbh = G::desc(smem_u32(b_hi(s))), dbl = G::desc(smem_u32(b_lo(s)));
-          if (kb == nkb - 1) {
-            // last K-block: the main products first, committed on their own barrier, so that the epilogue's loads of the
-            // MAIN accumulator overlap the eight cross-term MMAs (each accumulator still sees its MMAs in k order)
 #pragma unroll
-            for (int k = 0; k < BK / 8; ++k) {
-              const uint64_t adv = (uint64_t)(k * 2);
-              umma_2sm<F16>(d, dah + adv, dbh + adv, kIdesc, (kb | k) != 0);
-            }
-            umma_commit_2sm(tm_main);
+          for (int k = 0; k < BK / 8; ++k) {        // one MMA consumes 32 bytes of K: 8 TF32 or 16 FP16 elements
+            const uint64_t adv = (uint64_t)(k * 2);
             if (!kFast) {
-#pragma unroll
-              for (int k = 0; k < BK / 8; ++k) {
-                const uint64_t adv = (uint64_t)(k * 2);
-                umma_2sm<F16>(dl, dal + adv, dbh + adv, kIdesc, (kb | k) != 0);
-                umma_2sm<F16>(dl, dah + adv, dbl + adv, kIdesc, 1u);
-              }
+              umma_2sm<F16>(dl, dal + adv, dbh + adv, kIdesc, (kb | k) != 0);
+              umma_2sm<F16>(dl, dah + adv, dbl + adv, kIdesc, 1u);
             }
-          } else {
-#pragma unroll
-            for (int k = 0; k < BK / 8; ++k) {        // one MMA consumes 32 bytes of K: 8 TF32 or 16 FP16 elements
-              const uint64_t adv = (uint64_t)(k * 2);
-              if (!kFast) {
-                umma_2sm<F16>(dl, dal + adv, dbh + adv, kIdesc, (kb | k) != 0);
-                umma_2sm<F16>(dl, dah + adv, dbl + adv, kIdesc, 1u);
-              }
-              umma_2sm<F16>(d, dah + adv, dbh + adv, kIdesc, (kb | k) != 0);
-            }
+            umma_2sm<F16>(d, dah + adv, dbh + adv, kIdesc, (kb | k) != 0);
           }
           umma_commit_2sm(&empty[s]);
         }
@@ -711,8 +683,7 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constan
   uint64_t* empty = bars + kNS;
   uint64_t* tm_full = bars + 2 * kNS;
   uint64_t* tm_empty = bars + 2 * kNS + 1;
-  uint64_t* tm_main = bars + 2 * kNS + 2;      // the MAIN accumulator of the tile is final (committed before the last cross MMAs)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kNS + 3);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kNS + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -728,7 +699,6 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constan
       mbar_init(&empty[s], 1);
     }
     mbar_init(tm_full, 1);
-    mbar_init(tm_main, 1);
     mbar_init(tm_empty, 2 * kEpiWarps * 32);
     fence_barrier_init();
   }
@@ -746,13 +716,13 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constan
     for (int tile = pair; tile < total_tiles; tile += npairs, ++tcount) {
       int mt, nt;
       tile_coords(tile, m_tiles, n_tiles, group_m, mt, nt);
-      mbar_wait(tm_main, tcount & 1);
+      mbar_wait(tm_full, tcount & 1);
       tc_fence_after();
       if (threadIdx.x == 0) trace2(tcount, 2);
       const long long m_base = (long long)mt * 256 + rank * BM + quarter * 32;
       const uint32_t tcol = tmem_base + ((uint32_t)(quarter * 32) << 16);
       epilogue_tile<EP, !kFast, kChunks>(ep, tcol, half * (BNr / 2), BNr / 2, kLoScale, m_base, nt * BNr, M, N, stage, lane,
-                                         tm_empty, tcount, tm_full, (uint32_t)(tcount & 1));
+                                         tm_empty, tcount);
       if (threadIdx.x == 0) trace2(tcount, 4);
     }
   } else if (warp == kTmaWarp) {
@@ -802,31 +772,14 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constan
           tc_fence_after();
           const uint64_t dah = G::desc(smem_u32(a_hi(s))), dal = G::desc(smem_u32(a_lo(s)));
           const uint64_t dbh = G::desc(smem_u32(b_hi(s))), dbl = G::desc(smem_u32(b_lo(s)));
-          if (kb == nkb - 1) {                        // last K-block: main first, on its own barrier (see tc_gemm2_kernel)
 #pragma unroll
-            for (int k = 0; k < 2; ++k) {
-              const uint64_t adv = (uint64_t)(k * 2);
-              umma_2sm<true>(d, dah + adv, dbh + adv, idesc, (kb | k) != 0);
-            }
-            umma_commit_2sm(tm_main);
+          for (int k = 0; k < 2; ++k) {               // 32 halves = two K=16 steps of 32 bytes
+            const uint64_t adv = (uint64_t)(k * 2);
             if (!kFast) {
-#pragma unroll
-              for (int k = 0; k < 2; ++k) {
-                const uint64_t adv = (uint64_t)(k * 2);
-                umma_2sm<true>(dl, dal + adv, dbh + adv, idesc, (kb | k) != 0);
-                umma_2sm<true>(dl, dah + adv, dbl + adv, idesc, 1u);
-              }
+              umma_2sm<true>(dl, dal + adv, dbh + adv, idesc, (kb | k) != 0);
+              umma_2sm<true>(dl, dah + adv, dbl + adv, idesc, 1u);
             }
-          } else {
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {               // 32 halves = two K=16 steps of 32 bytes
-              const uint64_t adv = (uint64_t)(k * 2);
-              if (!kFast) {
-                umma_2sm<true>(dl, dal + adv, dbh + adv, idesc, (kb | k) != 0);
-                umma_2sm<true>(dl, dah + adv, dbl + adv, idesc, 1u);
-              }
-              umma_2sm<true>(d, dah + adv, dbh + adv, idesc, (kb | k) != 0);
-            }
+            umma_2sm<true>(d, dah + adv, dbh + adv, idesc, (kb | k) != 0);
           }
           umma_commit_2sm(&empty[s]);
         }

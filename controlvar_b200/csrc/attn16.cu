@@ -247,14 +247,6 @@ __device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t
                "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
                : "memory");
 }
-__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t* v) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(
-          taddr),
-      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
-      "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
-      : "memory");
-}
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // TMEM loads WITHOUT the wait: the destination registers are valid only after tmem_wait_ld()
@@ -407,7 +399,7 @@ attn16_tc_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_consta
     // nref = -ref * scale * log2e; t = fma(s, sl2, nref): the product is exact inside the FMA, and the rounding of nref
     // is a factor common to every key of the row (it cancels in the normalisation)
     auto chunk = [&](auto masked, uint32_t sb, int c, const float* a, float nref, int nvalid, float& rs) {
-      uint32_t pp[16];                             // cells [16c, 16c+8) = hi, [16c+8, 16c+16) = lo: one 16-column store
+      uint32_t ph[8], pl[8];
 #pragma unroll
       for (int i = 0; i < 16; i += 2) {
         float p0 = ex2_approx(fmaf(a[i], sl2, nref)), p1 = ex2_approx(fmaf(a[i + 1], sl2, nref));
@@ -417,33 +409,35 @@ attn16_tc_kernel(const __grid_constant__ CUtensorMap mapQhi, const __grid_consta
         }
         rs += p0 + p1;
         const __half2 h = __floats2half2_rn(p0, p1);                 // low half = lower key index
-        pp[i >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+        ph[i >> 1] = *reinterpret_cast<const uint32_t*>(&h);
         if (!kFast) {
           const float2 hf = __half22float2(h);
           const __half2 lo = __floats2half2_rn((p0 - hf.x) * kF16LoScale, (p1 - hf.y) * kF16LoScale);
-          pp[8 + (i >> 1)] = *reinterpret_cast<const uint32_t*>(&lo);
+          pl[i >> 1] = *reinterpret_cast<const uint32_t*>(&lo);
         }
       }
-      if (kFast)
-        tmem_st_32x32b_x8(tl + sb + 16 * c, pp);
-      else
-        tmem_st_32x32b_x16(tl + sb + 16 * c, pp);
+      tmem_st_32x32b_x8(tl + sb + 16 * c, ph);
+      if (!kFast) tmem_st_32x32b_x8(tl + sb + 16 * c + 8, pl);
     };
     // the whole tile against reference `ref`; chunk loads are prefetched one ahead (one exposed TMEM round trip)
     auto tile_pass = [&](auto masked, uint32_t sb, float nref, int nvalid, float& rs) {
-      // two 32-column loads (round 1: four of 16): half the tensor-memory round trips, the second in flight during the
-      // first half's exponentials
-      float a0[32], a1[32];
-      tmem_ld_nowait_x32(tl + sb, a0);
+      float a0[16], a1[16];
+      tmem_ld_nowait_x16(tl + sb, a0);
       tmem_wait_ld();
-      reg_fence32(a0);
-      tmem_ld_nowait_x32(tl + sb + 32, a1);
+      reg_fence16(a0);
+      tmem_ld_nowait_x16(tl + sb + 16, a1);
       chunk(masked, sb, 0, a0, nref, nvalid, rs);
-      chunk(masked, sb, 1, a0 + 16, nref, nvalid, rs);
       tmem_wait_ld();
-      reg_fence32(a1);
-      chunk(masked, sb, 2, a1, nref, nvalid, rs);
-      chunk(masked, sb, 3, a1 + 16, nref, nvalid, rs);
+      reg_fence16(a1);
+      tmem_ld_nowait_x16(tl + sb + 32, a0);
+      chunk(masked, sb, 1, a1, nref, nvalid, rs);
+      tmem_wait_ld();
+      reg_fence16(a0);
+      tmem_ld_nowait_x16(tl + sb + 48, a1);
+      chunk(masked, sb, 2, a0, nref, nvalid, rs);
+      tmem_wait_ld();
+      reg_fence16(a1);
+      chunk(masked, sb, 3, a1, nref, nvalid, rs);
     };
     // the same pass out of registers (kOnePass): a = columns [0,32), b = columns [32,64) of this row of S(j)
     auto tile_pass_regs = [&](auto masked, uint32_t sb, const float* a, const float* b, float nref, int nvalid, float& rs) {

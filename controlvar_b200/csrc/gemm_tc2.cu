@@ -58,7 +58,7 @@ constexpr uint32_t kPeerMask = 0xFEFFFFFFu;          // clears the CTA-rank bit 
 static int initial_group_m() {
   const char* e = getenv("CVAR_GROUP_M");
   int v = e ? atoi(e) : 4;
-  return v >= 1 && v <= 64 ? v : 4;
+  return (v >= 1 && v <= 64) || (v <= -1 && v >= -64) ? v : 4;   // < 0: column groups of -v weight tiles
 }
 int g_group_m = initial_group_m();      // CVAR_GROUP_M: A/B of the rasterisation group (diagnostic)
 // default 4:                           // pair-tiles (256 rows) per rasterisation group.  Small on purpose: every GEMM weight of the model (<= 38 MB as an FP16 pair at d24) fits in L2 next to the A rows of one group, so the weights stay resident and A streams through once; 16 / 32 (A of a group = 25 / 50 MB) thrashed the ~60 MB a die's L2 effectively holds: 2.2 / 3.1 GB of DRAM reads on fc1 against 0.44 GB of operands
@@ -126,6 +126,16 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
 }
 
 __device__ __forceinline__ void tile_coords(int tile, int m_tiles, int n_tiles, int kGroupM, int& mt, int& nt) {
+  if (kGroupM < 0) {   // column groups: -kGroupM weight tiles stay hot while every row tile passes them (row tile outer, weight tile inner)
+    const int per_group = -kGroupM * m_tiles;
+    const int g = tile / per_group;
+    const int first_n = g * -kGroupM;
+    const int gn = min(-kGroupM, n_tiles - first_n);
+    const int in_g = tile - g * per_group;
+    mt = in_g / gn;
+    nt = first_n + (in_g - mt * gn);
+    return;
+  }
   const int per_group = kGroupM * n_tiles;
   const int g = tile / per_group;
   const int first_m = g * kGroupM;

@@ -57,11 +57,16 @@ constexpr int kSmem = kStages * kStageBytes + kStagingBytes + 1024 + 1024;
 constexpr uint32_t kPeerMask = 0xFEFFFFFFu;          // clears the CTA-rank bit of a shared::cluster address (leader's copy)
 static int initial_group_m() {
   const char* e = getenv("CVAR_GROUP_M");
-  int v = e ? atoi(e) : 4;
-  return (v >= 1 && v <= 64) || (v <= -1 && v >= -64) ? v : 4;   // < 0: column groups of -v weight tiles
+  int v = e ? atoi(e) : 1;
+  return (v >= 1 && v <= 64) || (v <= -1 && v >= -64) ? v : 1;   // < 0: column groups of -v weight tiles
 }
-int g_group_m = initial_group_m();      // CVAR_GROUP_M: A/B of the rasterisation group (diagnostic)
-// default 4:                           // pair-tiles (256 rows) per rasterisation group.  Small on purpose: every GEMM weight of the model (<= 38 MB as an FP16 pair at d24) fits in L2 next to the A rows of one group, so the weights stay resident and A streams through once; 16 / 32 (A of a group = 25 / 50 MB) thrashed the ~60 MB a die's L2 effectively holds: 2.2 / 3.1 GB of DRAM reads on fc1 against 0.44 GB of operands
+// CVAR_GROUP_M: rasterisation of the pair-tiles (diagnostic knob).  g >= 1: groups of g row tiles, weight tile outer;
+// g <= -1: groups of -g weight tiles, row tile outer.  Default 1 = plain row-major: the 24 (fc1) column tiles of a row tile
+// run side by side, so A is read from DRAM exactly once (measured: profiles/r02_gemm_traffic.md).  What is re-read is the
+// WEIGHT pair: 38 MB at d24 fc1 / fc2 is swept once per wave of 74 pair-tiles and the part's L2 keeps only ~25-30 MB of such
+// a cyclic working set next to the A and result streams (each die caches its own copy of data every SM touches).  Larger
+// row groups only add A footprint (2.4 GB of reads at 8, 3.1 GB at 32); column groups trade weight re-reads for A re-reads.
+int g_group_m = initial_group_m();
 
 // Optional tile trace (diagnostics, cvar_debug_set_trace): CTA 0 stamps clock64() for its first 64 tiles.
 // trace[tile * 8 + ev]: 0 MMA thread has tensor memory (tm_empty seen), 1 last MMA of the tile committed,
@@ -514,7 +519,7 @@ template <class EP, bool F16, bool kFast = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 tc_gemm2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
                 const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo, EP ep,
-                long long M, int N, int K, int m_tiles, int n_tiles, int group_m) {
+                long long M, int N, int K, int m_tiles, int n_tiles, int group_m, int dbg_traffic) {
   using G = Geo<BK>;
   // instruction descriptor: D fp32; A/B format 2 = TF32 (kind::tf32) or 0 = FP16 (kind::f16); N, M of the pair tile
   constexpr uint32_t kFmt = F16 ? 0u : 2u;
@@ -585,8 +590,10 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constan
       for (int tile = pair; tile < total_tiles; tile += npairs) {
         int mt, nt;
         tile_coords(tile, m_tiles, n_tiles, group_m, mt, nt);
-        const int arow = mt * 256 + (int)rank * BM;
-        const int brow = nt * BN + (int)rank * (BN / 2);
+        // dbg_traffic (CVAR_DEBUG_TRAFFIC, diagnostics only - WRONG results): 1 = every tile reads the A rows of row tile 0,
+        // 2 = every tile reads the weight rows of column tile 0: attributes the DRAM reads of a launch to one operand
+        const int arow = ((dbg_traffic & 1) ? 0 : mt * 256) + (int)rank * BM;
+        const int brow = ((dbg_traffic & 2) ? 0 : nt * BN) + (int)rank * (BN / 2);
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % kNS;
           const uint32_t ph = (it / kNS) & 1;
@@ -913,7 +920,8 @@ int launch(const EP& ep, const void* A_hi, const void* A_lo, long long lda, cons
   }
   const int m_tiles = cdiv(M, 256), n_tiles = cdiv(N, BN);
   const int pairs = min(num_sms() / 2, m_tiles * n_tiles);
-  kern<<<2 * pairs, kThreads, kSmem, s>>>(mah, mal, mbh, mbl, ep, M, N, K, m_tiles, n_tiles, g_group_m);
+  static const int dbg_traffic = getenv("CVAR_DEBUG_TRAFFIC") ? atoi(getenv("CVAR_DEBUG_TRAFFIC")) : 0;
+  kern<<<2 * pairs, kThreads, kSmem, s>>>(mah, mal, mbh, mbl, ep, M, N, K, m_tiles, n_tiles, g_group_m, dbg_traffic);
   CVAR_CHECK_LAUNCH(name);
   return 0;
 }

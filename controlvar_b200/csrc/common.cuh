@@ -35,6 +35,11 @@ extern int g_fast_mode;     // 1: single-MMA FP16 operands (hi halves only) - NO
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// ln_stream.cu: the persistent streaming form of cvar_ln_modulate (FP16-pair output, large M)
+bool ln_stream_usable(int M, int C);
+int launch_ln_stream(const float* x, const float* scale, const float* shift, long long mod_stride, __half* y16_hi,
+                     __half* y16_lo, int M, int C, int rows_per_sample, float eps, cudaStream_t s);
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

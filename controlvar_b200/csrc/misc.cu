@@ -207,6 +207,14 @@ extern "C" int cvar_ln_modulate(const float* x, const float* scale, const float*
   dim3 grid(cdiv(M, 8));
   cudaStream_t s = (cudaStream_t)stream;
   int nv = C / 4;
+  static const bool stream_off = getenv("CVAR_LN_STREAM") != nullptr && getenv("CVAR_LN_STREAM")[0] == '0';   // A/B (diagnostic)
+  if (y == nullptr && y16_hi != nullptr && !stream_off && ln_stream_usable(M, C) && ((uintptr_t)x & 15) == 0) {
+    // large scales of the f16x3 path: persistent kernel, rows staged in shared memory by bulk copies (ln_stream.cu)
+    int rc = launch_ln_stream(x, scale, shift, mod_row_stride, y16_hi, y16_lo, M, C, rows_per_sample, eps, s);
+    if (rc) return rc;
+    CVAR_CHECK_LAUNCH("cvar_ln_modulate");
+    return 0;
+  }
   if (nv <= 32 * 4)
     ln_modulate_kernel<4><<<grid, 256, 0, s>>>(x, scale, shift, mod_row_stride, y, y_lo, y16_hi, y16_lo, M, C,
                                                rows_per_sample, eps);

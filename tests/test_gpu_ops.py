@@ -50,6 +50,29 @@ def test_ln_modulate(M, C, l):
     assert (out.cpu() - ref).abs().max().item() < 2e-5
 
 
+@pytest.mark.parametrize("C,l", [(768, 77), (1024, 50), (1536, 338), (1920, 200), (2048, 128)])
+def test_ln_modulate_streaming_kernel_is_bit_identical(C, l):
+    """Large-M FP16-pair calls take the persistent bulk-copy kernel (csrc/ln_stream.cu); the fp32-output call of the same
+    rows takes the warp-per-row kernel.  Same arithmetic: the pair must be exactly the split of the fp32 result, for a row count
+    that is not a multiple of anything (ragged last round of every warp's ring), and the fp32 result must match the oracle."""
+    torch.manual_seed(5)
+    M = 2 * 148 * 16 + 1237
+    R = M // l + 1
+    x = g(torch.randn(M, C) * 3 + 0.5)
+    ada = g(torch.randn(R, 6 * C) * 0.3)
+    scale, shift = ada[:, 2 * C:3 * C], ada[:, 4 * C:5 * C]
+    y32 = torch.empty(M, C, device=DEV)
+    ops.ln_modulate(x, scale, shift, 6 * C, y32, M, C, l, 1e-6)
+    pair = ops.F16Pair.empty((M, C), DEV)
+    pair.hi.fill_(7.0), pair.lo.fill_(7.0)
+    ops.ln_modulate(x, scale, shift, 6 * C, None, M, C, l, 1e-6, out16=pair)
+    want = ops.F16Pair.from_tensor(y32)
+    assert torch.equal(pair.hi, want.hi) and torch.equal(pair.lo, want.lo)
+    rows = torch.arange(M) // l
+    ref = O.ln_modulate(x.cpu(), scale.cpu()[rows], shift.cpu()[rows])
+    assert (y32.cpu() - ref).abs().max().item() < 2e-5
+
+
 def test_prologue_and_lvl_pos():
     cfg = PathConfig(depth=2, patch_nums=(1, 2, 3))
     sd = W.synthetic_var_state_dict(cfg, 0)

@@ -313,26 +313,34 @@ __global__ void gn_partial_kernel(const float* __restrict__ x, double* __restric
   }
 }
 
-// stage 2: fold mean / rstd with the affine into per-(n,c) a, b.
+// stage 2: fold mean / rstd with the affine into per-(n,c) a, b.  One warp per (image, group): the lanes stride over the partials
+// (2 048 per group at 256 x 256 from the conv epilogues), a fixed-order butterfly adds the 32 lane sums, then the lanes write the
+// group's channels.  (Round 1: one thread per CHANNEL walked all partials serially - 68 us per launch, 39 launches per call.)
 __global__ void gn_finalize_kernel(const double* __restrict__ scratch, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, float* __restrict__ a_out,
-                                   float* __restrict__ b_out, int HW, int C, int groups, int chunks, float eps) {
-  int n = blockIdx.x;
-  int cpg = C / groups;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    int g = c / cpg;
-    const double* sp = scratch + (((long long)n * groups + g) * chunks) * 2;
-    double s = 0.0, ss = 0.0;
-    for (int k = 0; k < chunks; ++k) {
-      s += sp[2 * k];
-      ss += sp[2 * k + 1];
-    }
-    double cnt = (double)HW * cpg;
-    double mean = s / cnt;
-    double var = ss / cnt - mean * mean;
-    if (var < 0.0) var = 0.0;
-    float rstd = 1.0f / sqrtf((float)var + eps);
-    float a = rstd * gamma[c];
+                                   float* __restrict__ b_out, int B, int HW, int C, int groups, int chunks, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (wid >= (long long)B * groups) return;
+  const int n = (int)(wid / groups), g = (int)(wid % groups);
+  const int cpg = C / groups;
+  const double2* sp = reinterpret_cast<const double2*>(scratch) + ((long long)n * groups + g) * chunks;
+  double s = 0.0, ss = 0.0;
+  for (int k = lane; k < chunks; k += 32) {
+    const double2 p = sp[k];
+    s += p.x;
+    ss += p.y;
+  }
+  s = warp_sum_d(s);
+  ss = warp_sum_d(ss);
+  const double cnt = (double)HW * cpg;
+  const double mean = s / cnt;
+  double var = ss / cnt - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float rstd = 1.0f / sqrtf((float)var + eps);
+  for (int j = lane; j < cpg; j += 32) {
+    const int c = g * cpg + j;
+    const float a = rstd * gamma[c];
     a_out[(long long)n * C + c] = a;
     b_out[(long long)n * C + c] = beta[c] - (float)mean * a;
   }
@@ -347,8 +355,8 @@ extern "C" int cvar_gn_stats(const float* x_nhwc, const float* gamma, const floa
   gn_partial_kernel<<<dim3(chunks, B), threads, 2 * C * sizeof(double), (cudaStream_t)stream>>>(x_nhwc, scratch, HW, C,
                                                                                               groups, chunks);
   CVAR_CHECK_LAUNCH("cvar_gn_stats/partial");
-  gn_finalize_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(scratch, gamma, beta, a_out, b_out, HW, C, groups, chunks,
-                                                          eps);
+  gn_finalize_kernel<<<cdiv((long long)B * groups, 8), 256, 0, (cudaStream_t)stream>>>(scratch, gamma, beta, a_out, b_out, B, HW,
+                                                                                        C, groups, chunks, eps);
   CVAR_CHECK_LAUNCH("cvar_gn_stats/finalize");
   return 0;
 }
@@ -358,11 +366,17 @@ extern "C" int cvar_gn_stats(const float* x_nhwc, const float* gamma, const floa
 extern "C" int cvar_gn_finalize_parts(const double* gn_part, const float* gamma, const float* beta, float* a_out, float* b_out,
                                       int B, int HW, int C, int groups, float eps, void* stream) {
   CVAR_REQUIRE(gn_part != nullptr && C % groups == 0 && HW % 32 == 0 && B > 0, "cvar_gn_finalize_parts: bad shape HW=%d C=%d", HW, C);
-  gn_finalize_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(gn_part, gamma, beta, a_out, b_out, HW, C, groups, HW / 32, eps);
+  gn_finalize_kernel<<<cdiv((long long)B * groups, 8), 256, 0, (cudaStream_t)stream>>>(gn_part, gamma, beta, a_out, b_out, B, HW,
+                                                                                        C, groups, HW / 32, eps);
   CVAR_CHECK_LAUNCH("cvar_gn_finalize_parts");
   return 0;
 }
 
+// kFastSilu (FP16-pair output only, i.e. the operand of an f16x3 convolution): x * rcp(1 + ex2(-x log2 e)) instead of the IEEE
+// division and the full-range expf - a few ulp, like the GELU of the dense-layer epilogue (gelu_tanh_fast), under the 2^-22 of
+// the pair product that consumes it.  With the exact form the kernel was issue-bound (~65 instructions per element, 3.07 of 4
+// issue slots, 0.72 of the copy bandwidth: profiles/r02_ln_affine.md).  The fp32-output path keeps the exact form.
+template <bool kFastSilu>
 __global__ void affine_nc_kernel(const float* __restrict__ x, const float* __restrict__ a, const float* __restrict__ b,
                                  float* __restrict__ y, __half* __restrict__ y16_hi, __half* __restrict__ y16_lo,
                                  long long HWC4, int C4, long long total4, int silu) {
@@ -379,10 +393,17 @@ __global__ void affine_nc_kernel(const float* __restrict__ x, const float* __res
   v.z = fmaf(v.z, av.z, bv.z);
   v.w = fmaf(v.w, av.w, bv.w);
   if (silu) {
-    v.x = silu_f(v.x);
-    v.y = silu_f(v.y);
-    v.z = silu_f(v.z);
-    v.w = silu_f(v.w);
+    if (kFastSilu) {
+      v.x = __fdividef(v.x, 1.0f + __expf(-v.x));
+      v.y = __fdividef(v.y, 1.0f + __expf(-v.y));
+      v.z = __fdividef(v.z, 1.0f + __expf(-v.z));
+      v.w = __fdividef(v.w, 1.0f + __expf(-v.w));
+    } else {
+      v.x = silu_f(v.x);
+      v.y = silu_f(v.y);
+      v.z = silu_f(v.z);
+      v.w = silu_f(v.w);
+    }
   }
   if (y16_hi != nullptr) {
     const float vv[4] = {v.x, v.y, v.z, v.w};
@@ -439,7 +460,9 @@ extern "C" int cvar_affine_nc(const float* x_nhwc, const float* a, const float* 
   CVAR_REQUIRE((y16_hi == nullptr) == (y16_lo == nullptr), "cvar_affine_nc: y16_hi/y16_lo must come together");
   long long total4 = (long long)B * HW * C / 4;
   CVAR_REQUIRE(B <= 65535 && (long long)HW * C / 4 < (1LL << 31), "cvar_affine_nc: shape too large");
-  affine_nc_kernel<<<dim3(cdiv((long long)HW * C / 4, 256), B), 256, 0, (cudaStream_t)stream>>>(
+  static const bool exact_silu = getenv("CVAR_EXACT_SILU") != nullptr && getenv("CVAR_EXACT_SILU")[0] == '1';   // A/B (diagnostic)
+  auto kern = (y == nullptr && !exact_silu) ? affine_nc_kernel<true> : affine_nc_kernel<false>;
+  kern<<<dim3(cdiv((long long)HW * C / 4, 256), B), 256, 0, (cudaStream_t)stream>>>(
       x_nhwc, a, b, y, reinterpret_cast<__half*>(y16_hi), reinterpret_cast<__half*>(y16_lo), (long long)HW * C / 4, C / 4,
       total4, silu);
   CVAR_CHECK_LAUNCH("cvar_affine_nc");

@@ -291,11 +291,22 @@ def test_affine_and_upsample_pair_producers():
     B, H, W, Cn = 2, 8, 8, 64
     x, a, b = g(torch.randn(B, H, W, Cn)), g(torch.rand(B, Cn) + 0.5), g(torch.randn(B, Cn))
     y = torch.empty(B, H, W, Cn, device=DEV)
-    ops.affine_nc(x, a, b, y, B, H * W, Cn, silu=True)
     p = ops.F16Pair.empty((B, H, W, Cn), DEV)
-    ops.affine_nc(x, a, b, None, B, H * W, Cn, silu=True, out16=p)
+    # without SiLU the pair is exactly the split of the fp32 result
+    ops.affine_nc(x, a, b, y, B, H * W, Cn, silu=False)
+    ops.affine_nc(x, a, b, None, B, H * W, Cn, silu=False, out16=p)
     chk = ops.F16Pair.from_tensor(y)
     assert torch.equal(chk.hi, p.hi) and torch.equal(chk.lo, p.lo)
+    # with SiLU the pair-only call uses x * rcp(1 + ex2(-x log2 e)) (a few ulp; the fp32 output keeps the IEEE division and expf):
+    # both must sit close to the float64 value
+    ops.affine_nc(x, a, b, y, B, H * W, Cn, silu=True)
+    ops.affine_nc(x, a, b, None, B, H * W, Cn, silu=True, out16=p)
+    t = x.double() * a.double()[:, None, None, :] + b.double()[:, None, None, :]
+    want = t / (1.0 + torch.exp(-t))
+    # fp32 rounding of a*x+b (2^-24) is amplified by up to ~(1 + |t|) through SiLU; __expf adds 2 + 1.16 |t| ulp; the pair 2^-22
+    assert ((y.double() - want).abs() <= 1e-6 * want.abs() + 1e-8).all()
+    assert ((p.float().double() - want).abs() <= 3e-6 * want.abs() + 1e-8).all()
+    assert (p.float() - y).abs().max().item() < 2e-6
     up = ops.F16Pair.empty((B, 2 * H, 2 * W, Cn), DEV)
     ops.upsample2x_split_f16(x, up, B, H, W, Cn)
     ref = ops.F16Pair.from_tensor(x.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2).contiguous())

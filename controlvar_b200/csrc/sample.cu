@@ -81,11 +81,17 @@ __global__ void __launch_bounds__(NT) cfg_sample_kernel(const float* __restrict_
   {
     const float* lg = logits + ((long long)b * l + t) * V_FIXED;
     const long long gstride = (long long)B * l * V_FIXED;
+    // (unrolled over the four possible groups: the run-time loop cost ~45 instructions per element, 10 % of the kernel)
+    const float* lg1 = lg + (groups > 1 ? gstride : 0);
+    const float* lg2 = lg + (groups > 2 ? 2 * gstride : 0);
+    const float* lg3 = lg + (groups > 3 ? 3 * gstride : 0);
 #pragma unroll
     for (int i = 0; i < PER; ++i) {
       int e = tid + i * NT;
       float v = __fmul_rn(coef.c[0], lg[e]);
-      for (int g = 1; g < groups; ++g) v = __fadd_rn(v, __fmul_rn(coef.c[g], lg[g * gstride + e]));
+      if (groups > 1) v = __fadd_rn(v, __fmul_rn(coef.c[1], lg1[e]));
+      if (groups > 2) v = __fadd_rn(v, __fmul_rn(coef.c[2], lg2[e]));
+      if (groups > 3) v = __fadd_rn(v, __fmul_rn(coef.c[3], lg3[e]));
       sm.vals[e] = v;
     }
   }
@@ -217,14 +223,16 @@ __global__ void __launch_bounds__(NT) cfg_sample_kernel(const float* __restrict_
 #pragma unroll
     for (int i = 0; i < PER; ++i) {
       float v = from_orderable((unsigned)(sm.keys[tid * PER + i] >> 32));
-      ev[i] = expf(v - vmax);
+      ev[i] = v == -INFINITY ? 0.f : expf(v - vmax);       // expf(-inf) is exactly 0: same value, no range reduction
       loc += ev[i];
     }
     const float total = block_sum(loc, sm.redf);
     float run = 0.f;
 #pragma unroll
     for (int i = 0; i < PER; ++i) {
-      ev[i] = ev[i] / total;
+      // 0 / total is exactly 0, but the IEEE division sends a zero numerator down its slow path (FCHK): three quarters of
+      // the entries are removed ones, and that path was 19 % of the kernel's instructions (profiles/r02_sample.md)
+      ev[i] = ev[i] == 0.f ? 0.f : ev[i] / total;
       run += ev[i];
       ev[i] = run;
     }
@@ -260,7 +268,8 @@ __global__ void __launch_bounds__(NT) cfg_sample_kernel(const float* __restrict_
   float loc = 0.f;
 #pragma unroll
   for (int i = 0; i < PER; ++i) {
-    ev[i] = expf(sm.vals[tid + i * NT] - vmax);
+    const float v = sm.vals[tid + i * NT];
+    ev[i] = v == -INFINITY ? 0.f : expf(v - vmax);         // removed entries: expf(-inf) is exactly 0
     loc += ev[i];
   }
   const float total = block_sum(loc, sm.redf);
@@ -276,7 +285,10 @@ __global__ void __launch_bounds__(NT) cfg_sample_kernel(const float* __restrict_
 #pragma unroll
     for (int i = 0; i < PER; ++i) {
       int e = tid + i * NT;
-      float r = (ev[i] / total) / qr[e];
+      // A removed entry has probability exactly 0, so (0 / total) / q is 0 for every q > 0: it can never beat the largest
+      // surviving entry ((1 / total) / q > 0).  Its noise value is not loaded and its two divisions - which take the IEEE
+      // slow path for a zero numerator - are not evaluated.
+      float r = ev[i] == 0.f ? 0.f : (ev[i] / total) / qr[e];
       if (r > best) {        // ascending e: the first maximum wins, like torch.argmax
         best = r;
         besti = e;

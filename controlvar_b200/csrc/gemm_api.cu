@@ -1,4 +1,5 @@
 // C-ABI entry points built on the GEMM engines: dense layers, fused QKV + KV-cache append, decoder convolutions.
+#include <stdlib.h>
 #include "sgemm.cuh"
 
 using namespace cvar;
@@ -316,6 +317,83 @@ __global__ void __launch_bounds__(kCoTH * kCoTW) conv3x3_small_cout_tiled_kernel
   ep.store(m, 0, v4, COUT, 0);
 }
 
+// Round 2, second step: the tile kernel above is bound by shared-memory bandwidth, not by its FMAs - per 16-byte slice of a
+// pixel it issues one 4-wavefront activation read and three broadcast weight reads for 12 FMAs (7 wavefronts per 12 warp-FMAs; the
+// LSU pipe delivers one wavefront per cycle, the four schedulers 12 FMAs in 3).  Here a thread owns FOUR vertically adjacent
+// output pixels: the six input rows it needs are read once per (kx, channel slice) and feed 3 ky x 3 channels x 4 rows x 4 = 144
+// FMAs against 6 + 9 reads (2.75 wavefronts per 12 FMAs).  Block = 128 threads = a 4 x 128 tile, 16-channel chunks (pixel pitch
+// 20 floats: conflict-free float4 reads), the chunk's 432 weights reloaded per chunk: 64 KB of shared memory, three CTAs per SM,
+// and the 6 x 130 halo costs 1.5 reads per input element instead of 2.
+constexpr int kR4TH = 4, kR4TW = 128, kR4Ch = 16, kR4Pitch = 20;
+template <int COUT>
+__global__ void __launch_bounds__(kR4TW) conv3x3_small_cout_rows4_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                                         ConvEpilogue ep, int H, int W, int Cin) {
+  extern __shared__ __align__(16) float smem_r4[];
+  float* w_s = smem_r4;                                   // [COUT][9][kR4Ch]
+  float* tile = smem_r4 + COUT * 9 * kR4Ch;               // [kR4TH + 2][kR4TW + 2][kR4Pitch]
+  const int K = 9 * Cin;
+  const int px = threadIdx.x;
+  const int x0 = blockIdx.x * kR4TW, y0 = blockIdx.y * kR4TH;
+  const long long n = blockIdx.z;
+  float acc[kR4TH][COUT];
+#pragma unroll
+  for (int j = 0; j < kR4TH; ++j)
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) acc[j][c] = 0.f;
+  constexpr int kHaloVec = (kR4TH + 2) * (kR4TW + 2) * (kR4Ch / 4);
+  for (int c0 = 0; c0 < Cin; c0 += kR4Ch) {
+    __syncthreads();                                      // previous chunk consumed
+    for (int i = px; i < COUT * 9 * (kR4Ch / 4); i += kR4TW) {
+      const int c4 = i & (kR4Ch / 4 - 1);
+      const int ct = i / (kR4Ch / 4);                     // channel * 9 + tap
+      const int c = ct / 9, tap = ct - 9 * c;
+      *reinterpret_cast<float4*>(w_s + ct * kR4Ch + c4 * 4) = ld4(w + (long long)c * K + tap * Cin + c0 + c4 * 4);
+    }
+    for (int i = px; i < kHaloVec; i += kR4TW) {
+      const int c4 = i & (kR4Ch / 4 - 1);
+      const int pp = i / (kR4Ch / 4);
+      const int r = pp / (kR4TW + 2), p = pp - r * (kR4TW + 2);
+      const int yy = y0 - 1 + r, xx = x0 - 1 + p;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = ld4(x + ((n * H + yy) * W + xx) * Cin + c0 + c4 * 4);
+      *reinterpret_cast<float4*>(tile + (r * (kR4TW + 2) + p) * kR4Pitch + c4 * 4) = v;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int kx = 0; kx < 3; ++kx) {
+#pragma unroll
+      for (int c4 = 0; c4 < kR4Ch / 4; ++c4) {
+        float4 xv[kR4TH + 2];
+#pragma unroll
+        for (int r = 0; r < kR4TH + 2; ++r)
+          xv[r] = *reinterpret_cast<const float4*>(tile + (r * (kR4TW + 2) + px + kx) * kR4Pitch + c4 * 4);
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+          for (int c = 0; c < COUT; ++c) {
+            const float4 ww = *reinterpret_cast<const float4*>(w_s + (c * 9 + ky * 3 + kx) * kR4Ch + c4 * 4);
+#pragma unroll
+            for (int j = 0; j < kR4TH; ++j) {
+              acc[j][c] = fmaf(xv[j + ky].x, ww.x, acc[j][c]);
+              acc[j][c] = fmaf(xv[j + ky].y, ww.y, acc[j][c]);
+              acc[j][c] = fmaf(xv[j + ky].z, ww.z, acc[j][c]);
+              acc[j][c] = fmaf(xv[j + ky].w, ww.w, acc[j][c]);
+            }
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < kR4TH; ++j) {
+    float v4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) v4[c] = acc[j][c];
+    const long long m = (n * H + (y0 + j)) * W + x0 + px;
+    ep.store(m, 0, v4, COUT, 0);
+  }
+}
+
 extern "C" int cvar_conv2d(const cvar_conv_args* a, void* stream) {
   CVAR_REQUIRE(a != nullptr, "cvar_conv2d: null args");
   CVAR_REQUIRE(a->ks == 1 || a->ks == 3, "cvar_conv2d: ks must be 1 or 3");
@@ -348,6 +426,18 @@ extern "C" int cvar_conv2d(const cvar_conv_args* a, void* stream) {
       (size_t)3 * K * sizeof(float) <= 48 * 1024) {
     ConvEpilogue ep3{a->out, a->bias, nullptr, a->Cout, a->out_mode, Hout, Wout, a->out_rows_total, a->row_offset};
     ep3.out_samples = a->out_samples;
+    static const bool rows4_off = getenv("CVAR_CONV3_ROWS4") != nullptr && getenv("CVAR_CONV3_ROWS4")[0] == '0';   // A/B (diagnostic)
+    if (!rows4_off && Wout % kR4TW == 0 && Hout % kR4TH == 0 && a->Cin % kR4Ch == 0 && a->B <= 65535 &&
+        ((((uintptr_t)a->x) | ((uintptr_t)a->w)) & 15) == 0) {
+      const size_t smem_r = ((size_t)3 * 9 * kR4Ch + (size_t)(kR4TH + 2) * (kR4TW + 2) * kR4Pitch) * sizeof(float);
+      auto kern = conv3x3_small_cout_rows4_kernel<3>;
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r);
+      CVAR_REQUIRE(e == cudaSuccess, "cvar_conv2d[cout3]: cannot raise shared memory: %s", cudaGetErrorString(e));
+      dim3 grid(Wout / kR4TW, Hout / kR4TH, a->B);
+      kern<<<grid, kR4TW, smem_r, s>>>(a->x, a->w, ep3, Hout, Wout, a->Cin);
+      CVAR_CHECK_LAUNCH("cvar_conv2d[cout3/rows4]");
+      return 0;
+    }
     const size_t smem_t = ((size_t)3 * K + (size_t)(kCoTH + 2) * (kCoTW + 2) * kCoPitch) * sizeof(float);
     if (Wout % kCoTW == 0 && Hout % kCoTH == 0 && a->Cin % kCoCh == 0 && a->B <= 65535 && smem_t <= 100 * 1024 &&
         ((((uintptr_t)a->x) | ((uintptr_t)a->w)) & 15) == 0) {

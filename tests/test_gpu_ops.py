@@ -320,6 +320,25 @@ def test_conv_out_image_mode():
     assert img[:, :, :H].abs().max().item() == 0
 
 
+@pytest.mark.parametrize("H,Wd,cin", [(8, 128, 32), (12, 256, 160), (4, 128, 16)])
+def test_conv_out_image_mode_wide(H, Wd, cin):
+    """Wide images (W a multiple of 128, H of 4) take the 4-rows-per-thread shared-memory kernel: zero padding on all four sides,
+    several row tiles, several 16-channel chunks, stacked halves (out_samples) - against fp64."""
+    torch.manual_seed(13)
+    B = 4
+    x = torch.randn(B, cin, H, Wd)
+    w = torch.randn(3, cin, 3, 3) / math.sqrt(cin * 9) * 3
+    b = torch.randn(3) * 0.1
+    ref = F.conv2d(x.double(), w.double(), b.double(), padding=1).clamp_(-1, 1).add_(1).mul_(0.5)
+    img = torch.zeros(B // 2, 3, 2 * H, Wd, device=DEV)
+    wp = ops.repack_conv_weight(g(w), torch.empty(3, 9 * cin, device=DEV))
+    # maps 0..1 are the upper halves of images 0..1, maps 2..3 the lower halves (the sampler's stacked decode)
+    ops.conv2d(g(x.permute(0, 2, 3, 1)), wp, g(b), img, B, H, Wd, cin, 3, 3, out_mode=1, out_rows_total=2 * H, row_offset=0,
+               out_samples=B // 2)
+    got = torch.cat((img[:, :, :H], img[:, :, H:]), 0).cpu().double()
+    assert (got - ref).abs().max().item() < 1e-5
+
+
 def test_fhat_to_img_matches_oracle_decoder():
     """VQVAE.fhat_to_img end to end (vqvae.py:88-89): pixels within 1e-4 abs of the fp32 oracle."""
     from controlvar_b200 import VQVAE

@@ -1,3 +1,3 @@
-mkdir -p gpurun_out
-timeout 300 python tools/time_sample.py 2>&1 | tail -5
-timeout 900 python -m pytest tests/test_gpu_ops.py tests/test_gpu_sampler.py tests/test_gpu_conditional.py -m gpu -x -q 2>&1 | tail -3
+CVAR_CONV3_ROWS4=0 timeout 200 python tools/time_conv_out.py 2>&1 | tail -1
+timeout 200 python tools/time_conv_out.py 2>&1 | tail -1
+timeout 600 python -m pytest tests/test_gpu_ops.py -m gpu -x -q -k "conv_out or fhat" 2>&1 | tail -3

@@ -22,7 +22,9 @@ CLASSES = [
     (r"attn_tc_kernel", "attention, tcgen05 (attn_tc_kernel, l >= 64)"),
     (r"attn_kvcache_kernel", "attention, SIMT (attn_kvcache_kernel, l < 64)"),
     (r"sgemm_kernel", "SIMT fp32 GEMM / conv (small, ragged or accuracy-pinned layers)"),
-    (r"ln_modulate_kernel", "ln_modulate_kernel"),
+    (r"ln_modulate_stream_kernel", "ln_modulate_stream_kernel (large scales: persistent, rows by bulk copy, modulation vectors in shared memory)"),
+    (r"ln_modulate_kernel", "ln_modulate_kernel (small scales: one warp per row)"),
+    (r"conv3x3_small_cout", "Decoder.conv_out, 3 output channels (conv3x3_small_cout_*_kernel, SIMT fp32)"),
     (r"affine_nc_kernel", "affine_nc_kernel (GroupNorm + SiLU, writes the FP16 pair)"),
     (r"upsample2x_split_kernel", "upsample2x_split_kernel"),
     (r"split_f16_kernel", "split_f16_kernel"),

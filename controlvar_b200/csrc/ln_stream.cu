@@ -97,7 +97,10 @@ __global__ void __launch_bounds__(512) ln_modulate_stream_kernel(const float* __
         }
       }
       const float mean = warp_sum(s) / (float)C;
-      // every lane's reads of the slot have returned (the sum consumed them): it can take the warp's next row
+      // every lane's reads of the slot have returned (the butterfly sum consumed them, and lane 0's result depends on all of
+      // them); __syncwarp orders them before lane 0's refill in the memory model as well.  (compute-sanitizer racecheck still
+      // reports the bulk copy against these reads: it does not follow mbarrier / async-proxy completion.)
+      __syncwarp();
       if (lane == 0 && ahead.valid()) {
         mbar_arrive_expect_tx(&bars[slot], row_bytes);
         bulk_load_row(ring + (size_t)slot * C, x + ahead.m * C, row_bytes, &bars[slot]);

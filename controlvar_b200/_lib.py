@@ -84,6 +84,10 @@ PROTOTYPES = {
                                   C.c_void_p]),
     "cvar_cfg_sample_multi": (C.c_int, [c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int,
                                         C.c_int, C.c_double, c_f, c_f, C.c_int, C.c_void_p]),
+    "cvar_cfg_sample_masked": (C.c_int, [c_f, c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int,
+                                         C.c_int, C.c_double, c_f, c_f, C.c_int, C.c_void_p]),
+    "cvar_gumbel_embed": (C.c_int, [c_f, c_f, c_f, c_f, C.c_longlong, C.c_longlong, C.c_int, C.c_int, C.c_double, C.c_double,
+                                    C.c_void_p]),
     "cvar_vq_step_ex": (C.c_int, [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, C.c_int, C.c_int, C.c_int,
                                   C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "cvar_area_pool_nc": (C.c_int, [c_f, c_f, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),

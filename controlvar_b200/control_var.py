@@ -19,7 +19,8 @@ per call instead of once per block per scale; the KV cache is a pre-allocated ar
 ``torch.cat`` growth; the control and image halves of ``f_hat`` are decoded in one decoder pass over 2B maps
 (``VQVAE._fhat_halves_to_img``) instead of two passes over B.
 Branches no released configuration uses (``separator``, ``type_pos``, ``bidirectional``, ``separate_decoding``,
-``shared_aln``, ``aln < 0``, ``mask_factor == 1``, ``more_smooth``) raise NotImplementedError.
+``shared_aln``, ``aln < 0``, ``mask_factor == 1``) raise NotImplementedError.  ``more_smooth`` (the reference's
+visualisation-only Gumbel-softmax mixture, control_var.py:511-515) runs eagerly: cvar_cfg_sample_masked + cvar_gumbel_embed.
 """
 from __future__ import annotations
 
@@ -286,8 +287,6 @@ class ControlVAR(nn.Module):
         more_smooth=False, cond_type=None,
     ) -> torch.Tensor:   # (B, 3, 2*H, W) in [0, 1]: control map on top, image below
         """Drop-in for ControlVAR.autoregressive_infer_cfg (control_var.py:356-565), released branch."""
-        if more_smooth:
-            raise NotImplementedError("more_smooth (Gumbel-softmax visualisation path) is not implemented")
         if not self.pos_1LC.is_cuda:
             raise RuntimeError("controlvar_b200.ControlVAR runs on CUDA only (no CPU fallback); call .cuda() first")
         dev = self.device
@@ -320,7 +319,7 @@ class ControlVAR(nn.Module):
         label_R = torch.cat((label_B, torch.full_like(label_B, self.num_classes)))         # control_var.py:381
         cond_R = torch.cat((cond_type, torch.full_like(cond_type, 4)))                     # control_var.py:399-400
         return self._sample(B, label_R, cond_R, groups=2, mix=lambda ratio: (cfg * ratio,), replicas=1,
-                            top_k=top_k, top_p=top_p, rng=rng)
+                            top_k=top_k, top_p=top_p, rng=rng, more_smooth=bool(more_smooth))
 
     @torch.no_grad()
     def conditional_infer_cfg(
@@ -332,8 +331,6 @@ class ControlVAR(nn.Module):
         replicas [class + type | type | none | none] of every sample run side by side (4B rows); c_mask / c_img
         (List[(B, pn*pn)] from VQVAE.img_to_idxBl) teacher-force the control / image tokens of the first three; the
         image is decoded from the first replica."""
-        if more_smooth:
-            raise NotImplementedError("more_smooth (Gumbel-softmax visualisation path) is not implemented")
         if not self.multi_cond:
             raise NotImplementedError("conditional_infer_cfg needs multi_cond=True (it reads cond_embed, control_var.py:265)")
         if not self.pos_1LC.is_cuda:
@@ -363,21 +360,22 @@ class ControlVAR(nn.Module):
         return self._sample(B, label_R, cond_R, groups=4,
                             mix=lambda ratio: (cfg[0] * ratio, cfg[1] * ratio, cfg[2] * ratio), replicas=4,
                             top_k=top_k, top_p=top_p, rng=rng, c_mask=self._check_forced(c_mask, B, "c_mask"),
-                            c_img=self._check_forced(c_img, B, "c_img"))
+                            c_img=self._check_forced(c_img, B, "c_img"), more_smooth=bool(more_smooth))
 
     # ------------------------------------------------------------------------------------ the shared scale loop
     def _sample(self, B: int, label_R: torch.Tensor, cond_R: torch.Tensor, *, groups: int, mix, replicas: int, top_k, top_p,
-                rng, c_mask=None, c_img=None) -> torch.Tensor:
+                rng, c_mask=None, c_img=None, more_smooth: bool = False) -> torch.Tensor:
         """Eager launch sequence, or capture / replay of it as a CUDA graph (see __init__).  Eager whenever a debug hook or
         the per-kernel profiler is active (both put host logic between launches)."""
         SN = len(self.patch_nums)
         ts_all = tuple(tuple(float(t) for t in mix(si / self.num_stages_minus_1)) for si in range(SN))
         Bf, V, lens = B * replicas, self.V, self.cfg.scale_lens
         graphable = (self.use_graphs and self.debug_forced_idx is None and not self.debug_capture_logits
-                     and self.debug_noise_fn is None and not ops.profiling())
-        if not graphable:
+                     and self.debug_noise_fn is None and not ops.profiling() and not more_smooth)
+        if not graphable:      # (more_smooth - the reference's visualisation-only mode - draws twice per scale: kept eager)
             return self._sample_body(B, label_R, cond_R, groups, ts_all, replicas, top_k, top_p,
-                                     lambda si, rows: self._noise_for_scale(si, rows, rng), c_mask, c_img)
+                                     lambda si, rows: self._noise_for_scale(si, rows, rng), c_mask, c_img,
+                                     more_smooth=more_smooth)
         vae = self.vae_proxy[0]
         key = (B, groups, replicas, int(top_k), float(top_p), ts_all, c_mask is not None, c_img is not None,
                ops.get_gemm_engine(), ops.get_fast_mode(), self.kv16, self.rng_device, vae.tc_min_hw, vae.ksplit_min_k)
@@ -440,7 +438,7 @@ class ControlVAR(nn.Module):
         return out
 
     def _sample_body(self, B: int, label_R: torch.Tensor, cond_R: torch.Tensor, groups: int, ts_all, replicas: int, top_k,
-                     top_p, noise_fn, c_mask=None, c_img=None) -> torch.Tensor:
+                     top_p, noise_fn, c_mask=None, c_img=None, more_smooth: bool = False) -> torch.Tensor:
         """The 10-scale loop both entry points share.  groups: guidance row groups in the transformer batch (R = groups*B
         rows).  replicas = 1: autoregressive_infer_cfg - one f_hat per sample, the next map is written to both CFG halves.
         replicas = groups = 4: conditional_infer_cfg - every replica row keeps its own samples and f_hat.
@@ -478,7 +476,26 @@ class ControlVAR(nn.Module):
                 q_noise = noise_fn(si, Bf * l)
             if self.debug_capture_logits:
                 self.last_logits.append(logits[:M].view(R, l, V).clone())
-            if groups == 2:
+            if more_smooth:
+                # control_var.py:511-515 / 326-331: the next map is built from a Gumbel-softmax MIXTURE of code vectors taken
+                # from the logits as sample_with_top_k_top_p_ left them, not from the sampled (or forced) tokens.  Two draws
+                # per scale from the same generator: torch.multinomial's, then helpers.py:26's.
+                masked = self._buf("masked_logits", (B * lmax, V))
+                coef = ((_f32(1 + ts[0]), -_f32(ts[0])) if groups == 2 else
+                        (_f32(1 + ts[0]), _f32(ts[1] - ts[0]), _f32(ts[2] - ts[1]), -_f32(ts[2])))
+                ops.cfg_sample_masked(logits, q_noise, idx, masked, B, l, V, coef, replicas, top_k, top_p,
+                                      forced_first=None if c_mask is None else c_mask[si],
+                                      forced_second=None if c_img is None else c_img[si],
+                                      forced_replicas=3 if groups == 4 else 0)
+                if self.debug_noise_fn is not None:
+                    e_noise = self.debug_noise_fn(si, Bf * l, V).to(device=dev, dtype=torch.float32).contiguous()
+                else:
+                    e_noise = noise_fn(si, Bf * l)
+                ratio = si / self.num_stages_minus_1
+                h_soft = self._buf("h_soft", (Bf * lmax, Cvae))
+                ops.gumbel_embed(masked, e_noise, cst["codebook"], h_soft, B * l, Bf * l, V, Cvae, 1 + ratio,
+                                 max(0.27 * (1 - ratio * 0.95), 0.005))
+            elif groups == 2:
                 ops.cfg_sample(logits, q_noise, idx, B, l, V, ts[0], top_k, top_p)
             else:
                 # (1 + t1)*L0 + (t2 - t1)*L1 + (t3 - t2)*L2 - t3*L3: python forms the scalars in double precision and
@@ -494,7 +511,12 @@ class ControlVAR(nn.Module):
             # VQ step + next-scale input
             phi_w, phi_b = cst["phi"][self.cfg.phi_index(si)]
             pn_next = self.patch_nums[si + 1] if si != SN - 1 else 0
-            ops.vq_step(idx, cst["codebook"], cst["U"].get(pn), phi_w, phi_b,
+            if more_smooth:
+                # the VQ step gathers embedding[idx]: row r of the mixture table through the identity index = the mixture itself
+                vq_idx, vq_table = self._arange_idx(Bf * lmax)[:Bf * l], h_soft
+            else:
+                vq_idx, vq_table = idx, cst["codebook"]
+            ops.vq_step(vq_idx, vq_table, cst["U"].get(pn), phi_w, phi_b,
                         self.get_parameter("word_embed.weight"), self.get_parameter("word_embed.bias"),
                         lvl_pos[cur_L:] if pn_next else None, f_hat, x if pn_next else None,
                         Bf, pn, pn_next, hw, Cvae, C, streams=2, x_replicas=(2 if replicas == 1 else 1))
@@ -503,6 +525,14 @@ class ControlVAR(nn.Module):
         img = vae._fhat_halves_to_img(f_hat, B, out_mode=1)       # one decoder pass over the 2B maps
         self.last_f_hat = f_hat
         return img
+
+    def _arange_idx(self, n: int) -> torch.Tensor:
+        """0 .. n-1 as int64 on the device (the identity index of the more_smooth VQ step), rebuilt when the workspace moved."""
+        t = self._buf("arange_idx", (n,), torch.int64)
+        if getattr(self, "_arange_state", None) != (t.data_ptr(), n):
+            t.copy_(torch.arange(n, device=t.device))
+            self._arange_state = (t.data_ptr(), n)
+        return t
 
     def _transformer(self, R: int, lmax: Optional[int] = None) -> "_Transformer":
         return _Transformer(self, R, lmax)

@@ -59,7 +59,8 @@ __global__ void __launch_bounds__(NT) cfg_sample_kernel(const float* __restrict_
                                                         int64_t* __restrict__ idx_out, int B, int l, int groups,
                                                         MixCoef coef, int replicas, int top_k, int use_top_p, float thr,
                                                         const int64_t* __restrict__ forced_first,
-                                                        const int64_t* __restrict__ forced_second, int forced_replicas) {
+                                                        const int64_t* __restrict__ forced_second, int forced_replicas,
+                                                        float* __restrict__ masked_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SampleSmem& sm = *reinterpret_cast<SampleSmem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -70,7 +71,7 @@ __global__ void __launch_bounds__(NT) cfg_sample_kernel(const float* __restrict_
   const int half = l >> 1;
   const int64_t* forced = t < half ? forced_first : forced_second;
   const long long forced_at = (long long)b * half + (t < half ? t : t - half);
-  if (forced != nullptr && forced_replicas >= replicas) {
+  if (forced != nullptr && forced_replicas >= replicas && masked_out == nullptr) {
     if (tid < replicas) idx_out[(long long)tid * B * l + row] = forced[forced_at];
     return;
   }
@@ -263,6 +264,13 @@ __global__ void __launch_bounds__(NT) cfg_sample_kernel(const float* __restrict_
     vmax = block_max(m, sm.redf);
   }
 
+  // more_smooth (control_var.py:513-515): the caller wants the logits as sample_with_top_k_top_p_ leaves them IN PLACE
+  // (helpers.py:10, 15: removed entries -inf) - they feed the Gumbel-softmax mixture of cvar_gumbel_embed
+  if (masked_out != nullptr) {
+#pragma unroll
+    for (int i = 0; i < PER; ++i) masked_out[row * V_FIXED + tid + i * NT] = sm.vals[tid + i * NT];
+  }
+
   // ---- multinomial(softmax(v), 1) = argmax(softmax(v) / q)                                 helpers.py:19
   float ev[PER];
   float loc = 0.f;
@@ -324,7 +332,8 @@ __global__ void __launch_bounds__(NT) cfg_sample_kernel(const float* __restrict_
 
 static int launch_cfg_sample(const float* logits, const float* q_noise, int64_t* idx_out, int B, int l, int groups,
                              MixCoef coef, int replicas, int top_k, double top_p, const int64_t* forced_first,
-                             const int64_t* forced_second, int forced_replicas, cudaStream_t stream, const char* name) {
+                             const int64_t* forced_second, int forced_replicas, cudaStream_t stream, const char* name,
+                             float* masked_out = nullptr) {
   // python evaluates (1 - top_p) in double, then the scalar meets an fp32 tensor as an fp32 value
   const float thr = (float)(1.0 - top_p);
   cudaError_t e = cudaFuncSetAttribute(cfg_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -332,7 +341,7 @@ static int launch_cfg_sample(const float* logits, const float* q_noise, int64_t*
   CVAR_REQUIRE(e == cudaSuccess, "%s: cannot raise shared memory: %s", name, cudaGetErrorString(e));
   cfg_sample_kernel<<<(unsigned)((long long)B * l), NT, sizeof(SampleSmem), stream>>>(
       logits, q_noise, idx_out, B, l, groups, coef, replicas, top_k, top_p > 0.0 ? 1 : 0, thr, forced_first,
-      forced_second, forced_replicas);
+      forced_second, forced_replicas, masked_out);
   CVAR_CHECK_LAUNCH(name);
   return 0;
 }
@@ -360,4 +369,92 @@ extern "C" int cvar_cfg_sample_multi(const float* logits, const float* q_noise, 
   for (int g = 0; g < groups; ++g) coef.c[g] = host_coef[g];
   return launch_cfg_sample(logits, q_noise, idx_out, B, l, groups, coef, replicas, top_k, top_p, forced_first,
                            forced_second, forced_replicas, (cudaStream_t)stream, "cvar_cfg_sample_multi");
+}
+
+// cvar_cfg_sample_multi that also returns the mixed logits as sample_with_top_k_top_p_ leaves them (B*l, V; removed entries
+// -inf): the input of the more_smooth path.
+extern "C" int cvar_cfg_sample_masked(const float* logits, const float* q_noise, int64_t* idx_out, float* masked_out, int B,
+                                      int l, int V, int groups, const float* host_coef, int replicas, int top_k, double top_p,
+                                      const int64_t* forced_first, const int64_t* forced_second, int forced_replicas,
+                                      void* stream) {
+  CVAR_REQUIRE(V == V_FIXED, "cvar_cfg_sample_masked: V must be %d (got %d)", V_FIXED, V);
+  CVAR_REQUIRE(masked_out != nullptr, "cvar_cfg_sample_masked: masked_out is null");
+  CVAR_REQUIRE(B > 0 && l > 0 && l % 2 == 0 && top_k >= 0 && top_k <= V, "cvar_cfg_sample_masked: bad arguments");
+  CVAR_REQUIRE(groups >= 1 && groups <= 4 && host_coef != nullptr, "cvar_cfg_sample_masked: 1..4 logit groups");
+  CVAR_REQUIRE(replicas >= 1 && replicas <= NT && forced_replicas >= 0 && forced_replicas <= replicas,
+               "cvar_cfg_sample_masked: bad replicas / forced_replicas");
+  MixCoef coef{{0.f, 0.f, 0.f, 0.f}};
+  for (int g = 0; g < groups; ++g) coef.c[g] = host_coef[g];
+  return launch_cfg_sample(logits, q_noise, idx_out, B, l, groups, coef, replicas, top_k, top_p, forced_first,
+                           forced_second, forced_replicas, (cudaStream_t)stream, "cvar_cfg_sample_masked", masked_out);
+}
+
+// ------------------------------------------------------------------------------------------------ more_smooth
+// h = softmax((logits * mul + (-log e)) / tau) @ embedding      control_var.py:514-515, helpers.py:26-28 (hard = False)
+// One CTA per output row; rows_in distinct logit rows are repeated (row % rows_in: logits_BlV.repeat(4, 1, 1) of
+// conditional_infer_cfg, control_var.py:306), every output row has its own Exp(1) noise.  Rounding follows the reference's
+// elementwise steps (mul, log, neg, add, div, then softmax = exp(x - max) / sum); the 4096-term products with the code
+// vectors are summed in a different order than ATen's matmul (a float path: compared within tolerance).
+namespace {
+constexpr int kGumCv = 32;
+__global__ void __launch_bounds__(NT) gumbel_embed_kernel(const float* __restrict__ masked, const float* __restrict__ e_noise,
+                                                          const float* __restrict__ emb, float* __restrict__ h_out,
+                                                          long long rows_in, float mul, float tau) {
+  __shared__ float y_s[V_FIXED];
+  __shared__ float red[NT / 32];
+  __shared__ float part[NT / 32][kGumCv];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long row = blockIdx.x;
+  const float* lg = masked + (row % rows_in) * V_FIXED;
+  const float* en = e_noise + row * V_FIXED;
+  float v[PER];
+  float m = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const int e = tid + i * NT;
+    const float g = -logf(en[e]);
+    v[i] = __fdiv_rn(__fadd_rn(__fmul_rn(lg[e], mul), g), tau);
+    m = fmaxf(m, v[i]);
+  }
+  const float vmax = block_max(m, red);
+  float loc = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    v[i] = v[i] == -INFINITY ? 0.f : expf(v[i] - vmax);
+    loc += v[i];
+  }
+  const float total = block_sum(loc, red);
+#pragma unroll
+  for (int i = 0; i < PER; ++i) y_s[tid + i * NT] = v[i] == 0.f ? 0.f : v[i] / total;
+  __syncthreads();
+  // warp w owns entries [w * 512, (w + 1) * 512), lane = channel: one 128-byte code vector per step
+  float acc = 0.f;
+  const int e0 = warp * (V_FIXED / (NT / 32));
+  for (int e = e0; e < e0 + V_FIXED / (NT / 32); ++e) {
+    const float y = y_s[e];
+    if (y != 0.f) acc = fmaf(y, emb[(long long)e * kGumCv + lane], acc);
+  }
+  part[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < NT / 32; ++w) t += part[w][lane];
+    h_out[row * kGumCv + lane] = t;
+  }
+}
+}  // namespace
+
+extern "C" int cvar_gumbel_embed(const float* masked_logits, const float* e_noise, const float* embedding, float* h_out,
+                                 long long rows_in, long long rows_out, int V, int Cvae, double mul, double tau,
+                                 void* stream) {
+  CVAR_REQUIRE(V == V_FIXED && Cvae == kGumCv, "cvar_gumbel_embed: V must be %d and Cvae %d", V_FIXED, kGumCv);
+  CVAR_REQUIRE(masked_logits && e_noise && embedding && h_out, "cvar_gumbel_embed: null pointer");
+  CVAR_REQUIRE(rows_in > 0 && rows_out > 0 && rows_out % rows_in == 0 && rows_out < (1LL << 31) && tau > 0.0,
+               "cvar_gumbel_embed: bad arguments");
+  // python forms (1 + ratio) and gum_t in double; they meet the fp32 tensors as fp32 values
+  gumbel_embed_kernel<<<(unsigned)rows_out, NT, 0, (cudaStream_t)stream>>>(masked_logits, e_noise, embedding, h_out, rows_in,
+                                                                        (float)mul, (float)tau);
+  CVAR_CHECK_LAUNCH("cvar_gumbel_embed");
+  return 0;
 }

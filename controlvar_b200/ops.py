@@ -397,6 +397,30 @@ def cfg_sample_multi(logits, q_noise, idx_out, B, l, V, coef, replicas, top_k, t
     return idx_out
 
 
+def cfg_sample_masked(logits, q_noise, idx_out, masked_out, B, l, V, coef, replicas, top_k, top_p, forced_first=None,
+                      forced_second=None, forced_replicas=0):
+    """cfg_sample_multi that also writes the mixed logits as sample_with_top_k_top_p_ leaves them (masked_out: (B*l, V),
+    removed entries -inf) - the input of gumbel_embed (more_smooth, control_var.py:513-515)."""
+    _chk(logits, q_noise, idx_out, masked_out, forced_first, forced_second)
+    G = len(coef)
+    arr = (C.c_float * G)(*[float(c) for c in coef])
+    with _Timed("sample", 0.0, 4.0 * B * l * V * (G + replicas + 1) + 8.0 * B * l * replicas):
+        check(_lib.load().cvar_cfg_sample_masked(_p(logits), _p(q_noise), _p(idx_out), _p(masked_out), B, l, V, G, arr,
+                                                 int(replicas), int(top_k), float(top_p), _p(forced_first), _p(forced_second),
+                                                 int(forced_replicas), _stream()), "cvar_cfg_sample_masked")
+    return idx_out
+
+
+def gumbel_embed(masked_logits, e_noise, embedding, h_out, rows_in, rows_out, V, Cvae, mul, tau):
+    """h = softmax((masked_logits * mul + (-log e_noise)) / tau) @ embedding (helpers.py:22-36 with hard=False); output row r
+    reads logits row r % rows_in."""
+    _chk(masked_logits, e_noise, embedding, h_out)
+    with _Timed("sample", 2.0 * rows_out * V * Cvae, 4.0 * V * (rows_in + rows_out) + 4.0 * rows_out * Cvae):
+        check(_lib.load().cvar_gumbel_embed(_p(masked_logits), _p(e_noise), _p(embedding), _p(h_out), int(rows_in),
+                                            int(rows_out), V, Cvae, float(mul), float(tau), _stream()), "cvar_gumbel_embed")
+    return h_out
+
+
 def vq_step(idx, embedding, U, phi_w, phi_b, word_w, word_b, lvl_pos_next, f_hat, x_next, B, pn, pn_next, hw, Cvae, Cdim,
             streams=2, x_replicas=2, f_rest=None):
     """streams / x_replicas / f_rest: see cvar_vq_step_ex (defaults = the autoregressive_infer_cfg step)."""

@@ -217,6 +217,21 @@ CVAR_API int cvar_cfg_sample_multi(const float* logits, const float* q_noise, in
                           int groups, const float* host_coef, int replicas, int top_k, double top_p,
                           const int64_t* forced_first, const int64_t* forced_second, int forced_replicas, void* stream);
 
+/* cvar_cfg_sample_multi that ALSO returns the mixed logits as sample_with_top_k_top_p_ leaves them in place
+ * (helpers.py:10, 15: masked_out (B*l, V) fp32, removed entries -inf): the input of the more_smooth path
+ * (control_var.py:513-515, 329-331).  Rows whose replicas are all forced are still evaluated. */
+CVAR_API int cvar_cfg_sample_masked(const float* logits, const float* q_noise, int64_t* idx_out, float* masked_out, int B, int l,
+                           int V, int groups, const float* host_coef, int replicas, int top_k, double top_p,
+                           const int64_t* forced_first, const int64_t* forced_second, int forced_replicas, void* stream);
+
+/* ---- more_smooth: gumbel_softmax_with_rng(logits.mul(1 + ratio), tau, hard=False) @ embedding ---------------------
+ * control_var.py:514-515 (and :330-331), helpers.py:22-36.  masked_logits (rows_in, V) from cvar_cfg_sample_masked;
+ * e_noise (rows_out, V): the Exp(1) tensor helpers.py:26 draws (gumbel = -log e); rows_out = k * rows_in: output row r
+ * uses logits row r % rows_in (logits_BlV.repeat(4, 1, 1), control_var.py:306).  h_out (rows_out, Cvae) fp32:
+ *   h = softmax((masked * mul + gumbel) / tau) @ embedding,   mul = 1 + ratio, tau = max(0.27 (1 - 0.95 ratio), 0.005). */
+CVAR_API int cvar_gumbel_embed(const float* masked_logits, const float* e_noise, const float* embedding, float* h_out,
+                      long long rows_in, long long rows_out, int V, int Cvae, double mul, double tau, void* stream);
+
 /* ---- multi-scale VQ step: control_var.py:512-560 + quant.py:243-270 ------------------------------------------
  * For sample b and stream s in {0: control, 1: image}:
  *   h  = embedding[idx[b, s*pn*pn + i], :] as a (32, pn, pn) map                      (control_var.py:512-524)

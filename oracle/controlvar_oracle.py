@@ -354,9 +354,10 @@ def autoregressive_infer_cfg(
     sd: Dict[str, Tensor], vsd: Dict[str, Tensor], patch_nums: Sequence[int], depth: int,
     B: int, label_B: Tensor, cond_type: Tensor, cfg: float, top_k: int, top_p: float,
     noise: Callable[[int, int, int], Tensor], decode: bool = True, trace: Optional[dict] = None,
-    forced_idx: Optional[List[Tensor]] = None, embed_dim: int = 0, num_heads: int = 0,
+    forced_idx: Optional[List[Tensor]] = None, embed_dim: int = 0, num_heads: int = 0, more_smooth: bool = False,
 ) -> Dict[str, object]:
     """ControlVAR.autoregressive_infer_cfg, released branch - models/control_var.py:373-409, 486-565.
+    ``more_smooth`` (:511-515, visualisation only): ``noise`` is then called twice per scale - multinomial, then Gumbel.
 
     ``noise(si, n_rows, V)`` returns the Exp(1) tensor that torch.multinomial would have drawn at scale si.
     ``forced_idx`` (teacher forcing, test helper) replaces the sampled tokens after sampling so that later scales
@@ -410,7 +411,12 @@ def autoregressive_infer_cfg(
         idx_all.append(idx_Bl.clone())
         if forced_idx is not None:
             idx_Bl = forced_idx[si].clone()
-        h_BChw = F.embedding(idx_Bl, emb)                                     # :512
+        if not more_smooth:
+            h_BChw = F.embedding(idx_Bl, emb)                                 # :512
+        else:
+            h_BChw = gumbel_soft_embedding(logits_BlV, ratio, noise(si, B * logits_BlV.shape[1], V), emb)   # :514-515
+            if trace is not None:
+                trace.setdefault("h_soft", []).append(h_BChw.clone())
         h_BChw = h_BChw.transpose_(1, 2)                                      # :522
         h1 = h_BChw[:, :, :pn * pn].reshape(B, Cvae, pn, pn)
         h2 = h_BChw[:, :, -pn * pn:].reshape(B, Cvae, pn, pn)
@@ -478,7 +484,7 @@ def conditional_infer_cfg(
     B: int, label_B: Tensor, cond_type: Tensor, cfg: Sequence[float], top_k: int, top_p: float,
     noise: Callable[[int, int, int], Tensor], c_mask: Optional[List[Tensor]] = None,
     c_img: Optional[List[Tensor]] = None, decode: bool = True, trace: Optional[dict] = None,
-    embed_dim: int = 0, num_heads: int = 0,
+    embed_dim: int = 0, num_heads: int = 0, more_smooth: bool = False,
 ) -> Dict[str, object]:
     """ControlVAR.conditional_infer_cfg - models/control_var.py:223-354 (pixel-level control: the condition map's
     and / or the image's tokens are teacher-forced into three of four guidance replicas).
@@ -539,7 +545,10 @@ def conditional_infer_cfg(
             for g in range(3):
                 idx_Bl[g * B:(g + 1) * B, pn * pn:] = c_img[si]
         idx_all.append(idx_Bl.clone())
-        h_BChw = F.embedding(idx_Bl, emb).transpose_(1, 2)                                  # :327, :334
+        if not more_smooth:
+            h_BChw = F.embedding(idx_Bl, emb).transpose_(1, 2)                              # :327, :334
+        else:   # :329-331: the mixture comes from the (repeated) masked logits; the forced tokens play no part in it
+            h_BChw = gumbel_soft_embedding(logits, ratio, noise(si, logits.shape[0] * logits.shape[1], V), emb).transpose_(1, 2)
         h1 = h_BChw[:, :, :pn * pn].reshape(rep * B, Cvae, pn, pn)
         h2 = h_BChw[:, :, -pn * pn:].reshape(rep * B, Cvae, pn, pn)
         f_hat_1 = f_hat[:, :, :HW, :]
@@ -559,6 +568,19 @@ def conditional_infer_cfg(
         img2 = fhat_to_img(f_hat_2[:B], vsd).add_(1).mul_(0.5)
         out["img"] = torch.concat([img1, img2], dim=2)                                      # :354
     return out
+
+
+def gumbel_soft_embedding(logits_masked: Tensor, ratio: float, e: Tensor, emb: Tensor) -> Tensor:
+    """The ``more_smooth`` replacement for ``embedding(idx_Bl)`` - models/control_var.py:513-515 (and :329-331),
+    models/helpers.py:22-36 with ``hard=False``: a Gumbel-softmax mixture of code vectors.
+
+    ``logits_masked`` are the guidance-mixed logits AFTER sample_with_top_k_top_p_ has masked them in place
+    (helpers.py:8-15: removed entries are -inf, so their weight is exactly 0); ``e`` is the Exp(1) tensor that
+    ``torch.empty_like(logits).exponential_(generator=rng)`` draws right after torch.multinomial's (helpers.py:26)."""
+    gum_t = max(0.27 * (1 - ratio * 0.95), 0.005)                             # control_var.py:514
+    gumbels = -e.view_as(logits_masked).log()                                 # helpers.py:26
+    gumbels = (logits_masked.mul(1 + ratio) + gumbels) / gum_t                # helpers.py:27, control_var.py:515
+    return gumbels.softmax(-1) @ emb.unsqueeze(0)                             # helpers.py:28, control_var.py:515
 
 
 def cpu_generator_noise(seed: int) -> Callable[[int, int, int], Tensor]:

@@ -257,7 +257,8 @@ def test_conditional_infer_matches_reference_golden(name):
     n0 = ops.launch_count()
     img = var.conditional_infer_cfg(m["B"], torch.tensor(m["labels"]), g_seed=m["seed"], cfg=tuple(m["cfg"]),
                                     top_k=m["top_k"], top_p=m["top_p"], cond_type=torch.tensor(m["cond"]),
-                                    c_mask=forced if m["c_mask"] else None, c_img=forced if m["c_img"] else None)
+                                    c_mask=forced if m["c_mask"] else None, c_img=forced if m["c_img"] else None,
+                                    more_smooth=bool(m.get("more_smooth", False)))
     torch.cuda.synchronize()
     assert ops.launch_count() > n0
     assert list(img.shape) == m["img_shape"]
@@ -267,7 +268,9 @@ def test_conditional_infer_matches_reference_golden(name):
     err = (img.cpu()[:, :, ::sub, ::sub] - gold["img_sub"]).abs().max().item()
     ferr = (var.last_f_hat[:m["B"]].cpu() - gold["f_hat"]).abs().max().item()
     print(f"\n[conditional {name}] pixel err {err:.2e}, f_hat err {ferr:.2e}")
-    assert err < 1e-4 and ferr < 1e-4
+    # more_smooth (control_var.py:326-331): the mixture's temperature amplifies logit differences ~70x at the last scale, so
+    # f_hat is compared at 1e-3 there (tests/test_gpu_sampler.py); the pixels keep the 1e-4 bound
+    assert err < 1e-4 and ferr < (1e-3 if m.get("more_smooth") else 1e-4)
 
 
 def test_conditional_pipeline_from_pixels():

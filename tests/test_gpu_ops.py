@@ -224,6 +224,38 @@ def test_cfg_sample_matches_reference_rule(top_k, top_p, t):
     assert n_bad <= (1 if top_p > 0 else 0), f"{n_bad} rows picked a token the reference filtered out"
 
 
+def test_cfg_sample_masked_and_gumbel_embed():
+    """more_smooth (control_var.py:511-515, helpers.py:22-36): cvar_cfg_sample_masked returns the logits as
+    sample_with_top_k_top_p_ leaves them in place and the same tokens as cvar_cfg_sample; cvar_gumbel_embed turns them
+    into the Gumbel-softmax mixture of code vectors (4 replicas re-using the logit rows, as conditional_infer_cfg does)."""
+    torch.manual_seed(21)
+    B, l, V, Cv, t, top_k, top_p = 2, 18, 4096, 32, 1.2, 900, 0.96
+    logits = torch.randn(2 * B, l, V) * 1.5
+    gen = torch.Generator().manual_seed(3)
+    q = torch.empty(B * l, V).exponential_(1, generator=gen)
+    masked_ref = O.mask_top_k_top_p_(O.cfg_combine(logits, B, t).clone(), top_k, top_p)
+    idx0 = torch.empty(B, l, dtype=torch.int64, device=DEV)
+    ops.cfg_sample(g(logits), g(q), idx0, B, l, V, t, top_k, top_p)
+    idx1 = torch.empty(B, l, dtype=torch.int64, device=DEV)
+    masked = torch.empty(B * l, V, device=DEV)
+    f32 = lambda v: float(torch.tensor(v, dtype=torch.float32))
+    ops.cfg_sample_masked(g(logits), g(q), idx1, masked, B, l, V, (f32(1 + t), -f32(t)), 1, top_k, top_p)
+    assert torch.equal(idx0, idx1)
+    mr = masked_ref.view(B * l, V)
+    same_mask = torch.isinf(masked.cpu()) == torch.isinf(mr)
+    assert (~same_mask).sum().item() <= 2                       # a top-p boundary entry may fall either way at fp32 resolution
+    keep = ~torch.isinf(mr) & same_mask
+    assert torch.equal(masked.cpu()[keep], mr[keep])            # the guidance mix is elementwise: bit-exact
+
+    emb = torch.randn(V, Cv)
+    rep, ratio = 4, 5 / 9
+    e = torch.empty(rep * B * l, V).exponential_(1, generator=gen)
+    ref = O.gumbel_soft_embedding(mr.view(B, l, V).repeat(rep, 1, 1), ratio, e, emb).view(rep * B * l, Cv)
+    h = torch.empty(rep * B * l, Cv, device=DEV)
+    ops.gumbel_embed(g(mr), g(e), g(emb), h, B * l, rep * B * l, V, Cv, 1 + ratio, max(0.27 * (1 - ratio * 0.95), 0.005))
+    assert (h.cpu() - ref).abs().max().item() < 2e-5 * ref.abs().max().item()
+
+
 # ----------------------------------------------------------------------------------------------- VQ step
 def test_vq_step_all_scales():
     cfg = PathConfig(depth=2)

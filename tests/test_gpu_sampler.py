@@ -46,13 +46,18 @@ def test_sampler_matches_reference_golden(engine, name):
     gold = load_golden(name)
     m, cfg = gold["meta"], gold["cfg"]
     vae, var, _, vsd = build(cfg, m["weight_seed"])
+    smooth = bool(m.get("more_smooth", False))      # control_var.py:511-515: Gumbel-softmax mixture instead of the sampled code
     img = var.autoregressive_infer_cfg(m["B"], torch.tensor(m["labels"]), g_seed=m["seed"], cfg=m["cfg"],
-                                       top_k=m["top_k"], top_p=m["top_p"], cond_type=torch.tensor(m["cond"]))
+                                       top_k=m["top_k"], top_p=m["top_p"], cond_type=torch.tensor(m["cond"]),
+                                       more_smooth=smooth)
     torch.cuda.synchronize()
     assert list(img.shape) == m["img_shape"]
     for si, (a, b) in enumerate(zip(gold["idx"], var.last_idx)):
         assert torch.equal(a, b.cpu()), f"{name}: token indices differ from the reference at scale {si}"
-    assert (var.last_f_hat.cpu() - gold["f_hat"]).abs().max().item() < 1e-4
+    # f_hat: 1e-4 abs.  more_smooth: the code-vector mixture is softmax((logits (1 + ratio) + gumbel) / tau) with tau down to 0.0135
+    # at the last scale (control_var.py:514) - a logit difference of 1e-5 is a 7e-4 relative difference of the weights, so f_hat
+    # (absmax ~6) is compared at 1e-3; the decoded pixels below still have to meet the 1e-4 bound.
+    assert (var.last_f_hat.cpu() - gold["f_hat"]).abs().max().item() < (1e-3 if smooth else 1e-4)
     sub = m["img_sub"]
     err = (img[:, :, ::sub, ::sub].cpu() - gold["img_sub"]).abs().max().item()
     assert err < PIXEL_TOL, f"{name}: pixel error {err:.3e}"
@@ -67,7 +72,8 @@ def test_sampler_matches_reference_golden(engine, name):
     assert err_full < PIXEL_TOL, f"{name}: full-image pixel error {err_full:.3e} on the [-1,1] scale"
     # deterministic for a fixed seed
     img2 = var.autoregressive_infer_cfg(m["B"], torch.tensor(m["labels"]), g_seed=m["seed"], cfg=m["cfg"],
-                                        top_k=m["top_k"], top_p=m["top_p"], cond_type=torch.tensor(m["cond"]))
+                                        top_k=m["top_k"], top_p=m["top_p"], cond_type=torch.tensor(m["cond"]),
+                                        more_smooth=smooth)
     assert torch.equal(img, img2)
 
 
@@ -122,8 +128,8 @@ def test_int_and_none_arguments():
     assert c.shape == d.shape == (4, 3, 96, 48)
     with pytest.raises(AssertionError):
         var.autoregressive_infer_cfg(2, 7, g_seed=1, cond_type=0)     # control_var.py:395
-    with pytest.raises(NotImplementedError):
-        var.autoregressive_infer_cfg(2, 7, g_seed=1, more_smooth=True, cond_type=1)
+    e = var.autoregressive_infer_cfg(2, 7, g_seed=1, more_smooth=True, cond_type=1)     # the Gumbel-softmax visualisation mode
+    assert e.shape == (2, 3, 96, 48) and torch.isfinite(e).all() and not torch.equal(e, a)
 
 
 def test_cuda_generator_path_is_deterministic():

@@ -21,7 +21,8 @@ def test_oracle_matches_reference_golden(name):
     vsd = W.synthetic_vae_state_dict(cfg, m["weight_seed"], with_encoder=False)
     out = O.autoregressive_infer_cfg(sd, vsd, cfg.patch_nums, cfg.depth, m["B"], torch.tensor(m["labels"]),
                                      torch.tensor(m["cond"]), m["cfg"], m["top_k"], m["top_p"],
-                                     O.cpu_generator_noise(m["seed"]), embed_dim=cfg.embed_dim, num_heads=cfg.heads)
+                                     O.cpu_generator_noise(m["seed"]), embed_dim=cfg.embed_dim, num_heads=cfg.heads,
+                                     more_smooth=bool(m.get("more_smooth", False)))
     for si, (a, b) in enumerate(zip(g["idx"], out["idx"])):
         assert torch.equal(a, b), f"tokens differ at scale {si}"
     sub = m["img_sub"]
@@ -62,7 +63,7 @@ def test_oracle_conditional_infer_matches_reference_golden(name):
     out = O.conditional_infer_cfg(sd, vsd, cfg.patch_nums, cfg.depth, m["B"], torch.tensor(m["labels"]),
                                   torch.tensor(m["cond"]), m["cfg"], m["top_k"], m["top_p"],
                                   O.cpu_generator_noise(m["seed"]), c_mask=g["forced"] if m["c_mask"] else None,
-                                  c_img=g["forced"] if m["c_img"] else None)
+                                  c_img=g["forced"] if m["c_img"] else None, more_smooth=bool(m.get("more_smooth", False)))
     for si, (a, b) in enumerate(zip(g["idx"], out["idx"])):
         assert torch.equal(a, b), f"tokens differ at scale {si}"
     sub = m["img_sub"]

@@ -526,6 +526,16 @@ class ControlVAR(nn.Module):
         self.last_f_hat = f_hat
         return img
 
+    def _start_rows_class_first(self, label_B: torch.Tensor, cond_type: torch.Tensor, tr: "_Transformer") -> torch.Tensor:
+        """forward(mask_first=False), control_var.py:587: the class token BEFORE the condition-type token.  Two rows per sample
+        of an option no released configuration uses: formed with torch ops in the reference's order of additions -
+        (token + pos_start) + (lvl_embed + pos_1LC), :588 and :618."""
+        import torch.nn.functional as F
+        sos = F.embedding(label_B, self.get_parameter("class_emb.weight")).unsqueeze(1)
+        ct = F.embedding(cond_type, self.get_parameter("cond_embed.weight")).unsqueeze(1)
+        first = torch.cat([sos, ct], dim=1) + self.pos_start.expand(label_B.shape[0], self.first_l, -1)
+        return first + tr.lvl_pos[:self.first_l]
+
     def _arange_idx(self, n: int) -> torch.Tensor:
         """0 .. n-1 as int64 on the device (the identity index of the more_smooth VQ step), rebuilt when the workspace moved."""
         t = self._buf("arange_idx", (n,), torch.int64)
@@ -550,8 +560,6 @@ class ControlVAR(nn.Module):
         even in eval mode (:577, :584): set ``cond_drop_rate = 0`` for deterministic logits."""
         if not self.pos_1LC.is_cuda:
             raise RuntimeError("controlvar_b200.ControlVAR runs on CUDA only (no CPU fallback); call .cuda() first")
-        if not mask_first:
-            raise NotImplementedError("mask_first=False (image token before the control token) is not implemented")
         if not self.multi_cond:
             raise NotImplementedError("forward is implemented for the released configuration (multi_cond=True)")
         dev = self.device
@@ -578,7 +586,7 @@ class ControlVAR(nn.Module):
                               tr.lvl_pos, label_B.contiguous(), cond_type.contiguous(), tr.cond_BD, tr.silu_cond, x0)
             tr.prologue_ada()
             xv = tr.x[:B * L].view(B, L, C)
-            xv[:, :self.first_l].copy_(x0.view(B, self.first_l, C))
+            xv[:, :self.first_l].copy_(x0.view(B, self.first_l, C) if mask_first else self._start_rows_class_first(label_B, cond_type, tr))
             # x = word_embed(teacher tokens) + (lvl_embed + pos_1LC) for every later token: one batched K = 32 GEMM (:616-618)
             ops.gemm(xin, ww, wb, xv[:, self.first_l:], Lin, C, Cvae, lda=Cvae, epilogue=ops.EPI_BIAS_RESID,
                      resid=tr.lvl_pos[self.first_l:], ldr=C, strideR=0, batch=B, strideA=Lin * Cvae, strideW=0, strideO=L * C)
@@ -586,6 +594,8 @@ class ControlVAR(nn.Module):
             return tr.logits[:B * L].view(B, L, V).clone()
         tr = self._transformer(B)
         tr.prologue(label_B.contiguous(), cond_type.contiguous())
+        if not mask_first:
+            tr.x[:B * self.first_l].view(B, self.first_l, C).copy_(self._start_rows_class_first(label_B, cond_type, tr))
         out = torch.empty(B, self.L, V, device=dev, dtype=torch.float32)
         cur_L = 0
         for si, l in enumerate(self.cfg.scale_lens):

@@ -446,7 +446,8 @@ def autoregressive_infer_cfg(
 
 @torch.no_grad()
 def forward_teacher_forced(sd: Dict[str, Tensor], patch_nums: Sequence[int], depth: int, label_B: Tensor,
-                           x_BLCv_wo_first_l: Tensor, cond_type: Tensor, embed_dim: int = 0, num_heads: int = 0) -> Tensor:
+                           x_BLCv_wo_first_l: Tensor, cond_type: Tensor, embed_dim: int = 0, num_heads: int = 0,
+                           mask_first: bool = True) -> Tensor:
     """ControlVAR.forward, released branch (multi_cond, mask_factor 2, mask_first=True, prog_si=-1) -
     models/control_var.py:566-651: one full-sequence pass under the block-causal attn_bias_for_masking.
     The label / condition-type dropout of :577 and :584 (torch.rand < cond_drop_rate, active even in eval) is the
@@ -460,7 +461,7 @@ def forward_teacher_forced(sd: Dict[str, Tensor], patch_nums: Sequence[int], dep
     sos = cond_BD = F.embedding(label_B.long(), sd["class_emb.weight"])                       # :578
     sos = sos.unsqueeze(1).expand(B, 1, -1)                                                   # :581
     cond_token = F.embedding(cond_type.long(), sd["cond_embed.weight"]).unsqueeze(1).expand(B, 1, -1)   # :585-586
-    sos = torch.concat([cond_token, sos], dim=1)                                              # :587 (mask_first)
+    sos = torch.concat([cond_token, sos], dim=1) if mask_first else torch.concat([sos, cond_token], dim=1)   # :587
     sos = sos + sd["pos_start"].expand(B, first_l, -1)                                        # :588
     x_BLC = torch.cat((sos, F.linear(x_BLCv_wo_first_l.float(), sd["word_embed.weight"], sd["word_embed.bias"])), dim=1)  # :616
     x_BLC += F.embedding(sd["lvl_1L"].expand(B, -1), sd["lvl_embed.weight"]) + sd["pos_1LC"]   # :618

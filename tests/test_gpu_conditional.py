@@ -328,14 +328,20 @@ def test_forward_teacher_forced_matches_reference_golden(name):
     var.cond_drop_rate = 0.0
     x = W.synthetic_teacher_input(cfg, m["B"], m["x_seed"])
     n0 = ops.launch_count()
-    logits = var(torch.tensor(m["labels"]), g(x), torch.tensor(m["cond"]))
+    mask_first = bool(m.get("mask_first", True))       # False: class token before the condition-type token (control_var.py:587)
+    logits = var(torch.tensor(m["labels"]), g(x), torch.tensor(m["cond"]), mask_first=mask_first)
     torch.cuda.synchronize()
     assert ops.launch_count() > n0 and list(logits.shape) == m["logits_shape"]
+    if not mask_first:      # both realisations of the pass
+        var.forward_single_pass = False
+        per_scale = var(torch.tensor(m["labels"]), g(x), torch.tensor(m["cond"]), mask_first=False)
+        var.forward_single_pass = True
+        assert (per_scale - logits).abs().max().item() < 2e-5
     err = (logits.cpu()[:, :, ::m["logits_sub"]] - gold["logits_sub"]).abs().max().item()
     # and against the oracle on every logit
     ref = O.forward_teacher_forced(W.synthetic_var_state_dict(cfg, m["weight_seed"]), cfg.patch_nums, cfg.depth,
                                    torch.tensor(m["labels"]), x, torch.tensor(m["cond"]), embed_dim=cfg.embed_dim,
-                                   num_heads=cfg.heads)
+                                   num_heads=cfg.heads, mask_first=mask_first)
     err_all = (logits.cpu() - ref).abs().max().item()
     print(f"\n[forward {name}] max |dlogit| {err_all:.2e} (golden sub-grid {err:.2e}), argmax agreement "
           f"{(logits.cpu().argmax(-1) == ref.argmax(-1)).float().mean().item():.4f}")

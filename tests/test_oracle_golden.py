@@ -80,7 +80,7 @@ def test_oracle_forward_matches_reference_golden(name):
     sd = W.synthetic_var_state_dict(cfg, m["weight_seed"])
     x = W.synthetic_teacher_input(cfg, m["B"], m["x_seed"])
     out = O.forward_teacher_forced(sd, cfg.patch_nums, cfg.depth, torch.tensor(m["labels"]), x, torch.tensor(m["cond"]),
-                                   embed_dim=cfg.embed_dim, num_heads=cfg.heads)
+                                   embed_dim=cfg.embed_dim, num_heads=cfg.heads, mask_first=bool(m.get("mask_first", True)))
     assert list(out.shape) == m["logits_shape"]
     assert (out[:, :, ::m["logits_sub"]] - g["logits_sub"]).abs().max().item() <= 2e-6
 

@@ -1,1 +1,1 @@
-timeout 900 python -m pytest tests/test_gpu_conditional.py -m gpu -x -q 2>&1 | tail -4
+timeout 900 python -m pytest tests/test_gpu_conditional.py -m gpu -x -q -k "forward" 2>&1 | tail -4

@@ -438,6 +438,8 @@ struct ConvRow {
   }
 };
 
+template <class EP> struct IsDenseRow { static constexpr bool value = false; };
+template <int MODE> struct IsDenseRow<DenseRow<MODE>> { static constexpr bool value = true; };
 template <class EP> struct IsRowEpilogue { static constexpr bool value = false; };
 template <int MODE> struct IsRowEpilogue<DenseRow<MODE>> { static constexpr bool value = true; };
 template <> struct IsRowEpilogue<QkvRow> { static constexpr bool value = true; };
@@ -515,7 +517,10 @@ __device__ __forceinline__ void epilogue_tile(const EP& ep, uint32_t tcol, int c
 
 // kFast (cvar_set_fast_mode; NOT a parity mode): the hi halves only - one MMA per product, half the operand bytes per
 // stage, twice the stages.
-template <class EP, bool F16, bool kFast = false>
+// kBN: columns of the pair tile.  256 everywhere except the NARROW variant (128) that launch() picks for FP16-pair row-epilogue
+// GEMMs whose 256-wide tiling would leave more than half of the machine idle (small scales, small batches): the same rows
+// of A against half the weight rows - less efficient per tile (the operand ingest per MMA doubles), but twice the tiles.
+template <class EP, bool F16, bool kFast = false, int kBN = BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 tc_gemm2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
                 const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo, EP ep,
@@ -523,8 +528,10 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constan
   using G = Geo<BK>;
   // instruction descriptor: D fp32; A/B format 2 = TF32 (kind::tf32) or 0 = FP16 (kind::f16); N, M of the pair tile
   constexpr uint32_t kFmt = F16 ? 0u : 2u;
-  constexpr uint32_t kIdesc = (1u << 4) | (kFmt << 7) | (kFmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+  constexpr uint32_t kIdesc = (1u << 4) | (kFmt << 7) | (kFmt << 10) | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
   constexpr int kBKe = F16 ? 2 * BK : BK;            // K elements per block
+  static_assert(kBN == BN || (kBN == 128 && F16 && !kFast), "narrow tiles: FP16 pairs, parity mode");
+  constexpr int kBBytesT = (kBN / 2) * BK * 4;       // bytes of the weight tile this CTA stages per operand half
   constexpr float kLoScale = F16 ? (1.0f / 2048.0f) : 1.0f;
   constexpr int kAccStride = 256;                    // main [0,256), lo [256,512)
 
@@ -579,8 +586,8 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constan
       if (threadIdx.x == 0) trace2(tcount, 2);
       const long long m_base = (long long)mt * 256 + rank * BM + quarter * 32;
       const uint32_t tcol = tmem_base + ((uint32_t)(quarter * 32) << 16);
-      epilogue_tile<EP, !kFast>(ep, tcol, half * (BN / 2), BN / 2, kLoScale, m_base, nt * BN, M, N, stage, lane, tm_empty,
-                                tcount);
+      epilogue_tile<EP, !kFast, kBN / 32>(ep, tcol, half * (kBN / 2), kBN / 2, kLoScale, m_base, nt * kBN, M, N, stage, lane,
+                                          tm_empty, tcount);
       if (threadIdx.x == 0) trace2(tcount, 4);
     }
   } else if (warp == kTmaWarp) {
@@ -593,14 +600,15 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constan
         // dbg_traffic (CVAR_DEBUG_TRAFFIC, diagnostics only - WRONG results): 1 = every tile reads the A rows of row tile 0,
         // 2 = every tile reads the weight rows of column tile 0: attributes the DRAM reads of a launch to one operand
         const int arow = ((dbg_traffic & 1) ? 0 : mt * 256) + (int)rank * BM;
-        const int brow = ((dbg_traffic & 2) ? 0 : nt * BN) + (int)rank * (BN / 2);
+        const int brow = ((dbg_traffic & 2) ? 0 : nt * kBN) + (int)rank * (kBN / 2);
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % kNS;
           const uint32_t ph = (it / kNS) & 1;
           mbar_wait(&empty[s], ph ^ 1);
           if (kb == 0) trace2(it / nkb, 5);
           if (kb == nkb - 1) trace2(it / nkb, 6);
-          if (rank == 0) mbar_arrive_expect_tx(&full[s], 2u * (uint32_t)kSB);   // bytes of BOTH CTAs
+          if (rank == 0)      // bytes of BOTH CTAs (the narrow variant stages half the weight rows in the same stage layout)
+            mbar_arrive_expect_tx(&full[s], 2u * (uint32_t)(kBN == BN ? kSB : 2 * kABytes + 2 * kBBytesT));
           tma_load_2d_2sm(&mapAhi, &full[s], a_hi(s), kb * kBKe, arow);
           if (!kFast) tma_load_2d_2sm(&mapAlo, &full[s], a_lo(s), kb * kBKe, arow);
           tma_load_2d_2sm(&mapBhi, &full[s], b_hi(s), kb * kBKe, brow);
@@ -828,7 +836,7 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 // row-major [rows, K] fp32 (or fp16) matrix -> (128 bytes x 128 rows) box, 128-byte swizzle, out-of-range rows zero-filled
-static int make_map(CUtensorMap* map, const void* base, long long rows, int K, long long ld, bool f16) {
+static int make_map(CUtensorMap* map, const void* base, long long rows, int K, long long ld, bool f16, int box_rows = 128) {
   EncodeTiledFn enc = get_encode();
   if (!enc) {
     set_error("tc_gemm2: cuTensorMapEncodeTiled is not available from the driver");
@@ -836,7 +844,7 @@ static int make_map(CUtensorMap* map, const void* base, long long rows, int K, l
   }
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * (f16 ? 2 : 4)};
-  cuuint32_t box[2] = {(cuuint32_t)(f16 ? 2 * BK : BK), 128};
+  cuuint32_t box[2] = {(cuuint32_t)(f16 ? 2 * BK : BK), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                    const_cast<void*>(base), dims, strides, box, estr,
@@ -904,21 +912,28 @@ static int num_sms() {
 template <class EP, bool F16>
 int launch(const EP& ep, const void* A_hi, const void* A_lo, long long lda, const void* W_hi, const void* W_lo,
            long long ldw, long long M, int N, int K, cudaStream_t s, const char* name) {
+  // Narrow tiles (256 x 128) when the 256 x 256 tiling fills less than half of the machine: dense layers of the small scales /
+  // small batches.  Same rows of A, same K order per output element: bit-identical results (tests/test_gpu_f16x3.py).
+  static const bool narrow_off = getenv("CVAR_NARROW_TILES") != nullptr && getenv("CVAR_NARROW_TILES")[0] == '0';   // A/B
+  constexpr bool kCanNarrow = F16 && IsDenseRow<EP>::value;
+  const bool narrow = kCanNarrow && !narrow_off && !g_fast_mode && N % 128 == 0 &&
+                      2 * (long long)cdiv(M, 256) * cdiv(N, BN) <= num_sms() / 2;
   CUtensorMap mah, mal, mbh, mbl;
   int rc = make_map(&mah, A_hi, M, K, lda, F16);
   if (!rc) rc = make_map(&mal, A_lo, M, K, lda, F16);
-  if (!rc) rc = make_map(&mbh, W_hi, N, K, ldw, F16);
-  if (!rc) rc = make_map(&mbl, W_lo, N, K, ldw, F16);
+  if (!rc) rc = make_map(&mbh, W_hi, N, K, ldw, F16, narrow ? 64 : 128);
+  if (!rc) rc = make_map(&mbl, W_lo, N, K, ldw, F16, narrow ? 64 : 128);
   if (rc) return rc;
   // fast mode (NOT a parity mode) exists for the FP16-pair row epilogues only
   auto kern = (F16 && IsRowEpilogue<EP>::value && g_fast_mode) ? tc_gemm2_kernel<EP, F16, F16 && IsRowEpilogue<EP>::value>
                                                                : tc_gemm2_kernel<EP, F16, false>;
+  if (narrow) kern = tc_gemm2_kernel<EP, F16, false, kCanNarrow ? 128 : BN>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
   if (e != cudaSuccess) {
     set_error("%s: cannot raise shared memory to %d: %s", name, kSmem, cudaGetErrorString(e));
     return -2;
   }
-  const int m_tiles = cdiv(M, 256), n_tiles = cdiv(N, BN);
+  const int m_tiles = cdiv(M, 256), n_tiles = cdiv(N, narrow ? 128 : BN);
   const int pairs = min(num_sms() / 2, m_tiles * n_tiles);
   static const int dbg_traffic = getenv("CVAR_DEBUG_TRAFFIC") ? atoi(getenv("CVAR_DEBUG_TRAFFIC")) : 0;
   kern<<<2 * pairs, kThreads, kSmem, s>>>(mah, mal, mbh, mbl, ep, M, N, K, m_tiles, n_tiles, g_group_m, dbg_traffic);

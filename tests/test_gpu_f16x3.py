@@ -85,6 +85,40 @@ def test_f16x3_gemm_vs_fp64_and_3xtf32(engine4, M, N, K):
     assert e4 <= 1.5 * e3 + 1e-7, "f16x3 should not be less accurate than 3xTF32"
 
 
+@pytest.mark.parametrize("M,N,K", [(256, 1536, 1536), (512, 1536, 6144), (200, 6144, 1536), (1100, 768, 768), (256, 4096, 1536)])
+def test_f16x3_narrow_tiles_are_bit_identical(engine4, M, N, K):
+    """Dense layers whose 256 x 256 tiling would fill less than half of the machine (small scales, small batches) run on
+    256 x 128 pair tiles.  Per output element the products and their order are the same, so the first M rows of a launch large
+    enough to take the regular kernel must come out bit-identical - for every epilogue kind, incl. the FP16-pair output."""
+    torch.manual_seed(M + N)
+    Mbig, l = 16384, 64
+    A = g(torch.randn(Mbig, K))
+    W16 = ops.SplitWeight(g(torch.randn(N, K) / math.sqrt(K)), f16=True)
+    b = g(torch.randn(N))
+    A16 = ops.F16Pair.from_tensor(A)
+    gamma = g(torch.randn(Mbig // l, N))
+    x0 = g(torch.randn(Mbig, N))
+    for epi in (ops.EPI_BIAS, ops.EPI_BIAS_GELU, ops.EPI_BIAS_GAMMA_RESID, ops.EPI_BIAS_RESID):
+        outs = []
+        for rows in (Mbig, M):
+            kw = dict(epilogue=epi)
+            out, out16 = x0.clone(), None
+            if epi == ops.EPI_BIAS_GAMMA_RESID:
+                kw.update(gamma=gamma, gamma_row_stride=N, rows_per_sample=l)
+            elif epi == ops.EPI_BIAS_RESID:
+                kw.update(resid=x0)
+                out = torch.empty(Mbig, N, device=DEV)
+            elif epi == ops.EPI_BIAS_GELU:
+                out, out16 = None, ops.F16Pair.empty((Mbig, N), DEV)
+            ops.gemm(None, W16, b, out, rows, N, K, A16=A16, out16=out16, **kw)
+            outs.append((out16.hi[:M].clone(), out16.lo[:M].clone()) if out16 is not None else (out[:M].clone(),))
+        assert all(torch.equal(a, c) for a, c in zip(*outs)), f"epilogue {epi}: narrow tiles differ from the regular kernel"
+    ref = A[:M].double().cpu() @ W16.w.double().cpu().T + b.double().cpu()
+    out = torch.empty(M, N, device=DEV)
+    ops.gemm(None, W16, b, out, M, N, K, A16=A16)
+    assert err(out.cpu(), ref) < 2e-5
+
+
 def test_f16x3_epilogues_and_pair_output(engine4):
     torch.manual_seed(3)
     R, l, C, K = 4, 128, 512, 1024

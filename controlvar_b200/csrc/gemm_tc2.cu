@@ -440,6 +440,7 @@ struct ConvRow {
 
 template <class EP> struct IsDenseRow { static constexpr bool value = false; };
 template <int MODE> struct IsDenseRow<DenseRow<MODE>> { static constexpr bool value = true; };
+template <> struct IsDenseRow<QkvRow> { static constexpr bool value = true; };    // QkvRow works per 16-column chunk on absolute columns: any tile width
 template <class EP> struct IsRowEpilogue { static constexpr bool value = false; };
 template <int MODE> struct IsRowEpilogue<DenseRow<MODE>> { static constexpr bool value = true; };
 template <> struct IsRowEpilogue<QkvRow> { static constexpr bool value = true; };

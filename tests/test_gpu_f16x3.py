@@ -223,6 +223,30 @@ def test_qkv_project_pair_operands(engine4):
     assert (c16.values(l) - c32.values(l)).abs().max().item() / scale < 5e-6
 
 
+@pytest.mark.parametrize("H,l,L_prev", [(12, 8, 10), (24, 18, 0), (30, 32, 28)])
+def test_qkv_project16_narrow_tiles_are_bit_identical(engine4, H, l, L_prev):
+    """cvar_qkv_project16 on few rows (small scales / batches) takes the 256 x 128 pair tiles: q, the appended K and V^T of the
+    first samples must equal, bit for bit, those of a launch with enough samples to take the regular tiles."""
+    torch.manual_seed(H + l)
+    C, T, R_small, R_big = H * 64, 64, 2, 128
+    A = g(torch.randn(R_big * l, C))
+    Wq = ops.SplitWeight(g(torch.randn(3 * C, C) / math.sqrt(C)), f16=True)
+    qb, kb, vb = g(torch.randn(C)), torch.zeros(C, device=DEV), g(torch.randn(C))
+    A16 = ops.F16Pair.from_tensor(A)
+    got = []
+    for R in (R_big, R_small):
+        kv = ops.KVCache16(R, H, T, DEV)
+        for t in (kv.k_hi, kv.k_lo, kv.vt_hi, kv.vt_lo):
+            t.zero_()
+        q16 = ops.F16Pair.empty((R, H, l, 64), DEV)
+        ops.qkv_project16(ops.F16Pair(A16.hi[:R * l], A16.lo[:R * l]), Wq, qb, kb, vb, q16, kv, R, l, L_prev, H, False, None)
+        n = R_small * H
+        got.append([q16.hi[:R_small].clone(), q16.lo[:R_small].clone()] +
+                   [t.view(R * H, -1)[:n].clone() for t in (kv.k_hi, kv.k_lo, kv.vt_hi, kv.vt_lo)])
+    assert all(torch.equal(a, b) for a, b in zip(*got))
+    assert got[1][0].abs().max().item() > 0 and got[1][4].abs().max().item() > 0
+
+
 # ------------------------------------------------------------------------------------------ convolution (decoder)
 def _conv_ref(x_nhwc, w_oihw, bias, resid=None):
     y = F.conv2d(x_nhwc.double().permute(0, 3, 1, 2), w_oihw.double(), bias.double(), padding=w_oihw.shape[-1] // 2)
